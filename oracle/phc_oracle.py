@@ -1,0 +1,276 @@
+"""CPU oracle for the PHC-GNN hot path — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+A functional, eager-PyTorch (CPU, fp32 or fp64) restatement of the reference algorithm for
+the hypercomplex message-passing stack.  Only ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import this module; the
+product package (``phc_gnn_b200``) never does.
+
+Parity pinning: ``oracle/make_golden.py`` imports the UNMODIFIED reference from
+``/root/reference`` (on top of ``oracle/refshim``) in the dev container and stores its
+inputs / weights / outputs / gradients under ``tests/golden/``; ``tests/test_oracle_golden.py``
+checks this restatement against those vectors.  The scatter semantics come from the
+documented behaviour of the pinned third-party versions (torch-scatter 2.0.5,
+torch-geometric 1.6.1 — not vendored in the reference), see SURVEY.md §8c.
+
+Parameters are addressed by the reference's own state-dict keys, e.g.
+``convs.0.transform.transform.linear1.W``; ``params`` is a flat ``dict[str, Tensor]``.
+
+Reference locations restated here (relative to /root/reference):
+  kron_sum / phm_linear      phc/hypercomplex/kronecker.py:35-48, layers.py:198-219
+  phm_norm                   phc/hypercomplex/norm.py:5-39
+  phm_dropout                phc/hypercomplex/layers.py:31-55
+  encoder                    phc/hypercomplex/encoder.py:7-41, phc/quaternion/encoder.py:9-60
+  aggregate / conv           phc/hypercomplex/undirectional/messagepassing.py:19-327
+  pooling                    phc/hypercomplex/pooling.py:10-66
+  downstream                 phc/hypercomplex/downstream.py:90-120
+  model_forward (Add model)  phc/hypercomplex/undirectional/models.py:200-249
+  weight_regularization      phc/hypercomplex/regularization.py:15-23
+  train_step                 benchmarks/train_hiv.py:165-202 (and the zinc/ppa/mnist variants)
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+Params = Dict[str, torch.Tensor]
+
+
+# ----------------------------------------------------------------------------- primitives
+def kron_sum(A: torch.Tensor, W: torch.Tensor) -> torch.Tensor:
+    """H[(a,k),(c,p)] = sum_b A[b,a,c] * W[b,k,p]   (kronecker.py:44-47 then .sum(0))."""
+    n, K, P = W.shape
+    return torch.einsum("bac,bkp->akcp", A, W).reshape(n * K, n * P)
+
+
+def phm_linear(x: torch.Tensor, p: Params, key: str) -> torch.Tensor:
+    y = x @ kron_sum(p[key + ".phm_rule"], p[key + ".W"])
+    b = p.get(key + ".b")
+    return y if b is None else y + b
+
+
+def activation(x: torch.Tensor, name: str) -> torch.Tensor:
+    name = name.lower()
+    if name == "identity":
+        return x
+    if name == "relu":
+        return F.relu(x)
+    if name == "lrelu":
+        return F.leaky_relu(x, 0.01)
+    if name == "elu":
+        return F.elu(x)
+    if name == "selu":
+        return F.selu(x)
+    if name == "swish":
+        return x * torch.sigmoid(x)
+    raise ValueError(name)
+
+
+def phm_norm(x: torch.Tensor, p: Params, key: str, n: int, training: bool,
+             momentum: float = 0.1, eps: float = 1e-5) -> torch.Tensor:
+    """n independent BatchNorm1d's over the n contiguous column blocks (norm.py:30-35).
+    Running statistics in ``p`` are updated in place in training mode."""
+    chunks = x.reshape(x.size(0), n, -1).unbind(1)
+    outs = []
+    for c, xc in enumerate(chunks):
+        k = f"{key}.bn.bn.{c}."
+        outs.append(F.batch_norm(xc, p[k + "running_mean"], p[k + "running_var"], p[k + "weight"],
+                                 p[k + "bias"], training, momentum, eps))
+        if training and (k + "num_batches_tracked") in p:
+            p[k + "num_batches_tracked"] += 1
+    return torch.cat(outs, -1)
+
+
+def phm_dropout(x: torch.Tensor, n: int, prob: float, training: bool, same: bool,
+                generator: Optional[torch.Generator] = None) -> torch.Tensor:
+    if not training or prob <= 0.0:
+        return x
+    if same:
+        keep = torch.bernoulli(torch.full((x.size(0), x.size(1) // n), 1.0 - prob, dtype=x.dtype),
+                               generator=generator)
+        return (x.reshape(x.size(0), n, -1) * keep[:, None, :] / (1.0 - prob)).reshape(x.shape)
+    keep = torch.bernoulli(torch.full_like(x, 1.0 - prob), generator=generator)
+    return x * keep / (1.0 - prob)
+
+
+def encoder(feat: torch.Tensor, p: Params, key: str, n: int, input_dims, dtype) -> torch.Tensor:
+    """PHMEncoder -> [rows, n*out_dim] with component c in column block c."""
+    comps = []
+    for c in range(n):
+        if isinstance(input_dims, (list, tuple)):
+            f = feat.unsqueeze(1) if feat.dim() == 1 else feat
+            acc = 0
+            for col in range(f.size(1)):
+                acc = acc + p[f"{key}.encoders.{c}.embeddings.{col}.weight"][f[:, col]]
+            comps.append(acc)
+        else:
+            comps.append(feat.to(dtype) @ p[f"{key}.encoders.{c}.weight"].t() + p[f"{key}.encoders.{c}.bias"])
+    return torch.cat(comps, -1)
+
+
+# ----------------------------------------------------------------------------- scatter
+def seg_sum(src: torch.Tensor, index: torch.Tensor, size: int) -> torch.Tensor:
+    return src.new_zeros((size,) + tuple(src.shape[1:])).index_add(0, index, src)
+
+
+def seg_ext(src: torch.Tensor, index: torch.Tensor, size: int, mode: str) -> torch.Tensor:
+    idx = index.view(-1, 1).expand_as(src)
+    out = src.new_zeros((size, src.size(1)))
+    return out.scatter_reduce(0, idx, src, mode, include_self=False)   # empty rows stay 0
+
+
+def aggregate(msg: torch.Tensor, index: torch.Tensor, size: int, aggr: str,
+              beta: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """torch_scatter.scatter(reduce=aggr) / scatter_softmax+scatter_sum (messagepassing.py:297-300)."""
+    if aggr in ("add", "sum"):
+        return seg_sum(msg, index, size)
+    if aggr == "mean":
+        cnt = seg_sum(torch.ones(msg.size(0), 1, dtype=msg.dtype), index, size)
+        return seg_sum(msg, index, size) / cnt.clamp(min=1)
+    if aggr == "max":
+        return seg_ext(msg, index, size, "amax")
+    if aggr == "min":
+        return seg_ext(msg, index, size, "amin")
+    if aggr == "softmax":
+        s = msg * beta
+        mx = seg_ext(s.detach(), index, size, "amax")
+        ex = (s - mx[index]).exp()
+        den = seg_sum(ex, index, size) + 1e-12
+        return seg_sum(msg * (ex / den[index]), index, size)
+    raise ValueError(aggr)
+
+
+def propagate(x, edge_index, edge_emb, aggr, msg_encoder, beta=None):
+    msg = activation(x[edge_index[0]] + edge_emb, msg_encoder)
+    return aggregate(msg, edge_index[1], x.size(0), aggr, beta)
+
+
+# ----------------------------------------------------------------------------- layers
+def conv(x, edge_index, edge_emb, p: Params, key: str, cfg: Dict, training: bool) -> torch.Tensor:
+    """PHMMessagePassing dispatch (messagepassing.py:481-507): key is ``convs.{i}``."""
+    n = cfg["phm_dim"]
+    aggr = "add" if cfg["msg_aggr"] == "sum" else cfg["msg_aggr"]
+    beta = p.get(key + ".transform.beta")
+    agg = propagate(x, edge_index, edge_emb, aggr, cfg["msg_encoder"], beta)
+    loops = cfg.get("add_self_loops", True)
+    t = key + ".transform.transform"
+    if cfg["mlp"]:
+        h = agg + x if loops else agg
+        h = phm_linear(h, p, t + ".linear1")
+        if cfg["norm_mp"] not in (None, "None"):
+            h = phm_norm(h, p, t + ".norm", n, training)
+        h = activation(h, cfg["activation"])
+        return phm_linear(h, p, t + ".linear2")
+    if cfg.get("same_dim", True):
+        h = phm_linear(agg, p, t)
+        return h + x if loops else h
+    return phm_linear(agg + x if loops else agg, p, t)
+
+
+def pooling(x, batch, num_graphs, p: Params, cfg: Dict) -> torch.Tensor:
+    n = cfg["phm_dim"]
+    if cfg["pooling"] == "softattention":
+        g = phm_linear(x, p, "pooling.linear")
+        g = torch.sigmoid(g @ p["pooling.real_trafo.affine.weight"].t() + p["pooling.real_trafo.affine.bias"])
+        x = (x.reshape(x.size(0), n, -1) * g[:, None, :]).reshape(x.shape)
+    return seg_sum(x, batch, num_graphs)
+
+
+def downstream(x, p: Params, cfg: Dict, training: bool, generator=None) -> torch.Tensor:
+    n = cfg["phm_dim"]
+    hidden = cfg["downstream_layers"]
+    drops = cfg["dropout_dn"]
+    drops = [drops] * len(hidden) if isinstance(drops, float) else drops
+    for j in range(len(hidden) + 1):
+        x = phm_linear(x, p, f"downstream.affine.{j}")
+        if j < len(hidden):
+            if cfg["norm_dn"] not in (None, "None"):
+                x = phm_norm(x, p, f"downstream.norm.{j}", n, training)
+            x = activation(x, cfg["activation"])
+            x = phm_dropout(x, n, drops[j], training, cfg["same_dropout"], generator)
+    return x @ p["downstream.real_trafo.affine.weight"].t() + p["downstream.real_trafo.affine.bias"]
+
+
+def model_forward(p: Params, cfg: Dict, data, training: bool = True, generator=None) -> torch.Tensor:
+    """PHMSkipConnectAdd.forward (models.py:219-249)."""
+    n = cfg["phm_dim"]
+    dtype = p["downstream.real_trafo.affine.bias"].dtype
+    edge_attr = data.edge_attr
+    h0 = encoder(data.x, p, "atomencoder", n, cfg["atom_input_dims"], dtype)
+    h = h0
+    for i in range(len(cfg["mp_layers"])):
+        if i == 0 or cfg["sc_type"] == "first":
+            skip = h0
+        elif cfg["sc_type"] == "last":
+            skip = h
+        else:
+            raise ValueError(cfg["sc_type"])
+        e = encoder(edge_attr, p, f"bondencoders.{i}", n, cfg["bond_input_dims"], dtype)
+        h = conv(h, data.edge_index, e, p, f"convs.{i}", cfg, training)
+        if cfg["norm_mp"] not in (None, "None"):
+            h = phm_norm(h, p, f"norms.{i}", n, training)
+        h = activation(h, cfg["activation"])
+        h = phm_dropout(h, n, cfg["dropout_mpnn"][i], training, cfg["same_dropout"], generator)
+        h = h + skip
+    out = pooling(h, data.batch, data.num_graphs, p, cfg)
+    return downstream(out, p, cfg, training, generator)
+
+
+def weight_regularization(p: Params, order: int = 2) -> torch.Tensor:
+    """Sum over every PHMLinear weight ``W`` of W.norm(p, dim=0).mean() (regularization.py:15-23)."""
+    reg = 0.0
+    for k, v in p.items():
+        if k.endswith(".W"):
+            reg = reg + v.norm(p=order, dim=0).mean()
+    return reg
+
+
+def task_loss(logits: torch.Tensor, y: torch.Tensor, kind: str) -> torch.Tensor:
+    if kind in ("bce", "bce_masked"):
+        mask = ~torch.isnan(y)
+        return F.binary_cross_entropy_with_logits(logits[mask], y[mask].to(logits.dtype))
+    if kind == "l1":
+        return (logits.squeeze() - y.to(logits.dtype)).abs().mean()
+    if kind == "ce":
+        return F.cross_entropy(logits, y.view(-1))
+    raise ValueError(kind)
+
+
+def trainable(p: Params):
+    return [v for v in p.values() if v.requires_grad]
+
+
+def train_step(p: Params, cfg: Dict, data, loss_kind: str, optimizer, lr: float, weight_decay: float,
+               grad_clip: float = 2.0, generator=None) -> torch.Tensor:
+    """One iteration of the reference's train() body (benchmarks/train_hiv.py:175-202)."""
+    optimizer.zero_grad()
+    logits = model_forward(p, cfg, data, True, generator)
+    loss = task_loss(logits, data.y, loss_kind)
+    if weight_decay > 0.0:
+        loss = loss + lr * weight_decay * weight_regularization(p, 2)
+    loss.backward()
+    if grad_clip > 0.0:
+        torch.nn.utils.clip_grad_norm_(trainable(p), max_norm=grad_clip, norm_type=2)
+    optimizer.step()
+    return loss.detach()
+
+
+# ----------------------------------------------------------------------------- integer structure
+def csr_by_target(edge_index: torch.Tensor, num_nodes: int):
+    """Bit-exact structure oracle: stable sort of edges by target."""
+    perm = torch.sort(edge_index[1], stable=True)[1]
+    col = edge_index[0][perm]
+    rowptr = torch.zeros(num_nodes + 1, dtype=torch.int64)
+    rowptr[1:] = torch.cumsum(torch.bincount(edge_index[1], minlength=num_nodes), 0)
+    return rowptr, col, perm
+
+
+def csr_by_source(edge_index: torch.Tensor, num_nodes: int):
+    return csr_by_target(edge_index.flip(0), num_nodes)
+
+
+def graph_ptr(batch: torch.Tensor, num_graphs: int) -> torch.Tensor:
+    ptr = torch.zeros(num_graphs + 1, dtype=torch.int64)
+    ptr[1:] = torch.cumsum(torch.bincount(batch, minlength=num_graphs), 0)
+    return ptr
