@@ -1,0 +1,132 @@
+/* phc_b200.h — C ABI of libphc_b200.so, the B200 (sm_100a) kernels behind the PHC-GNN
+ * hypercomplex message-passing stack.
+ *
+ * The reference (bayer-science-for-a-better-life/phc-gnn) has NO native layer: its "operator API"
+ * is the torch.nn.Module surface of phc/hypercomplex, and the device work is delegated to ATen,
+ * torch_scatter and torch_geometric.  Each entry point below cites the reference call site whose
+ * device work it replaces.  Conventions:
+ *   - plain C symbols, raw DEVICE pointers + sizes + cudaStream_t; no torch types;
+ *   - the library owns no memory: outputs and workspaces are allocated by the caller, every op with a
+ *     workspace has a *_workspace_bytes() query;
+ *   - returns 0 on success, non-zero on error (1 invalid argument, 2 unsupported, 3 CUDA error);
+ *     phc_last_error() returns the thread-local message.  Never throws, never synchronises, never
+ *     allocates, so every call is CUDA-graph capturable;
+ *   - all feature matrices are fp32 row-major [rows, width]; a hypercomplex row stores its n
+ *     components contiguously: component c occupies columns c*width/n .. (c+1)*width/n-1;
+ *   - indices produced by the library are int32; indices taken from the framework (edge_index,
+ *     batch, integer features) are int64 as PyTorch/PyG hand them over.
+ */
+#ifndef PHC_B200_H
+#define PHC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* phc_stream_t; /* == cudaStream_t */
+
+/* activation ids (reference phc/quaternion/activations.py:134-147 get_module_activation) */
+#define PHC_ACT_IDENTITY 0
+#define PHC_ACT_RELU 1
+#define PHC_ACT_LRELU 2
+#define PHC_ACT_ELU 3
+#define PHC_ACT_SELU 4
+#define PHC_ACT_SWISH 5
+/* neighbour reducers (PyG aggr add/mean/max/min; softmax: messagepassing.py:297-300) */
+#define PHC_RED_SUM 0
+#define PHC_RED_MEAN 1
+#define PHC_RED_MAX 2
+#define PHC_RED_MIN 3
+#define PHC_RED_SOFTMAX 4
+/* PHMLinear arithmetic */
+#define PHC_PREC_FP32 0   /* FFMA, bit-for-bit fp32 products */
+#define PHC_PREC_TF32X3 1 /* tcgen05 kind::tf32, 3-term split: fp32-class accuracy on tensor cores */
+#define PHC_PREC_BF16 2   /* tcgen05 kind::f16 (bf16 operands, fp32 accumulate) */
+
+const char* phc_last_error(void);
+int phc_version(void);
+
+/* ---- graph structure ------------------------------------------------------------------------
+ * Replaces the implicit structure of torch_scatter's atomic scatter used by PyG propagate
+ * (messagepassing.py:136,221,306) and of global_add_pool (pooling.py:18).
+ * edge_index: int64 [2,E] contiguous (row 0 source, row 1 target, any order).
+ * Outputs (int32): rowptr[N+1], col[E] (source of each slot), perm[E] (edge id of each slot) sorted
+ * stably by target; rowptr_t/col_t/perm_t the same keyed by source (col_t = target).  Bit-exact with
+ * a stable argsort.  status: device int, bit0 = index out of range, bit1 = batch not ascending. */
+size_t phc_csr_workspace_bytes(int num_nodes, int num_edges);
+int phc_csr_build(const long long* edge_index, int num_edges, int num_nodes, int* rowptr, int* col, int* perm, int* rowptr_t,
+                  int* col_t, int* perm_t, void* workspace, size_t workspace_bytes, int* status, phc_stream_t stream);
+/* graph_ptr[B+1] from an ascending int64 batch vector (PyG Batch.batch). */
+int phc_segment_ptr_build(const long long* batch, int num_nodes, int num_graphs, int* graph_ptr, int* status, phc_stream_t stream);
+int phc_narrow_int64(const long long* in, int n, int* out, phc_stream_t stream);
+
+/* ---- fused neighbour aggregation (messagepassing.py:72-74,136-138,297-300) -------------------
+ * out[i] = (self_loop ? x[i] : 0) + AGG_{e: dst(e)=i} act(x[src(e)] + ea[e])
+ * aux_f: [2,N,F] (softmax only: log-sum-exp and aggregate), aux_i: [N,F] (max/min only: winning edge id).
+ * beta: device pointer to the softmax inverse temperature (ignored otherwise). */
+int phc_aggregate_fwd(const float* x, const float* ea, const int* rowptr, const int* col, const int* perm, int num_nodes, int width,
+                      int reduce, int msg_act, const float* beta, int self_loop, float* out, float* aux_f, int* aux_i,
+                      phc_stream_t stream);
+size_t phc_aggregate_bwd_workspace_bytes(int num_nodes, int width);
+int phc_aggregate_bwd(const float* gout, const float* x, const float* ea, const float* aux_f, const int* aux_i, const int* rowptr,
+                      const int* col, const int* perm, const int* rowptr_t, const int* col_t, const int* perm_t, int num_nodes,
+                      int width, int reduce, int msg_act, const float* beta, int self_loop, float* dx, float* dea, float* dbeta,
+                      void* workspace, size_t workspace_bytes, phc_stream_t stream);
+
+/* ---- graph pooling (pooling.py:10-25 global_add_pool; :57-66 soft attention) ------------------
+ * gate_logits == NULL: plain sum.  Otherwise out[b,c,f] = sum_i sigmoid(gate_logits[i,f]) x[i,c,f],
+ * gate_logits [N, width/phm_dim]. */
+int phc_segment_pool_fwd(const float* x, const float* gate_logits, const int* graph_ptr, int num_graphs, int width, int phm_dim,
+                         float* out, phc_stream_t stream);
+int phc_segment_pool_bwd(const float* gout, const float* x, const float* gate_logits, const long long* batch, int num_nodes, int width,
+                         int phm_dim, float* dx, float* dgate_logits, phc_stream_t stream);
+
+/* ---- batch-norm + activation + dropout + skip add (norm.py:30-35, layers.py:31-55, models.py:206-215)
+ * y = skip + dropout(act(gamma*(h-mean)*rstd+beta)); gamma/beta/running_* are flat [width] vectors (the
+ * n per-component BatchNorm1d parameter blocks laid out back to back).  use_bn=0 skips the normalisation.
+ * Dropout masks are a pure function of (seed, element index); drop_same=1 shares one mask between the
+ * n components (layers.py:44-52). */
+size_t phc_bn_workspace_bytes(int rows, int width);
+int phc_bn_act_drop_skip_fwd(const float* h, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                             long long* num_batches_tracked, int n_tracked, const float* skip, int rows, int width, int phm_dim,
+                             int use_bn, int training, float momentum, float eps, int act, float drop_p, int drop_same,
+                             unsigned long long seed, float* y, float* save_mean, float* save_rstd, void* workspace,
+                             size_t workspace_bytes, phc_stream_t stream);
+int phc_bn_act_drop_skip_bwd(const float* dy, const float* h, const float* gamma, const float* beta, const float* save_mean,
+                             const float* save_rstd, int rows, int width, int phm_dim, int use_bn, int training, int act, float drop_p,
+                             int drop_same, unsigned long long seed, float* dh, float* dgamma, float* dbeta, void* workspace,
+                             size_t workspace_bytes, phc_stream_t stream);
+
+/* ---- encoders (encoder.py:31-34; quaternion/encoder.py:44-56) ---------------------------------
+ * tables / weights / biases are HOST arrays of device pointers, ordered [component][column]. */
+int phc_embed_sum_fwd(const long long* idx, const float* const* tables, const int* vocab, int rows, int cols, int phm_dim,
+                      int width_per_component, float* out, phc_stream_t stream);
+size_t phc_embed_bwd_workspace_bytes(int rows, int total_vocab, int width);
+int phc_embed_sum_bwd(const float* gout, const long long* idx, float* const* dtables, const int* vocab, int rows, int cols, int phm_dim,
+                      int width_per_component, void* workspace, size_t workspace_bytes, phc_stream_t stream);
+int phc_linear_encoder_fwd(const float* feat, const float* const* weights, const float* const* biases, int rows, int in_dim, int phm_dim,
+                           int width_per_component, float* out, phc_stream_t stream);
+size_t phc_linear_encoder_bwd_workspace_bytes(int rows, int in_dim, int width);
+int phc_linear_encoder_bwd(const float* gout, const float* feat, float* const* dweights, float* const* dbiases, int rows, int in_dim,
+                           int phm_dim, int width_per_component, void* workspace, size_t workspace_bytes, phc_stream_t stream);
+
+/* ---- PHMLinear (layers.py:198-219 matvec_product_new; kronecker.py:35-48) ---------------------
+ * y = act(x * (sum_b A_b (x) W_b) + bias) + residual, without materialising the Kronecker weight.
+ * phm_rule [n,n,n], W [n, in/n, out/n], bias [out] or NULL, residual [rows,out] or NULL.
+ * bwd: dx [rows,in] (NULL to skip), d_rule [n,n,n] (NULL to skip), dW [n,in/n,out/n], dbias (NULL to skip). */
+size_t phc_phm_linear_fwd_workspace_bytes(int rows, int in_features, int out_features, int phm_dim, int precision);
+size_t phc_phm_linear_bwd_workspace_bytes(int rows, int in_features, int out_features, int phm_dim, int precision);
+int phc_phm_linear_fwd(const float* x, const float* phm_rule, const float* W, const float* bias, const float* residual, float* y, int rows,
+                       int in_features, int out_features, int phm_dim, int act, int precision, void* workspace, size_t workspace_bytes,
+                       phc_stream_t stream);
+int phc_phm_linear_bwd(const float* gy, const float* x, const float* phm_rule, const float* W, float* dx, float* d_rule, float* dW,
+                       float* dbias, int rows, int in_features, int out_features, int phm_dim, int precision, void* workspace,
+                       size_t workspace_bytes, phc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHC_B200_H */

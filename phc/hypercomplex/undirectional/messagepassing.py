@@ -1,0 +1,2 @@
+from phc_gnn_b200.nn import (PHMConv, PHMGINEConv, PHMConvSoftmax, PHMGINEConvSoftmax,  # noqa: F401
+                             PHMMessagePassing)

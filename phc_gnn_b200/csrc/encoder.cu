@@ -1,0 +1,246 @@
+// Hypercomplex feature encoders (the step feeding the message-passing path).
+//
+//  * integer encoder: out[r, c*Fc + f] = sum_col table[c][col][ idx[r,col], f ]
+//      reference: PHMEncoder = n x IntegerEncoder, each a sum of per-column nn.Embedding lookups,
+//      stacked on a new component axis (phc/hypercomplex/encoder.py:31-34,
+//      phc/quaternion/encoder.py:44-56): n*#cols embedding launches + adds + stack; backward is
+//      n*#cols embedding_dense_backward launches (15 % of the reference's CPU step).
+//  * linear encoder: out[r, c*Fc + f] = sum_d feat[r,d] * W[c][f,d] + b[c][f]
+//      reference: n x nn.Linear(D -> Fc) + stack (phc/hypercomplex/encoder.py:17-20).
+//
+// The n*#cols parameter tensors stay separate nn.Parameters (state-dict compatibility); the kernels
+// take a small by-value table of device pointers.  Backward is deterministic: row chunks are
+// accumulated in row order by the thread that owns a feature column, chunk partials are summed in
+// chunk order.
+#include "common.cuh"
+
+#define PHC_MAX_TABLES 128
+
+struct PtrTable {
+  const float* p[PHC_MAX_TABLES];
+};
+struct MutPtrTable {
+  float* p[PHC_MAX_TABLES];
+};
+struct IntTable {
+  int v[PHC_MAX_TABLES];
+};
+
+namespace {
+
+template <int VEC>
+__global__ void __launch_bounds__(256) embed_fwd_kernel(const long long* __restrict__ idx, PtrTable tables, IntTable vocab, int R, int C,
+                                                        int n, int Fc, float* __restrict__ out) {
+  const int fcv = Fc / VEC;
+  const int F = n * Fc;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)R * n * fcv) return;
+  const int r = (int)(t / (n * fcv));
+  const int rem = (int)(t % (n * fcv));
+  const int c = rem / fcv, f = (rem % fcv) * VEC;
+  Vec<VEC> acc;
+#pragma unroll
+  for (int q = 0; q < VEC; ++q) acc.v[q] = 0.f;
+  for (int col = 0; col < C; ++col) {
+    long long v = __ldg(idx + (size_t)r * C + col);
+    v = v < 0 ? 0 : (v >= vocab.v[col] ? vocab.v[col] - 1 : v);
+    Vec<VEC> w = Vec<VEC>::load(tables.p[c * C + col] + (size_t)v * Fc + f);
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) acc.v[q] += w.v[q];
+  }
+  acc.store(out + (size_t)r * F + c * Fc + f);
+}
+
+// grid (row chunks, C, feature tiles of blockDim.x flat features). dynamic smem: vocab[col] * blockDim.x floats.
+__global__ void embed_bwd_partial_kernel(const float* __restrict__ g, const long long* __restrict__ idx, IntTable vocab, IntTable voff,
+                                         int R, int C, int F, int rows_per_chunk, int vtot, float* __restrict__ part) {
+  extern __shared__ float acc[];
+  const int col = blockIdx.y;
+  const int V = vocab.v[col];
+  const int ft = blockDim.x;
+  const int f = blockIdx.z * ft + threadIdx.x;
+  const bool active = f < F;
+  for (int v = 0; v < V; ++v) acc[v * ft + threadIdx.x] = 0.f;
+  const int r0 = blockIdx.x * rows_per_chunk, r1 = min(r0 + rows_per_chunk, R);
+  if (active) {
+    for (int r = r0; r < r1; ++r) {
+      long long v = __ldg(idx + (size_t)r * C + col);
+      v = v < 0 ? 0 : (v >= V ? V - 1 : v);
+      acc[(int)v * ft + threadIdx.x] += g[(size_t)r * F + f];
+    }
+    float* dst = part + ((size_t)blockIdx.x * vtot + voff.v[col]) * F + f;
+    for (int v = 0; v < V; ++v) dst[(size_t)v * F] = acc[v * ft + threadIdx.x];
+  }
+}
+
+// dtable[c][col][v, f'] = sum over chunks of part[chunk][voff[col]+v][c*Fc+f']
+__global__ void __launch_bounds__(256) embed_bwd_final_kernel(const float* __restrict__ part, MutPtrTable dtables, IntTable vocab,
+                                                              IntTable voff, int chunks, int C, int n, int Fc, int vtot) {
+  const int F = n * Fc;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)vtot * F) return;
+  const int vr = (int)(t / F), f = (int)(t % F);
+  int col = 0;
+  while (col + 1 < C && voff.v[col + 1] <= vr) ++col;
+  const int v = vr - voff.v[col];
+  float s = 0.f;
+  for (int k = 0; k < chunks; ++k) s += part[((size_t)k * vtot + vr) * F + f];
+  const int c = f / Fc, fp = f % Fc;
+  dtables.p[c * C + col][(size_t)v * Fc + fp] = s;
+}
+
+// ---- linear encoder ------------------------------------------------------------------------
+constexpr int LIN_MAX_D = 16;
+
+template <int VEC>
+__global__ void __launch_bounds__(256) linenc_fwd_kernel(const float* __restrict__ feat, PtrTable weights, PtrTable biases, int R, int D,
+                                                         int n, int Fc, float* __restrict__ out) {
+  const int fcv = Fc / VEC;
+  const int F = n * Fc;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)R * n * fcv) return;
+  const int r = (int)(t / (n * fcv));
+  const int rem = (int)(t % (n * fcv));
+  const int c = rem / fcv, f = (rem % fcv) * VEC;
+  const float* w = weights.p[c];
+  Vec<VEC> acc;
+#pragma unroll
+  for (int q = 0; q < VEC; ++q) acc.v[q] = biases.p[c] ? __ldg(biases.p[c] + f + q) : 0.f;
+  for (int d = 0; d < D; ++d) {
+    const float a = __ldg(feat + (size_t)r * D + d);
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) acc.v[q] += a * __ldg(w + (size_t)(f + q) * D + d);
+  }
+  acc.store_stream(out + (size_t)r * F + c * Fc + f);
+}
+
+// part[chunk][f][0..D] : d = 0..D-1 weight grads, d = D bias grad. grid (feature tiles, row chunks)
+__global__ void __launch_bounds__(128) linenc_bwd_partial_kernel(const float* __restrict__ g, const float* __restrict__ feat, int R, int D,
+                                                                 int F, int rows_per_chunk, float* __restrict__ part) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  const int r0 = blockIdx.y * rows_per_chunk, r1 = min(r0 + rows_per_chunk, R);
+  float acc[LIN_MAX_D + 1];
+#pragma unroll
+  for (int d = 0; d <= LIN_MAX_D; ++d) acc[d] = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    const float gv = g[(size_t)r * F + f];
+#pragma unroll
+    for (int d = 0; d < LIN_MAX_D; ++d)
+      if (d < D) acc[d] += gv * __ldg(feat + (size_t)r * D + d);
+    acc[LIN_MAX_D] += gv;
+  }
+  float* dst = part + ((size_t)blockIdx.y * F + f) * (D + 1);
+#pragma unroll
+  for (int d = 0; d < LIN_MAX_D; ++d)
+    if (d < D) dst[d] = acc[d];
+  dst[D] = acc[LIN_MAX_D];
+}
+
+__global__ void __launch_bounds__(256) linenc_bwd_final_kernel(const float* __restrict__ part, MutPtrTable dweights, MutPtrTable dbiases,
+                                                               int chunks, int D, int n, int Fc) {
+  const int F = n * Fc;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)F * (D + 1)) return;
+  const int f = (int)(t / (D + 1)), d = (int)(t % (D + 1));
+  float s = 0.f;
+  for (int k = 0; k < chunks; ++k) s += part[((size_t)k * F + f) * (D + 1) + d];
+  const int c = f / Fc, fp = f % Fc;
+  if (d < D) dweights.p[c][(size_t)fp * D + d] = s;
+  else if (dbiases.p[c]) dbiases.p[c][fp] = s;
+}
+
+int embed_chunks(int R) {
+  int chunks = phc_div_up(R, 512);
+  return chunks < 1 ? 1 : (chunks > 64 ? 64 : chunks);
+}
+int linenc_chunks(int R) {
+  int chunks = phc_div_up(R, 256);
+  return chunks < 1 ? 1 : (chunks > 296 ? 296 : chunks);
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t phc_embed_bwd_workspace_bytes(int rows, int total_vocab, int width) {
+  return sizeof(float) * (size_t)embed_chunks(rows) * total_vocab * width;
+}
+
+int phc_embed_sum_fwd(const long long* idx, const float* const* tables, const int* vocab, int rows, int cols, int phm_dim,
+                      int width_per_component, float* out, cudaStream_t stream) {
+  PHC_REQUIRE(cols > 0 && phm_dim > 0 && phm_dim * cols <= PHC_MAX_TABLES, "phc_embed_sum_fwd: phm_dim*cols=%d exceeds %d tables",
+              phm_dim * cols, PHC_MAX_TABLES);
+  if (rows == 0) return PHC_OK;
+  PtrTable tb; IntTable vc;
+  bool v4 = width_per_component % 4 == 0 && phc_aligned16(out);
+  for (int i = 0; i < phm_dim * cols; ++i) { tb.p[i] = tables[i]; v4 = v4 && phc_aligned16(tables[i]); }
+  for (int i = 0; i < cols; ++i) vc.v[i] = vocab[i];
+  const int n = phm_dim, Fc = width_per_component;
+  if (v4) embed_fwd_kernel<4><<<phc_div_up((long long)rows * n * (Fc / 4), 256), 256, 0, stream>>>(idx, tb, vc, rows, cols, n, Fc, out);
+  else embed_fwd_kernel<1><<<phc_div_up((long long)rows * n * Fc, 256), 256, 0, stream>>>(idx, tb, vc, rows, cols, n, Fc, out);
+  return phc_check_launch("phc_embed_sum_fwd");
+}
+
+int phc_embed_sum_bwd(const float* gout, const long long* idx, float* const* dtables, const int* vocab, int rows, int cols, int phm_dim,
+                      int width_per_component, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  PHC_REQUIRE(cols > 0 && phm_dim > 0 && phm_dim * cols <= PHC_MAX_TABLES, "phc_embed_sum_bwd: too many tables");
+  const int n = phm_dim, Fc = width_per_component, F = n * Fc;
+  MutPtrTable dt; IntTable vc, vo;
+  int vtot = 0, vmax = 0;
+  for (int i = 0; i < cols; ++i) { vc.v[i] = vocab[i]; vo.v[i] = vtot; vtot += vocab[i]; vmax = vocab[i] > vmax ? vocab[i] : vmax; }
+  for (int i = 0; i < n * cols; ++i) dt.p[i] = dtables[i];
+  PHC_REQUIRE(workspace_bytes >= phc_embed_bwd_workspace_bytes(rows, vtot, F), "phc_embed_sum_bwd: workspace too small");
+  const int ft = 128;
+  const size_t smem = sizeof(float) * (size_t)vmax * ft;
+  PHC_REQUIRE(smem <= 200 * 1024, "phc_embed_sum_bwd: vocabulary %d too large for the shared-memory accumulator", vmax);
+  const int chunks = embed_chunks(rows);
+  const int rpc = phc_div_up(rows > 0 ? rows : 1, chunks);
+  float* part = reinterpret_cast<float*>(workspace);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(embed_bwd_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  dim3 grid(chunks, cols, phc_div_up(F, ft));
+  embed_bwd_partial_kernel<<<grid, ft, smem, stream>>>(gout, idx, vc, vo, rows, cols, F, rpc, vtot, part);
+  embed_bwd_final_kernel<<<phc_div_up((long long)vtot * F, 256), 256, 0, stream>>>(part, dt, vc, vo, chunks, cols, n, Fc, vtot);
+  return phc_check_launch("phc_embed_sum_bwd");
+}
+
+size_t phc_linear_encoder_bwd_workspace_bytes(int rows, int in_dim, int width) {
+  return sizeof(float) * (size_t)linenc_chunks(rows) * width * (in_dim + 1);
+}
+
+int phc_linear_encoder_fwd(const float* feat, const float* const* weights, const float* const* biases, int rows, int in_dim, int phm_dim,
+                           int width_per_component, float* out, cudaStream_t stream) {
+  PHC_REQUIRE(phm_dim > 0 && phm_dim <= PHC_MAX_TABLES, "phc_linear_encoder_fwd: bad phm_dim");
+  PHC_REQUIRE(in_dim > 0 && in_dim <= LIN_MAX_D, "phc_linear_encoder_fwd: in_dim %d not in 1..%d", in_dim, LIN_MAX_D);
+  if (rows == 0) return PHC_OK;
+  PtrTable w, b;
+  for (int c = 0; c < phm_dim; ++c) { w.p[c] = weights[c]; b.p[c] = biases ? biases[c] : nullptr; }
+  const int n = phm_dim, Fc = width_per_component;
+  const bool v4 = Fc % 4 == 0 && phc_aligned16(out);
+  if (v4) linenc_fwd_kernel<4><<<phc_div_up((long long)rows * n * (Fc / 4), 256), 256, 0, stream>>>(feat, w, b, rows, in_dim, n, Fc, out);
+  else linenc_fwd_kernel<1><<<phc_div_up((long long)rows * n * Fc, 256), 256, 0, stream>>>(feat, w, b, rows, in_dim, n, Fc, out);
+  return phc_check_launch("phc_linear_encoder_fwd");
+}
+
+int phc_linear_encoder_bwd(const float* gout, const float* feat, float* const* dweights, float* const* dbiases, int rows, int in_dim,
+                           int phm_dim, int width_per_component, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  PHC_REQUIRE(phm_dim > 0 && phm_dim <= PHC_MAX_TABLES, "phc_linear_encoder_bwd: bad phm_dim");
+  PHC_REQUIRE(in_dim > 0 && in_dim <= LIN_MAX_D, "phc_linear_encoder_bwd: in_dim %d not in 1..%d", in_dim, LIN_MAX_D);
+  const int n = phm_dim, Fc = width_per_component, F = n * Fc;
+  PHC_REQUIRE(workspace_bytes >= phc_linear_encoder_bwd_workspace_bytes(rows, in_dim, F), "phc_linear_encoder_bwd: workspace too small");
+  MutPtrTable dw, db;
+  for (int c = 0; c < n; ++c) { dw.p[c] = dweights[c]; db.p[c] = dbiases ? dbiases[c] : nullptr; }
+  const int chunks = linenc_chunks(rows);
+  const int rpc = phc_div_up(rows > 0 ? rows : 1, chunks);
+  float* part = reinterpret_cast<float*>(workspace);
+  dim3 grid(phc_div_up(F, 128), chunks);
+  linenc_bwd_partial_kernel<<<grid, 128, 0, stream>>>(gout, feat, rows, in_dim, F, rpc, part);
+  linenc_bwd_final_kernel<<<phc_div_up((long long)F * (in_dim + 1), 256), 256, 0, stream>>>(part, dw, db, chunks, in_dim, n, Fc);
+  return phc_check_launch("phc_linear_encoder_bwd");
+}
+
+}  // extern "C"

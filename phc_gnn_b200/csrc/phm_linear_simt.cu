@@ -1,0 +1,290 @@
+// PHMLinear, exact-fp32 path on the FFMA pipe ("fp32" precision mode).
+//
+//   y[m, c*P+p] = sum_{a,k} x[m, a*K+k] * H[(a,k),(c,p)] + b[c*P+p],   H[(a,k),(c,p)] = sum_b A[b,a,c] W[b,k,p]
+//
+// Replaces reference phc/hypercomplex/layers.py:198-219 (matvec_product_new): an einsum that
+// materialises the [n,in,out] Kronecker stack, a sum over it, a cuBLAS SGEMM and a bias kernel —
+// again in backward.  Here H never exists in memory: every CTA builds the [BK,BN] tile of H it
+// needs in shared memory from the n^3 rule scalars and the n small W blocks (n FMAs per element).
+//
+// This file is the strict-fp32 mode used for rtol-1e-4 parity checks of everything else; the
+// tensor-core path (tcgen05, phm_linear_tc.cu) is the production mode.
+//
+// Backward:  dX = dY * H^T (same kernel, transposed tile builder),  dH = X^T dY via split-M partial
+// tiles reduced in a fixed order (no atomics), then  dW[b,k,p] = sum_{a,c} A[b,a,c] dH[(a,k),(c,p)],
+// dA[b,a,c] = sum_{k,p} W[b,k,p] dH[(a,k),(c,p)],  db = column sums of dY.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TM = 128, TN = 64, TK = 16;   // forward / dX tile
+constexpr int MAXN = 16;                    // largest supported phm_dim
+
+// Build element (r,q) of H (TRANS=false: r indexes `in`, q indexes `out`) or of H^T (TRANS=true:
+// r indexes `out`, q indexes `in`).
+template <bool TRANS>
+__device__ __forceinline__ float h_element(const float* __restrict__ As, const float* __restrict__ W, int n, int K, int P, int r, int q) {
+  int a, k, c, p;
+  if (!TRANS) { a = r / K; k = r % K; c = q / P; p = q % P; }
+  else { c = r / P; p = r % P; a = q / K; k = q % K; }
+  float h = 0.f;
+  for (int b = 0; b < n; ++b) h += As[(b * n + a) * n + c] * __ldg(W + ((size_t)b * K + k) * P + p);
+  return h;
+}
+
+// C[M, Nout] = act(X[M, Kred] * B[Kred, Nout] + bias) + residual, with B built on the fly.
+template <bool TRANS>
+__global__ void __launch_bounds__(256) phm_gemm_kernel(const float* __restrict__ X, const float* __restrict__ A, const float* __restrict__ W,
+                                                       const float* __restrict__ bias, const float* __restrict__ residual,
+                                                       float* __restrict__ Y, int M, int Kred, int Nout, int n, int K, int P, int act) {
+  __shared__ float Xs[TK][TM + 4];
+  __shared__ float Hs[TK][TN + 4];
+  extern __shared__ float As[];  // n^3 rule scalars
+  const int tid = threadIdx.x;
+  for (int i = tid; i < n * n * n; i += 256) As[i] = A[i];
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  const int ty = tid / 16, tx = tid % 16;  // 16x16 threads, each 8 rows x 4 cols
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  __syncthreads();
+
+  for (int k0 = 0; k0 < Kred; k0 += TK) {
+    // X tile: 128 rows x 16 k  -> 2048 elements, 8 per thread (coalesced along k)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int lin = tid + i * 256;
+      int mm = lin / TK, kk = lin % TK;
+      int gm = m0 + mm, gk = k0 + kk;
+      Xs[kk][mm] = (gm < M && gk < Kred) ? X[(size_t)gm * Kred + gk] : 0.f;
+    }
+    // H tile: 16 x 64 -> 1024 elements, 4 per thread
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int lin = tid + i * 256;
+      int kk = lin / TN, nn = lin % TN;
+      int gr = k0 + kk, gq = n0 + nn;
+      Hs[kk][nn] = (gr < Kred && gq < Nout) ? h_element<TRANS>(As, W, n, K, P, gr, gq) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < TK; ++kk) {
+      float xa[8], hb[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) xa[i] = Xs[kk][ty * 8 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) hb[j] = Hs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += xa[i] * hb[j];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int gm = m0 + ty * 8 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int gq = n0 + tx * 4 + j;
+      if (gq >= Nout) continue;
+      float v = acc[i][j];
+      if (bias) v += __ldg(bias + gq);
+      v = act_fwd_rt(act, v);
+      if (residual) v += residual[(size_t)gm * Nout + gq];
+      Y[(size_t)gm * Nout + gq] = v;
+    }
+  }
+}
+
+// dH partials: part[z][i][o] = sum_{m in split z} x[m,i] * dy[m,o].  64x64 tile, 256 threads x (4x4).
+__global__ void __launch_bounds__(256) phm_dh_kernel(const float* __restrict__ X, const float* __restrict__ G, int M, int In, int Out,
+                                                     int rows_per_split, float* __restrict__ part) {
+  __shared__ float Xs[16][64 + 4];
+  __shared__ float Gs[16][64 + 4];
+  const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16;
+  const int i0 = blockIdx.y * 64, o0 = blockIdx.x * 64;
+  const int mbeg = blockIdx.z * rows_per_split, mend = min(mbeg + rows_per_split, M);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int m0 = mbeg; m0 < mend; m0 += 16) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int lin = tid + i * 256;
+      int mm = lin / 64, cc = lin % 64;
+      int gm = m0 + mm;
+      Xs[mm][cc] = (gm < mend && i0 + cc < In) ? X[(size_t)gm * In + i0 + cc] : 0.f;
+      Gs[mm][cc] = (gm < mend && o0 + cc < Out) ? G[(size_t)gm * Out + o0 + cc] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int mm = 0; mm < 16; ++mm) {
+      float xa[4], gb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xa[i] = Xs[mm][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) gb[j] = Gs[mm][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += xa[i] * gb[j];
+    }
+    __syncthreads();
+  }
+  float* dst = part + (size_t)blockIdx.z * In * Out;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int gi = i0 + ty * 4 + i;
+    if (gi >= In) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int go = o0 + tx * 4 + j;
+      if (go < Out) dst[(size_t)gi * Out + go] = acc[i][j];
+    }
+  }
+}
+
+// One thread per (k,p): folds the split partials, contracts with A for dW and produces block
+// partials of dA[b,a,c] (reduced in fixed order: warp shuffle tree, then warps in order).
+__global__ void __launch_bounds__(256) phm_contract_kernel(const float* __restrict__ part, int splits, const float* __restrict__ A,
+                                                           const float* __restrict__ W, int n, int K, int P, float* __restrict__ dW,
+                                                           float* __restrict__ dA_part) {
+  extern __shared__ float sm[];
+  float* As = sm;                 // n^3
+  float* wred = sm + n * n * n;   // 8 warps
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < n * n * n; i += 256) As[i] = A[i];
+  __syncthreads();
+  const int In = n * K, Out = n * P;
+  const long long t = (long long)blockIdx.x * 256 + tid;
+  const bool active = t < (long long)K * P;
+  const int k = active ? (int)(t / P) : 0, p = active ? (int)(t % P) : 0;
+  float dw[MAXN];
+#pragma unroll
+  for (int b = 0; b < MAXN; ++b) dw[b] = 0.f;
+  for (int a = 0; a < n; ++a) {
+    for (int c = 0; c < n; ++c) {
+      float dh = 0.f;
+      if (active) {
+        const size_t off = (size_t)(a * K + k) * Out + (c * P + p);
+        for (int s = 0; s < splits; ++s) dh += part[(size_t)s * In * Out + off];
+      }
+#pragma unroll
+      for (int b = 0; b < MAXN; ++b) {
+        if (b < n) {
+          dw[b] += As[(b * n + a) * n + c] * dh;
+          float v = active ? __ldg(W + ((size_t)b * K + k) * P + p) * dh : 0.f;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (lane == 0) wred[warp] = v;
+          __syncthreads();
+          if (tid == 0) {
+            float s = 0.f;
+            for (int w = 0; w < 8; ++w) s += wred[w];
+            dA_part[(size_t)blockIdx.x * n * n * n + (b * n + a) * n + c] = s;
+          }
+          __syncthreads();
+        }
+      }
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int b = 0; b < MAXN; ++b)
+      if (b < n) dW[((size_t)b * K + k) * P + p] = dw[b];
+  }
+}
+
+__global__ void __launch_bounds__(256) phm_dA_final_kernel(const float* __restrict__ dA_part, int blocks, int n3, float* __restrict__ dA) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n3) return;
+  float s = 0.f;
+  for (int b = 0; b < blocks; ++b) s += dA_part[(size_t)b * n3 + i];
+  dA[i] = s;
+}
+
+// column sums of G (bias gradient): chunk partials then ordered final sum
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ G, int M, int F, int rows_per_chunk,
+                                                             float* __restrict__ part) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  const int r0 = blockIdx.y * rows_per_chunk, r1 = min(r0 + rows_per_chunk, M);
+  float s = 0.f;
+  for (int r = r0; r < r1; ++r) s += G[(size_t)r * F + f];
+  part[(size_t)blockIdx.y * F + f] = s;
+}
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ part, int chunks, int F, float* __restrict__ out) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  float s = 0.f;
+  for (int c = 0; c < chunks; ++c) s += part[(size_t)c * F + f];
+  out[f] = s;
+}
+
+int dh_splits(int M, int In, int Out) {
+  long long tiles = (long long)phc_div_up(In, 64) * phc_div_up(Out, 64);
+  int s = (int)((2 * 148 + tiles - 1) / tiles);
+  int maxs = phc_div_up(M, 64);
+  s = s < 1 ? 1 : s;
+  s = s > maxs ? maxs : s;
+  return s < 1 ? 1 : (s > 64 ? 64 : s);
+}
+int colsum_chunks(int M) {
+  int c = phc_div_up(M, 128);
+  return c < 1 ? 1 : (c > 128 ? 128 : c);
+}
+
+}  // namespace
+
+// shared with phm_linear_tc.cu
+size_t phm_simt_bwd_workspace_bytes(int rows, int in_features, int out_features, int phm_dim) {
+  const int n = phm_dim, K = in_features / n, P = out_features / n;
+  size_t dh = (size_t)dh_splits(rows, in_features, out_features) * in_features * out_features;
+  size_t da = (size_t)phc_div_up((long long)K * P, 256) * n * n * n;
+  size_t cs = (size_t)colsum_chunks(rows) * out_features;
+  return sizeof(float) * (dh + da + cs) + 64;
+}
+
+int phm_simt_fwd(const float* x, const float* A, const float* W, const float* bias, const float* residual, float* y, int rows,
+                 int in_features, int out_features, int phm_dim, int act, cudaStream_t stream) {
+  const int n = phm_dim, K = in_features / n, P = out_features / n;
+  dim3 grid(phc_div_up(out_features, TN), phc_div_up(rows, TM));
+  phm_gemm_kernel<false><<<grid, 256, sizeof(float) * n * n * n, stream>>>(x, A, W, bias, residual, y, rows, in_features, out_features, n, K,
+                                                                           P, act);
+  return phc_check_launch("phc_phm_linear_fwd(simt)");
+}
+
+int phm_simt_bwd(const float* gy, const float* x, const float* A, const float* W, float* dx, float* dA, float* dW, float* db, int rows,
+                 int in_features, int out_features, int phm_dim, void* workspace, cudaStream_t stream) {
+  const int n = phm_dim, K = in_features / n, P = out_features / n, M = rows;
+  const int n3 = n * n * n;
+  if (dx) {
+    dim3 grid(phc_div_up(in_features, TN), phc_div_up(M, TM));
+    phm_gemm_kernel<true><<<grid, 256, sizeof(float) * n3, stream>>>(gy, A, W, nullptr, nullptr, dx, M, out_features, in_features, n, K, P,
+                                                                      PHC_ACT_IDENTITY);
+  }
+  const int splits = dh_splits(M, in_features, out_features);
+  const int rps = phc_div_up(phc_div_up(M > 0 ? M : 1, splits), 16) * 16;
+  float* part = reinterpret_cast<float*>(workspace);
+  float* da_part = part + (size_t)splits * in_features * out_features;
+  const int cblocks = phc_div_up((long long)K * P, 256);
+  float* cs_part = da_part + (size_t)cblocks * n3;
+  dim3 g2(phc_div_up(out_features, 64), phc_div_up(in_features, 64), splits);
+  phm_dh_kernel<<<g2, 256, 0, stream>>>(x, gy, M, in_features, out_features, rps, part);
+  phm_contract_kernel<<<cblocks, 256, sizeof(float) * (n3 + 8), stream>>>(part, splits, A, W, n, K, P, dW, da_part);
+  if (dA) phm_dA_final_kernel<<<phc_div_up(n3, 256), 256, 0, stream>>>(da_part, cblocks, n3, dA);
+  if (db) {
+    const int chunks = colsum_chunks(M);
+    const int rpc = phc_div_up(M > 0 ? M : 1, chunks);
+    dim3 g3(phc_div_up(out_features, 256), chunks);
+    colsum_partial_kernel<<<g3, 256, 0, stream>>>(gy, M, out_features, rpc, cs_part);
+    colsum_final_kernel<<<phc_div_up(out_features, 256), 256, 0, stream>>>(cs_part, chunks, out_features, db);
+  }
+  return phc_check_launch("phc_phm_linear_bwd(simt)");
+}

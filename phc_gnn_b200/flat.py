@@ -1,0 +1,51 @@
+"""Flat aliasing of many small parameter tensors.
+
+The reference keeps per-component parameters as separate tensors (n BatchNorm1d modules per norm,
+n x #cols embedding tables per encoder; state-dict keys SURVEY.md §8b).  The kernels want one
+contiguous vector per role.  ``alias_flat`` lays a list of tensors back to back in one buffer and
+re-points each tensor's ``.data`` at its slice, so both views of the memory stay valid: the
+state-dict / optimizer see the individual tensors, the kernels see the flat vector.  The layout
+is re-established lazily whenever something (``module.to()``, ``param.data = ...`` as the
+reference's reset_parameters does, unpickling) broke the aliasing.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+
+def is_packed(flat: Optional[torch.Tensor], tensors: Sequence[torch.Tensor]) -> bool:
+    if flat is None or len(tensors) == 0:
+        return False
+    t0 = tensors[0]
+    if flat.device != t0.device or flat.dtype != t0.dtype:
+        return False
+    base = flat.data_ptr()
+    esz = flat.element_size()
+    off = 0
+    for t in tensors:
+        if t.device != flat.device or t.dtype != flat.dtype or not t.is_contiguous():
+            return False
+        if t.data_ptr() != base + off * esz:
+            return False
+        off += t.numel()
+    return off == flat.numel()
+
+
+def alias_flat(flat: Optional[torch.Tensor], tensors: Sequence[torch.Tensor]) -> torch.Tensor:
+    """Return a 1-D tensor whose storage IS the concatenation of ``tensors`` (re-packing if needed)."""
+    if is_packed(flat, tensors):
+        return flat
+    with torch.no_grad():
+        t0 = tensors[0]
+        total = sum(t.numel() for t in tensors)
+        new = torch.empty(total, dtype=t0.dtype, device=t0.device)
+        off = 0
+        for t in tensors:
+            k = t.numel()
+            view = new[off:off + k].view(t.shape)
+            view.copy_(t.detach().to(device=t0.device, dtype=t0.dtype))
+            t.data = view
+            off += k
+    return new

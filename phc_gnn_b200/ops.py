@@ -1,0 +1,362 @@
+"""torch.autograd bindings of the C ABI (include/phc_b200.h).
+
+Every function takes CUDA fp32 tensors, allocates outputs / workspaces with torch, and launches the
+hand-written kernels on torch's current stream through ctypes.  No CPU fallback: a non-CUDA tensor
+raises (see graph.require_cuda).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from .graph import EdgeStructure, SegmentStructure, require_cuda, _stream
+
+ACT_IDS = {"identity": 0, "relu": 1, "lrelu": 2, "elu": 3, "selu": 4, "swish": 5}
+REDUCE_IDS = {"add": 0, "sum": 0, "mean": 1, "max": 2, "min": 3, "softmax": 4}
+PRECISION_IDS = {"fp32": 0, "tf32x3": 1, "bf16": 2}
+
+
+def default_precision() -> int:
+    """PHMLinear arithmetic: env PHC_PRECISION in {fp32, tf32x3, bf16}; default tf32x3 (fp32-class
+    accuracy on the tensor cores).  Falls back to the FFMA path inside the library only for shapes
+    the tensor-core kernel does not cover (reported by phc_phm_linear_*_workspace_bytes)."""
+    return PRECISION_IDS[os.environ.get("PHC_PRECISION", "tf32x3").lower()]
+
+
+def act_id(name: Optional[str]) -> int:
+    return ACT_IDS[(name or "identity").lower()]
+
+
+def _f32c(t: torch.Tensor, what: str) -> torch.Tensor:
+    require_cuda(t, what)
+    if t.dtype != torch.float32:
+        raise TypeError(f"{what} must be float32 (got {t.dtype})")
+    return t.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def _ptr_array(tensors: Sequence[Optional[torch.Tensor]]):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr
+
+
+# --------------------------------------------------------------------------------- PHMLinear
+class _PHMLinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, rule, W, bias, residual, precision):
+        lib = _lib.load()
+        x = _f32c(x, "x"); rule = _f32c(rule, "phm_rule"); W = _f32c(W, "W")
+        n, K, P = W.shape
+        M, fin, fout = x.size(0), n * K, n * P
+        assert x.dim() == 2 and x.size(1) == fin, f"x has size(1): {x.size(-1)}. Should have {fin}"
+        if bias is not None:
+            bias = _f32c(bias, "b")
+        if residual is not None:
+            residual = _f32c(residual, "residual")
+            assert residual.shape == (M, fout)
+        y = torch.empty((M, fout), dtype=torch.float32, device=x.device)
+        nb = lib.phc_phm_linear_fwd_workspace_bytes(M, fin, fout, n, precision)
+        ws = _ws(nb, x.device)
+        _lib.check(lib.phc_phm_linear_fwd(x.data_ptr(), rule.data_ptr(), W.data_ptr(), _ptr(bias), _ptr(residual), y.data_ptr(), M,
+                                          fin, fout, n, 0, precision, ws.data_ptr(), ws.numel(), _stream(x.device)),
+                   "phc_phm_linear_fwd")
+        ctx.save_for_backward(x, rule, W)
+        ctx.meta = (bias is not None, residual is not None, precision)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib.load()
+        x, rule, W = ctx.saved_tensors
+        has_bias, has_res, precision = ctx.meta
+        gy = _f32c(gy, "grad_output")
+        n, K, P = W.shape
+        M, fin, fout = x.size(0), n * K, n * P
+        need = ctx.needs_input_grad
+        dx = torch.empty_like(x) if need[0] else None
+        d_rule = torch.empty_like(rule) if need[1] else None
+        dW = torch.empty_like(W)
+        db = torch.empty(fout, dtype=torch.float32, device=x.device) if (has_bias and need[3]) else None
+        nb = lib.phc_phm_linear_bwd_workspace_bytes(M, fin, fout, n, precision)
+        ws = _ws(nb, x.device)
+        _lib.check(lib.phc_phm_linear_bwd(gy.data_ptr(), x.data_ptr(), rule.data_ptr(), W.data_ptr(), _ptr(dx), _ptr(d_rule),
+                                          dW.data_ptr(), _ptr(db), M, fin, fout, n, precision, ws.data_ptr(), ws.numel(),
+                                          _stream(x.device)), "phc_phm_linear_bwd")
+        return dx, d_rule, (dW if need[2] else None), db, (gy if (has_res and need[4]) else None), None
+
+
+def phm_linear(x, rule, W, bias=None, residual=None, precision: Optional[int] = None) -> torch.Tensor:
+    """y = x @ (sum_b rule[b] (x) W[b]) + bias (+ residual)   — reference layers.py:198-219."""
+    return _PHMLinear.apply(x, rule, W, bias, residual, default_precision() if precision is None else precision)
+
+
+# --------------------------------------------------------------------------------- aggregation
+class _Aggregate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, ea, beta, struct: EdgeStructure, reduce: int, msg_act: int, self_loop: bool):
+        lib = _lib.load()
+        x = _f32c(x, "x"); ea = _f32c(ea, "edge_attr")
+        N, F = x.shape
+        assert N == struct.num_nodes, "x rows do not match the graph structure"
+        assert ea.size(0) == struct.num_edges and ea.size(-1) == F, \
+            f"edge_attr must be [E={struct.num_edges}, F={F}] (got {tuple(ea.shape)})"
+        out = torch.empty_like(x)
+        aux_f = torch.empty((2, N, F), dtype=torch.float32, device=x.device) if reduce == 4 else None
+        aux_i = torch.empty((N, F), dtype=torch.int32, device=x.device) if reduce in (2, 3) else None
+        if reduce == 4:
+            beta = _f32c(beta, "beta")
+        _lib.check(lib.phc_aggregate_fwd(x.data_ptr(), ea.data_ptr(), struct.rowptr.data_ptr(), struct.col.data_ptr(),
+                                         struct.perm.data_ptr(), N, F, reduce, msg_act, _ptr(beta if reduce == 4 else None),
+                                         int(self_loop), out.data_ptr(), _ptr(aux_f), _ptr(aux_i), _stream(x.device)),
+                   "phc_aggregate_fwd")
+        ctx.save_for_backward(x, ea, beta if reduce == 4 else None, aux_f, aux_i)
+        ctx.struct = struct
+        ctx.meta = (reduce, msg_act, bool(self_loop))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        x, ea, beta, aux_f, aux_i = ctx.saved_tensors
+        s = ctx.struct
+        reduce, msg_act, self_loop = ctx.meta
+        g = _f32c(g, "grad_output")
+        N, F = x.shape
+        dx = torch.empty_like(x)
+        dea = torch.empty_like(ea)
+        dbeta = torch.zeros((), dtype=torch.float32, device=x.device) if reduce == 4 else None
+        nb = lib.phc_aggregate_bwd_workspace_bytes(N, F)
+        ws = _ws(nb, x.device)
+        _lib.check(lib.phc_aggregate_bwd(g.data_ptr(), x.data_ptr(), ea.data_ptr(), _ptr(aux_f), _ptr(aux_i), s.rowptr.data_ptr(),
+                                         s.col.data_ptr(), s.perm.data_ptr(), s.rowptr_t.data_ptr(), s.col_t.data_ptr(),
+                                         s.perm_t.data_ptr(), N, F, reduce, msg_act, _ptr(beta), int(self_loop), dx.data_ptr(),
+                                         dea.data_ptr(), _ptr(dbeta), ws.data_ptr(), ws.numel(), _stream(x.device)),
+                   "phc_aggregate_bwd")
+        return dx, dea, dbeta, None, None, None, None
+
+
+def aggregate(x, edge_emb, struct: EdgeStructure, reduce: str = "add", msg_act: str = "identity",
+              beta: Optional[torch.Tensor] = None, self_loop: bool = False) -> torch.Tensor:
+    """out[i] = (x[i] if self_loop) + AGG_{e: dst(e)=i} act(x[src(e)] + edge_emb[e])."""
+    r = REDUCE_IDS[reduce]
+    if r == 4 and beta is None:
+        raise ValueError("softmax aggregation needs beta")
+    return _Aggregate.apply(x, edge_emb, beta if r == 4 else None, struct, r, act_id(msg_act), self_loop)
+
+
+# --------------------------------------------------------------------------------- pooling
+class _Pool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gate_logits, batch, seg: SegmentStructure, n: int):
+        lib = _lib.load()
+        x = _f32c(x, "x")
+        N, F = x.shape
+        assert N == seg.num_nodes
+        if gate_logits is not None:
+            gate_logits = _f32c(gate_logits, "gate_logits")
+            assert gate_logits.shape == (N, F // n)
+        out = torch.empty((seg.num_graphs, F), dtype=torch.float32, device=x.device)
+        _lib.check(lib.phc_segment_pool_fwd(x.data_ptr(), _ptr(gate_logits), seg.graph_ptr.data_ptr(), seg.num_graphs, F, n,
+                                            out.data_ptr(), _stream(x.device)), "phc_segment_pool_fwd")
+        ctx.save_for_backward(x, gate_logits, batch)
+        ctx.n = n
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        x, z, batch = ctx.saved_tensors
+        g = _f32c(g, "grad_output")
+        N, F = x.shape
+        dx = torch.empty_like(x)
+        dz = torch.empty_like(z) if z is not None else None
+        _lib.check(lib.phc_segment_pool_bwd(g.data_ptr(), x.data_ptr(), _ptr(z), batch.data_ptr(), N, F, ctx.n, dx.data_ptr(),
+                                            _ptr(dz), _stream(x.device)), "phc_segment_pool_bwd")
+        return dx, dz, None, None, None
+
+
+def segment_pool(x, batch, seg: SegmentStructure, phm_dim: int, gate_logits=None) -> torch.Tensor:
+    return _Pool.apply(x, gate_logits, batch.contiguous(), seg, phm_dim)
+
+
+# --------------------------------------------------------------------------------- norm/act/dropout/skip
+_SEED_GEN = None
+
+
+def next_dropout_seed(device) -> int:
+    """A fresh 63-bit seed drawn from torch's CPU generator (so torch.manual_seed controls dropout)."""
+    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
+
+class _BnActDropSkip(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, skip, cfg, flat, *params):
+        # params = n gammas followed by n betas (only for autograd bookkeeping; the kernel reads `flat`)
+        lib = _lib.load()
+        h = _f32c(h, "h")
+        M, F = h.shape
+        (n, use_bn, training, momentum, eps, act, p, same, seed) = cfg
+        gamma, beta, rmean, rvar, tracked = flat if flat is not None else (None,) * 5
+        if skip is not None:
+            skip = _f32c(skip, "skip")
+            assert skip.shape == h.shape
+        y = torch.empty_like(h)
+        dev = h.device
+        stats = torch.empty((2, F), dtype=torch.float32, device=dev) if use_bn else None
+        nb = lib.phc_bn_workspace_bytes(M, F) if (use_bn and training) else 16
+        ws = _ws(nb, dev)
+        upd = training and use_bn
+        _lib.check(lib.phc_bn_act_drop_skip_fwd(
+            h.data_ptr(), _ptr(gamma), _ptr(beta), _ptr(rmean) if (upd or not training) else 0,
+            _ptr(rvar) if (upd or not training) else 0, _ptr(tracked) if upd else 0,
+            0 if tracked is None else tracked.numel(), _ptr(skip), M, F, n, int(use_bn), int(training), momentum, eps, act,
+            float(p), int(same), seed, y.data_ptr(), _ptr(stats[0]) if use_bn else 0, _ptr(stats[1]) if use_bn else 0,
+            ws.data_ptr(), ws.numel(), _stream(dev)), "phc_bn_act_drop_skip_fwd")
+        ctx.save_for_backward(h, gamma, beta, stats)
+        ctx.cfg = cfg
+        ctx.nparams = len(params)
+        ctx.has_skip = skip is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib.load()
+        h, gamma, beta, stats = ctx.saved_tensors
+        (n, use_bn, training, momentum, eps, act, p, same, seed) = ctx.cfg
+        gy = _f32c(gy, "grad_output")
+        M, F = h.shape
+        dev = h.device
+        dh = torch.empty_like(h)
+        dgb = torch.empty((2, F), dtype=torch.float32, device=dev) if use_bn else None
+        nb = lib.phc_bn_workspace_bytes(M, F) if use_bn else 16
+        ws = _ws(nb, dev)
+        _lib.check(lib.phc_bn_act_drop_skip_bwd(
+            gy.data_ptr(), h.data_ptr(), _ptr(gamma), _ptr(beta), _ptr(stats[0]) if use_bn else 0,
+            _ptr(stats[1]) if use_bn else 0, M, F, n, int(use_bn), int(training), act, float(p), int(same), seed, dh.data_ptr(),
+            _ptr(dgb[0]) if use_bn else 0, _ptr(dgb[1]) if use_bn else 0, ws.data_ptr(), ws.numel(), _stream(dev)),
+            "phc_bn_act_drop_skip_bwd")
+        grads: List[Optional[torch.Tensor]] = []
+        if ctx.nparams:
+            k = ctx.nparams // 2
+            fc = F // k
+            grads = [dgb[0, c * fc:(c + 1) * fc] for c in range(k)] + [dgb[1, c * fc:(c + 1) * fc] for c in range(k)]
+        return (dh, gy if ctx.has_skip else None, None, None) + tuple(grads)
+
+
+def bn_act_drop_skip(h, skip, *, phm_dim: int, flat=None, params: Sequence[torch.Tensor] = (), use_bn: bool, training: bool,
+                     momentum: float = 0.1, eps: float = 1e-5, act: str = "identity", drop_p: float = 0.0,
+                     drop_same: bool = False) -> torch.Tensor:
+    """y = skip + dropout(act(batchnorm(h)));  ``flat`` = (gamma[F], beta[F], running_mean[F], running_var[F],
+    num_batches_tracked[n]) flat device vectors that alias the n per-component BatchNorm1d parameters."""
+    assert 0.0 <= drop_p <= 1.0, f"dropout rate must be in [0.0 ; 1.0]. {drop_p} was inserted!"
+    active_drop = training and drop_p > 0.0
+    seed = next_dropout_seed(h.device) if active_drop else 0
+    cfg = (phm_dim, bool(use_bn), bool(training), float(momentum), float(eps), act_id(act),
+           float(drop_p) if active_drop else 0.0, bool(drop_same), seed)
+    return _BnActDropSkip.apply(h, skip, cfg, flat, *params)
+
+
+# --------------------------------------------------------------------------------- encoders
+class _EmbedSum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, idx, n, cols, vocab, *tables):
+        lib = _lib.load()
+        require_cuda(idx, "integer features")
+        idx = idx.contiguous()
+        if idx.dtype != torch.int64:
+            idx = idx.to(torch.int64)
+        R = idx.size(0)
+        fc = tables[0].size(1)
+        for t in tables:
+            require_cuda(t, "embedding table")
+            assert t.is_contiguous() and t.dtype == torch.float32
+        out = torch.empty((R, n * fc), dtype=torch.float32, device=idx.device)
+        vc = (ctypes.c_int * cols)(*vocab)
+        _lib.check(lib.phc_embed_sum_fwd(idx.data_ptr(), _ptr_array(tables), vc, R, cols, n, fc, out.data_ptr(),
+                                         _stream(idx.device)), "phc_embed_sum_fwd")
+        ctx.save_for_backward(idx)
+        ctx.meta = (n, cols, tuple(vocab), fc)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        (idx,) = ctx.saved_tensors
+        n, cols, vocab, fc = ctx.meta
+        g = _f32c(g, "grad_output")
+        R = idx.size(0)
+        vtot = sum(vocab)
+        flat = torch.empty(n * vtot * fc, dtype=torch.float32, device=g.device)
+        grads, o = [], 0
+        for c in range(n):
+            for col in range(cols):
+                grads.append(flat[o:o + vocab[col] * fc].view(vocab[col], fc))
+                o += vocab[col] * fc
+        nb = lib.phc_embed_bwd_workspace_bytes(R, vtot, n * fc)
+        ws = _ws(nb, g.device)
+        vc = (ctypes.c_int * cols)(*vocab)
+        _lib.check(lib.phc_embed_sum_bwd(g.data_ptr(), idx.data_ptr(), _ptr_array(grads), vc, R, cols, n, fc, ws.data_ptr(),
+                                         ws.numel(), _stream(g.device)), "phc_embed_sum_bwd")
+        return (None, None, None, None) + tuple(grads)
+
+
+def embed_sum(idx: torch.Tensor, tables: Sequence[torch.Tensor], phm_dim: int, vocab: Sequence[int]) -> torch.Tensor:
+    """out[r, c*Fc+f] = sum_col tables[c*cols+col][idx[r,col], f]."""
+    cols = len(vocab)
+    return _EmbedSum.apply(idx, phm_dim, cols, tuple(int(v) for v in vocab), *tables)
+
+
+class _LinearEncoder(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, n, *wb):
+        lib = _lib.load()
+        feat = _f32c(feat, "features")
+        if feat.dim() == 1:
+            feat = feat.unsqueeze(1)
+        weights, biases = wb[:n], wb[n:]
+        R, D = feat.shape
+        fc = weights[0].size(0)
+        for t in wb:
+            require_cuda(t, "encoder parameter")
+            assert t.is_contiguous() and t.dtype == torch.float32
+        out = torch.empty((R, n * fc), dtype=torch.float32, device=feat.device)
+        _lib.check(lib.phc_linear_encoder_fwd(feat.data_ptr(), _ptr_array(weights), _ptr_array(biases), R, D, n, fc,
+                                              out.data_ptr(), _stream(feat.device)), "phc_linear_encoder_fwd")
+        ctx.save_for_backward(feat)
+        ctx.meta = (n, fc, D)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        (feat,) = ctx.saved_tensors
+        n, fc, D = ctx.meta
+        g = _f32c(g, "grad_output")
+        R = feat.size(0)
+        flat = torch.empty(n * fc * (D + 1), dtype=torch.float32, device=g.device)
+        dws = [flat[c * fc * D:(c + 1) * fc * D].view(fc, D) for c in range(n)]
+        dbs = [flat[n * fc * D + c * fc:n * fc * D + (c + 1) * fc] for c in range(n)]
+        nb = lib.phc_linear_encoder_bwd_workspace_bytes(R, D, n * fc)
+        ws = _ws(nb, g.device)
+        _lib.check(lib.phc_linear_encoder_bwd(g.data_ptr(), feat.data_ptr(), _ptr_array(dws), _ptr_array(dbs), R, D, n, fc,
+                                              ws.data_ptr(), ws.numel(), _stream(g.device)), "phc_linear_encoder_bwd")
+        return (None, None) + tuple(dws) + tuple(dbs)
+
+
+def linear_encoder(feat: torch.Tensor, weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor]) -> torch.Tensor:
+    """out[r, c*Fc+f] = feat[r,:] @ weights[c][f,:] + biases[c][f]."""
+    n = len(weights)
+    return _LinearEncoder.apply(feat.to(torch.float32), n, *weights, *biases)

@@ -1,0 +1,71 @@
+"""Helpers shared by the -m gpu parity tests: run the product model (CUDA kernels through the
+C ABI) and the CPU oracle on identical inputs/weights."""
+import torch
+
+from oracle import phc_oracle as O
+
+
+def cuda():
+    return torch.device("cuda:0")
+
+
+def product_model(cfg, state, device):
+    from phc.hypercomplex.undirectional.models import PHMSkipConnectAdd
+    m = PHMSkipConnectAdd(**cfg)
+    m.load_state_dict(state, strict=True)
+    return m.to(device)
+
+
+def oracle_params(state, dtype=torch.float32):
+    p = {}
+    for k, v in state.items():
+        v = v.detach().cpu().clone()
+        if v.is_floating_point():
+            v = v.to(dtype)
+            if "running" not in k:
+                v.requires_grad_(True)
+        p[k] = v
+    return p
+
+
+def product_train_eval(cfg, state, batch, loss_kind, reg_scale, device):
+    """-> dict(logits, loss, reg, grads, running, logits_eval) from the CUDA path."""
+    from phc.hypercomplex.regularization import phm_weight_regularization
+    m = product_model(cfg, state, device)
+    data = batch.to(device)
+    m.train()
+    logits = m(data)
+    reg = phm_weight_regularization(m, p=2)
+    loss = O.task_loss(logits, data.y, loss_kind) + reg_scale * reg
+    loss.backward()
+    torch.cuda.synchronize()
+    grads = {n: p.grad.detach().cpu().clone() for n, p in m.named_parameters() if p.grad is not None}
+    running = {n: v.detach().cpu().clone() for n, v in m.state_dict().items() if "running" in n or "tracked" in n}
+    m.eval()
+    with torch.no_grad():
+        ev = m(data)
+    return dict(logits=logits.detach().cpu(), loss=loss.detach().cpu(), reg=reg.detach().cpu(), grads=grads, running=running,
+                logits_eval=ev.cpu(), model=m)
+
+
+def oracle_train_eval(cfg, state, batch, loss_kind, reg_scale, dtype=torch.float32):
+    p = oracle_params(state, dtype)
+    logits = O.model_forward(p, cfg, batch, training=True)
+    reg = O.weight_regularization(p, 2)
+    loss = O.task_loss(logits, batch.y, loss_kind) + reg_scale * reg
+    loss.backward()
+    grads = {k: v.grad.detach().clone().float() for k, v in p.items() if v.requires_grad and v.grad is not None}
+    running = {k: v.detach().clone().float() for k, v in p.items() if "running" in k}
+    with torch.no_grad():
+        ev = O.model_forward(p, cfg, batch, training=False)
+    return dict(logits=logits.detach().float(), loss=loss.detach().float(), reg=reg.detach().float(), grads=grads,
+                running=running, logits_eval=ev.float())
+
+
+def assert_close(a, b, rtol, atol, what=""):
+    torch.testing.assert_close(a, b, rtol=rtol, atol=atol, msg=lambda m: f"{what}: {m}")
+
+
+def grad_tol(ref: torch.Tensor, rtol: float):
+    """absolute tolerance scaled to the tensor's magnitude (gradients span many orders)."""
+    return rtol * max(float(ref.abs().max()), 1e-6)

@@ -1,0 +1,87 @@
+"""Whole-model parity: the product modules (CUDA kernels through the C ABI) against (a) the vectors
+recorded from the UNMODIFIED reference (tests/golden) and (b) the CPU oracle on larger seeded batches."""
+import pytest
+import torch
+
+from conftest import golden_cases, load_golden
+from gpu_util import assert_close, grad_tol, oracle_train_eval, product_train_eval
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4      # north_star fp32 tolerance
+DEV = "cuda:0"
+
+
+def _compare(got, want, rtol, what):
+    scale = max(float(want["logits"].abs().max()), 1e-3)
+    assert_close(got["logits"], want["logits"], rtol, rtol * scale, f"{what}: train logits")
+    assert_close(got["reg"], want["reg"], rtol, 1e-6, f"{what}: regulariser")
+    assert_close(got["loss"], want["loss"], rtol, 1e-6, f"{what}: loss")
+    assert_close(got["logits_eval"], want["logits_eval"], rtol, rtol * scale, f"{what}: eval logits")
+    for k, g in want["grads"].items():
+        assert k in got["grads"], f"{what}: no gradient for {k}"
+        assert_close(got["grads"][k], g, 5 * rtol, grad_tol(g, 5 * rtol), f"{what}: grad {k}")
+    for k, v in want["running"].items():
+        assert_close(got["running"][k].float(), v.float(), rtol, 1e-5, f"{what}: {k}")
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_model_matches_reference_golden(name, monkeypatch):
+    monkeypatch.setenv("PHC_PRECISION", "fp32")
+    fx = load_golden(name)
+    got = product_train_eval(fx["cfg"], fx["state"], fx["batch"], fx["loss_kind"], fx["reg_scale"], DEV)
+    want = dict(logits=fx["logits_train"], loss=fx["loss"], reg=fx["reg"], grads=fx["grads"], running=fx["running_after"],
+                logits_eval=fx["logits_eval"])
+    _compare(got, want, RTOL, name)
+
+
+@pytest.mark.parametrize("wl_name,graphs,n", [("hiv", 32, 4), ("zinc", 32, 2), ("zinc", 32, 4), ("pcba", 24, 4), ("mnist", 8, 4), ("ppa", 2, 4)])
+def test_model_matches_oracle_on_workload_shapes(wl_name, graphs, n, monkeypatch):
+    """Full-width models (reference default hyper-parameters) on small batches of the benchmark shapes."""
+    monkeypatch.setenv("PHC_PRECISION", "fp32")
+    from phc.hypercomplex.undirectional.models import PHMSkipConnectAdd
+    from phc_gnn_b200.synthetic import workloads, make_batch
+    wl = workloads(n)[wl_name]
+    cfg = dict(wl.model)
+    cfg["dropout_mpnn"] = [0.0] * len(cfg["mp_layers"])
+    cfg["dropout_dn"] = [0.0] * len(cfg["downstream_layers"])
+    if wl_name in ("pcba", "ppa"):
+        cfg["mp_layers"] = cfg["mp_layers"][:3]
+        cfg["dropout_mpnn"] = cfg["dropout_mpnn"][:3]
+    torch.manual_seed(0)
+    import numpy as np
+    np.random.seed(0)
+    state = PHMSkipConnectAdd(**cfg).state_dict()
+    batch = make_batch(wl, seed=7, batch_graphs=graphs)
+    got = product_train_eval(cfg, state, batch, wl.loss, 0.01, DEV)
+    want = oracle_train_eval(cfg, state, batch, wl.loss, 0.01, torch.float64)
+    _compare(got, want, 2e-4, wl_name)
+
+
+def test_training_step_is_bitwise_reproducible(monkeypatch):
+    monkeypatch.setenv("PHC_PRECISION", "fp32")
+    fx = load_golden("hiv_n4_softmax_mlp")
+    a = product_train_eval(fx["cfg"], fx["state"], fx["batch"], fx["loss_kind"], fx["reg_scale"], DEV)
+    b = product_train_eval(fx["cfg"], fx["state"], fx["batch"], fx["loss_kind"], fx["reg_scale"], DEV)
+    assert torch.equal(a["logits"], b["logits"])
+    for k in a["grads"]:
+        assert torch.equal(a["grads"][k], b["grads"][k]), k
+
+
+def test_module_pickles_and_moves_between_devices():
+    import io
+    fx = load_golden("zinc_n4_sum_mlp_last")
+    from gpu_util import product_model
+    m = product_model(fx["cfg"], fx["state"], DEV)
+    m.train()
+    y1 = m(fx["batch"].to(DEV))
+    buf = io.BytesIO()
+    torch.save(m, buf)                                    # whole-module pickle, as the reference scripts do (train_hiv.py:344)
+    buf.seek(0)
+    m2 = torch.load(buf, weights_only=False)
+    m2.load_state_dict(fx["state"])
+    m2 = m2.cpu().to(DEV)                                 # .to() re-points parameter storage: flat caches must rebuild
+    m2.train()
+    y2 = m2(fx["batch"].to(DEV))
+    m.load_state_dict(fx["state"])
+    y1 = m(fx["batch"].to(DEV))
+    assert torch.equal(y1, y2)

@@ -1,0 +1,271 @@
+"""Operator-level parity of the CUDA kernels (through the C ABI) against the CPU oracle and the
+reference-recorded known answers.  fp32 tolerance: rtol 1e-4 (north_star), atol scaled per case."""
+import itertools
+
+import pytest
+import torch
+
+from gpu_util import assert_close, grad_tol
+from oracle import phc_oracle as O
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+DEV = "cuda:0"
+
+
+def _graph(n, e, seed, dup_free=True):
+    g = torch.Generator().manual_seed(seed)
+    ei = torch.randint(0, n, (2, 3 * e), generator=g, dtype=torch.int64)
+    if dup_free:
+        key = torch.unique(ei[0] * n + ei[1])
+        key = key[torch.randperm(key.numel(), generator=g)][:e]
+        ei = torch.stack([key // n, key % n])
+    return ei.contiguous()
+
+
+@pytest.mark.parametrize("reduce,act,F,self_loop", [
+    ("add", "identity", 16, True), ("add", "relu", 20, False), ("mean", "identity", 12, True), ("mean", "swish", 8, False),
+    ("max", "identity", 16, True), ("max", "relu", 16, False), ("min", "elu", 12, True), ("softmax", "identity", 16, True),
+    ("softmax", "relu", 8, False), ("softmax", "swish", 20, True), ("add", "identity", 7, True), ("max", "lrelu", 9, False),
+    ("softmax", "selu", 5, True), ("add", "identity", 500, True), ("softmax", "identity", 200, True)])
+def test_aggregate_fwd_bwd(reduce, act, F, self_loop):
+    from phc_gnn_b200 import ops
+    from phc_gnn_b200.graph import EdgeStructure
+    N, E = 57, 300
+    ei = _graph(N, E, 3)
+    E = ei.size(1)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(N, F, generator=g)
+    ea = torch.randn(E, F, generator=g)
+    beta = torch.tensor(0.8)
+    gout = torch.randn(N, F, generator=g)
+    # oracle in fp64
+    xo, eo, bo = (t.double().requires_grad_(True) for t in (x, ea, beta))
+    ref = O.propagate(xo, ei, eo, reduce, act, bo)
+    if self_loop:
+        ref = ref + xo
+    ref.backward(gout.double())
+    xs, es, bs = (t.to(DEV).requires_grad_(True) for t in (x, ea, beta))
+    s = EdgeStructure(ei.to(DEV), N)
+    out = ops.aggregate(xs, es, s, reduce, act, bs, self_loop)
+    out.backward(gout.to(DEV))
+    assert_close(out.detach().cpu(), ref.detach().float(), RTOL, 1e-5, "out")
+    assert_close(xs.grad.cpu(), xo.grad.float(), RTOL, grad_tol(xo.grad, RTOL), "dx")
+    assert_close(es.grad.cpu(), eo.grad.float(), RTOL, grad_tol(eo.grad, RTOL), "dea")
+    if reduce == "softmax":
+        assert_close(bs.grad.cpu(), bo.grad.float(), 1e-3, grad_tol(bo.grad, 1e-3), "dbeta")
+
+
+def test_aggregate_empty_rows_and_isolated_nodes():
+    from phc_gnn_b200 import ops
+    from phc_gnn_b200.graph import EdgeStructure
+    N, F = 9, 8
+    ei = torch.tensor([[0, 1, 2, 2], [1, 1, 1, 3]])
+    x, ea = torch.randn(N, F), torch.randn(4, F)
+    s = EdgeStructure(ei.to(DEV), N)
+    for red in ("add", "mean", "max", "min", "softmax"):
+        ref = O.propagate(x, ei, ea, red, "identity", torch.tensor(1.0))
+        out = ops.aggregate(x.to(DEV), ea.to(DEV), s, red, "identity", torch.tensor(1.0, device=DEV), False)
+        assert_close(out.cpu(), ref, RTOL, 1e-6, red)
+        assert float(out[5:].abs().max()) == 0.0          # untouched rows are exactly zero
+
+
+def test_aggregate_is_bitwise_deterministic():
+    from phc_gnn_b200 import ops
+    from phc_gnn_b200.graph import EdgeStructure
+    N, F = 2000, 64
+    ei = _graph(N, 30000, 5)
+    x = torch.randn(N, F, device=DEV, requires_grad=True)
+    ea = torch.randn(ei.size(1), F, device=DEV, requires_grad=True)
+    beta = torch.tensor(1.0, device=DEV, requires_grad=True)
+    outs = []
+    for _ in range(2):
+        s = EdgeStructure(ei.to(DEV), N)
+        out = ops.aggregate(x, ea, s, "softmax", "relu", beta, True)
+        gx, ge, gb = torch.autograd.grad(out.square().sum(), (x, ea, beta))
+        outs.append((out.detach().clone(), gx, ge, gb))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("gated,F,n", [(False, 16, 4), (True, 16, 4), (True, 20, 5), (False, 9, 3), (True, 9, 3), (True, 500, 4)])
+def test_pool_fwd_bwd(gated, F, n):
+    from phc_gnn_b200 import ops
+    from phc_gnn_b200.graph import SegmentStructure
+    sizes = [5, 1, 0, 17, 40, 3]
+    batch = torch.cat([torch.full((s,), i, dtype=torch.int64) for i, s in enumerate(sizes)])
+    N, B = batch.numel(), len(sizes)
+    x = torch.randn(N, F)
+    z = torch.randn(N, F // n) if gated else None
+    gout = torch.randn(B, F)
+    xo = x.double().requires_grad_(True)
+    zo = z.double().requires_grad_(True) if gated else None
+    xin = (xo.reshape(N, n, -1) * torch.sigmoid(zo)[:, None, :]).reshape(N, F) if gated else xo
+    ref = O.seg_sum(xin, batch, B)
+    ref.backward(gout.double())
+    xs = x.to(DEV).requires_grad_(True)
+    zs = z.to(DEV).requires_grad_(True) if gated else None
+    seg = SegmentStructure(batch.to(DEV), B)
+    out = ops.segment_pool(xs, batch.to(DEV), seg, n, gate_logits=zs)
+    out.backward(gout.to(DEV))
+    assert_close(out.detach().cpu(), ref.detach().float(), RTOL, 1e-5, "pool")
+    assert_close(xs.grad.cpu(), xo.grad.float(), RTOL, 1e-5, "dx")
+    if gated:
+        assert_close(zs.grad.cpu(), zo.grad.float(), RTOL, 1e-5, "dz")
+
+
+@pytest.mark.parametrize("M,F,n,act,affine,skip,training", [
+    (64, 16, 4, "relu", True, True, True), (300, 20, 5, "identity", True, False, True), (257, 12, 3, "swish", True, True, True),
+    (129, 9, 3, "elu", False, True, True), (64, 16, 4, "relu", True, True, False), (1000, 200, 4, "lrelu", True, True, True),
+    (2, 8, 2, "selu", True, False, True)])
+def test_norm_act_skip(M, F, n, act, affine, skip, training):
+    from phc.hypercomplex.norm import PHMNorm
+    g = torch.Generator().manual_seed(1)
+    h = torch.randn(M, F, generator=g) * 2.0 + 3.0          # non-zero mean: exercises the variance algorithm
+    sk = torch.randn(M, F, generator=g) if skip else None
+    gout = torch.randn(M, F, generator=g)
+    norm = PHMNorm(F, n, affine=affine)
+    p = {}
+    with torch.no_grad():
+        for c, bn in enumerate(norm.bn.bn):
+            if affine:
+                bn.weight.copy_(1 + 0.3 * torch.randn(F // n, generator=g)); bn.bias.copy_(0.2 * torch.randn(F // n, generator=g))
+            bn.running_mean.copy_(0.1 * torch.randn(F // n, generator=g)); bn.running_var.copy_(1 + torch.rand(F // n, generator=g))
+            for k in ("weight", "bias", "running_mean", "running_var"):
+                v = getattr(bn, k)
+                p[f"n.bn.bn.{c}.{k}"] = None if v is None else v.detach().clone().double()
+    for k, v in p.items():
+        if v is not None and "running" not in k:
+            v.requires_grad_(True)
+    ho = h.double().requires_grad_(True)
+    ref = O.activation(O.phm_norm(ho, p, "n", n, training), act)
+    if skip:
+        ref = ref + sk.double()
+    ref.backward(gout.double())
+    norm = norm.to(DEV)
+    norm.train(training)
+    hs = h.to(DEV).requires_grad_(True)
+    out = norm.fused(hs, skip=sk.to(DEV) if skip else None, act=act)
+    out.backward(gout.to(DEV))
+    assert_close(out.detach().cpu(), ref.detach().float(), RTOL, 2e-5, "y")
+    assert_close(hs.grad.cpu(), ho.grad.float(), 2e-4, grad_tol(ho.grad, 2e-4), "dh")
+    for c, bn in enumerate(norm.bn.bn):
+        if affine:
+            assert_close(bn.weight.grad.cpu(), p[f"n.bn.bn.{c}.weight"].grad.float(), 2e-4, grad_tol(p[f"n.bn.bn.{c}.weight"].grad, 2e-4), "dgamma")
+            assert_close(bn.bias.grad.cpu(), p[f"n.bn.bn.{c}.bias"].grad.float(), 2e-4, grad_tol(p[f"n.bn.bn.{c}.bias"].grad, 2e-4), "dbeta")
+        assert_close(bn.running_mean.cpu(), p[f"n.bn.bn.{c}.running_mean"].float(), RTOL, 1e-5, "running_mean")
+        assert_close(bn.running_var.cpu(), p[f"n.bn.bn.{c}.running_var"].float(), RTOL, 1e-5, "running_var")
+        assert int(bn.num_batches_tracked) == (1 if training else 0)
+
+
+def test_dropout_invariants():
+    # mirrors reference phc/hypercomplex/tests/test_ops_equal_quaternion.py:62-103
+    from phc.hypercomplex.layers import phm_dropout
+    n, M, Fc, p = 4, 512, 32, 0.3
+    x = torch.randn(M, n * Fc, device=DEV) + 5.0
+    torch.manual_seed(0)
+    y = phm_dropout(x, n, p=p, training=True, same=False)
+    kept = y != 0
+    assert_close(y[kept], (x / (1 - p))[kept], 1e-6, 1e-6, "scale")
+    frac = kept.float().mean().item()
+    assert abs(frac - (1 - p)) < 0.02
+    y2 = phm_dropout(x, n, p=p, training=True, same=True)
+    z = (y2 == 0).view(M, n, Fc)
+    assert bool((z == z[:, :1]).all())                     # identical zero pattern across components
+    assert abs((~z).float().mean().item() - (1 - p)) < 0.03
+    assert phm_dropout(x, n, p=p, training=False) is x
+    assert phm_dropout(x, n, p=0.0, training=True) is x
+    # backward uses the same mask as forward
+    xr = x.clone().requires_grad_(True)
+    torch.manual_seed(5)
+    yr = phm_dropout(xr, n, p=p, training=True)
+    yr.sum().backward()
+    assert torch.equal(xr.grad != 0, yr != 0)
+    torch.manual_seed(5)
+    assert torch.equal(phm_dropout(x, n, p=p, training=True), yr.detach())     # seeded => reproducible
+    with pytest.raises(AssertionError):
+        phm_dropout(x, n, p=1.5)
+
+
+@pytest.mark.parametrize("n,dims,Fc,R", [(4, [119, 4, 12, 12, 10, 6, 6, 2, 2], 8, 333), (2, [28], 6, 100), (4, [5, 6, 2], 50, 2000),
+                                         (3, [1], 5, 40), (5, [4], 4, 1)])
+def test_embedding_encoder(n, dims, Fc, R):
+    from phc.hypercomplex.encoder import PHMEncoder
+    g = torch.Generator().manual_seed(2)
+    enc = PHMEncoder(Fc, dims, n)
+    idx = torch.stack([torch.randint(0, d, (R,), generator=g) for d in dims], 1)
+    if len(dims) == 1:
+        idx = idx[:, 0]
+    p = {f"e.{k}": v.detach().clone().double().requires_grad_(True) for k, v in enc.state_dict().items()}
+    ref = O.encoder(idx, p, "e", n, dims, torch.float64)
+    gout = torch.randn(R, n * Fc, generator=g)
+    ref.backward(gout.double())
+    enc = enc.to(DEV)
+    out = enc(idx.to(DEV))
+    assert out.shape == (R, n, Fc)
+    out.reshape(R, -1).backward(gout.to(DEV))
+    assert_close(out.detach().cpu().reshape(R, -1), ref.detach().float(), 1e-6, 1e-6, "embed")
+    for k, v in enc.named_parameters():
+        assert_close(v.grad.cpu(), p["e." + k].grad.float(), RTOL, grad_tol(p["e." + k].grad, RTOL), k)
+
+
+@pytest.mark.parametrize("n,D,Fc,R", [(4, 7, 125, 3000), (4, 3, 56, 500), (2, 1, 6, 77), (4, 5, 5, 10)])
+def test_linear_encoder(n, D, Fc, R):
+    from phc.hypercomplex.encoder import PHMEncoder
+    g = torch.Generator().manual_seed(2)
+    enc = PHMEncoder(Fc, D, n)
+    feat = torch.rand(R, D, generator=g)
+    p = {f"e.{k}": v.detach().clone().double().requires_grad_(True) for k, v in enc.state_dict().items()}
+    ref = O.encoder(feat, p, "e", n, D, torch.float64)
+    gout = torch.randn(R, n * Fc, generator=g)
+    ref.backward(gout.double())
+    enc = enc.to(DEV)
+    out = enc.flat(feat.to(DEV))
+    out.backward(gout.to(DEV))
+    assert_close(out.detach().cpu(), ref.detach().float(), RTOL, 1e-5, "linear encoder")
+    for k, v in enc.named_parameters():
+        assert_close(v.grad.cpu(), p["e." + k].grad.float(), RTOL, grad_tol(p["e." + k].grad, RTOL), k)
+
+
+def _phm_linear_case(n, fin, fout, M, precision, rtol, seed=0):
+    from phc_gnn_b200 import ops
+    g = torch.Generator().manual_seed(seed)
+    A = torch.randn(n, n, n, generator=g) * 0.5
+    W = torch.randn(n, fin // n, fout // n, generator=g) * 0.2
+    b = torch.randn(fout, generator=g)
+    x = torch.randn(M, fin, generator=g)
+    res = torch.randn(M, fout, generator=g)
+    gy = torch.randn(M, fout, generator=g)
+    po = {"l.phm_rule": A.double().requires_grad_(True), "l.W": W.double().requires_grad_(True), "l.b": b.double().requires_grad_(True)}
+    xo = x.double().requires_grad_(True)
+    ro = res.double().requires_grad_(True)
+    ref = O.phm_linear(xo, po, "l") + ro
+    ref.backward(gy.double())
+    t = [v.to(DEV).requires_grad_(True) for v in (x, A, W, b, res)]
+    y = ops.phm_linear(t[0], t[1], t[2], t[3], t[4], precision=precision)
+    y.backward(gy.to(DEV))
+    scale = float(ref.abs().max())
+    assert_close(y.detach().cpu(), ref.detach().float(), rtol, rtol * scale, "y")
+    for got, want, nm in ((t[0].grad, xo.grad, "dx"), (t[1].grad, po["l.phm_rule"].grad, "dA"), (t[2].grad, po["l.W"].grad, "dW"),
+                          (t[3].grad, po["l.b"].grad, "db"), (t[4].grad, ro.grad, "dres")):
+        assert_close(got.cpu(), want.float(), rtol, grad_tol(want, rtol), nm)
+
+
+@pytest.mark.parametrize("n,fin,fout,M", [(4, 16, 24, 9), (2, 10, 6, 7), (3, 9, 12, 5), (5, 20, 10, 6), (1, 7, 5, 4), (8, 64, 32, 130),
+                                          (4, 200, 200, 333), (4, 500, 500, 300), (2, 180, 180, 257), (4, 224, 224, 1000),
+                                          (4, 512, 768, 64), (16, 32, 48, 50)])
+def test_phm_linear_fp32(n, fin, fout, M):
+    _phm_linear_case(n, fin, fout, M, precision=0, rtol=RTOL)
+
+
+def test_phm_linear_known_answers(ops_golden):
+    from phc_gnn_b200 import ops
+    for key, fx in ops_golden.items():
+        if not key.startswith("phmlinear"):
+            continue
+        t = {k: fx[k].to(DEV).requires_grad_(k in ("x", "A", "W", "b")) for k in ("x", "A", "W", "b", "gy")}
+        y = ops.phm_linear(t["x"], t["A"], t["W"], t["b"], precision=0)
+        assert_close(y.detach().cpu(), fx["y"], RTOL, 1e-5, key)
+        y.backward(t["gy"])
+        for got, want in ((t["x"].grad, fx["gx"]), (t["A"].grad, fx["gA"]), (t["W"].grad, fx["gW"]), (t["b"].grad, fx["gb"])):
+            assert_close(got.cpu(), want, RTOL, grad_tol(want, RTOL), key)
