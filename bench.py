@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""Throughput benchmark for the PHC-GNN hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload ppa|cifar|mnist|pcba|zinc|hiv] [--impl reference]
+
+Metric (BASELINE.json): train graphs/sec (fwd+bwd+step); roofline = achieved HBM GB/s of the fused
+neighbour-aggregation kernel vs the measured peak.  A step is one iteration of the reference's
+train() body (benchmarks/train_hiv.py:170-202) on one synthetic mini-batch per GPU (weak scaling:
+per-GPU batch fixed).  N>1 is launched by torchrun, one rank per GPU, gradients all-reduced by NCCL.
+Prints ONE JSON line on rank 0.  `--impl reference` times the CPU oracle port of the reference
+(oracle/phc_oracle.py; the reference is Python + PyG/torch_scatter which are not installable here).
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "train_graphs_per_sec"
+UNIT = "graphs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="ppa")
+    ap.add_argument("--phm-dim", type=int, default=4)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batches", type=int, default=8, help="distinct synthetic batches cycled per rank")
+    ap.add_argument("--precision", default=None, help="fp32 | tf32x3 | bf16 (default: PHC_PRECISION or tf32x3)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--kernel-timers", action="store_true", help="also print the per-op CUDA-event breakdown to stderr")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                mask = get(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        self.stop_flag = True
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def workload(args):
+    from phc_gnn_b200.synthetic import workloads
+    return workloads(args.phm_dim)[args.workload]
+
+
+def run_reference(args):
+    """CPU arm: the oracle port of the reference on the host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import phc_oracle as O
+    from phc_gnn_b200.synthetic import make_batch
+    from phc_gnn_b200.nn import PHMSkipConnectAdd
+    wl = workload(args)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample_graphs = max(2, wl.batch_graphs // 8) if wl.name in ("ppa", "pcba", "cifar") else wl.batch_graphs
+    torch.manual_seed(0)
+    state = PHMSkipConnectAdd(**wl.model).state_dict()
+    p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in state.items()}
+    opt = torch.optim.Adam(O.trainable(p), lr=wl.lr)
+    batches = [make_batch(wl, seed=i, batch_graphs=sample_graphs) for i in range(min(args.batches, 4))]
+    g = torch.Generator().manual_seed(0)
+    for i in range(args.warmup):
+        O.train_step(p, wl.model, batches[i % len(batches)], wl.loss, opt, wl.lr, wl.weight_decay, wl.grad_clip, g)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        O.train_step(p, wl.model, batches[i % len(batches)], wl.loss, opt, wl.lr, wl.weight_decay, wl.grad_clip, g)
+    dt = time.perf_counter() - t0
+    val = sample_graphs * args.steps / dt
+    sample = f"{sample_graphs} graphs/step x {args.steps} steps of the {wl.name}-shaped workload (full per-GPU batch is {wl.batch_graphs})"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(args, wl, sample_graphs, "cpu"),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def config_dict(args, wl, graphs_per_gpu, l2):
+    m = wl.model
+    return {"workload": f"{wl.name}-shaped synthetic graphs (BASELINE.json configs: PHC-GNN n={m['phm_dim']}, "
+                        f"{len(m['mp_layers'])}x{m['mp_layers'][0]}, aggr={m['msg_aggr']}, mlp={m['mlp']})",
+            "graphs_per_gpu_batch": graphs_per_gpu, "phm_dim": m["phm_dim"], "width": m["mp_layers"][0],
+            "layers": len(m["mp_layers"]), "aggr": m["msg_aggr"], "parallelism": f"dp{args.gpus}", "l2": l2}
+
+
+def cpu_baseline(wl, budget_s: float = 25.0):
+    """Oracle port timed on the host cores for a bounded sample (rank 0, N=1 only)."""
+    from oracle import phc_oracle as O
+    from phc_gnn_b200.synthetic import make_batch
+    from phc_gnn_b200.nn import PHMSkipConnectAdd
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample_graphs = max(2, wl.batch_graphs // 8) if wl.name in ("ppa", "pcba", "cifar") else wl.batch_graphs
+    torch.manual_seed(0)
+    state = PHMSkipConnectAdd(**wl.model).state_dict()
+    p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in state.items()}
+    opt = torch.optim.Adam(O.trainable(p), lr=wl.lr)
+    batch = make_batch(wl, seed=0, batch_graphs=sample_graphs)
+    g = torch.Generator().manual_seed(0)
+    O.train_step(p, wl.model, batch, wl.loss, opt, wl.lr, wl.weight_decay, wl.grad_clip, g)      # warm-up
+    t0 = time.perf_counter()
+    steps = 0
+    while steps < 2 or (time.perf_counter() - t0 < budget_s and steps < 50):
+        O.train_step(p, wl.model, batch, wl.loss, opt, wl.lr, wl.weight_decay, wl.grad_clip, g)
+        steps += 1
+    dt = time.perf_counter() - t0
+    return {"value": sample_graphs * steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{steps} steps x {sample_graphs} graphs of the same {wl.name}-shaped workload, oracle/phc_oracle.py "
+                      f"(torch CPU, {cores} threads), {dt:.1f} s"}
+
+
+def aggregation_bytes(N, E, F, softmax):
+    """Algorithmic HBM bytes of one fused aggregation forward."""
+    return 4 * F * (2 * N + E) + 8 * E + 4 * (N + 1) + (8 * N * F if softmax else 0)
+
+
+def run_b200(args):
+    import torch.distributed as dist
+    from phc_gnn_b200 import ops, graph
+    from phc_gnn_b200.nn import PHMSkipConnectAdd
+    from phc_gnn_b200.parallel import DataParallelPHC
+    from phc_gnn_b200.synthetic import make_batch
+    from phc_gnn_b200.train import TrainStep, make_optimizer
+
+    if args.precision:
+        os.environ["PHC_PRECISION"] = args.precision
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback; use --impl reference for the CPU arm)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    wl = workload(args)
+    torch.manual_seed(0)
+    import numpy as np
+    np.random.seed(0)
+    model = PHMSkipConnectAdd(**wl.model).to(dev)
+    dp = DataParallelPHC(model) if world > 1 else None
+    step = TrainStep(model, wl, make_optimizer(model, wl.lr), dp)
+    model.train()
+
+    host = [make_batch(wl, seed=rank * 1000 + i).pin_memory() for i in range(args.batches)]
+    devb = [b.to(dev) for b in host]
+    ws_bytes = sum(b.num_edges for b in host) / len(host) * wl.model["mp_layers"][0] * 4
+    flush = ws_bytes < 256e6          # per-layer edge tensor smaller than 2x L2 -> flush L2 between steps
+    flush_buf = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev) if flush else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one(i, timing_events=None):
+        graph.clear_cache()                      # the CSR/segment build is part of every step
+        if flush:
+            flush_buf.fill_(i & 0xFF)
+        if timing_events is not None:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+        loss = step(devb[i % len(devb)])
+        if timing_events is not None:
+            b.record()
+            timing_events.append((a, b))
+        return loss
+
+    for i in range(args.warmup):
+        one(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ops.PROFILE.reset(timing=True)
+    evs = []
+    for i in range(args.steps):
+        loss = one(args.warmup + i, evs)
+    barrier()
+    clocks = sampler.result()
+    launches = ops.PROFILE.launches
+    prof = ops.PROFILE.summary()
+    ops.PROFILE.reset(timing=False)
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    graphs = wl.batch_graphs * args.steps * world
+    value = graphs / (ms / 1e3)
+
+    # ---- end-to-end: host batches, H2D inside the timed region, loss read back every step -------------
+    e2e = None
+    if not args.no_e2e:
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for i in range(args.steps):
+            graph.clear_cache()
+            d = host[(args.warmup + i) % len(host)].to(dev, non_blocking=True)
+            float(step(d).item())
+        t1.record()
+        barrier()
+        tt = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": graphs / (float(tt.item()) / 1e3), "unit": UNIT,
+               "h2d_bytes_per_step": int(sum(b.nbytes() for b in host) / len(host)), "d2h_bytes_per_step": 4}
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        N = sum(b.num_nodes for b in host) / len(host)
+        E = sum(b.num_edges for b in host) / len(host)
+        F = wl.model["mp_layers"][0]
+        calls, agg_ms = prof.get("phc_aggregate_fwd", (0, 0.0))
+        roof = None
+        if calls:
+            byt = aggregation_bytes(N, E, F, wl.model["msg_aggr"] == "softmax")
+            ach = byt / (agg_ms / calls * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": "aggregate_fwd_kernel (fused gather + edge add + reduce)", "achieved": ach,
+                    "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": byt, "avg_launch_us": 1e3 * agg_ms / calls,
+                    "share_of_step": agg_ms / ms}
+        breakdown = {k: {"calls_per_step": v[0] / args.steps, "ms_per_step": v[1] / args.steps} for k, v in sorted(prof.items())}
+        if args.kernel_timers:
+            print(json.dumps(breakdown, indent=1), file=sys.stderr)
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": {"fp32": "f32", "tf32x3": "f32 (tf32x3 tensor-core split, fp32 accumulate)", "bf16": "bf16"}[
+                   os.environ.get("PHC_PRECISION", "tf32x3")],
+               "data": "synthetic",
+               "config": config_dict(args, wl, wl.batch_graphs, "flushed between steps" if flush else "inputs larger than L2"),
+               "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof,
+               "op_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in breakdown.items()},
+               "final_loss": float(loss.item())}
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(wl)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

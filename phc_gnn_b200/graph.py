@@ -47,9 +47,10 @@ class EdgeStructure(object):
         self.status = buf[o:o + 1]
         ws_bytes = lib.phc_csr_workspace_bytes(N, E)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        _lib.check(lib.phc_csr_build(ei.data_ptr(), E, N, self.rowptr.data_ptr(), self.col.data_ptr(), self.perm.data_ptr(),
-                                     self.rowptr_t.data_ptr(), self.col_t.data_ptr(), self.perm_t.data_ptr(), ws.data_ptr(),
-                                     ws_bytes, self.status.data_ptr(), _stream(dev)), "phc_csr_build")
+        from .ops import run
+        run("phc_csr_build", dev, ei.data_ptr(), E, N, self.rowptr.data_ptr(), self.col.data_ptr(), self.perm.data_ptr(),
+            self.rowptr_t.data_ptr(), self.col_t.data_ptr(), self.perm_t.data_ptr(), ws.data_ptr(), ws_bytes,
+            self.status.data_ptr(), _stream(dev))
         self.num_nodes, self.num_edges = N, E
 
     def validate(self):
@@ -74,8 +75,9 @@ class SegmentStructure(object):
         buf = torch.empty(num_graphs + 2, dtype=torch.int32, device=dev)
         self.graph_ptr = buf[:num_graphs + 1]
         self.status = buf[num_graphs + 1:]
-        _lib.check(lib.phc_segment_ptr_build(b.data_ptr(), b.numel(), num_graphs, self.graph_ptr.data_ptr(),
-                                             self.status.data_ptr(), _stream(dev)), "phc_segment_ptr_build")
+        from .ops import run
+        run("phc_segment_ptr_build", dev, b.data_ptr(), b.numel(), num_graphs, self.graph_ptr.data_ptr(),
+            self.status.data_ptr(), _stream(dev))
         self.num_nodes, self.num_graphs = b.numel(), int(num_graphs)
 
     def validate(self):

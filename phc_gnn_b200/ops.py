@@ -20,6 +20,49 @@ REDUCE_IDS = {"add": 0, "sum": 0, "mean": 1, "max": 2, "min": 3, "softmax": 4}
 PRECISION_IDS = {"fp32": 0, "tf32x3": 1, "bf16": 2}
 
 
+class _Profile(object):
+    """Launch counter + optional per-op CUDA-event timing (used by bench.py for the roofline line)."""
+
+    def __init__(self):
+        self.launches = 0
+        self.timing = False
+        self.events = {}
+
+    def reset(self, timing: bool = False):
+        self.launches = 0
+        self.timing = timing
+        self.events = {}
+
+    def summary(self):
+        """{op: (calls, total_ms)} — synchronises."""
+        torch.cuda.synchronize()
+        return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in self.events.items()}
+
+
+PROFILE = _Profile()
+
+# kernels launched per C-ABI call (memsets included), for the gpu_launches claim
+_KERNELS = {"phc_csr_build": 6, "phc_segment_ptr_build": 2, "phc_aggregate_fwd": 1, "phc_aggregate_bwd": 2,
+            "phc_segment_pool_fwd": 1, "phc_segment_pool_bwd": 1, "phc_bn_act_drop_skip_fwd": 3, "phc_bn_act_drop_skip_bwd": 3,
+            "phc_embed_sum_fwd": 1, "phc_embed_sum_bwd": 2, "phc_linear_encoder_fwd": 1, "phc_linear_encoder_bwd": 2,
+            "phc_phm_linear_fwd": 1, "phc_phm_linear_bwd": 6}
+
+
+def run(name: str, device, *args, tag: str = ""):
+    """Invoke C-ABI entry ``name`` on torch's current stream; raises on a non-zero status."""
+    fn = getattr(_lib.load(), name)
+    PROFILE.launches += _KERNELS.get(name, 1)
+    if PROFILE.timing:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = fn(*args)
+        b.record()
+        PROFILE.events.setdefault(name + tag, []).append((a, b))
+    else:
+        rc = fn(*args)
+    _lib.check(rc, name)
+
+
 def default_precision() -> int:
     """PHMLinear arithmetic: env PHC_PRECISION in {fp32, tf32x3, bf16}; default tf32x3 (fp32-class
     accuracy on the tensor cores).  Falls back to the FFMA path inside the library only for shapes
@@ -70,9 +113,8 @@ class _PHMLinear(torch.autograd.Function):
         y = torch.empty((M, fout), dtype=torch.float32, device=x.device)
         nb = lib.phc_phm_linear_fwd_workspace_bytes(M, fin, fout, n, precision)
         ws = _ws(nb, x.device)
-        _lib.check(lib.phc_phm_linear_fwd(x.data_ptr(), rule.data_ptr(), W.data_ptr(), _ptr(bias), _ptr(residual), y.data_ptr(), M,
-                                          fin, fout, n, 0, precision, ws.data_ptr(), ws.numel(), _stream(x.device)),
-                   "phc_phm_linear_fwd")
+        run("phc_phm_linear_fwd", None, x.data_ptr(), rule.data_ptr(), W.data_ptr(), _ptr(bias), _ptr(residual), y.data_ptr(), M,
+                                          fin, fout, n, 0, precision, ws.data_ptr(), ws.numel(), _stream(x.device))
         ctx.save_for_backward(x, rule, W)
         ctx.meta = (bias is not None, residual is not None, precision)
         return y
@@ -92,9 +134,9 @@ class _PHMLinear(torch.autograd.Function):
         db = torch.empty(fout, dtype=torch.float32, device=x.device) if (has_bias and need[3]) else None
         nb = lib.phc_phm_linear_bwd_workspace_bytes(M, fin, fout, n, precision)
         ws = _ws(nb, x.device)
-        _lib.check(lib.phc_phm_linear_bwd(gy.data_ptr(), x.data_ptr(), rule.data_ptr(), W.data_ptr(), _ptr(dx), _ptr(d_rule),
+        run("phc_phm_linear_bwd", None, gy.data_ptr(), x.data_ptr(), rule.data_ptr(), W.data_ptr(), _ptr(dx), _ptr(d_rule),
                                           dW.data_ptr(), _ptr(db), M, fin, fout, n, precision, ws.data_ptr(), ws.numel(),
-                                          _stream(x.device)), "phc_phm_linear_bwd")
+                                          _stream(x.device))
         return dx, d_rule, (dW if need[2] else None), db, (gy if (has_res and need[4]) else None), None
 
 
@@ -118,10 +160,9 @@ class _Aggregate(torch.autograd.Function):
         aux_i = torch.empty((N, F), dtype=torch.int32, device=x.device) if reduce in (2, 3) else None
         if reduce == 4:
             beta = _f32c(beta, "beta")
-        _lib.check(lib.phc_aggregate_fwd(x.data_ptr(), ea.data_ptr(), struct.rowptr.data_ptr(), struct.col.data_ptr(),
+        run("phc_aggregate_fwd", None, x.data_ptr(), ea.data_ptr(), struct.rowptr.data_ptr(), struct.col.data_ptr(),
                                          struct.perm.data_ptr(), N, F, reduce, msg_act, _ptr(beta if reduce == 4 else None),
-                                         int(self_loop), out.data_ptr(), _ptr(aux_f), _ptr(aux_i), _stream(x.device)),
-                   "phc_aggregate_fwd")
+                                         int(self_loop), out.data_ptr(), _ptr(aux_f), _ptr(aux_i), _stream(x.device))
         ctx.save_for_backward(x, ea, beta if reduce == 4 else None, aux_f, aux_i)
         ctx.struct = struct
         ctx.meta = (reduce, msg_act, bool(self_loop))
@@ -140,11 +181,10 @@ class _Aggregate(torch.autograd.Function):
         dbeta = torch.zeros((), dtype=torch.float32, device=x.device) if reduce == 4 else None
         nb = lib.phc_aggregate_bwd_workspace_bytes(N, F)
         ws = _ws(nb, x.device)
-        _lib.check(lib.phc_aggregate_bwd(g.data_ptr(), x.data_ptr(), ea.data_ptr(), _ptr(aux_f), _ptr(aux_i), s.rowptr.data_ptr(),
+        run("phc_aggregate_bwd", None, g.data_ptr(), x.data_ptr(), ea.data_ptr(), _ptr(aux_f), _ptr(aux_i), s.rowptr.data_ptr(),
                                          s.col.data_ptr(), s.perm.data_ptr(), s.rowptr_t.data_ptr(), s.col_t.data_ptr(),
                                          s.perm_t.data_ptr(), N, F, reduce, msg_act, _ptr(beta), int(self_loop), dx.data_ptr(),
-                                         dea.data_ptr(), _ptr(dbeta), ws.data_ptr(), ws.numel(), _stream(x.device)),
-                   "phc_aggregate_bwd")
+                                         dea.data_ptr(), _ptr(dbeta), ws.data_ptr(), ws.numel(), _stream(x.device))
         return dx, dea, dbeta, None, None, None, None
 
 
@@ -169,8 +209,8 @@ class _Pool(torch.autograd.Function):
             gate_logits = _f32c(gate_logits, "gate_logits")
             assert gate_logits.shape == (N, F // n)
         out = torch.empty((seg.num_graphs, F), dtype=torch.float32, device=x.device)
-        _lib.check(lib.phc_segment_pool_fwd(x.data_ptr(), _ptr(gate_logits), seg.graph_ptr.data_ptr(), seg.num_graphs, F, n,
-                                            out.data_ptr(), _stream(x.device)), "phc_segment_pool_fwd")
+        run("phc_segment_pool_fwd", None, x.data_ptr(), _ptr(gate_logits), seg.graph_ptr.data_ptr(), seg.num_graphs, F, n,
+                                            out.data_ptr(), _stream(x.device))
         ctx.save_for_backward(x, gate_logits, batch)
         ctx.n = n
         return out
@@ -183,8 +223,8 @@ class _Pool(torch.autograd.Function):
         N, F = x.shape
         dx = torch.empty_like(x)
         dz = torch.empty_like(z) if z is not None else None
-        _lib.check(lib.phc_segment_pool_bwd(g.data_ptr(), x.data_ptr(), _ptr(z), batch.data_ptr(), N, F, ctx.n, dx.data_ptr(),
-                                            _ptr(dz), _stream(x.device)), "phc_segment_pool_bwd")
+        run("phc_segment_pool_bwd", None, g.data_ptr(), x.data_ptr(), _ptr(z), batch.data_ptr(), N, F, ctx.n, dx.data_ptr(),
+                                            _ptr(dz), _stream(x.device))
         return dx, dz, None, None, None
 
 
@@ -219,12 +259,12 @@ class _BnActDropSkip(torch.autograd.Function):
         nb = lib.phc_bn_workspace_bytes(M, F) if (use_bn and training) else 16
         ws = _ws(nb, dev)
         upd = training and use_bn
-        _lib.check(lib.phc_bn_act_drop_skip_fwd(
+        run("phc_bn_act_drop_skip_fwd", None, 
             h.data_ptr(), _ptr(gamma), _ptr(beta), _ptr(rmean) if (upd or not training) else 0,
             _ptr(rvar) if (upd or not training) else 0, _ptr(tracked) if upd else 0,
             0 if tracked is None else tracked.numel(), _ptr(skip), M, F, n, int(use_bn), int(training), momentum, eps, act,
             float(p), int(same), seed, y.data_ptr(), _ptr(stats[0]) if use_bn else 0, _ptr(stats[1]) if use_bn else 0,
-            ws.data_ptr(), ws.numel(), _stream(dev)), "phc_bn_act_drop_skip_fwd")
+            ws.data_ptr(), ws.numel(), _stream(dev))
         ctx.save_for_backward(h, gamma, beta, stats)
         ctx.cfg = cfg
         ctx.nparams = len(params)
@@ -243,11 +283,10 @@ class _BnActDropSkip(torch.autograd.Function):
         dgb = torch.empty((2, F), dtype=torch.float32, device=dev) if use_bn else None
         nb = lib.phc_bn_workspace_bytes(M, F) if use_bn else 16
         ws = _ws(nb, dev)
-        _lib.check(lib.phc_bn_act_drop_skip_bwd(
+        run("phc_bn_act_drop_skip_bwd", None, 
             gy.data_ptr(), h.data_ptr(), _ptr(gamma), _ptr(beta), _ptr(stats[0]) if use_bn else 0,
             _ptr(stats[1]) if use_bn else 0, M, F, n, int(use_bn), int(training), act, float(p), int(same), seed, dh.data_ptr(),
-            _ptr(dgb[0]) if use_bn else 0, _ptr(dgb[1]) if use_bn else 0, ws.data_ptr(), ws.numel(), _stream(dev)),
-            "phc_bn_act_drop_skip_bwd")
+            _ptr(dgb[0]) if use_bn else 0, _ptr(dgb[1]) if use_bn else 0, ws.data_ptr(), ws.numel(), _stream(dev))
         grads: List[Optional[torch.Tensor]] = []
         if ctx.nparams:
             k = ctx.nparams // 2
@@ -285,8 +324,8 @@ class _EmbedSum(torch.autograd.Function):
             assert t.is_contiguous() and t.dtype == torch.float32
         out = torch.empty((R, n * fc), dtype=torch.float32, device=idx.device)
         vc = (ctypes.c_int * cols)(*vocab)
-        _lib.check(lib.phc_embed_sum_fwd(idx.data_ptr(), _ptr_array(tables), vc, R, cols, n, fc, out.data_ptr(),
-                                         _stream(idx.device)), "phc_embed_sum_fwd")
+        run("phc_embed_sum_fwd", None, idx.data_ptr(), _ptr_array(tables), vc, R, cols, n, fc, out.data_ptr(),
+                                         _stream(idx.device))
         ctx.save_for_backward(idx)
         ctx.meta = (n, cols, tuple(vocab), fc)
         return out
@@ -308,8 +347,8 @@ class _EmbedSum(torch.autograd.Function):
         nb = lib.phc_embed_bwd_workspace_bytes(R, vtot, n * fc)
         ws = _ws(nb, g.device)
         vc = (ctypes.c_int * cols)(*vocab)
-        _lib.check(lib.phc_embed_sum_bwd(g.data_ptr(), idx.data_ptr(), _ptr_array(grads), vc, R, cols, n, fc, ws.data_ptr(),
-                                         ws.numel(), _stream(g.device)), "phc_embed_sum_bwd")
+        run("phc_embed_sum_bwd", None, g.data_ptr(), idx.data_ptr(), _ptr_array(grads), vc, R, cols, n, fc, ws.data_ptr(),
+                                         ws.numel(), _stream(g.device))
         return (None, None, None, None) + tuple(grads)
 
 
@@ -333,8 +372,8 @@ class _LinearEncoder(torch.autograd.Function):
             require_cuda(t, "encoder parameter")
             assert t.is_contiguous() and t.dtype == torch.float32
         out = torch.empty((R, n * fc), dtype=torch.float32, device=feat.device)
-        _lib.check(lib.phc_linear_encoder_fwd(feat.data_ptr(), _ptr_array(weights), _ptr_array(biases), R, D, n, fc,
-                                              out.data_ptr(), _stream(feat.device)), "phc_linear_encoder_fwd")
+        run("phc_linear_encoder_fwd", None, feat.data_ptr(), _ptr_array(weights), _ptr_array(biases), R, D, n, fc,
+                                              out.data_ptr(), _stream(feat.device))
         ctx.save_for_backward(feat)
         ctx.meta = (n, fc, D)
         return out
@@ -351,8 +390,8 @@ class _LinearEncoder(torch.autograd.Function):
         dbs = [flat[n * fc * D + c * fc:n * fc * D + (c + 1) * fc] for c in range(n)]
         nb = lib.phc_linear_encoder_bwd_workspace_bytes(R, D, n * fc)
         ws = _ws(nb, g.device)
-        _lib.check(lib.phc_linear_encoder_bwd(g.data_ptr(), feat.data_ptr(), _ptr_array(dws), _ptr_array(dbs), R, D, n, fc,
-                                              ws.data_ptr(), ws.numel(), _stream(g.device)), "phc_linear_encoder_bwd")
+        run("phc_linear_encoder_bwd", None, g.data_ptr(), feat.data_ptr(), _ptr_array(dws), _ptr_array(dbs), R, D, n, fc,
+                                              ws.data_ptr(), ws.numel(), _stream(g.device))
         return (None, None) + tuple(dws) + tuple(dbs)
 
 

@@ -1,0 +1,88 @@
+"""Data-parallel training across the GPUs of one box: one process per GPU, full model replica per
+rank, graph mini-batches sharded by rank, ONE all-reduce per step over a flat fp32 gradient buffer
+(NCCL over NVLink 5 / NVSwitch; gloo on CPU for tests).
+
+The reference has no distributed path at all; the only hook is
+``get_model_blocks`` tolerating a ``.module`` wrapper (phc/quaternion/regularization.py:6-8), which
+this wrapper satisfies.  Message passing, CSR construction and pooling never cross ranks; BatchNorm
+uses per-rank batch statistics (DDP semantics).
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+
+class GradientBucket(object):
+    """Flat fp32 buffer that all gradients are packed into after backward; after ``reduce()`` every
+    ``param.grad`` is a view of the (averaged) flat buffer, so clipping and the optimizer step read
+    the reduced values without a copy back."""
+
+    def __init__(self, params: List[torch.nn.Parameter]):
+        self.params = [p for p in params if p.requires_grad]
+        self.numel = sum(p.numel() for p in self.params)
+        self.flat: Optional[torch.Tensor] = None
+        self.views: List[torch.Tensor] = []
+
+    def _ensure(self, device):
+        if self.flat is None or self.flat.device != device:
+            self.flat = torch.zeros(self.numel, dtype=torch.float32, device=device)
+            self.views, off = [], 0
+            for p in self.params:
+                self.views.append(self.flat[off:off + p.numel()].view(p.shape))
+                off += p.numel()
+
+    def pack(self):
+        dev = self.params[0].device
+        self._ensure(dev)
+        src, dst = [], []
+        for p, v in zip(self.params, self.views):
+            if p.grad is None:
+                v.zero_()
+            elif p.grad.data_ptr() != v.data_ptr():
+                src.append(p.grad)
+                dst.append(v)
+        if src:
+            torch._foreach_copy_(dst, src)
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+        return self.flat
+
+    def reduce(self, group=None, async_op: bool = False):
+        flat = self.pack()
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if world == 1:
+            return None
+        flat.div_(world)
+        return dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+
+class DataParallelPHC(nn.Module):
+    """Thin replica wrapper: broadcasts rank 0's parameters/buffers at construction and exposes
+    ``reduce_gradients()`` to be called between ``backward()`` and ``clip_grad_norm_`` / ``step()``
+    (the order of benchmarks/train_hiv.py:198-201 on the reduced gradients)."""
+
+    def __init__(self, module: nn.Module, group=None):
+        super().__init__()
+        self.module = module
+        self.group = group
+        self.bucket = GradientBucket(list(module.parameters()))
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            with torch.no_grad():
+                for t in list(module.parameters()) + list(module.buffers()):
+                    dist.broadcast(t.data, src=0, group=group)
+
+    def forward(self, *args, **kwargs):
+        return self.module(*args, **kwargs)
+
+    def reduce_gradients(self, async_op: bool = False):
+        return self.bucket.reduce(self.group, async_op)
+
+    def __getattr__(self, name):
+        try:
+            return super().__getattr__(name)
+        except AttributeError:
+            return getattr(super().__getattr__("module"), name)

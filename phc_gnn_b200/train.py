@@ -1,0 +1,66 @@
+"""The timed unit: one iteration of the reference's ``train()`` body
+(benchmarks/train_hiv.py:170-202 and the zinc / pcba / ppa / mnist variants):
+
+    zero_grad -> model(data) -> task loss + lr*wd*phm_weight_regularization -> backward
+    -> (data-parallel: all-reduce gradients) -> clip_grad_norm_(2.0) -> Adam step
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+from .nn import get_model_blocks, phm_weight_regularization
+from .synthetic import Workload
+
+BLOCKS = ("convs", "pooling", "downstream", "norms", "atomencoder", "bondencoders")
+
+
+def task_loss(logits: torch.Tensor, y: torch.Tensor, kind: str) -> torch.Tensor:
+    if kind in ("bce", "bce_masked"):
+        # mean BCE over the labelled entries (train_hiv.py:174,178); written without boolean-mask
+        # indexing so that no host sync is needed — same value as logits[mask] / y[mask]
+        mask = ~torch.isnan(y)
+        per = F.binary_cross_entropy_with_logits(logits, torch.where(mask, y, torch.zeros_like(y)).to(torch.float), reduction="none")
+        return (per * mask).sum() / mask.sum()
+    if kind == "l1":
+        return (logits.squeeze() - y).abs().mean()              # train_zinc.py:192
+    if kind == "ce":
+        return F.cross_entropy(logits, y.view(-1))              # train_ppa.py / train_mnist.py:200
+    raise ValueError(kind)
+
+
+def make_optimizer(model, lr: float):
+    """Adam over the six parameter blocks, weight_decay=0, as do_run() builds it (train_hiv.py:266-285)."""
+    groups = []
+    for b in BLOCKS:
+        groups += get_model_blocks(model, b, lr=lr, weight_decay=0.0)
+    n_groups = sum(p.numel() for g in groups for p in g["params"])
+    n_model = sum(p.numel() for p in model.parameters())
+    assert n_groups == n_model, "parameter blocks do not cover the model"        # train_hiv.py:279-282
+    return torch.optim.Adam(groups)
+
+
+class TrainStep(object):
+    def __init__(self, model, workload: Workload, optimizer=None, dp=None):
+        self.model = model
+        self.wl = workload
+        self.opt = optimizer if optimizer is not None else make_optimizer(model, workload.lr)
+        self.dp = dp                      # DataParallelPHC wrapper or None
+        self.params = [p for p in model.parameters()]
+
+    def __call__(self, data) -> torch.Tensor:
+        wl = self.wl
+        self.opt.zero_grad()
+        logits = self.model(data)
+        loss = task_loss(logits, data.y, wl.loss)
+        if wl.weight_decay > 0.0:
+            loss = loss + wl.lr * wl.weight_decay * phm_weight_regularization(self.model, p=2)
+        loss.backward()
+        if self.dp is not None:
+            self.dp.reduce_gradients()
+        if wl.grad_clip > 0.0:
+            torch.nn.utils.clip_grad_norm_(self.params, max_norm=wl.grad_clip, norm_type=2)
+        self.opt.step()
+        return loss.detach()

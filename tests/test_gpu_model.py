@@ -11,15 +11,23 @@ RTOL = 1e-4      # north_star fp32 tolerance
 DEV = "cuda:0"
 
 
-def _compare(got, want, rtol, what):
-    scale = max(float(want["logits"].abs().max()), 1e-3)
-    assert_close(got["logits"], want["logits"], rtol, rtol * scale, f"{what}: train logits")
+def _compare(got, want, rtol, what, noise=None):
+    """``noise`` (optional) = the same quantities from the oracle run in fp32: its distance to the fp64
+    oracle measures how ill-conditioned a value is (e.g. gradients that are exactly zero in exact
+    arithmetic); the CUDA path is allowed 5x that on top of rtol."""
+    def tol(key, ref, sub=None):
+        floor = 0.0
+        if noise is not None:
+            a = noise[key] if sub is None else noise[key][sub]
+            floor = 5.0 * float((a.float() - ref.float()).abs().max())
+        return max(rtol * float(ref.abs().max()), floor, 2e-6)
+    assert_close(got["logits"], want["logits"], rtol, tol("logits", want["logits"]), f"{what}: train logits")
     assert_close(got["reg"], want["reg"], rtol, 1e-6, f"{what}: regulariser")
-    assert_close(got["loss"], want["loss"], rtol, 1e-6, f"{what}: loss")
-    assert_close(got["logits_eval"], want["logits_eval"], rtol, rtol * scale, f"{what}: eval logits")
+    assert_close(got["loss"], want["loss"], rtol, tol("loss", want["loss"]), f"{what}: loss")
+    assert_close(got["logits_eval"], want["logits_eval"], rtol, tol("logits_eval", want["logits_eval"]), f"{what}: eval logits")
     for k, g in want["grads"].items():
         assert k in got["grads"], f"{what}: no gradient for {k}"
-        assert_close(got["grads"][k], g, 5 * rtol, grad_tol(g, 5 * rtol), f"{what}: grad {k}")
+        assert_close(got["grads"][k], g, 5 * rtol, 5 * tol("grads", g, k), f"{what}: grad {k}")
     for k, v in want["running"].items():
         assert_close(got["running"][k].float(), v.float(), rtol, 1e-5, f"{what}: {k}")
 
@@ -54,7 +62,8 @@ def test_model_matches_oracle_on_workload_shapes(wl_name, graphs, n, monkeypatch
     batch = make_batch(wl, seed=7, batch_graphs=graphs)
     got = product_train_eval(cfg, state, batch, wl.loss, 0.01, DEV)
     want = oracle_train_eval(cfg, state, batch, wl.loss, 0.01, torch.float64)
-    _compare(got, want, 2e-4, wl_name)
+    noise = oracle_train_eval(cfg, state, batch, wl.loss, 0.01, torch.float32)
+    _compare(got, want, RTOL, wl_name, noise)
 
 
 def test_training_step_is_bitwise_reproducible(monkeypatch):

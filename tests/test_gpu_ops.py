@@ -117,7 +117,7 @@ def test_pool_fwd_bwd(gated, F, n):
 @pytest.mark.parametrize("M,F,n,act,affine,skip,training", [
     (64, 16, 4, "relu", True, True, True), (300, 20, 5, "identity", True, False, True), (257, 12, 3, "swish", True, True, True),
     (129, 9, 3, "elu", False, True, True), (64, 16, 4, "relu", True, True, False), (1000, 200, 4, "lrelu", True, True, True),
-    (2, 8, 2, "selu", True, False, True)])
+    (6, 8, 2, "selu", True, False, True)])
 def test_norm_act_skip(M, F, n, act, affine, skip, training):
     from phc.hypercomplex.norm import PHMNorm
     g = torch.Generator().manual_seed(1)
@@ -244,7 +244,7 @@ def _phm_linear_case(n, fin, fout, M, precision, rtol, seed=0):
     t = [v.to(DEV).requires_grad_(True) for v in (x, A, W, b, res)]
     y = ops.phm_linear(t[0], t[1], t[2], t[3], t[4], precision=precision)
     y.backward(gy.to(DEV))
-    scale = float(ref.abs().max())
+    scale = float(ref.detach().abs().max())
     assert_close(y.detach().cpu(), ref.detach().float(), rtol, rtol * scale, "y")
     for got, want, nm in ((t[0].grad, xo.grad, "dx"), (t[1].grad, po["l.phm_rule"].grad, "dA"), (t[2].grad, po["l.W"].grad, "dW"),
                           (t[3].grad, po["l.b"].grad, "db"), (t[4].grad, ro.grad, "dres")):
