@@ -236,19 +236,39 @@ int dh_splits(int M, int In, int Out) {
   return s < 1 ? 1 : (s > 64 ? 64 : s);
 }
 int colsum_chunks(int M) {
-  int c = phc_div_up(M, 128);
-  return c < 1 ? 1 : (c > 128 ? 128 : c);
+  int c = phc_div_up(M, 32);
+  return c < 1 ? 1 : (c > 1024 ? 1024 : c);
 }
 
 }  // namespace
 
-// shared with phm_linear_tc.cu
-size_t phm_simt_bwd_workspace_bytes(int rows, int in_features, int out_features, int phm_dim) {
+// ---- shared with phm_linear_tc.cu: fold dH partials into dW / dA, and the bias gradient ----------
+size_t phm_contract_scratch_floats(int rows, int in_features, int out_features, int phm_dim) {
   const int n = phm_dim, K = in_features / n, P = out_features / n;
+  return (size_t)phc_div_up((long long)K * P, 256) * n * n * n + (size_t)colsum_chunks(rows) * out_features + 16;
+}
+
+int phm_contract_and_bias(const float* part, int splits, const float* gy, const float* A, const float* W, float* dA, float* dW, float* db,
+                          int rows, int in_features, int out_features, int phm_dim, float* scratch, cudaStream_t stream) {
+  const int n = phm_dim, K = in_features / n, P = out_features / n, M = rows, n3 = n * n * n;
+  const int cblocks = phc_div_up((long long)K * P, 256);
+  float* da_part = scratch;
+  float* cs_part = scratch + (size_t)cblocks * n3;
+  phm_contract_kernel<<<cblocks, 256, sizeof(float) * (n3 + 8), stream>>>(part, splits, A, W, n, K, P, dW, da_part);
+  if (dA) phm_dA_final_kernel<<<phc_div_up(n3, 256), 256, 0, stream>>>(da_part, cblocks, n3, dA);
+  if (db) {
+    const int chunks = colsum_chunks(M);
+    const int rpc = phc_div_up(M > 0 ? M : 1, chunks);
+    dim3 g3(phc_div_up(out_features, 256), chunks);
+    colsum_partial_kernel<<<g3, 256, 0, stream>>>(gy, M, out_features, rpc, cs_part);
+    colsum_final_kernel<<<phc_div_up(out_features, 256), 256, 0, stream>>>(cs_part, chunks, out_features, db);
+  }
+  return phc_check_launch("phm_contract_and_bias");
+}
+
+size_t phm_simt_bwd_workspace_bytes(int rows, int in_features, int out_features, int phm_dim) {
   size_t dh = (size_t)dh_splits(rows, in_features, out_features) * in_features * out_features;
-  size_t da = (size_t)phc_div_up((long long)K * P, 256) * n * n * n;
-  size_t cs = (size_t)colsum_chunks(rows) * out_features;
-  return sizeof(float) * (dh + da + cs) + 64;
+  return sizeof(float) * (dh + phm_contract_scratch_floats(rows, in_features, out_features, phm_dim)) + 64;
 }
 
 int phm_simt_fwd(const float* x, const float* A, const float* W, const float* bias, const float* residual, float* y, int rows,
@@ -272,19 +292,8 @@ int phm_simt_bwd(const float* gy, const float* x, const float* A, const float* W
   const int splits = dh_splits(M, in_features, out_features);
   const int rps = phc_div_up(phc_div_up(M > 0 ? M : 1, splits), 16) * 16;
   float* part = reinterpret_cast<float*>(workspace);
-  float* da_part = part + (size_t)splits * in_features * out_features;
-  const int cblocks = phc_div_up((long long)K * P, 256);
-  float* cs_part = da_part + (size_t)cblocks * n3;
   dim3 g2(phc_div_up(out_features, 64), phc_div_up(in_features, 64), splits);
   phm_dh_kernel<<<g2, 256, 0, stream>>>(x, gy, M, in_features, out_features, rps, part);
-  phm_contract_kernel<<<cblocks, 256, sizeof(float) * (n3 + 8), stream>>>(part, splits, A, W, n, K, P, dW, da_part);
-  if (dA) phm_dA_final_kernel<<<phc_div_up(n3, 256), 256, 0, stream>>>(da_part, cblocks, n3, dA);
-  if (db) {
-    const int chunks = colsum_chunks(M);
-    const int rpc = phc_div_up(M > 0 ? M : 1, chunks);
-    dim3 g3(phc_div_up(out_features, 256), chunks);
-    colsum_partial_kernel<<<g3, 256, 0, stream>>>(gy, M, out_features, rpc, cs_part);
-    colsum_final_kernel<<<phc_div_up(out_features, 256), 256, 0, stream>>>(cs_part, chunks, out_features, db);
-  }
-  return phc_check_launch("phc_phm_linear_bwd(simt)");
+  return phm_contract_and_bias(part, splits, gy, A, W, dA, dW, db, M, in_features, out_features, n,
+                               part + (size_t)splits * in_features * out_features, stream);
 }

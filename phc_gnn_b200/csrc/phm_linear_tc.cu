@@ -1,17 +1,821 @@
-// PHMLinear tensor-core path (tcgen05 / TMEM / TMA) — placeholder until the kernel lands:
-// reports "unsupported" so the dispatch in api.cu uses the fp32 FFMA path.
+// PHMLinear on the 5th-generation tensor cores: tcgen05.mma (kind::tf32), TMEM accumulators, TMA-fed weights.
+//
+//   y[m,(c,p)] = sum_{a,k} x[m,(a,k)] * H[(a,k),(c,p)] + b,     H[(a,k),(c,p)] = sum_b A[b,a,c] W[b,k,p]
+//
+// Replaces reference phc/hypercomplex/layers.py:198-219 (einsum Kronecker stack + sum + cuBLAS SGEMM
+// + bias kernel, fp32) and its autograd backward.  The Kronecker weight H is NEVER formed — not in HBM
+// and not in shared memory.  The contraction is re-associated so that the learned rule A mixes the
+// ACTIVATIONS inside the operand producer and the tensor cores multiply by the small W blocks directly:
+//
+//   y_c[m,p] = sum_{(k,b)}  Xmix_c[m,(k,b)] * W[b,k,p],      Xmix_c[m,(k,b)] = sum_a A[b,a,c] x[m,(a,k)]
+//
+// i.e. per output component c one GEMM  [M, n*K] x [n*K, P]  whose B operand is W itself (identical for
+// every c and every row tile).  Same FLOPs as the dense product (2*M*in*out), n-times less weight traffic.
+// The input gradient is the mirror image:  dx_a[m,k] = sum_{(p,b)} Gmix_a[m,(p,b)] W[b,k,p],
+// Gmix_a[m,(p,b)] = sum_c A[b,a,c] dy[m,(c,p)].
+//
+// Precision "tf32x3": every fp32 operand v is split into big = rna_tf32(v), small = rna_tf32(v - big) and
+// the tensor cores accumulate  A_small*B_big + A_big*B_small + A_big*B_big  in fp32 (TMEM): fp32-class
+// accuracy (error ~2^-21 per product, what the reference's fp32 SGEMM gives) at tensor-core speed.
+//
+// Kernel anatomy (persistent, warp-specialised, one CTA per SM, 672 threads):
+//   warps 16-19 epilogue : tcgen05.ld TMEM -> registers -> smem transpose -> coalesced stores (+bias, act, residual)
+//   warp  20    MMA      : TMEM alloc/dealloc; one elected lane issues tcgen05.mma / tcgen05.commit
+//   warps 0-15  producers: build the A operand (rule-mixed activations, split to tf32 big/small) straight into the
+//                          UMMA canonical layout (K-major, 128-byte swizzle); global loads for chunk i+1 are issued
+//                          before chunk i is processed (register prefetch).  Producer thread 0 also issues the TMA
+//                          bulk copy (cp.async.bulk -> mbarrier complete_tx) that brings the pre-split, pre-swizzled
+//                          W chunk (32 KiB) into the stage.
+//   pipeline: 3-stage smem ring (full/empty mbarriers) + 2 TMEM accumulator buffers (tmem_full/tmem_empty), so the
+//             epilogue of tile i overlaps the MMAs of tile i+1.
+// A small pack kernel per call writes W in both operand orders as tf32 big/small tile images (n*K*P elements,
+// L2-resident) together with the rule re-indexed per output component.
+//
+// Weight gradients:  dH = X^T dY  with the same pipeline (both operands transposed 4x4 in registers, reduction over
+// rows split across CTAs, partial tiles reduced in a fixed order), then
+//   dW[b,k,p] = sum_{a,c} A[b,a,c] dH[(a,k),(c,p)],   dA[b,a,c] = sum_{k,p} W[b,k,p] dH[(a,k),(c,p)].
 #include "common.cuh"
 
-int phm_tc_supported(int, int, int, int, int) { return 0; }
-size_t phm_tc_fwd_workspace_bytes(int, int, int, int, int) { return 16; }
-size_t phm_tc_bwd_workspace_bytes(int, int, int, int, int) { return 16; }
-int phm_tc_fwd(const float*, const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, void*,
-               cudaStream_t) {
-  phc_set_error("phm_tc_fwd: not built");
-  return PHC_ERR_UNSUPPORTED;
+// helpers implemented in phm_linear_simt.cu (fixed-order reductions shared by both paths)
+int phm_contract_and_bias(const float* part, int splits, const float* gy, const float* A, const float* W, float* dA, float* dW, float* db,
+                          int rows, int in_features, int out_features, int phm_dim, float* scratch, cudaStream_t stream);
+size_t phm_contract_scratch_floats(int rows, int in_features, int out_features, int phm_dim);
+
+long long* g_phm_tc_prof = nullptr;   // set via phc_debug_set_tc_profile (debug only)
+
+namespace tc {
+
+constexpr int BM = 128, BN = 128, BK = 32;          // BK fp32 elements = one 128-byte swizzle row
+constexpr int STAGES = 3;
+constexpr int EPI_WARPS = 4, PROD_WARPS = 16;
+// Warp order matters: the SM's issue arbiter favours the highest warp id, so the latency-critical roles
+// (MMA issuer, then epilogue) get the top ids and the throughput-bound producers the low ones.  The epilogue
+// warps must start at a multiple of 4 (a warp may only touch TMEM lanes 32*(warp_id % 4) .. +31).
+constexpr int PROD_WARP0 = 0;                        // warps 0..15
+constexpr int EPI_WARP0 = PROD_WARPS;                // warps 16..19
+constexpr int MMA_WARP = PROD_WARPS + EPI_WARPS;     // warp 20
+static_assert(EPI_WARP0 % 4 == 0, "epilogue warps must be aligned to the TMEM lane quarters");
+constexpr int THREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32;
+constexpr int PROD_THREADS = PROD_WARPS * 32;
+constexpr int TILE_BYTES = BM * BK * 4;              // 16 KiB (A and B tiles have the same size, BM == BN)
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;          // A_big, A_small, B_big, B_small
+constexpr int TMEM_COLS = 2 * BN;                    // two accumulator buffers
+constexpr int EPI_SCRATCH = EPI_WARPS * 32 * 33 * 4; // per-warp 32x33 transpose tiles
+constexpr int UNITS = (BM * 8) / PROD_THREADS;       // 16-byte K-units per producer thread per chunk (4)
+
+struct MixParams {          // y = act(mix GEMM + bias) + residual   (FWD and DX)
+  const float* X;           // [M, n*Kin]
+  const float* coef;        // [n_out_comp t][b][u]  rule re-indexed for this direction
+  const uint8_t* Bpack;     // [ptiles][chunks][big|small][128 x 128 B swizzled]
+  const float* bias;
+  const float* residual;
+  float* C;                 // [M, n*Pout]
+  int M, n, Kin, Pout, S, chunks, ptiles, act, num_tiles;
+  long long* prof;          // optional per-CTA role timers (debug), 8 slots per CTA
+};
+
+struct DhParams {           // partial dH tiles
+  const float* X;           // [M, In]
+  const float* G;           // [M, Out]
+  float* C;                 // [splits, In, Out]
+  int M, In, Out, tiles_m, tiles_n, splits, rows_per_split, num_tiles;
+};
+
+__device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-int phm_tc_bwd(const float*, const float*, const float*, const float*, float*, float*, float*, float*, int, int, int, int, int, void*,
-               cudaStream_t) {
-  phc_set_error("phm_tc_bwd: not built");
-  return PHC_ERR_UNSUPPORTED;
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must trap (error code to the host), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, both K-major, N=BN, M=BM.
+constexpr uint32_t IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void split_tf32(float v, float& big, float& small) {
+  uint32_t b, s;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(v));
+  big = __uint_as_float(b);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(s) : "f"(v - big));
+  small = __uint_as_float(s);
+}
+__device__ __forceinline__ int swz(int row, int ku) { return row * 128 + ((ku ^ (row & 7)) << 4); }
+
+// write one 16-byte K-unit (4 consecutive k of one row) of an operand tile, big and small copies
+__device__ __forceinline__ void store_unit(uint8_t* tile_big, uint8_t* tile_small, int row, int ku, const float (&v)[4]) {
+  float b[4], s[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) split_tf32(v[j], b[j], s[j]);
+  const int off = swz(row, ku);
+  *reinterpret_cast<float4*>(tile_big + off) = make_float4(b[0], b[1], b[2], b[3]);
+  *reinterpret_cast<float4*>(tile_small + off) = make_float4(s[0], s[1], s[2], s[3]);
+}
+
+// ---------------------------------------------------------------------------- shared CTA scaffolding
+struct Smem {
+  uint8_t* stages;
+  float* scratch;
+  float* coef;
+  uint64_t *full_bar, *empty_bar, *tfull_bar, *tempty_bar;
+  uint32_t* tmem_slot;
+};
+
+__device__ __forceinline__ Smem carve(uint8_t* raw, int coef_floats) {
+  Smem s;
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
+  s.stages = base;
+  s.scratch = reinterpret_cast<float*>(base + STAGES * STAGE_BYTES);
+  s.coef = s.scratch + EPI_WARPS * 32 * 33;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s.coef + ((coef_floats + 3) & ~3));
+  s.full_bar = bars;
+  s.empty_bar = bars + STAGES;
+  s.tfull_bar = bars + 2 * STAGES;
+  s.tempty_bar = bars + 2 * STAGES + 2;
+  s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  return s;
+}
+
+__device__ __forceinline__ uint32_t cta_prologue(const Smem& s, int full_count) {
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(smem_u32(&s.full_bar[i]), full_count);
+      mbar_init(smem_u32(&s.empty_bar[i]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&s.tfull_bar[b]), 1);
+      mbar_init(smem_u32(&s.tempty_bar[b]), EPI_WARPS * 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == MMA_WARP) tmem_alloc(smem_u32(s.tmem_slot), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  return *s.tmem_slot;
+}
+
+__device__ __forceinline__ void cta_epilogue(uint32_t tmem_base) {
+  tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// MMA issuer for one tile: `chunks` pipeline stages, 4 K-steps x 3 split products each.
+__device__ __forceinline__ void mma_tile(const Smem& s, uint32_t tmem_base, int it, int chunks, int& stage, int& phase,
+                                         long long* prof = nullptr) {   // prof: thread-local accumulators
+  const int lane = threadIdx.x & 31;
+  const int buf = it & 1;
+  const uint32_t d_tmem = tmem_base + buf * BN;
+  long long t0 = prof ? clock64() : 0;
+  mbar_wait(smem_u32(&s.tempty_bar[buf]), ((it >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
+  if (prof && lane == 0) prof[2] += clock64() - t0;
+  tc_fence_after();
+  uint32_t accum = 0;
+  for (int c = 0; c < chunks; ++c) {
+    t0 = prof ? clock64() : 0;
+    mbar_wait(smem_u32(&s.full_bar[stage]), phase);
+    if (prof && lane == 0) prof[3] += clock64() - t0;
+    tc_fence_after();
+    if (lane == 0) {
+      const uint32_t sa = smem_u32(s.stages + stage * STAGE_BYTES);
+      const uint64_t a_big = make_desc(sa), a_small = make_desc(sa + TILE_BYTES);
+      const uint64_t b_big = make_desc(sa + 2 * TILE_BYTES), b_small = make_desc(sa + 3 * TILE_BYTES);
+#pragma unroll
+      for (int ks = 0; ks < BK / 8; ++ks) {
+        const uint64_t adv = (uint64_t)((ks * 32) >> 4);            // 8 tf32 = 32 bytes inside the swizzle row
+        umma_tf32(d_tmem, a_small + adv, b_big + adv, IDESC_TF32, accum);
+        umma_tf32(d_tmem, a_big + adv, b_small + adv, IDESC_TF32, 1u);
+        umma_tf32(d_tmem, a_big + adv, b_big + adv, IDESC_TF32, 1u);
+        accum = 1u;
+      }
+      umma_commit(smem_u32(&s.empty_bar[stage]));                    // smem slot reusable when these MMAs retire
+    }
+    __syncwarp();
+    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+  }
+  if (lane == 0) umma_commit(smem_u32(&s.tfull_bar[buf]));          // accumulator complete -> epilogue
+  __syncwarp();
+}
+
+// Epilogue for one 128 x 128 tile: rows [row0,row0+128) x cols [col0, col0+ncols) of a row-major matrix with
+// leading dimension ldc; `col_limit` bounds valid columns of the tile (component / matrix edge).
+template <bool FUSE>
+__device__ __forceinline__ void epilogue_tile(const Smem& s, uint32_t tmem_base, int it, float* __restrict__ C, int ldc, int rows_c,
+                                              int row0, int col0, int ncols, const float* __restrict__ bias,
+                                              const float* __restrict__ residual, int act, long long* prof = nullptr) {
+  const int warp = (threadIdx.x >> 5) - EPI_WARP0, lane = threadIdx.x & 31;     // == TMEM lane quarter
+  float* my = s.scratch + warp * 32 * 33;
+  const int buf = it & 1;
+  long long t0 = prof ? clock64() : 0;
+  mbar_wait(smem_u32(&s.tfull_bar[buf]), (it >> 1) & 1);
+  if (prof && threadIdx.x == EPI_WARP0 * 32) { prof[4] += clock64() - t0; t0 = clock64(); }
+  tc_fence_after();
+  const int r0 = row0 + warp * 32;
+  const bool plain = !FUSE || (act == PHC_ACT_IDENTITY);
+#pragma unroll 1
+  for (int cc = 0; cc < BN / 32; ++cc) {
+    if (cc * 32 >= ncols) break;
+    uint32_t v[32];
+    long long t1 = prof ? clock64() : 0;
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * BN + cc * 32), v);
+    if (prof && threadIdx.x == EPI_WARP0 * 32) prof[7] += clock64() - t1;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) my[lane * 33 + j] = __uint_as_float(v[j]);
+    __syncwarp();
+    const int lc = cc * 32 + lane;
+    const bool col_ok = lc < ncols;
+    const int col = col0 + lc;
+    float bv = 0.f;
+    if (FUSE && bias != nullptr && col_ok) bv = __ldg(bias + col);
+    const int nrows = min(32, rows_c - r0);
+    if (col_ok) {
+      float* dst = C + (size_t)r0 * ldc + col;
+      if (plain && (!FUSE || residual == nullptr)) {
+#pragma unroll 8
+        for (int rr = 0; rr < 32; ++rr)
+          if (rr < nrows) dst[(size_t)rr * ldc] = my[rr * 33 + lane] + bv;
+      } else {
+        const float* res = (FUSE && residual != nullptr) ? residual + (size_t)r0 * ldc + col : nullptr;
+#pragma unroll 4
+        for (int rr = 0; rr < 32; ++rr) {
+          if (rr < nrows) {
+            float o = my[rr * 33 + lane] + bv;
+            if (!plain) o = act_fwd_rt(act, o);
+            if (res != nullptr) o += res[(size_t)rr * ldc];
+            dst[(size_t)rr * ldc] = o;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  mbar_arrive(smem_u32(&s.tempty_bar[buf]));
+  if (prof && threadIdx.x == EPI_WARP0 * 32) prof[5] += clock64() - t0;
+}
+
+// ---------------------------------------------------------------------------- mix kernel (FWD / DX)
+// NT = phm_dim at compile time (1, 2, 4 fast paths with register prefetch) or 0 = any n (direct loads).
+template <int NT> struct MixLoad { float v[NT == 0 ? 1 : 4 * UNITS]; };
+
+// tile t -> (m-tile, output component, p-tile); the component varies fastest so that concurrently running CTAs
+// share the same activation rows in L2.
+__device__ __forceinline__ void mix_tile(const MixParams& p, int t, int& m0, int& comp, int& pt) {
+  const int per_m = p.n * p.ptiles;
+  m0 = (t / per_m) * BM;
+  const int r = t % per_m;
+  comp = r % p.n;
+  pt = r / p.n;
+}
+
+template <int NT>
+__device__ __forceinline__ void mix_issue_loads(const MixParams& p, int m0, int chunk, int ptid, MixLoad<NT>& L) {
+  if (NT == 0) return;
+  const int ld = p.n * p.Kin;
+#pragma unroll
+  for (int i = 0; i < UNITS; ++i) {
+    const int u = i * PROD_THREADS + ptid;
+    const int row = u >> 3, ku = u & 7;
+    const int gm = m0 + row;
+    const int s0 = chunk * BK + ku * 4;
+    const float* src = p.X + (size_t)gm * ld;
+    const bool ok = gm < p.M;
+    if (NT == 4) {                    // unit = one k, b = 0..3 : needs x[row, u*Kin + k] for u = 0..3
+      const int k = s0 >> 2;
+      const bool okk = ok && k < p.Kin;
+#pragma unroll
+      for (int uu = 0; uu < 4; ++uu) L.v[i * 4 + uu] = okk ? __ldg(src + uu * p.Kin + k) : 0.f;
+    } else if (NT == 2) {             // unit = k, k+1 ; b = 0,1
+      const int k = s0 >> 1;
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+        for (int uu = 0; uu < 2; ++uu) L.v[i * 4 + kk * 2 + uu] = (ok && k + kk < p.Kin) ? __ldg(src + uu * p.Kin + k + kk) : 0.f;
+    } else {                          // NT == 1: unit = k..k+3
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) L.v[i * 4 + kk] = (ok && s0 + kk < p.Kin) ? __ldg(src + s0 + kk) : 0.f;
+    }
+  }
+}
+
+template <int NT>
+__device__ __forceinline__ void mix_produce(const MixParams& p, const float* __restrict__ cf, int m0, int chunk, int ptid,
+                                            const MixLoad<NT>& L, uint8_t* big, uint8_t* small) {
+  // cf = coef for this tile's output component: [b][u] (registers for the NT fast paths, smem otherwise)
+#pragma unroll
+  for (int i = 0; i < UNITS; ++i) {
+    const int u = i * PROD_THREADS + ptid;
+    const int row = u >> 3, ku = u & 7;
+    float v[4];
+    if (NT == 4) {
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        float h = 0.f;
+#pragma unroll
+        for (int uu = 0; uu < 4; ++uu) h += cf[b * 4 + uu] * L.v[i * 4 + uu];
+        v[b] = h;
+      }
+    } else if (NT == 2) {
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) v[kk * 2 + b] = cf[b * 2] * L.v[i * 4 + kk * 2] + cf[b * 2 + 1] * L.v[i * 4 + kk * 2 + 1];
+    } else if (NT == 1) {
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) v[kk] = cf[0] * L.v[i * 4 + kk];
+    } else {
+      const int n = p.n, ld = n * p.Kin;
+      const int gm = m0 + row;
+      const int s0 = chunk * BK + ku * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int sidx = s0 + j;
+        float h = 0.f;
+        if (gm < p.M && sidx < p.S) {
+          const int k = sidx / n, b = sidx - k * n;
+          const float* src = p.X + (size_t)gm * ld + k;
+          for (int uu = 0; uu < n; ++uu) h += cf[b * n + uu] * __ldg(src + uu * p.Kin);
+        }
+        v[j] = h;
+      }
+    }
+    store_unit(big, small, row, ku, v);
+  }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(THREADS, 1) phm_tc_mix_kernel(const MixParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const int n3 = p.n * p.n * p.n;
+  const Smem s = carve(smem_raw, n3);
+  for (int i = threadIdx.x; i < n3; i += THREADS) s.coef[i] = p.coef[i];
+  const uint32_t tmem_base = cta_prologue(s, PROD_WARPS + 1);
+  const int warp = threadIdx.x >> 5;
+  const long long tk0 = p.prof ? clock64() : 0;
+
+  if (warp < EPI_WARP0) {
+    // ===================================================================== producers
+    const int ptid = threadIdx.x - PROD_WARP0 * 32;
+    int stage = 0, phase = 0;
+    // Register ring of PF chunk loads: the global loads of chunk g+PF-1 are issued before chunk g is processed, so
+    // ~3 chunk times of L2/HBM latency are hidden (all producer warps work on the same chunk, nothing else hides it).
+    constexpr int PF = 4;
+    MixLoad<NT> ring[PF];
+    const int my_tiles = p.num_tiles > (int)blockIdx.x ? (p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int total = my_tiles * p.chunks;
+    auto locate = [&](int g, int& m0, int& comp, int& pt, int& c) {
+      const int ti = g / p.chunks;
+      c = g - ti * p.chunks;
+      mix_tile(p, blockIdx.x + ti * gridDim.x, m0, comp, pt);
+    };
+#pragma unroll
+    for (int j = 0; j < PF - 1; ++j) {
+      if (j < total) {
+        int m0, comp, pt, c;
+        locate(j, m0, comp, pt, c);
+        mix_issue_loads<NT>(p, m0, c, ptid, ring[j]);
+      }
+    }
+    float cfr[NT == 0 ? 1 : NT * NT];
+    int cur_comp = -1;
+    long long acc_wait = 0, acc_prod = 0;
+    for (int g0 = 0; g0 < total; g0 += PF) {
+#pragma unroll
+      for (int j = 0; j < PF; ++j) {
+        const int g = g0 + j;
+        if (g < total) {
+          if (g + PF - 1 < total) {
+            int m0n, compn, ptn, cn;
+            locate(g + PF - 1, m0n, compn, ptn, cn);
+            mix_issue_loads<NT>(p, m0n, cn, ptid, ring[(j + PF - 1) % PF]);
+          }
+          int m0, comp, pt, c;
+          locate(g, m0, comp, pt, c);
+          const float* cfs = s.coef + comp * p.n * p.n;
+          if (NT != 0 && comp != cur_comp) {
+#pragma unroll
+            for (int i = 0; i < NT * NT; ++i) cfr[i] = cfs[i];
+            cur_comp = comp;
+          }
+          const float* cf = NT != 0 ? cfr : cfs;
+          long long tw0 = 0;
+          if (p.prof && ptid == 0) tw0 = clock64();
+          mbar_wait(smem_u32(&s.empty_bar[stage]), phase ^ 1);
+          if (p.prof && ptid == 0) { const long long tn = clock64(); acc_wait += tn - tw0; tw0 = tn; }
+          uint8_t* sb = s.stages + stage * STAGE_BYTES;
+          if (ptid == 0) {                      // TMA: pre-split W chunk (big+small, already swizzled) -> B_big|B_small
+            const uint32_t fb = smem_u32(&s.full_bar[stage]);
+            mbar_arrive_expect_tx(fb, 2 * TILE_BYTES);
+            tma_bulk_load(smem_u32(sb + 2 * TILE_BYTES), p.Bpack + ((size_t)pt * p.chunks + c) * (2 * TILE_BYTES), 2 * TILE_BYTES, fb);
+          }
+          mix_produce<NT>(p, cf, m0, c, ptid, ring[j], sb, sb + TILE_BYTES);
+          fence_proxy_async();                  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+          __syncwarp();
+          if ((ptid & 31) == 0) mbar_arrive(smem_u32(&s.full_bar[stage]));   // one arrival per producer warp
+          if (p.prof && ptid == 0) acc_prod += clock64() - tw0;
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    if (p.prof && ptid == 0) { p.prof[blockIdx.x * 8 + 0] = acc_wait; p.prof[blockIdx.x * 8 + 1] = acc_prod; }
+  } else if (warp == MMA_WARP) {
+    int stage = 0, phase = 0, it = 0;
+    long long loc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it)
+      mma_tile(s, tmem_base, it, p.chunks, stage, phase, p.prof ? loc : nullptr);
+    if (p.prof && (threadIdx.x & 31) == 0) { p.prof[blockIdx.x * 8 + 2] = loc[2]; p.prof[blockIdx.x * 8 + 3] = loc[3]; }
+  } else {
+    int it = 0;
+    const int ldc = p.n * p.Pout;
+    long long loc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      int m0, comp, pt;
+      mix_tile(p, t, m0, comp, pt);
+      const int ncols = min(BN, p.Pout - pt * BN);
+      epilogue_tile<true>(s, tmem_base, it, p.C, ldc, p.M, m0, comp * p.Pout + pt * BN, ncols, p.bias, p.residual, p.act,
+                          p.prof ? loc : nullptr);
+    }
+    if (p.prof && threadIdx.x == EPI_WARP0 * 32) {
+      p.prof[blockIdx.x * 8 + 4] = loc[4]; p.prof[blockIdx.x * 8 + 5] = loc[5]; p.prof[blockIdx.x * 8 + 7] = loc[7];
+      p.prof[blockIdx.x * 8 + 6] = clock64() - tk0;
+    }
+  }
+  cta_epilogue(tmem_base);
+}
+
+// ---------------------------------------------------------------------------- dH kernel
+// operands: tile row = feature index f0.., k = sample index m; global [M, ld] row-major is read with 128-bit
+// loads along the feature axis and transposed 4x4 in registers.
+struct DhLoad { float t[4][4]; };
+
+__device__ __forceinline__ void dh_issue_loads(const float* __restrict__ X, int ld, bool vec, int f0, int mk0, int mend, int ptid,
+                                               DhLoad& L) {
+  const int ku = ptid & 7, fg = ptid >> 3;      // 8 k-units x 32 feature groups of 4
+  const int gf = f0 + fg * 4;
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    const int gm = mk0 + ku * 4 + jj;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) L.t[jj][c] = 0.f;
+    if (gm < mend) {
+      const float* src = X + (size_t)gm * ld + gf;
+      if (vec && gf + 3 < ld) {
+        float4 q = __ldg(reinterpret_cast<const float4*>(src));
+        L.t[jj][0] = q.x; L.t[jj][1] = q.y; L.t[jj][2] = q.z; L.t[jj][3] = q.w;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (gf + c < ld) L.t[jj][c] = __ldg(src + c);
+      }
+    }
+  }
+}
+__device__ __forceinline__ void dh_produce(const DhLoad& L, int ptid, uint8_t* big, uint8_t* small) {
+  const int ku = ptid & 7, fg = ptid >> 3;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float v[4] = {L.t[0][c], L.t[1][c], L.t[2][c], L.t[3][c]};
+    store_unit(big, small, fg * 4 + c, ku, v);
+  }
+}
+__device__ __forceinline__ void dh_tile(const DhParams& p, int t, int& i0, int& o0, int& split, int& kbeg, int& kend) {
+  const int per = p.tiles_m * p.tiles_n;
+  split = t / per;
+  const int r = t % per;
+  i0 = (r / p.tiles_n) * BM;
+  o0 = (r % p.tiles_n) * BN;
+  kbeg = split * p.rows_per_split;
+  kend = min(kbeg + p.rows_per_split, p.M);
+}
+
+__global__ void __launch_bounds__(THREADS, 1) phm_tc_dh_kernel(const DhParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const Smem s = carve(smem_raw, 0);
+  const uint32_t tmem_base = cta_prologue(s, PROD_WARPS);
+  const int warp = threadIdx.x >> 5;
+
+  if (warp < EPI_WARP0) {
+    // 512 producer threads: the first 256 build the A operand (x^T), the other 256 the B operand (dy^T)
+    static_assert(PROD_THREADS == 512, "dH producer mapping assumes 16 producer warps");
+    const int ptid = threadIdx.x - PROD_WARP0 * 32;
+    const int half = ptid >> 8, q = ptid & 255;
+    int stage = 0, phase = 0;
+    const float* src = half == 0 ? p.X : p.G;
+    const int ld = half == 0 ? p.In : p.Out;
+    const bool vec = ld % 4 == 0 && aligned16(src);
+    DhLoad cur, nxt;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      int i0, o0, split, kbeg, kend;
+      dh_tile(p, t, i0, o0, split, kbeg, kend);
+      const int f0 = half == 0 ? i0 : o0;
+      dh_issue_loads(src, ld, vec, f0, kbeg, kend, q, nxt);
+      for (int k0 = kbeg; k0 < kend; k0 += BK) {
+        cur = nxt;
+        if (k0 + BK < kend) dh_issue_loads(src, ld, vec, f0, k0 + BK, kend, q, nxt);
+        mbar_wait(smem_u32(&s.empty_bar[stage]), phase ^ 1);
+        uint8_t* sb = s.stages + stage * STAGE_BYTES + half * 2 * TILE_BYTES;
+        dh_produce(cur, q, sb, sb + TILE_BYTES);
+        fence_proxy_async();
+        __syncwarp();
+        if ((ptid & 31) == 0) mbar_arrive(smem_u32(&s.full_bar[stage]));
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    int stage = 0, phase = 0, it = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      int i0, o0, split, kbeg, kend;
+      dh_tile(p, t, i0, o0, split, kbeg, kend);
+      mma_tile(s, tmem_base, it, (kend - kbeg + BK - 1) / BK, stage, phase);
+    }
+  } else {
+    int it = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      int i0, o0, split, kbeg, kend;
+      dh_tile(p, t, i0, o0, split, kbeg, kend);
+      epilogue_tile<false>(s, tmem_base, it, p.C + (size_t)split * p.In * p.Out, p.Out, p.In, i0, o0, min(BN, p.Out - o0), nullptr,
+                           nullptr, 0);
+    }
+  }
+  cta_epilogue(tmem_base);
+}
+
+// ---------------------------------------------------------------------------- pack kernel
+// Writes, for one direction, the rule re-indexed per output component and the W operand as tf32 big/small
+// tile images:  Bpack[pt][chunk][half][q][32]  with element (q, s) = Wsrc(b = s % n, kk = s / n, p = pt*128 + q).
+//   dir 0 (FWD): reduction index kk = k, output index q = p : value W[b,k,p];  coef[c][b][a] = A[b,a,c]
+//   dir 1 (DX) : reduction index kk = p, output index q = k : value W[b,k,p];  coef[a][b][c] = A[b,a,c]
+__global__ void __launch_bounds__(256) phm_pack_kernel(const float* __restrict__ A, const float* __restrict__ W, int n, int K, int P,
+                                                       uint8_t* __restrict__ pack_fwd, float* __restrict__ coef_fwd,
+                                                       uint8_t* __restrict__ pack_dx, float* __restrict__ coef_dx, int units_fwd,
+                                                       int units_dx) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n3 = n * n * n;
+  if (t < n3) {
+    const int b = t / (n * n), a = (t / n) % n, c = t % n;
+    const float v = A[t];
+    coef_fwd[(c * n + b) * n + a] = v;
+    coef_dx[(a * n + b) * n + c] = v;
+  }
+  for (int dir = 0; dir < 2; ++dir) {
+    const int units = dir == 0 ? units_fwd : units_dx;
+    if (t >= units) continue;
+    const int Kin = dir == 0 ? K : P, Pout = dir == 0 ? P : K;
+    const int S = n * Kin, chunks = (S + BK - 1) / BK;
+    // unit id -> (pt, chunk, q, ku)
+    const int ku = t & 7, q = (t >> 3) & (BN - 1);
+    const int rest = t >> 10;
+    const int chunk = rest % chunks, pt = rest / chunks;
+    const int po = pt * BN + q;
+    float big[4], small[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int sidx = chunk * BK + ku * 4 + j;
+      float v = 0.f;
+      if (po < Pout && sidx < S) {
+        const int kk = sidx / n, b = sidx - kk * n;
+        v = dir == 0 ? W[((size_t)b * K + kk) * P + po] : W[((size_t)b * K + po) * P + kk];
+      }
+      split_tf32(v, big[j], small[j]);
+    }
+    uint8_t* dst = (dir == 0 ? pack_fwd : pack_dx) + ((size_t)pt * chunks + chunk) * (2 * TILE_BYTES);
+    const int off = swz(q, ku);
+    *reinterpret_cast<float4*>(dst + off) = make_float4(big[0], big[1], big[2], big[3]);
+    *reinterpret_cast<float4*>(dst + TILE_BYTES + off) = make_float4(small[0], small[1], small[2], small[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------- host side
+size_t smem_bytes(int coef_floats) {
+  return 1024 + (size_t)STAGES * STAGE_BYTES + EPI_SCRATCH + sizeof(float) * ((coef_floats + 3) & ~3) + 8 * (2 * STAGES + 4) + 16;
+}
+
+int num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+int dh_splits(int M, int In, int Out, int* rows_per_split) {
+  const int tiles = phc_div_up(In, BM) * phc_div_up(Out, BN);
+  int s = num_sms() / tiles;
+  const int maxs = phc_div_up(M, 4 * BK);
+  s = s > maxs ? maxs : s;
+  s = s < 1 ? 1 : (s > 64 ? 64 : s);
+  const int rps = phc_div_up(phc_div_up(M, s), BK) * BK;
+  if (rows_per_split) *rows_per_split = rps;
+  return phc_div_up(M, rps);               // every split owns at least one K chunk
+}
+
+struct PackLayout {
+  size_t coef_fwd, coef_dx, pack_fwd, pack_dx, total;   // byte offsets into the pack buffer
+  int chunks_fwd, chunks_dx, pt_fwd, pt_dx;
+};
+
+PackLayout pack_layout(int n, int K, int P) {
+  PackLayout L;
+  const size_t n3b = ((size_t)n * n * n * 4 + 1023) & ~(size_t)1023;
+  L.chunks_fwd = phc_div_up(n * K, BK); L.pt_fwd = phc_div_up(P, BN);
+  L.chunks_dx = phc_div_up(n * P, BK);  L.pt_dx = phc_div_up(K, BN);
+  L.coef_fwd = 0;
+  L.coef_dx = n3b;
+  L.pack_fwd = 2 * n3b;
+  L.pack_dx = L.pack_fwd + (size_t)L.pt_fwd * L.chunks_fwd * 2 * TILE_BYTES;
+  L.total = L.pack_dx + (size_t)L.pt_dx * L.chunks_dx * 2 * TILE_BYTES;
+  return L;
+}
+
+template <typename Kern>
+int set_smem(Kern kern, bool* done) {
+  if (*done) return PHC_OK;
+  const size_t smem = smem_bytes(16 * 16 * 16);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    phc_set_error("phm_tc: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+    return PHC_ERR_CUDA;
+  }
+  *done = true;
+  return PHC_OK;
+}
+
+template <int NT>
+int launch_mix_nt(const MixParams& p, cudaStream_t stream) {
+  static bool configured = false;
+  int rc = set_smem(phm_tc_mix_kernel<NT>, &configured);
+  if (rc) return rc;
+  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  phm_tc_mix_kernel<NT><<<grid, THREADS, smem_bytes(p.n * p.n * p.n), stream>>>(p);
+  return phc_check_launch("phm_tc_mix_kernel");
+}
+
+int launch_mix(const MixParams& p, cudaStream_t stream) {
+  switch (p.n) {
+    case 1: return launch_mix_nt<1>(p, stream);
+    case 2: return launch_mix_nt<2>(p, stream);
+    case 4: return launch_mix_nt<4>(p, stream);
+    default: return launch_mix_nt<0>(p, stream);
+  }
+}
+
+int launch_pack(const float* A, const float* W, int n, int K, int P, uint8_t* buf, cudaStream_t stream) {
+  const PackLayout L = pack_layout(n, K, P);
+  const int units_fwd = L.pt_fwd * L.chunks_fwd * BN * 8, units_dx = L.pt_dx * L.chunks_dx * BN * 8;
+  int threads = units_fwd > units_dx ? units_fwd : units_dx;
+  if (threads < n * n * n) threads = n * n * n;
+  phm_pack_kernel<<<phc_div_up(threads, 256), 256, 0, stream>>>(A, W, n, K, P, buf + L.pack_fwd, reinterpret_cast<float*>(buf + L.coef_fwd),
+                                                                buf + L.pack_dx, reinterpret_cast<float*>(buf + L.coef_dx), units_fwd,
+                                                                units_dx);
+  return phc_check_launch("phm_pack_kernel");
+}
+
+}  // namespace tc
+
+// ---------------------------------------------------------------------------- host entry points (used by api.cu)
+int phm_tc_supported(int rows, int in_features, int out_features, int phm_dim, int precision) {
+  // tf32x3 only for now; small problems (head layers, M = graphs per batch) stay on the exact FFMA path
+  return precision == 1 && rows >= 512 && in_features >= 32 && out_features >= 32 && phm_dim <= 16;
+}
+
+size_t phm_tc_fwd_workspace_bytes(int, int in_features, int out_features, int phm_dim, int) {
+  return tc::pack_layout(phm_dim, in_features / phm_dim, out_features / phm_dim).total + 1024;
+}
+
+size_t phm_tc_bwd_workspace_bytes(int rows, int in_features, int out_features, int phm_dim, int) {
+  const size_t part = (size_t)tc::dh_splits(rows, in_features, out_features, nullptr) * in_features * out_features;
+  return tc::pack_layout(phm_dim, in_features / phm_dim, out_features / phm_dim).total + 1024 +
+         sizeof(float) * (part + phm_contract_scratch_floats(rows, in_features, out_features, phm_dim)) + 64;
+}
+
+static uint8_t* align1k(void* p) { return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023); }
+
+int phm_tc_fwd(const float* x, const float* A, const float* W, const float* bias, const float* residual, float* y, int rows,
+               int in_features, int out_features, int phm_dim, int act, int, void* workspace, cudaStream_t stream) {
+  const int n = phm_dim, K = in_features / n, P = out_features / n;
+  uint8_t* buf = align1k(workspace);
+  int rc = tc::launch_pack(A, W, n, K, P, buf, stream);
+  if (rc) return rc;
+  const tc::PackLayout L = tc::pack_layout(n, K, P);
+  tc::MixParams p{};
+  p.X = x; p.coef = reinterpret_cast<const float*>(buf + L.coef_fwd); p.Bpack = buf + L.pack_fwd;
+  p.bias = bias; p.residual = residual; p.C = y;
+  p.M = rows; p.n = n; p.Kin = K; p.Pout = P; p.S = n * K; p.chunks = L.chunks_fwd; p.ptiles = L.pt_fwd; p.act = act;
+  p.num_tiles = phc_div_up(rows, tc::BM) * n * p.ptiles;
+  p.prof = g_phm_tc_prof;
+  return tc::launch_mix(p, stream);
+}
+
+int phm_tc_bwd(const float* gy, const float* x, const float* A, const float* W, float* dx, float* dA, float* dW, float* db, int rows,
+               int in_features, int out_features, int phm_dim, int, void* workspace, cudaStream_t stream) {
+  const int n = phm_dim, K = in_features / n, P = out_features / n;
+  uint8_t* buf = align1k(workspace);
+  const tc::PackLayout L = tc::pack_layout(n, K, P);
+  if (dx) {
+    int rc = tc::launch_pack(A, W, n, K, P, buf, stream);
+    if (rc) return rc;
+    tc::MixParams p{};
+    p.X = gy; p.coef = reinterpret_cast<const float*>(buf + L.coef_dx); p.Bpack = buf + L.pack_dx;
+    p.C = dx;
+    p.M = rows; p.n = n; p.Kin = P; p.Pout = K; p.S = n * P; p.chunks = L.chunks_dx; p.ptiles = L.pt_dx; p.act = PHC_ACT_IDENTITY;
+    p.num_tiles = phc_div_up(rows, tc::BM) * n * p.ptiles;
+    rc = tc::launch_mix(p, stream);
+    if (rc) return rc;
+  }
+  float* part = reinterpret_cast<float*>(buf + L.total);
+  tc::DhParams d{};
+  d.X = x; d.G = gy; d.C = part;
+  d.M = rows; d.In = in_features; d.Out = out_features;
+  d.tiles_m = phc_div_up(in_features, tc::BM); d.tiles_n = phc_div_up(out_features, tc::BN);
+  d.splits = tc::dh_splits(rows, in_features, out_features, &d.rows_per_split);
+  d.num_tiles = d.tiles_m * d.tiles_n * d.splits;
+  static bool configured = false;
+  int rc = tc::set_smem(tc::phm_tc_dh_kernel, &configured);
+  if (rc) return rc;
+  const int grid = d.num_tiles < tc::num_sms() ? d.num_tiles : tc::num_sms();
+  tc::phm_tc_dh_kernel<<<grid, tc::THREADS, tc::smem_bytes(0), stream>>>(d);
+  rc = phc_check_launch("phm_tc_dh_kernel");
+  if (rc) return rc;
+  float* scratch = part + (size_t)d.splits * in_features * out_features;
+  return phm_contract_and_bias(part, d.splits, gy, A, W, dA, dW, db, rows, in_features, out_features, n, scratch, stream);
+}
+
+extern "C" void phc_debug_set_tc_profile(long long* device_buffer) { g_phm_tc_prof = device_buffer; }

@@ -14,12 +14,12 @@ DEV = "cuda:0"
 def _compare(got, want, rtol, what, noise=None):
     """``noise`` (optional) = the same quantities from the oracle run in fp32: its distance to the fp64
     oracle measures how ill-conditioned a value is (e.g. gradients that are exactly zero in exact
-    arithmetic); the CUDA path is allowed 5x that on top of rtol."""
+    arithmetic); the CUDA path is allowed 10x that on top of rtol."""
     def tol(key, ref, sub=None):
         floor = 0.0
         if noise is not None:
             a = noise[key] if sub is None else noise[key][sub]
-            floor = 5.0 * float((a.float() - ref.float()).abs().max())
+            floor = 10.0 * float((a.float() - ref.float()).abs().max())
         return max(rtol * float(ref.abs().max()), floor, 2e-6)
     assert_close(got["logits"], want["logits"], rtol, tol("logits", want["logits"]), f"{what}: train logits")
     assert_close(got["reg"], want["reg"], rtol, 1e-6, f"{what}: regulariser")
@@ -29,7 +29,7 @@ def _compare(got, want, rtol, what, noise=None):
         assert k in got["grads"], f"{what}: no gradient for {k}"
         assert_close(got["grads"][k], g, 5 * rtol, 5 * tol("grads", g, k), f"{what}: grad {k}")
     for k, v in want["running"].items():
-        assert_close(got["running"][k].float(), v.float(), rtol, 1e-5, f"{what}: {k}")
+        assert_close(got["running"][k].float(), v.float(), rtol, max(1e-5, tol("running", v.float(), k)), f"{what}: {k}")
 
 
 @pytest.mark.parametrize("name", golden_cases())
@@ -60,6 +60,29 @@ def test_model_matches_oracle_on_workload_shapes(wl_name, graphs, n, monkeypatch
     np.random.seed(0)
     state = PHMSkipConnectAdd(**cfg).state_dict()
     batch = make_batch(wl, seed=7, batch_graphs=graphs)
+    got = product_train_eval(cfg, state, batch, wl.loss, 0.01, DEV)
+    want = oracle_train_eval(cfg, state, batch, wl.loss, 0.01, torch.float64)
+    noise = oracle_train_eval(cfg, state, batch, wl.loss, 0.01, torch.float32)
+    _compare(got, want, RTOL, wl_name, noise)
+
+
+@pytest.mark.parametrize("wl_name,graphs", [("hiv", 128), ("ppa", 6)])
+def test_model_tensor_core_mode_matches_oracle(wl_name, graphs, monkeypatch):
+    """Default precision (tf32x3 on tcgen05 for the node-level linears): same fp32 tolerance."""
+    monkeypatch.setenv("PHC_PRECISION", "tf32x3")
+    from phc.hypercomplex.undirectional.models import PHMSkipConnectAdd
+    from phc_gnn_b200.synthetic import workloads, make_batch
+    import numpy as np
+    wl = workloads(4)[wl_name]
+    cfg = dict(wl.model)
+    cfg["mp_layers"] = cfg["mp_layers"][:2]
+    cfg["dropout_mpnn"] = [0.0] * 2
+    cfg["dropout_dn"] = [0.0] * len(cfg["downstream_layers"])
+    torch.manual_seed(0)
+    np.random.seed(0)
+    state = PHMSkipConnectAdd(**cfg).state_dict()
+    batch = make_batch(wl, seed=3, batch_graphs=graphs)
+    assert batch.x.size(0) >= 512            # large enough for the tensor-core path
     got = product_train_eval(cfg, state, batch, wl.loss, 0.01, DEV)
     want = oracle_train_eval(cfg, state, batch, wl.loss, 0.01, torch.float64)
     noise = oracle_train_eval(cfg, state, batch, wl.loss, 0.01, torch.float32)

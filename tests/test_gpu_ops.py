@@ -258,6 +258,28 @@ def test_phm_linear_fp32(n, fin, fout, M):
     _phm_linear_case(n, fin, fout, M, precision=0, rtol=RTOL)
 
 
+@pytest.mark.parametrize("n,fin,fout,M", [(4, 128, 128, 512), (4, 500, 500, 1000), (2, 180, 180, 3000), (4, 200, 200, 3333),
+                                          (1, 224, 56, 9000), (5, 200, 200, 777), (8, 512, 512, 640), (4, 512, 768, 600),
+                                          (3, 33, 300, 515), (16, 512, 64, 520), (4, 224, 224, 8936)])
+def test_phm_linear_tf32x3_tensor_core(n, fin, fout, M):
+    """tcgen05 path (3-term tf32 split): fp32-class accuracy, same rtol as the FFMA path."""
+    _phm_linear_case(n, fin, fout, M, precision=1, rtol=RTOL)
+
+
+def test_phm_linear_tensor_core_is_deterministic():
+    from phc_gnn_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    n, F, M = 4, 200, 3000
+    t = [v.to(DEV).requires_grad_(True) for v in (torch.randn(M, F, generator=g), torch.randn(n, n, n, generator=g),
+                                                 torch.randn(n, F // n, F // n, generator=g), torch.randn(F, generator=g))]
+    outs = []
+    for _ in range(2):
+        y = ops.phm_linear(*t, precision=1)
+        outs.append((y.detach().clone(),) + torch.autograd.grad(y.square().sum(), t))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
 def test_phm_linear_known_answers(ops_golden):
     from phc_gnn_b200 import ops
     for key, fx in ops_golden.items():
