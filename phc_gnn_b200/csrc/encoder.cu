@@ -91,32 +91,90 @@ __global__ void __launch_bounds__(256) embed_bwd_final_kernel(const float* __res
 
 // ---- linear encoder ------------------------------------------------------------------------
 constexpr int LIN_MAX_D = 16;
+constexpr int LIN_ROWS = 32;     // rows per block in forward
 
-template <int VEC>
-__global__ void __launch_bounds__(256) linenc_fwd_kernel(const float* __restrict__ feat, PtrTable weights, PtrTable biases, int R, int D,
-                                                         int n, int Fc, float* __restrict__ out) {
-  const int fcv = Fc / VEC;
-  const int F = n * Fc;
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (long long)R * n * fcv) return;
-  const int r = (int)(t / (n * fcv));
-  const int rem = (int)(t % (n * fcv));
-  const int c = rem / fcv, f = (rem % fcv) * VEC;
-  const float* w = weights.p[c];
-  Vec<VEC> acc;
+// One thread owns 4 consecutive flat features: its 4 x D weights and 4 biases live in registers and are
+// reused for LIN_ROWS rows; per row it reads D broadcast features and writes one 128-bit result.
+template <int D>
+__global__ void __launch_bounds__(128) linenc_fwd_kernel(const float* __restrict__ feat, PtrTable weights, PtrTable biases, int R, int Fc,
+                                                         int F, float* __restrict__ out) {
+  const int f = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (f >= F) return;
+  float w[4][D], bq[4];
 #pragma unroll
-  for (int q = 0; q < VEC; ++q) acc.v[q] = biases.p[c] ? __ldg(biases.p[c] + f + q) : 0.f;
-  for (int d = 0; d < D; ++d) {
-    const float a = __ldg(feat + (size_t)r * D + d);
+  for (int q = 0; q < 4; ++q) {
+    const int c = (f + q) / Fc, fp = (f + q) - c * Fc;
+    bq[q] = biases.p[c] ? __ldg(biases.p[c] + fp) : 0.f;
 #pragma unroll
-    for (int q = 0; q < VEC; ++q) acc.v[q] += a * __ldg(w + (size_t)(f + q) * D + d);
+    for (int d = 0; d < D; ++d) w[q][d] = __ldg(weights.p[c] + (size_t)fp * D + d);
   }
-  acc.store_stream(out + (size_t)r * F + c * Fc + f);
+  const int r0 = blockIdx.y * LIN_ROWS, r1 = min(r0 + LIN_ROWS, R);
+#pragma unroll 4
+  for (int r = r0; r < r1; ++r) {
+    float a[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) a[d] = __ldg(feat + (size_t)r * D + d);
+    float o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float v = bq[q];
+#pragma unroll
+      for (int d = 0; d < D; ++d) v += a[d] * w[q][d];
+      o[q] = v;
+    }
+    Vec<4> t; t.v[0] = o[0]; t.v[1] = o[1]; t.v[2] = o[2]; t.v[3] = o[3];
+    t.store_stream(out + (size_t)r * F + f);
+  }
 }
 
-// part[chunk][f][0..D] : d = 0..D-1 weight grads, d = D bias grad. grid (feature tiles, row chunks)
-__global__ void __launch_bounds__(128) linenc_bwd_partial_kernel(const float* __restrict__ g, const float* __restrict__ feat, int R, int D,
-                                                                 int F, int rows_per_chunk, float* __restrict__ part) {
+// generic fallback (F % 4 != 0 or unaligned): one thread per output element
+__global__ void __launch_bounds__(256) linenc_fwd_scalar_kernel(const float* __restrict__ feat, PtrTable weights, PtrTable biases, int R,
+                                                                int D, int Fc, int F, float* __restrict__ out) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)R * F) return;
+  const int r = (int)(t / F), f = (int)(t % F);
+  const int c = f / Fc, fp = f - c * Fc;
+  float v = biases.p[c] ? __ldg(biases.p[c] + fp) : 0.f;
+  for (int d = 0; d < D; ++d) v += __ldg(feat + (size_t)r * D + d) * __ldg(weights.p[c] + (size_t)fp * D + d);
+  out[(size_t)r * F + f] = v;
+}
+
+// part[chunk][f][0..D] : d = 0..D-1 weight grads, d = D bias grad. grid (feature quads / 128, row chunks).
+// One thread owns 4 features (one 128-bit load of g per row) and 4 x (D+1) accumulators.
+template <int D>
+__global__ void __launch_bounds__(128) linenc_bwd_partial_kernel(const float* __restrict__ g, const float* __restrict__ feat, int R, int F,
+                                                                 int rows_per_chunk, float* __restrict__ part) {
+  const int f = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (f >= F) return;
+  const int r0 = blockIdx.y * rows_per_chunk, r1 = min(r0 + rows_per_chunk, R);
+  float acc[4][D + 1];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int d = 0; d <= D; ++d) acc[q][d] = 0.f;
+#pragma unroll 4
+  for (int r = r0; r < r1; ++r) {
+    const Vec<4> gv = Vec<4>::load_stream(g + (size_t)r * F + f);
+    float a[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) a[d] = __ldg(feat + (size_t)r * D + d);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) acc[q][d] += gv.v[q] * a[d];
+      acc[q][D] += gv.v[q];
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float* dst = part + ((size_t)blockIdx.y * F + f + q) * (D + 1);
+#pragma unroll
+    for (int d = 0; d <= D; ++d) dst[d] = acc[q][d];
+  }
+}
+
+__global__ void __launch_bounds__(128) linenc_bwd_partial_scalar_kernel(const float* __restrict__ g, const float* __restrict__ feat, int R,
+                                                                        int D, int F, int rows_per_chunk, float* __restrict__ part) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= F) return;
   const int r0 = blockIdx.y * rows_per_chunk, r1 = min(r0 + rows_per_chunk, R);
@@ -150,13 +208,24 @@ __global__ void __launch_bounds__(256) linenc_bwd_final_kernel(const float* __re
   else if (dbiases.p[c]) dbiases.p[c][fp] = s;
 }
 
+template <int D>
+void launch_linenc_fwd(const float* feat, const PtrTable& w, const PtrTable& b, int R, int Fc, int F, float* out, cudaStream_t st) {
+  dim3 grid(phc_div_up(F / 4, 128), phc_div_up(R, LIN_ROWS));
+  linenc_fwd_kernel<D><<<grid, 128, 0, st>>>(feat, w, b, R, Fc, F, out);
+}
+template <int D>
+void launch_linenc_bwd(const float* g, const float* feat, int R, int F, int rpc, int chunks, float* part, cudaStream_t st) {
+  dim3 grid(phc_div_up(F / 4, 128), chunks);
+  linenc_bwd_partial_kernel<D><<<grid, 128, 0, st>>>(g, feat, R, F, rpc, part);
+}
+
 int embed_chunks(int R) {
   int chunks = phc_div_up(R, 512);
   return chunks < 1 ? 1 : (chunks > 64 ? 64 : chunks);
 }
 int linenc_chunks(int R) {
-  int chunks = phc_div_up(R, 256);
-  return chunks < 1 ? 1 : (chunks > 296 ? 296 : chunks);
+  int chunks = phc_div_up(R, 128);
+  return chunks < 1 ? 1 : (chunks > 1184 ? 1184 : chunks);
 }
 
 }  // namespace
@@ -219,10 +288,18 @@ int phc_linear_encoder_fwd(const float* feat, const float* const* weights, const
   if (rows == 0) return PHC_OK;
   PtrTable w, b;
   for (int c = 0; c < phm_dim; ++c) { w.p[c] = weights[c]; b.p[c] = biases ? biases[c] : nullptr; }
-  const int n = phm_dim, Fc = width_per_component;
-  const bool v4 = Fc % 4 == 0 && phc_aligned16(out);
-  if (v4) linenc_fwd_kernel<4><<<phc_div_up((long long)rows * n * (Fc / 4), 256), 256, 0, stream>>>(feat, w, b, rows, in_dim, n, Fc, out);
-  else linenc_fwd_kernel<1><<<phc_div_up((long long)rows * n * Fc, 256), 256, 0, stream>>>(feat, w, b, rows, in_dim, n, Fc, out);
+  const int n = phm_dim, Fc = width_per_component, F = n * Fc;
+  const bool v4 = F % 4 == 0 && phc_aligned16(out);
+  if (v4) {
+    switch (in_dim) {
+#define PHC_CASE(D) case D: launch_linenc_fwd<D>(feat, w, b, rows, Fc, F, out, stream); break;
+      PHC_CASE(1) PHC_CASE(2) PHC_CASE(3) PHC_CASE(4) PHC_CASE(5) PHC_CASE(6) PHC_CASE(7) PHC_CASE(8)
+      PHC_CASE(9) PHC_CASE(10) PHC_CASE(11) PHC_CASE(12) PHC_CASE(13) PHC_CASE(14) PHC_CASE(15) PHC_CASE(16)
+#undef PHC_CASE
+    }
+  } else {
+    linenc_fwd_scalar_kernel<<<phc_div_up((long long)rows * F, 256), 256, 0, stream>>>(feat, w, b, rows, in_dim, Fc, F, out);
+  }
   return phc_check_launch("phc_linear_encoder_fwd");
 }
 
@@ -237,8 +314,17 @@ int phc_linear_encoder_bwd(const float* gout, const float* feat, float* const* d
   const int chunks = linenc_chunks(rows);
   const int rpc = phc_div_up(rows > 0 ? rows : 1, chunks);
   float* part = reinterpret_cast<float*>(workspace);
-  dim3 grid(phc_div_up(F, 128), chunks);
-  linenc_bwd_partial_kernel<<<grid, 128, 0, stream>>>(gout, feat, rows, in_dim, F, rpc, part);
+  if (F % 4 == 0 && phc_aligned16(gout)) {
+    switch (in_dim) {
+#define PHC_CASE(D) case D: launch_linenc_bwd<D>(gout, feat, rows, F, rpc, chunks, part, stream); break;
+      PHC_CASE(1) PHC_CASE(2) PHC_CASE(3) PHC_CASE(4) PHC_CASE(5) PHC_CASE(6) PHC_CASE(7) PHC_CASE(8)
+      PHC_CASE(9) PHC_CASE(10) PHC_CASE(11) PHC_CASE(12) PHC_CASE(13) PHC_CASE(14) PHC_CASE(15) PHC_CASE(16)
+#undef PHC_CASE
+    }
+  } else {
+    dim3 grid(phc_div_up(F, 128), chunks);
+    linenc_bwd_partial_scalar_kernel<<<grid, 128, 0, stream>>>(gout, feat, rows, in_dim, F, rpc, part);
+  }
   linenc_bwd_final_kernel<<<phc_div_up((long long)F * (in_dim + 1), 256), 256, 0, stream>>>(part, dw, db, chunks, in_dim, n, Fc);
   return phc_check_launch("phc_linear_encoder_bwd");
 }

@@ -89,22 +89,39 @@ __global__ void __launch_bounds__(BN_SLICES * BN_LANES) bn_chunk_stats_kernel(co
 }
 
 // ---- finalize: merge chunks (Chan), produce mean / rstd, update running statistics ----------
-__global__ void __launch_bounds__(128) bn_finalize_kernel(const float* __restrict__ part, int chunks, int M, int F, float eps,
+// One warp per feature: lane l merges chunks l, l+32, ... in order, then the 32 lane results are merged by a
+// fixed butterfly (xor 16, 8, 4, 2, 1) — a fixed association order, hence deterministic.
+__device__ __forceinline__ void chan_merge(double& cnt, double& mean, double& m2, double nb, double mb, double m2b) {
+  if (nb == 0.0) return;
+  const double tot = cnt + nb, delta = mb - mean;
+  mean += delta * nb / tot;
+  m2 += m2b + delta * delta * cnt * nb / tot;
+  cnt = tot;
+}
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ part, int chunks, int M, int F, float eps,
                                                           float momentum, float* __restrict__ running_mean,
                                                           float* __restrict__ running_var, float* __restrict__ save_mean,
                                                           float* __restrict__ save_rstd, long long* __restrict__ tracked, int n_tracked) {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f == 0 && tracked) for (int c = 0; c < n_tracked; ++c) tracked[c] += 1;
+  const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && tracked) for (int c = 0; c < n_tracked; ++c) tracked[c] += 1;
   if (f >= F) return;
   double mean = 0.0, m2 = 0.0, cnt = 0.0;
-  for (int c = 0; c < chunks; ++c) {
+  for (int c = lane; c < chunks; c += 32) {
     const double nb = (double)min(BN_ROWS, M - c * BN_ROWS);
-    const double mb = part[((size_t)c * 2 + 0) * F + f], m2b = part[((size_t)c * 2 + 1) * F + f];
-    const double tot = cnt + nb, delta = mb - mean;
-    mean += delta * nb / tot;
-    m2 += m2b + delta * delta * cnt * nb / tot;
-    cnt = tot;
+    chan_merge(cnt, mean, m2, nb, (double)part[((size_t)c * 2 + 0) * F + f], (double)part[((size_t)c * 2 + 1) * F + f]);
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ocnt = __shfl_xor_sync(0xffffffffu, cnt, o), omean = __shfl_xor_sync(0xffffffffu, mean, o),
+                 om2 = __shfl_xor_sync(0xffffffffu, m2, o);
+    // merge (lower lane's partial first so both partners compute the identical result)
+    double c0 = (lane & o) ? ocnt : cnt, me0 = (lane & o) ? omean : mean, q0 = (lane & o) ? om2 : m2;
+    const double c1 = (lane & o) ? cnt : ocnt, me1 = (lane & o) ? mean : omean, q1 = (lane & o) ? m2 : om2;
+    chan_merge(c0, me0, q0, c1, me1, q1);
+    cnt = c0; mean = me0; m2 = q0;
+  }
+  if (lane != 0) return;
   const double var = m2 / (double)M;
   save_mean[f] = (float)mean;
   save_rstd[f] = (float)(1.0 / sqrt(var + (double)eps));
@@ -210,17 +227,25 @@ __global__ void __launch_bounds__(BN_SLICES * BN_LANES) bn_bwd_reduce_kernel(EwP
   }
 }
 
-__global__ void __launch_bounds__(128) bn_bwd_finalize_kernel(const float* __restrict__ part, int chunks, int F, float* __restrict__ dgamma,
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ part, int chunks, int F, float* __restrict__ dgamma,
                                                               float* __restrict__ dbeta) {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (f >= F) return;
   double a = 0.0, b = 0.0;
-  for (int c = 0; c < chunks; ++c) {
+  for (int c = lane; c < chunks; c += 32) {
     a += part[((size_t)c * 2 + 0) * F + f];
     b += part[((size_t)c * 2 + 1) * F + f];
   }
-  dbeta[f] = (float)a;
-  dgamma[f] = (float)b;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if (lane == 0) {
+    dbeta[f] = (float)a;
+    dgamma[f] = (float)b;
+  }
 }
 
 // dh = gamma * rstd * (da - sum_da/M - xhat * sum_da_xhat/M)   [training]   or gamma * rstd * da   [eval]
@@ -293,7 +318,7 @@ int phc_bn_act_drop_skip_fwd(const float* h, const float* gamma, const float* be
       dim3 grid(phc_div_up(F, BN_LANES * (v4s ? 4 : 1)), chunks);
       if (v4s) bn_chunk_stats_kernel<4><<<grid, BN_SLICES * BN_LANES, 0, stream>>>(h, M, F, part);
       else bn_chunk_stats_kernel<1><<<grid, BN_SLICES * BN_LANES, 0, stream>>>(h, M, F, part);
-      bn_finalize_kernel<<<phc_div_up(F, 128), 128, 0, stream>>>(part, chunks, M, F, eps, momentum, running_mean, running_var, save_mean,
+      bn_finalize_kernel<<<phc_div_up((long long)F * 32, 256), 256, 0, stream>>>(part, chunks, M, F, eps, momentum, running_mean, running_var, save_mean,
                                                                 save_rstd, num_batches_tracked, n_tracked);
     } else {
       PHC_REQUIRE(running_mean && running_var, "phc_bn_act_drop_skip_fwd: eval mode needs running statistics");
@@ -326,7 +351,7 @@ int phc_bn_act_drop_skip_bwd(const float* dy, const float* h, const float* gamma
     dim3 grid(phc_div_up(F, BN_LANES * (v4 ? 4 : 1)), chunks);
     if (v4) bn_bwd_reduce_kernel<4><<<grid, BN_SLICES * BN_LANES, 0, stream>>>(p, dy, h, gamma, beta, save_mean, save_rstd, part);
     else bn_bwd_reduce_kernel<1><<<grid, BN_SLICES * BN_LANES, 0, stream>>>(p, dy, h, gamma, beta, save_mean, save_rstd, part);
-    bn_bwd_finalize_kernel<<<phc_div_up(F, 128), 128, 0, stream>>>(part, chunks, F, dgamma, dbeta);
+    bn_bwd_finalize_kernel<<<phc_div_up((long long)F * 32, 256), 256, 0, stream>>>(part, chunks, F, dgamma, dbeta);
   }
   if (v4)
     bn_apply_bwd_kernel<4><<<phc_div_up((long long)M * (F / 4), 256), 256, 0, stream>>>(p, training, dy, h, gamma, beta, save_mean, save_rstd,

@@ -27,7 +27,7 @@ def _compare(got, want, rtol, what, noise=None):
     assert_close(got["logits_eval"], want["logits_eval"], rtol, tol("logits_eval", want["logits_eval"]), f"{what}: eval logits")
     for k, g in want["grads"].items():
         assert k in got["grads"], f"{what}: no gradient for {k}"
-        assert_close(got["grads"][k], g, 5 * rtol, 5 * tol("grads", g, k), f"{what}: grad {k}")
+        assert_close(got["grads"][k], g, 5 * rtol, 10 * tol("grads", g, k), f"{what}: grad {k}")
     for k, v in want["running"].items():
         assert_close(got["running"][k].float(), v.float(), rtol, max(1e-5, tol("running", v.float(), k)), f"{what}: {k}")
 
