@@ -126,6 +126,14 @@ int phc_phm_linear_bwd(const float* gy, const float* x, const float* phm_rule, c
                        float* dbias, int rows, int in_features, int out_features, int phm_dim, int precision, void* workspace,
                        size_t workspace_bytes, phc_stream_t stream);
 
+/* ---- weight regulariser (regularization.py:15-23): out = sum_l mean_{k,p} ||W_l[:,k,p]||_2 ------------
+ * weights / dweights: HOST arrays of device pointers to the [n_l, K_l, P_l] weight tensors; kp[l] = K_l*P_l. */
+size_t phc_weight_reg_workspace_bytes(int count);
+int phc_weight_reg_fwd(const float* const* weights, const int* phm_dims, const int* kp, int count, float* out, void* workspace,
+                       size_t workspace_bytes, phc_stream_t stream);
+int phc_weight_reg_bwd(const float* gout, const float* const* weights, float* const* dweights, const int* phm_dims, const int* kp,
+                       int count, phc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,8 @@
 // rows split across CTAs, partial tiles reduced in a fixed order), then
 //   dW[b,k,p] = sum_{a,c} A[b,a,c] dH[(a,k),(c,p)],   dA[b,a,c] = sum_{k,p} W[b,k,p] dH[(a,k),(c,p)].
 #include "common.cuh"
+#include <stdlib.h>
+#include <cuda.h>   // CUtensorMap (encoded through the runtime's driver entry point; libcuda is not linked)
 
 // helpers implemented in phm_linear_simt.cu (fixed-order reductions shared by both paths)
 int phm_contract_and_bias(const float* part, int splits, const float* gy, const float* A, const float* W, float* dA, float* dW, float* db,
@@ -236,6 +238,7 @@ __device__ __forceinline__ void cta_epilogue(uint32_t tmem_base) {
 }
 
 // MMA issuer for one tile: `chunks` pipeline stages, 4 K-steps x 3 split products each.
+template <int NS = STAGES>
 __device__ __forceinline__ void mma_tile(const Smem& s, uint32_t tmem_base, int it, int chunks, int& stage, int& phase,
                                          long long* prof = nullptr) {   // prof: thread-local accumulators
   const int lane = threadIdx.x & 31;
@@ -266,7 +269,7 @@ __device__ __forceinline__ void mma_tile(const Smem& s, uint32_t tmem_base, int 
       umma_commit(smem_u32(&s.empty_bar[stage]));                    // smem slot reusable when these MMAs retire
     }
     __syncwarp();
-    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    if (++stage == NS) { stage = 0; phase ^= 1; }
   }
   if (lane == 0) umma_commit(smem_u32(&s.tfull_bar[buf]));          // accumulator complete -> epilogue
   __syncwarp();
@@ -518,6 +521,179 @@ __global__ void __launch_bounds__(THREADS, 1) phm_tc_mix_kernel(const MixParams 
   cta_epilogue(tmem_base);
 }
 
+// ---------------------------------------------------------------------------- mix kernel, TMA-staged activations
+// Same contraction as phm_tc_mix_kernel, but the raw activation tiles are fetched by the TMA engine
+// (cp.async.bulk.tensor.2d, one [128 rows x 32/n floats] box per input component and K chunk, zero-filled
+// outside the matrix) into a 4-deep shared-memory ring, so the producer warps never wait on global memory:
+// they read the raw tile from smem, mix it with the rule, split to tf32 big/small and write the UMMA operand.
+//   warps 0-15 producers | 16-19 epilogue | 20 MMA issuer | 21 TMA(x) | 22 TMA(W pack)
+constexpr int TMA_OP_STAGES = 2, TMA_RAW_STAGES = 3;
+constexpr int TMA_X_WARP = MMA_WARP + 1, TMA_B_WARP = MMA_WARP + 2;
+constexpr int TMA_THREADS = (MMA_WARP + 3) * 32;
+// Raw stage: n boxes of 128 rows x (32/n [+4]) floats.  TMA needs a 16-byte aligned start column; when the
+// component width is not a multiple of 4 floats the box starts at the aligned-down column and is 4 floats
+// wider, and the producers skip the (constant per component) 0..3 leading floats.
+constexpr int RAW_BYTES = BM * (BK + 16) * 4;   // 24 KiB covers the padded n = 4 case
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap* tmap, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+
+template <int NT>
+__device__ __forceinline__ void mix_produce_raw(const float* __restrict__ raw, const float (&cf)[NT * NT], int c, int Kin, int pitch,
+                                                int ptid, uint8_t* big, uint8_t* small) {
+  constexpr int KQ = BK / NT;            // k values per chunk
+  // component uu's box: BM rows of `pitch` floats, first needed float at offset (uu*Kin) & 3 when padded
+  const int pad = pitch != KQ;
+#pragma unroll
+  for (int i = 0; i < UNITS; ++i) {
+    const int u = i * PROD_THREADS + ptid;
+    const int row = u >> 3, ku = u & 7;
+    float v[4];
+    if (NT == 4) {
+      const bool ok = c * KQ + ku < Kin;
+      float xv[4];
+#pragma unroll
+      for (int uu = 0; uu < 4; ++uu) xv[uu] = ok ? raw[uu * (BM * pitch) + row * pitch + (pad ? ((uu * Kin) & 3) : 0) + ku] : 0.f;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) v[b] = cf[b * 4] * xv[0] + cf[b * 4 + 1] * xv[1] + cf[b * 4 + 2] * xv[2] + cf[b * 4 + 3] * xv[3];
+    } else if (NT == 2) {
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        const bool ok = c * KQ + 2 * ku + kk < Kin;
+        const float x0 = ok ? raw[row * pitch + 2 * ku + kk] : 0.f;
+        const float x1 = ok ? raw[BM * pitch + row * pitch + (pad ? (Kin & 3) : 0) + 2 * ku + kk] : 0.f;
+        v[kk * 2 + 0] = cf[0] * x0 + cf[1] * x1;
+        v[kk * 2 + 1] = cf[2] * x0 + cf[3] * x1;
+      }
+    } else {
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) v[kk] = (c * KQ + ku * 4 + kk < Kin) ? cf[0] * raw[row * pitch + ku * 4 + kk] : 0.f;
+    }
+    store_unit(big, small, row, ku, v);
+  }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(TMA_THREADS, 1) phm_tc_mix_tma_kernel(const MixParams p, const __grid_constant__ CUtensorMap tmapX) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  Smem s;
+  s.stages = base;                                                          // [2][A_big|A_small|B_big|B_small]
+  uint8_t* rawbuf = base + TMA_OP_STAGES * STAGE_BYTES;                     // [4][16 KiB]
+  s.scratch = reinterpret_cast<float*>(rawbuf + TMA_RAW_STAGES * RAW_BYTES);
+  s.coef = s.scratch + EPI_WARPS * 32 * 33;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s.coef + ((NT * NT * NT + 3) & ~3));
+  s.full_bar = bars;                         // [2]
+  s.empty_bar = bars + 2;                    // [2]
+  uint64_t* rfull_bar = bars + 4;            // [4]
+  uint64_t* rempty_bar = bars + 8;           // [4]
+  s.tfull_bar = bars + 12;                   // [2]
+  s.tempty_bar = bars + 14;                  // [2]
+  s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < NT * NT * NT; i += TMA_THREADS) s.coef[i] = p.coef[i];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TMA_OP_STAGES; ++i) {
+      mbar_init(smem_u32(&s.full_bar[i]), PROD_WARPS + 1);
+      mbar_init(smem_u32(&s.empty_bar[i]), 1);
+    }
+    for (int i = 0; i < TMA_RAW_STAGES; ++i) {
+      mbar_init(smem_u32(&rfull_bar[i]), 1);
+      mbar_init(smem_u32(&rempty_bar[i]), PROD_WARPS);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&s.tfull_bar[b]), 1);
+      mbar_init(smem_u32(&s.tempty_bar[b]), EPI_WARPS * 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == MMA_WARP) tmem_alloc(smem_u32(s.tmem_slot), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s.tmem_slot;
+
+  constexpr int KQ = BK / NT;
+  const int my_tiles = p.num_tiles > (int)blockIdx.x ? (p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int pitch = (p.Kin & 3) ? KQ + 4 : KQ;           // must match the tensor map's box width
+
+  if (warp < EPI_WARP0) {
+    // ===================================================================== producers
+    const int ptid = threadIdx.x;
+    float cfr[NT * NT];
+    int g = 0;
+    for (int ti = 0; ti < my_tiles; ++ti) {
+      int m0, comp, pt;
+      mix_tile(p, blockIdx.x + ti * gridDim.x, m0, comp, pt);
+#pragma unroll
+      for (int i = 0; i < NT * NT; ++i) cfr[i] = s.coef[comp * NT * NT + i];
+      for (int c = 0; c < p.chunks; ++c, ++g) {
+        const int rs = g % TMA_RAW_STAGES, os = g % TMA_OP_STAGES;
+        mbar_wait(smem_u32(&rfull_bar[rs]), (g / TMA_RAW_STAGES) & 1);                 // raw x tile landed (TMA)
+        mbar_wait(smem_u32(&s.empty_bar[os]), ((g / TMA_OP_STAGES) & 1) ^ 1);           // operand slot free (MMA done)
+        uint8_t* sb = s.stages + os * STAGE_BYTES;
+        mix_produce_raw<NT>(reinterpret_cast<const float*>(rawbuf + rs * RAW_BYTES), cfr, c, p.Kin, pitch, ptid, sb, sb + TILE_BYTES);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(smem_u32(&s.full_bar[os]));
+          mbar_arrive(smem_u32(&rempty_bar[rs]));
+        }
+      }
+    }
+  } else if (warp == TMA_X_WARP) {
+    // ===================================================================== TMA: raw activation boxes
+    if (lane == 0) {
+      int g = 0;
+      for (int ti = 0; ti < my_tiles; ++ti) {
+        int m0, comp, pt;
+        mix_tile(p, blockIdx.x + ti * gridDim.x, m0, comp, pt);
+        for (int c = 0; c < p.chunks; ++c, ++g) {
+          const int rs = g % TMA_RAW_STAGES;
+          mbar_wait(smem_u32(&rempty_bar[rs]), ((g / TMA_RAW_STAGES) & 1) ^ 1);
+          const uint32_t bar = smem_u32(&rfull_bar[rs]);
+          mbar_arrive_expect_tx(bar, NT * BM * pitch * 4);
+#pragma unroll
+          for (int uu = 0; uu < NT; ++uu)
+            tma_load_2d(smem_u32(rawbuf + rs * RAW_BYTES + uu * (BM * pitch * 4)), &tmapX, (uu * p.Kin + c * KQ) & ~3, m0, bar);
+        }
+      }
+    }
+  } else if (warp == TMA_B_WARP) {
+    // ===================================================================== TMA: pre-split W chunks
+    if (lane == 0) {
+      int g = 0;
+      for (int ti = 0; ti < my_tiles; ++ti) {
+        int m0, comp, pt;
+        mix_tile(p, blockIdx.x + ti * gridDim.x, m0, comp, pt);
+        for (int c = 0; c < p.chunks; ++c, ++g) {
+          const int os = g % TMA_OP_STAGES;
+          mbar_wait(smem_u32(&s.empty_bar[os]), ((g / TMA_OP_STAGES) & 1) ^ 1);
+          const uint32_t fb = smem_u32(&s.full_bar[os]);
+          mbar_arrive_expect_tx(fb, 2 * TILE_BYTES);
+          tma_bulk_load(smem_u32(s.stages + os * STAGE_BYTES + 2 * TILE_BYTES),
+                        p.Bpack + ((size_t)pt * p.chunks + c) * (2 * TILE_BYTES), 2 * TILE_BYTES, fb);
+        }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    int stage = 0, phase = 0;
+    for (int it = 0; it < my_tiles; ++it) mma_tile<TMA_OP_STAGES>(s, tmem_base, it, p.chunks, stage, phase);
+  } else {
+    const int ldc = p.n * p.Pout;
+    for (int it = 0; it < my_tiles; ++it) {
+      int m0, comp, pt;
+      mix_tile(p, blockIdx.x + it * gridDim.x, m0, comp, pt);
+      const int ncols = min(BN, p.Pout - pt * BN);
+      epilogue_tile<true>(s, tmem_base, it, p.C, ldc, p.M, m0, comp * p.Pout + pt * BN, ncols, p.bias, p.residual, p.act);
+    }
+  }
+  cta_epilogue(tmem_base);
+}
+
 // ---------------------------------------------------------------------------- dH kernel
 // operands: tile row = feature index f0.., k = sample index m; global [M, ld] row-major is read with 128-bit
 // loads along the feature axis and transposed 4x4 in registers.
@@ -728,12 +904,73 @@ int launch_mix_nt(const MixParams& p, cudaStream_t stream) {
   return phc_check_launch("phm_tc_mix_kernel");
 }
 
-int launch_mix(const MixParams& p, cudaStream_t stream) {
+int launch_mix(const MixParams& p, cudaStream_t stream);
+int launch_mix_v2(const MixParams& p, cudaStream_t stream) {
   switch (p.n) {
     case 1: return launch_mix_nt<1>(p, stream);
     case 2: return launch_mix_nt<2>(p, stream);
     case 4: return launch_mix_nt<4>(p, stream);
     default: return launch_mix_nt<0>(p, stream);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+size_t smem_bytes_tma(int nt) {
+  return 1024 + (size_t)TMA_OP_STAGES * STAGE_BYTES + (size_t)TMA_RAW_STAGES * RAW_BYTES + EPI_SCRATCH +
+         sizeof(float) * ((nt * nt * nt + 3) & ~3) + 8 * 16 + 16;
+}
+
+template <int NT>
+int launch_mix_tma_nt(const MixParams& p, const CUtensorMap& tmap, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(phm_tc_mix_tma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_tma(NT));
+    if (e != cudaSuccess) {
+      phc_set_error("phm_tc: cannot reserve %zu bytes of shared memory: %s", smem_bytes_tma(NT), cudaGetErrorString(e));
+      return PHC_ERR_CUDA;
+    }
+    configured = true;
+  }
+  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  phm_tc_mix_tma_kernel<NT><<<grid, TMA_THREADS, smem_bytes_tma(NT), stream>>>(p, tmap);
+  return phc_check_launch("phm_tc_mix_tma_kernel");
+}
+
+// TMA path: n in {1,2,4}, 16-byte aligned rows.  Returns -1 when not applicable (caller falls back).
+int try_launch_mix_tma(const MixParams& p, cudaStream_t stream) {
+  const int n = p.n, Fin = p.n * p.Kin;
+  if (!(n == 1 || n == 2 || n == 4) || Fin % 4 != 0 || (reinterpret_cast<uintptr_t>(p.X) & 15u) != 0) return -1;
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (enc == nullptr) return -1;
+  CUtensorMap tmap;
+  const cuuint64_t gdim[2] = {(cuuint64_t)Fin, (cuuint64_t)p.M};
+  const cuuint64_t gstride[1] = {(cuuint64_t)Fin * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)(BK / n + ((p.Kin & 3) ? 4 : 0)), (cuuint32_t)BM};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p.X), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return -1;
+  switch (n) {
+    case 1: return launch_mix_tma_nt<1>(p, tmap, stream);
+    case 2: return launch_mix_tma_nt<2>(p, tmap, stream);
+    default: return launch_mix_tma_nt<4>(p, tmap, stream);
   }
 }
 
@@ -746,6 +983,15 @@ int launch_pack(const float* A, const float* W, int n, int K, int P, uint8_t* bu
                                                                 buf + L.pack_dx, reinterpret_cast<float*>(buf + L.coef_dx), units_fwd,
                                                                 units_dx);
   return phc_check_launch("phm_pack_kernel");
+}
+
+int launch_mix(const MixParams& p, cudaStream_t stream) {
+  static const bool use_tma = getenv("PHC_TC_NO_TMA") == nullptr;       // debug switch: force the register-prefetch kernel
+  if (use_tma && p.prof == nullptr) {
+    const int rc = try_launch_mix_tma(p, stream);
+    if (rc >= 0) return rc;
+  }
+  return launch_mix_v2(p, stream);
 }
 
 }  // namespace tc

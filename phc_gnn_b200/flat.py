@@ -25,9 +25,7 @@ def is_packed(flat: Optional[torch.Tensor], tensors: Sequence[torch.Tensor]) -> 
     esz = flat.element_size()
     off = 0
     for t in tensors:
-        if t.device != flat.device or t.dtype != flat.dtype or not t.is_contiguous():
-            return False
-        if t.data_ptr() != base + off * esz:
+        if t.data_ptr() != base + off * esz:      # also false after .to(device) / .data re-pointing
             return False
         off += t.numel()
     return off == flat.numel()

@@ -15,7 +15,10 @@ from . import _lib
 
 
 def _stream(device) -> int:
-    return torch.cuda.current_stream(device).cuda_stream
+    """Raw cudaStream_t of torch's current stream (the fast private getter; ~30x cheaper than
+    torch.cuda.current_stream().cuda_stream, which matters for launch-bound molecule-sized batches)."""
+    idx = device.index if device is not None and device.index is not None else torch.cuda.current_device()
+    return torch._C._cuda_getCurrentRawStream(idx)
 
 
 def require_cuda(t: torch.Tensor, what: str):

@@ -744,11 +744,12 @@ class PHMSkipConnectConcat(_PHMSkipConnectBase):
 # ============================================================================ regularisers
 def phm_weight_regularization(model, p: int = 2, device=None):
     """sum over modules with a ``W`` of W.norm(p, dim=0).mean() — reference regularization.py:15-23."""
+    ws = [w for _, module in model.named_modules() for w in (getattr(module, "W", None),) if w is not None]
+    if p == 2 and ws and all(w.is_cuda and w.dim() == 3 for w in ws) and len(ws) <= 256:
+        return ops.weight_regularization_l2(ws)              # one fused kernel pair (csrc/regularizer.cu)
     reg = 0.0
-    for _, module in model.named_modules():
-        w = getattr(module, "W", None)
-        if w is not None:
-            reg = reg + w.norm(p=p, dim=0).mean()
+    for w in ws:
+        reg = reg + w.norm(p=p, dim=0).mean()
     return reg
 
 

@@ -45,7 +45,7 @@ PROFILE = _Profile()
 _KERNELS = {"phc_csr_build": 6, "phc_segment_ptr_build": 2, "phc_aggregate_fwd": 1, "phc_aggregate_bwd": 2,
             "phc_segment_pool_fwd": 1, "phc_segment_pool_bwd": 1, "phc_bn_act_drop_skip_fwd": 3, "phc_bn_act_drop_skip_bwd": 3,
             "phc_embed_sum_fwd": 1, "phc_embed_sum_bwd": 2, "phc_linear_encoder_fwd": 1, "phc_linear_encoder_bwd": 2,
-            "phc_phm_linear_fwd": 1, "phc_phm_linear_bwd": 6}
+            "phc_phm_linear_fwd": 2, "phc_phm_linear_bwd": 8, "phc_weight_reg_fwd": 2, "phc_weight_reg_bwd": 1}
 
 
 def run(name: str, device, *args, tag: str = ""):
@@ -399,3 +399,42 @@ def linear_encoder(feat: torch.Tensor, weights: Sequence[torch.Tensor], biases: 
     """out[r, c*Fc+f] = feat[r,:] @ weights[c][f,:] + biases[c][f]."""
     n = len(weights)
     return _LinearEncoder.apply(feat.to(torch.float32), n, *weights, *biases)
+
+
+# --------------------------------------------------------------------------------- weight regulariser
+class _WeightReg(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, *weights):
+        lib = _lib.load()
+        dev = weights[0].device
+        ws_ = [_f32c(w, "W") for w in weights]
+        cnt = len(ws_)
+        ns = (ctypes.c_int * cnt)(*[w.size(0) for w in ws_])
+        kps = (ctypes.c_int * cnt)(*[w.size(1) * w.size(2) for w in ws_])
+        out = torch.empty((), dtype=torch.float32, device=dev)
+        nb = lib.phc_weight_reg_workspace_bytes(cnt)
+        ws = _ws(nb, dev)
+        run("phc_weight_reg_fwd", dev, _ptr_array(ws_), ns, kps, cnt, out.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev))
+        ctx.save_for_backward(*ws_)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        ws_ = ctx.saved_tensors
+        dev = ws_[0].device
+        cnt = len(ws_)
+        g = _f32c(g, "grad_output")
+        flat = torch.empty(sum(w.numel() for w in ws_), dtype=torch.float32, device=dev)
+        grads, o = [], 0
+        for w in ws_:
+            grads.append(flat[o:o + w.numel()].view(w.shape))
+            o += w.numel()
+        ns = (ctypes.c_int * cnt)(*[w.size(0) for w in ws_])
+        kps = (ctypes.c_int * cnt)(*[w.size(1) * w.size(2) for w in ws_])
+        run("phc_weight_reg_bwd", dev, g.data_ptr(), _ptr_array(ws_), _ptr_array(grads), ns, kps, cnt, _stream(dev))
+        return tuple(grads)
+
+
+def weight_regularization_l2(weights: Sequence[torch.Tensor]) -> torch.Tensor:
+    """sum_l W_l.norm(p=2, dim=0).mean() over [n,K,P] weight tensors, one fused launch pair."""
+    return _WeightReg.apply(*weights)

@@ -291,3 +291,25 @@ def test_phm_linear_known_answers(ops_golden):
         y.backward(t["gy"])
         for got, want in ((t["x"].grad, fx["gx"]), (t["A"].grad, fx["gA"]), (t["W"].grad, fx["gW"]), (t["b"].grad, fx["gb"])):
             assert_close(got.cpu(), want, RTOL, grad_tol(want, RTOL), key)
+
+
+def test_weight_regulariser():
+    from phc.hypercomplex.layers import PHMLinear
+    from phc.hypercomplex.regularization import phm_weight_regularization
+    torch.manual_seed(0)
+    m = torch.nn.Sequential(PHMLinear(16, 24, 4), PHMLinear(24, 8, 4), PHMLinear(10, 6, 2), PHMLinear(500, 500, 4)).to(DEV)
+    with torch.no_grad():
+        m[0].W[:, 0, 0] = 0.0                                  # zero-norm column: gradient must be 0, not NaN
+    reg = phm_weight_regularization(m, p=2)
+    (3.0 * reg).backward()
+    ref = 0.0
+    ws = [l.W.detach().double().cpu().requires_grad_(True) for l in m]
+    for w in ws:
+        ref = ref + w.norm(p=2, dim=0).mean()
+    (3.0 * ref).backward()
+    assert_close(reg.detach().cpu(), ref.detach().float(), RTOL, 1e-6, "reg")
+    for l, w in zip(m, ws):
+        g = torch.nan_to_num(w.grad.float())
+        assert_close(l.W.grad.cpu(), g, RTOL, grad_tol(g, RTOL), "dW")
+    r1 = phm_weight_regularization(m, p=1)                      # other norms take the generic path
+    assert torch.isfinite(r1)
