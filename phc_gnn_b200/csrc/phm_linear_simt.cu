@@ -219,12 +219,73 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __rest
   for (int r = r0; r < r1; ++r) s += G[(size_t)r * F + f];
   part[(size_t)blockIdx.y * F + f] = s;
 }
+// one warp per column: lane l sums chunks l, l+32, ... in order, then a fixed butterfly
 __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ part, int chunks, int F, float* __restrict__ out) {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (f >= F) return;
   float s = 0.f;
-  for (int c = 0; c < chunks; ++c) s += part[(size_t)c * F + f];
-  out[f] = s;
+  for (int c = lane; c < chunks; c += 32) s += part[(size_t)c * F + f];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[f] = s;
+}
+
+// Fast contraction for small phm_dim (N <= 4): every thread keeps its N^3 dA contributions in registers and the
+// block reduces them once at the end (fixed order: shuffle butterfly, then warps 0..7).
+template <int N>
+__global__ void __launch_bounds__(256) phm_contract_small_kernel(const float* __restrict__ part, int splits, const float* __restrict__ A,
+                                                                 const float* __restrict__ W, int K, int P, float* __restrict__ dW,
+                                                                 float* __restrict__ dA_part) {
+  constexpr int N3 = N * N * N;
+  __shared__ float As[N3];
+  __shared__ float red[8][N3];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < N3; i += 256) As[i] = A[i];
+  __syncthreads();
+  const int In = N * K, Out = N * P;
+  const long long t = (long long)blockIdx.x * 256 + tid;
+  const bool active = t < (long long)K * P;
+  const int k = active ? (int)(t / P) : 0, p = active ? (int)(t % P) : 0;
+  float dw[N], da[N3], w[N];
+#pragma unroll
+  for (int b = 0; b < N; ++b) { dw[b] = 0.f; w[b] = active ? __ldg(W + ((size_t)b * K + k) * P + p) : 0.f; }
+#pragma unroll
+  for (int i = 0; i < N3; ++i) da[i] = 0.f;
+#pragma unroll
+  for (int a = 0; a < N; ++a) {
+#pragma unroll
+    for (int c = 0; c < N; ++c) {
+      float dh = 0.f;
+      if (active) {
+        const size_t off = (size_t)(a * K + k) * Out + (c * P + p);
+        for (int s = 0; s < splits; ++s) dh += part[(size_t)s * In * Out + off];
+      }
+#pragma unroll
+      for (int b = 0; b < N; ++b) {
+        dw[b] += As[(b * N + a) * N + c] * dh;
+        da[(b * N + a) * N + c] = w[b] * dh;
+      }
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int b = 0; b < N; ++b) dW[((size_t)b * K + k) * P + p] = dw[b];
+  }
+#pragma unroll
+  for (int i = 0; i < N3; ++i) {
+    float v = da[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp][i] = v;
+  }
+  __syncthreads();
+  if (tid < N3) {
+    float s = 0.f;
+#pragma unroll
+    for (int wi = 0; wi < 8; ++wi) s += red[wi][tid];
+    dA_part[(size_t)blockIdx.x * N3 + tid] = s;
+  }
 }
 
 int dh_splits(int M, int In, int Out) {
@@ -254,14 +315,20 @@ int phm_contract_and_bias(const float* part, int splits, const float* gy, const 
   const int cblocks = phc_div_up((long long)K * P, 256);
   float* da_part = scratch;
   float* cs_part = scratch + (size_t)cblocks * n3;
-  phm_contract_kernel<<<cblocks, 256, sizeof(float) * (n3 + 8), stream>>>(part, splits, A, W, n, K, P, dW, da_part);
+  switch (n) {
+    case 1: phm_contract_small_kernel<1><<<cblocks, 256, 0, stream>>>(part, splits, A, W, K, P, dW, da_part); break;
+    case 2: phm_contract_small_kernel<2><<<cblocks, 256, 0, stream>>>(part, splits, A, W, K, P, dW, da_part); break;
+    case 3: phm_contract_small_kernel<3><<<cblocks, 256, 0, stream>>>(part, splits, A, W, K, P, dW, da_part); break;
+    case 4: phm_contract_small_kernel<4><<<cblocks, 256, 0, stream>>>(part, splits, A, W, K, P, dW, da_part); break;
+    default: phm_contract_kernel<<<cblocks, 256, sizeof(float) * (n3 + 8), stream>>>(part, splits, A, W, n, K, P, dW, da_part);
+  }
   if (dA) phm_dA_final_kernel<<<phc_div_up(n3, 256), 256, 0, stream>>>(da_part, cblocks, n3, dA);
   if (db) {
     const int chunks = colsum_chunks(M);
     const int rpc = phc_div_up(M > 0 ? M : 1, chunks);
     dim3 g3(phc_div_up(out_features, 256), chunks);
     colsum_partial_kernel<<<g3, 256, 0, stream>>>(gy, M, out_features, rpc, cs_part);
-    colsum_final_kernel<<<phc_div_up(out_features, 256), 256, 0, stream>>>(cs_part, chunks, out_features, db);
+    colsum_final_kernel<<<phc_div_up((long long)out_features * 32, 256), 256, 0, stream>>>(cs_part, chunks, out_features, db);
   }
   return phc_check_launch("phm_contract_and_bias");
 }

@@ -791,6 +791,116 @@ __global__ void __launch_bounds__(THREADS, 1) phm_tc_dh_kernel(const DhParams p)
   cta_epilogue(tmem_base);
 }
 
+// ---------------------------------------------------------------------------- dH kernel, TMA-staged
+// Raw [32 samples x 128 features] boxes of x and dy arrive by TMA; the producers transpose them out of shared
+// memory (4 strided LDS per 16-byte K-unit, conflict-free) into the K-major UMMA operands.
+constexpr int DH_RAW_STAGES = 2;
+constexpr int DH_RAW_BYTES = 2 * BK * BM * 4;     // x box + dy box = 32 KiB
+constexpr int DH_TMA_THREADS = (MMA_WARP + 2) * 32;
+
+__global__ void __launch_bounds__(DH_TMA_THREADS, 1) phm_tc_dh_tma_kernel(const DhParams p, const __grid_constant__ CUtensorMap tmapX,
+                                                                         const __grid_constant__ CUtensorMap tmapG) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  Smem s;
+  s.stages = base;
+  uint8_t* rawbuf = base + TMA_OP_STAGES * STAGE_BYTES;
+  s.scratch = reinterpret_cast<float*>(rawbuf + DH_RAW_STAGES * DH_RAW_BYTES);
+  s.coef = s.scratch + EPI_WARPS * 32 * 33;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s.coef);
+  s.full_bar = bars;                         // [2]
+  s.empty_bar = bars + 2;                    // [2]
+  uint64_t* rfull_bar = bars + 4;            // [2]
+  uint64_t* rempty_bar = bars + 6;           // [2]
+  s.tfull_bar = bars + 8;
+  s.tempty_bar = bars + 10;
+  s.tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TMA_OP_STAGES; ++i) {
+      mbar_init(smem_u32(&s.full_bar[i]), PROD_WARPS);
+      mbar_init(smem_u32(&s.empty_bar[i]), 1);
+    }
+    for (int i = 0; i < DH_RAW_STAGES; ++i) {
+      mbar_init(smem_u32(&rfull_bar[i]), 1);
+      mbar_init(smem_u32(&rempty_bar[i]), PROD_WARPS);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&s.tfull_bar[b]), 1);
+      mbar_init(smem_u32(&s.tempty_bar[b]), EPI_WARPS * 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == MMA_WARP) tmem_alloc(smem_u32(s.tmem_slot), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s.tmem_slot;
+
+  if (warp < EPI_WARP0) {
+    const int ptid = threadIdx.x;
+    const int half = ptid >> 8, q = ptid & 255;          // first 256 threads: A (x^T), others: B (dy^T)
+    int g = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      int i0, o0, split, kbeg, kend;
+      dh_tile(p, t, i0, o0, split, kbeg, kend);
+      for (int k0 = kbeg; k0 < kend; k0 += BK, ++g) {
+        const int rs = g % DH_RAW_STAGES, os = g % TMA_OP_STAGES;
+        mbar_wait(smem_u32(&rfull_bar[rs]), (g / DH_RAW_STAGES) & 1);
+        mbar_wait(smem_u32(&s.empty_bar[os]), ((g / TMA_OP_STAGES) & 1) ^ 1);
+        const float* raw = reinterpret_cast<const float*>(rawbuf + rs * DH_RAW_BYTES + half * (BK * BM * 4));
+        uint8_t* sb = s.stages + os * STAGE_BYTES + half * 2 * TILE_BYTES;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int u = i * 256 + q;
+          const int f = u & (BM - 1), ku = u >> 7;
+          const float v[4] = {raw[(ku * 4 + 0) * BM + f], raw[(ku * 4 + 1) * BM + f], raw[(ku * 4 + 2) * BM + f],
+                              raw[(ku * 4 + 3) * BM + f]};
+          store_unit(sb, sb + TILE_BYTES, f, ku, v);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(smem_u32(&s.full_bar[os]));
+          mbar_arrive(smem_u32(&rempty_bar[rs]));
+        }
+      }
+    }
+  } else if (warp == MMA_WARP + 1) {
+    if (lane == 0) {
+      int g = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        int i0, o0, split, kbeg, kend;
+        dh_tile(p, t, i0, o0, split, kbeg, kend);
+        for (int k0 = kbeg; k0 < kend; k0 += BK, ++g) {
+          const int rs = g % DH_RAW_STAGES;
+          mbar_wait(smem_u32(&rempty_bar[rs]), ((g / DH_RAW_STAGES) & 1) ^ 1);
+          const uint32_t bar = smem_u32(&rfull_bar[rs]);
+          mbar_arrive_expect_tx(bar, DH_RAW_BYTES);
+          tma_load_2d(smem_u32(rawbuf + rs * DH_RAW_BYTES), &tmapX, i0, k0, bar);
+          tma_load_2d(smem_u32(rawbuf + rs * DH_RAW_BYTES + BK * BM * 4), &tmapG, o0, k0, bar);
+        }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    int stage = 0, phase = 0, it = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      int i0, o0, split, kbeg, kend;
+      dh_tile(p, t, i0, o0, split, kbeg, kend);
+      mma_tile<TMA_OP_STAGES>(s, tmem_base, it, (kend - kbeg + BK - 1) / BK, stage, phase);
+    }
+  } else {
+    int it = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      int i0, o0, split, kbeg, kend;
+      dh_tile(p, t, i0, o0, split, kbeg, kend);
+      epilogue_tile<false>(s, tmem_base, it, p.C + (size_t)split * p.In * p.Out, p.Out, p.In, i0, o0, min(BN, p.Out - o0), nullptr,
+                           nullptr, 0);
+    }
+  }
+  cta_epilogue(tmem_base);
+}
+
 // ---------------------------------------------------------------------------- pack kernel
 // Writes, for one direction, the rule re-indexed per output component and the W operand as tf32 big/small
 // tile images:  Bpack[pt][chunk][half][q][32]  with element (q, s) = Wsrc(b = s % n, kk = s / n, p = pt*128 + q).
@@ -985,6 +1095,40 @@ int launch_pack(const float* A, const float* W, int n, int K, int P, uint8_t* bu
   return phc_check_launch("phm_pack_kernel");
 }
 
+bool encode_2d(CUtensorMap* tmap, const float* ptr, int rows, int cols, int box_cols, int box_rows) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (enc == nullptr || cols % 4 != 0 || (reinterpret_cast<uintptr_t>(ptr) & 15u) != 0) return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)cols * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+size_t smem_bytes_dh_tma() {
+  return 1024 + (size_t)TMA_OP_STAGES * STAGE_BYTES + (size_t)DH_RAW_STAGES * DH_RAW_BYTES + EPI_SCRATCH + 8 * 16 + 16;
+}
+
+// returns -1 when the TMA path is not applicable
+int try_launch_dh_tma(const DhParams& d, cudaStream_t stream) {
+  static const bool use_tma = getenv("PHC_TC_NO_TMA") == nullptr;
+  if (!use_tma) return -1;
+  CUtensorMap tx, tg;
+  if (!encode_2d(&tx, d.X, d.M, d.In, BM, BK) || !encode_2d(&tg, d.G, d.M, d.Out, BN, BK)) return -1;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(phm_tc_dh_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_dh_tma()) != cudaSuccess) {
+      cudaGetLastError();
+      return -1;
+    }
+    configured = true;
+  }
+  const int grid = d.num_tiles < num_sms() ? d.num_tiles : num_sms();
+  phm_tc_dh_tma_kernel<<<grid, DH_TMA_THREADS, smem_bytes_dh_tma(), stream>>>(d, tx, tg);
+  return phc_check_launch("phm_tc_dh_tma_kernel");
+}
+
 int launch_mix(const MixParams& p, cudaStream_t stream) {
   static const bool use_tma = getenv("PHC_TC_NO_TMA") == nullptr;       // debug switch: force the register-prefetch kernel
   if (use_tma && p.prof == nullptr) {
@@ -1053,12 +1197,15 @@ int phm_tc_bwd(const float* gy, const float* x, const float* A, const float* W, 
   d.tiles_m = phc_div_up(in_features, tc::BM); d.tiles_n = phc_div_up(out_features, tc::BN);
   d.splits = tc::dh_splits(rows, in_features, out_features, &d.rows_per_split);
   d.num_tiles = d.tiles_m * d.tiles_n * d.splits;
-  static bool configured = false;
-  int rc = tc::set_smem(tc::phm_tc_dh_kernel, &configured);
-  if (rc) return rc;
-  const int grid = d.num_tiles < tc::num_sms() ? d.num_tiles : tc::num_sms();
-  tc::phm_tc_dh_kernel<<<grid, tc::THREADS, tc::smem_bytes(0), stream>>>(d);
-  rc = phc_check_launch("phm_tc_dh_kernel");
+  int rc = tc::try_launch_dh_tma(d, stream);
+  if (rc < 0) {
+    static bool configured = false;
+    rc = tc::set_smem(tc::phm_tc_dh_kernel, &configured);
+    if (rc) return rc;
+    const int grid = d.num_tiles < tc::num_sms() ? d.num_tiles : tc::num_sms();
+    tc::phm_tc_dh_kernel<<<grid, tc::THREADS, tc::smem_bytes(0), stream>>>(d);
+    rc = phc_check_launch("phm_tc_dh_kernel");
+  }
   if (rc) return rc;
   float* scratch = part + (size_t)d.splits * in_features * out_features;
   return phm_contract_and_bias(part, d.splits, gy, A, W, dA, dW, db, rows, in_features, out_features, n, scratch, stream);
