@@ -126,6 +126,24 @@ int phc_phm_linear_bwd(const float* gy, const float* x, const float* phm_rule, c
                        float* dbias, int rows, int in_features, int out_features, int phm_dim, int precision, void* workspace,
                        size_t workspace_bytes, phc_stream_t stream);
 
+/* ---- aggregation with the edge encoder fused in (models.py:238-243 + messagepassing.py:72-74,136-138,297-300)
+ * out[i] = (self_loop ? x[i] : 0) + AGG_e act(x[src(e)] + enc(edge_attr[e])); the [E,F] edge embedding is never
+ * materialised.  enc_kind 0: n x Linear(enc_dim -> F/n), edge_attr float [E,enc_dim], params = HOST array of the n
+ * weight pointers ([F/n, enc_dim]) followed by the n bias pointers.  enc_kind 1: integer features int64
+ * [E,enc_dim], vocab[enc_dim], params = n*enc_dim embedding tables ordered [component][column].
+ * table_rows = enc_dim+1 (Linear) or sum(vocab) (embeddings).  bwd writes the parameter gradients through
+ * dparams (same order), dx and dbeta. */
+int phc_conv_fused_supported(int width, int phm_dim, int enc_kind, int enc_dim, int table_rows);
+int phc_conv_fused_fwd(const float* x, const void* edge_attr, int enc_kind, int enc_dim, const int* vocab, const float* const* params,
+                       const int* rowptr, const int* col, const int* perm, int num_nodes, int width, int phm_dim, int reduce,
+                       int msg_act, const float* beta, int self_loop, float* out, float* aux_f, int* aux_i, phc_stream_t stream);
+size_t phc_conv_fused_bwd_workspace_bytes(int num_nodes, int width, int table_rows);
+int phc_conv_fused_bwd(const float* gout, const float* x, const void* edge_attr, int enc_kind, int enc_dim, const int* vocab,
+                       const float* const* params, float* const* dparams, const float* aux_f, const int* aux_i, const int* rowptr,
+                       const int* col, const int* perm, const int* rowptr_t, const int* col_t, const int* perm_t, int num_nodes,
+                       int width, int phm_dim, int reduce, int msg_act, const float* beta, int self_loop, float* dx, float* dbeta,
+                       void* workspace, size_t workspace_bytes, phc_stream_t stream);
+
 /* ---- weight regulariser (regularization.py:15-23): out = sum_l mean_{k,p} ||W_l[:,k,p]||_2 ------------
  * weights / dweights: HOST arrays of device pointers to the [n_l, K_l, P_l] weight tensors; kp[l] = K_l*P_l. */
 size_t phc_weight_reg_workspace_bytes(int count);

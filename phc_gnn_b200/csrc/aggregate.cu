@@ -341,6 +341,14 @@ bool vec_ok(int F, const void* a, const void* b, const void* c, const void* d) {
 
 }  // namespace
 
+// input gradient of the sum/mean + identity-message case (no edge features needed) — shared with conv_fused.cu
+int phc_aggregate_bwd_node_simple(bool mean, const float* g, const int* rowptr, const int* rowptr_t, const int* col_t, const int* perm_t,
+                                  int N, int F, int self_loop, float* dx, cudaStream_t stream) {
+  if (F % 4 == 0 && phc_aligned16(g) && phc_aligned16(dx))
+    return dispatch_bwd_node<4>(true, mean, g, nullptr, rowptr, rowptr_t, col_t, perm_t, N, F, self_loop, dx, stream);
+  return dispatch_bwd_node<1>(true, mean, g, nullptr, rowptr, rowptr_t, col_t, perm_t, N, F, self_loop, dx, stream);
+}
+
 extern "C" {
 
 int phc_aggregate_fwd(const float* x, const float* ea, const int* rowptr, const int* col, const int* perm, int num_nodes, int width,

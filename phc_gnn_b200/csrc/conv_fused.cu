@@ -1,0 +1,501 @@
+// Neighbour aggregation with the per-layer bond/edge ENCODER fused in:
+//
+//   out[i,:] = (self ? x[i,:] : 0) + AGG_{e: dst(e)=i} phi( x[src(e),:] + enc(edge_attr[e]) )
+//   enc = n x Linear(D -> F/n) (float edge features)  or  n x sum of per-column embeddings (integer features)
+//
+// Replaces reference phc/hypercomplex/undirectional/models.py:238-243 (bondencoders[i](edge_attr) -> [E,F] tensor
+// -> conv) + messagepassing.py:72-74,136-138,297-300.  The [E,F] edge embedding is never written: each block keeps
+// the encoder parameters as a small [R,F] table in shared memory (R = D+1 rows for Linear incl. bias, total
+// vocabulary for embeddings) and rebuilds an edge's embedding from its D raw features (28 B instead of 2000 B per
+// edge at ppa shape).  Backward never writes the [E,F] edge gradient either: encoder-parameter gradients are
+// accumulated per block in shared memory (one private column per thread, one slot per concurrently processed row;
+// no atomics) and block partials are summed in block order.
+// Roofline: the x[src] row gather (E*F*4 bytes, served by L2 — x is N*F*4 = 31 MB) instead of HBM streaming.
+#include "common.cuh"
+#include <float.h>
+
+// simple (sum/mean, identity message) input gradient lives in aggregate.cu
+int phc_aggregate_bwd_node_simple(bool mean, const float* g, const int* rowptr, const int* rowptr_t, const int* col_t, const int* perm_t,
+                                  int N, int F, int self_loop, float* dx, cudaStream_t stream);
+
+#define ENC_LINEAR 0
+#define ENC_EMBED 1
+#define ENC_MAX_COLS 16
+#define ENC_MAX_PTRS 128
+
+struct EncDesc {
+  int kind, D, R, Fc, n;            // D: Linear input width / number of integer columns; R: table rows
+  int voff[ENC_MAX_COLS], vsz[ENC_MAX_COLS];
+  const float* p[ENC_MAX_PTRS];     // Linear: weights[c] (c < n) then biases[n + c]; embed: tables[c*D + col]
+  float* dp[ENC_MAX_PTRS];          // gradients, same order (backward only)
+};
+
+namespace {
+
+template <int RED> struct Acc {
+  float a, s, t;
+  int arg;
+  __device__ __forceinline__ void init() {
+    a = (RED == PHC_RED_MAX || RED == PHC_RED_SOFTMAX) ? -INFINITY : (RED == PHC_RED_MIN ? INFINITY : 0.f);
+    s = 0.f; t = 0.f; arg = -1;
+  }
+  __device__ __forceinline__ void push(float m, int e, float beta) {
+    if (RED == PHC_RED_SUM || RED == PHC_RED_MEAN) a += m;
+    else if (RED == PHC_RED_MAX) { if (m > a) { a = m; arg = e; } }
+    else if (RED == PHC_RED_MIN) { if (m < a) { a = m; arg = e; } }
+    else {
+      const float sc = beta * m;
+      if (sc > a) { const float r = expf(a - sc); s = s * r + 1.f; t = t * r + m; a = sc; }
+      else { const float w = expf(sc - a); s += w; t += w * m; }
+    }
+  }
+};
+
+// cooperative load of the encoder table into shared memory: tab[r*F + f]
+__device__ void load_table(const EncDesc& enc, int F, float* tab) {
+  for (int idx = threadIdx.x; idx < enc.R * F; idx += blockDim.x) {
+    const int r = idx / F, f = idx - r * F;
+    const int c = f / enc.Fc, fp = f - c * enc.Fc;
+    float v;
+    if (enc.kind == ENC_LINEAR) {
+      if (r < enc.D) v = __ldg(enc.p[c] + (size_t)fp * enc.D + r);
+      else v = enc.p[enc.n + c] ? __ldg(enc.p[enc.n + c] + fp) : 0.f;
+    } else {
+      int col = 0;
+      while (col + 1 < enc.D && enc.voff[col + 1] <= r) ++col;
+      v = __ldg(enc.p[c * enc.D + col] + (size_t)(r - enc.voff[col]) * enc.Fc + fp);
+    }
+    tab[idx] = v;
+  }
+}
+
+// edge embedding for 4 features starting at f
+__device__ __forceinline__ void edge_embed(const EncDesc& enc, const float* tab, int F, const void* attr, int e, int f, float (&ev)[4]) {
+  if (enc.kind == ENC_LINEAR) {
+    const float4 b = *reinterpret_cast<const float4*>(tab + (size_t)enc.D * F + f);
+    ev[0] = b.x; ev[1] = b.y; ev[2] = b.z; ev[3] = b.w;
+    const float* a = reinterpret_cast<const float*>(attr) + (size_t)e * enc.D;
+    for (int d = 0; d < enc.D; ++d) {
+      const float av = __ldg(a + d);
+      const float4 w = *reinterpret_cast<const float4*>(tab + (size_t)d * F + f);
+      ev[0] += av * w.x; ev[1] += av * w.y; ev[2] += av * w.z; ev[3] += av * w.w;
+    }
+  } else {
+    ev[0] = ev[1] = ev[2] = ev[3] = 0.f;
+    const long long* a = reinterpret_cast<const long long*>(attr) + (size_t)e * enc.D;
+    for (int col = 0; col < enc.D; ++col) {
+      long long v = __ldg(a + col);
+      v = v < 0 ? 0 : (v >= enc.vsz[col] ? enc.vsz[col] - 1 : v);
+      const float4 w = *reinterpret_cast<const float4*>(tab + (size_t)(enc.voff[col] + (int)v) * F + f);
+      ev[0] += w.x; ev[1] += w.y; ev[2] += w.z; ev[3] += w.w;
+    }
+  }
+}
+
+template <int RED>
+__global__ void conv_fwd_kernel(const EncDesc enc, const float* __restrict__ x, const void* __restrict__ attr, const int* __restrict__ rowptr,
+                                const int* __restrict__ col, const int* __restrict__ perm, int N, int F, int rpi, int act,
+                                const float* __restrict__ beta_ptr, int self_loop, float* __restrict__ out, float* __restrict__ aux_f,
+                                int* __restrict__ aux_i) {
+  extern __shared__ __align__(16) float tab[];
+  load_table(enc, F, tab);
+  __syncthreads();
+  const int fv = F / 4;
+  const int slot = threadIdx.x / fv, f = (threadIdx.x - slot * fv) * 4;
+  const float beta = (RED == PHC_RED_SOFTMAX) ? __ldg(beta_ptr) : 0.f;
+  const bool has_act = act != PHC_ACT_IDENTITY;
+  for (int i = blockIdx.x * rpi + slot; i < N; i += gridDim.x * rpi) {
+    const int beg = rowptr[i], end = rowptr[i + 1];
+    Acc<RED> acc[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q].init();
+    int k = beg;
+    for (; k + 2 <= end; k += 2) {                 // two edges in flight
+      const int j0 = __ldg(col + k), e0 = __ldg(perm + k), j1 = __ldg(col + k + 1), e1 = __ldg(perm + k + 1);
+      const float4 x0 = *reinterpret_cast<const float4*>(x + (size_t)j0 * F + f);
+      const float4 x1 = *reinterpret_cast<const float4*>(x + (size_t)j1 * F + f);
+      float v0[4], v1[4];
+      edge_embed(enc, tab, F, attr, e0, f, v0);
+      edge_embed(enc, tab, F, attr, e1, f, v1);
+      const float m0[4] = {x0.x + v0[0], x0.y + v0[1], x0.z + v0[2], x0.w + v0[3]};
+      const float m1[4] = {x1.x + v1[0], x1.y + v1[1], x1.z + v1[2], x1.w + v1[3]};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q].push(has_act ? act_fwd_rt(act, m0[q]) : m0[q], e0, beta);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q].push(has_act ? act_fwd_rt(act, m1[q]) : m1[q], e1, beta);
+    }
+    for (; k < end; ++k) {
+      const int j0 = __ldg(col + k), e0 = __ldg(perm + k);
+      const float4 x0 = *reinterpret_cast<const float4*>(x + (size_t)j0 * F + f);
+      float v0[4];
+      edge_embed(enc, tab, F, attr, e0, f, v0);
+      const float m0[4] = {x0.x + v0[0], x0.y + v0[1], x0.z + v0[2], x0.w + v0[3]};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q].push(has_act ? act_fwd_rt(act, m0[q]) : m0[q], e0, beta);
+    }
+    const int deg = end - beg;
+    float o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (RED == PHC_RED_SUM) o[q] = acc[q].a;
+      else if (RED == PHC_RED_MEAN) o[q] = acc[q].a / (float)max(deg, 1);
+      else if (RED == PHC_RED_MAX || RED == PHC_RED_MIN) o[q] = deg > 0 ? acc[q].a : 0.f;
+      else o[q] = deg > 0 ? acc[q].t / (acc[q].s + 1e-12f) : 0.f;
+    }
+    const size_t off = (size_t)i * F + f;
+    if (RED == PHC_RED_SOFTMAX) {
+      float4 lse;
+      lse.x = deg > 0 ? acc[0].a + logf(acc[0].s + 1e-12f) : 0.f; lse.y = deg > 0 ? acc[1].a + logf(acc[1].s + 1e-12f) : 0.f;
+      lse.z = deg > 0 ? acc[2].a + logf(acc[2].s + 1e-12f) : 0.f; lse.w = deg > 0 ? acc[3].a + logf(acc[3].s + 1e-12f) : 0.f;
+      *reinterpret_cast<float4*>(aux_f + off) = lse;
+      *reinterpret_cast<float4*>(aux_f + (size_t)N * F + off) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+    if (RED == PHC_RED_MAX || RED == PHC_RED_MIN)
+      *reinterpret_cast<int4*>(aux_i + off) = make_int4(acc[0].arg, acc[1].arg, acc[2].arg, acc[3].arg);
+    if (self_loop) {
+      const float4 xi = *reinterpret_cast<const float4*>(x + off);
+      o[0] += xi.x; o[1] += xi.y; o[2] += xi.z; o[3] += xi.w;
+    }
+    *reinterpret_cast<float4*>(out + off) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// per-edge d(pre) for 4 features (shared by both backward kernels)
+template <int RED>
+__device__ __forceinline__ void edge_dpre(int act, bool need_pre, float beta, const float (&pre)[4], const float (&g)[4],
+                                          const float (&lse)[4], const float (&agg)[4], const int (&arg)[4], int e, float (&d)[4],
+                                          float& dbeta) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float dm;
+    if (RED == PHC_RED_SUM || RED == PHC_RED_MEAN) dm = g[q];
+    else if (RED == PHC_RED_MAX || RED == PHC_RED_MIN) dm = (arg[q] == e) ? g[q] : 0.f;
+    else {
+      const float m = act != PHC_ACT_IDENTITY ? act_fwd_rt(act, pre[q]) : pre[q];
+      const float w = expf(beta * m - lse[q]);
+      const float c = m - agg[q];
+      dm = g[q] * w * (1.f + beta * c);
+      dbeta += g[q] * w * m * c;
+    }
+    d[q] = (need_pre && act != PHC_ACT_IDENTITY) ? dm * act_bwd_rt(act, pre[q]) : dm;
+  }
+}
+
+// encoder-parameter gradients + d(beta): by target rows, shared-memory accumulators, block partials
+template <int RED>
+__global__ void conv_bwd_param_kernel(const EncDesc enc, const float* __restrict__ g, const float* __restrict__ x,
+                                      const void* __restrict__ attr, const float* __restrict__ aux_f, const int* __restrict__ aux_i,
+                                      const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ perm, int N,
+                                      int F, int rpi, int act, const float* __restrict__ beta_ptr, float* __restrict__ part,
+                                      float* __restrict__ dbeta_part) {
+  extern __shared__ __align__(16) float smem[];
+  float* tab = smem;                            // [R][F]
+  float* accs = smem + (size_t)enc.R * F;       // [rpi][R][F]
+  load_table(enc, F, tab);
+  for (int idx = threadIdx.x; idx < rpi * enc.R * F; idx += blockDim.x) accs[idx] = 0.f;
+  __syncthreads();
+  const int fv = F / 4;
+  const int slot = threadIdx.x / fv, f = (threadIdx.x - slot * fv) * 4;
+  float* mine = accs + (size_t)slot * enc.R * F;
+  const float beta = (RED == PHC_RED_SOFTMAX) ? __ldg(beta_ptr) : 0.f;
+  const bool need_pre = act != PHC_ACT_IDENTITY || RED == PHC_RED_SOFTMAX;
+  float db = 0.f;
+  for (int i = blockIdx.x * rpi + slot; i < N; i += gridDim.x * rpi) {
+    const int beg = rowptr[i], end = rowptr[i + 1];
+    const size_t off = (size_t)i * F + f;
+    const float4 g4 = *reinterpret_cast<const float4*>(g + off);
+    float gi[4] = {g4.x, g4.y, g4.z, g4.w};
+    float lse[4] = {0.f, 0.f, 0.f, 0.f}, agg[4] = {0.f, 0.f, 0.f, 0.f};
+    int arg[4] = {-1, -1, -1, -1};
+    if (RED == PHC_RED_SOFTMAX) {
+      const float4 l = *reinterpret_cast<const float4*>(aux_f + off), a = *reinterpret_cast<const float4*>(aux_f + (size_t)N * F + off);
+      lse[0] = l.x; lse[1] = l.y; lse[2] = l.z; lse[3] = l.w;
+      agg[0] = a.x; agg[1] = a.y; agg[2] = a.z; agg[3] = a.w;
+    }
+    if (RED == PHC_RED_MAX || RED == PHC_RED_MIN) {
+      const int4 a = *reinterpret_cast<const int4*>(aux_i + off);
+      arg[0] = a.x; arg[1] = a.y; arg[2] = a.z; arg[3] = a.w;
+    }
+    if (RED == PHC_RED_MEAN) {
+      const float inv = 1.f / (float)max(end - beg, 1);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) gi[q] *= inv;
+    }
+    for (int k = beg; k < end; ++k) {
+      const int e = __ldg(perm + k);
+      float pre[4] = {0.f, 0.f, 0.f, 0.f};
+      if (need_pre) {
+        const int j = __ldg(col + k);
+        const float4 xv = *reinterpret_cast<const float4*>(x + (size_t)j * F + f);
+        float ev[4];
+        edge_embed(enc, tab, F, attr, e, f, ev);
+        pre[0] = xv.x + ev[0]; pre[1] = xv.y + ev[1]; pre[2] = xv.z + ev[2]; pre[3] = xv.w + ev[3];
+      }
+      float d[4];
+      edge_dpre<RED>(act, need_pre, beta, pre, gi, lse, agg, arg, e, d, db);
+      if (enc.kind == ENC_LINEAR) {
+        const float* a = reinterpret_cast<const float*>(attr) + (size_t)e * enc.D;
+        for (int dd = 0; dd < enc.D; ++dd) {
+          const float av = __ldg(a + dd);
+          float4* p = reinterpret_cast<float4*>(mine + (size_t)dd * F + f);
+          float4 t = *p;
+          t.x += av * d[0]; t.y += av * d[1]; t.z += av * d[2]; t.w += av * d[3];
+          *p = t;
+        }
+        float4* p = reinterpret_cast<float4*>(mine + (size_t)enc.D * F + f);
+        float4 t = *p;
+        t.x += d[0]; t.y += d[1]; t.z += d[2]; t.w += d[3];
+        *p = t;
+      } else {
+        const long long* a = reinterpret_cast<const long long*>(attr) + (size_t)e * enc.D;
+        for (int cc = 0; cc < enc.D; ++cc) {
+          long long v = __ldg(a + cc);
+          v = v < 0 ? 0 : (v >= enc.vsz[cc] ? enc.vsz[cc] - 1 : v);
+          float4* p = reinterpret_cast<float4*>(mine + (size_t)(enc.voff[cc] + (int)v) * F + f);
+          float4 t = *p;
+          t.x += d[0]; t.y += d[1]; t.z += d[2]; t.w += d[3];
+          *p = t;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // block partial: slots summed in slot order
+  float* dst = part + (size_t)blockIdx.x * enc.R * F;
+  for (int idx = threadIdx.x; idx < enc.R * F; idx += blockDim.x) {
+    float s = 0.f;
+    for (int sl = 0; sl < rpi; ++sl) s += accs[(size_t)sl * enc.R * F + idx];
+    dst[idx] = s;
+  }
+  if (RED == PHC_RED_SOFTMAX) {
+    __syncthreads();
+    float* red = accs;                 // reuse
+    red[threadIdx.x] = db;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+      for (int t = 0; t < (int)blockDim.x; ++t) s += red[t];
+      dbeta_part[blockIdx.x] = s;
+    }
+  }
+}
+
+// sum block partials in block order and scatter into the individual parameter gradients
+__global__ void __launch_bounds__(256) conv_bwd_param_final_kernel(const EncDesc enc, const float* __restrict__ part, int blocks, int F) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)enc.R * F) return;
+  const int r = (int)(t / F), f = (int)(t - (long long)r * F);
+  float s = 0.f;
+  for (int b = 0; b < blocks; ++b) s += part[((size_t)b * enc.R + r) * F + f];
+  const int c = f / enc.Fc, fp = f - c * enc.Fc;
+  if (enc.kind == ENC_LINEAR) {
+    if (r < enc.D) enc.dp[c][(size_t)fp * enc.D + r] = s;
+    else if (enc.dp[enc.n + c]) enc.dp[enc.n + c][fp] = s;
+  } else {
+    int col = 0;
+    while (col + 1 < enc.D && enc.voff[col + 1] <= r) ++col;
+    enc.dp[c * enc.D + col][(size_t)(r - enc.voff[col]) * enc.Fc + fp] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restrict__ part, int n, float* __restrict__ out) {
+  __shared__ float red[256];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) s += part[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int k = 128; k > 0; k >>= 1) {
+    if ((int)threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = red[0];
+}
+
+// input gradient, general case (message activation and/or max/min/softmax): by source rows, recomputes d(pre)
+template <int RED>
+__global__ void conv_bwd_node_kernel(const EncDesc enc, const float* __restrict__ g, const float* __restrict__ x,
+                                     const void* __restrict__ attr, const float* __restrict__ aux_f, const int* __restrict__ aux_i,
+                                     const int* __restrict__ rowptr, const int* __restrict__ rowptr_t, const int* __restrict__ col_t,
+                                     const int* __restrict__ perm_t, int N, int F, int rpi, int act, const float* __restrict__ beta_ptr,
+                                     int self_loop, float* __restrict__ dx) {
+  extern __shared__ __align__(16) float tab[];
+  load_table(enc, F, tab);
+  __syncthreads();
+  const int fv = F / 4;
+  const int slot = threadIdx.x / fv, f = (threadIdx.x - slot * fv) * 4;
+  const float beta = (RED == PHC_RED_SOFTMAX) ? __ldg(beta_ptr) : 0.f;
+  const bool need_pre = act != PHC_ACT_IDENTITY || RED == PHC_RED_SOFTMAX;
+  float unused = 0.f;
+  for (int j = blockIdx.x * rpi + slot; j < N; j += gridDim.x * rpi) {
+    const size_t offj = (size_t)j * F + f;
+    const float4 xj = *reinterpret_cast<const float4*>(x + offj);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (self_loop) {
+      const float4 gj = *reinterpret_cast<const float4*>(g + offj);
+      acc[0] = gj.x; acc[1] = gj.y; acc[2] = gj.z; acc[3] = gj.w;
+    }
+    for (int k = rowptr_t[j]; k < rowptr_t[j + 1]; ++k) {
+      const int e = __ldg(perm_t + k), i = __ldg(col_t + k);
+      const size_t offi = (size_t)i * F + f;
+      const float4 g4 = *reinterpret_cast<const float4*>(g + offi);
+      float gi[4] = {g4.x, g4.y, g4.z, g4.w};
+      float lse[4] = {0.f, 0.f, 0.f, 0.f}, agg[4] = {0.f, 0.f, 0.f, 0.f};
+      int arg[4] = {-1, -1, -1, -1};
+      if (RED == PHC_RED_SOFTMAX) {
+        const float4 l = *reinterpret_cast<const float4*>(aux_f + offi), a = *reinterpret_cast<const float4*>(aux_f + (size_t)N * F + offi);
+        lse[0] = l.x; lse[1] = l.y; lse[2] = l.z; lse[3] = l.w;
+        agg[0] = a.x; agg[1] = a.y; agg[2] = a.z; agg[3] = a.w;
+      }
+      if (RED == PHC_RED_MAX || RED == PHC_RED_MIN) {
+        const int4 a = *reinterpret_cast<const int4*>(aux_i + offi);
+        arg[0] = a.x; arg[1] = a.y; arg[2] = a.z; arg[3] = a.w;
+      }
+      if (RED == PHC_RED_MEAN) {
+        const float inv = 1.f / (float)max(__ldg(rowptr + i + 1) - __ldg(rowptr + i), 1);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) gi[q] *= inv;
+      }
+      float pre[4] = {0.f, 0.f, 0.f, 0.f};
+      if (need_pre) {
+        float ev[4];
+        edge_embed(enc, tab, F, attr, e, f, ev);
+        pre[0] = xj.x + ev[0]; pre[1] = xj.y + ev[1]; pre[2] = xj.z + ev[2]; pre[3] = xj.w + ev[3];
+      }
+      float d[4];
+      edge_dpre<RED>(act, need_pre, beta, pre, gi, lse, agg, arg, e, d, unused);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q] += d[q];
+    }
+    *reinterpret_cast<float4*>(dx + offj) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  }
+}
+
+int make_desc(EncDesc& d, int kind, int dim, const int* vocab, const float* const* params, float* const* dparams, int n, int F) {
+  d.kind = kind; d.D = dim; d.n = n; d.Fc = F / n;
+  const int nptr = kind == ENC_LINEAR ? 2 * n : n * dim;
+  if (nptr > ENC_MAX_PTRS || dim > ENC_MAX_COLS || dim < 1) return -1;
+  int r = 0;
+  for (int c = 0; c < ENC_MAX_COLS; ++c) { d.voff[c] = 0; d.vsz[c] = 0; }
+  if (kind == ENC_EMBED) {
+    for (int c = 0; c < dim; ++c) { d.voff[c] = r; d.vsz[c] = vocab[c]; r += vocab[c]; }
+  } else {
+    r = dim + 1;
+  }
+  d.R = r;
+  for (int i = 0; i < ENC_MAX_PTRS; ++i) { d.p[i] = i < nptr ? params[i] : nullptr; d.dp[i] = (dparams && i < nptr) ? dparams[i] : nullptr; }
+  return 0;
+}
+
+struct Geometry { int rpi, threads, blocks; };
+Geometry geometry(int N, int F) {
+  Geometry g;
+  const int fv = F / 4;
+  g.rpi = 256 / fv; if (g.rpi < 1) g.rpi = 1;
+  g.threads = g.rpi * fv;
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  const int want = 4 * sms;
+  const int groups = (N + g.rpi - 1) / g.rpi;
+  g.blocks = groups < want ? (groups < 1 ? 1 : groups) : want;
+  return g;
+}
+
+template <typename K>
+bool ensure_smem(K kern, size_t bytes) {
+  if (bytes <= 48 * 1024) return true;
+  if (bytes > 200 * 1024) return false;
+  return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess;
+}
+
+}  // namespace
+
+extern "C" {
+
+// 1 if the fused path can run this configuration (otherwise the caller uses encoder + phc_aggregate_*)
+int phc_conv_fused_supported(int width, int phm_dim, int enc_kind, int enc_dim, int table_rows) {
+  if (width % 4 != 0 || width / 4 > 256 || phm_dim < 1 || width % phm_dim != 0) return 0;
+  if (enc_dim < 1 || enc_dim > ENC_MAX_COLS) return 0;
+  if ((enc_kind == ENC_LINEAR ? 2 * phm_dim : phm_dim * enc_dim) > ENC_MAX_PTRS) return 0;
+  int rpi = 256 / (width / 4); if (rpi < 1) rpi = 1;
+  const size_t bwd = sizeof(float) * (size_t)(1 + rpi) * table_rows * width;
+  return bwd <= 200 * 1024 ? 1 : 0;
+}
+
+int phc_conv_fused_fwd(const float* x, const void* edge_attr, int enc_kind, int enc_dim, const int* vocab, const float* const* params,
+                       const int* rowptr, const int* col, const int* perm, int num_nodes, int width, int phm_dim, int reduce,
+                       int msg_act, const float* beta, int self_loop, float* out, float* aux_f, int* aux_i, cudaStream_t stream) {
+  PHC_REQUIRE(reduce >= PHC_RED_SUM && reduce <= PHC_RED_SOFTMAX, "phc_conv_fused_fwd: bad reduce %d", reduce);
+  PHC_REQUIRE(msg_act >= PHC_ACT_IDENTITY && msg_act <= PHC_ACT_SWISH, "phc_conv_fused_fwd: bad msg_act %d", msg_act);
+  EncDesc d;
+  PHC_REQUIRE(make_desc(d, enc_kind, enc_dim, vocab, params, nullptr, phm_dim, width) == 0, "phc_conv_fused_fwd: unsupported encoder");
+  PHC_REQUIRE(phc_conv_fused_supported(width, phm_dim, enc_kind, enc_dim, d.R), "phc_conv_fused_fwd: unsupported shape");
+  if (num_nodes == 0) return PHC_OK;
+  const Geometry g = geometry(num_nodes, width);
+  const size_t smem = sizeof(float) * (size_t)d.R * width;
+#define PHC_LAUNCH(RED)                                                                                                          \
+  if (!ensure_smem(conv_fwd_kernel<RED>, smem)) { phc_set_error("phc_conv_fused_fwd: shared memory"); return PHC_ERR_CUDA; }     \
+  conv_fwd_kernel<RED><<<g.blocks, g.threads, smem, stream>>>(d, x, edge_attr, rowptr, col, perm, num_nodes, width, g.rpi, msg_act, beta, \
+                                                              self_loop, out, aux_f, aux_i);
+  switch (reduce) {
+    case PHC_RED_SUM: PHC_LAUNCH(PHC_RED_SUM) break;
+    case PHC_RED_MEAN: PHC_LAUNCH(PHC_RED_MEAN) break;
+    case PHC_RED_MAX: PHC_LAUNCH(PHC_RED_MAX) break;
+    case PHC_RED_MIN: PHC_LAUNCH(PHC_RED_MIN) break;
+    default: PHC_LAUNCH(PHC_RED_SOFTMAX) break;
+  }
+#undef PHC_LAUNCH
+  return phc_check_launch("phc_conv_fused_fwd");
+}
+
+size_t phc_conv_fused_bwd_workspace_bytes(int num_nodes, int width, int table_rows) {
+  const Geometry g = geometry(num_nodes, width);
+  return sizeof(float) * ((size_t)g.blocks * table_rows * width + g.blocks) + 64;
+}
+
+int phc_conv_fused_bwd(const float* gout, const float* x, const void* edge_attr, int enc_kind, int enc_dim, const int* vocab,
+                       const float* const* params, float* const* dparams, const float* aux_f, const int* aux_i, const int* rowptr,
+                       const int* col, const int* perm, const int* rowptr_t, const int* col_t, const int* perm_t, int num_nodes,
+                       int width, int phm_dim, int reduce, int msg_act, const float* beta, int self_loop, float* dx, float* dbeta,
+                       void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  EncDesc d;
+  PHC_REQUIRE(make_desc(d, enc_kind, enc_dim, vocab, params, dparams, phm_dim, width) == 0, "phc_conv_fused_bwd: unsupported encoder");
+  PHC_REQUIRE(phc_conv_fused_supported(width, phm_dim, enc_kind, enc_dim, d.R), "phc_conv_fused_bwd: unsupported shape");
+  PHC_REQUIRE(workspace_bytes >= phc_conv_fused_bwd_workspace_bytes(num_nodes, width, d.R), "phc_conv_fused_bwd: workspace too small");
+  const int N = num_nodes, F = width;
+  const Geometry g = geometry(N, F);
+  float* part = reinterpret_cast<float*>(workspace);
+  float* dbp = part + (size_t)g.blocks * d.R * F;
+  const size_t smem_p = sizeof(float) * (size_t)(1 + g.rpi) * d.R * F;
+  const size_t smem_n = sizeof(float) * (size_t)d.R * F;
+  const bool simple = (reduce == PHC_RED_SUM || reduce == PHC_RED_MEAN) && msg_act == PHC_ACT_IDENTITY;
+#define PHC_LAUNCH(RED)                                                                                                               \
+  if (!ensure_smem(conv_bwd_param_kernel<RED>, smem_p) || !ensure_smem(conv_bwd_node_kernel<RED>, smem_n)) {                          \
+    phc_set_error("phc_conv_fused_bwd: shared memory"); return PHC_ERR_CUDA; }                                                       \
+  if (N > 0) conv_bwd_param_kernel<RED><<<g.blocks, g.threads, smem_p, stream>>>(d, gout, x, edge_attr, aux_f, aux_i, rowptr, col, perm, N, F, \
+                                                                                 g.rpi, msg_act, beta, part, dbp);                    \
+  if (N > 0 && dx && !simple) conv_bwd_node_kernel<RED><<<g.blocks, g.threads, smem_n, stream>>>(d, gout, x, edge_attr, aux_f, aux_i, rowptr,   \
+                                                                                        rowptr_t, col_t, perm_t, N, F, g.rpi, msg_act, \
+                                                                                        beta, self_loop, dx);
+  switch (reduce) {
+    case PHC_RED_SUM: PHC_LAUNCH(PHC_RED_SUM) break;
+    case PHC_RED_MEAN: PHC_LAUNCH(PHC_RED_MEAN) break;
+    case PHC_RED_MAX: PHC_LAUNCH(PHC_RED_MAX) break;
+    case PHC_RED_MIN: PHC_LAUNCH(PHC_RED_MIN) break;
+    default: PHC_LAUNCH(PHC_RED_SOFTMAX) break;
+  }
+#undef PHC_LAUNCH
+  const int blocks_used = N > 0 ? g.blocks : 0;
+  conv_bwd_param_final_kernel<<<phc_div_up((long long)d.R * F, 256), 256, 0, stream>>>(d, part, blocks_used, F);
+  if (reduce == PHC_RED_SOFTMAX && dbeta) sum_partials_kernel<<<1, 256, 0, stream>>>(dbp, blocks_used, dbeta);
+  int rc = phc_check_launch("phc_conv_fused_bwd");
+  if (rc) return rc;
+  if (dx && simple && N > 0)
+    return phc_aggregate_bwd_node_simple(reduce == PHC_RED_MEAN, gout, rowptr, rowptr_t, col_t, perm_t, N, F, self_loop, dx, stream);
+  return PHC_OK;
+}
+
+}  // extern "C"

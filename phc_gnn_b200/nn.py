@@ -314,6 +314,19 @@ class PHMEncoder(nn.Module):
         for e in self.encoders:
             e.reset_parameters()
 
+    def fusable_params(self):
+        """(is_linear, parameter list in kernel order, vocabulary sizes) for the fused encoder+aggregation kernel."""
+        if isinstance(self.input_dims, list):
+            return False, [emb.weight for enc in self.encoders for emb in enc.embeddings], list(self.input_dims)
+        return True, [e.weight for e in self.encoders] + [e.bias for e in self.encoders], []
+
+    def can_fuse(self, width: int) -> bool:
+        if isinstance(self.input_dims, list):
+            if self.combine != "sum":
+                return False
+            return ops.conv_fused_supported(width, self.phm_dim, False, len(self.input_dims), self.input_dims)
+        return ops.conv_fused_supported(width, self.phm_dim, True, int(self.input_dims), [])
+
     def flat(self, x: torch.Tensor) -> torch.Tensor:
         """[rows, n*out_dim] with component c in column block c."""
         if isinstance(self.input_dims, list):
@@ -470,6 +483,15 @@ class _PHMConvBase(nn.Module):
         beta = getattr(self, "beta", None)
         return ops.aggregate(x, edge_attr, struct, self.aggr, self.msg_encoder_str.lower(), beta, self_loop=fuse_self)
 
+    def propagate_fused(self, x, edge_index, raw_edge_attr, encoder, fuse_self: bool):
+        """Same as ``propagate`` but takes the RAW edge features and the layer's bond encoder: the [E,F] edge
+        embedding is rebuilt on the fly inside the aggregation kernel (csrc/conv_fused.cu)."""
+        struct = edge_structure(edge_index, x.size(0))
+        beta = getattr(self, "beta", None)
+        linear, params, vocab = encoder.fusable_params()
+        return ops.conv_aggregate_fused(x, raw_edge_attr, struct, linear=linear, params=params, phm_dim=self.phm_dim, vocab=vocab,
+                                        reduce=self.aggr, msg_act=self.msg_encoder_str.lower(), beta=beta, self_loop=fuse_self)
+
     def _reset_beta(self):
         if getattr(self, "beta", None) is not None:
             self.beta.data.fill_(self.initial_beta)
@@ -495,11 +517,13 @@ class PHMConv(_PHMConvBase):
         self.transform.reset_parameters()
         self._reset_beta()
 
-    def forward(self, x, edge_index, edge_attr, size=None):
+    def forward(self, x, edge_index, edge_attr, size=None, encoder=None):
+        """``encoder`` given: ``edge_attr`` holds the RAW edge features and the encoder is fused into the aggregation."""
+        prop = self.propagate if encoder is None else (lambda a, b, c, fuse_self: self.propagate_fused(a, b, c, encoder, fuse_self))
         if self.same_dim:
-            agg = self.propagate(x, edge_index, edge_attr, fuse_self=False)
+            agg = prop(x, edge_index, edge_attr, fuse_self=False)
             return self.transform(agg, residual=x if self.add_self_loops else None)
-        agg = self.propagate(x, edge_index, edge_attr, fuse_self=self.add_self_loops)
+        agg = prop(x, edge_index, edge_attr, fuse_self=self.add_self_loops)
         return self.transform(agg)
 
 
@@ -523,7 +547,9 @@ class PHMGINEConv(_PHMConvBase):
         self.transform.reset_parameters()
         self._reset_beta()
 
-    def forward(self, x, edge_index, edge_attr, size=None):
+    def forward(self, x, edge_index, edge_attr, size=None, encoder=None):
+        if encoder is not None:
+            return self.transform(self.propagate_fused(x, edge_index, edge_attr, encoder, fuse_self=self.add_self_loops))
         return self.transform(self.propagate(x, edge_index, edge_attr, fuse_self=self.add_self_loops))
 
 
@@ -579,7 +605,9 @@ class PHMMessagePassing(nn.Module):
     def get_num_params(self):
         return sum(p.numel() for p in self.parameters() if p.requires_grad)
 
-    def forward(self, x, edge_index, edge_attr, size=None):
+    def forward(self, x, edge_index, edge_attr, size=None, encoder=None):
+        if encoder is not None:
+            return self.transform(x, edge_index, edge_attr, size, encoder=encoder)
         return self.transform(x, edge_index, edge_attr, size)
 
 
@@ -613,6 +641,7 @@ class _PHMSkipConnectBase(nn.Module):
         self.downstream_layers, self.target_dim, self.dropout_dn = downstream_layers, target_dim, dropout_dn
         self.norm_dn_type = None if norm_dn == "None" else norm_dn
         self.input_dim = atom_encoded_dim
+        self.fuse_edge_encoder = True        # B200 path: rebuild edge embeddings inside the aggregation kernel
         self.f_act = get_module_activation(activation)
         self.sc_type = sc_type
         Enc = NaivePHMEncoder if naive_encoder else PHMEncoder
@@ -698,6 +727,13 @@ class PHMSkipConnectAdd(_PHMSkipConnectBase):
                 skip = h
             else:
                 raise ValueError
+            enc = self.bondencoders[i]
+            if self.fuse_edge_encoder and isinstance(enc, PHMEncoder) and enc.can_fuse(h.size(1)):
+                # bond encoder fused into the aggregation: the [E,F] edge embedding of models.py:238-240 is never formed
+                z = self.convs[i](h, edge_index, edge_attr, size, encoder=enc)
+                h = norm_act_drop_skip(self.norms[i], z, skip, self.activation_str.lower(), self.phm_dim, self.training,
+                                       drop_p=self.dropout_mpnn[i], drop_same=self.same_dropout)
+                continue
             e = self._encode_edges(i, edge_attr)
             h = self.compute_hidden_layer_embedding(self.convs[i], self.norms[i], [h, skip], edge_index, e, self.dropout_mpnn[i], size)
         num_graphs = getattr(data, "num_graphs", None)

@@ -45,7 +45,8 @@ PROFILE = _Profile()
 _KERNELS = {"phc_csr_build": 6, "phc_segment_ptr_build": 2, "phc_aggregate_fwd": 1, "phc_aggregate_bwd": 2,
             "phc_segment_pool_fwd": 1, "phc_segment_pool_bwd": 1, "phc_bn_act_drop_skip_fwd": 3, "phc_bn_act_drop_skip_bwd": 3,
             "phc_embed_sum_fwd": 1, "phc_embed_sum_bwd": 2, "phc_linear_encoder_fwd": 1, "phc_linear_encoder_bwd": 2,
-            "phc_phm_linear_fwd": 2, "phc_phm_linear_bwd": 8, "phc_weight_reg_fwd": 2, "phc_weight_reg_bwd": 1}
+            "phc_phm_linear_fwd": 2, "phc_phm_linear_bwd": 8, "phc_weight_reg_fwd": 2, "phc_weight_reg_bwd": 1,
+            "phc_conv_fused_fwd": 1, "phc_conv_fused_bwd": 3}
 
 
 def run(name: str, device, *args, tag: str = ""):
@@ -438,3 +439,79 @@ class _WeightReg(torch.autograd.Function):
 def weight_regularization_l2(weights: Sequence[torch.Tensor]) -> torch.Tensor:
     """sum_l W_l.norm(p=2, dim=0).mean() over [n,K,P] weight tensors, one fused launch pair."""
     return _WeightReg.apply(*weights)
+
+
+# --------------------------------------------------------------------------------- aggregation with fused edge encoder
+def conv_fused_supported(width: int, phm_dim: int, linear: bool, enc_dim: int, vocab: Sequence[int]) -> bool:
+    rows = enc_dim + 1 if linear else int(sum(vocab))
+    return bool(_lib.load().phc_conv_fused_supported(width, phm_dim, 0 if linear else 1, enc_dim, rows))
+
+
+class _ConvFused(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, attr, beta, struct: EdgeStructure, meta, *params):
+        (linear, enc_dim, vocab, n, reduce, msg_act, self_loop) = meta
+        x = _f32c(x, "x")
+        require_cuda(attr, "edge_attr")
+        attr = attr.contiguous()
+        if linear:
+            attr = attr.to(torch.float32)
+        elif attr.dtype != torch.int64:
+            attr = attr.to(torch.int64)
+        N, F = x.shape
+        assert N == struct.num_nodes and attr.size(0) == struct.num_edges
+        for t in params:
+            require_cuda(t, "encoder parameter")
+            assert t.is_contiguous() and t.dtype == torch.float32
+        out = torch.empty_like(x)
+        aux_f = torch.empty((2, N, F), dtype=torch.float32, device=x.device) if reduce == 4 else None
+        aux_i = torch.empty((N, F), dtype=torch.int32, device=x.device) if reduce in (2, 3) else None
+        if reduce == 4:
+            beta = _f32c(beta, "beta")
+        vc = (ctypes.c_int * max(len(vocab), 1))(*vocab) if vocab else None
+        run("phc_conv_fused_fwd", None, x.data_ptr(), attr.data_ptr(), 0 if linear else 1, enc_dim, vc, _ptr_array(params),
+            struct.rowptr.data_ptr(), struct.col.data_ptr(), struct.perm.data_ptr(), N, F, n, reduce, msg_act,
+            _ptr(beta if reduce == 4 else None), int(self_loop), out.data_ptr(), _ptr(aux_f), _ptr(aux_i), _stream(x.device))
+        ctx.save_for_backward(x, attr, beta if reduce == 4 else None, aux_f, aux_i, *params)
+        ctx.struct = struct
+        ctx.meta = meta
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        x, attr, beta, aux_f, aux_i = ctx.saved_tensors[:5]
+        params = ctx.saved_tensors[5:]
+        (linear, enc_dim, vocab, n, reduce, msg_act, self_loop) = ctx.meta
+        s = ctx.struct
+        g = _f32c(g, "grad_output")
+        N, F = x.shape
+        dx = torch.empty_like(x)
+        flat = torch.empty(sum(p.numel() for p in params), dtype=torch.float32, device=x.device)
+        grads, o = [], 0
+        for p in params:
+            grads.append(flat[o:o + p.numel()].view(p.shape))
+            o += p.numel()
+        dbeta = torch.zeros((), dtype=torch.float32, device=x.device) if reduce == 4 else None
+        rows = enc_dim + 1 if linear else int(sum(vocab))
+        nb = lib.phc_conv_fused_bwd_workspace_bytes(N, F, rows)
+        ws = _ws(nb, x.device)
+        vc = (ctypes.c_int * max(len(vocab), 1))(*vocab) if vocab else None
+        run("phc_conv_fused_bwd", None, g.data_ptr(), x.data_ptr(), attr.data_ptr(), 0 if linear else 1, enc_dim, vc,
+            _ptr_array(params), _ptr_array(grads), _ptr(aux_f), _ptr(aux_i), s.rowptr.data_ptr(), s.col.data_ptr(),
+            s.perm.data_ptr(), s.rowptr_t.data_ptr(), s.col_t.data_ptr(), s.perm_t.data_ptr(), N, F, n, reduce, msg_act,
+            _ptr(beta), int(self_loop), dx.data_ptr(), _ptr(dbeta), ws.data_ptr(), ws.numel(), _stream(x.device))
+        return (dx, None, dbeta, None, None) + tuple(grads)
+
+
+def conv_aggregate_fused(x, edge_attr, struct: EdgeStructure, *, linear: bool, params: Sequence[torch.Tensor], phm_dim: int,
+                         vocab: Sequence[int] = (), reduce: str = "add", msg_act: str = "identity",
+                         beta: Optional[torch.Tensor] = None, self_loop: bool = False) -> torch.Tensor:
+    """out[i] = (x[i] if self_loop) + AGG_e act(x[src(e)] + enc(edge_attr[e])) without materialising enc(edge_attr).
+    linear: params = n weights [F/n, D] then n biases; otherwise n*#cols embedding tables ordered [component][column]."""
+    r = REDUCE_IDS[reduce]
+    if edge_attr.dim() == 1:
+        edge_attr = edge_attr.unsqueeze(1)
+    enc_dim = edge_attr.size(1)
+    meta = (bool(linear), int(enc_dim), tuple(int(v) for v in vocab), int(phm_dim), r, act_id(msg_act), bool(self_loop))
+    return _ConvFused.apply(x, edge_attr, beta if r == 4 else None, struct, meta, *params)

@@ -28,10 +28,11 @@ def oracle_params(state, dtype=torch.float32):
     return p
 
 
-def product_train_eval(cfg, state, batch, loss_kind, reg_scale, device):
+def product_train_eval(cfg, state, batch, loss_kind, reg_scale, device, fuse_edge_encoder=True):
     """-> dict(logits, loss, reg, grads, running, logits_eval) from the CUDA path."""
     from phc.hypercomplex.regularization import phm_weight_regularization
     m = product_model(cfg, state, device)
+    m.fuse_edge_encoder = fuse_edge_encoder
     data = batch.to(device)
     m.train()
     logits = m(data)

@@ -313,3 +313,42 @@ def test_weight_regulariser():
         assert_close(l.W.grad.cpu(), g, RTOL, grad_tol(g, RTOL), "dW")
     r1 = phm_weight_regularization(m, p=1)                      # other norms take the generic path
     assert torch.isfinite(r1)
+
+
+@pytest.mark.parametrize("reduce,act,linear,F,n", [
+    ("add", "identity", True, 500, 4), ("mean", "relu", True, 224, 4), ("max", "identity", True, 500, 4), ("min", "swish", True, 20, 5),
+    ("softmax", "identity", False, 200, 4), ("softmax", "relu", False, 16, 4), ("add", "identity", False, 512, 4),
+    ("max", "elu", False, 180, 2), ("mean", "identity", False, 12, 3), ("softmax", "swish", True, 64, 1)])
+def test_conv_aggregate_with_fused_encoder(reduce, act, linear, F, n):
+    """Aggregation with the edge encoder fused in == encoder followed by aggregation (oracle, fp64)."""
+    from phc.hypercomplex.encoder import PHMEncoder
+    from phc_gnn_b200 import ops
+    from phc_gnn_b200.graph import EdgeStructure
+    N, E = 301, 2500
+    ei = _graph(N, E, 9)
+    E = ei.size(1)
+    g = torch.Generator().manual_seed(4)
+    dims = 7 if linear else [5, 6, 2]
+    enc = PHMEncoder(F // n, dims, n)
+    attr = torch.rand(E, 7, generator=g) if linear else torch.stack([torch.randint(0, d, (E,), generator=g) for d in dims], 1)
+    x = torch.randn(N, F, generator=g)
+    beta = torch.tensor(0.9)
+    gout = torch.randn(N, F, generator=g)
+    po = {f"e.{k}": v.detach().clone().double().requires_grad_(True) for k, v in enc.state_dict().items()}
+    xo, bo = x.double().requires_grad_(True), beta.double().requires_grad_(True)
+    ref = O.propagate(xo, ei, O.encoder(attr, po, "e", n, dims, torch.float64), reduce, act, bo) + xo
+    ref.backward(gout.double())
+    enc = enc.to(DEV)
+    assert enc.can_fuse(F)
+    linear_, params, vocab = enc.fusable_params()
+    xs, bs = x.to(DEV).requires_grad_(True), beta.to(DEV).requires_grad_(True)
+    s = EdgeStructure(ei.to(DEV), N)
+    out = ops.conv_aggregate_fused(xs, attr.to(DEV), s, linear=linear_, params=params, phm_dim=n, vocab=vocab, reduce=reduce,
+                                   msg_act=act, beta=bs, self_loop=True)
+    out.backward(gout.to(DEV))
+    assert_close(out.detach().cpu(), ref.detach().float(), RTOL, 2e-5, "out")
+    assert_close(xs.grad.cpu(), xo.grad.float(), RTOL, grad_tol(xo.grad, RTOL), "dx")
+    for k, v in enc.named_parameters():
+        assert_close(v.grad.cpu(), po["e." + k].grad.float(), 2e-4, grad_tol(po["e." + k].grad, 2e-4), k)
+    if reduce == "softmax":
+        assert_close(bs.grad.cpu(), bo.grad.float(), 1e-3, grad_tol(bo.grad, 1e-3), "dbeta")
