@@ -92,7 +92,43 @@ __device__ __forceinline__ void edge_embed(const EncDesc& enc, const float* tab,
   }
 }
 
-template <int RED>
+// Linear encoder with compile-time input width DT: the thread's 4 x DT weights and 4 biases live in registers
+// (no shared-memory traffic per edge).  DT == 0 selects the generic shared-memory table path above.
+template <int DT> struct LinRegs {
+  float w[DT > 0 ? DT : 1][4], b[4];
+  __device__ __forceinline__ void load(const float* tab, int F, int f) {
+    if (DT > 0) {
+#pragma unroll
+      for (int d = 0; d < DT; ++d) {
+        const float4 t = *reinterpret_cast<const float4*>(tab + (size_t)d * F + f);
+        w[d][0] = t.x; w[d][1] = t.y; w[d][2] = t.z; w[d][3] = t.w;
+      }
+      const float4 t = *reinterpret_cast<const float4*>(tab + (size_t)DT * F + f);
+      b[0] = t.x; b[1] = t.y; b[2] = t.z; b[3] = t.w;
+    }
+  }
+};
+template <int DT>
+__device__ __forceinline__ void edge_embed_t(const LinRegs<DT>& lr, const EncDesc& enc, const float* tab, int F, const void* attr, int e,
+                                             int f, float (&ev)[4]) {
+  if (DT > 0) {
+    const float* a = reinterpret_cast<const float*>(attr) + (size_t)e * DT;
+    float av[DT > 0 ? DT : 1];
+#pragma unroll
+    for (int d = 0; d < DT; ++d) av[d] = __ldg(a + d);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float v = lr.b[q];
+#pragma unroll
+      for (int d = 0; d < DT; ++d) v += av[d] * lr.w[d][q];
+      ev[q] = v;
+    }
+  } else {
+    edge_embed(enc, tab, F, attr, e, f, ev);
+  }
+}
+
+template <int RED, int DT>
 __global__ void conv_fwd_kernel(const EncDesc enc, const float* __restrict__ x, const void* __restrict__ attr, const int* __restrict__ rowptr,
                                 const int* __restrict__ col, const int* __restrict__ perm, int N, int F, int rpi, int act,
                                 const float* __restrict__ beta_ptr, int self_loop, float* __restrict__ out, float* __restrict__ aux_f,
@@ -104,31 +140,35 @@ __global__ void conv_fwd_kernel(const EncDesc enc, const float* __restrict__ x, 
   const int slot = threadIdx.x / fv, f = (threadIdx.x - slot * fv) * 4;
   const float beta = (RED == PHC_RED_SOFTMAX) ? __ldg(beta_ptr) : 0.f;
   const bool has_act = act != PHC_ACT_IDENTITY;
+  LinRegs<DT> lr;
+  lr.load(tab, F, f);
   for (int i = blockIdx.x * rpi + slot; i < N; i += gridDim.x * rpi) {
     const int beg = rowptr[i], end = rowptr[i + 1];
     Acc<RED> acc[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) acc[q].init();
     int k = beg;
-    for (; k + 2 <= end; k += 2) {                 // two edges in flight
-      const int j0 = __ldg(col + k), e0 = __ldg(perm + k), j1 = __ldg(col + k + 1), e1 = __ldg(perm + k + 1);
-      const float4 x0 = *reinterpret_cast<const float4*>(x + (size_t)j0 * F + f);
-      const float4 x1 = *reinterpret_cast<const float4*>(x + (size_t)j1 * F + f);
-      float v0[4], v1[4];
-      edge_embed(enc, tab, F, attr, e0, f, v0);
-      edge_embed(enc, tab, F, attr, e1, f, v1);
-      const float m0[4] = {x0.x + v0[0], x0.y + v0[1], x0.z + v0[2], x0.w + v0[3]};
-      const float m1[4] = {x1.x + v1[0], x1.y + v1[1], x1.z + v1[2], x1.w + v1[3]};
+    for (; k + 4 <= end; k += 4) {                 // four edges in flight
+      int j[4], e[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) acc[q].push(has_act ? act_fwd_rt(act, m0[q]) : m0[q], e0, beta);
+      for (int u = 0; u < 4; ++u) { j[u] = __ldg(col + k + u); e[u] = __ldg(perm + k + u); }
+      float4 xv[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) acc[q].push(has_act ? act_fwd_rt(act, m1[q]) : m1[q], e1, beta);
+      for (int u = 0; u < 4; ++u) xv[u] = *reinterpret_cast<const float4*>(x + (size_t)j[u] * F + f);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float ev[4];
+        edge_embed_t<DT>(lr, enc, tab, F, attr, e[u], f, ev);
+        const float m[4] = {xv[u].x + ev[0], xv[u].y + ev[1], xv[u].z + ev[2], xv[u].w + ev[3]};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q].push(has_act ? act_fwd_rt(act, m[q]) : m[q], e[u], beta);
+      }
     }
     for (; k < end; ++k) {
       const int j0 = __ldg(col + k), e0 = __ldg(perm + k);
       const float4 x0 = *reinterpret_cast<const float4*>(x + (size_t)j0 * F + f);
       float v0[4];
-      edge_embed(enc, tab, F, attr, e0, f, v0);
+      edge_embed_t<DT>(lr, enc, tab, F, attr, e0, f, v0);
       const float m0[4] = {x0.x + v0[0], x0.y + v0[1], x0.z + v0[2], x0.w + v0[3]};
 #pragma unroll
       for (int q = 0; q < 4; ++q) acc[q].push(has_act ? act_fwd_rt(act, m0[q]) : m0[q], e0, beta);
@@ -182,7 +222,7 @@ __device__ __forceinline__ void edge_dpre(int act, bool need_pre, float beta, co
 }
 
 // encoder-parameter gradients + d(beta): by target rows, shared-memory accumulators, block partials
-template <int RED>
+template <int RED, int DT>
 __global__ void conv_bwd_param_kernel(const EncDesc enc, const float* __restrict__ g, const float* __restrict__ x,
                                       const void* __restrict__ attr, const float* __restrict__ aux_f, const int* __restrict__ aux_i,
                                       const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ perm, int N,
@@ -200,6 +240,11 @@ __global__ void conv_bwd_param_kernel(const EncDesc enc, const float* __restrict
   const float beta = (RED == PHC_RED_SOFTMAX) ? __ldg(beta_ptr) : 0.f;
   const bool need_pre = act != PHC_ACT_IDENTITY || RED == PHC_RED_SOFTMAX;
   float db = 0.f;
+  LinRegs<DT> lr;
+  lr.load(tab, F, f);
+  float racc[DT > 0 ? DT + 1 : 1][4];          // register accumulators for the small Linear encoders
+#pragma unroll
+  for (int d = 0; d < (DT > 0 ? DT + 1 : 1); ++d) racc[d][0] = racc[d][1] = racc[d][2] = racc[d][3] = 0.f;
   for (int i = blockIdx.x * rpi + slot; i < N; i += gridDim.x * rpi) {
     const int beg = rowptr[i], end = rowptr[i + 1];
     const size_t off = (size_t)i * F + f;
@@ -228,12 +273,22 @@ __global__ void conv_bwd_param_kernel(const EncDesc enc, const float* __restrict
         const int j = __ldg(col + k);
         const float4 xv = *reinterpret_cast<const float4*>(x + (size_t)j * F + f);
         float ev[4];
-        edge_embed(enc, tab, F, attr, e, f, ev);
+        edge_embed_t<DT>(lr, enc, tab, F, attr, e, f, ev);
         pre[0] = xv.x + ev[0]; pre[1] = xv.y + ev[1]; pre[2] = xv.z + ev[2]; pre[3] = xv.w + ev[3];
       }
       float d[4];
       edge_dpre<RED>(act, need_pre, beta, pre, gi, lse, agg, arg, e, d, db);
-      if (enc.kind == ENC_LINEAR) {
+      if (DT > 0) {
+        const float* a = reinterpret_cast<const float*>(attr) + (size_t)e * DT;
+#pragma unroll
+        for (int dd = 0; dd < DT; ++dd) {
+          const float av = __ldg(a + dd);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) racc[dd][q] += av * d[q];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) racc[DT > 0 ? DT : 0][q] += d[q];
+      } else if (enc.kind == ENC_LINEAR) {
         const float* a = reinterpret_cast<const float*>(attr) + (size_t)e * enc.D;
         for (int dd = 0; dd < enc.D; ++dd) {
           const float av = __ldg(a + dd);
@@ -258,6 +313,10 @@ __global__ void conv_bwd_param_kernel(const EncDesc enc, const float* __restrict
         }
       }
     }
+  }
+  if (DT > 0) {
+#pragma unroll
+    for (int d = 0; d <= DT; ++d) *reinterpret_cast<float4*>(mine + (size_t)d * F + f) = make_float4(racc[d][0], racc[d][1], racc[d][2], racc[d][3]);
   }
   __syncthreads();
   // block partial: slots summed in slot order
@@ -436,10 +495,16 @@ int phc_conv_fused_fwd(const float* x, const void* edge_attr, int enc_kind, int 
   if (num_nodes == 0) return PHC_OK;
   const Geometry g = geometry(num_nodes, width);
   const size_t smem = sizeof(float) * (size_t)d.R * width;
+  const int dt = (enc_kind == ENC_LINEAR && enc_dim <= 8) ? enc_dim : 0;
+#define PHC_LAUNCH2(RED, DT)                                                                                                     \
+  { if (!ensure_smem(conv_fwd_kernel<RED, DT>, smem)) { phc_set_error("phc_conv_fused_fwd: shared memory"); return PHC_ERR_CUDA; } \
+    conv_fwd_kernel<RED, DT><<<g.blocks, g.threads, smem, stream>>>(d, x, edge_attr, rowptr, col, perm, num_nodes, width, g.rpi, msg_act, \
+                                                                    beta, self_loop, out, aux_f, aux_i); }
 #define PHC_LAUNCH(RED)                                                                                                          \
-  if (!ensure_smem(conv_fwd_kernel<RED>, smem)) { phc_set_error("phc_conv_fused_fwd: shared memory"); return PHC_ERR_CUDA; }     \
-  conv_fwd_kernel<RED><<<g.blocks, g.threads, smem, stream>>>(d, x, edge_attr, rowptr, col, perm, num_nodes, width, g.rpi, msg_act, beta, \
-                                                              self_loop, out, aux_f, aux_i);
+  switch (dt) {                                                                                                                  \
+    case 1: PHC_LAUNCH2(RED, 1) break; case 2: PHC_LAUNCH2(RED, 2) break; case 3: PHC_LAUNCH2(RED, 3) break;                     \
+    case 4: PHC_LAUNCH2(RED, 4) break; case 5: PHC_LAUNCH2(RED, 5) break; case 6: PHC_LAUNCH2(RED, 6) break;                     \
+    case 7: PHC_LAUNCH2(RED, 7) break; case 8: PHC_LAUNCH2(RED, 8) break; default: PHC_LAUNCH2(RED, 0) break; }
   switch (reduce) {
     case PHC_RED_SUM: PHC_LAUNCH(PHC_RED_SUM) break;
     case PHC_RED_MEAN: PHC_LAUNCH(PHC_RED_MEAN) break;
@@ -448,6 +513,7 @@ int phc_conv_fused_fwd(const float* x, const void* edge_attr, int enc_kind, int 
     default: PHC_LAUNCH(PHC_RED_SOFTMAX) break;
   }
 #undef PHC_LAUNCH
+#undef PHC_LAUNCH2
   return phc_check_launch("phc_conv_fused_fwd");
 }
 
@@ -472,11 +538,17 @@ int phc_conv_fused_bwd(const float* gout, const float* x, const void* edge_attr,
   const size_t smem_p = sizeof(float) * (size_t)(1 + g.rpi) * d.R * F;
   const size_t smem_n = sizeof(float) * (size_t)d.R * F;
   const bool simple = (reduce == PHC_RED_SUM || reduce == PHC_RED_MEAN) && msg_act == PHC_ACT_IDENTITY;
+  const int dt = (enc_kind == ENC_LINEAR && enc_dim <= 8) ? enc_dim : 0;
+#define PHC_PARAM(RED, DT)                                                                                                            \
+  { if (!ensure_smem(conv_bwd_param_kernel<RED, DT>, smem_p)) { phc_set_error("phc_conv_fused_bwd: shared memory"); return PHC_ERR_CUDA; } \
+    if (N > 0) conv_bwd_param_kernel<RED, DT><<<g.blocks, g.threads, smem_p, stream>>>(d, gout, x, edge_attr, aux_f, aux_i, rowptr, col, perm, \
+                                                                                       N, F, g.rpi, msg_act, beta, part, dbp); }
 #define PHC_LAUNCH(RED)                                                                                                               \
-  if (!ensure_smem(conv_bwd_param_kernel<RED>, smem_p) || !ensure_smem(conv_bwd_node_kernel<RED>, smem_n)) {                          \
-    phc_set_error("phc_conv_fused_bwd: shared memory"); return PHC_ERR_CUDA; }                                                       \
-  if (N > 0) conv_bwd_param_kernel<RED><<<g.blocks, g.threads, smem_p, stream>>>(d, gout, x, edge_attr, aux_f, aux_i, rowptr, col, perm, N, F, \
-                                                                                 g.rpi, msg_act, beta, part, dbp);                    \
+  if (!ensure_smem(conv_bwd_node_kernel<RED>, smem_n)) { phc_set_error("phc_conv_fused_bwd: shared memory"); return PHC_ERR_CUDA; }   \
+  switch (dt) {                                                                                                                       \
+    case 1: PHC_PARAM(RED, 1) break; case 2: PHC_PARAM(RED, 2) break; case 3: PHC_PARAM(RED, 3) break; case 4: PHC_PARAM(RED, 4) break; \
+    case 5: PHC_PARAM(RED, 5) break; case 6: PHC_PARAM(RED, 6) break; case 7: PHC_PARAM(RED, 7) break; case 8: PHC_PARAM(RED, 8) break; \
+    default: PHC_PARAM(RED, 0) break; }                                                                                               \
   if (N > 0 && dx && !simple) conv_bwd_node_kernel<RED><<<g.blocks, g.threads, smem_n, stream>>>(d, gout, x, edge_attr, aux_f, aux_i, rowptr,   \
                                                                                         rowptr_t, col_t, perm_t, N, F, g.rpi, msg_act, \
                                                                                         beta, self_loop, dx);
@@ -488,6 +560,7 @@ int phc_conv_fused_bwd(const float* gout, const float* x, const void* edge_attr,
     default: PHC_LAUNCH(PHC_RED_SOFTMAX) break;
   }
 #undef PHC_LAUNCH
+#undef PHC_PARAM
   const int blocks_used = N > 0 ? g.blocks : 0;
   conv_bwd_param_final_kernel<<<phc_div_up((long long)d.R * F, 256), 256, 0, stream>>>(d, part, blocks_used, F);
   if (reduce == PHC_RED_SOFTMAX && dbeta) sum_partials_kernel<<<1, 256, 0, stream>>>(dbp, blocks_used, dbeta);
