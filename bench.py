@@ -226,18 +226,17 @@ def run_b200(args):
 
     for i in range(args.warmup):
         one(i)
+    # ---- timed region: K steps, device-resident batches, no per-op instrumentation --------------------------
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    ops.PROFILE.reset(timing=True)
+    ops.PROFILE.reset(timing=False)
     evs = []
     for i in range(args.steps):
         loss = one(args.warmup + i, evs)
     barrier()
     clocks = sampler.result()
     launches = ops.PROFILE.launches
-    prof = ops.PROFILE.summary()
-    ops.PROFILE.reset(timing=False)
     ms = sum(a.elapsed_time(b) for a, b in evs)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -246,39 +245,122 @@ def run_b200(args):
     graphs = wl.batch_graphs * args.steps * world
     value = graphs / (ms / 1e3)
 
+    # ---- the same K steps again with a CUDA-event pair around every kernel call (per-op breakdown / roofline);
+    #      kept out of the headline region because the event records themselves cost host time ---------------
+    barrier()
+    ops.PROFILE.reset(timing=True)
+    evs2 = []
+    for i in range(args.steps):
+        one(args.warmup + i, evs2)
+    barrier()
+    prof = ops.PROFILE.summary()
+    ops.PROFILE.reset(timing=False)
+    ms_instr = sum(a.elapsed_time(b) for a, b in evs2)
+
+    # the unfused aggregation kernel at the SURVEY 8(d) boundary (edge embedding [E,F] given), same batch shapes:
+    # reported next to the fused kernel for reference; it is NOT part of the timed step any more
+    unfused = None
+    if rank == 0:
+        bt = devb[0]
+        Fw = wl.model["mp_layers"][0]
+        xs = torch.randn(bt.num_nodes, Fw, device=dev)
+        es = torch.randn(bt.num_edges, Fw, device=dev)
+        st = graph.EdgeStructure(bt.edge_index, bt.num_nodes)
+        red = "add" if wl.model["msg_aggr"] in ("sum", "add") else wl.model["msg_aggr"]
+        beta_t = torch.ones((), device=dev)
+        for _ in range(3):
+            ops.aggregate(xs, es, st, red, wl.model["msg_encoder"], beta_t, True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            ops.aggregate(xs, es, st, red, wl.model["msg_encoder"], beta_t, True)
+        e1.record()
+        torch.cuda.synchronize()
+        us = 1e3 * e0.elapsed_time(e1) / 10
+        byt = aggregation_bytes(bt.num_nodes, bt.num_edges, Fw, red == "softmax")
+        unfused = {"kernel": "aggregate_fwd_kernel (edge embedding [E,F] read from HBM)", "avg_launch_us": us,
+                   "achieved": byt / us / 1e3, "unit": "GB/s", "in_timed_step": False}
+        del xs, es
+
     # ---- end-to-end: host batches, H2D inside the timed region, loss read back every step -------------
     e2e = None
     if not args.no_e2e:
+        # Every step: its batch is copied from pinned host memory (side stream, one step ahead of the compute
+        # stream) and its loss is copied back to pinned host memory; the host reads loss i while step i+1 is
+        # already queued, so the host never stalls the device (the reference blocks on loss.item() each step).
+        copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+        loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+        total_loss = 0.0
+
+        def fetch(i):
+            with torch.cuda.stream(copy_stream):
+                d = host[i % len(host)].to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return d, ev
+
         barrier()
         t0 = torch.cuda.Event(enable_timing=True)
         t1 = torch.cuda.Event(enable_timing=True)
         t0.record()
+        nxt = fetch(args.warmup)
         for i in range(args.steps):
+            d, ev = nxt
+            main.wait_event(ev)
+            for name in ("x", "edge_index", "edge_attr", "batch", "y"):
+                getattr(d, name).record_stream(main)
+            if i + 1 < args.steps:
+                nxt = fetch(args.warmup + i + 1)
             graph.clear_cache()
-            d = host[(args.warmup + i) % len(host)].to(dev, non_blocking=True)
-            float(step(d).item())
+            l = step(d)
+            loss_host[i & 1].copy_(l, non_blocking=True)
+            loss_ev[i & 1].record(main)
+            if i > 0:
+                loss_ev[(i - 1) & 1].synchronize()
+                total_loss += float(loss_host[(i - 1) & 1]) * wl.batch_graphs
+        loss_ev[(args.steps - 1) & 1].synchronize()
+        total_loss += float(loss_host[(args.steps - 1) & 1]) * wl.batch_graphs
         t1.record()
         barrier()
         tt = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": graphs / (float(tt.item()) / 1e3), "unit": UNIT,
-               "h2d_bytes_per_step": int(sum(b.nbytes() for b in host) / len(host)), "d2h_bytes_per_step": 4}
+               "h2d_bytes_per_step": int(sum(b.nbytes() for b in host) / len(host)), "d2h_bytes_per_step": 4,
+               "mean_loss": total_loss / (args.steps * wl.batch_graphs)}
 
     if rank == 0:
         peak, peak_src = peaks()
         N = sum(b.num_nodes for b in host) / len(host)
         E = sum(b.num_edges for b in host) / len(host)
         F = wl.model["mp_layers"][0]
-        calls, agg_ms = prof.get("phc_aggregate_fwd", (0, 0.0))
+        fused = "phc_conv_fused_fwd" in prof
+        calls, agg_ms = prof.get("phc_conv_fused_fwd" if fused else "phc_aggregate_fwd", (0, 0.0))
         roof = None
         if calls:
-            byt = aggregation_bytes(N, E, F, wl.model["msg_aggr"] == "softmax")
-            ach = byt / (agg_ms / calls * 1e-3) / 1e9
-            roof = {"bound": "hbm", "kernel": "aggregate_fwd_kernel (fused gather + edge add + reduce)", "achieved": ach,
-                    "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": byt, "avg_launch_us": 1e3 * agg_ms / calls,
-                    "share_of_step": agg_ms / ms}
+            softmax = wl.model["msg_aggr"] == "softmax"
+            byt = aggregation_bytes(N, E, F, softmax)                 # SURVEY 8(d) unit: one layer's propagate
+            us = 1e3 * agg_ms / calls
+            ach = byt / us / 1e3
+            roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": byt, "avg_launch_us": us,
+                    "share_of_step": agg_ms / ms_instr, "timed": "CUDA events around each launch, instrumented repeat of the K steps"}
+            if fused:
+                dims = wl.model["bond_input_dims"]
+                attr_b = (4 * dims if isinstance(dims, int) else 8 * len(dims)) * E
+                actual = 4 * F * 2 * N + attr_b + 8 * E + 4 * (N + 1) + (8 * N * F if softmax else 0)
+                roof.update({
+                    "kernel": "conv_fwd_kernel (gather + edge ENCODER + edge add + reduce fused)",
+                    "note": "achieved = SURVEY 8(d) algorithmic bytes of the unit (edge embedding [E,F] counted) / time, i.e. "
+                            "effective bandwidth; the fused kernel rebuilds the embedding from the raw edge features and really "
+                            "moves only hbm_bytes_model bytes, it is bound by the L2 row gather and FMA issue, not by HBM",
+                    "hbm_bytes_model": actual, "hbm_gbs_model": actual / us / 1e3, "unfused_boundary_kernel": unfused})
+                if unfused:
+                    unfused["frac"] = unfused["achieved"] / peak
+            else:
+                roof["kernel"] = "aggregate_fwd_kernel (fused gather + edge add + reduce)"
         breakdown = {k: {"calls_per_step": v[0] / args.steps, "ms_per_step": v[1] / args.steps} for k, v in sorted(prof.items())}
         if args.kernel_timers:
             print(json.dumps(breakdown, indent=1), file=sys.stderr)
@@ -288,7 +370,7 @@ def run_b200(args):
                    os.environ.get("PHC_PRECISION", "tf32x3")],
                "data": "synthetic",
                "config": config_dict(args, wl, wl.batch_graphs, "flushed between steps" if flush else "inputs larger than L2"),
-               "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof,
+               "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "ms_per_step_instrumented": ms_instr / args.steps,
                "op_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in breakdown.items()},
                "final_loss": float(loss.item())}
         if world == 1 and not args.no_cpu_baseline:

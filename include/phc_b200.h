@@ -141,8 +141,13 @@ size_t phc_conv_fused_bwd_workspace_bytes(int num_nodes, int width, int table_ro
 int phc_conv_fused_bwd(const float* gout, const float* x, const void* edge_attr, int enc_kind, int enc_dim, const int* vocab,
                        const float* const* params, float* const* dparams, const float* aux_f, const int* aux_i, const int* rowptr,
                        const int* col, const int* perm, const int* rowptr_t, const int* col_t, const int* perm_t, int num_nodes,
-                       int width, int phm_dim, int reduce, int msg_act, const float* beta, int self_loop, float* dx, float* dbeta,
-                       void* workspace, size_t workspace_bytes, phc_stream_t stream);
+                       int width, int phm_dim, int reduce, int msg_act, const float* beta, int self_loop, const float* node_sums,
+                       float* dx, float* dbeta, void* workspace, size_t workspace_bytes, phc_stream_t stream);
+/* node_sums [N, table_rows] (optional, sum/mean + identity message only): per-node sums of the edge features
+ * (Linear: raw features and in-degree; embeddings: value histograms), scaled by 1/deg for mean.  Depends only on
+ * the batch, so it is computed once and shared by all layers; with it the encoder gradients need no edge loop. */
+int phc_edge_feature_sums(const void* edge_attr, int enc_kind, int enc_dim, const int* vocab, const int* rowptr, const int* perm,
+                          int num_nodes, int mean, float* node_sums, phc_stream_t stream);
 
 /* ---- weight regulariser (regularization.py:15-23): out = sum_l mean_{k,p} ||W_l[:,k,p]||_2 ------------
  * weights / dweights: HOST arrays of device pointers to the [n_l, K_l, P_l] weight tensors; kp[l] = K_l*P_l. */

@@ -339,13 +339,18 @@ __global__ void conv_bwd_param_kernel(const EncDesc enc, const float* __restrict
   }
 }
 
-// sum block partials in block order and scatter into the individual parameter gradients
+// sum block partials (lane l takes blocks l, l+32, ... in order, then a fixed butterfly) and scatter into the
+// individual parameter gradients; one warp per table element
 __global__ void __launch_bounds__(256) conv_bwd_param_final_kernel(const EncDesc enc, const float* __restrict__ part, int blocks, int F) {
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long t = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (t >= (long long)enc.R * F) return;
   const int r = (int)(t / F), f = (int)(t - (long long)r * F);
   float s = 0.f;
-  for (int b = 0; b < blocks; ++b) s += part[((size_t)b * enc.R + r) * F + f];
+  for (int b = lane; b < blocks; b += 32) s += part[((size_t)b * enc.R + r) * F + f];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane != 0) return;
   const int c = f / enc.Fc, fp = f - c * enc.Fc;
   if (enc.kind == ENC_LINEAR) {
     if (r < enc.D) enc.dp[c][(size_t)fp * enc.D + r] = s;
@@ -355,6 +360,56 @@ __global__ void __launch_bounds__(256) conv_bwd_param_final_kernel(const EncDesc
     while (col + 1 < enc.D && enc.voff[col + 1] <= r) ++col;
     enc.dp[c * enc.D + col][(size_t)(r - enc.voff[col]) * enc.Fc + fp] = s;
   }
+}
+
+// ---- sum / mean aggregation with identity message: d(pre_e) = g[dst(e)] * scale, so the encoder-parameter
+// gradient collapses to  dTab[r,f] = sum_i S[i,r] * g[i,f]  with the per-NODE feature sums
+//   S[i,r] = scale_i * sum_{e -> i} phi_r(edge_attr[e])    (phi = raw features + constant 1, or one-hot of the integer columns)
+// S depends only on the batch (not on the layer), is N x R (R <= 16) and is computed once per batch.
+__global__ void __launch_bounds__(256) edge_feature_sums_kernel(const EncDesc enc, const void* __restrict__ attr, const int* __restrict__ rowptr,
+                                                                const int* __restrict__ perm, int N, int mean, float* __restrict__ S) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)N * enc.R) return;
+  const int i = (int)(t / enc.R), r = (int)(t - (long long)i * enc.R);
+  const int beg = rowptr[i], end = rowptr[i + 1];
+  float s = 0.f;
+  if (enc.kind == ENC_LINEAR) {
+    if (r == enc.D) s = (float)(end - beg);
+    else for (int k = beg; k < end; ++k) s += __ldg(reinterpret_cast<const float*>(attr) + (size_t)__ldg(perm + k) * enc.D + r);
+  } else {
+    int col = 0;
+    while (col + 1 < enc.D && enc.voff[col + 1] <= r) ++col;
+    const int v = r - enc.voff[col];
+    for (int k = beg; k < end; ++k) {
+      long long a = __ldg(reinterpret_cast<const long long*>(attr) + (size_t)__ldg(perm + k) * enc.D + col);
+      a = a < 0 ? 0 : (a >= enc.vsz[col] ? enc.vsz[col] - 1 : a);
+      s += (a == v) ? 1.f : 0.f;
+    }
+  }
+  S[t] = mean ? s / (float)max(end - beg, 1) : s;
+}
+
+template <int RT>
+__global__ void __launch_bounds__(128) conv_bwd_param_simple_kernel(const float* __restrict__ g, const float* __restrict__ S, int N, int F,
+                                                                    int rows_per_block, float* __restrict__ part) {
+  const int f = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
+  if (f >= F) return;
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, N);
+  float acc[RT][4];
+#pragma unroll
+  for (int r = 0; r < RT; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
+#pragma unroll 2
+  for (int i = r0; i < r1; ++i) {
+    const float4 gv = *reinterpret_cast<const float4*>(g + (size_t)i * F + f);
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      const float sv = __ldg(S + (size_t)i * RT + r);
+      acc[r][0] += sv * gv.x; acc[r][1] += sv * gv.y; acc[r][2] += sv * gv.z; acc[r][3] += sv * gv.w;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RT; ++r)
+    *reinterpret_cast<float4*>(part + ((size_t)blockIdx.x * RT + r) * F + f) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
 }
 
 __global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restrict__ part, int n, float* __restrict__ out) {
@@ -517,16 +572,30 @@ int phc_conv_fused_fwd(const float* x, const void* edge_attr, int enc_kind, int 
   return phc_check_launch("phc_conv_fused_fwd");
 }
 
+int phc_edge_feature_sums(const void* edge_attr, int enc_kind, int enc_dim, const int* vocab, const int* rowptr, const int* perm,
+                          int num_nodes, int mean, float* node_sums, cudaStream_t stream) {
+  EncDesc d;
+  const float* none[ENC_MAX_PTRS] = {nullptr};
+  PHC_REQUIRE(make_desc(d, enc_kind, enc_dim, vocab, none, nullptr, 1, 4) == 0, "phc_edge_feature_sums: unsupported encoder");
+  if (num_nodes == 0) return PHC_OK;
+  edge_feature_sums_kernel<<<phc_div_up((long long)num_nodes * d.R, 256), 256, 0, stream>>>(d, edge_attr, rowptr, perm, num_nodes, mean,
+                                                                                           node_sums);
+  return phc_check_launch("phc_edge_feature_sums");
+}
+
 size_t phc_conv_fused_bwd_workspace_bytes(int num_nodes, int width, int table_rows) {
   const Geometry g = geometry(num_nodes, width);
-  return sizeof(float) * ((size_t)g.blocks * table_rows * width + g.blocks) + 64;
+  size_t blocks = (size_t)g.blocks;
+  const size_t nb = (size_t)phc_div_up(num_nodes, 64);
+  if (nb > blocks) blocks = nb;
+  return sizeof(float) * (blocks * table_rows * width + blocks) + 64;
 }
 
 int phc_conv_fused_bwd(const float* gout, const float* x, const void* edge_attr, int enc_kind, int enc_dim, const int* vocab,
                        const float* const* params, float* const* dparams, const float* aux_f, const int* aux_i, const int* rowptr,
                        const int* col, const int* perm, const int* rowptr_t, const int* col_t, const int* perm_t, int num_nodes,
-                       int width, int phm_dim, int reduce, int msg_act, const float* beta, int self_loop, float* dx, float* dbeta,
-                       void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                       int width, int phm_dim, int reduce, int msg_act, const float* beta, int self_loop, const float* node_sums,
+                       float* dx, float* dbeta, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   EncDesc d;
   PHC_REQUIRE(make_desc(d, enc_kind, enc_dim, vocab, params, dparams, phm_dim, width) == 0, "phc_conv_fused_bwd: unsupported encoder");
   PHC_REQUIRE(phc_conv_fused_supported(width, phm_dim, enc_kind, enc_dim, d.R), "phc_conv_fused_bwd: unsupported shape");
@@ -538,6 +607,24 @@ int phc_conv_fused_bwd(const float* gout, const float* x, const void* edge_attr,
   const size_t smem_p = sizeof(float) * (size_t)(1 + g.rpi) * d.R * F;
   const size_t smem_n = sizeof(float) * (size_t)d.R * F;
   const bool simple = (reduce == PHC_RED_SUM || reduce == PHC_RED_MEAN) && msg_act == PHC_ACT_IDENTITY;
+  if (simple && node_sums != nullptr && d.R <= 16 && N > 0) {
+    // parameter gradients from the per-node feature sums: dTab = S^T g (reads g once, no edge loop)
+    const int rpb = 64;
+    const int nb = phc_div_up(N, rpb);
+    PHC_REQUIRE((size_t)nb * d.R * F * sizeof(float) <= workspace_bytes, "phc_conv_fused_bwd: workspace too small for the node-sum path");
+    dim3 grid(nb, phc_div_up(F / 4, 128));
+    switch (d.R) {
+#define PHC_CASE(RT) case RT: conv_bwd_param_simple_kernel<RT><<<grid, 128, 0, stream>>>(gout, node_sums, N, F, rpb, part); break;
+      PHC_CASE(1) PHC_CASE(2) PHC_CASE(3) PHC_CASE(4) PHC_CASE(5) PHC_CASE(6) PHC_CASE(7) PHC_CASE(8)
+      PHC_CASE(9) PHC_CASE(10) PHC_CASE(11) PHC_CASE(12) PHC_CASE(13) PHC_CASE(14) PHC_CASE(15) PHC_CASE(16)
+#undef PHC_CASE
+    }
+    conv_bwd_param_final_kernel<<<phc_div_up((long long)d.R * F * 32, 256), 256, 0, stream>>>(d, part, nb, F);
+    int rc = phc_check_launch("phc_conv_fused_bwd(node sums)");
+    if (rc) return rc;
+    if (dx) return phc_aggregate_bwd_node_simple(reduce == PHC_RED_MEAN, gout, rowptr, rowptr_t, col_t, perm_t, N, F, self_loop, dx, stream);
+    return PHC_OK;
+  }
   const int dt = (enc_kind == ENC_LINEAR && enc_dim <= 8) ? enc_dim : 0;
 #define PHC_PARAM(RED, DT)                                                                                                            \
   { if (!ensure_smem(conv_bwd_param_kernel<RED, DT>, smem_p)) { phc_set_error("phc_conv_fused_bwd: shared memory"); return PHC_ERR_CUDA; } \
@@ -562,7 +649,7 @@ int phc_conv_fused_bwd(const float* gout, const float* x, const void* edge_attr,
 #undef PHC_LAUNCH
 #undef PHC_PARAM
   const int blocks_used = N > 0 ? g.blocks : 0;
-  conv_bwd_param_final_kernel<<<phc_div_up((long long)d.R * F, 256), 256, 0, stream>>>(d, part, blocks_used, F);
+  conv_bwd_param_final_kernel<<<phc_div_up((long long)d.R * F * 32, 256), 256, 0, stream>>>(d, part, blocks_used, F);
   if (reduce == PHC_RED_SOFTMAX && dbeta) sum_partials_kernel<<<1, 256, 0, stream>>>(dbp, blocks_used, dbeta);
   int rc = phc_check_launch("phc_conv_fused_bwd");
   if (rc) return rc;

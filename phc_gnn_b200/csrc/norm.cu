@@ -35,6 +35,27 @@ __device__ __forceinline__ float drop_factor(const EwParams& p, int row, int f) 
   return dropout_keep(p.seed, idx, p.keep_thr) ? p.drop_scale : 0.f;
 }
 
+// dropout factors for VEC consecutive features starting at f (f % 4 == 0 when VEC == 4): one Philox call yields
+// the four uniforms of the aligned element quad, exactly the values drop_factor() produces one by one.
+template <int VEC>
+__device__ __forceinline__ void drop_factors(const EwParams& p, int row, int f, float (&out)[VEC]) {
+  if (!p.drop_on) {
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) out[q] = 1.f;
+    return;
+  }
+  if (VEC == 4 && !p.drop_same && (p.F & 3) == 0) {
+    const unsigned long long idx = (unsigned long long)row * p.F + f;      // multiple of 4
+    uint32_t r[4];
+    philox4x32_10((uint32_t)(idx >> 2), (uint32_t)(idx >> 34), 0u, 0u, (uint32_t)p.seed, (uint32_t)(p.seed >> 32), r);
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) out[q] = r[q] < p.keep_thr ? p.drop_scale : 0.f;
+    return;
+  }
+#pragma unroll
+  for (int q = 0; q < VEC; ++q) out[q] = drop_factor(p, row, f + q);
+}
+
 // ---- chunk statistics: part[chunk][0][f] = chunk mean, part[chunk][1][f] = chunk M2 ----------
 template <int VEC>
 __global__ void __launch_bounds__(BN_SLICES * BN_LANES) bn_chunk_stats_kernel(const float* __restrict__ h, int M, int F,
@@ -51,6 +72,7 @@ __global__ void __launch_bounds__(BN_SLICES * BN_LANES) bn_chunk_stats_kernel(co
     Vec<VEC> k = Vec<VEC>::load(h + (size_t)r0 * F + f);   // shift = first row of the chunk
 #pragma unroll
     for (int q = 0; q < VEC; ++q) sh[q] = k.v[q];
+#pragma unroll 4
     for (int r = r0 + slice; r < r1; r += BN_SLICES) {
       Vec<VEC> v = Vec<VEC>::load(h + (size_t)r * F + f);
 #pragma unroll
@@ -139,6 +161,8 @@ __global__ void __launch_bounds__(128) bn_eval_stats_kernel(const float* __restr
 }
 
 // ---- apply -------------------------------------------------------------------------------------
+constexpr int EW_ROWS = 4;   // rows per thread in the apply kernels (independent 128-bit loads in flight)
+
 template <int VEC>
 __global__ void __launch_bounds__(256) bn_apply_fwd_kernel(EwParams p, const float* __restrict__ h, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, const float* __restrict__ mean,
@@ -146,27 +170,37 @@ __global__ void __launch_bounds__(256) bn_apply_fwd_kernel(EwParams p, const flo
                                                            float* __restrict__ y) {
   const int fv = p.F / VEC;
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (long long)p.M * fv) return;
-  const int r = (int)(t / fv), f = (int)(t % fv) * VEC;
-  const size_t off = (size_t)r * p.F + f;
-  Vec<VEC> v = Vec<VEC>::load(h + off);
-  Vec<VEC> s;
-  if (skip) s = Vec<VEC>::load(skip + off);
+  const int rgroups = (p.M + EW_ROWS - 1) / EW_ROWS;
+  if (t >= (long long)rgroups * fv) return;
+  const int rg = (int)(t / fv), f = (int)(t % fv) * VEC;
+  Vec<VEC> v[EW_ROWS], s[EW_ROWS];
 #pragma unroll
-  for (int q = 0; q < VEC; ++q) {
-    float a = v.v[q];
-    if (p.use_bn) {
-      a = (a - __ldg(mean + f + q)) * __ldg(rstd + f + q);
-      if (gamma) a = a * __ldg(gamma + f + q) + __ldg(beta + f + q);
+  for (int j = 0; j < EW_ROWS; ++j) {
+    const int r = rg * EW_ROWS + j;
+    if (r < p.M) {
+      v[j] = Vec<VEC>::load(h + (size_t)r * p.F + f);
+      if (skip) s[j] = Vec<VEC>::load(skip + (size_t)r * p.F + f);
     }
-    a = act_fwd_rt(p.act, a) * drop_factor(p, r, f + q);
-    v.v[q] = skip ? a + s.v[q] : a;
   }
-  v.store(y + off);
+#pragma unroll
+  for (int j = 0; j < EW_ROWS; ++j) {
+    const int r = rg * EW_ROWS + j;
+    if (r >= p.M) break;
+    float df[VEC];
+    drop_factors<VEC>(p, r, f, df);
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) {
+      float a = p.use_bn ? (v[j].v[q] - __ldg(mean + f + q)) * __ldg(rstd + f + q) : v[j].v[q];
+      if (p.use_bn && gamma) a = a * __ldg(gamma + f + q) + __ldg(beta + f + q);
+      a = act_fwd_rt(p.act, a) * df[q];
+      v[j].v[q] = skip ? a + s[j].v[q] : a;
+    }
+    v[j].store(y + (size_t)r * p.F + f);
+  }
 }
 
 // d(act input) for one element, shared by the reduction and the apply pass of backward
-__device__ __forceinline__ float bn_da(const EwParams& p, float dy, float hv, int r, int f, const float* gamma, const float* beta,
+__device__ __forceinline__ float bn_da(const EwParams& p, float dy, float hv, float dfac, int f, const float* gamma, const float* beta,
                                        const float* mean, const float* rstd, float* xhat_out) {
   float xh = hv, pre = hv;
   if (p.use_bn) {
@@ -174,7 +208,7 @@ __device__ __forceinline__ float bn_da(const EwParams& p, float dy, float hv, in
     pre = gamma ? xh * __ldg(gamma + f) + __ldg(beta + f) : xh;
   }
   *xhat_out = xh;
-  return dy * drop_factor(p, r, f) * act_bwd_rt(p.act, pre);
+  return dy * dfac * act_bwd_rt(p.act, pre);
 }
 
 // part[chunk][0][f] = sum da ; part[chunk][1][f] = sum da * xhat
@@ -192,13 +226,16 @@ __global__ void __launch_bounds__(BN_SLICES * BN_LANES) bn_bwd_reduce_kernel(EwP
 #pragma unroll
   for (int q = 0; q < VEC; ++q) { s1[q] = 0.f; s2[q] = 0.f; }
   if (active) {
+#pragma unroll 4
     for (int r = r0 + slice; r < r1; r += BN_SLICES) {
       Vec<VEC> g = Vec<VEC>::load(dy + (size_t)r * p.F + f);
       Vec<VEC> v = Vec<VEC>::load(h + (size_t)r * p.F + f);
+      float df[VEC];
+      drop_factors<VEC>(p, r, f, df);
 #pragma unroll
       for (int q = 0; q < VEC; ++q) {
         float xh;
-        float da = bn_da(p, g.v[q], v.v[q], r, f + q, gamma, beta, mean, rstd, &xh);
+        float da = bn_da(p, g.v[q], v.v[q], df[q], f + q, gamma, beta, mean, rstd, &xh);
         s1[q] += da;
         s2[q] += da * xh;
       }
@@ -257,24 +294,43 @@ __global__ void __launch_bounds__(256) bn_apply_bwd_kernel(EwParams p, int train
                                                            float* __restrict__ dh) {
   const int fv = p.F / VEC;
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (long long)p.M * fv) return;
-  const int r = (int)(t / fv), f = (int)(t % fv) * VEC;
-  const size_t off = (size_t)r * p.F + f;
-  Vec<VEC> g = Vec<VEC>::load(dy + off);
-  Vec<VEC> v = Vec<VEC>::load(h + off);
+  const int rgroups = (p.M + EW_ROWS - 1) / EW_ROWS;
+  if (t >= (long long)rgroups * fv) return;
+  const int rg = (int)(t / fv), f = (int)(t % fv) * VEC;
   const float invM = 1.f / (float)p.M;
+  float scq[VEC], c1[VEC], c2[VEC];
 #pragma unroll
   for (int q = 0; q < VEC; ++q) {
-    float xh;
-    float da = bn_da(p, g.v[q], v.v[q], r, f + q, gamma, beta, mean, rstd, &xh);
+    scq[q] = 1.f; c1[q] = 0.f; c2[q] = 0.f;
     if (p.use_bn) {
-      float sc = __ldg(rstd + f + q) * (gamma ? __ldg(gamma + f + q) : 1.f);
-      if (training) da = da - __ldg(sum_da + f + q) * invM - xh * __ldg(sum_da_xhat + f + q) * invM;
-      da *= sc;
+      scq[q] = __ldg(rstd + f + q) * (gamma ? __ldg(gamma + f + q) : 1.f);
+      if (training) { c1[q] = __ldg(sum_da + f + q) * invM; c2[q] = __ldg(sum_da_xhat + f + q) * invM; }
     }
-    v.v[q] = da;
   }
-  v.store(dh + off);
+  Vec<VEC> g[EW_ROWS], v[EW_ROWS];
+#pragma unroll
+  for (int j = 0; j < EW_ROWS; ++j) {
+    const int r = rg * EW_ROWS + j;
+    if (r < p.M) {
+      g[j] = Vec<VEC>::load(dy + (size_t)r * p.F + f);
+      v[j] = Vec<VEC>::load(h + (size_t)r * p.F + f);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < EW_ROWS; ++j) {
+    const int r = rg * EW_ROWS + j;
+    if (r >= p.M) break;
+    float df[VEC];
+    drop_factors<VEC>(p, r, f, df);
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) {
+      float xh;
+      float da = bn_da(p, g[j].v[q], v[j].v[q], df[q], f + q, gamma, beta, mean, rstd, &xh);
+      if (p.use_bn) da = (da - c1[q] - xh * c2[q]) * scq[q];
+      v[j].v[q] = da;
+    }
+    v[j].store(dh + (size_t)r * p.F + f);
+  }
 }
 
 EwParams make_params(int M, int F, int n, int use_bn, int act, float drop_p, int drop_same, int training, unsigned long long seed) {
@@ -327,8 +383,9 @@ int phc_bn_act_drop_skip_fwd(const float* h, const float* gamma, const float* be
   }
   EwParams p = make_params(M, F, phm_dim, use_bn, act, drop_p, drop_same, training, seed);
   const bool v4 = F % 4 == 0 && phc_aligned16(h) && phc_aligned16(y) && phc_aligned16(skip);
-  if (v4) bn_apply_fwd_kernel<4><<<phc_div_up((long long)M * (F / 4), 256), 256, 0, stream>>>(p, h, gamma, beta, save_mean, save_rstd, skip, y);
-  else bn_apply_fwd_kernel<1><<<phc_div_up((long long)M * F, 256), 256, 0, stream>>>(p, h, gamma, beta, save_mean, save_rstd, skip, y);
+  const long long rgroups = (M + EW_ROWS - 1) / EW_ROWS;
+  if (v4) bn_apply_fwd_kernel<4><<<phc_div_up(rgroups * (F / 4), 256), 256, 0, stream>>>(p, h, gamma, beta, save_mean, save_rstd, skip, y);
+  else bn_apply_fwd_kernel<1><<<phc_div_up(rgroups * F, 256), 256, 0, stream>>>(p, h, gamma, beta, save_mean, save_rstd, skip, y);
   return phc_check_launch("phc_bn_act_drop_skip_fwd");
 }
 
@@ -353,12 +410,13 @@ int phc_bn_act_drop_skip_bwd(const float* dy, const float* h, const float* gamma
     else bn_bwd_reduce_kernel<1><<<grid, BN_SLICES * BN_LANES, 0, stream>>>(p, dy, h, gamma, beta, save_mean, save_rstd, part);
     bn_bwd_finalize_kernel<<<phc_div_up((long long)F * 32, 256), 256, 0, stream>>>(part, chunks, F, dgamma, dbeta);
   }
+  const long long rgroups = (M + EW_ROWS - 1) / EW_ROWS;
   if (v4)
-    bn_apply_bwd_kernel<4><<<phc_div_up((long long)M * (F / 4), 256), 256, 0, stream>>>(p, training, dy, h, gamma, beta, save_mean, save_rstd,
-                                                                                      sum_da, sum_da_xhat, dh);
+    bn_apply_bwd_kernel<4><<<phc_div_up(rgroups * (F / 4), 256), 256, 0, stream>>>(p, training, dy, h, gamma, beta, save_mean, save_rstd,
+                                                                                 sum_da, sum_da_xhat, dh);
   else
-    bn_apply_bwd_kernel<1><<<phc_div_up((long long)M * F, 256), 256, 0, stream>>>(p, training, dy, h, gamma, beta, save_mean, save_rstd,
-                                                                                sum_da, sum_da_xhat, dh);
+    bn_apply_bwd_kernel<1><<<phc_div_up(rgroups * F, 256), 256, 0, stream>>>(p, training, dy, h, gamma, beta, save_mean, save_rstd,
+                                                                           sum_da, sum_da_xhat, dh);
   return phc_check_launch("phc_bn_act_drop_skip_bwd");
 }
 

@@ -1143,7 +1143,8 @@ int launch_mix(const MixParams& p, cudaStream_t stream) {
 // ---------------------------------------------------------------------------- host entry points (used by api.cu)
 int phm_tc_supported(int rows, int in_features, int out_features, int phm_dim, int precision) {
   // tf32x3 only for now; small problems (head layers, M = graphs per batch) stay on the exact FFMA path
-  return precision == 1 && rows >= 512 && in_features >= 32 && out_features >= 32 && phm_dim <= 16;
+  // (tiny M is latency-bound either way; the tensor-core kernel needs fewer serial K iterations than the FFMA tile)
+  return precision == 1 && rows >= 32 && in_features >= 32 && out_features >= 32 && phm_dim <= 16;
 }
 
 size_t phm_tc_fwd_workspace_bytes(int, int in_features, int out_features, int phm_dim, int) {

@@ -28,7 +28,7 @@ def require_cuda(t: torch.Tensor, what: str):
 
 
 class EdgeStructure(object):
-    __slots__ = ("num_nodes", "num_edges", "rowptr", "col", "perm", "rowptr_t", "col_t", "perm_t", "status", "__weakref__")
+    __slots__ = ("num_nodes", "num_edges", "rowptr", "col", "perm", "rowptr_t", "col_t", "perm_t", "status", "extras", "__weakref__")
 
     def __init__(self, edge_index: torch.Tensor, num_nodes: int):
         require_cuda(edge_index, "edge_index")
@@ -55,6 +55,7 @@ class EdgeStructure(object):
             self.rowptr_t.data_ptr(), self.col_t.data_ptr(), self.perm_t.data_ptr(), ws.data_ptr(), ws_bytes,
             self.status.data_ptr(), _stream(dev))
         self.num_nodes, self.num_edges = N, E
+        self.extras = {}            # per-batch derived data shared by all layers (e.g. per-node edge-feature sums)
 
     def validate(self):
         """Synchronising check of the device status word (debug / tests)."""

@@ -46,7 +46,7 @@ _KERNELS = {"phc_csr_build": 6, "phc_segment_ptr_build": 2, "phc_aggregate_fwd":
             "phc_segment_pool_fwd": 1, "phc_segment_pool_bwd": 1, "phc_bn_act_drop_skip_fwd": 3, "phc_bn_act_drop_skip_bwd": 3,
             "phc_embed_sum_fwd": 1, "phc_embed_sum_bwd": 2, "phc_linear_encoder_fwd": 1, "phc_linear_encoder_bwd": 2,
             "phc_phm_linear_fwd": 2, "phc_phm_linear_bwd": 8, "phc_weight_reg_fwd": 2, "phc_weight_reg_bwd": 1,
-            "phc_conv_fused_fwd": 1, "phc_conv_fused_bwd": 3}
+            "phc_conv_fused_fwd": 1, "phc_conv_fused_bwd": 3, "phc_edge_feature_sums": 1}
 
 
 def run(name: str, device, *args, tag: str = ""):
@@ -497,10 +497,22 @@ class _ConvFused(torch.autograd.Function):
         nb = lib.phc_conv_fused_bwd_workspace_bytes(N, F, rows)
         ws = _ws(nb, x.device)
         vc = (ctypes.c_int * max(len(vocab), 1))(*vocab) if vocab else None
+        sums = None
+        if reduce in (0, 1) and msg_act == 0 and rows <= 16:
+            # per-node edge-feature sums: a property of the batch, computed once and shared by every layer
+            # (keyed by storage address: the cache entry keeps `attr` alive, so the address cannot be recycled)
+            key = ("sums", attr.data_ptr(), tuple(attr.shape), attr._version, linear, enc_dim, vocab, reduce == 1)
+            sums = s.extras.get(key)
+            if sums is None:
+                sums = torch.empty((N, rows), dtype=torch.float32, device=x.device)
+                run("phc_edge_feature_sums", None, attr.data_ptr(), 0 if linear else 1, enc_dim, vc, s.rowptr.data_ptr(),
+                    s.perm.data_ptr(), N, int(reduce == 1), sums.data_ptr(), _stream(x.device))
+                s.extras[key] = sums
+                s.extras[("keepalive", attr.data_ptr())] = attr
         run("phc_conv_fused_bwd", None, g.data_ptr(), x.data_ptr(), attr.data_ptr(), 0 if linear else 1, enc_dim, vc,
             _ptr_array(params), _ptr_array(grads), _ptr(aux_f), _ptr(aux_i), s.rowptr.data_ptr(), s.col.data_ptr(),
             s.perm.data_ptr(), s.rowptr_t.data_ptr(), s.col_t.data_ptr(), s.perm_t.data_ptr(), N, F, n, reduce, msg_act,
-            _ptr(beta), int(self_loop), dx.data_ptr(), _ptr(dbeta), ws.data_ptr(), ws.numel(), _stream(x.device))
+            _ptr(beta), int(self_loop), _ptr(sums), dx.data_ptr(), _ptr(dbeta), ws.data_ptr(), ws.numel(), _stream(x.device))
         return (dx, None, dbeta, None, None) + tuple(grads)
 
 

@@ -42,7 +42,10 @@ def make_optimizer(model, lr: float):
     # same update rule as the scripts' torch.optim.Adam(params); on CUDA use the single-kernel-per-group
     # implementation so the step is not dominated by optimizer launches
     fused = all(p.is_cuda for g in groups for p in g["params"])
-    return torch.optim.Adam(groups, fused=True) if fused else torch.optim.Adam(groups)
+    if fused:
+        # all six blocks share lr / weight_decay: one group is the same update with one fused kernel per step
+        return torch.optim.Adam([p for g in groups for p in g["params"]], lr=lr, weight_decay=0.0, fused=True)
+    return torch.optim.Adam(groups)
 
 
 class TrainStep(object):

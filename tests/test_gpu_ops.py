@@ -260,7 +260,8 @@ def test_phm_linear_fp32(n, fin, fout, M):
 
 @pytest.mark.parametrize("n,fin,fout,M", [(4, 128, 128, 512), (4, 500, 500, 1000), (2, 180, 180, 3000), (4, 200, 200, 3333),
                                           (1, 224, 56, 9000), (5, 200, 200, 777), (8, 512, 512, 640), (4, 512, 768, 600),
-                                          (3, 33, 300, 515), (16, 512, 64, 520), (4, 224, 224, 8936)])
+                                          (3, 33, 300, 515), (16, 512, 64, 520), (4, 224, 224, 8936), (4, 500, 512, 64), (4, 512, 256, 33),
+                                          (2, 180, 80, 128), (4, 256, 148, 64), (1, 500, 125, 200)])
 def test_phm_linear_tf32x3_tensor_core(n, fin, fout, M):
     """tcgen05 path (3-term tf32 split): fp32-class accuracy, same rtol as the FFMA path."""
     _phm_linear_case(n, fin, fout, M, precision=1, rtol=RTOL)
