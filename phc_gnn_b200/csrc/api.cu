@@ -34,7 +34,7 @@ size_t phm_tc_bwd_workspace_bytes(int rows, int in_features, int out_features, i
 int phm_tc_fwd(const float* x, const float* A, const float* W, const float* bias, const float* residual, float* y, int rows,
                int in_features, int out_features, int phm_dim, int act, int precision, void* workspace, cudaStream_t stream);
 int phm_tc_bwd(const float* gy, const float* x, const float* A, const float* W, float* dx, float* dA, float* dW, float* db, int rows,
-               int in_features, int out_features, int phm_dim, int precision, void* workspace, cudaStream_t stream);
+               int in_features, int out_features, int phm_dim, int precision, void* workspace, const void* fwd_pack, cudaStream_t stream);
 
 enum { PHC_PREC_FP32 = 0, PHC_PREC_TF32X3 = 1, PHC_PREC_BF16 = 2 };
 
@@ -80,14 +80,15 @@ int phc_phm_linear_fwd(const float* x, const float* phm_rule, const float* W, co
 
 int phc_phm_linear_bwd(const float* gy, const float* x, const float* phm_rule, const float* W, float* dx, float* d_rule, float* dW,
                        float* dbias, int rows, int in_features, int out_features, int phm_dim, int precision, void* workspace,
-                       size_t workspace_bytes, cudaStream_t stream) {
+                       size_t workspace_bytes, const void* fwd_workspace, cudaStream_t stream) {
   int rc = check_linear_shape("phc_phm_linear_bwd", rows, in_features, out_features, phm_dim, precision);
   if (rc) return rc;
   PHC_REQUIRE(dW != nullptr, "phc_phm_linear_bwd: dW is required");
   PHC_REQUIRE(workspace_bytes >= phc_phm_linear_bwd_workspace_bytes(rows, in_features, out_features, phm_dim, precision),
               "phc_phm_linear_bwd: workspace too small");
   if (precision != PHC_PREC_FP32 && phm_tc_supported(rows, in_features, out_features, phm_dim, precision))
-    return phm_tc_bwd(gy, x, phm_rule, W, dx, d_rule, dW, dbias, rows, in_features, out_features, phm_dim, precision, workspace, stream);
+    return phm_tc_bwd(gy, x, phm_rule, W, dx, d_rule, dW, dbias, rows, in_features, out_features, phm_dim, precision, workspace,
+                      fwd_workspace, stream);
   return phm_simt_bwd(gy, x, phm_rule, W, dx, d_rule, dW, dbias, rows, in_features, out_features, phm_dim, workspace, stream);
 }
 

@@ -586,7 +586,7 @@ int phc_edge_feature_sums(const void* edge_attr, int enc_kind, int enc_dim, cons
 size_t phc_conv_fused_bwd_workspace_bytes(int num_nodes, int width, int table_rows) {
   const Geometry g = geometry(num_nodes, width);
   size_t blocks = (size_t)g.blocks;
-  const size_t nb = (size_t)phc_div_up(num_nodes, 64);
+  const size_t nb = (size_t)phc_div_up(num_nodes, 16);
   if (nb > blocks) blocks = nb;
   return sizeof(float) * (blocks * table_rows * width + blocks) + 64;
 }
@@ -609,7 +609,7 @@ int phc_conv_fused_bwd(const float* gout, const float* x, const void* edge_attr,
   const bool simple = (reduce == PHC_RED_SUM || reduce == PHC_RED_MEAN) && msg_act == PHC_ACT_IDENTITY;
   if (simple && node_sums != nullptr && d.R <= 16 && N > 0) {
     // parameter gradients from the per-node feature sums: dTab = S^T g (reads g once, no edge loop)
-    const int rpb = 64;
+    const int rpb = 16;
     const int nb = phc_div_up(N, rpb);
     PHC_REQUIRE((size_t)nb * d.R * F * sizeof(float) <= workspace_bytes, "phc_conv_fused_bwd: workspace too small for the node-sum path");
     dim3 grid(nb, phc_div_up(F / 4, 128));

@@ -16,7 +16,7 @@
 
 namespace {
 
-constexpr int BN_ROWS = 128;   // rows per statistics chunk
+constexpr int BN_ROWS = 64;    // rows per statistics chunk
 constexpr int BN_SLICES = 8;   // row slices per block
 constexpr int BN_LANES = 32;   // feature lanes per block
 

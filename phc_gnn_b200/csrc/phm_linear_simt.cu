@@ -209,15 +209,41 @@ __global__ void __launch_bounds__(256) phm_dA_final_kernel(const float* __restri
   dA[i] = s;
 }
 
-// column sums of G (bias gradient): chunk partials then ordered final sum
+// column sums of G (bias gradient): chunk partials then ordered final sum.
+// block = 32 feature lanes (x4 floats) x 8 row slices; slices reduced in fixed order through shared memory.
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ G, int M, int F, int rows_per_chunk,
                                                              float* __restrict__ part) {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= F) return;
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
   const int r0 = blockIdx.y * rows_per_chunk, r1 = min(r0 + rows_per_chunk, M);
-  float s = 0.f;
-  for (int r = r0; r < r1; ++r) s += G[(size_t)r * F + f];
-  part[(size_t)blockIdx.y * F + f] = s;
+  __shared__ float red[8][128];
+  const bool vec = (F & 3) == 0 && ((reinterpret_cast<uintptr_t>(G) & 15u) == 0);
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  const int f = (blockIdx.x * 32 + lane) * 4;
+  if (f < F) {
+#pragma unroll 4
+    for (int r = r0 + slice; r < r1; r += 8) {
+      if (vec) {
+        const float4 v = *reinterpret_cast<const float4*>(G + (size_t)r * F + f);
+        s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (f + q < F) s[q] += G[(size_t)r * F + f + q];
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) red[slice][lane * 4 + q] = s[q];
+  __syncthreads();
+  if (slice == 0 && f < F) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float t = 0.f;
+#pragma unroll
+      for (int sl = 0; sl < 8; ++sl) t += red[sl][lane * 4 + q];
+      if (f + q < F) part[(size_t)blockIdx.y * F + f + q] = t;
+    }
+  }
 }
 // one warp per column: lane l sums chunks l, l+32, ... in order, then a fixed butterfly
 __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ part, int chunks, int F, float* __restrict__ out) {
@@ -297,7 +323,7 @@ int dh_splits(int M, int In, int Out) {
   return s < 1 ? 1 : (s > 64 ? 64 : s);
 }
 int colsum_chunks(int M) {
-  int c = phc_div_up(M, 32);
+  int c = phc_div_up(M, 64);
   return c < 1 ? 1 : (c > 1024 ? 1024 : c);
 }
 
@@ -326,7 +352,7 @@ int phm_contract_and_bias(const float* part, int splits, const float* gy, const 
   if (db) {
     const int chunks = colsum_chunks(M);
     const int rpc = phc_div_up(M > 0 ? M : 1, chunks);
-    dim3 g3(phc_div_up(out_features, 256), chunks);
+    dim3 g3(phc_div_up(out_features, 128), chunks);
     colsum_partial_kernel<<<g3, 256, 0, stream>>>(gy, M, out_features, rpc, cs_part);
     colsum_final_kernel<<<phc_div_up((long long)out_features * 32, 256), 256, 0, stream>>>(cs_part, chunks, out_features, db);
   }

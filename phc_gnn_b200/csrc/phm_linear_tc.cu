@@ -36,6 +36,7 @@
 //   dW[b,k,p] = sum_{a,c} A[b,a,c] dH[(a,k),(c,p)],   dA[b,a,c] = sum_{k,p} W[b,k,p] dH[(a,k),(c,p)].
 #include "common.cuh"
 #include <stdlib.h>
+#include <cuda_bf16.h>
 #include <cuda.h>   // CUtensorMap (encoded through the runtime's driver entry point; libcuda is not linked)
 
 // helpers implemented in phm_linear_simt.cu (fixed-order reductions shared by both paths)
@@ -73,6 +74,7 @@ struct MixParams {          // y = act(mix GEMM + bias) + residual   (FWD and DX
   const float* residual;
   float* C;                 // [M, n*Pout]
   int M, n, Kin, Pout, S, chunks, ptiles, act, num_tiles;
+  int single;               // 1: "bf16" mode — operands rounded to bf16, one tensor-core pass (no big/small split)
   long long* prof;          // optional per-CTA role timers (debug), 8 slots per CTA
 };
 
@@ -81,6 +83,7 @@ struct DhParams {           // partial dH tiles
   const float* G;           // [M, Out]
   float* C;                 // [splits, In, Out]
   int M, In, Out, tiles_m, tiles_n, splits, rows_per_split, num_tiles;
+  int single;
 };
 
 __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -175,11 +178,17 @@ __device__ __forceinline__ void split_tf32(float v, float& big, float& small) {
 __device__ __forceinline__ int swz(int row, int ku) { return row * 128 + ((ku ^ (row & 7)) << 4); }
 
 // write one 16-byte K-unit (4 consecutive k of one row) of an operand tile, big and small copies
-__device__ __forceinline__ void store_unit(uint8_t* tile_big, uint8_t* tile_small, int row, int ku, const float (&v)[4]) {
+__device__ __forceinline__ float round_bf16(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+__device__ __forceinline__ void store_unit(uint8_t* tile_big, uint8_t* tile_small, int row, int ku, const float (&v)[4], int single = 0) {
+  const int off = swz(row, ku);
+  if (single) {     // bf16-precision operands (exactly representable in tf32), no correction term
+    *reinterpret_cast<float4*>(tile_big + off) = make_float4(round_bf16(v[0]), round_bf16(v[1]), round_bf16(v[2]), round_bf16(v[3]));
+    return;
+  }
   float b[4], s[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) split_tf32(v[j], b[j], s[j]);
-  const int off = swz(row, ku);
   *reinterpret_cast<float4*>(tile_big + off) = make_float4(b[0], b[1], b[2], b[3]);
   *reinterpret_cast<float4*>(tile_small + off) = make_float4(s[0], s[1], s[2], s[3]);
 }
@@ -240,7 +249,7 @@ __device__ __forceinline__ void cta_epilogue(uint32_t tmem_base) {
 // MMA issuer for one tile: `chunks` pipeline stages, 4 K-steps x 3 split products each.
 template <int NS = STAGES>
 __device__ __forceinline__ void mma_tile(const Smem& s, uint32_t tmem_base, int it, int chunks, int& stage, int& phase,
-                                         long long* prof = nullptr) {   // prof: thread-local accumulators
+                                         long long* prof = nullptr, int single = 0) {   // prof: thread-local accumulators
   const int lane = threadIdx.x & 31;
   const int buf = it & 1;
   const uint32_t d_tmem = tmem_base + buf * BN;
@@ -261,9 +270,13 @@ __device__ __forceinline__ void mma_tile(const Smem& s, uint32_t tmem_base, int 
 #pragma unroll
       for (int ks = 0; ks < BK / 8; ++ks) {
         const uint64_t adv = (uint64_t)((ks * 32) >> 4);            // 8 tf32 = 32 bytes inside the swizzle row
-        umma_tf32(d_tmem, a_small + adv, b_big + adv, IDESC_TF32, accum);
-        umma_tf32(d_tmem, a_big + adv, b_small + adv, IDESC_TF32, 1u);
-        umma_tf32(d_tmem, a_big + adv, b_big + adv, IDESC_TF32, 1u);
+        if (single) {
+          umma_tf32(d_tmem, a_big + adv, b_big + adv, IDESC_TF32, accum);
+        } else {
+          umma_tf32(d_tmem, a_small + adv, b_big + adv, IDESC_TF32, accum);
+          umma_tf32(d_tmem, a_big + adv, b_small + adv, IDESC_TF32, 1u);
+          umma_tf32(d_tmem, a_big + adv, b_big + adv, IDESC_TF32, 1u);
+        }
         accum = 1u;
       }
       umma_commit(smem_u32(&s.empty_bar[stage]));                    // smem slot reusable when these MMAs retire
@@ -417,7 +430,7 @@ __device__ __forceinline__ void mix_produce(const MixParams& p, const float* __r
         v[j] = h;
       }
     }
-    store_unit(big, small, row, ku, v);
+    store_unit(big, small, row, ku, v, p.single);
   }
 }
 
@@ -483,8 +496,9 @@ __global__ void __launch_bounds__(THREADS, 1) phm_tc_mix_kernel(const MixParams 
           uint8_t* sb = s.stages + stage * STAGE_BYTES;
           if (ptid == 0) {                      // TMA: pre-split W chunk (big+small, already swizzled) -> B_big|B_small
             const uint32_t fb = smem_u32(&s.full_bar[stage]);
-            mbar_arrive_expect_tx(fb, 2 * TILE_BYTES);
-            tma_bulk_load(smem_u32(sb + 2 * TILE_BYTES), p.Bpack + ((size_t)pt * p.chunks + c) * (2 * TILE_BYTES), 2 * TILE_BYTES, fb);
+            const uint32_t bbytes = p.single ? TILE_BYTES : 2 * TILE_BYTES;
+            mbar_arrive_expect_tx(fb, bbytes);
+            tma_bulk_load(smem_u32(sb + 2 * TILE_BYTES), p.Bpack + ((size_t)pt * p.chunks + c) * (2 * TILE_BYTES), bbytes, fb);
           }
           mix_produce<NT>(p, cf, m0, c, ptid, ring[j], sb, sb + TILE_BYTES);
           fence_proxy_async();                  // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -500,7 +514,7 @@ __global__ void __launch_bounds__(THREADS, 1) phm_tc_mix_kernel(const MixParams 
     int stage = 0, phase = 0, it = 0;
     long long loc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it)
-      mma_tile(s, tmem_base, it, p.chunks, stage, phase, p.prof ? loc : nullptr);
+      mma_tile(s, tmem_base, it, p.chunks, stage, phase, p.prof ? loc : nullptr, p.single);
     if (p.prof && (threadIdx.x & 31) == 0) { p.prof[blockIdx.x * 8 + 2] = loc[2]; p.prof[blockIdx.x * 8 + 3] = loc[3]; }
   } else {
     int it = 0;
@@ -542,7 +556,7 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap
 
 template <int NT>
 __device__ __forceinline__ void mix_produce_raw(const float* __restrict__ raw, const float (&cf)[NT * NT], int c, int Kin, int pitch,
-                                                int ptid, uint8_t* big, uint8_t* small) {
+                                                int ptid, uint8_t* big, uint8_t* small, int single) {
   constexpr int KQ = BK / NT;            // k values per chunk
   // component uu's box: BM rows of `pitch` floats, first needed float at offset (uu*Kin) & 3 when padded
   const int pad = pitch != KQ;
@@ -571,7 +585,7 @@ __device__ __forceinline__ void mix_produce_raw(const float* __restrict__ raw, c
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) v[kk] = (c * KQ + ku * 4 + kk < Kin) ? cf[0] * raw[row * pitch + ku * 4 + kk] : 0.f;
     }
-    store_unit(big, small, row, ku, v);
+    store_unit(big, small, row, ku, v, single);
   }
 }
 
@@ -635,7 +649,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) phm_tc_mix_tma_kernel(const Mi
         mbar_wait(smem_u32(&rfull_bar[rs]), (g / TMA_RAW_STAGES) & 1);                 // raw x tile landed (TMA)
         mbar_wait(smem_u32(&s.empty_bar[os]), ((g / TMA_OP_STAGES) & 1) ^ 1);           // operand slot free (MMA done)
         uint8_t* sb = s.stages + os * STAGE_BYTES;
-        mix_produce_raw<NT>(reinterpret_cast<const float*>(rawbuf + rs * RAW_BYTES), cfr, c, p.Kin, pitch, ptid, sb, sb + TILE_BYTES);
+        mix_produce_raw<NT>(reinterpret_cast<const float*>(rawbuf + rs * RAW_BYTES), cfr, c, p.Kin, pitch, ptid, sb, sb + TILE_BYTES, p.single);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
@@ -673,15 +687,16 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) phm_tc_mix_tma_kernel(const Mi
           const int os = g % TMA_OP_STAGES;
           mbar_wait(smem_u32(&s.empty_bar[os]), ((g / TMA_OP_STAGES) & 1) ^ 1);
           const uint32_t fb = smem_u32(&s.full_bar[os]);
-          mbar_arrive_expect_tx(fb, 2 * TILE_BYTES);
+          const uint32_t bbytes = p.single ? TILE_BYTES : 2 * TILE_BYTES;     // bf16 mode needs the "big" image only
+          mbar_arrive_expect_tx(fb, bbytes);
           tma_bulk_load(smem_u32(s.stages + os * STAGE_BYTES + 2 * TILE_BYTES),
-                        p.Bpack + ((size_t)pt * p.chunks + c) * (2 * TILE_BYTES), 2 * TILE_BYTES, fb);
+                        p.Bpack + ((size_t)pt * p.chunks + c) * (2 * TILE_BYTES), bbytes, fb);
         }
       }
     }
   } else if (warp == MMA_WARP) {
     int stage = 0, phase = 0;
-    for (int it = 0; it < my_tiles; ++it) mma_tile<TMA_OP_STAGES>(s, tmem_base, it, p.chunks, stage, phase);
+    for (int it = 0; it < my_tiles; ++it) mma_tile<TMA_OP_STAGES>(s, tmem_base, it, p.chunks, stage, phase, nullptr, p.single);
   } else {
     const int ldc = p.n * p.Pout;
     for (int it = 0; it < my_tiles; ++it) {
@@ -721,12 +736,12 @@ __device__ __forceinline__ void dh_issue_loads(const float* __restrict__ X, int 
     }
   }
 }
-__device__ __forceinline__ void dh_produce(const DhLoad& L, int ptid, uint8_t* big, uint8_t* small) {
+__device__ __forceinline__ void dh_produce(const DhLoad& L, int ptid, uint8_t* big, uint8_t* small, int single) {
   const int ku = ptid & 7, fg = ptid >> 3;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     const float v[4] = {L.t[0][c], L.t[1][c], L.t[2][c], L.t[3][c]};
-    store_unit(big, small, fg * 4 + c, ku, v);
+    store_unit(big, small, fg * 4 + c, ku, v, single);
   }
 }
 __device__ __forceinline__ void dh_tile(const DhParams& p, int t, int& i0, int& o0, int& split, int& kbeg, int& kend) {
@@ -765,7 +780,7 @@ __global__ void __launch_bounds__(THREADS, 1) phm_tc_dh_kernel(const DhParams p)
         if (k0 + BK < kend) dh_issue_loads(src, ld, vec, f0, k0 + BK, kend, q, nxt);
         mbar_wait(smem_u32(&s.empty_bar[stage]), phase ^ 1);
         uint8_t* sb = s.stages + stage * STAGE_BYTES + half * 2 * TILE_BYTES;
-        dh_produce(cur, q, sb, sb + TILE_BYTES);
+        dh_produce(cur, q, sb, sb + TILE_BYTES, p.single);
         fence_proxy_async();
         __syncwarp();
         if ((ptid & 31) == 0) mbar_arrive(smem_u32(&s.full_bar[stage]));
@@ -777,7 +792,7 @@ __global__ void __launch_bounds__(THREADS, 1) phm_tc_dh_kernel(const DhParams p)
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
       int i0, o0, split, kbeg, kend;
       dh_tile(p, t, i0, o0, split, kbeg, kend);
-      mma_tile(s, tmem_base, it, (kend - kbeg + BK - 1) / BK, stage, phase);
+      mma_tile(s, tmem_base, it, (kend - kbeg + BK - 1) / BK, stage, phase, nullptr, p.single);
     }
   } else {
     int it = 0;
@@ -856,7 +871,7 @@ __global__ void __launch_bounds__(DH_TMA_THREADS, 1) phm_tc_dh_tma_kernel(const 
           const int f = u & (BM - 1), ku = u >> 7;
           const float v[4] = {raw[(ku * 4 + 0) * BM + f], raw[(ku * 4 + 1) * BM + f], raw[(ku * 4 + 2) * BM + f],
                               raw[(ku * 4 + 3) * BM + f]};
-          store_unit(sb, sb + TILE_BYTES, f, ku, v);
+          store_unit(sb, sb + TILE_BYTES, f, ku, v, p.single);
         }
         fence_proxy_async();
         __syncwarp();
@@ -887,7 +902,7 @@ __global__ void __launch_bounds__(DH_TMA_THREADS, 1) phm_tc_dh_tma_kernel(const 
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
       int i0, o0, split, kbeg, kend;
       dh_tile(p, t, i0, o0, split, kbeg, kend);
-      mma_tile<TMA_OP_STAGES>(s, tmem_base, it, (kend - kbeg + BK - 1) / BK, stage, phase);
+      mma_tile<TMA_OP_STAGES>(s, tmem_base, it, (kend - kbeg + BK - 1) / BK, stage, phase, nullptr, p.single);
     }
   } else {
     int it = 0;
@@ -909,7 +924,7 @@ __global__ void __launch_bounds__(DH_TMA_THREADS, 1) phm_tc_dh_tma_kernel(const 
 __global__ void __launch_bounds__(256) phm_pack_kernel(const float* __restrict__ A, const float* __restrict__ W, int n, int K, int P,
                                                        uint8_t* __restrict__ pack_fwd, float* __restrict__ coef_fwd,
                                                        uint8_t* __restrict__ pack_dx, float* __restrict__ coef_dx, int units_fwd,
-                                                       int units_dx) {
+                                                       int units_dx, int single) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int n3 = n * n * n;
   if (t < n3) {
@@ -937,7 +952,8 @@ __global__ void __launch_bounds__(256) phm_pack_kernel(const float* __restrict__
         const int kk = sidx / n, b = sidx - kk * n;
         v = dir == 0 ? W[((size_t)b * K + kk) * P + po] : W[((size_t)b * K + po) * P + kk];
       }
-      split_tf32(v, big[j], small[j]);
+      if (single) { big[j] = round_bf16(v); small[j] = 0.f; }
+      else split_tf32(v, big[j], small[j]);
     }
     uint8_t* dst = (dir == 0 ? pack_fwd : pack_dx) + ((size_t)pt * chunks + chunk) * (2 * TILE_BYTES);
     const int off = swz(q, ku);
@@ -1084,14 +1100,14 @@ int try_launch_mix_tma(const MixParams& p, cudaStream_t stream) {
   }
 }
 
-int launch_pack(const float* A, const float* W, int n, int K, int P, uint8_t* buf, cudaStream_t stream) {
+int launch_pack(const float* A, const float* W, int n, int K, int P, uint8_t* buf, int single, cudaStream_t stream) {
   const PackLayout L = pack_layout(n, K, P);
   const int units_fwd = L.pt_fwd * L.chunks_fwd * BN * 8, units_dx = L.pt_dx * L.chunks_dx * BN * 8;
   int threads = units_fwd > units_dx ? units_fwd : units_dx;
   if (threads < n * n * n) threads = n * n * n;
   phm_pack_kernel<<<phc_div_up(threads, 256), 256, 0, stream>>>(A, W, n, K, P, buf + L.pack_fwd, reinterpret_cast<float*>(buf + L.coef_fwd),
                                                                 buf + L.pack_dx, reinterpret_cast<float*>(buf + L.coef_dx), units_fwd,
-                                                                units_dx);
+                                                                units_dx, single);
   return phc_check_launch("phm_pack_kernel");
 }
 
@@ -1144,7 +1160,7 @@ int launch_mix(const MixParams& p, cudaStream_t stream) {
 int phm_tc_supported(int rows, int in_features, int out_features, int phm_dim, int precision) {
   // tf32x3 only for now; small problems (head layers, M = graphs per batch) stay on the exact FFMA path
   // (tiny M is latency-bound either way; the tensor-core kernel needs fewer serial K iterations than the FFMA tile)
-  return precision == 1 && rows >= 32 && in_features >= 32 && out_features >= 32 && phm_dim <= 16;
+  return (precision == 1 || precision == 2) && rows >= 32 && in_features >= 32 && out_features >= 32 && phm_dim <= 16;
 }
 
 size_t phm_tc_fwd_workspace_bytes(int, int in_features, int out_features, int phm_dim, int) {
@@ -1160,10 +1176,11 @@ size_t phm_tc_bwd_workspace_bytes(int rows, int in_features, int out_features, i
 static uint8_t* align1k(void* p) { return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023); }
 
 int phm_tc_fwd(const float* x, const float* A, const float* W, const float* bias, const float* residual, float* y, int rows,
-               int in_features, int out_features, int phm_dim, int act, int, void* workspace, cudaStream_t stream) {
+               int in_features, int out_features, int phm_dim, int act, int precision, void* workspace, cudaStream_t stream) {
   const int n = phm_dim, K = in_features / n, P = out_features / n;
+  const int single = precision == 2;
   uint8_t* buf = align1k(workspace);
-  int rc = tc::launch_pack(A, W, n, K, P, buf, stream);
+  int rc = tc::launch_pack(A, W, n, K, P, buf, single, stream);
   if (rc) return rc;
   const tc::PackLayout L = tc::pack_layout(n, K, P);
   tc::MixParams p{};
@@ -1171,23 +1188,31 @@ int phm_tc_fwd(const float* x, const float* A, const float* W, const float* bias
   p.bias = bias; p.residual = residual; p.C = y;
   p.M = rows; p.n = n; p.Kin = K; p.Pout = P; p.S = n * K; p.chunks = L.chunks_fwd; p.ptiles = L.pt_fwd; p.act = act;
   p.num_tiles = phc_div_up(rows, tc::BM) * n * p.ptiles;
+  p.single = single;
   p.prof = g_phm_tc_prof;
   return tc::launch_mix(p, stream);
 }
 
 int phm_tc_bwd(const float* gy, const float* x, const float* A, const float* W, float* dx, float* dA, float* dW, float* db, int rows,
-               int in_features, int out_features, int phm_dim, int, void* workspace, cudaStream_t stream) {
+               int in_features, int out_features, int phm_dim, int precision, void* workspace, const void* fwd_pack, cudaStream_t stream) {
   const int n = phm_dim, K = in_features / n, P = out_features / n;
+  const int single = precision == 2;
   uint8_t* buf = align1k(workspace);
   const tc::PackLayout L = tc::pack_layout(n, K, P);
   if (dx) {
-    int rc = tc::launch_pack(A, W, n, K, P, buf, stream);
-    if (rc) return rc;
+    // the forward call already wrote both operand packs (same A, W); reuse them when the caller kept that workspace
+    const uint8_t* pk = fwd_pack ? align1k(const_cast<void*>(fwd_pack)) : buf;
+    if (!fwd_pack) {
+      int rc0 = tc::launch_pack(A, W, n, K, P, buf, single, stream);
+      if (rc0) return rc0;
+    }
+    int rc = PHC_OK;
     tc::MixParams p{};
-    p.X = gy; p.coef = reinterpret_cast<const float*>(buf + L.coef_dx); p.Bpack = buf + L.pack_dx;
+    p.X = gy; p.coef = reinterpret_cast<const float*>(pk + L.coef_dx); p.Bpack = pk + L.pack_dx;
     p.C = dx;
     p.M = rows; p.n = n; p.Kin = P; p.Pout = K; p.S = n * P; p.chunks = L.chunks_dx; p.ptiles = L.pt_dx; p.act = PHC_ACT_IDENTITY;
     p.num_tiles = phc_div_up(rows, tc::BM) * n * p.ptiles;
+    p.single = single;
     rc = tc::launch_mix(p, stream);
     if (rc) return rc;
   }
@@ -1198,6 +1223,7 @@ int phm_tc_bwd(const float* gy, const float* x, const float* A, const float* W, 
   d.tiles_m = phc_div_up(in_features, tc::BM); d.tiles_n = phc_div_up(out_features, tc::BN);
   d.splits = tc::dh_splits(rows, in_features, out_features, &d.rows_per_split);
   d.num_tiles = d.tiles_m * d.tiles_n * d.splits;
+  d.single = single;
   int rc = tc::try_launch_dh_tma(d, stream);
   if (rc < 0) {
     static bool configured = false;

@@ -90,6 +90,29 @@ def test_model_tensor_core_mode_matches_oracle(wl_name, graphs, monkeypatch):
     _compare(got, want, RTOL, wl_name, noise)
 
 
+def test_model_bf16_mode_within_stated_tolerance(monkeypatch):
+    """PHC_PRECISION=bf16: logits within 3e-2 (relative to their scale) of the fp64 oracle, loss within 1e-2."""
+    monkeypatch.setenv("PHC_PRECISION", "bf16")
+    from phc.hypercomplex.undirectional.models import PHMSkipConnectAdd
+    from phc_gnn_b200.synthetic import workloads, make_batch
+    import numpy as np
+    wl = workloads(4)["hiv"]
+    cfg = dict(wl.model)
+    cfg["dropout_mpnn"] = [0.0] * 2
+    cfg["dropout_dn"] = [0.0] * 2
+    torch.manual_seed(0)
+    np.random.seed(0)
+    state = PHMSkipConnectAdd(**cfg).state_dict()
+    batch = make_batch(wl, seed=3, batch_graphs=128)
+    got = product_train_eval(cfg, state, batch, wl.loss, 0.01, DEV)
+    want = oracle_train_eval(cfg, state, batch, wl.loss, 0.01, torch.float64)
+    scale = float(want["logits"].abs().max())
+    assert float((got["logits"] - want["logits"]).abs().max()) <= 3e-2 * scale
+    assert abs(float(got["loss"]) - float(want["loss"])) <= 1e-2 * abs(float(want["loss"]))
+    for k, g in want["grads"].items():
+        assert torch.isfinite(got["grads"][k]).all(), k
+
+
 def test_training_step_is_bitwise_reproducible(monkeypatch):
     monkeypatch.setenv("PHC_PRECISION", "fp32")
     fx = load_golden("hiv_n4_softmax_mlp")

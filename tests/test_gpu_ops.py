@@ -267,6 +267,16 @@ def test_phm_linear_tf32x3_tensor_core(n, fin, fout, M):
     _phm_linear_case(n, fin, fout, M, precision=1, rtol=RTOL)
 
 
+BF16_RTOL = 2e-2    # stated tolerance of the bf16-operand tensor-core mode (8-bit mantissa operands, fp32 accumulate)
+
+
+@pytest.mark.parametrize("n,fin,fout,M", [(4, 500, 500, 1000), (2, 180, 180, 3000), (4, 200, 200, 3333), (1, 224, 56, 2000),
+                                          (5, 200, 200, 777), (4, 512, 256, 64)])
+def test_phm_linear_bf16_tensor_core(n, fin, fout, M):
+    """"bf16" precision mode: operands rounded to bf16, single tensor-core pass, fp32 accumulation."""
+    _phm_linear_case(n, fin, fout, M, precision=2, rtol=BF16_RTOL)
+
+
 def test_phm_linear_tensor_core_is_deterministic():
     from phc_gnn_b200 import ops
     g = torch.Generator().manual_seed(3)

@@ -48,7 +48,7 @@ if __name__ == "__main__":
         x = torch.randn(M, F, device=DEV, requires_grad=True); A = torch.randn(n, n, n, device=DEV, requires_grad=True)
         W = torch.randn(n, F // n, F // n, device=DEV, requires_grad=True); b = torch.randn(F, device=DEV, requires_grad=True)
         gy = torch.randn(M, F, device=DEV)
-        for prec in (0, 1):
+        for prec in (0, 1, 2):
             for _ in range(3):
                 y = ops.phm_linear(x, A, W, b, precision=prec); y.backward(gy)
             e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
