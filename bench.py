@@ -168,6 +168,11 @@ def cpu_baseline(wl, budget_s: float = 25.0):
                       f"(torch CPU, {cores} threads), {dt:.1f} s"}
 
 
+# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the aggregation forward kernel from the
+# committed ncu --set full capture of this same command (profiles/r01_fused_conv_and_tc_kernels_ncu.txt)
+NCU_TRAFFIC_BYTES = {"ppa": 41.93e6 + 5.19e6}
+
+
 def aggregation_bytes(N, E, F, softmax):
     """Algorithmic HBM bytes of one fused aggregation forward."""
     return 4 * F * (2 * N + E) + 8 * E + 4 * (N + 1) + (8 * N * F if softmax else 0)
@@ -344,7 +349,8 @@ def run_b200(args):
             byt = aggregation_bytes(N, E, F, softmax)                 # SURVEY 8(d) unit: one layer's propagate
             us = 1e3 * agg_ms / calls
             ach = byt / us / 1e3
-            roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": NCU_TRAFFIC_BYTES.get(wl.name) if fused else None,
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": byt, "avg_launch_us": us,
                     "share_of_step": agg_ms / ms_instr, "timed": "CUDA events around each launch, instrumented repeat of the K steps"}
             if fused:

@@ -129,7 +129,7 @@ __device__ __forceinline__ void edge_embed_t(const LinRegs<DT>& lr, const EncDes
 }
 
 template <int RED, int DT>
-__global__ void conv_fwd_kernel(const EncDesc enc, const float* __restrict__ x, const void* __restrict__ attr, const int* __restrict__ rowptr,
+__global__ void __launch_bounds__(256, 4) conv_fwd_kernel(const EncDesc enc, const float* __restrict__ x, const void* __restrict__ attr, const int* __restrict__ rowptr,
                                 const int* __restrict__ col, const int* __restrict__ perm, int N, int F, int rpi, int act,
                                 const float* __restrict__ beta_ptr, int self_loop, float* __restrict__ out, float* __restrict__ aux_f,
                                 int* __restrict__ aux_i) {

