@@ -159,6 +159,14 @@ int phc_weight_reg_fwd(const float* const* weights, const int* phm_dims, const i
 int phc_weight_reg_bwd(const float* gout, const float* const* weights, float* const* dweights, const int* phm_dims, const int* kp,
                        int count, phc_stream_t stream);
 
+/* ---- clip_grad_norm_(max_norm) + Adam.step() on one flat buffer (train_hiv.py:199-201) --------------------
+ * coef = min(1, max_norm/(||grads||_2 + 1e-6)) (max_norm <= 0: no clipping); Adam with weight_decay 0;
+ * bias_correction{1,2} = 1 - beta^t computed by the caller.  grad_norm_out (optional) receives ||grads||_2. */
+size_t phc_adam_workspace_bytes(void);
+int phc_adam_clip_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long numel, float lr, float beta1,
+                       float beta2, float eps, float bias_correction1, float bias_correction2, float max_norm, float* grad_norm_out,
+                       void* workspace, size_t workspace_bytes, phc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

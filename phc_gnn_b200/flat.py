@@ -31,10 +31,29 @@ def is_packed(flat: Optional[torch.Tensor], tensors: Sequence[torch.Tensor]) -> 
     return off == flat.numel()
 
 
+def view_if_contiguous(tensors: Sequence[torch.Tensor]) -> Optional[torch.Tensor]:
+    """If ``tensors`` already sit back to back inside one storage (e.g. because a larger flat buffer — the optimizer's —
+    contains them in this order), return a flat view over exactly that memory; otherwise None."""
+    t0 = tensors[0]
+    base, esz, off = t0.data_ptr(), t0.element_size(), 0
+    for t in tensors:
+        if t.device != t0.device or t.dtype != t0.dtype or not t.is_contiguous() or t.data_ptr() != base + off * esz:
+            return None
+        off += t.numel()
+    st = t0.untyped_storage()
+    start = base - st.data_ptr()
+    if start < 0 or start % esz or start + off * esz > st.nbytes():
+        return None
+    return torch.empty(0, dtype=t0.dtype, device=t0.device).set_(st, start // esz, (off,))
+
+
 def alias_flat(flat: Optional[torch.Tensor], tensors: Sequence[torch.Tensor]) -> torch.Tensor:
     """Return a 1-D tensor whose storage IS the concatenation of ``tensors`` (re-packing if needed)."""
     if is_packed(flat, tensors):
         return flat
+    v = view_if_contiguous(tensors)
+    if v is not None:
+        return v
     with torch.no_grad():
         t0 = tensors[0]
         total = sum(t.numel() for t in tensors)

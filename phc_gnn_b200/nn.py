@@ -814,7 +814,13 @@ class PHMSkipConnectConcat(_PHMSkipConnectBase):
 # ============================================================================ regularisers
 def phm_weight_regularization(model, p: int = 2, device=None):
     """sum over modules with a ``W`` of W.norm(p, dim=0).mean() — reference regularization.py:15-23."""
-    ws = [w for _, module in model.named_modules() for w in (getattr(module, "W", None),) if w is not None]
+    ws = getattr(model, "_phc_W_cache", None)       # the module tree is static: walk it once
+    if ws is None:
+        ws = [w for _, module in model.named_modules() for w in (getattr(module, "W", None),) if w is not None]
+        try:
+            object.__setattr__(model, "_phc_W_cache", ws)
+        except Exception:
+            pass
     if p == 2 and ws and all(w.is_cuda and w.dim() == 3 for w in ws) and len(ws) <= 256:
         return ops.weight_regularization_l2(ws)              # one fused kernel pair (csrc/regularizer.cu)
     reg = 0.0

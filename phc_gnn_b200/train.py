@@ -49,10 +49,19 @@ def make_optimizer(model, lr: float):
 
 
 class TrainStep(object):
+    """optimizer=None -> the flat two-kernel clip+Adam (optim.FlatClipAdam, same update rule); pass a torch optimizer
+    (e.g. make_optimizer(model, lr)) to run the reference's torch.optim.Adam + clip_grad_norm_ instead."""
+
     def __init__(self, model, workload: Workload, optimizer=None, dp=None):
+        from .optim import FlatClipAdam
         self.model = model
         self.wl = workload
-        self.opt = optimizer if optimizer is not None else make_optimizer(model, workload.lr)
+        self.flat_opt = optimizer is None and next(model.parameters()).is_cuda
+        if self.flat_opt:
+            make_optimizer(model, workload.lr)     # keeps the scripts' "blocks cover all parameters" assertion
+            self.opt = FlatClipAdam(model, lr=workload.lr, max_norm=workload.grad_clip)
+        else:
+            self.opt = optimizer if optimizer is not None else make_optimizer(model, workload.lr)
         self.dp = dp                      # DataParallelPHC wrapper or None
         self.params = [p for p in model.parameters()]
 
@@ -64,6 +73,9 @@ class TrainStep(object):
         if wl.weight_decay > 0.0:
             loss = loss + wl.lr * wl.weight_decay * phm_weight_regularization(self.model, p=2)
         loss.backward()
+        if self.flat_opt:
+            self.opt.step(reduce=self.dp is not None, reduce_group=self.dp.group if self.dp is not None else None)
+            return loss.detach()
         if self.dp is not None:
             self.dp.reduce_gradients()
         if wl.grad_clip > 0.0:

@@ -142,3 +142,40 @@ def test_module_pickles_and_moves_between_devices():
     m.load_state_dict(fx["state"])
     y1 = m(fx["batch"].to(DEV))
     assert torch.equal(y1, y2)
+
+
+def test_flat_clip_adam_matches_torch(monkeypatch):
+    """optim.FlatClipAdam (2 launches) == clip_grad_norm_(max_norm) + torch.optim.Adam fed the SAME gradients (model b's
+    gradients are copied into model a, so the comparison checks the update rule, not two chaotic trajectories)."""
+    monkeypatch.setenv("PHC_PRECISION", "fp32")
+    from gpu_util import product_model
+    from phc_gnn_b200.optim import FlatClipAdam
+    from phc_gnn_b200.train import task_loss
+    fx = load_golden("hiv_n4_softmax_mlp")
+    data = fx["batch"].to(DEV)
+    ma, mb = product_model(fx["cfg"], fx["state"], DEV), product_model(fx["cfg"], fx["state"], DEV)
+    mb.train()
+    opt_a = torch.optim.Adam(ma.parameters(), lr=1e-2)
+    opt_b = FlatClipAdam(mb, lr=1e-2, max_norm=0.5)
+    pa = dict(ma.named_parameters())
+    for it in range(4):
+        opt_b.zero_grad()
+        (task_loss(mb(data), data.y, "bce") * 50).backward()
+        for k, p in mb.named_parameters():
+            pa[k].grad = None if p.grad is None else p.grad.detach().clone()
+        na = torch.nn.utils.clip_grad_norm_(list(ma.parameters()), max_norm=0.5)
+        opt_a.step()
+        opt_b.step()
+        assert_close(opt_b.grad_norm.cpu(), na.cpu(), 1e-5, 1e-7, "grad norm")
+        for k, p in mb.named_parameters():
+            if p.grad is not None:
+                assert_close(p.detach().cpu(), pa[k].detach().cpu(), 1e-5, 1e-6, f"step {it}: {k}")
+                pa[k].data.copy_(p.detach())          # keep both trajectories on the same point
+    # the model still works after its parameters were re-pointed into the flat buffer, and pickles
+    import io
+    buf = io.BytesIO()
+    torch.save(mb, buf)
+    mb.eval()
+    with torch.no_grad():
+        y = mb(data)
+    assert torch.isfinite(y).all()

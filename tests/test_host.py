@@ -105,6 +105,16 @@ def test_flat_alias_repacks_after_data_swap():
     assert is_packed(flat2, ps) and torch.equal(flat2[3:], torch.zeros(3))
 
 
+def test_flat_alias_reuses_enclosing_buffer():
+    from phc_gnn_b200.flat import alias_flat
+    big = torch.arange(10.0)
+    ps = [torch.nn.Parameter(torch.zeros(2)), torch.nn.Parameter(torch.zeros(3))]
+    ps[0].data = big[4:6]
+    ps[1].data = big[6:9]                                 # back to back inside a larger buffer (the optimizer's)
+    v = alias_flat(None, ps)
+    assert v.data_ptr() == big[4:].data_ptr() and v.numel() == 5 and torch.equal(v, big[4:9])
+
+
 def test_cpu_tensors_are_refused():
     from phc.hypercomplex.layers import PHMLinear
     lin = PHMLinear(8, 8, 4, c_init="standard")
