@@ -151,6 +151,21 @@ int phc_conv_fused_bwd(const float* gout, const float* x, const void* edge_attr,
 int phc_edge_feature_sums(const void* edge_attr, int enc_kind, int enc_dim, const int* vocab, const int* rowptr, const int* perm,
                           int num_nodes, int mean, float* node_sums, phc_stream_t stream);
 
+/* ---- principal-neighbourhood aggregation (messagepassing.py:421-438 PHMPNAConvSimple.message/aggregate;
+ * aggregator.py:70-93 aggregators, :112-135 scalers; utils.py:122-135 phm_cat) -------------------------------
+ * out[i, c, s, t, j] = scale_s(deg_i) * AGG_t{act(x[src(e)] + ea[e]) : dst(e) = i}[c*F/n + j], out is [N, S*T*F].
+ * aggr_code / scaler_code: the lists packed 4 bits per entry, first entry in the lowest nibble, 0 terminates.
+ * aggregators: 1 sum, 2 mean, 3 min, 4 max, 5 var, 6 std.  scalers: 1 identity, 2 amplification, 3 attenuation,
+ * 4 linear, 5 inverse_linear.  aux_f [2,N,F] (mean, var; needed by var/std), aux_i [2,N,F] (argmin, argmax edge
+ * ids; needed by min/max) are written by fwd for bwd.  bwd writes dx [N,F] and dea [E,F]. */
+int phc_pna_aggregate_fwd(const float* x, const float* ea, const int* rowptr, const int* col, const int* perm, int num_nodes, int width,
+                          int phm_dim, int msg_act, unsigned long long aggr_code, unsigned long long scaler_code, float avg_deg_log,
+                          float avg_deg_lin, float* out, float* aux_f, int* aux_i, phc_stream_t stream);
+int phc_pna_aggregate_bwd(const float* gout, const float* x, const float* ea, const float* aux_f, const int* aux_i, const int* rowptr,
+                          const int* col, const int* perm, const int* rowptr_t, const int* col_t, const int* perm_t, int num_nodes,
+                          int width, int phm_dim, int msg_act, unsigned long long aggr_code, unsigned long long scaler_code,
+                          float avg_deg_log, float avg_deg_lin, float* dx, float* dea, phc_stream_t stream);
+
 /* ---- weight regulariser (regularization.py:15-23): out = sum_l mean_{k,p} ||W_l[:,k,p]||_2 ------------
  * weights / dweights: HOST arrays of device pointers to the [n_l, K_l, P_l] weight tensors; kp[l] = K_l*P_l. */
 size_t phc_weight_reg_workspace_bytes(int count);

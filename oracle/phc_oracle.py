@@ -146,10 +146,85 @@ def propagate(x, edge_index, edge_emb, aggr, msg_encoder, beta=None):
     return aggregate(msg, edge_index[1], x.size(0), aggr, beta)
 
 
+# ----------------------------------------------------------------------------- PNA
+def phm_cat(tensors, n: int) -> torch.Tensor:
+    """component-wise concatenation (utils.py:122-135): result[:, c] = cat_i tensors[i][:, c]."""
+    parts = [t.reshape(t.size(0), n, -1) for t in tensors]
+    return torch.cat(parts, dim=-1).reshape(tensors[0].size(0), -1)
+
+
+def pna_avg_deg(deg: torch.Tensor) -> Dict[str, float]:
+    """PHMPNAConvSimple.__init__ (messagepassing.py:376-381): plain means over the histogram tensor."""
+    d = deg.to(torch.float)
+    return {"lin": d.mean().item(), "log": (d + 1).log().mean().item(), "exp": d.exp().mean().item()}
+
+
+def pna_aggregate(msg: torch.Tensor, index: torch.Tensor, size: int, n: int, aggregators, scalers, avg_deg) -> torch.Tensor:
+    """PHMPNAConvSimple.aggregate (messagepassing.py:426-438) with aggregator.py:70-93 / :112-135."""
+    cnt = seg_sum(torch.ones(msg.size(0), 1, dtype=msg.dtype), index, size)
+
+    def mean(v):
+        return seg_sum(v, index, size) / cnt.clamp(min=1)
+
+    def one(name):
+        if name == "sum":
+            return seg_sum(msg, index, size)
+        if name == "mean":
+            return mean(msg)
+        if name == "min":
+            return seg_ext(msg, index, size, "amin")
+        if name == "max":
+            return seg_ext(msg, index, size, "amax")
+        var = mean(msg * msg) - mean(msg) * mean(msg)
+        return var if name == "var" else torch.sqrt(torch.relu(var) + 1e-5)
+
+    out = phm_cat([one(a) for a in aggregators], n)
+    deg = cnt                                            # torch_geometric.utils.degree(index, dim_size).view(-1, 1)
+
+    def scale(name):
+        if name == "identity":
+            return out
+        if name == "amplification":
+            return out * (torch.log(deg + 1) / avg_deg["log"])
+        if name == "attenuation":
+            sc = avg_deg["log"] / torch.log(deg + 1)
+            return out * torch.where(deg == 0, torch.ones_like(sc), sc)
+        if name == "linear":
+            return out * (deg / avg_deg["lin"])
+        if name == "inverse_linear":
+            sc = avg_deg["lin"] / deg
+            return out * torch.where(deg == 0, torch.ones_like(sc), sc)
+        raise ValueError(name)
+
+    return phm_cat([scale(sname) for sname in scalers], n)
+
+
+def pna_conv(x, edge_index, edge_emb, p: Params, key: str, cfg: Dict, training: bool) -> torch.Tensor:
+    """PHMPNAConvSimple.forward (messagepassing.py:408-419): the dispatcher hard-wires msg_encoder="relu"
+    (messagepassing.py:490); no self term; transform = PHMLinear [-> PHMNorm -> act -> PHMLinear]*(post_layers-1)."""
+    n = cfg["phm_dim"]
+    msg = activation(x[edge_index[0]] + edge_emb, "relu")
+    h = pna_aggregate(msg, edge_index[1], x.size(0), n, cfg["aggregators"], cfg["scalers"], pna_avg_deg(cfg["deg"]))
+    t = key + ".transform.transform"
+    h = phm_linear(h, p, t + ".0")
+    idx = 1
+    for _ in range(int(cfg.get("post_layers") or 1) - 1):
+        if cfg["norm_mp"] not in (None, "None"):
+            h = phm_norm(h, p, f"{t}.{idx}", n, training)
+            idx += 1
+        h = activation(h, cfg["activation"])
+        idx += 1
+        h = phm_linear(h, p, f"{t}.{idx}")
+        idx += 1
+    return h
+
+
 # ----------------------------------------------------------------------------- layers
 def conv(x, edge_index, edge_emb, p: Params, key: str, cfg: Dict, training: bool) -> torch.Tensor:
     """PHMMessagePassing dispatch (messagepassing.py:481-507): key is ``convs.{i}``."""
     n = cfg["phm_dim"]
+    if cfg["msg_aggr"] == "pna":
+        return pna_conv(x, edge_index, edge_emb, p, key, cfg, training)
     aggr = "add" if cfg["msg_aggr"] == "sum" else cfg["msg_aggr"]
     beta = p.get(key + ".transform.beta")
     agg = propagate(x, edge_index, edge_emb, aggr, cfg["msg_encoder"], beta)

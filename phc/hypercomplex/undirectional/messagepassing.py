@@ -1,2 +1,2 @@
 from phc_gnn_b200.nn import (PHMConv, PHMGINEConv, PHMConvSoftmax, PHMGINEConvSoftmax,  # noqa: F401
-                             PHMMessagePassing)
+                             PHMPNAConvSimple, PHMMessagePassing)

@@ -349,6 +349,14 @@ int phc_aggregate_bwd_node_simple(bool mean, const float* g, const int* rowptr, 
   return dispatch_bwd_node<1>(true, mean, g, nullptr, rowptr, rowptr_t, col_t, perm_t, N, F, self_loop, dx, stream);
 }
 
+// input gradient as the sum of already computed per-edge gradient rows over each node's out-edges — shared with pna.cu
+int phc_aggregate_bwd_node_from_edges(const float* dea, const int* rowptr_t, const int* col_t, const int* perm_t, int N, int F, float* dx,
+                                      cudaStream_t stream) {
+  if (F % 4 == 0 && phc_aligned16(dea) && phc_aligned16(dx))
+    return dispatch_bwd_node<4>(false, false, nullptr, dea, nullptr, rowptr_t, col_t, perm_t, N, F, 0, dx, stream);
+  return dispatch_bwd_node<1>(false, false, nullptr, dea, nullptr, rowptr_t, col_t, perm_t, N, F, 0, dx, stream);
+}
+
 extern "C" {
 
 int phc_aggregate_fwd(const float* x, const float* ea, const int* rowptr, const int* col, const int* perm, int num_nodes, int width,

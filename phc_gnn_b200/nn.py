@@ -598,6 +598,69 @@ class PHMGINEConvSoftmax(PHMGINEConv):
                          w_init, c_init, "softmax", msg_encoder, **kwargs)
 
 
+class PHMPNAConvSimple(nn.Module):
+    """Principal-neighbourhood aggregation conv — reference messagepassing.py:339-453: relu(x_j + e) messages,
+    aggregators x degree scalers concatenated component-wise (one kernel, csrc/pna.cu), then
+    ``transform`` = PHMLinear(S*T*F -> F) [-> PHMNorm -> act -> PHMLinear(F -> F)] * (post_layers - 1).  No self term.
+    As in the reference the inner PHMLinears always learn their rule (``learn_phm`` is not forwarded, :386-399)."""
+
+    def __init__(self, in_features: int, out_features: int, phm_dim: int, phm_rule, learn_phm: bool, bias: bool, activation: str,
+                 norm: Optional[str], w_init: str, c_init: str, deg: torch.Tensor,
+                 aggregators: List[str] = ["mean", "min", "max", "std"],
+                 scalers: List[str] = ["identity", "amplification", "attenuation"], post_layers: int = 1,
+                 msg_encoder: str = "relu", **kwargs):
+        super().__init__()
+        self.in_features, self.out_features, self.bias_flag, self.activation_str = in_features, out_features, bias, activation
+        self.norm, self.phm_dim, self.phm_rule, self.w_init, self.c_init, self.learn_phm = norm, phm_dim, phm_rule, w_init, c_init, learn_phm
+        self.aggregators_l, self.scalers_l = list(aggregators), list(scalers)
+        for a in self.aggregators_l:
+            ops.PNA_AGGREGATOR_IDS[a]                      # KeyError on unknown names, like AGGREGATORS[aggr]
+        for sc in self.scalers_l:
+            ops.PNA_SCALER_IDS[sc]
+        self.F_in, self.F_out = in_features, out_features
+        self.deg = deg.to(torch.float)
+        self.avg_deg = {"lin": self.deg.mean().item(), "log": (self.deg + 1).log().mean().item(),
+                        "exp": self.deg.exp().mean().item()}
+        wide = len(self.aggregators_l) * len(self.scalers_l) * in_features
+        modules = [PHMLinear(in_features=wide, out_features=out_features, bias=bias, phm_dim=phm_dim, phm_rule=phm_rule,
+                             w_init=w_init, c_init=c_init)]
+        self.post_layers = post_layers
+        for _ in range(post_layers - 1):
+            if self.norm:
+                modules += [PHMNorm(num_features=out_features, phm_dim=phm_dim, type="naive-batch-norm")]
+            modules += [get_module_activation(activation)]
+            modules += [PHMLinear(in_features=out_features, out_features=out_features, bias=bias, phm_dim=phm_dim,
+                                  phm_rule=phm_rule, w_init=w_init, c_init=c_init)]
+        self.transform = nn.Sequential(*modules)
+        self.msg_encoder_str = msg_encoder
+        assert msg_encoder.lower() in _ACTIVATIONS
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        for m in self.transform:
+            if hasattr(m, "reset_parameters"):
+                m.reset_parameters()
+
+    def propagate(self, x, edge_index, edge_attr):
+        struct = edge_structure(edge_index, x.size(0))
+        if edge_attr is None:                                # message() returns x_j unchanged (messagepassing.py:422)
+            edge_attr, act = torch.zeros((edge_index.size(1), x.size(1)), dtype=x.dtype, device=x.device), "identity"
+        else:
+            act = self.msg_encoder_str.lower()
+        return ops.pna_aggregate(x, edge_attr, struct, self.phm_dim, self.aggregators_l, self.scalers_l,
+                                 self.avg_deg["log"], self.avg_deg["lin"], msg_act=act)
+
+    def forward(self, x, edge_index, edge_attr=None, size=None):
+        return self.transform(self.propagate(x, edge_index, edge_attr))
+
+    def can_fuse_layer(self, outer_norm) -> bool:
+        return False
+
+    def __repr__(self):
+        return (f"{self.__class__.__name__}(in_features={self.in_features}, out_features={self.out_features}, phm_dim={self.phm_dim}, "
+                f"aggregators={self.aggregators_l}, scalers={self.scalers_l}, post_layers={self.post_layers})")
+
+
 class PHMMessagePassing(nn.Module):
     """Dispatcher over the conv operators — reference messagepassing.py:456-518."""
 
@@ -610,8 +673,12 @@ class PHMMessagePassing(nn.Module):
         self.activation_str, self.w_init, self.c_init, self.aggr = activation, w_init, c_init, aggr
         self.mlp, self.same_dim, self.msg_encoder_str = mlp, same_dim, msg_encoder
         if aggr == "pna":
-            raise NotImplementedError("aggr='pna' (PHMPNAConvSimple) is not built yet — SURVEY.md §8(f) rank 3")
-        if aggr == "softmax":
+            self.transform = PHMPNAConvSimple(in_features=in_features, out_features=out_features, phm_dim=phm_dim, phm_rule=phm_rule,
+                                              learn_phm=learn_phm, bias=bias, activation=activation, norm=norm, w_init=w_init,
+                                              c_init=c_init, deg=kwargs.get("deg"), aggregators=kwargs.get("aggregators"),
+                                              scalers=kwargs.get("scalers"), post_layers=kwargs.get("post_layers"),
+                                              msg_encoder="relu")
+        elif aggr == "softmax":
             if mlp:
                 self.transform = PHMGINEConvSoftmax(in_features, out_features, phm_dim, phm_rule, learn_phm, bias, add_self_loops,
                                                     norm, activation, w_init, c_init, aggr, msg_encoder, **kwargs)
@@ -756,7 +823,8 @@ class PHMSkipConnectAdd(_PHMSkipConnectBase):
             else:
                 raise ValueError
             enc = self.bondencoders[i]
-            if self.fuse_edge_encoder and isinstance(enc, PHMEncoder) and enc.can_fuse(h.size(1)):
+            pna = isinstance(self.convs[i].transform, PHMPNAConvSimple)       # PNA reads the materialised edge embedding
+            if self.fuse_edge_encoder and not pna and isinstance(enc, PHMEncoder) and enc.can_fuse(h.size(1)):
                 conv = self.convs[i].transform
                 if self.fuse_layer and conv.can_fuse_layer(self.norms[i]):
                     # the whole layer (conv + norm + act + dropout + skip) as one autograd node

@@ -46,7 +46,8 @@ _KERNELS = {"phc_csr_build": 6, "phc_segment_ptr_build": 2, "phc_aggregate_fwd":
             "phc_segment_pool_fwd": 1, "phc_segment_pool_bwd": 1, "phc_bn_act_drop_skip_fwd": 3, "phc_bn_act_drop_skip_bwd": 3,
             "phc_embed_sum_fwd": 1, "phc_embed_sum_bwd": 2, "phc_linear_encoder_fwd": 1, "phc_linear_encoder_bwd": 2,
             "phc_phm_linear_fwd": 2, "phc_phm_linear_bwd": 8, "phc_weight_reg_fwd": 2, "phc_weight_reg_bwd": 1,
-            "phc_conv_fused_fwd": 1, "phc_conv_fused_bwd": 3, "phc_edge_feature_sums": 1}
+            "phc_conv_fused_fwd": 1, "phc_conv_fused_bwd": 3, "phc_edge_feature_sums": 1, "phc_pna_aggregate_fwd": 1,
+            "phc_pna_aggregate_bwd": 2, "phc_adam_clip_step": 2}
 
 
 def run(name: str, device, *args, tag: str = ""):
@@ -145,6 +146,66 @@ class _PHMLinear(torch.autograd.Function):
 def phm_linear(x, rule, W, bias=None, residual=None, precision: Optional[int] = None) -> torch.Tensor:
     """y = x @ (sum_b rule[b] (x) W[b]) + bias (+ residual)   — reference layers.py:198-219."""
     return _PHMLinear.apply(x, rule, W, bias, residual, default_precision() if precision is None else precision)
+
+
+# --------------------------------------------------------------------------------- PNA aggregation
+PNA_AGGREGATOR_IDS = {"sum": 1, "mean": 2, "min": 3, "max": 4, "var": 5, "std": 6}
+PNA_SCALER_IDS = {"identity": 1, "amplification": 2, "attenuation": 3, "linear": 4, "inverse_linear": 5}
+
+
+def _pna_code(names: Sequence[str], table) -> int:
+    if not 1 <= len(names) <= 8:
+        raise ValueError("PNA supports 1..8 aggregators / scalers")
+    code = 0
+    for i, nm in enumerate(names):
+        code |= table[nm] << (4 * i)            # KeyError on an unknown name, like the reference's dict lookup
+    return code
+
+
+class _PnaAggregate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, ea, struct: EdgeStructure, n: int, msg_act: int, acode: int, scode: int, T: int, S: int, avg_log: float,
+                avg_lin: float, need_f: bool, need_i: bool):
+        x = _f32c(x, "x"); ea = _f32c(ea, "edge_attr")
+        N, F = x.shape
+        assert N == struct.num_nodes, "x rows do not match the graph structure"
+        assert ea.size(0) == struct.num_edges and ea.size(-1) == F, \
+            f"edge_attr must be [E={struct.num_edges}, F={F}] (got {tuple(ea.shape)})"
+        out = torch.empty((N, S * T * F), dtype=torch.float32, device=x.device)
+        aux_f = torch.empty((2, N, F), dtype=torch.float32, device=x.device) if need_f else None
+        aux_i = torch.empty((2, N, F), dtype=torch.int32, device=x.device) if need_i else None
+        run("phc_pna_aggregate_fwd", None, x.data_ptr(), ea.data_ptr(), struct.rowptr.data_ptr(), struct.col.data_ptr(),
+            struct.perm.data_ptr(), N, F, n, msg_act, acode, scode, avg_log, avg_lin, out.data_ptr(), _ptr(aux_f), _ptr(aux_i),
+            _stream(x.device))
+        ctx.save_for_backward(x, ea, aux_f, aux_i)
+        ctx.struct = struct
+        ctx.meta = (n, msg_act, acode, scode, avg_log, avg_lin)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, ea, aux_f, aux_i = ctx.saved_tensors
+        s = ctx.struct
+        n, msg_act, acode, scode, avg_log, avg_lin = ctx.meta
+        g = _f32c(g, "grad_output")
+        N, F = x.shape
+        dx = torch.empty_like(x)
+        dea = torch.empty_like(ea)
+        run("phc_pna_aggregate_bwd", None, g.data_ptr(), x.data_ptr(), ea.data_ptr(), _ptr(aux_f), _ptr(aux_i), s.rowptr.data_ptr(),
+            s.col.data_ptr(), s.perm.data_ptr(), s.rowptr_t.data_ptr(), s.col_t.data_ptr(), s.perm_t.data_ptr(), N, F, n, msg_act,
+            acode, scode, avg_log, avg_lin, dx.data_ptr(), dea.data_ptr(), _stream(x.device))
+        return (dx, dea) + (None,) * 11
+
+
+def pna_aggregate(x, edge_emb, struct: EdgeStructure, phm_dim: int, aggregators: Sequence[str], scalers: Sequence[str],
+                  avg_deg_log: float, avg_deg_lin: float, msg_act: str = "relu") -> torch.Tensor:
+    """[N,F] -> [N, S*T*F]: every aggregator x every degree scaler of act(x[src] + edge_emb), concatenated
+    component-wise (reference messagepassing.py:421-438) — one kernel (csrc/pna.cu)."""
+    acode, scode = _pna_code(aggregators, PNA_AGGREGATOR_IDS), _pna_code(scalers, PNA_SCALER_IDS)
+    need_f = any(a in ("var", "std") for a in aggregators)
+    need_i = any(a in ("min", "max") for a in aggregators)
+    return _PnaAggregate.apply(x, edge_emb, struct, phm_dim, act_id(msg_act), acode, scode, len(aggregators), len(scalers),
+                               float(avg_deg_log), float(avg_deg_lin), need_f, need_i)
 
 
 # --------------------------------------------------------------------------------- aggregation

@@ -56,6 +56,44 @@ def test_aggregate_fwd_bwd(reduce, act, F, self_loop):
         assert_close(bs.grad.cpu(), bo.grad.float(), 1e-3, grad_tol(bo.grad, 1e-3), "dbeta")
 
 
+@pytest.mark.parametrize("aggregators,scalers,act,F,n", [
+    (["mean", "min", "max", "std"], ["identity", "amplification", "attenuation"], "relu", 16, 4),      # the reference default
+    (["sum", "var"], ["linear", "inverse_linear"], "identity", 12, 2),
+    (["std", "max", "mean", "min", "sum", "var"], ["attenuation", "identity"], "swish", 20, 5),
+    (["mean", "min", "max", "std"], ["identity", "amplification", "attenuation"], "elu", 500, 4),      # Fc = 125: scalar stores
+    (["max"], ["identity"], "relu", 7, 1)])
+def test_pna_aggregate_fwd_bwd(aggregators, scalers, act, F, n):
+    """csrc/pna.cu against the oracle restatement of PHMPNAConvSimple.aggregate (fp64); isolated nodes included."""
+    from phc_gnn_b200 import ops
+    from phc_gnn_b200.graph import EdgeStructure
+    N, E = 61, 260
+    ei = _graph(N - 4, E, 5)                     # the last 4 nodes have no edges at all
+    E = ei.size(1)
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(N, F, generator=g)
+    ea = torch.randn(E, F, generator=g)
+    avg = O.pna_avg_deg(torch.tensor([0, 4, 9, 3, 1]))
+    S, T = len(scalers), len(aggregators)
+    gout = torch.randn(N, S * T * F, generator=g)
+    xo, eo = (t.double().requires_grad_(True) for t in (x, ea))
+    msg = O.activation(xo[ei[0]] + eo, act)
+    ref = O.pna_aggregate(msg, ei[1], N, n, aggregators, scalers, avg)
+    ref.backward(gout.double())
+    xs, es = (t.to(DEV).requires_grad_(True) for t in (x, ea))
+    s = EdgeStructure(ei.to(DEV), N)
+    out = ops.pna_aggregate(xs, es, s, n, aggregators, scalers, avg["log"], avg["lin"], msg_act=act)
+    assert out.shape == (N, S * T * F)
+    out.backward(gout.to(DEV))
+    assert_close(out.detach().cpu(), ref.detach().float(), RTOL, 2e-5, "out")
+    # var = E[m^2] - E[m]^2 cancels in fp32: its gradient inherits that relative error through 1/(2 std)
+    loose = 20 if any(a in ("std", "var") for a in aggregators) else 1
+    assert_close(xs.grad.cpu(), xo.grad.float(), loose * RTOL, loose * grad_tol(xo.grad, RTOL), "dx")
+    assert_close(es.grad.cpu(), eo.grad.float(), loose * RTOL, loose * grad_tol(eo.grad, RTOL), "dea")
+    # run-to-run bitwise determinism
+    out2 = ops.pna_aggregate(xs.detach(), es.detach(), s, n, aggregators, scalers, avg["log"], avg["lin"], msg_act=act)
+    assert torch.equal(out2, out.detach())
+
+
 def test_aggregate_empty_rows_and_isolated_nodes():
     from phc_gnn_b200 import ops
     from phc_gnn_b200.graph import EdgeStructure
