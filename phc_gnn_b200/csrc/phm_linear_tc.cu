@@ -709,6 +709,359 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) phm_tc_mix_tma_kernel(const Mi
   cta_epilogue(tmem_base);
 }
 
+// ---------------------------------------------------------------------------- mix kernel v3 (n = 4): A operand in TENSOR MEMORY,
+// two output components per CTA.
+// Measured on B200 (in-kernel role timers, tools/tc_bench.py), the smem-staged kernels above are NOT bound by the
+// tensor pipe: (1) the operand producers are instruction-issue bound (cvt.rna.tf32.f32 is emulated by 4 SASS
+// instructions on sm_100a, ~800 instructions per thread and chunk), (2) every tile pulls 32 KiB of W pack + 24 KiB of raw
+// activations per 32-wide K chunk through L2 (~42 B/clk/SM => ~1300 cycles) and (3) moves ~210 KiB through shared
+// memory (~1640 cycles) against 768 tensor cycles (12 MMAs).  This kernel attacks all three:
+//  * one CTA computes TWO output components of the same 128-row tile, so each W-pack chunk and each raw activation
+//    box is fetched once for two tiles;
+//  * the rule-mixed, tf32-split A operand never touches shared memory: a producer thread owns ONE row of the tile
+//    (TMEM lane == row), mixes its 32 K-columns in registers and writes them with tcgen05.st into a TMEM operand
+//    slot; the MMAs take A from TMEM (tcgen05.mma [d], [a], b_desc), only the W pack is read from shared memory;
+//  * the fp32 -> tf32 big/small split is a mask and a subtract (big = v & ~0x1fff, small = v - big, exact; the tensor
+//    core ignores the low 13 bits of `small`, an error of 2^-21 |v|): 2 instructions instead of 9.
+//   TMEM (512 columns): 2 accumulators x 128 | 2 chunk parities x 2 components x (32 big + 32 small) operand columns
+//   warps 0-15 producers: (lane quarter q, component h of the pair, chunk parity g) = (w & 3, (w >> 2) & 1, w >> 3);
+//   they also drain the accumulators (warp (q,h,g): rows of quarter q, accumulator h, column half g) — the tensor
+//   pipe is idle then anyway, both accumulators being busy.  16 MMA | 17 TMA(x) | 18 TMA(W pack)
+constexpr int V3_NB = 3;                        // W-pack stages (big|small, 32 KiB each)
+constexpr int V3_NR = 2;                        // raw activation stages == chunk parities
+constexpr int V3_RAW_BYTES = BM * 12 * 4 * 4;   // 4 input components x 128 rows x (8 + 4 pad) floats = 24 KiB
+constexpr int V3_A_COL0 = 2 * BN;               // first operand-slot column
+constexpr int V3_TMEM_COLS = 512;
+constexpr int V3_BARS = 2 * V3_NB + 4 * V3_NR + 2;
+constexpr int V3_MMA_WARP = PROD_WARPS, V3_TMA_X_WARP = PROD_WARPS + 1, V3_TMA_B_WARP = PROD_WARPS + 2;
+constexpr int V3_THREADS = (PROD_WARPS + 3) * 32;
+constexpr int V3_SPITCH = 36;                   // floats per scratch row: 16-byte aligned rows, conflict-free both ways
+constexpr int V3_SCRATCH = PROD_WARPS * 32 * V3_SPITCH * 4;
+
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                 "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
+                 "r"(__float_as_uint(v[7]))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// unit u -> (m-tile, p-tile, component pair)
+__device__ __forceinline__ void v3_unit(const MixParams& p, int u, int& m0, int& pair, int& pt) {
+  const int per_m = 2 * p.ptiles;
+  m0 = (u / per_m) * BM;
+  const int r = u % per_m;
+  pair = r & 1;
+  pt = r >> 1;
+}
+
+// One warp drains 32 rows x 64 columns of an accumulator: TMEM -> registers -> smem transpose -> coalesced row stores.
+__device__ __forceinline__ void v3_drain(float* __restrict__ my, uint32_t taddr, float* __restrict__ C, int ldc, int nrows, int r0,
+                                         int col0, int ncols, const float* __restrict__ bias, const float* __restrict__ residual, int act) {
+  const int lane = threadIdx.x & 31;
+  const bool plain = act == PHC_ACT_IDENTITY && residual == nullptr;
+#pragma unroll 1
+  for (int cc = 0; cc < 2; ++cc) {
+    if (cc * 32 >= ncols) break;
+    uint32_t v[32];
+    tmem_ld32(taddr + (uint32_t)(cc * 32), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<float4*>(my + lane * V3_SPITCH + j * 4) =
+          make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+    __syncwarp();
+    const int lc = cc * 32 + lane;
+    if (lc < ncols) {
+      const int col = col0 + lc;
+      const float bv = bias != nullptr ? __ldg(bias + col) : 0.f;
+      float* dst = C + (size_t)r0 * ldc + col;
+      const float* src = my + lane;
+      if (plain && nrows == 32) {
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr) dst[rr * ldc] = src[rr * V3_SPITCH] + bv;
+      } else if (plain) {
+        for (int rr = 0; rr < nrows; ++rr) dst[rr * ldc] = src[rr * V3_SPITCH] + bv;
+      } else {
+        const float* res = residual != nullptr ? residual + (size_t)r0 * ldc + col : nullptr;
+        for (int rr = 0; rr < nrows; ++rr) {
+          float o = act_fwd_rt(act, src[rr * V3_SPITCH] + bv);
+          if (res != nullptr) o += res[rr * ldc];
+          dst[rr * ldc] = o;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// R = Kin & 3: component uu's box starts (uu*R)&3 floats before its first needed float (TMA boxes start 16-byte aligned)
+template <int R, bool SINGLE>
+__global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixParams p, const __grid_constant__ CUtensorMap tmapX) {
+  constexpr int NT = 4, KQ = BK / NT;                       // 8 k values per chunk
+  constexpr int PITCH = R == 0 ? KQ : KQ + 4;               // floats per raw row (must match the tensor map's box)
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* bstage = base;                                                   // [V3_NB][B_big | B_small]
+  uint8_t* rawbuf = base + V3_NB * 2 * TILE_BYTES;                          // [V3_NR][4][128][PITCH]
+  float* scratch = reinterpret_cast<float*>(rawbuf + V3_NR * V3_RAW_BYTES);  // [16 warps][32][V3_SPITCH]
+  float* coef = scratch + PROD_WARPS * 32 * V3_SPITCH;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(coef + NT * NT * NT);
+  uint64_t* bfull = bars;                                  // [V3_NB]
+  uint64_t* bempty = bars + V3_NB;                         // [V3_NB]
+  uint64_t* afull = bars + 2 * V3_NB;                      // [2]
+  uint64_t* aempty = afull + V3_NR;                        // [2]
+  uint64_t* rfull = aempty + V3_NR;                        // [2]
+  uint64_t* rempty = rfull + V3_NR;                        // [2]
+  uint64_t* tfull = rempty + V3_NR;                        // accumulators complete -> drain
+  uint64_t* tempty = tfull + 1;                            // accumulators drained  -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + V3_BARS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < NT * NT * NT; i += V3_THREADS) coef[i] = p.coef[i];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < V3_NB; ++i) { mbar_init(smem_u32(&bfull[i]), 1); mbar_init(smem_u32(&bempty[i]), 1); }
+    for (int i = 0; i < V3_NR; ++i) {
+      mbar_init(smem_u32(&afull[i]), 8);      // the parity's eight producer warps (2 components x 4 lane quarters)
+      mbar_init(smem_u32(&aempty[i]), 1);     // tcgen05.commit
+      mbar_init(smem_u32(&rfull[i]), 1);      // TMA transaction
+      mbar_init(smem_u32(&rempty[i]), 8);
+    }
+    mbar_init(smem_u32(tfull), 1);
+    mbar_init(smem_u32(tempty), PROD_WARPS);
+    fence_barrier_init();
+  }
+  if (warp == V3_MMA_WARP) tmem_alloc(smem_u32(tmem_slot), V3_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int my_units = p.num_tiles > (int)blockIdx.x ? (p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;   // num_tiles = #units
+
+  if (warp < PROD_WARPS) {
+    // ===================================================================== producers (+ accumulator drain)
+    const int q = warp & 3, h = (warp >> 2) & 1, g = warp >> 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const uint32_t a_slot = tmem_base + lane_base + (uint32_t)(V3_A_COL0 + (g * 2 + h) * 64);
+    const uint32_t rawg = smem_u32(rawbuf + g * V3_RAW_BYTES) + (uint32_t)(row * PITCH * 4);
+    float* my = scratch + warp * 32 * V3_SPITCH;
+    const int ldc = p.n * p.Pout;
+    float cf[NT * NT];
+    int cur_comp = -1;
+    const bool prof = p.prof != nullptr && warp == 0 && lane == 0;
+    long long t_rfull = 0, t_aempty = 0, t_work = 0, t_drain = 0, tp = 0;
+
+    auto produce = [&](int gi, int c, int comp) {
+      if (comp != cur_comp) {
+#pragma unroll
+        for (int i = 0; i < NT * NT; ++i) cf[i] = coef[comp * NT * NT + i];      // [b][uu]
+        cur_comp = comp;
+      }
+      const int use = gi >> 1;                                   // how often this parity's stage / slot has been used
+      if (prof) tp = clock64();
+      mbar_wait(smem_u32(&rfull[g]), use & 1);                  // raw boxes landed (TMA)
+      if (prof) { const long long tn = clock64(); t_rfull += tn - tp; tp = tn; }
+      float xr[NT][KQ];
+      uint32_t landed = 0;                                       // data dependence on every load (see the release below)
+#pragma unroll
+      for (int uu = 0; uu < NT; ++uu) {
+        constexpr int NV = PITCH / 4;
+        float t[NV * 4];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(t[4 * v]), "=f"(t[4 * v + 1]), "=f"(t[4 * v + 2]), "=f"(t[4 * v + 3])
+                       : "r"(rawg + (uint32_t)((uu * (BM * PITCH) + v * 4) * 4)));
+          landed |= __float_as_uint(t[4 * v]);
+        }
+        const int off = (uu * R) & 3;                            // compile-time after unrolling
+#pragma unroll
+        for (int k = 0; k < KQ; ++k) xr[uu][k] = t[off + k];
+      }
+      // Early release: the row is in registers, let TMA refill the stage while we mix.  The arrive must not be performed
+      // before the loads have RETURNED (issuing them is not enough: measured as a rare corruption with the short
+      // R = 0 rows).  A shared-memory store of a value that depends on every load cannot issue before they return, and
+      // the arrive (release) stays behind the store.
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(smem_u32(my + lane)), "r"(landed) : "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&rempty[g]));
+      if (c == p.chunks - 1) {                                   // K tail: columns past the component belong to its neighbour
+#pragma unroll
+        for (int k = 0; k < KQ; ++k)
+          if (c * KQ + k >= p.Kin) {
+#pragma unroll
+            for (int uu = 0; uu < NT; ++uu) xr[uu][k] = 0.f;
+          }
+      }
+      if (prof) { const long long tn = clock64(); t_work += tn - tp; tp = tn; }
+      mbar_wait(smem_u32(&aempty[g]), (use & 1) ^ 1);           // the MMAs that read this operand slot have retired
+      if (prof) { const long long tn = clock64(); t_aempty += tn - tp; tp = tn; }
+      tc_fence_after();
+#pragma unroll
+      for (int kp = 0; kp < KQ; kp += 2) {                       // 2 k values = 8 operand columns (column = k*4 + b)
+        float big[8], small[8];
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+          for (int b = 0; b < NT; ++b) {
+            const float v = cf[b * 4] * xr[0][kp + kk] + cf[b * 4 + 1] * xr[1][kp + kk] + cf[b * 4 + 2] * xr[2][kp + kk] +
+                            cf[b * 4 + 3] * xr[3][kp + kk];
+            if (SINGLE) {                                        // bf16 operands: round to nearest (ties away) by add + mask
+              big[kk * 4 + b] = __uint_as_float((__float_as_uint(v) + 0x8000u) & 0xFFFF0000u);
+            } else {
+              big[kk * 4 + b] = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+              small[kk * 4 + b] = v - big[kk * 4 + b];
+            }
+          }
+        tmem_st8(a_slot + kp * 4, big);
+        if (!SINGLE) tmem_st8(a_slot + 32 + kp * 4, small);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&afull[g]));
+      if (prof) t_work += clock64() - tp;
+    };
+    auto drain = [&](int ui) {
+      int m0, pair, pt;
+      v3_unit(p, blockIdx.x + ui * gridDim.x, m0, pair, pt);
+      const int ncols = min(BN, p.Pout - pt * BN) - g * 64;     // valid columns of this warp's half
+      const long long td0 = prof ? clock64() : 0;
+      mbar_wait(smem_u32(tfull), ui & 1);
+      tc_fence_after();
+      const int r0 = m0 + q * 32;
+      if (ncols > 0 && r0 < p.M)
+        v3_drain(my, tmem_base + lane_base + (uint32_t)(h * BN + g * 64), p.C, ldc, min(32, p.M - r0), r0,
+                 (2 * pair + h) * p.Pout + pt * BN + g * 64, ncols, p.bias, p.residual, p.act);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(tempty));
+      if (prof) t_drain += clock64() - td0;
+    };
+
+    int gi0 = 0;                                                 // global chunk index of the unit's first chunk
+    for (int ui = 0; ui < my_units; ++ui, gi0 += p.chunks) {
+      int m0, pair, pt;
+      v3_unit(p, blockIdx.x + ui * gridDim.x, m0, pair, pt);
+      const int comp = 2 * pair + h;
+      int c = (gi0 & 1) == g ? 0 : 1;                            // this parity's first chunk of the unit
+      if (c < p.chunks) { produce(gi0 + c, c, comp); c += 2; }  // ... goes in BEFORE draining the previous unit, so the
+      if (ui > 0) drain(ui - 1);                                 //     tensor pipe restarts the moment the accumulators are free
+      for (; c < p.chunks; c += 2) produce(gi0 + c, c, comp);
+    }
+    if (my_units > 0) drain(my_units - 1);
+    if (prof) {
+      p.prof[blockIdx.x * 8 + 0] = t_rfull; p.prof[blockIdx.x * 8 + 1] = t_work; p.prof[blockIdx.x * 8 + 7] = t_aempty;
+      p.prof[blockIdx.x * 8 + 5] = t_drain;
+    }
+  } else if (warp == V3_TMA_X_WARP) {
+    // ===================================================================== TMA: raw activation boxes
+    if (lane == 0) {
+      int gi = 0;
+      for (int ui = 0; ui < my_units; ++ui) {
+        int m0, pair, pt;
+        v3_unit(p, blockIdx.x + ui * gridDim.x, m0, pair, pt);
+        for (int c = 0; c < p.chunks; ++c, ++gi) {
+          const int rs = gi & 1;
+          mbar_wait(smem_u32(&rempty[rs]), ((gi >> 1) & 1) ^ 1);
+          const uint32_t bar = smem_u32(&rfull[rs]);
+          mbar_arrive_expect_tx(bar, NT * BM * PITCH * 4);
+#pragma unroll
+          for (int uu = 0; uu < NT; ++uu)
+            tma_load_2d(smem_u32(rawbuf + rs * V3_RAW_BYTES + uu * (BM * PITCH * 4)), &tmapX, (uu * p.Kin + c * KQ) & ~3, m0, bar);
+        }
+      }
+    }
+  } else if (warp == V3_TMA_B_WARP) {
+    // ===================================================================== TMA: pre-split W chunks
+    if (lane == 0) {
+      int gi = 0;
+      for (int ui = 0; ui < my_units; ++ui) {
+        int m0, pair, pt;
+        v3_unit(p, blockIdx.x + ui * gridDim.x, m0, pair, pt);
+        for (int c = 0; c < p.chunks; ++c, ++gi) {
+          const int bs = gi % V3_NB;
+          mbar_wait(smem_u32(&bempty[bs]), ((gi / V3_NB) & 1) ^ 1);
+          const uint32_t fb = smem_u32(&bfull[bs]);
+          const uint32_t bbytes = SINGLE ? TILE_BYTES : 2 * TILE_BYTES;
+          mbar_arrive_expect_tx(fb, bbytes);
+          tma_bulk_load(smem_u32(bstage + bs * 2 * TILE_BYTES), p.Bpack + ((size_t)pt * p.chunks + c) * (2 * TILE_BYTES), bbytes, fb);
+        }
+      }
+    }
+  } else {
+    // ===================================================================== MMA issuer: A from TMEM, B from smem
+    int gi = 0;
+    const bool prof = p.prof != nullptr && lane == 0;
+    long long t_tempty = 0, t_afull = 0, t_bfull = 0, tp = 0;
+    const long long tk0 = prof ? clock64() : 0;
+    for (int ui = 0; ui < my_units; ++ui) {
+      if (prof) tp = clock64();
+      mbar_wait(smem_u32(tempty), (ui & 1) ^ 1);                // both accumulators drained
+      if (prof) t_tempty += clock64() - tp;
+      tc_fence_after();
+      uint32_t accum = 0;
+      for (int c = 0; c < p.chunks; ++c, ++gi) {
+        const int g = gi & 1, bs = gi % V3_NB;
+        if (prof) tp = clock64();
+        mbar_wait(smem_u32(&afull[g]), (gi >> 1) & 1);
+        if (prof) { const long long tn = clock64(); t_afull += tn - tp; tp = tn; }
+        mbar_wait(smem_u32(&bfull[bs]), (gi / V3_NB) & 1);
+        if (prof) t_bfull += clock64() - tp;
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sb = smem_u32(bstage + bs * 2 * TILE_BYTES);
+          const uint64_t b_big = make_desc(sb), b_small = make_desc(sb + TILE_BYTES);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t d_tmem = tmem_base + h * BN;
+            const uint32_t a_big = tmem_base + (uint32_t)(V3_A_COL0 + (g * 2 + h) * 64), a_small = a_big + 32;
+            uint32_t acc = accum;
+#pragma unroll
+            for (int ks = 0; ks < BK / 8; ++ks) {
+              const uint64_t adv = (uint64_t)((ks * 32) >> 4);
+              if (SINGLE) {
+                umma_tf32_ts(d_tmem, a_big + ks * 8, b_big + adv, IDESC_TF32, acc);
+              } else {
+                umma_tf32_ts(d_tmem, a_small + ks * 8, b_big + adv, IDESC_TF32, acc);
+                umma_tf32_ts(d_tmem, a_big + ks * 8, b_small + adv, IDESC_TF32, 1u);
+                umma_tf32_ts(d_tmem, a_big + ks * 8, b_big + adv, IDESC_TF32, 1u);
+              }
+              acc = 1u;
+            }
+          }
+          accum = 1u;
+          umma_commit(smem_u32(&aempty[g]));
+          umma_commit(smem_u32(&bempty[bs]));
+        }
+        __syncwarp();
+      }
+      if (lane == 0) umma_commit(smem_u32(tfull));
+      __syncwarp();
+    }
+    if (prof) {
+      p.prof[blockIdx.x * 8 + 2] = t_tempty; p.prof[blockIdx.x * 8 + 3] = t_afull; p.prof[blockIdx.x * 8 + 4] = t_bfull;
+      p.prof[blockIdx.x * 8 + 6] = clock64() - tk0;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == V3_MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, V3_TMEM_COLS);
+  }
+}
+
 // ---------------------------------------------------------------------------- dH kernel
 // operands: tile row = feature index f0.., k = sample index m; global [M, ld] row-major is read with 128-bit
 // loads along the feature axis and transposed 4x4 in registers.
@@ -1100,6 +1453,58 @@ int try_launch_mix_tma(const MixParams& p, cudaStream_t stream) {
   }
 }
 
+size_t smem_bytes_v3() {
+  return 1024 + (size_t)V3_NB * 2 * TILE_BYTES + (size_t)V3_NR * V3_RAW_BYTES + V3_SCRATCH + sizeof(float) * 64 + 8 * V3_BARS + 16;
+}
+
+template <int R, bool SINGLE>
+int launch_mix_v3_rs(const MixParams& p, const CUtensorMap& tmap, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(phm_tc_mix_v3_kernel<R, SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_v3());
+    if (e != cudaSuccess) {
+      phc_set_error("phm_tc: cannot reserve %zu bytes of shared memory: %s", smem_bytes_v3(), cudaGetErrorString(e));
+      return PHC_ERR_CUDA;
+    }
+    configured = true;
+  }
+  MixParams q = p;
+  q.num_tiles = phc_div_up(p.M, BM) * 2 * p.ptiles;           // units: (m-tile, p-tile, component pair)
+  const int grid = q.num_tiles < num_sms() ? q.num_tiles : num_sms();
+  phm_tc_mix_v3_kernel<R, SINGLE><<<grid, V3_THREADS, smem_bytes_v3(), stream>>>(q, tmap);
+  return phc_check_launch("phm_tc_mix_v3_kernel");
+}
+
+template <int R>
+int launch_mix_v3_r(const MixParams& p, const CUtensorMap& tmap, cudaStream_t stream) {
+  return p.single ? launch_mix_v3_rs<R, true>(p, tmap, stream) : launch_mix_v3_rs<R, false>(p, tmap, stream);
+}
+
+// TMEM-operand path: n == 4, 16-byte aligned rows.  Returns -1 when not applicable (caller falls back).
+int try_launch_mix_v3(const MixParams& p, cudaStream_t stream) {
+  static const bool use_v3 = getenv("PHC_TC_NO_TMEM_A") == nullptr;
+  const int Fin = p.n * p.Kin;
+  if (!use_v3 || p.n != 4 || Fin % 4 != 0 || (reinterpret_cast<uintptr_t>(p.X) & 15u) != 0) return -1;
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (enc == nullptr) return -1;
+  CUtensorMap tmap;
+  const int R = p.Kin & 3;
+  const cuuint64_t gdim[2] = {(cuuint64_t)Fin, (cuuint64_t)p.M};
+  const cuuint64_t gstride[1] = {(cuuint64_t)Fin * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)(BK / 4 + (R ? 4 : 0)), (cuuint32_t)BM};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p.X), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return -1;
+  switch (R) {
+    case 0: return launch_mix_v3_r<0>(p, tmap, stream);
+    case 1: return launch_mix_v3_r<1>(p, tmap, stream);
+    case 2: return launch_mix_v3_r<2>(p, tmap, stream);
+    default: return launch_mix_v3_r<3>(p, tmap, stream);
+  }
+}
+
 int launch_pack(const float* A, const float* W, int n, int K, int P, uint8_t* buf, int single, cudaStream_t stream) {
   const PackLayout L = pack_layout(n, K, P);
   const int units_fwd = L.pt_fwd * L.chunks_fwd * BN * 8, units_dx = L.pt_dx * L.chunks_dx * BN * 8;
@@ -1147,8 +1552,10 @@ int try_launch_dh_tma(const DhParams& d, cudaStream_t stream) {
 
 int launch_mix(const MixParams& p, cudaStream_t stream) {
   static const bool use_tma = getenv("PHC_TC_NO_TMA") == nullptr;       // debug switch: force the register-prefetch kernel
-  if (use_tma && p.prof == nullptr) {
-    const int rc = try_launch_mix_tma(p, stream);
+  if (use_tma) {
+    int rc = try_launch_mix_v3(p, stream);
+    if (rc >= 0) return rc;
+    rc = p.prof == nullptr ? try_launch_mix_tma(p, stream) : -1;
     if (rc >= 0) return rc;
   }
   return launch_mix_v2(p, stream);

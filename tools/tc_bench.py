@@ -36,6 +36,6 @@ if os.environ.get("TC_PROF"):
     torch.cuda.synchronize()
     lib.phc_debug_set_tc_profile(None)
     r = buf.view(148, 8).float().cpu()
-    names = ["prod wait_empty", "prod produce", "mma wait_tempty", "mma wait_full", "epi wait_tfull", "epi work", "kernel total", "epi tmem_ld"]
+    names = ["prod wait_rfull", "prod work", "mma wait_tempty", "mma wait_afull", "mma wait_bfull", "drain (incl. wait)", "kernel total", "prod wait_aempty"]
     for i, nm in enumerate(names):
         print(f"  {nm:18s} mean {r[:, i].mean():12.0f}  min {r[:, i].min():12.0f}  max {r[:, i].max():12.0f} cycles")
