@@ -16,12 +16,20 @@
 
 namespace {
 
-constexpr int BN_ROWS = 64;    // rows per statistics chunk
+// Work decomposition shared by every kernel of this file: a block is 32 column lanes (x VEC columns each) by 8 row
+// slices; blockIdx.x = row chunk, blockIdx.y = column group.  A thread keeps its per-column parameters in registers
+// and walks its rows four at a time with all loads of the four rows issued before any arithmetic (the kernels are
+// latency-bound otherwise: measured 1.5 TB/s with two loads in flight per thread against 4+ TB/s with eight).
+// The chunk height is chosen on the host so that all blocks of a launch are co-resident in one balanced wave.
 constexpr int BN_SLICES = 8;   // row slices per block
-constexpr int BN_LANES = 32;   // feature lanes per block
+constexpr int BN_LANES = 32;   // column lanes per block
+constexpr int BN_BATCH = 4;    // rows in flight per thread
+constexpr int BN_THREADS = BN_SLICES * BN_LANES;
+constexpr int BN_MIN_ROWS = 32;  // smallest chunk height (bounds the workspace: 2 * ceil(M/32) * F floats)
 
 struct EwParams {
   int M, F, Fc;            // rows, width, width per component
+  int rpc;                 // rows per chunk (multiple of BN_SLICES * BN_BATCH)
   int use_bn, act;
   int drop_on, drop_same;  // dropout active / one mask shared by the n components
   unsigned int keep_thr;   // keep iff philox < keep_thr
@@ -29,63 +37,78 @@ struct EwParams {
   unsigned long long seed;
 };
 
-__device__ __forceinline__ float drop_factor(const EwParams& p, int row, int f) {
-  if (!p.drop_on) return 1.f;
+__device__ __forceinline__ bool drop_keep_bit(const EwParams& p, int row, int f) {
   unsigned long long idx = p.drop_same ? (unsigned long long)row * p.Fc + (f % p.Fc) : (unsigned long long)row * p.F + f;
-  return dropout_keep(p.seed, idx, p.keep_thr) ? p.drop_scale : 0.f;
+  return dropout_keep(p.seed, idx, p.keep_thr);
 }
 
-// dropout factors for VEC consecutive features starting at f (f % 4 == 0 when VEC == 4): one Philox call yields
-// the four uniforms of the aligned element quad, exactly the values drop_factor() produces one by one.
-template <int VEC>
-__device__ __forceinline__ void drop_factors(const EwParams& p, int row, int f, float (&out)[VEC]) {
-  if (!p.drop_on) {
-#pragma unroll
-    for (int q = 0; q < VEC; ++q) out[q] = 1.f;
-    return;
-  }
+// keep bits of VEC consecutive features starting at f (f % 4 == 0 when VEC == 4): one Philox call yields the four
+// uniforms of the aligned element quad, exactly the values drop_factor() produces one by one.  Computed for the
+// whole row batch while its loads are in flight, so the generator's temporaries are dead when the arithmetic starts.
+template <int VEC, bool DROP>
+__device__ __forceinline__ uint32_t keep_bits(const EwParams& p, int row, int f) {
+  if (!DROP) return 0xFu;
+  uint32_t bits = 0;
   if (VEC == 4 && !p.drop_same && (p.F & 3) == 0) {
     const unsigned long long idx = (unsigned long long)row * p.F + f;      // multiple of 4
     uint32_t r[4];
     philox4x32_10((uint32_t)(idx >> 2), (uint32_t)(idx >> 34), 0u, 0u, (uint32_t)p.seed, (uint32_t)(p.seed >> 32), r);
 #pragma unroll
-    for (int q = 0; q < VEC; ++q) out[q] = r[q] < p.keep_thr ? p.drop_scale : 0.f;
-    return;
+    for (int q = 0; q < VEC; ++q) bits |= (r[q] < p.keep_thr ? 1u : 0u) << q;
+    return bits;
   }
 #pragma unroll
-  for (int q = 0; q < VEC; ++q) out[q] = drop_factor(p, row, f + q);
+  for (int q = 0; q < VEC; ++q) bits |= (drop_keep_bit(p, row, f + q) ? 1u : 0u) << q;
+  return bits;
 }
-
-// ---- chunk statistics: part[chunk][0][f] = chunk mean, part[chunk][1][f] = chunk M2 ----------
-template <int VEC>
-__global__ void __launch_bounds__(BN_SLICES * BN_LANES) bn_chunk_stats_kernel(const float* __restrict__ h, int M, int F,
-                                                                             float* __restrict__ part) {
-  const int lane = threadIdx.x % BN_LANES, slice = threadIdx.x / BN_LANES;
-  const int f = (blockIdx.x * BN_LANES + lane) * VEC;
-  const int r0 = blockIdx.y * BN_ROWS;
-  const int r1 = min(r0 + BN_ROWS, M);
-  const bool active = f < F;
-  float sh[VEC], s1[VEC], s2[VEC];
+template <int VEC, bool DROP>
+__device__ __forceinline__ uint32_t keep_bits_batch(const EwParams& p, int rb, int r1, int f) {
+  uint32_t m = 0;
+  if (DROP) {
 #pragma unroll
-  for (int q = 0; q < VEC; ++q) { sh[q] = 0.f; s1[q] = 0.f; s2[q] = 0.f; }
-  if (active) {
-    Vec<VEC> k = Vec<VEC>::load(h + (size_t)r0 * F + f);   // shift = first row of the chunk
-#pragma unroll
-    for (int q = 0; q < VEC; ++q) sh[q] = k.v[q];
-#pragma unroll 4
-    for (int r = r0 + slice; r < r1; r += BN_SLICES) {
-      Vec<VEC> v = Vec<VEC>::load(h + (size_t)r * F + f);
-#pragma unroll
-      for (int q = 0; q < VEC; ++q) {
-        float d = v.v[q] - sh[q];
-        s1[q] += d;
-        s2[q] += d * d;
-      }
+    for (int j = 0; j < BN_BATCH; ++j) {
+      const int r = rb + j * BN_SLICES;
+      if (r < r1) m |= keep_bits<VEC, DROP>(p, r, f) << (4 * j);
     }
   }
-  __shared__ float red[2][BN_SLICES][BN_LANES * VEC];
+  return m;
+}
+template <bool DROP>
+__device__ __forceinline__ float drop_of(const EwParams& p, uint32_t mask, int j, int q) {
+  if (!DROP) return 1.f;
+  return (mask >> (4 * j + q)) & 1u ? p.drop_scale : 0.f;
+}
+
+// ACT >= 0: activation fixed at compile time (identity / relu, the common cases); ACT < 0: runtime switch
+template <int ACT> __device__ __forceinline__ float actf(int rt, float v) {
+  if constexpr (ACT >= 0) return act_fwd<ACT>(v);
+  else return act_fwd_rt(rt, v);
+}
+template <int ACT> __device__ __forceinline__ float actb(int rt, float v) {
+  if constexpr (ACT >= 0) return act_bwd<ACT>(v);
+  else return act_bwd_rt(rt, v);
+}
+
+// per-column batch-norm parameters of a thread's VEC columns; without batch-norm (or without affine) the neutral
+// values make  pre = (h - 0) * 1 * 1 + 0 = h  exactly, so one code path serves every configuration
+template <int VEC>
+struct Cols {
+  float mean[VEC], rstd[VEC], gamma[VEC], beta[VEC];
+  __device__ __forceinline__ void load(const EwParams& p, int f, const float* __restrict__ g, const float* __restrict__ b,
+                                       const float* __restrict__ m, const float* __restrict__ r) {
 #pragma unroll
-  for (int q = 0; q < VEC; ++q) { red[0][slice][lane * VEC + q] = s1[q]; red[1][slice][lane * VEC + q] = s2[q]; }
+    for (int q = 0; q < VEC; ++q) {
+      mean[q] = p.use_bn ? __ldg(m + f + q) : 0.f;
+      rstd[q] = p.use_bn ? __ldg(r + f + q) : 1.f;
+      gamma[q] = (p.use_bn && g) ? __ldg(g + f + q) : 1.f;
+      beta[q] = (p.use_bn && g) ? __ldg(b + f + q) : 0.f;
+    }
+  }
+};
+
+// reduce the 8 row slices of a block: red[which][slice][col] -> slice 0
+template <int VEC>
+__device__ __forceinline__ void slice_reduce(float (&red)[2][BN_SLICES][BN_LANES * VEC], int slice, int lane) {
   __syncthreads();
   for (int s = BN_SLICES / 2; s > 0; s >>= 1) {
     if (slice < s) {
@@ -97,6 +120,46 @@ __global__ void __launch_bounds__(BN_SLICES * BN_LANES) bn_chunk_stats_kernel(co
     }
     __syncthreads();
   }
+}
+
+// ---- chunk statistics: part[chunk][0][f] = chunk mean, part[chunk][1][f] = chunk M2 ----------
+template <int VEC>
+__global__ void __launch_bounds__(BN_THREADS, 4) bn_chunk_stats_kernel(const float* __restrict__ h, int M, int F, int rpc,
+                                                                       float* __restrict__ part) {
+  const int lane = threadIdx.x % BN_LANES, slice = threadIdx.x / BN_LANES;
+  const int f = (blockIdx.y * BN_LANES + lane) * VEC;
+  const int r0 = blockIdx.x * rpc;
+  const int r1 = min(r0 + rpc, M);
+  const bool active = f < F;
+  float sh[VEC], s1[VEC], s2[VEC];
+#pragma unroll
+  for (int q = 0; q < VEC; ++q) { sh[q] = 0.f; s1[q] = 0.f; s2[q] = 0.f; }
+  if (active) {
+    Vec<VEC> k = Vec<VEC>::load(h + (size_t)r0 * F + f);   // shift = first row of the chunk
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) sh[q] = k.v[q];
+    for (int rb = r0 + slice; rb < r1; rb += BN_SLICES * BN_BATCH) {
+      Vec<VEC> v[BN_BATCH];
+#pragma unroll
+      for (int j = 0; j < BN_BATCH; ++j) {
+        const int r = rb + j * BN_SLICES;
+        if (r < r1) v[j] = Vec<VEC>::load(h + (size_t)r * F + f);
+        else v[j] = k;                                       // contributes d = 0
+      }
+#pragma unroll
+      for (int j = 0; j < BN_BATCH; ++j)
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) {
+          float d = v[j].v[q] - sh[q];
+          s1[q] += d;
+          s2[q] += d * d;
+        }
+    }
+  }
+  __shared__ float red[2][BN_SLICES][BN_LANES * VEC];
+#pragma unroll
+  for (int q = 0; q < VEC; ++q) { red[0][slice][lane * VEC + q] = s1[q]; red[1][slice][lane * VEC + q] = s2[q]; }
+  slice_reduce<VEC>(red, slice, lane);
   if (slice == 0 && active) {
     const float cnt = (float)(r1 - r0);
 #pragma unroll
@@ -104,23 +167,23 @@ __global__ void __launch_bounds__(BN_SLICES * BN_LANES) bn_chunk_stats_kernel(co
       float a = red[0][0][lane * VEC + q], b = red[1][0][lane * VEC + q];
       float mean = sh[q] + a / cnt;
       float m2 = fmaxf(b - a * a / cnt, 0.f);
-      part[((size_t)blockIdx.y * 2 + 0) * F + f + q] = mean;
-      part[((size_t)blockIdx.y * 2 + 1) * F + f + q] = m2;
+      part[((size_t)blockIdx.x * 2 + 0) * F + f + q] = mean;
+      part[((size_t)blockIdx.x * 2 + 1) * F + f + q] = m2;
     }
   }
 }
 
-// ---- finalize: merge chunks (Chan), produce mean / rstd, update running statistics ----------
-// One warp per feature: lane l merges chunks l, l+32, ... in order, then the 32 lane results are merged by a
-// fixed butterfly (xor 16, 8, 4, 2, 1) — a fixed association order, hence deterministic.
-__device__ __forceinline__ void chan_merge(double& cnt, double& mean, double& m2, double nb, double mb, double m2b) {
-  if (nb == 0.0) return;
-  const double tot = cnt + nb, delta = mb - mean;
-  mean += delta * nb / tot;
-  m2 += m2b + delta * delta * cnt * nb / tot;
-  cnt = tot;
+// ---- finalize: merge the chunk moments, produce mean / rstd, update running statistics ----------
+// One warp per feature, two passes over the (L2-resident) partials, all in double and in a fixed order:
+//   mean = sum_c n_c mean_c / M ;   M2 = sum_c [ M2_c + n_c (mean_c - mean)^2 ]      (Chan's pairwise update, unrolled:
+// every term is non-negative, so there is no cancellation).  Lane l takes chunks l, l+32, ...; the 32 lane sums are
+// combined by a fixed butterfly — deterministic.
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
 }
-__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ part, int chunks, int M, int F, float eps,
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ part, int chunks, int rpc, int M, int F, float eps,
                                                           float momentum, float* __restrict__ running_mean,
                                                           float* __restrict__ running_var, float* __restrict__ save_mean,
                                                           float* __restrict__ save_rstd, long long* __restrict__ tracked, int n_tracked) {
@@ -128,21 +191,17 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restric
   const int lane = threadIdx.x & 31;
   if (blockIdx.x == 0 && threadIdx.x == 0 && tracked) for (int c = 0; c < n_tracked; ++c) tracked[c] += 1;
   if (f >= F) return;
-  double mean = 0.0, m2 = 0.0, cnt = 0.0;
+  double s = 0.0;
+#pragma unroll 4
+  for (int c = lane; c < chunks; c += 32) s += (double)min(rpc, M - c * rpc) * (double)part[((size_t)c * 2 + 0) * F + f];
+  const double mean = warp_sum(s) / (double)M;
+  double m2 = 0.0;
+#pragma unroll 4
   for (int c = lane; c < chunks; c += 32) {
-    const double nb = (double)min(BN_ROWS, M - c * BN_ROWS);
-    chan_merge(cnt, mean, m2, nb, (double)part[((size_t)c * 2 + 0) * F + f], (double)part[((size_t)c * 2 + 1) * F + f]);
+    const double d = (double)part[((size_t)c * 2 + 0) * F + f] - mean;
+    m2 += (double)part[((size_t)c * 2 + 1) * F + f] + (double)min(rpc, M - c * rpc) * d * d;
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const double ocnt = __shfl_xor_sync(0xffffffffu, cnt, o), omean = __shfl_xor_sync(0xffffffffu, mean, o),
-                 om2 = __shfl_xor_sync(0xffffffffu, m2, o);
-    // merge (lower lane's partial first so both partners compute the identical result)
-    double c0 = (lane & o) ? ocnt : cnt, me0 = (lane & o) ? omean : mean, q0 = (lane & o) ? om2 : m2;
-    const double c1 = (lane & o) ? cnt : ocnt, me1 = (lane & o) ? mean : omean, q1 = (lane & o) ? m2 : om2;
-    chan_merge(c0, me0, q0, c1, me1, q1);
-    cnt = c0; mean = me0; m2 = q0;
-  }
+  m2 = warp_sum(m2);
   if (lane != 0) return;
   const double var = m2 / (double)M;
   save_mean[f] = (float)mean;
@@ -161,105 +220,102 @@ __global__ void __launch_bounds__(128) bn_eval_stats_kernel(const float* __restr
 }
 
 // ---- apply -------------------------------------------------------------------------------------
-constexpr int EW_ROWS = 4;   // rows per thread in the apply kernels (independent 128-bit loads in flight)
-
-template <int VEC>
-__global__ void __launch_bounds__(256) bn_apply_fwd_kernel(EwParams p, const float* __restrict__ h, const float* __restrict__ gamma,
-                                                           const float* __restrict__ beta, const float* __restrict__ mean,
-                                                           const float* __restrict__ rstd, const float* __restrict__ skip,
-                                                           float* __restrict__ y) {
-  const int fv = p.F / VEC;
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int rgroups = (p.M + EW_ROWS - 1) / EW_ROWS;
-  if (t >= (long long)rgroups * fv) return;
-  const int rg = (int)(t / fv), f = (int)(t % fv) * VEC;
-  Vec<VEC> v[EW_ROWS], s[EW_ROWS];
+template <int VEC, int ACT, bool DROP>
+__global__ void __launch_bounds__(BN_THREADS, 3) bn_apply_fwd_kernel(EwParams p, const float* __restrict__ h, const float* __restrict__ gamma,
+                                                                     const float* __restrict__ beta, const float* __restrict__ mean,
+                                                                     const float* __restrict__ rstd, const float* __restrict__ skip,
+                                                                     float* __restrict__ y) {
+  const int lane = threadIdx.x % BN_LANES, slice = threadIdx.x / BN_LANES;
+  const int f = (blockIdx.y * BN_LANES + lane) * VEC;
+  if (f >= p.F) return;
+  const int r0 = blockIdx.x * p.rpc, r1 = min(r0 + p.rpc, p.M);
+  Cols<VEC> c;
+  c.load(p, f, gamma, beta, mean, rstd);
+  for (int rb = r0 + slice; rb < r1; rb += BN_SLICES * BN_BATCH) {
+    Vec<VEC> v[BN_BATCH], s[BN_BATCH];
 #pragma unroll
-  for (int j = 0; j < EW_ROWS; ++j) {
-    const int r = rg * EW_ROWS + j;
-    if (r < p.M) {
-      v[j] = Vec<VEC>::load(h + (size_t)r * p.F + f);
-      if (skip) s[j] = Vec<VEC>::load(skip + (size_t)r * p.F + f);
+    for (int j = 0; j < BN_BATCH; ++j) {
+      const int r = rb + j * BN_SLICES;
+      if (r < r1) {
+        v[j] = Vec<VEC>::load(h + (size_t)r * p.F + f);
+        if (skip) s[j] = Vec<VEC>::load(skip + (size_t)r * p.F + f);
+      }
     }
-  }
+    const uint32_t keep = keep_bits_batch<VEC, DROP>(p, rb, r1, f);
 #pragma unroll
-  for (int j = 0; j < EW_ROWS; ++j) {
-    const int r = rg * EW_ROWS + j;
-    if (r >= p.M) break;
-    float df[VEC];
-    drop_factors<VEC>(p, r, f, df);
+    for (int j = 0; j < BN_BATCH; ++j) {
+      const int r = rb + j * BN_SLICES;
+      if (r >= r1) break;
 #pragma unroll
-    for (int q = 0; q < VEC; ++q) {
-      float a = p.use_bn ? (v[j].v[q] - __ldg(mean + f + q)) * __ldg(rstd + f + q) : v[j].v[q];
-      if (p.use_bn && gamma) a = a * __ldg(gamma + f + q) + __ldg(beta + f + q);
-      a = act_fwd_rt(p.act, a) * df[q];
-      v[j].v[q] = skip ? a + s[j].v[q] : a;
+      for (int q = 0; q < VEC; ++q) {
+        float a = (v[j].v[q] - c.mean[q]) * c.rstd[q];
+        a = a * c.gamma[q] + c.beta[q];
+        a = actf<ACT>(p.act, a) * drop_of<DROP>(p, keep, j, q);
+        v[j].v[q] = skip ? a + s[j].v[q] : a;
+      }
+      v[j].store(y + (size_t)r * p.F + f);
     }
-    v[j].store(y + (size_t)r * p.F + f);
   }
 }
 
-// d(act input) for one element, shared by the reduction and the apply pass of backward
-__device__ __forceinline__ float bn_da(const EwParams& p, float dy, float hv, float dfac, int f, const float* gamma, const float* beta,
-                                       const float* mean, const float* rstd, float* xhat_out) {
-  float xh = hv, pre = hv;
-  if (p.use_bn) {
-    xh = (hv - __ldg(mean + f)) * __ldg(rstd + f);
-    pre = gamma ? xh * __ldg(gamma + f) + __ldg(beta + f) : xh;
-  }
+// d(act input) and xhat for one element, shared by the reduction and the apply pass of backward
+template <int ACT>
+__device__ __forceinline__ float bn_da(int act, float dy, float hv, float dfac, float mean, float rstd, float gamma, float beta, float* xhat_out) {
+  const float xh = (hv - mean) * rstd;
   *xhat_out = xh;
-  return dy * dfac * act_bwd_rt(p.act, pre);
+  return dy * dfac * actb<ACT>(act, xh * gamma + beta);
 }
 
 // part[chunk][0][f] = sum da ; part[chunk][1][f] = sum da * xhat
-template <int VEC>
-__global__ void __launch_bounds__(BN_SLICES * BN_LANES) bn_bwd_reduce_kernel(EwParams p, const float* __restrict__ dy,
-                                                                            const float* __restrict__ h, const float* __restrict__ gamma,
-                                                                            const float* __restrict__ beta, const float* __restrict__ mean,
-                                                                            const float* __restrict__ rstd, float* __restrict__ part) {
+template <int VEC, int ACT, bool DROP>
+__global__ void __launch_bounds__(BN_THREADS, 3) bn_bwd_reduce_kernel(EwParams p, const float* __restrict__ dy, const float* __restrict__ h,
+                                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                      float* __restrict__ part) {
   const int lane = threadIdx.x % BN_LANES, slice = threadIdx.x / BN_LANES;
-  const int f = (blockIdx.x * BN_LANES + lane) * VEC;
-  const int r0 = blockIdx.y * BN_ROWS;
-  const int r1 = min(r0 + BN_ROWS, p.M);
+  const int f = (blockIdx.y * BN_LANES + lane) * VEC;
+  const int r0 = blockIdx.x * p.rpc, r1 = min(r0 + p.rpc, p.M);
   const bool active = f < p.F;
   float s1[VEC], s2[VEC];
 #pragma unroll
   for (int q = 0; q < VEC; ++q) { s1[q] = 0.f; s2[q] = 0.f; }
   if (active) {
-#pragma unroll 4
-    for (int r = r0 + slice; r < r1; r += BN_SLICES) {
-      Vec<VEC> g = Vec<VEC>::load(dy + (size_t)r * p.F + f);
-      Vec<VEC> v = Vec<VEC>::load(h + (size_t)r * p.F + f);
-      float df[VEC];
-      drop_factors<VEC>(p, r, f, df);
+    Cols<VEC> c;
+    c.load(p, f, gamma, beta, mean, rstd);
+    for (int rb = r0 + slice; rb < r1; rb += BN_SLICES * BN_BATCH) {
+      Vec<VEC> g[BN_BATCH], v[BN_BATCH];
 #pragma unroll
-      for (int q = 0; q < VEC; ++q) {
-        float xh;
-        float da = bn_da(p, g.v[q], v.v[q], df[q], f + q, gamma, beta, mean, rstd, &xh);
-        s1[q] += da;
-        s2[q] += da * xh;
+      for (int j = 0; j < BN_BATCH; ++j) {
+        const int r = rb + j * BN_SLICES;
+        if (r < r1) {
+          g[j] = Vec<VEC>::load(dy + (size_t)r * p.F + f);
+          v[j] = Vec<VEC>::load(h + (size_t)r * p.F + f);
+        }
+      }
+      const uint32_t keep = keep_bits_batch<VEC, DROP>(p, rb, r1, f);
+#pragma unroll
+      for (int j = 0; j < BN_BATCH; ++j) {
+        const int r = rb + j * BN_SLICES;
+        if (r >= r1) break;
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) {
+          float xh;
+          const float da = bn_da<ACT>(p.act, g[j].v[q], v[j].v[q], drop_of<DROP>(p, keep, j, q), c.mean[q], c.rstd[q], c.gamma[q], c.beta[q], &xh);
+          s1[q] += da;
+          s2[q] += da * xh;
+        }
       }
     }
   }
   __shared__ float red[2][BN_SLICES][BN_LANES * VEC];
 #pragma unroll
   for (int q = 0; q < VEC; ++q) { red[0][slice][lane * VEC + q] = s1[q]; red[1][slice][lane * VEC + q] = s2[q]; }
-  __syncthreads();
-  for (int s = BN_SLICES / 2; s > 0; s >>= 1) {
-    if (slice < s) {
-#pragma unroll
-      for (int q = 0; q < VEC; ++q) {
-        red[0][slice][lane * VEC + q] += red[0][slice + s][lane * VEC + q];
-        red[1][slice][lane * VEC + q] += red[1][slice + s][lane * VEC + q];
-      }
-    }
-    __syncthreads();
-  }
+  slice_reduce<VEC>(red, slice, lane);
   if (slice == 0 && active) {
 #pragma unroll
     for (int q = 0; q < VEC; ++q) {
-      part[((size_t)blockIdx.y * 2 + 0) * p.F + f + q] = red[0][0][lane * VEC + q];
-      part[((size_t)blockIdx.y * 2 + 1) * p.F + f + q] = red[1][0][lane * VEC + q];
+      part[((size_t)blockIdx.x * 2 + 0) * p.F + f + q] = red[0][0][lane * VEC + q];
+      part[((size_t)blockIdx.x * 2 + 1) * p.F + f + q] = red[1][0][lane * VEC + q];
     }
   }
 }
@@ -270,15 +326,13 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __res
   const int lane = threadIdx.x & 31;
   if (f >= F) return;
   double a = 0.0, b = 0.0;
+#pragma unroll 4
   for (int c = lane; c < chunks; c += 32) {
     a += part[((size_t)c * 2 + 0) * F + f];
     b += part[((size_t)c * 2 + 1) * F + f];
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    a += __shfl_xor_sync(0xffffffffu, a, o);
-    b += __shfl_xor_sync(0xffffffffu, b, o);
-  }
+  a = warp_sum(a);
+  b = warp_sum(b);
   if (lane == 0) {
     dbeta[f] = (float)a;
     dgamma[f] = (float)b;
@@ -286,56 +340,77 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __res
 }
 
 // dh = gamma * rstd * (da - sum_da/M - xhat * sum_da_xhat/M)   [training]   or gamma * rstd * da   [eval]
-template <int VEC>
-__global__ void __launch_bounds__(256) bn_apply_bwd_kernel(EwParams p, int training, const float* __restrict__ dy, const float* __restrict__ h,
-                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                           const float* __restrict__ sum_da, const float* __restrict__ sum_da_xhat,
-                                                           float* __restrict__ dh) {
-  const int fv = p.F / VEC;
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int rgroups = (p.M + EW_ROWS - 1) / EW_ROWS;
-  if (t >= (long long)rgroups * fv) return;
-  const int rg = (int)(t / fv), f = (int)(t % fv) * VEC;
+template <int VEC, int ACT, bool DROP>
+__global__ void __launch_bounds__(BN_THREADS, 3) bn_apply_bwd_kernel(EwParams p, int training, const float* __restrict__ dy,
+                                                                     const float* __restrict__ h, const float* __restrict__ gamma,
+                                                                     const float* __restrict__ beta, const float* __restrict__ mean,
+                                                                     const float* __restrict__ rstd, const float* __restrict__ sum_da,
+                                                                     const float* __restrict__ sum_da_xhat, float* __restrict__ dh) {
+  const int lane = threadIdx.x % BN_LANES, slice = threadIdx.x / BN_LANES;
+  const int f = (blockIdx.y * BN_LANES + lane) * VEC;
+  if (f >= p.F) return;
+  const int r0 = blockIdx.x * p.rpc, r1 = min(r0 + p.rpc, p.M);
+  Cols<VEC> c;
+  c.load(p, f, gamma, beta, mean, rstd);
   const float invM = 1.f / (float)p.M;
   float scq[VEC], c1[VEC], c2[VEC];
 #pragma unroll
   for (int q = 0; q < VEC; ++q) {
-    scq[q] = 1.f; c1[q] = 0.f; c2[q] = 0.f;
-    if (p.use_bn) {
-      scq[q] = __ldg(rstd + f + q) * (gamma ? __ldg(gamma + f + q) : 1.f);
-      if (training) { c1[q] = __ldg(sum_da + f + q) * invM; c2[q] = __ldg(sum_da_xhat + f + q) * invM; }
+    scq[q] = c.rstd[q] * c.gamma[q];
+    c1[q] = 0.f; c2[q] = 0.f;
+    if (p.use_bn && training) { c1[q] = __ldg(sum_da + f + q) * invM; c2[q] = __ldg(sum_da_xhat + f + q) * invM; }
+  }
+  for (int rb = r0 + slice; rb < r1; rb += BN_SLICES * BN_BATCH) {
+    Vec<VEC> g[BN_BATCH], v[BN_BATCH];
+#pragma unroll
+    for (int j = 0; j < BN_BATCH; ++j) {
+      const int r = rb + j * BN_SLICES;
+      if (r < r1) {
+        g[j] = Vec<VEC>::load(dy + (size_t)r * p.F + f);
+        v[j] = Vec<VEC>::load(h + (size_t)r * p.F + f);
+      }
+    }
+    const uint32_t keep = keep_bits_batch<VEC, DROP>(p, rb, r1, f);
+#pragma unroll
+    for (int j = 0; j < BN_BATCH; ++j) {
+      const int r = rb + j * BN_SLICES;
+      if (r >= r1) break;
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) {
+        float xh;
+        float da = bn_da<ACT>(p.act, g[j].v[q], v[j].v[q], drop_of<DROP>(p, keep, j, q), c.mean[q], c.rstd[q], c.gamma[q], c.beta[q], &xh);
+        if (p.use_bn) da = (da - c1[q] - xh * c2[q]) * scq[q];
+        v[j].v[q] = da;
+      }
+      v[j].store(dh + (size_t)r * p.F + f);
     }
   }
-  Vec<VEC> g[EW_ROWS], v[EW_ROWS];
-#pragma unroll
-  for (int j = 0; j < EW_ROWS; ++j) {
-    const int r = rg * EW_ROWS + j;
-    if (r < p.M) {
-      g[j] = Vec<VEC>::load(dy + (size_t)r * p.F + f);
-      v[j] = Vec<VEC>::load(h + (size_t)r * p.F + f);
-    }
+}
+
+int bn_num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v;
+    else sms = 148;
   }
-#pragma unroll
-  for (int j = 0; j < EW_ROWS; ++j) {
-    const int r = rg * EW_ROWS + j;
-    if (r >= p.M) break;
-    float df[VEC];
-    drop_factors<VEC>(p, r, f, df);
-#pragma unroll
-    for (int q = 0; q < VEC; ++q) {
-      float xh;
-      float da = bn_da(p, g[j].v[q], v[j].v[q], df[q], f + q, gamma, beta, mean, rstd, &xh);
-      if (p.use_bn) da = (da - c1[q] - xh * c2[q]) * scq[q];
-      v[j].v[q] = da;
-    }
-    v[j].store(dh + (size_t)r * p.F + f);
-  }
+  return sms;
+}
+
+// chunk height so that (column groups) x (row chunks) blocks fill the GPU once, `per_sm` blocks per SM
+int bn_rows_per_chunk(int M, int colgroups, int per_sm) {
+  const int unit = BN_SLICES * BN_BATCH;
+  int want = (bn_num_sms() * per_sm) / (colgroups > 0 ? colgroups : 1);
+  if (want < 1) want = 1;
+  long long rpc = ((long long)M + want - 1) / want;
+  rpc = (rpc + unit - 1) / unit * unit;
+  if (rpc < BN_MIN_ROWS) rpc = BN_MIN_ROWS;
+  return (int)rpc;
 }
 
 EwParams make_params(int M, int F, int n, int use_bn, int act, float drop_p, int drop_same, int training, unsigned long long seed) {
   EwParams p;
-  p.M = M; p.F = F; p.Fc = F / n; p.use_bn = use_bn; p.act = act;
+  p.M = M; p.F = F; p.Fc = F / n; p.use_bn = use_bn; p.act = act; p.rpc = BN_MIN_ROWS;
   p.drop_on = (training && drop_p > 0.f) ? 1 : 0;
   p.drop_same = drop_same;
   double keep = 1.0 - (double)drop_p;
@@ -346,11 +421,32 @@ EwParams make_params(int M, int F, int n, int use_bn, int act, float drop_p, int
   return p;
 }
 
+// compile-time activation for the common cases, runtime switch (-1) otherwise
+#define BN_DISPATCH(KERNEL, V4, P, GRID, STREAM, ...)                                                                   \
+  do {                                                                                                                  \
+    const int a_ = (P).act == PHC_ACT_IDENTITY ? 0 : ((P).act == PHC_ACT_RELU ? 1 : 2);                                  \
+    const int key_ = ((V4) ? 6 : 0) + a_ * 2 + ((P).drop_on ? 1 : 0);                                                    \
+    switch (key_) {                                                                                                     \
+      case 0: KERNEL<1, PHC_ACT_IDENTITY, false><<<GRID, BN_THREADS, 0, STREAM>>>(__VA_ARGS__); break;                  \
+      case 1: KERNEL<1, PHC_ACT_IDENTITY, true><<<GRID, BN_THREADS, 0, STREAM>>>(__VA_ARGS__); break;                   \
+      case 2: KERNEL<1, PHC_ACT_RELU, false><<<GRID, BN_THREADS, 0, STREAM>>>(__VA_ARGS__); break;                      \
+      case 3: KERNEL<1, PHC_ACT_RELU, true><<<GRID, BN_THREADS, 0, STREAM>>>(__VA_ARGS__); break;                       \
+      case 4: KERNEL<1, -1, false><<<GRID, BN_THREADS, 0, STREAM>>>(__VA_ARGS__); break;                                \
+      case 5: KERNEL<1, -1, true><<<GRID, BN_THREADS, 0, STREAM>>>(__VA_ARGS__); break;                                 \
+      case 6: KERNEL<4, PHC_ACT_IDENTITY, false><<<GRID, BN_THREADS, 0, STREAM>>>(__VA_ARGS__); break;                  \
+      case 7: KERNEL<4, PHC_ACT_IDENTITY, true><<<GRID, BN_THREADS, 0, STREAM>>>(__VA_ARGS__); break;                   \
+      case 8: KERNEL<4, PHC_ACT_RELU, false><<<GRID, BN_THREADS, 0, STREAM>>>(__VA_ARGS__); break;                      \
+      case 9: KERNEL<4, PHC_ACT_RELU, true><<<GRID, BN_THREADS, 0, STREAM>>>(__VA_ARGS__); break;                       \
+      case 10: KERNEL<4, -1, false><<<GRID, BN_THREADS, 0, STREAM>>>(__VA_ARGS__); break;                               \
+      default: KERNEL<4, -1, true><<<GRID, BN_THREADS, 0, STREAM>>>(__VA_ARGS__); break;                                \
+    }                                                                                                                   \
+  } while (0)
+
 }  // namespace
 
 extern "C" {
 
-size_t phc_bn_workspace_bytes(int rows, int width) { return sizeof(float) * 2 * (size_t)phc_div_up(rows, BN_ROWS) * width + 16; }
+size_t phc_bn_workspace_bytes(int rows, int width) { return sizeof(float) * 2 * ((size_t)phc_div_up(rows, BN_MIN_ROWS) + 1) * width + 16; }
 
 int phc_bn_act_drop_skip_fwd(const float* h, const float* gamma, const float* beta, float* running_mean, float* running_var,
                              long long* num_batches_tracked, int n_tracked, const float* skip, int rows, int width, int phm_dim,
@@ -368,14 +464,17 @@ int phc_bn_act_drop_skip_fwd(const float* h, const float* gamma, const float* be
     if (training) {
       PHC_REQUIRE(M > 1, "phc_bn_act_drop_skip_fwd: batch-norm in training mode needs more than 1 row");
       PHC_REQUIRE(workspace_bytes >= phc_bn_workspace_bytes(M, F), "phc_bn_act_drop_skip_fwd: workspace too small");
-      const int chunks = phc_div_up(M, BN_ROWS);
       float* part = reinterpret_cast<float*>(workspace);
       const bool v4s = F % 4 == 0 && phc_aligned16(h);
-      dim3 grid(phc_div_up(F, BN_LANES * (v4s ? 4 : 1)), chunks);
-      if (v4s) bn_chunk_stats_kernel<4><<<grid, BN_SLICES * BN_LANES, 0, stream>>>(h, M, F, part);
-      else bn_chunk_stats_kernel<1><<<grid, BN_SLICES * BN_LANES, 0, stream>>>(h, M, F, part);
-      bn_finalize_kernel<<<phc_div_up((long long)F * 32, 256), 256, 0, stream>>>(part, chunks, M, F, eps, momentum, running_mean, running_var, save_mean,
-                                                                save_rstd, num_batches_tracked, n_tracked);
+      const int colgroups = phc_div_up(F, BN_LANES * (v4s ? 4 : 1));
+      const int rpc = bn_rows_per_chunk(M, colgroups, 4);
+      const int chunks = phc_div_up(M, rpc);
+      dim3 grid(chunks, colgroups);
+      if (v4s) bn_chunk_stats_kernel<4><<<grid, BN_THREADS, 0, stream>>>(h, M, F, rpc, part);
+      else bn_chunk_stats_kernel<1><<<grid, BN_THREADS, 0, stream>>>(h, M, F, rpc, part);
+      bn_finalize_kernel<<<phc_div_up((long long)F * 32, 256), 256, 0, stream>>>(part, chunks, rpc, M, F, eps, momentum, running_mean,
+                                                                                running_var, save_mean, save_rstd, num_batches_tracked,
+                                                                                n_tracked);
     } else {
       PHC_REQUIRE(running_mean && running_var, "phc_bn_act_drop_skip_fwd: eval mode needs running statistics");
       bn_eval_stats_kernel<<<phc_div_up(F, 128), 128, 0, stream>>>(running_mean, running_var, F, eps, save_mean, save_rstd);
@@ -383,9 +482,10 @@ int phc_bn_act_drop_skip_fwd(const float* h, const float* gamma, const float* be
   }
   EwParams p = make_params(M, F, phm_dim, use_bn, act, drop_p, drop_same, training, seed);
   const bool v4 = F % 4 == 0 && phc_aligned16(h) && phc_aligned16(y) && phc_aligned16(skip);
-  const long long rgroups = (M + EW_ROWS - 1) / EW_ROWS;
-  if (v4) bn_apply_fwd_kernel<4><<<phc_div_up(rgroups * (F / 4), 256), 256, 0, stream>>>(p, h, gamma, beta, save_mean, save_rstd, skip, y);
-  else bn_apply_fwd_kernel<1><<<phc_div_up(rgroups * F, 256), 256, 0, stream>>>(p, h, gamma, beta, save_mean, save_rstd, skip, y);
+  const int colgroups = phc_div_up(F, BN_LANES * (v4 ? 4 : 1));
+  p.rpc = bn_rows_per_chunk(M, colgroups, 3);
+  dim3 grid(phc_div_up(M, p.rpc), colgroups);
+  BN_DISPATCH(bn_apply_fwd_kernel, v4, p, grid, stream, p, h, gamma, beta, save_mean, save_rstd, skip, y);
   return phc_check_launch("phc_bn_act_drop_skip_fwd");
 }
 
@@ -398,25 +498,22 @@ int phc_bn_act_drop_skip_bwd(const float* dy, const float* h, const float* gamma
   const int M = rows, F = width;
   EwParams p = make_params(M, F, phm_dim, use_bn, act, drop_p, drop_same, training, seed);
   const bool v4 = F % 4 == 0 && phc_aligned16(h) && phc_aligned16(dy) && phc_aligned16(dh);
+  const int colgroups = phc_div_up(F, BN_LANES * (v4 ? 4 : 1));
   float* sum_da = dbeta;
   float* sum_da_xhat = dgamma;
   if (use_bn) {
     PHC_REQUIRE(dgamma && dbeta, "phc_bn_act_drop_skip_bwd: dgamma/dbeta buffers required with batch-norm");
     PHC_REQUIRE(workspace_bytes >= phc_bn_workspace_bytes(M, F), "phc_bn_act_drop_skip_bwd: workspace too small");
-    const int chunks = phc_div_up(M, BN_ROWS);
     float* part = reinterpret_cast<float*>(workspace);
-    dim3 grid(phc_div_up(F, BN_LANES * (v4 ? 4 : 1)), chunks);
-    if (v4) bn_bwd_reduce_kernel<4><<<grid, BN_SLICES * BN_LANES, 0, stream>>>(p, dy, h, gamma, beta, save_mean, save_rstd, part);
-    else bn_bwd_reduce_kernel<1><<<grid, BN_SLICES * BN_LANES, 0, stream>>>(p, dy, h, gamma, beta, save_mean, save_rstd, part);
+    p.rpc = bn_rows_per_chunk(M, colgroups, 3);
+    const int chunks = phc_div_up(M, p.rpc);
+    dim3 grid(chunks, colgroups);
+    BN_DISPATCH(bn_bwd_reduce_kernel, v4, p, grid, stream, p, dy, h, gamma, beta, save_mean, save_rstd, part);
     bn_bwd_finalize_kernel<<<phc_div_up((long long)F * 32, 256), 256, 0, stream>>>(part, chunks, F, dgamma, dbeta);
   }
-  const long long rgroups = (M + EW_ROWS - 1) / EW_ROWS;
-  if (v4)
-    bn_apply_bwd_kernel<4><<<phc_div_up(rgroups * (F / 4), 256), 256, 0, stream>>>(p, training, dy, h, gamma, beta, save_mean, save_rstd,
-                                                                                 sum_da, sum_da_xhat, dh);
-  else
-    bn_apply_bwd_kernel<1><<<phc_div_up(rgroups * F, 256), 256, 0, stream>>>(p, training, dy, h, gamma, beta, save_mean, save_rstd,
-                                                                           sum_da, sum_da_xhat, dh);
+  p.rpc = bn_rows_per_chunk(M, colgroups, 3);
+  dim3 grid(phc_div_up(M, p.rpc), colgroups);
+  BN_DISPATCH(bn_apply_bwd_kernel, v4, p, grid, stream, p, training, dy, h, gamma, beta, save_mean, save_rstd, sum_da, sum_da_xhat, dh);
   return phc_check_launch("phc_bn_act_drop_skip_bwd");
 }
 
