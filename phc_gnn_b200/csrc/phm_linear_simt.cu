@@ -201,12 +201,31 @@ __global__ void __launch_bounds__(256) phm_contract_kernel(const float* __restri
   }
 }
 
-__global__ void __launch_bounds__(256) phm_dA_final_kernel(const float* __restrict__ dA_part, int blocks, int n3, float* __restrict__ dA) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n3) return;
-  float s = 0.f;
-  for (int b = 0; b < blocks; ++b) s += dA_part[(size_t)b * n3 + i];
-  dA[i] = s;
+// Last step of the backward: ordered sums of the per-block dA partials (one warp per rule entry: lane l takes blocks
+// l, l+32, ..., then a fixed butterfly) and, when the dH kernel produced column-sum partials of dy, of the bias gradient
+// (one thread per column, partials in order).
+__global__ void __launch_bounds__(256) phm_bwd_final_kernel(const float* __restrict__ dA_part, int blocks, int n3, float* __restrict__ dA,
+                                                            const float* __restrict__ db_part, int db_parts, int Out,
+                                                            float* __restrict__ db) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  if (t < n3 * 32) {
+    const int i = t >> 5;
+    float s = 0.f;
+#pragma unroll 4
+    for (int b = lane; b < blocks; b += 32) s += dA_part[(size_t)b * n3 + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) dA[i] = s;
+    return;
+  }
+  const int f = t - n3 * 32;
+  if (db_part != nullptr && f < Out) {
+    float s = 0.f;
+#pragma unroll 4
+    for (int q = 0; q < db_parts; ++q) s += db_part[(size_t)q * Out + f];
+    db[f] = s;
+  }
 }
 
 // column sums of G (bias gradient): chunk partials then ordered final sum.
@@ -257,60 +276,69 @@ __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restri
   if (lane == 0) out[f] = s;
 }
 
-// Fast contraction for small phm_dim (N <= 4): every thread keeps its N^3 dA contributions in registers and the
-// block reduces them once at the end (fixed order: shuffle butterfly, then warps 0..7).
+// Fast contraction for small phm_dim (N <= 4).  Thread (a, j): input component a of the block's j-th (k,p) pair
+// (64 pairs per block, 64*N threads, the two warps of one `a` are adjacent).  The thread folds the split partials of
+// its N dH entries (a; c = 0..N-1) with independent loads, contributes sum_c A[b,a,c] dh[c] to dW[b,k,p] (summed over a
+// through shared memory, a = 0..N-1 in order) and w[b] dh[c] to dA[b,a,c] (warp butterfly, then the a's two warps).
+constexpr int CJ = 64;
 template <int N>
-__global__ void __launch_bounds__(256) phm_contract_small_kernel(const float* __restrict__ part, int splits, const float* __restrict__ A,
-                                                                 const float* __restrict__ W, int K, int P, float* __restrict__ dW,
-                                                                 float* __restrict__ dA_part) {
-  constexpr int N3 = N * N * N;
+__global__ void __launch_bounds__(CJ * N) phm_contract_small_kernel(const float* __restrict__ part, int splits, const float* __restrict__ A,
+                                                                    const float* __restrict__ W, int K, int P, float* __restrict__ dW,
+                                                                    float* __restrict__ dA_part) {
+  constexpr int N2 = N * N, N3 = N * N * N;
   __shared__ float As[N3];
-  __shared__ float red[8][N3];
+  __shared__ float dws[N][CJ][N];
+  __shared__ float red[2 * N][N2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < N3; i += 256) As[i] = A[i];
+  const int a = tid / CJ, j = tid % CJ;
+  for (int i = tid; i < N3; i += CJ * N) As[i] = A[i];
   __syncthreads();
   const int In = N * K, Out = N * P;
-  const long long t = (long long)blockIdx.x * 256 + tid;
+  const long long t = (long long)blockIdx.x * CJ + j;
   const bool active = t < (long long)K * P;
   const int k = active ? (int)(t / P) : 0, p = active ? (int)(t % P) : 0;
-  float dw[N], da[N3], w[N];
+  float dh[N], w[N];
 #pragma unroll
-  for (int b = 0; b < N; ++b) { dw[b] = 0.f; w[b] = active ? __ldg(W + ((size_t)b * K + k) * P + p) : 0.f; }
+  for (int c = 0; c < N; ++c) dh[c] = 0.f;
 #pragma unroll
-  for (int i = 0; i < N3; ++i) da[i] = 0.f;
+  for (int b = 0; b < N; ++b) w[b] = active ? __ldg(W + ((size_t)b * K + k) * P + p) : 0.f;
+  if (active) {
+    const float* src = part + (size_t)(a * K + k) * Out + p;
+    const size_t stride = (size_t)In * Out;
+#pragma unroll 4
+    for (int s = 0; s < splits; ++s)
 #pragma unroll
-  for (int a = 0; a < N; ++a) {
+      for (int c = 0; c < N; ++c) dh[c] += src[(size_t)s * stride + c * P];
+  }
+#pragma unroll
+  for (int b = 0; b < N; ++b) {
+    float v = 0.f;
+#pragma unroll
+    for (int c = 0; c < N; ++c) v += As[(b * N + a) * N + c] * dh[c];
+    dws[a][j][b] = v;
+  }
+#pragma unroll
+  for (int b = 0; b < N; ++b)
 #pragma unroll
     for (int c = 0; c < N; ++c) {
-      float dh = 0.f;
-      if (active) {
-        const size_t off = (size_t)(a * K + k) * Out + (c * P + p);
-        for (int s = 0; s < splits; ++s) dh += part[(size_t)s * In * Out + off];
-      }
+      float v = w[b] * dh[c];
 #pragma unroll
-      for (int b = 0; b < N; ++b) {
-        dw[b] += As[(b * N + a) * N + c] * dh;
-        da[(b * N + a) * N + c] = w[b] * dh;
-      }
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red[warp][b * N + c] = v;
+    }
+  __syncthreads();
+  if (a == 0 && active) {
+#pragma unroll
+    for (int b = 0; b < N; ++b) {
+      float v = 0.f;
+#pragma unroll
+      for (int aa = 0; aa < N; ++aa) v += dws[aa][j][b];
+      dW[((size_t)b * K + k) * P + p] = v;
     }
   }
-  if (active) {
-#pragma unroll
-    for (int b = 0; b < N; ++b) dW[((size_t)b * K + k) * P + p] = dw[b];
-  }
-#pragma unroll
-  for (int i = 0; i < N3; ++i) {
-    float v = da[i];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) red[warp][i] = v;
-  }
-  __syncthreads();
   if (tid < N3) {
-    float s = 0.f;
-#pragma unroll
-    for (int wi = 0; wi < 8; ++wi) s += red[wi][tid];
-    dA_part[(size_t)blockIdx.x * N3 + tid] = s;
+    const int b = tid / N2, aa = (tid / N) % N, c = tid % N;
+    dA_part[(size_t)blockIdx.x * N3 + tid] = red[2 * aa][b * N + c] + red[2 * aa + 1][b * N + c];
   }
 }
 
@@ -330,31 +358,46 @@ int colsum_chunks(int M) {
 }  // namespace
 
 // ---- shared with phm_linear_tc.cu: fold dH partials into dW / dA, and the bias gradient ----------
+static int contract_blocks(int n, int K, int P) { return phc_div_up((long long)K * P, n <= 4 ? CJ : 256); }
+static int bias_part_rows(int rows) { int c = colsum_chunks(rows); return c > 2 * 64 ? c : 2 * 64; }   // colsum chunks or 2 x dH splits
+
 size_t phm_contract_scratch_floats(int rows, int in_features, int out_features, int phm_dim) {
   const int n = phm_dim, K = in_features / n, P = out_features / n;
-  return (size_t)phc_div_up((long long)K * P, 256) * n * n * n + (size_t)colsum_chunks(rows) * out_features + 16;
+  return (size_t)contract_blocks(n, K, P) * n * n * n + (size_t)bias_part_rows(rows) * out_features + 16;
 }
 
+// the bias-gradient partials live behind the dA partials in the scratch area
+float* phm_contract_bias_partials(float* scratch, int in_features, int out_features, int phm_dim) {
+  const int n = phm_dim;
+  return scratch + (size_t)contract_blocks(n, in_features / n, out_features / n) * n * n * n;
+}
+
+// db_parts > 0: the dH kernel already wrote db_parts column-sum partials of gy to phm_contract_bias_partials(scratch, ...)
 int phm_contract_and_bias(const float* part, int splits, const float* gy, const float* A, const float* W, float* dA, float* dW, float* db,
-                          int rows, int in_features, int out_features, int phm_dim, float* scratch, cudaStream_t stream) {
+                          int rows, int in_features, int out_features, int phm_dim, float* scratch, int db_parts, cudaStream_t stream) {
   const int n = phm_dim, K = in_features / n, P = out_features / n, M = rows, n3 = n * n * n;
-  const int cblocks = phc_div_up((long long)K * P, 256);
+  const int cblocks = contract_blocks(n, K, P);
   float* da_part = scratch;
-  float* cs_part = scratch + (size_t)cblocks * n3;
+  float* cs_part = phm_contract_bias_partials(scratch, in_features, out_features, n);
   switch (n) {
-    case 1: phm_contract_small_kernel<1><<<cblocks, 256, 0, stream>>>(part, splits, A, W, K, P, dW, da_part); break;
-    case 2: phm_contract_small_kernel<2><<<cblocks, 256, 0, stream>>>(part, splits, A, W, K, P, dW, da_part); break;
-    case 3: phm_contract_small_kernel<3><<<cblocks, 256, 0, stream>>>(part, splits, A, W, K, P, dW, da_part); break;
-    case 4: phm_contract_small_kernel<4><<<cblocks, 256, 0, stream>>>(part, splits, A, W, K, P, dW, da_part); break;
+    case 1: phm_contract_small_kernel<1><<<cblocks, CJ * 1, 0, stream>>>(part, splits, A, W, K, P, dW, da_part); break;
+    case 2: phm_contract_small_kernel<2><<<cblocks, CJ * 2, 0, stream>>>(part, splits, A, W, K, P, dW, da_part); break;
+    case 3: phm_contract_small_kernel<3><<<cblocks, CJ * 3, 0, stream>>>(part, splits, A, W, K, P, dW, da_part); break;
+    case 4: phm_contract_small_kernel<4><<<cblocks, CJ * 4, 0, stream>>>(part, splits, A, W, K, P, dW, da_part); break;
     default: phm_contract_kernel<<<cblocks, 256, sizeof(float) * (n3 + 8), stream>>>(part, splits, A, W, n, K, P, dW, da_part);
   }
-  if (dA) phm_dA_final_kernel<<<phc_div_up(n3, 256), 256, 0, stream>>>(da_part, cblocks, n3, dA);
-  if (db) {
+  const bool fused_bias = db != nullptr && db_parts > 0;
+  if (db && !fused_bias) {
     const int chunks = colsum_chunks(M);
     const int rpc = phc_div_up(M > 0 ? M : 1, chunks);
     dim3 g3(phc_div_up(out_features, 128), chunks);
     colsum_partial_kernel<<<g3, 256, 0, stream>>>(gy, M, out_features, rpc, cs_part);
     colsum_final_kernel<<<phc_div_up((long long)out_features * 32, 256), 256, 0, stream>>>(cs_part, chunks, out_features, db);
+  }
+  if (dA || fused_bias) {
+    const int na = dA ? n3 : 0;
+    phm_bwd_final_kernel<<<phc_div_up((long long)na * 32 + (fused_bias ? out_features : 0), 256), 256, 0, stream>>>(
+        da_part, cblocks, na, dA, fused_bias ? cs_part : nullptr, db_parts, out_features, db);
   }
   return phc_check_launch("phm_contract_and_bias");
 }
@@ -388,5 +431,5 @@ int phm_simt_bwd(const float* gy, const float* x, const float* A, const float* W
   dim3 g2(phc_div_up(out_features, 64), phc_div_up(in_features, 64), splits);
   phm_dh_kernel<<<g2, 256, 0, stream>>>(x, gy, M, in_features, out_features, rps, part);
   return phm_contract_and_bias(part, splits, gy, A, W, dA, dW, db, M, in_features, out_features, n,
-                               part + (size_t)splits * in_features * out_features, stream);
+                               part + (size_t)splits * in_features * out_features, 0, stream);
 }

@@ -41,7 +41,8 @@
 
 // helpers implemented in phm_linear_simt.cu (fixed-order reductions shared by both paths)
 int phm_contract_and_bias(const float* part, int splits, const float* gy, const float* A, const float* W, float* dA, float* dW, float* db,
-                          int rows, int in_features, int out_features, int phm_dim, float* scratch, cudaStream_t stream);
+                          int rows, int in_features, int out_features, int phm_dim, float* scratch, int db_parts, cudaStream_t stream);
+float* phm_contract_bias_partials(float* scratch, int in_features, int out_features, int phm_dim);
 size_t phm_contract_scratch_floats(int rows, int in_features, int out_features, int phm_dim);
 
 long long* g_phm_tc_prof = nullptr;   // set via phc_debug_set_tc_profile (debug only)
@@ -82,6 +83,7 @@ struct DhParams {           // partial dH tiles
   const float* X;           // [M, In]
   const float* G;           // [M, Out]
   float* C;                 // [splits, In, Out]
+  float* db_part;           // optional [2 * splits, Out]: column sums of G per split (bias gradient), TMA kernel only
   int M, In, Out, tiles_m, tiles_n, splits, rows_per_split, num_tiles;
   int single;
 };
@@ -1212,6 +1214,7 @@ __global__ void __launch_bounds__(DH_TMA_THREADS, 1) phm_tc_dh_tma_kernel(const 
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
       int i0, o0, split, kbeg, kend;
       dh_tile(p, t, i0, o0, split, kbeg, kend);
+      float colsum = 0.f;      // dy producers: this thread's share of the column sum of feature o0 + (q & 127) (bias gradient)
       for (int k0 = kbeg; k0 < kend; k0 += BK, ++g) {
         const int rs = g % DH_RAW_STAGES, os = g % TMA_OP_STAGES;
         mbar_wait(smem_u32(&rfull_bar[rs]), (g / DH_RAW_STAGES) & 1);
@@ -1225,6 +1228,7 @@ __global__ void __launch_bounds__(DH_TMA_THREADS, 1) phm_tc_dh_tma_kernel(const 
           const float v[4] = {raw[(ku * 4 + 0) * BM + f], raw[(ku * 4 + 1) * BM + f], raw[(ku * 4 + 2) * BM + f],
                               raw[(ku * 4 + 3) * BM + f]};
           store_unit(sb, sb + TILE_BYTES, f, ku, v, p.single);
+          colsum += (v[0] + v[1]) + (v[2] + v[3]);              // rows past M are zero-filled by TMA
         }
         fence_proxy_async();
         __syncwarp();
@@ -1233,6 +1237,10 @@ __global__ void __launch_bounds__(DH_TMA_THREADS, 1) phm_tc_dh_tma_kernel(const 
           mbar_arrive(smem_u32(&rempty_bar[rs]));
         }
       }
+      // bias gradient for free: the dy tile passes through these threads anyway.  One i-tile per (o-tile, split) writes;
+      // threads q and q + 128 hold the two halves of a column's sum (k-units 2i and 2i + 1), summed later in fixed order.
+      if (half == 1 && p.db_part != nullptr && i0 == 0 && o0 + (q & (BN - 1)) < p.Out)
+        p.db_part[((size_t)split * 2 + (q >> 7)) * p.Out + o0 + (q & (BN - 1))] = colsum;
     }
   } else if (warp == MMA_WARP + 1) {
     if (lane == 0) {
@@ -1631,8 +1639,12 @@ int phm_tc_bwd(const float* gy, const float* x, const float* A, const float* W, 
   d.splits = tc::dh_splits(rows, in_features, out_features, &d.rows_per_split);
   d.num_tiles = d.tiles_m * d.tiles_n * d.splits;
   d.single = single;
+  float* scratch = part + (size_t)d.splits * in_features * out_features;
+  d.db_part = db ? phm_contract_bias_partials(scratch, in_features, out_features, n) : nullptr;
+  int db_parts = db ? 2 * d.splits : 0;            // the TMA kernel also emits the column sums of gy (bias gradient)
   int rc = tc::try_launch_dh_tma(d, stream);
   if (rc < 0) {
+    db_parts = 0;
     static bool configured = false;
     rc = tc::set_smem(tc::phm_tc_dh_kernel, &configured);
     if (rc) return rc;
@@ -1641,8 +1653,7 @@ int phm_tc_bwd(const float* gy, const float* x, const float* A, const float* W, 
     rc = phc_check_launch("phm_tc_dh_kernel");
   }
   if (rc) return rc;
-  float* scratch = part + (size_t)d.splits * in_features * out_features;
-  return phm_contract_and_bias(part, d.splits, gy, A, W, dA, dW, db, rows, in_features, out_features, n, scratch, stream);
+  return phm_contract_and_bias(part, d.splits, gy, A, W, dA, dW, db, rows, in_features, out_features, n, scratch, db_parts, stream);
 }
 
 extern "C" void phc_debug_set_tc_profile(long long* device_buffer) { g_phm_tc_prof = device_buffer; }

@@ -55,11 +55,17 @@ for ev in prof.events():
         k = short(ev.name)
         agg[k][0] += 1
         agg[k][1] += dur
-        spans.append((ev.time_range.start, ev.time_range.end))
+        spans.append((ev.time_range.start, ev.time_range.end, k))
 tot = sum(v[1] for v in agg.values())
 spans.sort()
 busy, cur_s, cur_e = 0.0, None, None
-for s, e in spans:
+gaps = collections.defaultdict(lambda: [0, 0.0])
+prev = None
+for s, e, k in spans:
+    if prev is not None and s > prev[1]:
+        gaps[prev[2] + " -> " + k][0] += 1
+        gaps[prev[2] + " -> " + k][1] += s - prev[1]
+    prev = (s, e, k) if prev is None or e >= prev[1] else prev
     if cur_e is None or s > cur_e:
         if cur_e is not None:
             busy += cur_e - cur_s
@@ -73,3 +79,6 @@ print(f"# kernel time {tot / steps / 1e3:.3f} ms/step; device busy {busy / steps
 print(f"{'us/step':>10} {'share':>6} {'n/step':>7} {'avg us':>8}  kernel")
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"{v[1] / steps:10.1f} {100 * v[1] / tot:5.1f}% {v[0] / steps:7.1f} {v[1] / v[0]:8.1f}  {k}")
+print(f"\n# idle gaps between consecutive kernels (us/step), top 25 of {sum(v[1] for v in gaps.values()) / steps:.1f} us/step")
+for k, v in sorted(gaps.items(), key=lambda kv: -kv[1][1])[:25]:
+    print(f"{v[1] / steps:10.1f} {v[0] / steps:7.1f} {v[1] / v[0]:8.1f}  {k}")
