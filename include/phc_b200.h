@@ -22,6 +22,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include "phc_b200_layer.h" /* phc_conv_layer: descriptor of one whole message-passing layer */
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -150,6 +152,15 @@ int phc_conv_fused_bwd(const float* gout, const float* x, const void* edge_attr,
  * the batch, so it is computed once and shared by all layers; with it the encoder gradients need no edge loop. */
 int phc_edge_feature_sums(const void* edge_attr, int enc_kind, int enc_dim, const int* vocab, const int* rowptr, const int* perm,
                           int num_nodes, int mean, float* node_sums, phc_stream_t stream);
+
+/* ---- one whole message-passing layer per call (models.py:200-217; descriptor in phc_b200_layer.h) -----------
+ * fwd: conv (aggregation + fused edge encoder) -> PHMLinear [-> BN -> act -> PHMLinear] -> BN -> act -> dropout -> + skip.
+ * bwd: the gradients of all of it (dx, encoder / rule / W / bias / BN-affine gradients, d softmax beta).  Same kernels
+ * and arithmetic as the per-operator entry points above, sequenced on `stream` by the library. */
+size_t phc_conv_layer_desc_bytes(void);
+size_t phc_conv_layer_workspace_bytes(int num_nodes, int width, int phm_dim, int table_rows, int precision);
+int phc_conv_layer_fwd(const phc_conv_layer* layer, phc_stream_t stream);
+int phc_conv_layer_bwd(const phc_conv_layer* layer, phc_stream_t stream);
 
 /* ---- principal-neighbourhood aggregation (messagepassing.py:421-438 PHMPNAConvSimple.message/aggregate;
  * aggregator.py:70-93 aggregators, :112-135 scalers; utils.py:122-135 phm_cat) -------------------------------

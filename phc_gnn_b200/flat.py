@@ -15,14 +15,18 @@ from typing import List, Optional, Sequence
 import torch
 
 
-def is_packed(flat: Optional[torch.Tensor], tensors: Sequence[torch.Tensor]) -> bool:
+def is_packed(flat: Optional[torch.Tensor], tensors: Sequence[torch.Tensor], quick: bool = False) -> bool:
+    """quick: only the first and the last tensor are checked (hot path; a group is moved / re-initialised as a whole)."""
     if flat is None or len(tensors) == 0:
         return False
     t0 = tensors[0]
-    if flat.device != t0.device or flat.dtype != t0.dtype:
-        return False
     base = flat.data_ptr()
     esz = flat.element_size()
+    if quick:
+        tl = tensors[-1]
+        return t0.data_ptr() == base and tl.data_ptr() == base + (flat.numel() - tl.numel()) * esz
+    if flat.device != t0.device or flat.dtype != t0.dtype:
+        return False
     off = 0
     for t in tensors:
         if t.data_ptr() != base + off * esz:      # also false after .to(device) / .data re-pointing
@@ -47,9 +51,9 @@ def view_if_contiguous(tensors: Sequence[torch.Tensor]) -> Optional[torch.Tensor
     return torch.empty(0, dtype=t0.dtype, device=t0.device).set_(st, start // esz, (off,))
 
 
-def alias_flat(flat: Optional[torch.Tensor], tensors: Sequence[torch.Tensor]) -> torch.Tensor:
+def alias_flat(flat: Optional[torch.Tensor], tensors: Sequence[torch.Tensor], quick: bool = False) -> torch.Tensor:
     """Return a 1-D tensor whose storage IS the concatenation of ``tensors`` (re-packing if needed)."""
-    if is_packed(flat, tensors):
+    if is_packed(flat, tensors, quick):
         return flat
     v = view_if_contiguous(tensors)
     if v is not None:

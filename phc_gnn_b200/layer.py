@@ -7,6 +7,11 @@ separate autograd Functions and ten nn.Module calls costs more host time than th
 molecule-sized batches, so the model's fast path runs the whole layer inside ONE autograd Function: forward
 launches the five kernels back to back, backward launches their gradients in reverse.  The arithmetic and the
 kernels are exactly those of ops.py; only the host-side orchestration differs.
+
+Two implementations of the node: ``_ConvLayer`` issues one C-ABI call per operator (used when the per-operator
+CUDA-event instrumentation is on, and as the cross-check in the tests); ``_ConvLayerCall`` hands the whole layer to
+the library in ONE call per direction (``phc_conv_layer_fwd`` / ``phc_conv_layer_bwd``, include/phc_b200_layer.h) —
+at ppa shape the Python cost of thirteen foreign calls per layer had caught up with the GPU time of their kernels.
 """
 from __future__ import annotations
 
@@ -17,7 +22,7 @@ import torch
 
 from . import _lib
 from .graph import EdgeStructure, _stream
-from .ops import REDUCE_IDS, _ptr, _ptr_array, _ws, act_id, default_precision, next_dropout_seed, run
+from .ops import PROFILE, REDUCE_IDS, _ptr, _ptr_array, _ws, act_id, default_precision, next_dropout_seed, run
 
 _WS_CACHE = {}
 
@@ -202,6 +207,174 @@ class _ConvLayer(torch.autograd.Function):
         return (None, None, None, dx, g if ctx.has_skip else None, None) + tuple(grads)
 
 
+SINGLE_CALL = True      # False: one C-ABI call per operator (the cross-check path of the tests)
+_SCRATCH = {}
+
+
+def _scratch(nbytes: int, device, stream: int) -> torch.Tensor:
+    """Grow-only scratch per (device, stream): every user is ordered on that stream, so one buffer serves all layers."""
+    key = (device.index, stream)
+    t = _SCRATCH.get(key)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _SCRATCH[key] = t
+    return t
+
+
+def _node_sums(struct, attr, linear, enc_dim, vocab, vc, reduce, msg_act, rows, N, dev, st):
+    """Per-node sums of the raw edge features (depends only on the batch: shared by all layers through struct.extras)."""
+    if not (reduce in (0, 1) and msg_act == 0 and rows <= 16):
+        return None
+    key = ("sums", attr.data_ptr(), tuple(attr.shape), attr._version, linear, enc_dim, vocab, reduce == 1)
+    sums = struct.extras.get(key)
+    if sums is None:
+        sums = torch.empty((N, rows), dtype=torch.float32, device=dev)
+        run("phc_edge_feature_sums", None, attr.data_ptr(), 0 if linear else 1, enc_dim, vc, struct.rowptr.data_ptr(),
+            struct.perm.data_ptr(), N, int(reduce == 1), sums.data_ptr(), st)
+        struct.extras[key] = sums
+        struct.extras[("keepalive", attr.data_ptr())] = attr
+    return sums
+
+
+class _ConvLayerCall(torch.autograd.Function):
+    """Same node as _ConvLayer, one library call per direction."""
+
+    @staticmethod
+    def forward(ctx, cfg, struct: EdgeStructure, flats, x, skip, attr, *tensors):
+        (n, linear, enc_dim, vocab, reduce, msg_act, self_loops, mlp, act1, act2, use_bn1, use_bn2, training, drop_p, same, seed,
+         precision, n_enc, has_beta, nb1, nb2, mom1, eps1, mom2, eps2) = cfg
+        flat1, flat2 = flats
+        dev = x.device
+        st = _stream(dev)
+        i = 0
+        beta = tensors[0] if has_beta else None
+        i += 1 if has_beta else 0
+        enc = tensors[i:i + n_enc]; i += n_enc
+        r1, W1, b1 = tensors[i:i + 3]; i += 3 + nb1
+        r2 = W2 = b2 = None
+        if mlp:
+            r2, W2, b2 = tensors[i:i + 3]
+        N, F = x.shape
+        f32 = dict(dtype=torch.float32, device=dev)
+        acts = torch.empty((4 if mlp else 2, N, F), **f32)          # agg, [y1, a1,] z: saved for backward
+        out = torch.empty((N, F), **f32)                            # own storage: callers may modify it in place
+        stats = torch.empty((4, F), **f32)
+        aux_f = torch.empty((2, N, F), **f32) if reduce == 4 else None
+        aux_i = torch.empty((N, F), dtype=torch.int32, device=dev) if reduce in (2, 3) else None
+        nb_lin = _ws_bytes("phc_phm_linear_fwd_workspace_bytes", N, F, F, n, precision)
+        ws_lin1 = _ws(nb_lin, dev)
+        ws_lin2 = _ws(nb_lin, dev) if mlp else None
+        rows = enc_dim + 1 if linear else int(sum(vocab))
+        ws = _scratch(_ws_bytes("phc_conv_layer_workspace_bytes", N, F, n, rows, precision), dev, st)
+        vc = (ctypes.c_int * max(len(vocab), 1))(*vocab) if vocab else None
+        encp = _ptr_array(enc)
+        D = _lib.conv_layer_struct()()
+        D.num_nodes, D.width, D.phm_dim = N, F, n
+        D.enc_kind, D.enc_dim, D.table_rows = 0 if linear else 1, enc_dim, rows
+        D.reduce, D.msg_act, D.self_loops, D.mlp = reduce, msg_act, int(self_loops), int(mlp)
+        D.act1, D.act2, D.use_bn1, D.use_bn2 = act1, act2, int(use_bn1 and mlp), int(use_bn2)
+        D.training, D.drop_same, D.precision = int(training), int(same), precision
+        D.drop_p, D.momentum1, D.eps1, D.momentum2, D.eps2, D.seed = float(drop_p), mom1, eps1, mom2, eps2, seed
+        D.rowptr, D.col, D.perm = struct.rowptr.data_ptr(), struct.col.data_ptr(), struct.perm.data_ptr()
+        D.rowptr_t, D.col_t, D.perm_t = struct.rowptr_t.data_ptr(), struct.col_t.data_ptr(), struct.perm_t.data_ptr()
+        D.x, D.skip, D.edge_attr = x.data_ptr(), _ptr(skip), attr.data_ptr()
+        D.vocab = ctypes.cast(vc, ctypes.c_void_p) if vc is not None else None
+        D.enc_params = ctypes.cast(encp, ctypes.c_void_p)
+        D.softmax_beta = _ptr(beta)
+        D.rule1, D.W1, D.b1 = r1.data_ptr(), W1.data_ptr(), _ptr(b1)
+        if mlp:
+            D.rule2, D.W2, D.b2 = r2.data_ptr(), W2.data_ptr(), _ptr(b2)
+        for k, flat in ((1, flat1 if mlp else None), (2, flat2)):
+            if flat is None:
+                continue
+            gamma, bt, rmean, rvar, tracked = flat
+            setattr(D, f"gamma{k}", _ptr(gamma)); setattr(D, f"beta{k}", _ptr(bt))
+            setattr(D, f"running_mean{k}", _ptr(rmean)); setattr(D, f"running_var{k}", _ptr(rvar))
+            setattr(D, f"tracked{k}", _ptr(tracked)); setattr(D, f"n_tracked{k}", 0 if tracked is None else tracked.numel())
+        ap = acts.data_ptr()
+        sz = N * F * 4
+        if mlp:
+            D.agg, D.y1, D.a1, D.z = ap, ap + sz, ap + 2 * sz, ap + 3 * sz
+        else:
+            D.agg, D.z = ap, ap + sz
+        D.out = out.data_ptr()
+        D.stats1, D.stats2 = stats.data_ptr(), stats.data_ptr() + 2 * F * 4
+        D.aux_f, D.aux_i = _ptr(aux_f), _ptr(aux_i)
+        D.ws_lin1, D.ws_lin1_bytes = ws_lin1.data_ptr(), ws_lin1.numel()
+        if mlp:
+            D.ws_lin2, D.ws_lin2_bytes = ws_lin2.data_ptr(), ws_lin2.numel()
+        D.ws, D.ws_bytes = ws.data_ptr(), ws.numel()
+        run("phc_conv_layer_fwd", None, ctypes.byref(D), st, launches=11 if mlp else 6)
+        ctx.save_for_backward(x, attr, acts, stats, aux_f, aux_i)
+        ctx.misc = (cfg, struct, D, vc, encp, ws_lin1, ws_lin2, tensors, skip is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        cfg, struct, D, vc, encp, ws_lin1, ws_lin2, tensors, has_skip = ctx.misc
+        (n, linear, enc_dim, vocab, reduce, msg_act, self_loops, mlp, act1, act2, use_bn1, use_bn2, training, drop_p, same, seed,
+         precision, n_enc, has_beta, nb1, nb2, mom1, eps1, mom2, eps2) = cfg
+        x, attr, acts, stats, aux_f, aux_i = ctx.saved_tensors
+        i = 1 if has_beta else 0
+        enc = tensors[i:i + n_enc]; i += n_enc
+        r1, W1, b1 = tensors[i:i + 3]; i += 3 + nb1
+        r2 = W2 = b2 = None
+        if mlp:
+            r2, W2, b2 = tensors[i:i + 3]
+        dev = x.device
+        st = _stream(dev)
+        g = g.contiguous()
+        N, F = x.shape
+        f32 = dict(dtype=torch.float32, device=dev)
+        tmp = torch.empty((2, N, F), **f32)
+        dx = torch.empty_like(x)
+        # every parameter gradient of the layer lives in one flat buffer
+        sizes = [p.numel() for p in enc] + [r1.numel(), W1.numel(), 0 if b1 is None else b1.numel()]
+        sizes += [r2.numel(), W2.numel(), 0 if b2 is None else b2.numel()] if mlp else [0, 0, 0]
+        sizes += [2 * F if nb1 else 0, 2 * F if nb2 else 0]
+        flatg = torch.empty(sum((k + 3) & ~3 for k in sizes) + 4, **f32)
+        base, offs, o = flatg.data_ptr(), [], 0
+        for k in sizes:
+            offs.append(o)
+            o += (k + 3) & ~3                   # 16-byte aligned pieces
+        genc = [flatg[offs[j]:offs[j] + sizes[j]].view(enc[j].shape) for j in range(n_enc)]
+        j = n_enc
+
+        def piece(t, jj, want=True):
+            return flatg[offs[jj]:offs[jj] + sizes[jj]].view(t.shape) if (t is not None and want) else None
+
+        dr1, dW1, db1 = piece(r1, j, r1.requires_grad), piece(W1, j + 1), piece(b1, j + 2)
+        dr2, dW2, db2 = (piece(r2, j + 3, r2.requires_grad), piece(W2, j + 4), piece(b2, j + 5)) if mlp else (None, None, None)
+        dgb1 = flatg[offs[j + 6]:offs[j + 6] + 2 * F].view(2, F) if nb1 else None
+        dgb2 = flatg[offs[j + 7]:offs[j + 7] + 2 * F].view(2, F) if nb2 else None
+        dbeta = torch.zeros((), **f32) if reduce == 4 else None
+        rows = enc_dim + 1 if linear else int(sum(vocab))
+        ws = _scratch(_ws_bytes("phc_conv_layer_workspace_bytes", N, F, n, rows, precision), dev, st)
+        sums = _node_sums(struct, attr, linear, enc_dim, vocab, vc, reduce, msg_act, rows, N, dev, st)
+        gencp = _ptr_array(genc)
+        D.ws, D.ws_bytes = ws.data_ptr(), ws.numel()
+        D.gout, D.node_sums = g.data_ptr(), _ptr(sums)
+        D.tmp_a, D.tmp_b, D.dx = tmp.data_ptr(), tmp.data_ptr() + N * F * 4, dx.data_ptr()
+        D.d_softmax_beta = _ptr(dbeta)
+        D.d_enc_params = ctypes.cast(gencp, ctypes.c_void_p)
+        D.d_rule1, D.d_W1, D.d_b1 = _ptr(dr1), _ptr(dW1), _ptr(db1)
+        D.d_rule2, D.d_W2, D.d_b2 = _ptr(dr2), _ptr(dW2), _ptr(db2)
+        D.d_gb1, D.d_gb2 = _ptr(dgb1), _ptr(dgb2)
+        run("phc_conv_layer_bwd", None, ctypes.byref(D), st, launches=17 if mlp else 10)
+        if not mlp and self_loops:
+            dx.add_(tmp[0])                     # residual branch of PHMLinear(agg) + x
+        grads = []
+        if has_beta:
+            grads.append(dbeta)
+        grads += genc
+        grads += [dr1, dW1, db1]
+        grads += _split_gb(dgb1, nb1 // 2, F) if nb1 else []
+        if mlp:
+            grads += [dr2, dW2, db2]
+        grads += _split_gb(dgb2, nb2 // 2, F) if nb2 else []
+        return (None, None, None, dx, g if has_skip else None, None) + tuple(grads)
+
+
 def conv_layer(x, skip, edge_attr, struct: EdgeStructure, *, phm_dim: int, enc_linear: bool, enc_params: Sequence[torch.Tensor],
                enc_vocab: Sequence[int], reduce: str, msg_act: str, beta: Optional[torch.Tensor], add_self_loops: bool, mlp: bool,
                lin1, lin2, norm1, norm2, act1: str, act2: str, training: bool, drop_p: float, drop_same: bool) -> torch.Tensor:
@@ -239,4 +412,5 @@ def conv_layer(x, skip, edge_attr, struct: EdgeStructure, *, phm_dim: int, enc_l
            float(drop_p) if active_drop else 0.0, bool(drop_same), seed, default_precision(), len(enc_params), has_beta, len(p1), len(p2),
            float(norm1.momentum) if norm1 is not None else 0.1, float(norm1.eps) if norm1 is not None else 1e-5,
            float(norm2.momentum) if norm2 is not None else 0.1, float(norm2.eps) if norm2 is not None else 1e-5)
-    return _ConvLayer.apply(cfg, struct, (flat1, flat2), x, skip, edge_attr, *tensors)
+    node = _ConvLayerCall if (SINGLE_CALL and not PROFILE.timing) else _ConvLayer    # per-operator calls when each is being timed
+    return node.apply(cfg, struct, (flat1, flat2), x, skip, edge_attr, *tensors)

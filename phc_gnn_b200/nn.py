@@ -145,7 +145,7 @@ class NaivePHMNorm(nn.Module):
         else:
             groups += [None, None, None]
         for i, g in enumerate(groups):
-            self._flat[i] = alias_flat(self._flat[i], g) if g is not None else None
+            self._flat[i] = alias_flat(self._flat[i], g, quick=True) if g is not None else None
         return tuple(self._flat)
 
     def autograd_params(self):

@@ -32,13 +32,16 @@ def _compare(got, want, rtol, what, noise=None):
         assert_close(got["running"][k].float(), v.float(), rtol, max(1e-5, tol("running", v.float(), k)), f"{what}: {k}")
 
 
-@pytest.mark.parametrize("fuse", ["layer", "encoder", "none"], ids=["one-node-per-layer", "fused-encoder", "separate-ops"])
+@pytest.mark.parametrize("fuse", ["call", "layer", "encoder", "none"],
+                         ids=["one-call-per-layer", "one-node-per-layer", "fused-encoder", "separate-ops"])
 @pytest.mark.parametrize("name", golden_cases())
 def test_model_matches_reference_golden(name, fuse, monkeypatch):
     monkeypatch.setenv("PHC_PRECISION", "fp32")
+    from phc_gnn_b200 import layer
+    monkeypatch.setattr(layer, "SINGLE_CALL", fuse == "call")        # phc_conv_layer_fwd/bwd vs one C-ABI call per operator
     fx = load_golden(name)
     got = product_train_eval(fx["cfg"], fx["state"], fx["batch"], fx["loss_kind"], fx["reg_scale"], DEV,
-                             fuse_edge_encoder=fuse != "none", fuse_layer=fuse == "layer")
+                             fuse_edge_encoder=fuse != "none", fuse_layer=fuse in ("call", "layer"))
     want = dict(logits=fx["logits_train"], loss=fx["loss"], reg=fx["reg"], grads=fx["grads"], running=fx["running_after"],
                 logits_eval=fx["logits_eval"])
     _compare(got, want, RTOL, name)
