@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(256) aggregate_fwd_kernel(const float* __restr
                                                             const int* __restrict__ perm, int N, int F, int act,
                                                             const float* __restrict__ beta_ptr, int self_loop, float* __restrict__ out,
                                                             float* __restrict__ aux_f, int* __restrict__ aux_i) {
+  pdl_begin();
   const int fv = F / VEC;
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)N * fv) return;
@@ -140,6 +141,7 @@ __global__ void __launch_bounds__(256) aggregate_bwd_edge_kernel(const float* __
                                                                  const int* __restrict__ col, const int* __restrict__ perm, int N, int F,
                                                                  int act, const float* __restrict__ beta_ptr, float* __restrict__ dea,
                                                                  float* __restrict__ dbeta_part) {
+  pdl_begin();
   constexpr bool NEED_PRE = HAS_ACT || RED == PHC_RED_SOFTMAX;
   const int fv = F / VEC;
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -209,6 +211,7 @@ __global__ void __launch_bounds__(256) aggregate_bwd_node_kernel(const float* __
                                                                  const int* __restrict__ rowptr, const int* __restrict__ rowptr_t,
                                                                  const int* __restrict__ col_t, const int* __restrict__ perm_t, int N,
                                                                  int F, int self_loop, float* __restrict__ dx) {
+  pdl_begin();
   const int fv = F / VEC;
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)N * fv) return;
@@ -262,6 +265,7 @@ __global__ void __launch_bounds__(256) aggregate_bwd_node_kernel(const float* __
 }
 
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ part, int n, float* __restrict__ out) {
+  pdl_begin();
   __shared__ float red[256];
   float s = 0.f;
   for (int i = threadIdx.x; i < n; i += 256) s += part[i];
@@ -280,9 +284,9 @@ int launch_fwd(const float* x, const float* ea, const int* rowptr, const int* co
   long long threads = (long long)N * (F / VEC);
   int grid = phc_div_up(threads, 256);
   if (act == PHC_ACT_IDENTITY)
-    aggregate_fwd_kernel<VEC, RED, false><<<grid, 256, 0, st>>>(x, ea, rowptr, col, perm, N, F, act, beta, self_loop, out, aux_f, aux_i);
+    phc_launch(aggregate_fwd_kernel<VEC, RED, false>, dim3(grid), dim3(256), 0, st, x, ea, rowptr, col, perm, N, F, act, beta, self_loop, out, aux_f, aux_i);
   else
-    aggregate_fwd_kernel<VEC, RED, true><<<grid, 256, 0, st>>>(x, ea, rowptr, col, perm, N, F, act, beta, self_loop, out, aux_f, aux_i);
+    phc_launch(aggregate_fwd_kernel<VEC, RED, true>, dim3(grid), dim3(256), 0, st, x, ea, rowptr, col, perm, N, F, act, beta, self_loop, out, aux_f, aux_i);
   return phc_check_launch("phc_aggregate_fwd");
 }
 
@@ -291,9 +295,9 @@ int launch_bwd_edge(const float* g, const float* x, const float* ea, const float
                     const int* col, const int* perm, int N, int F, int act, const float* beta, float* dea, float* part, int grid,
                     cudaStream_t st) {
   if (act == PHC_ACT_IDENTITY)
-    aggregate_bwd_edge_kernel<VEC, RED, false><<<grid, 256, 0, st>>>(g, x, ea, aux_f, aux_i, rowptr, col, perm, N, F, act, beta, dea, part);
+    phc_launch(aggregate_bwd_edge_kernel<VEC, RED, false>, dim3(grid), dim3(256), 0, st, g, x, ea, aux_f, aux_i, rowptr, col, perm, N, F, act, beta, dea, part);
   else
-    aggregate_bwd_edge_kernel<VEC, RED, true><<<grid, 256, 0, st>>>(g, x, ea, aux_f, aux_i, rowptr, col, perm, N, F, act, beta, dea, part);
+    phc_launch(aggregate_bwd_edge_kernel<VEC, RED, true>, dim3(grid), dim3(256), 0, st, g, x, ea, aux_f, aux_i, rowptr, col, perm, N, F, act, beta, dea, part);
   return phc_check_launch("phc_aggregate_bwd(edge)");
 }
 
@@ -327,11 +331,11 @@ int dispatch_bwd_node(bool simple, bool mean, const float* g, const float* dea, 
                       const int* perm_t, int N, int F, int self_loop, float* dx, cudaStream_t st) {
   int grid = phc_div_up((long long)N * (F / VEC), 256);
   if (simple && mean)
-    aggregate_bwd_node_kernel<VEC, true, true><<<grid, 256, 0, st>>>(g, dea, rowptr, rowptr_t, col_t, perm_t, N, F, self_loop, dx);
+    phc_launch(aggregate_bwd_node_kernel<VEC, true, true>, dim3(grid), dim3(256), 0, st, g, dea, rowptr, rowptr_t, col_t, perm_t, N, F, self_loop, dx);
   else if (simple)
-    aggregate_bwd_node_kernel<VEC, true, false><<<grid, 256, 0, st>>>(g, dea, rowptr, rowptr_t, col_t, perm_t, N, F, self_loop, dx);
+    phc_launch(aggregate_bwd_node_kernel<VEC, true, false>, dim3(grid), dim3(256), 0, st, g, dea, rowptr, rowptr_t, col_t, perm_t, N, F, self_loop, dx);
   else
-    aggregate_bwd_node_kernel<VEC, false, false><<<grid, 256, 0, st>>>(g, dea, rowptr, rowptr_t, col_t, perm_t, N, F, self_loop, dx);
+    phc_launch(aggregate_bwd_node_kernel<VEC, false, false>, dim3(grid), dim3(256), 0, st, g, dea, rowptr, rowptr_t, col_t, perm_t, N, F, self_loop, dx);
   return phc_check_launch("phc_aggregate_bwd(node)");
 }
 
@@ -395,7 +399,7 @@ int phc_aggregate_bwd(const float* gout, const float* x, const float* ea, const 
   else rc = dispatch_bwd_edge<1>(reduce, gout, x, ea, aux_f, aux_i, rowptr, col, perm, N, F, msg_act, beta, dea, part, grid, stream);
   if (rc) return rc;
   if (reduce == PHC_RED_SOFTMAX && dbeta) {
-    reduce_partials_kernel<<<1, 256, 0, stream>>>(part, grid, dbeta);
+    phc_launch(reduce_partials_kernel, dim3(1), dim3(256), 0, stream, part, grid, dbeta);
     rc = phc_check_launch("phc_aggregate_bwd(dbeta)");
     if (rc) return rc;
   }

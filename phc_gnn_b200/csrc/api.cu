@@ -1,6 +1,7 @@
 // libphc_b200.so: error reporting, version, and the PHMLinear precision-mode dispatch.
 #include "common.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 static thread_local char g_err[512] = "";
 
@@ -9,6 +10,11 @@ void phc_set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool phc_pdl_enabled() {
+  static const bool on = getenv("PHC_NO_PDL") == nullptr;
+  return on;
 }
 
 int phc_check_launch(const char* what) {

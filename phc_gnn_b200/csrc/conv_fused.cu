@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(256, 4) conv_fwd_kernel(const EncDesc enc, con
                                 const int* __restrict__ col, const int* __restrict__ perm, int N, int F, int rpi, int act,
                                 const float* __restrict__ beta_ptr, int self_loop, float* __restrict__ out, float* __restrict__ aux_f,
                                 int* __restrict__ aux_i) {
+  pdl_begin();
   extern __shared__ __align__(16) float tab[];
   load_table(enc, F, tab);
   __syncthreads();
@@ -228,6 +229,7 @@ __global__ void conv_bwd_param_kernel(const EncDesc enc, const float* __restrict
                                       const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ perm, int N,
                                       int F, int rpi, int act, const float* __restrict__ beta_ptr, float* __restrict__ part,
                                       float* __restrict__ dbeta_part) {
+  pdl_begin();
   extern __shared__ __align__(16) float smem[];
   float* tab = smem;                            // [R][F]
   float* accs = smem + (size_t)enc.R * F;       // [rpi][R][F]
@@ -342,6 +344,7 @@ __global__ void conv_bwd_param_kernel(const EncDesc enc, const float* __restrict
 // sum block partials (lane l takes blocks l, l+32, ... in order, then a fixed butterfly) and scatter into the
 // individual parameter gradients; one warp per table element
 __global__ void __launch_bounds__(256) conv_bwd_param_final_kernel(const EncDesc enc, const float* __restrict__ part, int blocks, int F) {
+  pdl_begin();
   const long long t = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (t >= (long long)enc.R * F) return;
@@ -368,6 +371,7 @@ __global__ void __launch_bounds__(256) conv_bwd_param_final_kernel(const EncDesc
 // S depends only on the batch (not on the layer), is N x R (R <= 16) and is computed once per batch.
 __global__ void __launch_bounds__(256) edge_feature_sums_kernel(const EncDesc enc, const void* __restrict__ attr, const int* __restrict__ rowptr,
                                                                 const int* __restrict__ perm, int N, int mean, float* __restrict__ S) {
+  pdl_begin();
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)N * enc.R) return;
   const int i = (int)(t / enc.R), r = (int)(t - (long long)i * enc.R);
@@ -392,6 +396,7 @@ __global__ void __launch_bounds__(256) edge_feature_sums_kernel(const EncDesc en
 template <int RT>
 __global__ void __launch_bounds__(128) conv_bwd_param_simple_kernel(const float* __restrict__ g, const float* __restrict__ S, int N, int F,
                                                                     int rows_per_block, float* __restrict__ part) {
+  pdl_begin();
   const int f = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
   if (f >= F) return;
   const int r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, N);
@@ -413,6 +418,7 @@ __global__ void __launch_bounds__(128) conv_bwd_param_simple_kernel(const float*
 }
 
 __global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restrict__ part, int n, float* __restrict__ out) {
+  pdl_begin();
   __shared__ float red[256];
   float s = 0.f;
   for (int i = threadIdx.x; i < n; i += 256) s += part[i];
@@ -432,6 +438,7 @@ __global__ void conv_bwd_node_kernel(const EncDesc enc, const float* __restrict_
                                      const int* __restrict__ rowptr, const int* __restrict__ rowptr_t, const int* __restrict__ col_t,
                                      const int* __restrict__ perm_t, int N, int F, int rpi, int act, const float* __restrict__ beta_ptr,
                                      int self_loop, float* __restrict__ dx) {
+  pdl_begin();
   extern __shared__ __align__(16) float tab[];
   load_table(enc, F, tab);
   __syncthreads();
@@ -553,7 +560,7 @@ int phc_conv_fused_fwd(const float* x, const void* edge_attr, int enc_kind, int 
   const int dt = (enc_kind == ENC_LINEAR && enc_dim <= 8) ? enc_dim : 0;
 #define PHC_LAUNCH2(RED, DT)                                                                                                     \
   { if (!ensure_smem(conv_fwd_kernel<RED, DT>, smem)) { phc_set_error("phc_conv_fused_fwd: shared memory"); return PHC_ERR_CUDA; } \
-    conv_fwd_kernel<RED, DT><<<g.blocks, g.threads, smem, stream>>>(d, x, edge_attr, rowptr, col, perm, num_nodes, width, g.rpi, msg_act, \
+    phc_launch(conv_fwd_kernel<RED, DT>, dim3(g.blocks), dim3(g.threads), smem, stream, d, x, edge_attr, rowptr, col, perm, num_nodes, width, g.rpi, msg_act, \
                                                                     beta, self_loop, out, aux_f, aux_i); }
 #define PHC_LAUNCH(RED)                                                                                                          \
   switch (dt) {                                                                                                                  \
@@ -578,7 +585,7 @@ int phc_edge_feature_sums(const void* edge_attr, int enc_kind, int enc_dim, cons
   const float* none[ENC_MAX_PTRS] = {nullptr};
   PHC_REQUIRE(make_desc(d, enc_kind, enc_dim, vocab, none, nullptr, 1, 4) == 0, "phc_edge_feature_sums: unsupported encoder");
   if (num_nodes == 0) return PHC_OK;
-  edge_feature_sums_kernel<<<phc_div_up((long long)num_nodes * d.R, 256), 256, 0, stream>>>(d, edge_attr, rowptr, perm, num_nodes, mean,
+  phc_launch(edge_feature_sums_kernel, dim3(phc_div_up((long long)num_nodes * d.R, 256)), dim3(256), 0, stream, d, edge_attr, rowptr, perm, num_nodes, mean,
                                                                                            node_sums);
   return phc_check_launch("phc_edge_feature_sums");
 }
@@ -614,12 +621,12 @@ int phc_conv_fused_bwd(const float* gout, const float* x, const void* edge_attr,
     PHC_REQUIRE((size_t)nb * d.R * F * sizeof(float) <= workspace_bytes, "phc_conv_fused_bwd: workspace too small for the node-sum path");
     dim3 grid(nb, phc_div_up(F / 4, 128));
     switch (d.R) {
-#define PHC_CASE(RT) case RT: conv_bwd_param_simple_kernel<RT><<<grid, 128, 0, stream>>>(gout, node_sums, N, F, rpb, part); break;
+#define PHC_CASE(RT) case RT: phc_launch(conv_bwd_param_simple_kernel<RT>, dim3(grid), dim3(128), 0, stream, gout, node_sums, N, F, rpb, part); break;
       PHC_CASE(1) PHC_CASE(2) PHC_CASE(3) PHC_CASE(4) PHC_CASE(5) PHC_CASE(6) PHC_CASE(7) PHC_CASE(8)
       PHC_CASE(9) PHC_CASE(10) PHC_CASE(11) PHC_CASE(12) PHC_CASE(13) PHC_CASE(14) PHC_CASE(15) PHC_CASE(16)
 #undef PHC_CASE
     }
-    conv_bwd_param_final_kernel<<<phc_div_up((long long)d.R * F * 32, 256), 256, 0, stream>>>(d, part, nb, F);
+    phc_launch(conv_bwd_param_final_kernel, dim3(phc_div_up((long long)d.R * F * 32, 256)), dim3(256), 0, stream, d, part, nb, F);
     int rc = phc_check_launch("phc_conv_fused_bwd(node sums)");
     if (rc) return rc;
     if (dx) return phc_aggregate_bwd_node_simple(reduce == PHC_RED_MEAN, gout, rowptr, rowptr_t, col_t, perm_t, N, F, self_loop, dx, stream);
@@ -628,7 +635,7 @@ int phc_conv_fused_bwd(const float* gout, const float* x, const void* edge_attr,
   const int dt = (enc_kind == ENC_LINEAR && enc_dim <= 8) ? enc_dim : 0;
 #define PHC_PARAM(RED, DT)                                                                                                            \
   { if (!ensure_smem(conv_bwd_param_kernel<RED, DT>, smem_p)) { phc_set_error("phc_conv_fused_bwd: shared memory"); return PHC_ERR_CUDA; } \
-    if (N > 0) conv_bwd_param_kernel<RED, DT><<<g.blocks, g.threads, smem_p, stream>>>(d, gout, x, edge_attr, aux_f, aux_i, rowptr, col, perm, \
+    if (N > 0) phc_launch(conv_bwd_param_kernel<RED, DT>, dim3(g.blocks), dim3(g.threads), smem_p, stream, d, gout, x, edge_attr, aux_f, aux_i, rowptr, col, perm, \
                                                                                        N, F, g.rpi, msg_act, beta, part, dbp); }
 #define PHC_LAUNCH(RED)                                                                                                               \
   if (!ensure_smem(conv_bwd_node_kernel<RED>, smem_n)) { phc_set_error("phc_conv_fused_bwd: shared memory"); return PHC_ERR_CUDA; }   \
@@ -636,7 +643,7 @@ int phc_conv_fused_bwd(const float* gout, const float* x, const void* edge_attr,
     case 1: PHC_PARAM(RED, 1) break; case 2: PHC_PARAM(RED, 2) break; case 3: PHC_PARAM(RED, 3) break; case 4: PHC_PARAM(RED, 4) break; \
     case 5: PHC_PARAM(RED, 5) break; case 6: PHC_PARAM(RED, 6) break; case 7: PHC_PARAM(RED, 7) break; case 8: PHC_PARAM(RED, 8) break; \
     default: PHC_PARAM(RED, 0) break; }                                                                                               \
-  if (N > 0 && dx && !simple) conv_bwd_node_kernel<RED><<<g.blocks, g.threads, smem_n, stream>>>(d, gout, x, edge_attr, aux_f, aux_i, rowptr,   \
+  if (N > 0 && dx && !simple) phc_launch(conv_bwd_node_kernel<RED>, dim3(g.blocks), dim3(g.threads), smem_n, stream, d, gout, x, edge_attr, aux_f, aux_i, rowptr,   \
                                                                                         rowptr_t, col_t, perm_t, N, F, g.rpi, msg_act, \
                                                                                         beta, self_loop, dx);
   switch (reduce) {
@@ -649,8 +656,8 @@ int phc_conv_fused_bwd(const float* gout, const float* x, const void* edge_attr,
 #undef PHC_LAUNCH
 #undef PHC_PARAM
   const int blocks_used = N > 0 ? g.blocks : 0;
-  conv_bwd_param_final_kernel<<<phc_div_up((long long)d.R * F * 32, 256), 256, 0, stream>>>(d, part, blocks_used, F);
-  if (reduce == PHC_RED_SOFTMAX && dbeta) sum_partials_kernel<<<1, 256, 0, stream>>>(dbp, blocks_used, dbeta);
+  phc_launch(conv_bwd_param_final_kernel, dim3(phc_div_up((long long)d.R * F * 32, 256)), dim3(256), 0, stream, d, part, blocks_used, F);
+  if (reduce == PHC_RED_SOFTMAX && dbeta) phc_launch(sum_partials_kernel, dim3(1), dim3(256), 0, stream, dbp, blocks_used, dbeta);
   int rc = phc_check_launch("phc_conv_fused_bwd");
   if (rc) return rc;
   if (dx && simple && N > 0)

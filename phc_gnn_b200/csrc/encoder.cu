@@ -31,6 +31,7 @@ namespace {
 template <int VEC>
 __global__ void __launch_bounds__(256) embed_fwd_kernel(const long long* __restrict__ idx, PtrTable tables, IntTable vocab, int R, int C,
                                                         int n, int Fc, float* __restrict__ out) {
+  pdl_begin();
   const int fcv = Fc / VEC;
   const int F = n * Fc;
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -54,6 +55,7 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const long long* __restr
 // grid (row chunks, C, feature tiles of blockDim.x flat features). dynamic smem: vocab[col] * blockDim.x floats.
 __global__ void embed_bwd_partial_kernel(const float* __restrict__ g, const long long* __restrict__ idx, IntTable vocab, IntTable voff,
                                          int R, int C, int F, int rows_per_chunk, int vtot, float* __restrict__ part) {
+  pdl_begin();
   extern __shared__ float acc[];
   const int col = blockIdx.y;
   const int V = vocab.v[col];
@@ -76,6 +78,7 @@ __global__ void embed_bwd_partial_kernel(const float* __restrict__ g, const long
 // dtable[c][col][v, f'] = sum over chunks of part[chunk][voff[col]+v][c*Fc+f']
 __global__ void __launch_bounds__(256) embed_bwd_final_kernel(const float* __restrict__ part, MutPtrTable dtables, IntTable vocab,
                                                               IntTable voff, int chunks, int C, int n, int Fc, int vtot) {
+  pdl_begin();
   const int F = n * Fc;
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)vtot * F) return;
@@ -98,6 +101,7 @@ constexpr int LIN_ROWS = 32;     // rows per block in forward
 template <int D>
 __global__ void __launch_bounds__(128) linenc_fwd_kernel(const float* __restrict__ feat, PtrTable weights, PtrTable biases, int R, int Fc,
                                                          int F, float* __restrict__ out) {
+  pdl_begin();
   const int f = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (f >= F) return;
   float w[4][D], bq[4];
@@ -130,6 +134,7 @@ __global__ void __launch_bounds__(128) linenc_fwd_kernel(const float* __restrict
 // generic fallback (F % 4 != 0 or unaligned): one thread per output element
 __global__ void __launch_bounds__(256) linenc_fwd_scalar_kernel(const float* __restrict__ feat, PtrTable weights, PtrTable biases, int R,
                                                                 int D, int Fc, int F, float* __restrict__ out) {
+  pdl_begin();
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)R * F) return;
   const int r = (int)(t / F), f = (int)(t % F);
@@ -144,6 +149,7 @@ __global__ void __launch_bounds__(256) linenc_fwd_scalar_kernel(const float* __r
 template <int D>
 __global__ void __launch_bounds__(128) linenc_bwd_partial_kernel(const float* __restrict__ g, const float* __restrict__ feat, int R, int F,
                                                                  int rows_per_chunk, float* __restrict__ part) {
+  pdl_begin();
   const int f = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (f >= F) return;
   const int r0 = blockIdx.y * rows_per_chunk, r1 = min(r0 + rows_per_chunk, R);
@@ -175,6 +181,7 @@ __global__ void __launch_bounds__(128) linenc_bwd_partial_kernel(const float* __
 
 __global__ void __launch_bounds__(128) linenc_bwd_partial_scalar_kernel(const float* __restrict__ g, const float* __restrict__ feat, int R,
                                                                         int D, int F, int rows_per_chunk, float* __restrict__ part) {
+  pdl_begin();
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= F) return;
   const int r0 = blockIdx.y * rows_per_chunk, r1 = min(r0 + rows_per_chunk, R);
@@ -197,6 +204,7 @@ __global__ void __launch_bounds__(128) linenc_bwd_partial_scalar_kernel(const fl
 
 __global__ void __launch_bounds__(256) linenc_bwd_final_kernel(const float* __restrict__ part, MutPtrTable dweights, MutPtrTable dbiases,
                                                                int chunks, int D, int n, int Fc) {
+  pdl_begin();
   const int F = n * Fc;
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)F * (D + 1)) return;
@@ -211,12 +219,12 @@ __global__ void __launch_bounds__(256) linenc_bwd_final_kernel(const float* __re
 template <int D>
 void launch_linenc_fwd(const float* feat, const PtrTable& w, const PtrTable& b, int R, int Fc, int F, float* out, cudaStream_t st) {
   dim3 grid(phc_div_up(F / 4, 128), phc_div_up(R, LIN_ROWS));
-  linenc_fwd_kernel<D><<<grid, 128, 0, st>>>(feat, w, b, R, Fc, F, out);
+  phc_launch(linenc_fwd_kernel<D>, dim3(grid), dim3(128), 0, st, feat, w, b, R, Fc, F, out);
 }
 template <int D>
 void launch_linenc_bwd(const float* g, const float* feat, int R, int F, int rpc, int chunks, float* part, cudaStream_t st) {
   dim3 grid(phc_div_up(F / 4, 128), chunks);
-  linenc_bwd_partial_kernel<D><<<grid, 128, 0, st>>>(g, feat, R, F, rpc, part);
+  phc_launch(linenc_bwd_partial_kernel<D>, dim3(grid), dim3(128), 0, st, g, feat, R, F, rpc, part);
 }
 
 int embed_chunks(int R) {
@@ -246,8 +254,8 @@ int phc_embed_sum_fwd(const long long* idx, const float* const* tables, const in
   for (int i = 0; i < phm_dim * cols; ++i) { tb.p[i] = tables[i]; v4 = v4 && phc_aligned16(tables[i]); }
   for (int i = 0; i < cols; ++i) vc.v[i] = vocab[i];
   const int n = phm_dim, Fc = width_per_component;
-  if (v4) embed_fwd_kernel<4><<<phc_div_up((long long)rows * n * (Fc / 4), 256), 256, 0, stream>>>(idx, tb, vc, rows, cols, n, Fc, out);
-  else embed_fwd_kernel<1><<<phc_div_up((long long)rows * n * Fc, 256), 256, 0, stream>>>(idx, tb, vc, rows, cols, n, Fc, out);
+  if (v4) phc_launch(embed_fwd_kernel<4>, dim3(phc_div_up((long long)rows * n * (Fc / 4), 256)), dim3(256), 0, stream, idx, tb, vc, rows, cols, n, Fc, out);
+  else phc_launch(embed_fwd_kernel<1>, dim3(phc_div_up((long long)rows * n * Fc, 256)), dim3(256), 0, stream, idx, tb, vc, rows, cols, n, Fc, out);
   return phc_check_launch("phc_embed_sum_fwd");
 }
 
@@ -272,8 +280,8 @@ int phc_embed_sum_bwd(const float* gout, const long long* idx, float* const* dta
     attr_set = true;
   }
   dim3 grid(chunks, cols, phc_div_up(F, ft));
-  embed_bwd_partial_kernel<<<grid, ft, smem, stream>>>(gout, idx, vc, vo, rows, cols, F, rpc, vtot, part);
-  embed_bwd_final_kernel<<<phc_div_up((long long)vtot * F, 256), 256, 0, stream>>>(part, dt, vc, vo, chunks, cols, n, Fc, vtot);
+  phc_launch(embed_bwd_partial_kernel, dim3(grid), dim3(ft), smem, stream, gout, idx, vc, vo, rows, cols, F, rpc, vtot, part);
+  phc_launch(embed_bwd_final_kernel, dim3(phc_div_up((long long)vtot * F, 256)), dim3(256), 0, stream, part, dt, vc, vo, chunks, cols, n, Fc, vtot);
   return phc_check_launch("phc_embed_sum_bwd");
 }
 
@@ -298,7 +306,7 @@ int phc_linear_encoder_fwd(const float* feat, const float* const* weights, const
 #undef PHC_CASE
     }
   } else {
-    linenc_fwd_scalar_kernel<<<phc_div_up((long long)rows * F, 256), 256, 0, stream>>>(feat, w, b, rows, in_dim, Fc, F, out);
+    phc_launch(linenc_fwd_scalar_kernel, dim3(phc_div_up((long long)rows * F, 256)), dim3(256), 0, stream, feat, w, b, rows, in_dim, Fc, F, out);
   }
   return phc_check_launch("phc_linear_encoder_fwd");
 }
@@ -323,9 +331,9 @@ int phc_linear_encoder_bwd(const float* gout, const float* feat, float* const* d
     }
   } else {
     dim3 grid(phc_div_up(F, 128), chunks);
-    linenc_bwd_partial_scalar_kernel<<<grid, 128, 0, stream>>>(gout, feat, rows, in_dim, F, rpc, part);
+    phc_launch(linenc_bwd_partial_scalar_kernel, dim3(grid), dim3(128), 0, stream, gout, feat, rows, in_dim, F, rpc, part);
   }
-  linenc_bwd_final_kernel<<<phc_div_up((long long)F * (in_dim + 1), 256), 256, 0, stream>>>(part, dw, db, chunks, in_dim, n, Fc);
+  phc_launch(linenc_bwd_final_kernel, dim3(phc_div_up((long long)F * (in_dim + 1), 256)), dim3(256), 0, stream, part, dw, db, chunks, in_dim, n, Fc);
   return phc_check_launch("phc_linear_encoder_bwd");
 }
 

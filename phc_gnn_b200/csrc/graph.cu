@@ -18,6 +18,7 @@ namespace {
 
 __global__ void hist_kernel(const long long* __restrict__ ei, int E, int N, int* __restrict__ cnt_dst,
                             int* __restrict__ cnt_src, int* __restrict__ status) {
+  pdl_begin();
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
   long long s = ei[e], d = ei[(size_t)E + e];
@@ -30,6 +31,7 @@ __global__ void hist_kernel(const long long* __restrict__ ei, int E, int N, int*
 // into rowptr[0..N] and a copy into cursor[0..N) for the ticket scatter.
 __global__ void __launch_bounds__(1024) scan_kernel(const int* __restrict__ cnt_all, int N, int* __restrict__ rowptr_dst,
                                                     int* __restrict__ rowptr_src, int* __restrict__ cursor_all) {
+  pdl_begin();
   const int* cnt = cnt_all + (size_t)blockIdx.x * N;
   int* rowptr = blockIdx.x == 0 ? rowptr_dst : rowptr_src;
   int* cursor = cursor_all + (size_t)blockIdx.x * N;
@@ -59,6 +61,7 @@ __global__ void __launch_bounds__(1024) scan_kernel(const int* __restrict__ cnt_
 
 __global__ void ticket_kernel(const long long* __restrict__ ei, int E, int N, int* __restrict__ cursor_all,
                               int* __restrict__ slot_dst, int* __restrict__ slot_src) {
+  pdl_begin();
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
   long long s = ei[e], d = ei[(size_t)E + e];
@@ -76,6 +79,7 @@ __global__ void __launch_bounds__(256) rowsort_kernel(const long long* __restric
                                                       const int* __restrict__ slot_dst, const int* __restrict__ slot_src,
                                                       int* __restrict__ perm_dst, int* __restrict__ col_dst,
                                                       int* __restrict__ perm_src, int* __restrict__ col_src) {
+  pdl_begin();
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (warp >= 2 * N) return;
@@ -119,6 +123,7 @@ __global__ void __launch_bounds__(256) rowsort_kernel(const long long* __restric
 
 // graph_ptr from an ascending batch vector: ptr[b] = first node of graph b (empty graphs allowed).
 __global__ void segptr_kernel(const long long* __restrict__ batch, int N, int B, int* __restrict__ ptr, int* __restrict__ status) {
+  pdl_begin();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i > N) return;
   if (N == 0) { if (i == 0) for (int b = 0; b <= B; ++b) ptr[b] = 0; return; }
@@ -136,6 +141,7 @@ __global__ void segptr_kernel(const long long* __restrict__ batch, int N, int B,
 }
 
 __global__ void narrow_i64_kernel(const long long* __restrict__ in, int n, int* __restrict__ out) {
+  pdl_begin();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = (int)in[i];
 }
@@ -160,11 +166,11 @@ int phc_csr_build(const long long* edge_index, int num_edges, int num_nodes, int
   int* slot_src = slot_dst + E;
   cudaMemsetAsync(cnt, 0, sizeof(int) * 2 * (size_t)N, stream);
   cudaMemsetAsync(status, 0, sizeof(int), stream);
-  if (E > 0) hist_kernel<<<phc_div_up(E, 256), 256, 0, stream>>>(edge_index, E, N, cnt, cnt + N, status);
-  scan_kernel<<<2, 1024, 0, stream>>>(cnt, N, rowptr, rowptr_t, cursor);
+  if (E > 0) phc_launch(hist_kernel, dim3(phc_div_up(E, 256)), dim3(256), 0, stream, edge_index, E, N, cnt, cnt + N, status);
+  phc_launch(scan_kernel, dim3(2), dim3(1024), 0, stream, cnt, N, rowptr, rowptr_t, cursor);
   if (E > 0 && N > 0) {
-    ticket_kernel<<<phc_div_up(E, 256), 256, 0, stream>>>(edge_index, E, N, cursor, slot_dst, slot_src);
-    rowsort_kernel<<<phc_div_up(2LL * N * 32, 256), 256, 0, stream>>>(edge_index, E, N, rowptr, rowptr_t, slot_dst, slot_src, perm, col,
+    phc_launch(ticket_kernel, dim3(phc_div_up(E, 256)), dim3(256), 0, stream, edge_index, E, N, cursor, slot_dst, slot_src);
+    phc_launch(rowsort_kernel, dim3(phc_div_up(2LL * N * 32, 256)), dim3(256), 0, stream, edge_index, E, N, rowptr, rowptr_t, slot_dst, slot_src, perm, col,
                                                                     perm_t, col_t);
   }
   return phc_check_launch("phc_csr_build");
@@ -173,12 +179,12 @@ int phc_csr_build(const long long* edge_index, int num_edges, int num_nodes, int
 int phc_segment_ptr_build(const long long* batch, int num_nodes, int num_graphs, int* graph_ptr, int* status, cudaStream_t stream) {
   PHC_REQUIRE(num_nodes >= 0 && num_graphs >= 0, "phc_segment_ptr_build: negative size");
   cudaMemsetAsync(status, 0, sizeof(int), stream);
-  segptr_kernel<<<phc_div_up(num_nodes + 1, 256), 256, 0, stream>>>(batch, num_nodes, num_graphs, graph_ptr, status);
+  phc_launch(segptr_kernel, dim3(phc_div_up(num_nodes + 1, 256)), dim3(256), 0, stream, batch, num_nodes, num_graphs, graph_ptr, status);
   return phc_check_launch("phc_segment_ptr_build");
 }
 
 int phc_narrow_int64(const long long* in, int n, int* out, cudaStream_t stream) {
-  if (n > 0) narrow_i64_kernel<<<phc_div_up(n, 256), 256, 0, stream>>>(in, n, out);
+  if (n > 0) phc_launch(narrow_i64_kernel, dim3(phc_div_up(n, 256)), dim3(256), 0, stream, in, n, out);
   return phc_check_launch("phc_narrow_int64");
 }
 

@@ -126,6 +126,7 @@ __device__ __forceinline__ void slice_reduce(float (&red)[2][BN_SLICES][BN_LANES
 template <int VEC>
 __global__ void __launch_bounds__(BN_THREADS, 4) bn_chunk_stats_kernel(const float* __restrict__ h, int M, int F, int rpc,
                                                                        float* __restrict__ part) {
+  pdl_begin();
   const int lane = threadIdx.x % BN_LANES, slice = threadIdx.x / BN_LANES;
   const int f = (blockIdx.y * BN_LANES + lane) * VEC;
   const int r0 = blockIdx.x * rpc;
@@ -187,6 +188,7 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restric
                                                           float momentum, float* __restrict__ running_mean,
                                                           float* __restrict__ running_var, float* __restrict__ save_mean,
                                                           float* __restrict__ save_rstd, long long* __restrict__ tracked, int n_tracked) {
+  pdl_begin();
   const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (blockIdx.x == 0 && threadIdx.x == 0 && tracked) for (int c = 0; c < n_tracked; ++c) tracked[c] += 1;
@@ -213,6 +215,7 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restric
 __global__ void __launch_bounds__(128) bn_eval_stats_kernel(const float* __restrict__ running_mean, const float* __restrict__ running_var,
                                                             int F, float eps, float* __restrict__ save_mean,
                                                             float* __restrict__ save_rstd) {
+  pdl_begin();
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= F) return;
   save_mean[f] = running_mean[f];
@@ -225,6 +228,7 @@ __global__ void __launch_bounds__(BN_THREADS, 3) bn_apply_fwd_kernel(EwParams p,
                                                                      const float* __restrict__ beta, const float* __restrict__ mean,
                                                                      const float* __restrict__ rstd, const float* __restrict__ skip,
                                                                      float* __restrict__ y) {
+  pdl_begin();
   const int lane = threadIdx.x % BN_LANES, slice = threadIdx.x / BN_LANES;
   const int f = (blockIdx.y * BN_LANES + lane) * VEC;
   if (f >= p.F) return;
@@ -272,6 +276,7 @@ __global__ void __launch_bounds__(BN_THREADS, 3) bn_bwd_reduce_kernel(EwParams p
                                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                       const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                       float* __restrict__ part) {
+  pdl_begin();
   const int lane = threadIdx.x % BN_LANES, slice = threadIdx.x / BN_LANES;
   const int f = (blockIdx.y * BN_LANES + lane) * VEC;
   const int r0 = blockIdx.x * p.rpc, r1 = min(r0 + p.rpc, p.M);
@@ -322,6 +327,7 @@ __global__ void __launch_bounds__(BN_THREADS, 3) bn_bwd_reduce_kernel(EwParams p
 
 __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ part, int chunks, int F, float* __restrict__ dgamma,
                                                               float* __restrict__ dbeta) {
+  pdl_begin();
   const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (f >= F) return;
@@ -346,6 +352,7 @@ __global__ void __launch_bounds__(BN_THREADS, 3) bn_apply_bwd_kernel(EwParams p,
                                                                      const float* __restrict__ beta, const float* __restrict__ mean,
                                                                      const float* __restrict__ rstd, const float* __restrict__ sum_da,
                                                                      const float* __restrict__ sum_da_xhat, float* __restrict__ dh) {
+  pdl_begin();
   const int lane = threadIdx.x % BN_LANES, slice = threadIdx.x / BN_LANES;
   const int f = (blockIdx.y * BN_LANES + lane) * VEC;
   if (f >= p.F) return;
@@ -427,18 +434,18 @@ EwParams make_params(int M, int F, int n, int use_bn, int act, float drop_p, int
     const int a_ = (P).act == PHC_ACT_IDENTITY ? 0 : ((P).act == PHC_ACT_RELU ? 1 : 2);                                  \
     const int key_ = ((V4) ? 6 : 0) + a_ * 2 + ((P).drop_on ? 1 : 0);                                                    \
     switch (key_) {                                                                                                     \
-      case 0: KERNEL<1, PHC_ACT_IDENTITY, false><<<GRID, BN_THREADS, 0, STREAM>>>(__VA_ARGS__); break;                  \
-      case 1: KERNEL<1, PHC_ACT_IDENTITY, true><<<GRID, BN_THREADS, 0, STREAM>>>(__VA_ARGS__); break;                   \
-      case 2: KERNEL<1, PHC_ACT_RELU, false><<<GRID, BN_THREADS, 0, STREAM>>>(__VA_ARGS__); break;                      \
-      case 3: KERNEL<1, PHC_ACT_RELU, true><<<GRID, BN_THREADS, 0, STREAM>>>(__VA_ARGS__); break;                       \
-      case 4: KERNEL<1, -1, false><<<GRID, BN_THREADS, 0, STREAM>>>(__VA_ARGS__); break;                                \
-      case 5: KERNEL<1, -1, true><<<GRID, BN_THREADS, 0, STREAM>>>(__VA_ARGS__); break;                                 \
-      case 6: KERNEL<4, PHC_ACT_IDENTITY, false><<<GRID, BN_THREADS, 0, STREAM>>>(__VA_ARGS__); break;                  \
-      case 7: KERNEL<4, PHC_ACT_IDENTITY, true><<<GRID, BN_THREADS, 0, STREAM>>>(__VA_ARGS__); break;                   \
-      case 8: KERNEL<4, PHC_ACT_RELU, false><<<GRID, BN_THREADS, 0, STREAM>>>(__VA_ARGS__); break;                      \
-      case 9: KERNEL<4, PHC_ACT_RELU, true><<<GRID, BN_THREADS, 0, STREAM>>>(__VA_ARGS__); break;                       \
-      case 10: KERNEL<4, -1, false><<<GRID, BN_THREADS, 0, STREAM>>>(__VA_ARGS__); break;                               \
-      default: KERNEL<4, -1, true><<<GRID, BN_THREADS, 0, STREAM>>>(__VA_ARGS__); break;                                \
+      case 0: phc_launch(KERNEL<1, PHC_ACT_IDENTITY, false>, dim3(GRID), dim3(BN_THREADS), 0, STREAM, __VA_ARGS__); break;                  \
+      case 1: phc_launch(KERNEL<1, PHC_ACT_IDENTITY, true>, dim3(GRID), dim3(BN_THREADS), 0, STREAM, __VA_ARGS__); break;                   \
+      case 2: phc_launch(KERNEL<1, PHC_ACT_RELU, false>, dim3(GRID), dim3(BN_THREADS), 0, STREAM, __VA_ARGS__); break;                      \
+      case 3: phc_launch(KERNEL<1, PHC_ACT_RELU, true>, dim3(GRID), dim3(BN_THREADS), 0, STREAM, __VA_ARGS__); break;                       \
+      case 4: phc_launch(KERNEL<1, -1, false>, dim3(GRID), dim3(BN_THREADS), 0, STREAM, __VA_ARGS__); break;                                \
+      case 5: phc_launch(KERNEL<1, -1, true>, dim3(GRID), dim3(BN_THREADS), 0, STREAM, __VA_ARGS__); break;                                 \
+      case 6: phc_launch(KERNEL<4, PHC_ACT_IDENTITY, false>, dim3(GRID), dim3(BN_THREADS), 0, STREAM, __VA_ARGS__); break;                  \
+      case 7: phc_launch(KERNEL<4, PHC_ACT_IDENTITY, true>, dim3(GRID), dim3(BN_THREADS), 0, STREAM, __VA_ARGS__); break;                   \
+      case 8: phc_launch(KERNEL<4, PHC_ACT_RELU, false>, dim3(GRID), dim3(BN_THREADS), 0, STREAM, __VA_ARGS__); break;                      \
+      case 9: phc_launch(KERNEL<4, PHC_ACT_RELU, true>, dim3(GRID), dim3(BN_THREADS), 0, STREAM, __VA_ARGS__); break;                       \
+      case 10: phc_launch(KERNEL<4, -1, false>, dim3(GRID), dim3(BN_THREADS), 0, STREAM, __VA_ARGS__); break;                               \
+      default: phc_launch(KERNEL<4, -1, true>, dim3(GRID), dim3(BN_THREADS), 0, STREAM, __VA_ARGS__); break;                                \
     }                                                                                                                   \
   } while (0)
 
@@ -470,14 +477,14 @@ int phc_bn_act_drop_skip_fwd(const float* h, const float* gamma, const float* be
       const int rpc = bn_rows_per_chunk(M, colgroups, 4);
       const int chunks = phc_div_up(M, rpc);
       dim3 grid(chunks, colgroups);
-      if (v4s) bn_chunk_stats_kernel<4><<<grid, BN_THREADS, 0, stream>>>(h, M, F, rpc, part);
-      else bn_chunk_stats_kernel<1><<<grid, BN_THREADS, 0, stream>>>(h, M, F, rpc, part);
-      bn_finalize_kernel<<<phc_div_up((long long)F * 32, 256), 256, 0, stream>>>(part, chunks, rpc, M, F, eps, momentum, running_mean,
+      if (v4s) phc_launch(bn_chunk_stats_kernel<4>, dim3(grid), dim3(BN_THREADS), 0, stream, h, M, F, rpc, part);
+      else phc_launch(bn_chunk_stats_kernel<1>, dim3(grid), dim3(BN_THREADS), 0, stream, h, M, F, rpc, part);
+      phc_launch(bn_finalize_kernel, dim3(phc_div_up((long long)F * 32, 256)), dim3(256), 0, stream, part, chunks, rpc, M, F, eps, momentum, running_mean,
                                                                                 running_var, save_mean, save_rstd, num_batches_tracked,
                                                                                 n_tracked);
     } else {
       PHC_REQUIRE(running_mean && running_var, "phc_bn_act_drop_skip_fwd: eval mode needs running statistics");
-      bn_eval_stats_kernel<<<phc_div_up(F, 128), 128, 0, stream>>>(running_mean, running_var, F, eps, save_mean, save_rstd);
+      phc_launch(bn_eval_stats_kernel, dim3(phc_div_up(F, 128)), dim3(128), 0, stream, running_mean, running_var, F, eps, save_mean, save_rstd);
     }
   }
   EwParams p = make_params(M, F, phm_dim, use_bn, act, drop_p, drop_same, training, seed);
@@ -509,7 +516,7 @@ int phc_bn_act_drop_skip_bwd(const float* dy, const float* h, const float* gamma
     const int chunks = phc_div_up(M, p.rpc);
     dim3 grid(chunks, colgroups);
     BN_DISPATCH(bn_bwd_reduce_kernel, v4, p, grid, stream, p, dy, h, gamma, beta, save_mean, save_rstd, part);
-    bn_bwd_finalize_kernel<<<phc_div_up((long long)F * 32, 256), 256, 0, stream>>>(part, chunks, F, dgamma, dbeta);
+    phc_launch(bn_bwd_finalize_kernel, dim3(phc_div_up((long long)F * 32, 256)), dim3(256), 0, stream, part, chunks, F, dgamma, dbeta);
   }
   p.rpc = bn_rows_per_chunk(M, colgroups, 3);
   dim3 grid(phc_div_up(M, p.rpc), colgroups);

@@ -10,6 +10,7 @@ namespace {
 constexpr int OPT_BLOCKS = 296;
 
 __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restrict__ g, long long n, float* __restrict__ part) {
+  pdl_begin();
   float s = 0.f;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) { const float v = g[i]; s += v * v; }
   __shared__ float red[256];
@@ -26,6 +27,7 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(float* __restrict__ p, c
                                                         float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
                                                         float bc1, float bc2, float max_norm, const float* __restrict__ part, int nparts,
                                                         float* __restrict__ norm_out) {
+  pdl_begin();
   __shared__ float coef_s;
   if (threadIdx.x == 0) {
     float coef = 1.f;
@@ -64,8 +66,8 @@ int phc_adam_clip_step(float* params, const float* grads, float* exp_avg, float*
   PHC_REQUIRE(workspace_bytes >= phc_adam_workspace_bytes(), "phc_adam_clip_step: workspace too small");
   if (numel == 0) return PHC_OK;
   float* part = reinterpret_cast<float*>(workspace);
-  if (max_norm > 0.f) sumsq_partial_kernel<<<OPT_BLOCKS, 256, 0, stream>>>(grads, numel, part);
-  adam_clip_kernel<<<OPT_BLOCKS, 256, 0, stream>>>(params, grads, exp_avg, exp_avg_sq, numel, lr, beta1, beta2, eps, bias_correction1,
+  if (max_norm > 0.f) phc_launch(sumsq_partial_kernel, dim3(OPT_BLOCKS), dim3(256), 0, stream, grads, numel, part);
+  phc_launch(adam_clip_kernel, dim3(OPT_BLOCKS), dim3(256), 0, stream, params, grads, exp_avg, exp_avg_sq, numel, lr, beta1, beta2, eps, bias_correction1,
                                                    bias_correction2, max_norm, part, OPT_BLOCKS, grad_norm_out);
   return phc_check_launch("phc_adam_clip_step");
 }

@@ -37,6 +37,7 @@ template <bool TRANS>
 __global__ void __launch_bounds__(256) phm_gemm_kernel(const float* __restrict__ X, const float* __restrict__ A, const float* __restrict__ W,
                                                        const float* __restrict__ bias, const float* __restrict__ residual,
                                                        float* __restrict__ Y, int M, int Kred, int Nout, int n, int K, int P, int act) {
+  pdl_begin();
   __shared__ float Xs[TK][TM + 4];
   __shared__ float Hs[TK][TN + 4];
   extern __shared__ float As[];  // n^3 rule scalars
@@ -103,6 +104,7 @@ __global__ void __launch_bounds__(256) phm_gemm_kernel(const float* __restrict__
 // dH partials: part[z][i][o] = sum_{m in split z} x[m,i] * dy[m,o].  64x64 tile, 256 threads x (4x4).
 __global__ void __launch_bounds__(256) phm_dh_kernel(const float* __restrict__ X, const float* __restrict__ G, int M, int In, int Out,
                                                      int rows_per_split, float* __restrict__ part) {
+  pdl_begin();
   __shared__ float Xs[16][64 + 4];
   __shared__ float Gs[16][64 + 4];
   const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16;
@@ -155,6 +157,7 @@ __global__ void __launch_bounds__(256) phm_dh_kernel(const float* __restrict__ X
 __global__ void __launch_bounds__(256) phm_contract_kernel(const float* __restrict__ part, int splits, const float* __restrict__ A,
                                                            const float* __restrict__ W, int n, int K, int P, float* __restrict__ dW,
                                                            float* __restrict__ dA_part) {
+  pdl_begin();
   extern __shared__ float sm[];
   float* As = sm;                 // n^3
   float* wred = sm + n * n * n;   // 8 warps
@@ -207,6 +210,7 @@ __global__ void __launch_bounds__(256) phm_contract_kernel(const float* __restri
 __global__ void __launch_bounds__(256) phm_bwd_final_kernel(const float* __restrict__ dA_part, int blocks, int n3, float* __restrict__ dA,
                                                             const float* __restrict__ db_part, int db_parts, int Out,
                                                             float* __restrict__ db) {
+  pdl_begin();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   if (t < n3 * 32) {
@@ -232,6 +236,7 @@ __global__ void __launch_bounds__(256) phm_bwd_final_kernel(const float* __restr
 // block = 32 feature lanes (x4 floats) x 8 row slices; slices reduced in fixed order through shared memory.
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ G, int M, int F, int rows_per_chunk,
                                                              float* __restrict__ part) {
+  pdl_begin();
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
   const int r0 = blockIdx.y * rows_per_chunk, r1 = min(r0 + rows_per_chunk, M);
   __shared__ float red[8][128];
@@ -266,6 +271,7 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __rest
 }
 // one warp per column: lane l sums chunks l, l+32, ... in order, then a fixed butterfly
 __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ part, int chunks, int F, float* __restrict__ out) {
+  pdl_begin();
   const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (f >= F) return;
@@ -285,6 +291,7 @@ template <int N>
 __global__ void __launch_bounds__(CJ * N) phm_contract_small_kernel(const float* __restrict__ part, int splits, const float* __restrict__ A,
                                                                     const float* __restrict__ W, int K, int P, float* __restrict__ dW,
                                                                     float* __restrict__ dA_part) {
+  pdl_begin();
   constexpr int N2 = N * N, N3 = N * N * N;
   __shared__ float As[N3];
   __shared__ float dws[N][CJ][N];
@@ -380,24 +387,23 @@ int phm_contract_and_bias(const float* part, int splits, const float* gy, const 
   float* da_part = scratch;
   float* cs_part = phm_contract_bias_partials(scratch, in_features, out_features, n);
   switch (n) {
-    case 1: phm_contract_small_kernel<1><<<cblocks, CJ * 1, 0, stream>>>(part, splits, A, W, K, P, dW, da_part); break;
-    case 2: phm_contract_small_kernel<2><<<cblocks, CJ * 2, 0, stream>>>(part, splits, A, W, K, P, dW, da_part); break;
-    case 3: phm_contract_small_kernel<3><<<cblocks, CJ * 3, 0, stream>>>(part, splits, A, W, K, P, dW, da_part); break;
-    case 4: phm_contract_small_kernel<4><<<cblocks, CJ * 4, 0, stream>>>(part, splits, A, W, K, P, dW, da_part); break;
-    default: phm_contract_kernel<<<cblocks, 256, sizeof(float) * (n3 + 8), stream>>>(part, splits, A, W, n, K, P, dW, da_part);
+    case 1: phc_launch(phm_contract_small_kernel<1>, dim3(cblocks), dim3(CJ * 1), 0, stream, part, splits, A, W, K, P, dW, da_part); break;
+    case 2: phc_launch(phm_contract_small_kernel<2>, dim3(cblocks), dim3(CJ * 2), 0, stream, part, splits, A, W, K, P, dW, da_part); break;
+    case 3: phc_launch(phm_contract_small_kernel<3>, dim3(cblocks), dim3(CJ * 3), 0, stream, part, splits, A, W, K, P, dW, da_part); break;
+    case 4: phc_launch(phm_contract_small_kernel<4>, dim3(cblocks), dim3(CJ * 4), 0, stream, part, splits, A, W, K, P, dW, da_part); break;
+    default: phc_launch(phm_contract_kernel, dim3(cblocks), dim3(256), sizeof(float) * (n3 + 8), stream, part, splits, A, W, n, K, P, dW, da_part);
   }
   const bool fused_bias = db != nullptr && db_parts > 0;
   if (db && !fused_bias) {
     const int chunks = colsum_chunks(M);
     const int rpc = phc_div_up(M > 0 ? M : 1, chunks);
     dim3 g3(phc_div_up(out_features, 128), chunks);
-    colsum_partial_kernel<<<g3, 256, 0, stream>>>(gy, M, out_features, rpc, cs_part);
-    colsum_final_kernel<<<phc_div_up((long long)out_features * 32, 256), 256, 0, stream>>>(cs_part, chunks, out_features, db);
+    phc_launch(colsum_partial_kernel, dim3(g3), dim3(256), 0, stream, gy, M, out_features, rpc, cs_part);
+    phc_launch(colsum_final_kernel, dim3(phc_div_up((long long)out_features * 32, 256)), dim3(256), 0, stream, cs_part, chunks, out_features, db);
   }
   if (dA || fused_bias) {
     const int na = dA ? n3 : 0;
-    phm_bwd_final_kernel<<<phc_div_up((long long)na * 32 + (fused_bias ? out_features : 0), 256), 256, 0, stream>>>(
-        da_part, cblocks, na, dA, fused_bias ? cs_part : nullptr, db_parts, out_features, db);
+    phc_launch(phm_bwd_final_kernel, dim3(phc_div_up((long long)na * 32 + (fused_bias ? out_features : 0), 256)), dim3(256), 0, stream, da_part, cblocks, na, dA, fused_bias ? cs_part : nullptr, db_parts, out_features, db);
   }
   return phc_check_launch("phm_contract_and_bias");
 }
@@ -411,7 +417,7 @@ int phm_simt_fwd(const float* x, const float* A, const float* W, const float* bi
                  int in_features, int out_features, int phm_dim, int act, cudaStream_t stream) {
   const int n = phm_dim, K = in_features / n, P = out_features / n;
   dim3 grid(phc_div_up(out_features, TN), phc_div_up(rows, TM));
-  phm_gemm_kernel<false><<<grid, 256, sizeof(float) * n * n * n, stream>>>(x, A, W, bias, residual, y, rows, in_features, out_features, n, K,
+  phc_launch(phm_gemm_kernel<false>, dim3(grid), dim3(256), sizeof(float) * n * n * n, stream, x, A, W, bias, residual, y, rows, in_features, out_features, n, K,
                                                                            P, act);
   return phc_check_launch("phc_phm_linear_fwd(simt)");
 }
@@ -422,14 +428,14 @@ int phm_simt_bwd(const float* gy, const float* x, const float* A, const float* W
   const int n3 = n * n * n;
   if (dx) {
     dim3 grid(phc_div_up(in_features, TN), phc_div_up(M, TM));
-    phm_gemm_kernel<true><<<grid, 256, sizeof(float) * n3, stream>>>(gy, A, W, nullptr, nullptr, dx, M, out_features, in_features, n, K, P,
+    phc_launch(phm_gemm_kernel<true>, dim3(grid), dim3(256), sizeof(float) * n3, stream, gy, A, W, nullptr, nullptr, dx, M, out_features, in_features, n, K, P,
                                                                       PHC_ACT_IDENTITY);
   }
   const int splits = dh_splits(M, in_features, out_features);
   const int rps = phc_div_up(phc_div_up(M > 0 ? M : 1, splits), 16) * 16;
   float* part = reinterpret_cast<float*>(workspace);
   dim3 g2(phc_div_up(out_features, 64), phc_div_up(in_features, 64), splits);
-  phm_dh_kernel<<<g2, 256, 0, stream>>>(x, gy, M, in_features, out_features, rps, part);
+  phc_launch(phm_dh_kernel, dim3(g2), dim3(256), 0, stream, x, gy, M, in_features, out_features, rps, part);
   return phm_contract_and_bias(part, splits, gy, A, W, dA, dW, db, M, in_features, out_features, n,
                                part + (size_t)splits * in_features * out_features, 0, stream);
 }

@@ -438,6 +438,7 @@ __device__ __forceinline__ void mix_produce(const MixParams& p, const float* __r
 
 template <int NT>
 __global__ void __launch_bounds__(THREADS, 1) phm_tc_mix_kernel(const MixParams p) {
+  pdl_begin();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int n3 = p.n * p.n * p.n;
   const Smem s = carve(smem_raw, n3);
@@ -593,6 +594,7 @@ __device__ __forceinline__ void mix_produce_raw(const float* __restrict__ raw, c
 
 template <int NT>
 __global__ void __launch_bounds__(TMA_THREADS, 1) phm_tc_mix_tma_kernel(const MixParams p, const __grid_constant__ CUtensorMap tmapX) {
+  pdl_begin();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   Smem s;
@@ -808,6 +810,7 @@ __device__ __forceinline__ void v3_drain(float* __restrict__ my, uint32_t taddr,
 // R = Kin & 3: component uu's box starts (uu*R)&3 floats before its first needed float (TMA boxes start 16-byte aligned)
 template <int R, bool SINGLE>
 __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixParams p, const __grid_constant__ CUtensorMap tmapX) {
+  pdl_begin();
   constexpr int NT = 4, KQ = BK / NT;                       // 8 k values per chunk
   constexpr int PITCH = R == 0 ? KQ : KQ + 4;               // floats per raw row (must match the tensor map's box)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -1110,6 +1113,7 @@ __device__ __forceinline__ void dh_tile(const DhParams& p, int t, int& i0, int& 
 }
 
 __global__ void __launch_bounds__(THREADS, 1) phm_tc_dh_kernel(const DhParams p) {
+  pdl_begin();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const Smem s = carve(smem_raw, 0);
   const uint32_t tmem_base = cta_prologue(s, PROD_WARPS);
@@ -1170,6 +1174,7 @@ constexpr int DH_TMA_THREADS = (MMA_WARP + 2) * 32;
 
 __global__ void __launch_bounds__(DH_TMA_THREADS, 1) phm_tc_dh_tma_kernel(const DhParams p, const __grid_constant__ CUtensorMap tmapX,
                                                                          const __grid_constant__ CUtensorMap tmapG) {
+  pdl_begin();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   Smem s;
@@ -1286,6 +1291,7 @@ __global__ void __launch_bounds__(256) phm_pack_kernel(const float* __restrict__
                                                        uint8_t* __restrict__ pack_fwd, float* __restrict__ coef_fwd,
                                                        uint8_t* __restrict__ pack_dx, float* __restrict__ coef_dx, int units_fwd,
                                                        int units_dx, int single) {
+  pdl_begin();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int n3 = n * n * n;
   if (t < n3) {
@@ -1387,7 +1393,7 @@ int launch_mix_nt(const MixParams& p, cudaStream_t stream) {
   int rc = set_smem(phm_tc_mix_kernel<NT>, &configured);
   if (rc) return rc;
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  phm_tc_mix_kernel<NT><<<grid, THREADS, smem_bytes(p.n * p.n * p.n), stream>>>(p);
+  phc_launch(phm_tc_mix_kernel<NT>, dim3(grid), dim3(THREADS), smem_bytes(p.n * p.n * p.n), stream, p);
   return phc_check_launch("phm_tc_mix_kernel");
 }
 
@@ -1435,7 +1441,7 @@ int launch_mix_tma_nt(const MixParams& p, const CUtensorMap& tmap, cudaStream_t 
     configured = true;
   }
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  phm_tc_mix_tma_kernel<NT><<<grid, TMA_THREADS, smem_bytes_tma(NT), stream>>>(p, tmap);
+  phc_launch(phm_tc_mix_tma_kernel<NT>, dim3(grid), dim3(TMA_THREADS), smem_bytes_tma(NT), stream, p, tmap);
   return phc_check_launch("phm_tc_mix_tma_kernel");
 }
 
@@ -1479,7 +1485,7 @@ int launch_mix_v3_rs(const MixParams& p, const CUtensorMap& tmap, cudaStream_t s
   MixParams q = p;
   q.num_tiles = phc_div_up(p.M, BM) * 2 * p.ptiles;           // units: (m-tile, p-tile, component pair)
   const int grid = q.num_tiles < num_sms() ? q.num_tiles : num_sms();
-  phm_tc_mix_v3_kernel<R, SINGLE><<<grid, V3_THREADS, smem_bytes_v3(), stream>>>(q, tmap);
+  phc_launch(phm_tc_mix_v3_kernel<R, SINGLE>, dim3(grid), dim3(V3_THREADS), smem_bytes_v3(), stream, q, tmap);
   return phc_check_launch("phm_tc_mix_v3_kernel");
 }
 
@@ -1518,7 +1524,7 @@ int launch_pack(const float* A, const float* W, int n, int K, int P, uint8_t* bu
   const int units_fwd = L.pt_fwd * L.chunks_fwd * BN * 8, units_dx = L.pt_dx * L.chunks_dx * BN * 8;
   int threads = units_fwd > units_dx ? units_fwd : units_dx;
   if (threads < n * n * n) threads = n * n * n;
-  phm_pack_kernel<<<phc_div_up(threads, 256), 256, 0, stream>>>(A, W, n, K, P, buf + L.pack_fwd, reinterpret_cast<float*>(buf + L.coef_fwd),
+  phc_launch(phm_pack_kernel, dim3(phc_div_up(threads, 256)), dim3(256), 0, stream, A, W, n, K, P, buf + L.pack_fwd, reinterpret_cast<float*>(buf + L.coef_fwd),
                                                                 buf + L.pack_dx, reinterpret_cast<float*>(buf + L.coef_dx), units_fwd,
                                                                 units_dx, single);
   return phc_check_launch("phm_pack_kernel");
@@ -1554,7 +1560,7 @@ int try_launch_dh_tma(const DhParams& d, cudaStream_t stream) {
     configured = true;
   }
   const int grid = d.num_tiles < num_sms() ? d.num_tiles : num_sms();
-  phm_tc_dh_tma_kernel<<<grid, DH_TMA_THREADS, smem_bytes_dh_tma(), stream>>>(d, tx, tg);
+  phc_launch(phm_tc_dh_tma_kernel, dim3(grid), dim3(DH_TMA_THREADS), smem_bytes_dh_tma(), stream, d, tx, tg);
   return phc_check_launch("phm_tc_dh_tma_kernel");
 }
 
@@ -1649,7 +1655,7 @@ int phm_tc_bwd(const float* gy, const float* x, const float* A, const float* W, 
     rc = tc::set_smem(tc::phm_tc_dh_kernel, &configured);
     if (rc) return rc;
     const int grid = d.num_tiles < tc::num_sms() ? d.num_tiles : tc::num_sms();
-    tc::phm_tc_dh_kernel<<<grid, tc::THREADS, tc::smem_bytes(0), stream>>>(d);
+    phc_launch(tc::phm_tc_dh_kernel, dim3(grid), dim3(tc::THREADS), tc::smem_bytes(0), stream, d);
     rc = phc_check_launch("phm_tc_dh_kernel");
   }
   if (rc) return rc;

@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(256) pna_fwd_kernel(const float* __restrict__ 
                                                       const int* __restrict__ rowptr, const int* __restrict__ col,
                                                       const int* __restrict__ perm, int N, int F, int Fc, int act, PnaCfg cfg,
                                                       float* __restrict__ out, float* __restrict__ aux_f, int* __restrict__ aux_i) {
+  pdl_begin();
   const int fv = F / VEC;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)N * fv) return;
@@ -167,6 +168,7 @@ __global__ void __launch_bounds__(256) pna_bwd_edge_kernel(const float* __restri
                                                            const int* __restrict__ aux_i, const int* __restrict__ rowptr,
                                                            const int* __restrict__ col, const int* __restrict__ perm, int N, int F, int Fc,
                                                            int act, PnaCfg cfg, float* __restrict__ dea) {
+  pdl_begin();
   const int fv = F / VEC;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)N * fv) return;
@@ -278,9 +280,9 @@ int phc_pna_aggregate_fwd(const float* x, const float* ea, const int* rowptr, co
   const int N = num_nodes, F = width, Fc = width / phm_dim;
   const bool v4 = F % 4 == 0 && phc_aligned16(x) && phc_aligned16(ea) && phc_aligned16(out) && phc_aligned16(aux_f) && phc_aligned16(aux_i);
   if (v4)
-    pna_fwd_kernel<4><<<phc_div_up((long long)N * (F / 4), 256), 256, 0, stream>>>(x, ea, rowptr, col, perm, N, F, Fc, msg_act, cfg, out, aux_f, aux_i);
+    phc_launch(pna_fwd_kernel<4>, dim3(phc_div_up((long long)N * (F / 4), 256)), dim3(256), 0, stream, x, ea, rowptr, col, perm, N, F, Fc, msg_act, cfg, out, aux_f, aux_i);
   else
-    pna_fwd_kernel<1><<<phc_div_up((long long)N * F, 256), 256, 0, stream>>>(x, ea, rowptr, col, perm, N, F, Fc, msg_act, cfg, out, aux_f, aux_i);
+    phc_launch(pna_fwd_kernel<1>, dim3(phc_div_up((long long)N * F, 256)), dim3(256), 0, stream, x, ea, rowptr, col, perm, N, F, Fc, msg_act, cfg, out, aux_f, aux_i);
   return phc_check_launch("phc_pna_aggregate_fwd");
 }
 
@@ -302,9 +304,9 @@ int phc_pna_aggregate_bwd(const float* gout, const float* x, const float* ea, co
   const int N = num_nodes, F = width, Fc = width / phm_dim;
   const bool v4 = F % 4 == 0 && phc_aligned16(x) && phc_aligned16(ea) && phc_aligned16(dea) && phc_aligned16(aux_f) && phc_aligned16(aux_i);
   if (v4)
-    pna_bwd_edge_kernel<4><<<phc_div_up((long long)N * (F / 4), 256), 256, 0, stream>>>(gout, x, ea, aux_f, aux_i, rowptr, col, perm, N, F, Fc, msg_act, cfg, dea);
+    phc_launch(pna_bwd_edge_kernel<4>, dim3(phc_div_up((long long)N * (F / 4), 256)), dim3(256), 0, stream, gout, x, ea, aux_f, aux_i, rowptr, col, perm, N, F, Fc, msg_act, cfg, dea);
   else
-    pna_bwd_edge_kernel<1><<<phc_div_up((long long)N * F, 256), 256, 0, stream>>>(gout, x, ea, aux_f, aux_i, rowptr, col, perm, N, F, Fc, msg_act, cfg, dea);
+    phc_launch(pna_bwd_edge_kernel<1>, dim3(phc_div_up((long long)N * F, 256)), dim3(256), 0, stream, gout, x, ea, aux_f, aux_i, rowptr, col, perm, N, F, Fc, msg_act, cfg, dea);
   int rc = phc_check_launch("phc_pna_aggregate_bwd(edge)");
   if (rc) return rc;
   return phc_aggregate_bwd_node_from_edges(dea, rowptr_t, col_t, perm_t, N, F, dx, stream);

@@ -19,6 +19,7 @@ template <int VEC, bool GATED>
 __global__ void __launch_bounds__(POOL_SLICES * POOL_LANES) pool_fwd_kernel(const float* __restrict__ x, const float* __restrict__ z,
                                                                            const int* __restrict__ gptr, int F, int Fc,
                                                                            float* __restrict__ out) {
+  pdl_begin();
   const int b = blockIdx.x;
   const int lane = threadIdx.x % POOL_LANES;
   const int slice = threadIdx.x / POOL_LANES;
@@ -63,6 +64,7 @@ __global__ void __launch_bounds__(POOL_SLICES * POOL_LANES) pool_fwd_kernel(cons
 __global__ void __launch_bounds__(256) pool_bwd_gated_kernel(const float* __restrict__ g, const float* __restrict__ x,
                                                              const float* __restrict__ z, const long long* __restrict__ batch, int N,
                                                              int F, int Fc, float* __restrict__ dx, float* __restrict__ dz) {
+  pdl_begin();
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)N * Fc) return;
   const int i = (int)(t / Fc), fp = (int)(t % Fc);
@@ -81,6 +83,7 @@ __global__ void __launch_bounds__(256) pool_bwd_gated_kernel(const float* __rest
 template <int VEC>
 __global__ void __launch_bounds__(256) pool_bwd_plain_kernel(const float* __restrict__ g, const long long* __restrict__ batch, int N, int F,
                                                              float* __restrict__ dx) {
+  pdl_begin();
   const int fv = F / VEC;
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)N * fv) return;
@@ -102,11 +105,11 @@ int phc_segment_pool_fwd(const float* x, const float* gate_logits, const int* gr
   dim3 grid(num_graphs, phc_div_up(width, POOL_LANES * (v4 ? 4 : 1)));
   const int threads = POOL_SLICES * POOL_LANES;
   if (gate_logits) {
-    if (v4) pool_fwd_kernel<4, true><<<grid, threads, 0, stream>>>(x, gate_logits, graph_ptr, width, Fc, out);
-    else pool_fwd_kernel<1, true><<<grid, threads, 0, stream>>>(x, gate_logits, graph_ptr, width, Fc, out);
+    if (v4) phc_launch(pool_fwd_kernel<4, true>, dim3(grid), dim3(threads), 0, stream, x, gate_logits, graph_ptr, width, Fc, out);
+    else phc_launch(pool_fwd_kernel<1, true>, dim3(grid), dim3(threads), 0, stream, x, gate_logits, graph_ptr, width, Fc, out);
   } else {
-    if (v4) pool_fwd_kernel<4, false><<<grid, threads, 0, stream>>>(x, gate_logits, graph_ptr, width, Fc, out);
-    else pool_fwd_kernel<1, false><<<grid, threads, 0, stream>>>(x, gate_logits, graph_ptr, width, Fc, out);
+    if (v4) phc_launch(pool_fwd_kernel<4, false>, dim3(grid), dim3(threads), 0, stream, x, gate_logits, graph_ptr, width, Fc, out);
+    else phc_launch(pool_fwd_kernel<1, false>, dim3(grid), dim3(threads), 0, stream, x, gate_logits, graph_ptr, width, Fc, out);
   }
   return phc_check_launch("phc_segment_pool_fwd");
 }
@@ -117,12 +120,12 @@ int phc_segment_pool_bwd(const float* gout, const float* x, const float* gate_lo
   if (num_nodes == 0) return PHC_OK;
   const int Fc = width / phm_dim;
   if (gate_logits) {
-    pool_bwd_gated_kernel<<<phc_div_up((long long)num_nodes * Fc, 256), 256, 0, stream>>>(gout, x, gate_logits, batch, num_nodes, width, Fc,
+    phc_launch(pool_bwd_gated_kernel, dim3(phc_div_up((long long)num_nodes * Fc, 256)), dim3(256), 0, stream, gout, x, gate_logits, batch, num_nodes, width, Fc,
                                                                                          dx, dgate_logits);
   } else {
     const bool v4 = width % 4 == 0 && phc_aligned16(gout) && phc_aligned16(dx);
-    if (v4) pool_bwd_plain_kernel<4><<<phc_div_up((long long)num_nodes * (width / 4), 256), 256, 0, stream>>>(gout, batch, num_nodes, width, dx);
-    else pool_bwd_plain_kernel<1><<<phc_div_up((long long)num_nodes * width, 256), 256, 0, stream>>>(gout, batch, num_nodes, width, dx);
+    if (v4) phc_launch(pool_bwd_plain_kernel<4>, dim3(phc_div_up((long long)num_nodes * (width / 4), 256)), dim3(256), 0, stream, gout, batch, num_nodes, width, dx);
+    else phc_launch(pool_bwd_plain_kernel<1>, dim3(phc_div_up((long long)num_nodes * width, 256)), dim3(256), 0, stream, gout, batch, num_nodes, width, dx);
   }
   return phc_check_launch("phc_segment_pool_bwd");
 }

@@ -16,6 +16,7 @@ struct RegTable {
 namespace {
 
 __global__ void __launch_bounds__(256) reg_fwd_kernel(RegTable t, float* __restrict__ part) {
+  pdl_begin();
   const int l = blockIdx.y;
   const int n = t.n[l], kp = t.kp[l];
   const float* w = t.w[l];
@@ -36,6 +37,7 @@ __global__ void __launch_bounds__(256) reg_fwd_kernel(RegTable t, float* __restr
 }
 
 __global__ void reg_final_kernel(const float* __restrict__ part, int count, float* __restrict__ out) {
+  pdl_begin();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     float s = 0.f;
     for (int i = 0; i < count * PHC_REG_BLOCKS; ++i) s += part[i];
@@ -45,6 +47,7 @@ __global__ void reg_final_kernel(const float* __restrict__ part, int count, floa
 
 // dW[b,i] = g * W[b,i] / (||W[:,i]|| * kp)
 __global__ void __launch_bounds__(256) reg_bwd_kernel(RegTable t, const float* __restrict__ gout) {
+  pdl_begin();
   const int l = blockIdx.y;
   const int n = t.n[l], kp = t.kp[l];
   const float* w = t.w[l];
@@ -82,8 +85,8 @@ int phc_weight_reg_fwd(const float* const* weights, const int* phm_dims, const i
   RegTable t;
   fill(t, weights, nullptr, phm_dims, kp, count);
   float* part = reinterpret_cast<float*>(workspace);
-  reg_fwd_kernel<<<dim3(PHC_REG_BLOCKS, count), 256, 0, stream>>>(t, part);
-  reg_final_kernel<<<1, 32, 0, stream>>>(part, count, out);
+  phc_launch(reg_fwd_kernel, dim3(dim3(PHC_REG_BLOCKS, count)), dim3(256), 0, stream, t, part);
+  phc_launch(reg_final_kernel, dim3(1), dim3(32), 0, stream, part, count, out);
   return phc_check_launch("phc_weight_reg_fwd");
 }
 
@@ -93,7 +96,7 @@ int phc_weight_reg_bwd(const float* gout, const float* const* weights, float* co
   if (count == 0) return PHC_OK;
   RegTable t;
   fill(t, weights, dweights, phm_dims, kp, count);
-  reg_bwd_kernel<<<dim3(PHC_REG_BLOCKS, count), 256, 0, stream>>>(t, gout);
+  phc_launch(reg_bwd_kernel, dim3(dim3(PHC_REG_BLOCKS, count)), dim3(256), 0, stream, t, gout);
   return phc_check_launch("phc_weight_reg_bwd");
 }
 

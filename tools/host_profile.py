@@ -7,13 +7,13 @@ import torch
 from phc_gnn_b200 import graph
 from phc_gnn_b200.nn import PHMSkipConnectAdd
 from phc_gnn_b200.synthetic import make_batch, workloads
-from phc_gnn_b200.train import TrainStep, make_optimizer
+from phc_gnn_b200.train import TrainStep
 name = sys.argv[1] if len(sys.argv) > 1 else "zinc"
 wl = workloads(4)[name]
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 model = PHMSkipConnectAdd(**wl.model).to(dev)
-step = TrainStep(model, wl, make_optimizer(model, wl.lr))
+step = TrainStep(model, wl)        # flat clip+Adam, as bench.py runs it
 model.train()
 batches = [make_batch(wl, seed=i).to(dev) for i in range(4)]
 for i in range(5):
