@@ -208,6 +208,7 @@ class _ConvLayer(torch.autograd.Function):
 
 
 SINGLE_CALL = True      # False: one C-ABI call per operator (the cross-check path of the tests)
+DIRECT_PARAM_GRADS = True   # parameter gradients written in place by the layer's backward instead of flowing through autograd
 _SCRATCH = {}
 
 
@@ -236,143 +237,239 @@ def _node_sums(struct, attr, linear, enc_dim, vocab, vc, reduce, msg_act, rows, 
     return sums
 
 
+def _unpack(cfg, tensors):
+    """tensors = [beta?] + encoder params + [rule1, W1, b1] + bn1 params + [rule2, W2, b2]? + bn2 params (see conv_layer)."""
+    n_enc, has_beta, nb1, mlp = cfg[17], cfg[18], cfg[19], cfg[7]
+    i = 1 if has_beta else 0
+    beta = tensors[0] if has_beta else None
+    enc = tensors[i:i + n_enc]; i += n_enc
+    lin1 = tensors[i:i + 3]; i += 3
+    bn1 = tensors[i:i + nb1]; i += nb1
+    lin2 = (None, None, None)
+    if mlp:
+        lin2 = tensors[i:i + 3]; i += 3
+    bn2 = tensors[i:]
+    return beta, enc, lin1, bn1, lin2, bn2
+
+
+def _call_fwd(cfg, struct: EdgeStructure, flats, x, skip, attr, tensors):
+    """Whole layer forward through phc_conv_layer_fwd.  -> (out, saved tensors, host-side state for backward)."""
+    (n, linear, enc_dim, vocab, reduce, msg_act, self_loops, mlp, act1, act2, use_bn1, use_bn2, training, drop_p, same, seed,
+     precision, n_enc, has_beta, nb1, nb2, mom1, eps1, mom2, eps2) = cfg
+    flat1, flat2 = flats
+    dev = x.device
+    st = _stream(dev)
+    beta, enc, (r1, W1, b1), _, (r2, W2, b2), _ = _unpack(cfg, tensors)
+    N, F = x.shape
+    f32 = dict(dtype=torch.float32, device=dev)
+    acts = torch.empty((4 if mlp else 2, N, F), **f32)          # agg, [y1, a1,] z: saved for backward
+    out = torch.empty((N, F), **f32)                            # own storage: callers may modify it in place
+    stats = torch.empty((4, F), **f32)
+    aux_f = torch.empty((2, N, F), **f32) if reduce == 4 else None
+    aux_i = torch.empty((N, F), dtype=torch.int32, device=dev) if reduce in (2, 3) else None
+    nb_lin = _ws_bytes("phc_phm_linear_fwd_workspace_bytes", N, F, F, n, precision)
+    nb_lin = (nb_lin + 1023) & ~1023
+    ws_lin = _ws(nb_lin * (2 if mlp else 1), dev)               # PHMLinear operand packs, kept for backward
+    rows = enc_dim + 1 if linear else int(sum(vocab))
+    ws = _scratch(_ws_bytes("phc_conv_layer_workspace_bytes", N, F, n, rows, precision), dev, st)
+    vc = (ctypes.c_int * max(len(vocab), 1))(*vocab) if vocab else None
+    encp = _ptr_array(enc)
+    D = _lib.conv_layer_struct()()
+    D.num_nodes, D.width, D.phm_dim = N, F, n
+    D.enc_kind, D.enc_dim, D.table_rows = 0 if linear else 1, enc_dim, rows
+    D.reduce, D.msg_act, D.self_loops, D.mlp = reduce, msg_act, int(self_loops), int(mlp)
+    D.act1, D.act2, D.use_bn1, D.use_bn2 = act1, act2, int(use_bn1 and mlp), int(use_bn2)
+    D.training, D.drop_same, D.precision = int(training), int(same), precision
+    D.drop_p, D.momentum1, D.eps1, D.momentum2, D.eps2, D.seed = float(drop_p), mom1, eps1, mom2, eps2, seed
+    D.rowptr, D.col, D.perm = struct.rowptr.data_ptr(), struct.col.data_ptr(), struct.perm.data_ptr()
+    D.rowptr_t, D.col_t, D.perm_t = struct.rowptr_t.data_ptr(), struct.col_t.data_ptr(), struct.perm_t.data_ptr()
+    D.x, D.skip, D.edge_attr = x.data_ptr(), _ptr(skip), attr.data_ptr()
+    D.vocab = ctypes.cast(vc, ctypes.c_void_p) if vc is not None else None
+    D.enc_params = ctypes.cast(encp, ctypes.c_void_p)
+    D.softmax_beta = _ptr(beta)
+    D.rule1, D.W1, D.b1 = r1.data_ptr(), W1.data_ptr(), _ptr(b1)
+    if mlp:
+        D.rule2, D.W2, D.b2 = r2.data_ptr(), W2.data_ptr(), _ptr(b2)
+    if flat1 is not None and mlp:
+        gamma, bt, rmean, rvar, tracked = flat1
+        D.gamma1, D.beta1, D.running_mean1, D.running_var1 = _ptr(gamma), _ptr(bt), _ptr(rmean), _ptr(rvar)
+        D.tracked1, D.n_tracked1 = _ptr(tracked), 0 if tracked is None else tracked.numel()
+    if flat2 is not None:
+        gamma, bt, rmean, rvar, tracked = flat2
+        D.gamma2, D.beta2, D.running_mean2, D.running_var2 = _ptr(gamma), _ptr(bt), _ptr(rmean), _ptr(rvar)
+        D.tracked2, D.n_tracked2 = _ptr(tracked), 0 if tracked is None else tracked.numel()
+    ap = acts.data_ptr()
+    sz = N * F * 4
+    if mlp:
+        D.agg, D.y1, D.a1, D.z = ap, ap + sz, ap + 2 * sz, ap + 3 * sz
+    else:
+        D.agg, D.z = ap, ap + sz
+    D.out = out.data_ptr()
+    D.stats1, D.stats2 = stats.data_ptr(), stats.data_ptr() + 2 * F * 4
+    D.aux_f, D.aux_i = _ptr(aux_f), _ptr(aux_i)
+    D.ws_lin1, D.ws_lin1_bytes = ws_lin.data_ptr(), nb_lin
+    if mlp:
+        D.ws_lin2, D.ws_lin2_bytes = ws_lin.data_ptr() + nb_lin, nb_lin
+    D.ws, D.ws_bytes = ws.data_ptr(), ws.numel()
+    run("phc_conv_layer_fwd", None, ctypes.byref(D), st, launches=11 if mlp else 6)
+    return out, (acts, stats, aux_f, aux_i), (D, vc, encp, ws_lin)
+
+
+def _call_bwd(cfg, struct: EdgeStructure, host, x, attr, g, tensors, sinks=None):
+    """Whole layer backward through phc_conv_layer_bwd.  ``sinks`` (optional, aligned with ``tensors``): tensors to write
+    the parameter gradients INTO (None entries get fresh storage).  -> (dx, grads aligned with ``tensors``)."""
+    (n, linear, enc_dim, vocab, reduce, msg_act, self_loops, mlp, act1, act2, use_bn1, use_bn2, training, drop_p, same, seed,
+     precision, n_enc, has_beta, nb1, nb2, mom1, eps1, mom2, eps2) = cfg
+    D, vc = host[0], host[1]
+    dev = x.device
+    st = _stream(dev)
+    g = g.contiguous()
+    N, F = x.shape
+    f32 = dict(dtype=torch.float32, device=dev)
+    tmp = torch.empty((2, N, F), **f32)
+    dx = torch.empty_like(x)
+    nt = len(tensors)
+    grads = [None] * nt
+    if sinks is None:
+        sinks = [None] * nt
+    # which gradients are wanted, and how large is the fresh storage for those without a sink
+    i0 = 1 if has_beta else 0
+    i_lin1 = i0 + n_enc
+    i_bn1 = i_lin1 + 3
+    i_lin2 = i_bn1 + nb1
+    i_bn2 = i_lin2 + (3 if mlp else 0)
+    single = list(range(i0, i_bn1)) + (list(range(i_lin2, i_bn2)) if mlp else [])      # encoder tables, rule / W / b
+
+    def wanted(k):
+        t = tensors[k]
+        if t is None:
+            return False
+        if k < i_lin1:
+            return True                                 # encoder tables: the kernel writes all of them
+        j = (k - i_lin1) if k < i_bn1 else (k - i_lin2)
+        return True if j == 1 else (t.requires_grad if j == 0 else True)     # rule: only when learned; W, b: always
+
+    need = 0
+    for k in single:
+        if wanted(k) and sinks[k] is None:
+            need += (tensors[k].numel() + 3) & ~3
+    groups = []                                         # batch-norm affine groups: one [2, F] block = n gammas then n betas
+    for start, cnt in ((i_bn1, nb1), (i_bn2, nb2)):
+        if cnt == 0:
+            groups.append(None)
+            continue
+        sk = sinks[start:start + cnt]
+        base = sk[0].data_ptr() if sk[0] is not None else 0
+        ok, off = base != 0, 0
+        if ok:
+            for q in sk:
+                if q is None or q.data_ptr() != base + off * 4:
+                    ok = False
+                    break
+                off += q.numel()
+        groups.append((start, cnt, ok, base))
+        if not ok:
+            need += 2 * F
+    fresh = torch.empty(need + 4, **f32) if need else None
+    o = 0
+    ptrs = [0] * nt
+    for k in single:
+        t = tensors[k]
+        if not wanted(k):
+            continue
+        if sinks[k] is not None:
+            grads[k] = sinks[k]
+        else:
+            grads[k] = fresh[o:o + t.numel()].view(t.shape)
+            o += (t.numel() + 3) & ~3
+        ptrs[k] = grads[k].data_ptr()
+    gb_ptr = [0, 0]
+    for gi, grp in enumerate(groups):
+        if grp is None:
+            continue
+        start, cnt, ok, base = grp
+        if ok:
+            gb_ptr[gi] = base
+            for q in range(cnt):
+                grads[start + q] = sinks[start + q]
+        else:
+            blk = fresh[o:o + 2 * F].view(2, F)
+            o += 2 * F
+            gb_ptr[gi] = blk.data_ptr()
+            for q, v in enumerate(_split_gb(blk, cnt // 2, F)):
+                grads[start + q] = v
+    dbeta = None
+    if has_beta:
+        dbeta = sinks[0] if sinks[0] is not None else torch.empty((), **f32)
+        dbeta.zero_()
+        grads[0] = dbeta
+    rows = enc_dim + 1 if linear else int(sum(vocab))
+    ws = _scratch(_ws_bytes("phc_conv_layer_workspace_bytes", N, F, n, rows, precision), dev, st)
+    sums = _node_sums(struct, attr, linear, enc_dim, vocab, vc, reduce, msg_act, rows, N, dev, st)
+    gencp = (ctypes.c_void_p * max(n_enc, 1))(*[ptrs[i0 + q] for q in range(n_enc)])
+    D.ws, D.ws_bytes = ws.data_ptr(), ws.numel()
+    D.gout, D.node_sums = g.data_ptr(), _ptr(sums)
+    D.tmp_a, D.tmp_b, D.dx = tmp.data_ptr(), tmp.data_ptr() + N * F * 4, dx.data_ptr()
+    D.d_softmax_beta = _ptr(dbeta)
+    D.d_enc_params = ctypes.cast(gencp, ctypes.c_void_p)
+    D.d_rule1, D.d_W1, D.d_b1 = ptrs[i_lin1], ptrs[i_lin1 + 1], ptrs[i_lin1 + 2]
+    if mlp:
+        D.d_rule2, D.d_W2, D.d_b2 = ptrs[i_lin2], ptrs[i_lin2 + 1], ptrs[i_lin2 + 2]
+    D.d_gb1, D.d_gb2 = gb_ptr[0], gb_ptr[1]
+    run("phc_conv_layer_bwd", None, ctypes.byref(D), st, launches=17 if mlp else 10)
+    if not mlp and self_loops:
+        dx.add_(tmp[0])                     # residual branch of PHMLinear(agg) + x
+    return dx, g, grads
+
+
 class _ConvLayerCall(torch.autograd.Function):
-    """Same node as _ConvLayer, one library call per direction."""
+    """Same node as _ConvLayer, one library call per direction; parameter gradients returned through autograd."""
 
     @staticmethod
     def forward(ctx, cfg, struct: EdgeStructure, flats, x, skip, attr, *tensors):
-        (n, linear, enc_dim, vocab, reduce, msg_act, self_loops, mlp, act1, act2, use_bn1, use_bn2, training, drop_p, same, seed,
-         precision, n_enc, has_beta, nb1, nb2, mom1, eps1, mom2, eps2) = cfg
-        flat1, flat2 = flats
-        dev = x.device
-        st = _stream(dev)
-        i = 0
-        beta = tensors[0] if has_beta else None
-        i += 1 if has_beta else 0
-        enc = tensors[i:i + n_enc]; i += n_enc
-        r1, W1, b1 = tensors[i:i + 3]; i += 3 + nb1
-        r2 = W2 = b2 = None
-        if mlp:
-            r2, W2, b2 = tensors[i:i + 3]
-        N, F = x.shape
-        f32 = dict(dtype=torch.float32, device=dev)
-        acts = torch.empty((4 if mlp else 2, N, F), **f32)          # agg, [y1, a1,] z: saved for backward
-        out = torch.empty((N, F), **f32)                            # own storage: callers may modify it in place
-        stats = torch.empty((4, F), **f32)
-        aux_f = torch.empty((2, N, F), **f32) if reduce == 4 else None
-        aux_i = torch.empty((N, F), dtype=torch.int32, device=dev) if reduce in (2, 3) else None
-        nb_lin = _ws_bytes("phc_phm_linear_fwd_workspace_bytes", N, F, F, n, precision)
-        ws_lin1 = _ws(nb_lin, dev)
-        ws_lin2 = _ws(nb_lin, dev) if mlp else None
-        rows = enc_dim + 1 if linear else int(sum(vocab))
-        ws = _scratch(_ws_bytes("phc_conv_layer_workspace_bytes", N, F, n, rows, precision), dev, st)
-        vc = (ctypes.c_int * max(len(vocab), 1))(*vocab) if vocab else None
-        encp = _ptr_array(enc)
-        D = _lib.conv_layer_struct()()
-        D.num_nodes, D.width, D.phm_dim = N, F, n
-        D.enc_kind, D.enc_dim, D.table_rows = 0 if linear else 1, enc_dim, rows
-        D.reduce, D.msg_act, D.self_loops, D.mlp = reduce, msg_act, int(self_loops), int(mlp)
-        D.act1, D.act2, D.use_bn1, D.use_bn2 = act1, act2, int(use_bn1 and mlp), int(use_bn2)
-        D.training, D.drop_same, D.precision = int(training), int(same), precision
-        D.drop_p, D.momentum1, D.eps1, D.momentum2, D.eps2, D.seed = float(drop_p), mom1, eps1, mom2, eps2, seed
-        D.rowptr, D.col, D.perm = struct.rowptr.data_ptr(), struct.col.data_ptr(), struct.perm.data_ptr()
-        D.rowptr_t, D.col_t, D.perm_t = struct.rowptr_t.data_ptr(), struct.col_t.data_ptr(), struct.perm_t.data_ptr()
-        D.x, D.skip, D.edge_attr = x.data_ptr(), _ptr(skip), attr.data_ptr()
-        D.vocab = ctypes.cast(vc, ctypes.c_void_p) if vc is not None else None
-        D.enc_params = ctypes.cast(encp, ctypes.c_void_p)
-        D.softmax_beta = _ptr(beta)
-        D.rule1, D.W1, D.b1 = r1.data_ptr(), W1.data_ptr(), _ptr(b1)
-        if mlp:
-            D.rule2, D.W2, D.b2 = r2.data_ptr(), W2.data_ptr(), _ptr(b2)
-        for k, flat in ((1, flat1 if mlp else None), (2, flat2)):
-            if flat is None:
-                continue
-            gamma, bt, rmean, rvar, tracked = flat
-            setattr(D, f"gamma{k}", _ptr(gamma)); setattr(D, f"beta{k}", _ptr(bt))
-            setattr(D, f"running_mean{k}", _ptr(rmean)); setattr(D, f"running_var{k}", _ptr(rvar))
-            setattr(D, f"tracked{k}", _ptr(tracked)); setattr(D, f"n_tracked{k}", 0 if tracked is None else tracked.numel())
-        ap = acts.data_ptr()
-        sz = N * F * 4
-        if mlp:
-            D.agg, D.y1, D.a1, D.z = ap, ap + sz, ap + 2 * sz, ap + 3 * sz
-        else:
-            D.agg, D.z = ap, ap + sz
-        D.out = out.data_ptr()
-        D.stats1, D.stats2 = stats.data_ptr(), stats.data_ptr() + 2 * F * 4
-        D.aux_f, D.aux_i = _ptr(aux_f), _ptr(aux_i)
-        D.ws_lin1, D.ws_lin1_bytes = ws_lin1.data_ptr(), ws_lin1.numel()
-        if mlp:
-            D.ws_lin2, D.ws_lin2_bytes = ws_lin2.data_ptr(), ws_lin2.numel()
-        D.ws, D.ws_bytes = ws.data_ptr(), ws.numel()
-        run("phc_conv_layer_fwd", None, ctypes.byref(D), st, launches=11 if mlp else 6)
-        ctx.save_for_backward(x, attr, acts, stats, aux_f, aux_i)
-        ctx.misc = (cfg, struct, D, vc, encp, ws_lin1, ws_lin2, tensors, skip is not None)
+        out, saved, host = _call_fwd(cfg, struct, flats, x, skip, attr, tensors)
+        ctx.save_for_backward(x, attr, *saved)
+        ctx.misc = (cfg, struct, host, tensors, skip is not None)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        cfg, struct, D, vc, encp, ws_lin1, ws_lin2, tensors, has_skip = ctx.misc
-        (n, linear, enc_dim, vocab, reduce, msg_act, self_loops, mlp, act1, act2, use_bn1, use_bn2, training, drop_p, same, seed,
-         precision, n_enc, has_beta, nb1, nb2, mom1, eps1, mom2, eps2) = cfg
-        x, attr, acts, stats, aux_f, aux_i = ctx.saved_tensors
-        i = 1 if has_beta else 0
-        enc = tensors[i:i + n_enc]; i += n_enc
-        r1, W1, b1 = tensors[i:i + 3]; i += 3 + nb1
-        r2 = W2 = b2 = None
-        if mlp:
-            r2, W2, b2 = tensors[i:i + 3]
-        dev = x.device
-        st = _stream(dev)
-        g = g.contiguous()
-        N, F = x.shape
-        f32 = dict(dtype=torch.float32, device=dev)
-        tmp = torch.empty((2, N, F), **f32)
-        dx = torch.empty_like(x)
-        # every parameter gradient of the layer lives in one flat buffer
-        sizes = [p.numel() for p in enc] + [r1.numel(), W1.numel(), 0 if b1 is None else b1.numel()]
-        sizes += [r2.numel(), W2.numel(), 0 if b2 is None else b2.numel()] if mlp else [0, 0, 0]
-        sizes += [2 * F if nb1 else 0, 2 * F if nb2 else 0]
-        flatg = torch.empty(sum((k + 3) & ~3 for k in sizes) + 4, **f32)
-        base, offs, o = flatg.data_ptr(), [], 0
-        for k in sizes:
-            offs.append(o)
-            o += (k + 3) & ~3                   # 16-byte aligned pieces
-        genc = [flatg[offs[j]:offs[j] + sizes[j]].view(enc[j].shape) for j in range(n_enc)]
-        j = n_enc
-
-        def piece(t, jj, want=True):
-            return flatg[offs[jj]:offs[jj] + sizes[jj]].view(t.shape) if (t is not None and want) else None
-
-        dr1, dW1, db1 = piece(r1, j, r1.requires_grad), piece(W1, j + 1), piece(b1, j + 2)
-        dr2, dW2, db2 = (piece(r2, j + 3, r2.requires_grad), piece(W2, j + 4), piece(b2, j + 5)) if mlp else (None, None, None)
-        dgb1 = flatg[offs[j + 6]:offs[j + 6] + 2 * F].view(2, F) if nb1 else None
-        dgb2 = flatg[offs[j + 7]:offs[j + 7] + 2 * F].view(2, F) if nb2 else None
-        dbeta = torch.zeros((), **f32) if reduce == 4 else None
-        rows = enc_dim + 1 if linear else int(sum(vocab))
-        ws = _scratch(_ws_bytes("phc_conv_layer_workspace_bytes", N, F, n, rows, precision), dev, st)
-        sums = _node_sums(struct, attr, linear, enc_dim, vocab, vc, reduce, msg_act, rows, N, dev, st)
-        gencp = _ptr_array(genc)
-        D.ws, D.ws_bytes = ws.data_ptr(), ws.numel()
-        D.gout, D.node_sums = g.data_ptr(), _ptr(sums)
-        D.tmp_a, D.tmp_b, D.dx = tmp.data_ptr(), tmp.data_ptr() + N * F * 4, dx.data_ptr()
-        D.d_softmax_beta = _ptr(dbeta)
-        D.d_enc_params = ctypes.cast(gencp, ctypes.c_void_p)
-        D.d_rule1, D.d_W1, D.d_b1 = _ptr(dr1), _ptr(dW1), _ptr(db1)
-        D.d_rule2, D.d_W2, D.d_b2 = _ptr(dr2), _ptr(dW2), _ptr(db2)
-        D.d_gb1, D.d_gb2 = _ptr(dgb1), _ptr(dgb2)
-        run("phc_conv_layer_bwd", None, ctypes.byref(D), st, launches=17 if mlp else 10)
-        if not mlp and self_loops:
-            dx.add_(tmp[0])                     # residual branch of PHMLinear(agg) + x
-        grads = []
-        if has_beta:
-            grads.append(dbeta)
-        grads += genc
-        grads += [dr1, dW1, db1]
-        grads += _split_gb(dgb1, nb1 // 2, F) if nb1 else []
-        if mlp:
-            grads += [dr2, dW2, db2]
-        grads += _split_gb(dgb2, nb2 // 2, F) if nb2 else []
+        cfg, struct, host, tensors, has_skip = ctx.misc
+        x, attr = ctx.saved_tensors[:2]
+        dx, g, grads = _call_bwd(cfg, struct, host, x, attr, g, tensors)
         return (None, None, None, dx, g if has_skip else None, None) + tuple(grads)
+
+
+class _ConvLayerDirect(torch.autograd.Function):
+    """The node with the parameters OUTSIDE the autograd graph: only x and skip are graph inputs; backward writes every
+    parameter gradient straight into its final place — the parameter's slice of the flat gradient buffer when a
+    GradientBucket registered one (``param._phc_sink``), fresh storage otherwise — and assigns / accumulates ``param.grad``
+    itself, as AccumulateGrad would.  At ppa shape the 24 parameter inputs per layer cost more host time in
+    Function.apply, the engine and AccumulateGrad than the layer's kernels take on the GPU.  Not visible to
+    torch.autograd.grad(), parameter hooks or double backward: set ``layer.DIRECT_PARAM_GRADS = False`` for those."""
+
+    @staticmethod
+    def forward(ctx, plan, x, skip):
+        cfg, struct, flats, attr, tensors = plan
+        out, saved, host = _call_fwd(cfg, struct, flats, x, skip, attr, tensors)
+        ctx.save_for_backward(x, attr, *saved)
+        ctx.misc = (cfg, struct, host, tensors, skip is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        cfg, struct, host, tensors, has_skip = ctx.misc
+        x, attr = ctx.saved_tensors[:2]
+        sinks = [None if (t is None or t.grad is not None) else getattr(t, "_phc_sink", None) for t in tensors]
+        dx, g, grads = _call_bwd(cfg, struct, host, x, attr, g, tensors, sinks)
+        for t, gr in zip(tensors, grads):
+            if gr is None or t is None or not t.requires_grad:
+                continue
+            if t.grad is None:
+                t.grad = gr
+            else:
+                t.grad.add_(gr)
+        return None, dx, (g if has_skip else None)
 
 
 def conv_layer(x, skip, edge_attr, struct: EdgeStructure, *, phm_dim: int, enc_linear: bool, enc_params: Sequence[torch.Tensor],
@@ -412,5 +509,8 @@ def conv_layer(x, skip, edge_attr, struct: EdgeStructure, *, phm_dim: int, enc_l
            float(drop_p) if active_drop else 0.0, bool(drop_same), seed, default_precision(), len(enc_params), has_beta, len(p1), len(p2),
            float(norm1.momentum) if norm1 is not None else 0.1, float(norm1.eps) if norm1 is not None else 1e-5,
            float(norm2.momentum) if norm2 is not None else 0.1, float(norm2.eps) if norm2 is not None else 1e-5)
-    node = _ConvLayerCall if (SINGLE_CALL and not PROFILE.timing) else _ConvLayer    # per-operator calls when each is being timed
-    return node.apply(cfg, struct, (flat1, flat2), x, skip, edge_attr, *tensors)
+    if SINGLE_CALL and not PROFILE.timing:
+        if DIRECT_PARAM_GRADS and torch.is_grad_enabled() and x.requires_grad:
+            return _ConvLayerDirect.apply((cfg, struct, (flat1, flat2), edge_attr, tensors), x, skip)
+        return _ConvLayerCall.apply(cfg, struct, (flat1, flat2), x, skip, edge_attr, *tensors)
+    return _ConvLayer.apply(cfg, struct, (flat1, flat2), x, skip, edge_attr, *tensors)       # per-operator calls (each one timed)

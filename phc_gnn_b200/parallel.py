@@ -34,6 +34,8 @@ class GradientBucket(object):
             for p in self.params:
                 self.views.append(self.flat[off:off + p.numel()].view(p.shape))
                 off += p.numel()
+            for p, v in zip(self.params, self.views):
+                p._phc_sink = v            # layer.py writes this parameter's gradient straight into the flat buffer
 
     def pack(self):
         dev = self.params[0].device

@@ -32,16 +32,17 @@ def _compare(got, want, rtol, what, noise=None):
         assert_close(got["running"][k].float(), v.float(), rtol, max(1e-5, tol("running", v.float(), k)), f"{what}: {k}")
 
 
-@pytest.mark.parametrize("fuse", ["call", "layer", "encoder", "none"],
-                         ids=["one-call-per-layer", "one-node-per-layer", "fused-encoder", "separate-ops"])
+@pytest.mark.parametrize("fuse", ["direct", "call", "layer", "encoder", "none"],
+                         ids=["one-call-direct-grads", "one-call-per-layer", "one-node-per-layer", "fused-encoder", "separate-ops"])
 @pytest.mark.parametrize("name", golden_cases())
 def test_model_matches_reference_golden(name, fuse, monkeypatch):
     monkeypatch.setenv("PHC_PRECISION", "fp32")
     from phc_gnn_b200 import layer
-    monkeypatch.setattr(layer, "SINGLE_CALL", fuse == "call")        # phc_conv_layer_fwd/bwd vs one C-ABI call per operator
+    monkeypatch.setattr(layer, "SINGLE_CALL", fuse in ("direct", "call"))   # phc_conv_layer_fwd/bwd vs one C-ABI call per operator
+    monkeypatch.setattr(layer, "DIRECT_PARAM_GRADS", fuse == "direct")      # parameter gradients written in place vs through autograd
     fx = load_golden(name)
     got = product_train_eval(fx["cfg"], fx["state"], fx["batch"], fx["loss_kind"], fx["reg_scale"], DEV,
-                             fuse_edge_encoder=fuse != "none", fuse_layer=fuse in ("call", "layer"))
+                             fuse_edge_encoder=fuse != "none", fuse_layer=fuse in ("direct", "call", "layer"))
     want = dict(logits=fx["logits_train"], loss=fx["loss"], reg=fx["reg"], grads=fx["grads"], running=fx["running_after"],
                 logits_eval=fx["logits_eval"])
     _compare(got, want, RTOL, name)
@@ -182,3 +183,45 @@ def test_flat_clip_adam_matches_torch(monkeypatch):
     with torch.no_grad():
         y = mb(data)
     assert torch.isfinite(y).all()
+
+
+def test_direct_parameter_gradients_use_bucket_sinks_and_accumulate(monkeypatch):
+    """layer._ConvLayerDirect: gradients written straight into the flat gradient buffer equal the autograd-routed ones
+    bit for bit, land in the bucket's memory (no copy at pack time), and a second backward accumulates."""
+    monkeypatch.setenv("PHC_PRECISION", "fp32")
+    from gpu_util import product_model
+    from phc_gnn_b200 import layer
+    from phc_gnn_b200.optim import ordered_parameters
+    from phc_gnn_b200.parallel import GradientBucket
+    from phc_gnn_b200.train import task_loss
+    fx = load_golden("ppa_n4_sum_mlp")
+    data = fx["batch"].to(DEV)
+
+    def grads(direct, with_bucket, passes=1):
+        monkeypatch.setattr(layer, "DIRECT_PARAM_GRADS", direct)
+        m = product_model(fx["cfg"], fx["state"], DEV)
+        m.train()
+        bucket = None
+        if with_bucket:
+            bucket = GradientBucket(ordered_parameters(m))
+            bucket._ensure(torch.device(DEV))
+        for _ in range(passes):
+            task_loss(m(data), data.y, fx["loss_kind"]).backward()
+        return m, bucket, {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+
+    _, _, ref = grads(False, False)
+    m, bucket, got = grads(True, True)
+    assert set(ref) == set(got)
+    for k in ref:
+        assert torch.equal(ref[k], got[k]), k
+    lo, hi = bucket.flat.data_ptr(), bucket.flat.data_ptr() + bucket.flat.numel() * 4
+    inside = [k for k, p in m.named_parameters() if k.startswith("convs.") and p.grad is not None and lo <= p.grad.data_ptr() < hi]
+    assert len(inside) >= 0.9 * len([k for k in ref if k.startswith("convs.")]), "layer gradients were not written into the bucket"
+    flat = bucket.pack().clone()
+    for p, v in zip(bucket.params, bucket.views):
+        if p.grad is not None:
+            assert torch.equal(p.grad, v)
+    _, _, twice = grads(True, True, passes=2)
+    for k in ref:
+        assert_close(twice[k].cpu(), (2 * ref[k]).cpu(), 1e-5, 1e-7 + 1e-5 * float(ref[k].abs().max()), f"accumulated {k}")
+    assert torch.isfinite(flat).all()

@@ -12,6 +12,8 @@ from phc_gnn_b200.train import TrainStep
 name = sys.argv[1] if len(sys.argv) > 1 else "ppa"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 wl = workloads(4)[name]
+if len(sys.argv) > 3:               # fewer graphs per batch: the GPU work shrinks, the step time approaches the pure host cost
+    wl.batch_graphs = int(sys.argv[3])
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 model = PHMSkipConnectAdd(**wl.model).to(dev)
