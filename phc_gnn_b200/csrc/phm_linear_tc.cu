@@ -161,6 +161,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 
 // Shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor).
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
@@ -732,14 +742,15 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) phm_tc_mix_tma_kernel(const Mi
 //   they also drain the accumulators (warp (q,h,g): rows of quarter q, accumulator h, column half g) — the tensor
 //   pipe is idle then anyway, both accumulators being busy.  16 MMA | 17 TMA(x) | 18 TMA(W pack)
 constexpr int V3_NB = 3;                        // W-pack stages (big|small, 32 KiB each)
-constexpr int V3_NR = 2;                        // raw activation stages == chunk parities
+constexpr int V3_NR = 2;                        // chunk parities (operand slots in tensor memory)
+constexpr int V3_NRAW = 3;                      // raw activation stages: deeper than the parities, the boxes come from L2 / HBM
 constexpr int V3_RAW_BYTES = BM * 12 * 4 * 4;   // 4 input components x 128 rows x (8 + 4 pad) floats = 24 KiB
 constexpr int V3_A_COL0 = 2 * BN;               // first operand-slot column
 constexpr int V3_TMEM_COLS = 512;
-constexpr int V3_BARS = 2 * V3_NB + 4 * V3_NR + 2;
+constexpr int V3_BARS = 2 * V3_NB + 2 * V3_NR + 2 * V3_NRAW + 2;
 constexpr int V3_MMA_WARP = PROD_WARPS, V3_TMA_X_WARP = PROD_WARPS + 1, V3_TMA_B_WARP = PROD_WARPS + 2;
 constexpr int V3_THREADS = (PROD_WARPS + 3) * 32;
-constexpr int V3_SPITCH = 36;                   // floats per scratch row: 16-byte aligned rows, conflict-free both ways
+constexpr int V3_SPITCH = 20;                   // floats per scratch row (16 columns per drain pass): 16-byte aligned rows, conflict-free writes
 constexpr int V3_SCRATCH = PROD_WARPS * 32 * V3_SPITCH * 4;
 
 __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -768,35 +779,37 @@ __device__ __forceinline__ void v3_unit(const MixParams& p, int u, int& m0, int&
   pt = r >> 1;
 }
 
-// One warp drains 32 rows x 64 columns of an accumulator: TMEM -> registers -> smem transpose -> coalesced row stores.
+// One warp drains 32 rows x 64 columns of an accumulator, 16 columns per pass: TMEM -> registers -> smem transpose ->
+// row stores (each half warp writes 64 contiguous bytes of one row; the component offset c*P makes rows only 4-byte aligned).
 __device__ __forceinline__ void v3_drain(float* __restrict__ my, uint32_t taddr, float* __restrict__ C, int ldc, int nrows, int r0,
                                          int col0, int ncols, const float* __restrict__ bias, const float* __restrict__ residual, int act) {
   const int lane = threadIdx.x & 31;
+  const int rsel = lane >> 4, lc16 = lane & 15;
   const bool plain = act == PHC_ACT_IDENTITY && residual == nullptr;
 #pragma unroll 1
-  for (int cc = 0; cc < 2; ++cc) {
-    if (cc * 32 >= ncols) break;
-    uint32_t v[32];
-    tmem_ld32(taddr + (uint32_t)(cc * 32), v);
+  for (int cc = 0; cc < 4; ++cc) {
+    if (cc * 16 >= ncols) break;
+    uint32_t v[16];
+    tmem_ld16(taddr + (uint32_t)(cc * 16), v);
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
+    for (int j = 0; j < 4; ++j)
       *reinterpret_cast<float4*>(my + lane * V3_SPITCH + j * 4) =
           make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
     __syncwarp();
-    const int lc = cc * 32 + lane;
+    const int lc = cc * 16 + lc16;
     if (lc < ncols) {
       const int col = col0 + lc;
       const float bv = bias != nullptr ? __ldg(bias + col) : 0.f;
       float* dst = C + (size_t)r0 * ldc + col;
-      const float* src = my + lane;
+      const float* src = my + lc16;
       if (plain && nrows == 32) {
 #pragma unroll
-        for (int rr = 0; rr < 32; ++rr) dst[rr * ldc] = src[rr * V3_SPITCH] + bv;
+        for (int rr = 0; rr < 16; ++rr) dst[(2 * rr + rsel) * ldc] = src[(2 * rr + rsel) * V3_SPITCH] + bv;
       } else if (plain) {
-        for (int rr = 0; rr < nrows; ++rr) dst[rr * ldc] = src[rr * V3_SPITCH] + bv;
+        for (int rr = rsel; rr < nrows; rr += 2) dst[rr * ldc] = src[rr * V3_SPITCH] + bv;
       } else {
         const float* res = residual != nullptr ? residual + (size_t)r0 * ldc + col : nullptr;
-        for (int rr = 0; rr < nrows; ++rr) {
+        for (int rr = rsel; rr < nrows; rr += 2) {
           float o = act_fwd_rt(act, src[rr * V3_SPITCH] + bv);
           if (res != nullptr) o += res[rr * ldc];
           dst[rr * ldc] = o;
@@ -816,17 +829,17 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* bstage = base;                                                   // [V3_NB][B_big | B_small]
-  uint8_t* rawbuf = base + V3_NB * 2 * TILE_BYTES;                          // [V3_NR][4][128][PITCH]
-  float* scratch = reinterpret_cast<float*>(rawbuf + V3_NR * V3_RAW_BYTES);  // [16 warps][32][V3_SPITCH]
+  uint8_t* rawbuf = base + V3_NB * 2 * TILE_BYTES;                          // [V3_NRAW][4][128][PITCH]
+  float* scratch = reinterpret_cast<float*>(rawbuf + V3_NRAW * V3_RAW_BYTES);  // [16 warps][32][V3_SPITCH]
   float* coef = scratch + PROD_WARPS * 32 * V3_SPITCH;
   uint64_t* bars = reinterpret_cast<uint64_t*>(coef + NT * NT * NT);
   uint64_t* bfull = bars;                                  // [V3_NB]
   uint64_t* bempty = bars + V3_NB;                         // [V3_NB]
   uint64_t* afull = bars + 2 * V3_NB;                      // [2]
   uint64_t* aempty = afull + V3_NR;                        // [2]
-  uint64_t* rfull = aempty + V3_NR;                        // [2]
-  uint64_t* rempty = rfull + V3_NR;                        // [2]
-  uint64_t* tfull = rempty + V3_NR;                        // accumulators complete -> drain
+  uint64_t* rfull = aempty + V3_NR;                        // [V3_NRAW]
+  uint64_t* rempty = rfull + V3_NRAW;                      // [V3_NRAW]
+  uint64_t* tfull = rempty + V3_NRAW;                      // accumulators complete -> drain
   uint64_t* tempty = tfull + 1;                            // accumulators drained  -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + V3_BARS);
 
@@ -837,8 +850,10 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
     for (int i = 0; i < V3_NR; ++i) {
       mbar_init(smem_u32(&afull[i]), 8);      // the parity's eight producer warps (2 components x 4 lane quarters)
       mbar_init(smem_u32(&aempty[i]), 1);     // tcgen05.commit
+    }
+    for (int i = 0; i < V3_NRAW; ++i) {
       mbar_init(smem_u32(&rfull[i]), 1);      // TMA transaction
-      mbar_init(smem_u32(&rempty[i]), 8);
+      mbar_init(smem_u32(&rempty[i]), 8);     // the eight producer warps that consume the chunk
     }
     mbar_init(smem_u32(tfull), 1);
     mbar_init(smem_u32(tempty), PROD_WARPS);
@@ -858,7 +873,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
     const int row = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const uint32_t a_slot = tmem_base + lane_base + (uint32_t)(V3_A_COL0 + (g * 2 + h) * 64);
-    const uint32_t rawg = smem_u32(rawbuf + g * V3_RAW_BYTES) + (uint32_t)(row * PITCH * 4);
+    const uint32_t raw0 = smem_u32(rawbuf) + (uint32_t)(row * PITCH * 4);
     float* my = scratch + warp * 32 * V3_SPITCH;
     const int ldc = p.n * p.Pout;
     float cf[NT * NT];
@@ -872,9 +887,11 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
         for (int i = 0; i < NT * NT; ++i) cf[i] = coef[comp * NT * NT + i];      // [b][uu]
         cur_comp = comp;
       }
-      const int use = gi >> 1;                                   // how often this parity's stage / slot has been used
+      const int use = gi >> 1;                                   // how often this parity's operand slot has been used
+      const int rs = gi % V3_NRAW;                               // raw stage of this chunk
+      const uint32_t rawg = raw0 + (uint32_t)(rs * V3_RAW_BYTES);
       if (prof) tp = clock64();
-      mbar_wait(smem_u32(&rfull[g]), use & 1);                  // raw boxes landed (TMA)
+      mbar_wait(smem_u32(&rfull[rs]), (gi / V3_NRAW) & 1);      // raw boxes landed (TMA)
       if (prof) { const long long tn = clock64(); t_rfull += tn - tp; tp = tn; }
       float xr[NT][KQ];
       uint32_t landed = 0;                                       // data dependence on every load (see the release below)
@@ -899,7 +916,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
       // the arrive (release) stays behind the store.
       asm volatile("st.shared.b32 [%0], %1;" ::"r"(smem_u32(my + lane)), "r"(landed) : "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&rempty[g]));
+      if (lane == 0) mbar_arrive(smem_u32(&rempty[rs]));
       if (c == p.chunks - 1) {                                   // K tail: columns past the component belong to its neighbour
 #pragma unroll
         for (int k = 0; k < KQ; ++k)
@@ -977,8 +994,8 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
         int m0, pair, pt;
         v3_unit(p, blockIdx.x + ui * gridDim.x, m0, pair, pt);
         for (int c = 0; c < p.chunks; ++c, ++gi) {
-          const int rs = gi & 1;
-          mbar_wait(smem_u32(&rempty[rs]), ((gi >> 1) & 1) ^ 1);
+          const int rs = gi % V3_NRAW;
+          mbar_wait(smem_u32(&rempty[rs]), ((gi / V3_NRAW) & 1) ^ 1);
           const uint32_t bar = smem_u32(&rfull[rs]);
           mbar_arrive_expect_tx(bar, NT * BM * PITCH * 4);
 #pragma unroll
@@ -1468,7 +1485,7 @@ int try_launch_mix_tma(const MixParams& p, cudaStream_t stream) {
 }
 
 size_t smem_bytes_v3() {
-  return 1024 + (size_t)V3_NB * 2 * TILE_BYTES + (size_t)V3_NR * V3_RAW_BYTES + V3_SCRATCH + sizeof(float) * 64 + 8 * V3_BARS + 16;
+  return 1024 + (size_t)V3_NB * 2 * TILE_BYTES + (size_t)V3_NRAW * V3_RAW_BYTES + V3_SCRATCH + sizeof(float) * 64 + 8 * V3_BARS + 16;
 }
 
 template <int R, bool SINGLE>
