@@ -127,8 +127,8 @@ int phc_phm_linear_fwd(const float* x, const float* phm_rule, const float* W, co
 int phc_phm_linear_bwd(const float* gy, const float* x, const float* phm_rule, const float* W, float* dx, float* d_rule, float* dW,
                        float* dbias, int rows, int in_features, int out_features, int phm_dim, int precision, void* workspace,
                        size_t workspace_bytes, const void* fwd_workspace, phc_stream_t stream);
-/* fwd_workspace: optional — the (unchanged) workspace of the matching phc_phm_linear_fwd call; lets the tensor-core
- * path reuse the operand packs written there instead of re-packing W. */
+/* fwd_workspace: optional — the workspace of the matching phc_phm_linear_fwd call, untouched since; lets the
+ * tensor-core path reuse the operand packs written there instead of re-packing W (its scratch part is reused too). */
 
 /* ---- aggregation with the edge encoder fused in (models.py:238-243 + messagepassing.py:72-74,136-138,297-300)
  * out[i] = (self_loop ? x[i] : 0) + AGG_e act(x[src(e)] + enc(edge_attr[e])); the [E,F] edge embedding is never

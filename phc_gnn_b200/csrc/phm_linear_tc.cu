@@ -77,6 +77,8 @@ struct MixParams {          // y = act(mix GEMM + bias) + residual   (FWD and DX
   int M, n, Kin, Pout, S, chunks, ptiles, act, num_tiles;
   int single;               // 1: "bf16" mode — operands rounded to bf16, one tensor-core pass (no big/small split)
   long long* prof;          // optional per-CTA role timers (debug), 8 slots per CTA
+  float* sk_part;           // v3 stream-K: per-CTA partial accumulators [grid][16 warps][32 rows][64 cols] (NULL: whole units only)
+  unsigned int* sk_flags;   // v3 stream-K: [grid][16] "partial written" flags, zero between launches
 };
 
 struct DhParams {           // partial dH tiles
@@ -779,18 +781,83 @@ __device__ __forceinline__ void v3_unit(const MixParams& p, int u, int& m0, int&
   pt = r >> 1;
 }
 
+// Stream-K work split: the (unit, K chunk) list is linearised and CTA b owns the contiguous range [gb, ge) of it, so every
+// CTA runs the same number of chunk-steps (+-1) whatever the number of units (244 units on 148 CTAs used to cost two
+// full units on 96 CTAs and one on the rest).  A unit that straddles a boundary is computed by two CTAs: the CTA holding
+// its LAST chunks processes them first and parks the partial accumulators in global memory (16 warp regions + flags); the
+// CTA holding its FIRST chunks processes them last, adds the partial (long since written) and stores the result.  The
+// split points and the order of the addition are fixed: results are reproducible run to run.
+struct V3Seg { int u, c0, c1; };
+__device__ __forceinline__ int v3_range(const MixParams& p, long long& gb, long long& ge) {
+  if (p.sk_part != nullptr) {
+    const long long G = (long long)p.num_tiles * p.chunks;
+    gb = G * blockIdx.x / gridDim.x;
+    ge = G * (blockIdx.x + 1) / gridDim.x;
+  } else {                                                         // whole units only
+    gb = ((long long)p.num_tiles * blockIdx.x / gridDim.x) * p.chunks;
+    ge = ((long long)p.num_tiles * (blockIdx.x + 1) / gridDim.x) * p.chunks;
+  }
+  return ge > gb ? (int)((ge - 1) / p.chunks - gb / p.chunks + 1) : 0;
+}
+__device__ __forceinline__ V3Seg v3_seg(const MixParams& p, long long gb, long long ge, int i) {
+  V3Seg sg;
+  sg.u = (int)(gb / p.chunks) + i;
+  const long long base = (long long)sg.u * p.chunks;
+  sg.c0 = gb > base ? (int)(gb - base) : 0;
+  sg.c1 = ge - base < p.chunks ? (int)(ge - base) : p.chunks;
+  return sg;
+}
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* ptr) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned int* ptr, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory");
+}
+
 // One warp drains 32 rows x 64 columns of an accumulator, 16 columns per pass: TMEM -> registers -> smem transpose ->
 // row stores (each half warp writes 64 contiguous bytes of one row; the component offset c*P makes rows only 4-byte aligned).
+// mode 0: whole unit; 1: park the partial accumulators in `part` and raise `flag`; 2: add the partner's partial first
 __device__ __forceinline__ void v3_drain(float* __restrict__ my, uint32_t taddr, float* __restrict__ C, int ldc, int nrows, int r0,
-                                         int col0, int ncols, const float* __restrict__ bias, const float* __restrict__ residual, int act) {
+                                         int col0, int ncols, const float* __restrict__ bias, const float* __restrict__ residual, int act,
+                                         int mode, float* __restrict__ part, unsigned int* __restrict__ flag) {
   const int lane = threadIdx.x & 31;
   const int rsel = lane >> 4, lc16 = lane & 15;
   const bool plain = act == PHC_ACT_IDENTITY && residual == nullptr;
+  if (mode == 2) {
+    if (lane == 0 && ld_acquire_u32(flag) == 0u) {
+      const long long t0 = clock64();
+      while (ld_acquire_u32(flag) == 0u) {
+        __nanosleep(64);
+        if (clock64() - t0 > 4000000000LL) __trap();               // bounded: a protocol bug must trap, never hang
+      }
+    }
+    __syncwarp();
+  }
 #pragma unroll 1
   for (int cc = 0; cc < 4; ++cc) {
     if (cc * 16 >= ncols) break;
     uint32_t v[16];
     tmem_ld16(taddr + (uint32_t)(cc * 16), v);
+    if (mode != 0) {
+      float4* pp = reinterpret_cast<float4*>(part + lane * 64 + cc * 16);
+      if (mode == 1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          __stcg(pp + j, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                     __uint_as_float(v[4 * j + 3])));
+        continue;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 t = __ldcg(pp + j);                           // written by another SM: bypass L1
+        v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + t.x);
+        v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + t.y);
+        v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + t.z);
+        v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + t.w);
+      }
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       *reinterpret_cast<float4*>(my + lane * V3_SPITCH + j * 4) =
@@ -817,6 +884,14 @@ __device__ __forceinline__ void v3_drain(float* __restrict__ my, uint32_t taddr,
       }
     }
     __syncwarp();
+  }
+  if (mode == 1) {
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) st_release_u32(flag, 1u);
+  } else if (mode == 2) {
+    __syncwarp();
+    if (lane == 0) *flag = 0u;                                     // consumed: the flags are zero again for the next launch
   }
 }
 
@@ -865,7 +940,8 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int my_units = p.num_tiles > (int)blockIdx.x ? (p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;   // num_tiles = #units
+  long long gb, ge;
+  const int nseg = v3_range(p, gb, ge);                              // num_tiles = #units; this CTA's share of the (unit, chunk) list
 
   if (warp < PROD_WARPS) {
     // ===================================================================== producers (+ accumulator drain)
@@ -954,34 +1030,43 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
       if (lane == 0) mbar_arrive(smem_u32(&afull[g]));
       if (prof) t_work += clock64() - tp;
     };
-    auto drain = [&](int ui) {
+    auto drain = [&](int si) {
+      const V3Seg sg = v3_seg(p, gb, ge, si);
       int m0, pair, pt;
-      v3_unit(p, blockIdx.x + ui * gridDim.x, m0, pair, pt);
+      v3_unit(p, sg.u, m0, pair, pt);
       const int ncols = min(BN, p.Pout - pt * BN) - g * 64;     // valid columns of this warp's half
       const long long td0 = prof ? clock64() : 0;
-      mbar_wait(smem_u32(tfull), ui & 1);
+      mbar_wait(smem_u32(tfull), si & 1);
       tc_fence_after();
       const int r0 = m0 + q * 32;
+      // split unit: its last chunks (c0 > 0) are parked in this CTA's slot; its first chunks (c1 < chunks) belong to the
+      // owner, which adds the partial parked by the NEXT CTA (whose first segment is the rest of this unit)
+      const int mode = sg.c0 > 0 ? 1 : (sg.c1 < p.chunks ? 2 : 0);
+      const int slot = (int)blockIdx.x + (mode == 2 ? 1 : 0);
       if (ncols > 0 && r0 < p.M)
         v3_drain(my, tmem_base + lane_base + (uint32_t)(h * BN + g * 64), p.C, ldc, min(32, p.M - r0), r0,
-                 (2 * pair + h) * p.Pout + pt * BN + g * 64, ncols, p.bias, p.residual, p.act);
+                 (2 * pair + h) * p.Pout + pt * BN + g * 64, ncols, p.bias, p.residual, p.act, mode,
+                 mode ? p.sk_part + ((size_t)slot * PROD_WARPS + warp) * (32 * 64) : nullptr,
+                 mode ? p.sk_flags + slot * PROD_WARPS + warp : nullptr);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(tempty));
       if (prof) t_drain += clock64() - td0;
     };
 
-    int gi0 = 0;                                                 // global chunk index of the unit's first chunk
-    for (int ui = 0; ui < my_units; ++ui, gi0 += p.chunks) {
+    int gi0 = 0;                                                 // CTA-local index of the segment's first chunk
+    for (int si = 0; si < nseg; ++si) {
+      const V3Seg sg = v3_seg(p, gb, ge, si);
       int m0, pair, pt;
-      v3_unit(p, blockIdx.x + ui * gridDim.x, m0, pair, pt);
+      v3_unit(p, sg.u, m0, pair, pt);
       const int comp = 2 * pair + h;
-      int c = (gi0 & 1) == g ? 0 : 1;                            // this parity's first chunk of the unit
-      if (c < p.chunks) { produce(gi0 + c, c, comp); c += 2; }  // ... goes in BEFORE draining the previous unit, so the
-      if (ui > 0) drain(ui - 1);                                 //     tensor pipe restarts the moment the accumulators are free
-      for (; c < p.chunks; c += 2) produce(gi0 + c, c, comp);
+      int c = sg.c0 + ((gi0 & 1) == g ? 0 : 1);                  // this parity's first chunk of the segment
+      if (c < sg.c1) { produce(gi0 + c - sg.c0, c, comp); c += 2; }   // ... goes in BEFORE draining the previous one, so the
+      if (si > 0) drain(si - 1);                                 //     tensor pipe restarts the moment the accumulators are free
+      for (; c < sg.c1; c += 2) produce(gi0 + c - sg.c0, c, comp);
+      gi0 += sg.c1 - sg.c0;
     }
-    if (my_units > 0) drain(my_units - 1);
+    if (nseg > 0) drain(nseg - 1);
     if (prof) {
       p.prof[blockIdx.x * 8 + 0] = t_rfull; p.prof[blockIdx.x * 8 + 1] = t_work; p.prof[blockIdx.x * 8 + 7] = t_aempty;
       p.prof[blockIdx.x * 8 + 5] = t_drain;
@@ -990,10 +1075,11 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
     // ===================================================================== TMA: raw activation boxes
     if (lane == 0) {
       int gi = 0;
-      for (int ui = 0; ui < my_units; ++ui) {
+      for (int si = 0; si < nseg; ++si) {
+        const V3Seg sg = v3_seg(p, gb, ge, si);
         int m0, pair, pt;
-        v3_unit(p, blockIdx.x + ui * gridDim.x, m0, pair, pt);
-        for (int c = 0; c < p.chunks; ++c, ++gi) {
+        v3_unit(p, sg.u, m0, pair, pt);
+        for (int c = sg.c0; c < sg.c1; ++c, ++gi) {
           const int rs = gi % V3_NRAW;
           mbar_wait(smem_u32(&rempty[rs]), ((gi / V3_NRAW) & 1) ^ 1);
           const uint32_t bar = smem_u32(&rfull[rs]);
@@ -1008,10 +1094,11 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
     // ===================================================================== TMA: pre-split W chunks
     if (lane == 0) {
       int gi = 0;
-      for (int ui = 0; ui < my_units; ++ui) {
+      for (int si = 0; si < nseg; ++si) {
+        const V3Seg sg = v3_seg(p, gb, ge, si);
         int m0, pair, pt;
-        v3_unit(p, blockIdx.x + ui * gridDim.x, m0, pair, pt);
-        for (int c = 0; c < p.chunks; ++c, ++gi) {
+        v3_unit(p, sg.u, m0, pair, pt);
+        for (int c = sg.c0; c < sg.c1; ++c, ++gi) {
           const int bs = gi % V3_NB;
           mbar_wait(smem_u32(&bempty[bs]), ((gi / V3_NB) & 1) ^ 1);
           const uint32_t fb = smem_u32(&bfull[bs]);
@@ -1027,13 +1114,14 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
     const bool prof = p.prof != nullptr && lane == 0;
     long long t_tempty = 0, t_afull = 0, t_bfull = 0, tp = 0;
     const long long tk0 = prof ? clock64() : 0;
-    for (int ui = 0; ui < my_units; ++ui) {
+    for (int si = 0; si < nseg; ++si) {
+      const V3Seg sg = v3_seg(p, gb, ge, si);
       if (prof) tp = clock64();
-      mbar_wait(smem_u32(tempty), (ui & 1) ^ 1);                // both accumulators drained
+      mbar_wait(smem_u32(tempty), (si & 1) ^ 1);                // both accumulators drained
       if (prof) t_tempty += clock64() - tp;
       tc_fence_after();
       uint32_t accum = 0;
-      for (int c = 0; c < p.chunks; ++c, ++gi) {
+      for (int c = sg.c0; c < sg.c1; ++c, ++gi) {
         const int g = gi & 1, bs = gi % V3_NB;
         if (prof) tp = clock64();
         mbar_wait(smem_u32(&afull[g]), (gi >> 1) & 1);
@@ -1307,10 +1395,11 @@ __global__ void __launch_bounds__(DH_TMA_THREADS, 1) phm_tc_dh_tma_kernel(const 
 __global__ void __launch_bounds__(256) phm_pack_kernel(const float* __restrict__ A, const float* __restrict__ W, int n, int K, int P,
                                                        uint8_t* __restrict__ pack_fwd, float* __restrict__ coef_fwd,
                                                        uint8_t* __restrict__ pack_dx, float* __restrict__ coef_dx, int units_fwd,
-                                                       int units_dx, int single) {
+                                                       int units_dx, int single, unsigned int* __restrict__ sk_flags, int n_flags) {
   pdl_begin();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int n3 = n * n * n;
+  if (sk_flags != nullptr && t < n_flags) sk_flags[t] = 0u;       // stream-K "partial written" flags of the mix kernel
   if (t < n3) {
     const int b = t / (n * n), a = (t / n) % n, c = t % n;
     const float v = A[t];
@@ -1351,6 +1440,14 @@ size_t smem_bytes(int coef_floats) {
   return 1024 + (size_t)STAGES * STAGE_BYTES + EPI_SCRATCH + sizeof(float) * ((coef_floats + 3) & ~3) + 8 * (2 * STAGES + 4) + 16;
 }
 
+// Stream-K split of the n = 4 mix kernel's unit list (v3_range): balances the CTAs (244 units on 148 CTAs at ppa shape) but
+// every split unit costs two extra accumulator drains (park + add), and the drain is not overlapped with the MMAs because
+// tensor memory is full.  Measured on B200 at ppa shape: 61.7 us with the split against 50.1 us without — opt-in only.
+bool stream_k_enabled() {
+  static const bool on = getenv("PHC_TC_STREAM_K") != nullptr;
+  return on;
+}
+
 int num_sms() {
   static int sms = 0;
   if (sms == 0) {
@@ -1375,8 +1472,10 @@ int dh_splits(int M, int In, int Out, int* rows_per_split) {
 
 struct PackLayout {
   size_t coef_fwd, coef_dx, pack_fwd, pack_dx, total;   // byte offsets into the pack buffer
+  size_t sk_flags, sk_part;                             // stream-K scratch of the n = 4 mix kernel (0: none), inside `total`
   int chunks_fwd, chunks_dx, pt_fwd, pt_dx;
 };
+constexpr size_t SK_PART_BYTES = (size_t)PROD_WARPS * 32 * 64 * 4;     // one CTA's parked accumulators (128 KiB)
 
 PackLayout pack_layout(int n, int K, int P) {
   PackLayout L;
@@ -1388,6 +1487,13 @@ PackLayout pack_layout(int n, int K, int P) {
   L.pack_fwd = 2 * n3b;
   L.pack_dx = L.pack_fwd + (size_t)L.pt_fwd * L.chunks_fwd * 2 * TILE_BYTES;
   L.total = L.pack_dx + (size_t)L.pt_dx * L.chunks_dx * 2 * TILE_BYTES;
+  L.sk_flags = L.sk_part = 0;
+  if (n == 4 && stream_k_enabled()) {
+    const size_t ctas = (size_t)num_sms() + 1;
+    L.sk_flags = L.total;
+    L.sk_part = (L.sk_flags + ctas * PROD_WARPS * 4 + 1023) & ~(size_t)1023;
+    L.total = L.sk_part + ctas * SK_PART_BYTES;
+  }
   return L;
 }
 
@@ -1541,9 +1647,11 @@ int launch_pack(const float* A, const float* W, int n, int K, int P, uint8_t* bu
   const int units_fwd = L.pt_fwd * L.chunks_fwd * BN * 8, units_dx = L.pt_dx * L.chunks_dx * BN * 8;
   int threads = units_fwd > units_dx ? units_fwd : units_dx;
   if (threads < n * n * n) threads = n * n * n;
+  const int n_flags = L.sk_part ? (num_sms() + 1) * PROD_WARPS : 0;
+  if (threads < n_flags) threads = n_flags;
   phc_launch(phm_pack_kernel, dim3(phc_div_up(threads, 256)), dim3(256), 0, stream, A, W, n, K, P, buf + L.pack_fwd, reinterpret_cast<float*>(buf + L.coef_fwd),
                                                                 buf + L.pack_dx, reinterpret_cast<float*>(buf + L.coef_dx), units_fwd,
-                                                                units_dx, single);
+                                                                units_dx, single, L.sk_part ? reinterpret_cast<unsigned int*>(buf + L.sk_flags) : nullptr, n_flags);
   return phc_check_launch("phm_pack_kernel");
 }
 
@@ -1628,6 +1736,10 @@ int phm_tc_fwd(const float* x, const float* A, const float* W, const float* bias
   p.num_tiles = phc_div_up(rows, tc::BM) * n * p.ptiles;
   p.single = single;
   p.prof = g_phm_tc_prof;
+  if (L.sk_part && tc::stream_k_enabled()) {
+    p.sk_part = reinterpret_cast<float*>(buf + L.sk_part);
+    p.sk_flags = reinterpret_cast<unsigned int*>(buf + L.sk_flags);
+  }
   return tc::launch_mix(p, stream);
 }
 
@@ -1651,6 +1763,11 @@ int phm_tc_bwd(const float* gy, const float* x, const float* A, const float* W, 
     p.M = rows; p.n = n; p.Kin = P; p.Pout = K; p.S = n * P; p.chunks = L.chunks_dx; p.ptiles = L.pt_dx; p.act = PHC_ACT_IDENTITY;
     p.num_tiles = phc_div_up(rows, tc::BM) * n * p.ptiles;
     p.single = single;
+    if (L.sk_part && tc::stream_k_enabled()) {          // scratch region of the pack workspace (the forward call's when its packs are reused)
+      uint8_t* wpk = const_cast<uint8_t*>(pk);
+      p.sk_part = reinterpret_cast<float*>(wpk + L.sk_part);
+      p.sk_flags = reinterpret_cast<unsigned int*>(wpk + L.sk_flags);
+    }
     rc = tc::launch_mix(p, stream);
     if (rc) return rc;
   }
