@@ -97,6 +97,13 @@ int phc_bn_act_drop_skip_fwd(const float* h, const float* gamma, const float* be
                              int use_bn, int training, float momentum, float eps, int act, float drop_p, int drop_same,
                              unsigned long long seed, float* y, float* save_mean, float* save_rstd, void* workspace,
                              size_t workspace_bytes, phc_stream_t stream);
+/* Training-mode forward with the chunk moments already produced by the kernel that wrote h (see phc_phm_linear_fwd_bnstats):
+ * partials[ceil(rows/chunk_rows)][2][width] = (chunk mean, chunk M2). */
+int phc_bn_act_drop_skip_fwd_partials(const float* h, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                      long long* num_batches_tracked, int n_tracked, const float* skip, int rows, int width, int phm_dim,
+                                      int training, float momentum, float eps, int act, float drop_p, int drop_same,
+                                      unsigned long long seed, float* y, float* save_mean, float* save_rstd, const float* partials,
+                                      int chunk_rows, phc_stream_t stream);
 int phc_bn_act_drop_skip_bwd(const float* dy, const float* h, const float* gamma, const float* beta, const float* save_mean,
                              const float* save_rstd, int rows, int width, int phm_dim, int use_bn, int training, int act, float drop_p,
                              int drop_same, unsigned long long seed, float* dh, float* dgamma, float* dbeta, void* workspace,
@@ -124,6 +131,13 @@ size_t phc_phm_linear_bwd_workspace_bytes(int rows, int in_features, int out_fea
 int phc_phm_linear_fwd(const float* x, const float* phm_rule, const float* W, const float* bias, const float* residual, float* y, int rows,
                        int in_features, int out_features, int phm_dim, int act, int precision, void* workspace, size_t workspace_bytes,
                        phc_stream_t stream);
+/* As phc_phm_linear_fwd; additionally the epilogue of the tensor-core n = 4 kernel writes, for a batch-norm that follows
+ * (norm.py:30-35 after layers.py:349-355), the per-32-row-chunk column moments of y (chunk mean, chunk M2) to
+ * bn_partials[ceil(rows/32)][2][out_features]; *bn_produced = 1 when they were written (other paths: 0, use the plain
+ * phc_bn_act_drop_skip_fwd).  Consume them with phc_bn_act_drop_skip_fwd_partials(..., bn_partials, 32, ...). */
+int phc_phm_linear_fwd_bnstats(const float* x, const float* phm_rule, const float* W, const float* bias, const float* residual, float* y,
+                               int rows, int in_features, int out_features, int phm_dim, int act, int precision, void* workspace,
+                               size_t workspace_bytes, float* bn_partials, int* bn_produced, phc_stream_t stream);
 int phc_phm_linear_bwd(const float* gy, const float* x, const float* phm_rule, const float* W, float* dx, float* d_rule, float* dW,
                        float* dbias, int rows, int in_features, int out_features, int phm_dim, int precision, void* workspace,
                        size_t workspace_bytes, const void* fwd_workspace, phc_stream_t stream);

@@ -38,7 +38,8 @@ int phm_tc_supported(int rows, int in_features, int out_features, int phm_dim, i
 size_t phm_tc_fwd_workspace_bytes(int rows, int in_features, int out_features, int phm_dim, int precision);
 size_t phm_tc_bwd_workspace_bytes(int rows, int in_features, int out_features, int phm_dim, int precision);
 int phm_tc_fwd(const float* x, const float* A, const float* W, const float* bias, const float* residual, float* y, int rows,
-               int in_features, int out_features, int phm_dim, int act, int precision, void* workspace, cudaStream_t stream);
+               int in_features, int out_features, int phm_dim, int act, int precision, void* workspace, float* bn_partials,
+               int* bn_produced, cudaStream_t stream);
 int phm_tc_bwd(const float* gy, const float* x, const float* A, const float* W, float* dx, float* dA, float* dW, float* db, int rows,
                int in_features, int out_features, int phm_dim, int precision, void* workspace, const void* fwd_pack, cudaStream_t stream);
 
@@ -70,9 +71,10 @@ size_t phc_phm_linear_bwd_workspace_bytes(int rows, int in_features, int out_fea
   return phm_simt_bwd_workspace_bytes(rows, in_features, out_features, phm_dim);
 }
 
-int phc_phm_linear_fwd(const float* x, const float* phm_rule, const float* W, const float* bias, const float* residual, float* y, int rows,
-                       int in_features, int out_features, int phm_dim, int act, int precision, void* workspace, size_t workspace_bytes,
-                       cudaStream_t stream) {
+int phc_phm_linear_fwd_bnstats(const float* x, const float* phm_rule, const float* W, const float* bias, const float* residual, float* y,
+                               int rows, int in_features, int out_features, int phm_dim, int act, int precision, void* workspace,
+                               size_t workspace_bytes, float* bn_partials, int* bn_produced, cudaStream_t stream) {
+  if (bn_produced) *bn_produced = 0;
   int rc = check_linear_shape("phc_phm_linear_fwd", rows, in_features, out_features, phm_dim, precision);
   if (rc) return rc;
   PHC_REQUIRE(act >= PHC_ACT_IDENTITY && act <= PHC_ACT_SWISH, "phc_phm_linear_fwd: bad act %d", act);
@@ -80,8 +82,16 @@ int phc_phm_linear_fwd(const float* x, const float* phm_rule, const float* W, co
               "phc_phm_linear_fwd: workspace too small");
   if (rows == 0) return PHC_OK;
   if (precision != PHC_PREC_FP32 && phm_tc_supported(rows, in_features, out_features, phm_dim, precision))
-    return phm_tc_fwd(x, phm_rule, W, bias, residual, y, rows, in_features, out_features, phm_dim, act, precision, workspace, stream);
+    return phm_tc_fwd(x, phm_rule, W, bias, residual, y, rows, in_features, out_features, phm_dim, act, precision, workspace, bn_partials,
+                      bn_produced, stream);
   return phm_simt_fwd(x, phm_rule, W, bias, residual, y, rows, in_features, out_features, phm_dim, act, stream);
+}
+
+int phc_phm_linear_fwd(const float* x, const float* phm_rule, const float* W, const float* bias, const float* residual, float* y, int rows,
+                       int in_features, int out_features, int phm_dim, int act, int precision, void* workspace, size_t workspace_bytes,
+                       cudaStream_t stream) {
+  return phc_phm_linear_fwd_bnstats(x, phm_rule, W, bias, residual, y, rows, in_features, out_features, phm_dim, act, precision, workspace,
+                                    workspace_bytes, nullptr, nullptr, stream);
 }
 
 int phc_phm_linear_bwd(const float* gy, const float* x, const float* phm_rule, const float* W, float* dx, float* d_rule, float* dW,

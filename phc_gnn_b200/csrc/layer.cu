@@ -7,6 +7,7 @@
 // layer instead of six (forward) / seven (backward) — at ppa shape the Python-side cost of those calls had caught up
 // with the GPU time of the kernels.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include "../../include/phc_b200.h"
 
 void phc_set_error(const char* fmt, ...);
@@ -52,24 +53,41 @@ int phc_conv_layer_fwd(const phc_conv_layer* L, phc_stream_t stream) {
   rc = phc_conv_fused_fwd(L->x, L->edge_attr, L->enc_kind, L->enc_dim, L->vocab, L->enc_params, L->rowptr, L->col, L->perm, N, F, n, L->reduce,
                           L->msg_act, L->softmax_beta, L->self_loops && L->mlp, L->agg, L->aux_f, L->aux_i, stream);
   if (rc) return rc;
-  // 2.-4. PHM transform
+  // 2.-4. PHM transform.  When a training-mode batch-norm follows a PHMLinear, the linear kernel's epilogue also emits the
+  // chunk moments of its output (into the scratch workspace) and the norm only merges them.
+  float* part = reinterpret_cast<float*>(L->ws);
+  static const bool fuse_stats = getenv("PHC_NO_FUSED_BN_STATS") == nullptr;      // A/B switch
+  const bool part_fits = fuse_stats && L->ws_bytes >= sizeof(float) * 2 * ((size_t)(N + 31) / 32) * F;
+  int got1 = 0, got2 = 0;
   if (L->mlp) {
-    rc = phc_phm_linear_fwd(L->agg, L->rule1, L->W1, L->b1, nullptr, L->y1, N, F, F, n, PHC_ACT_IDENTITY, L->precision, L->ws_lin1,
-                            L->ws_lin1_bytes, stream);
+    const bool want1 = L->use_bn1 && L->training && part_fits;
+    rc = phc_phm_linear_fwd_bnstats(L->agg, L->rule1, L->W1, L->b1, nullptr, L->y1, N, F, F, n, PHC_ACT_IDENTITY, L->precision, L->ws_lin1,
+                                    L->ws_lin1_bytes, want1 ? part : nullptr, &got1, stream);
     if (rc) return rc;
-    rc = phc_bn_act_drop_skip_fwd(L->y1, L->gamma1, L->beta1, L->use_bn1 ? L->running_mean1 : nullptr, L->use_bn1 ? L->running_var1 : nullptr,
-                                  (L->use_bn1 && L->training) ? L->tracked1 : nullptr, L->n_tracked1, nullptr, N, F, n, L->use_bn1, L->training,
-                                  L->momentum1, L->eps1, L->act1, 0.f, 0, 0ull, L->a1, L->use_bn1 ? L->stats1 : nullptr,
-                                  L->use_bn1 ? L->stats1 + F : nullptr, L->ws, L->ws_bytes, stream);
+    if (got1)
+      rc = phc_bn_act_drop_skip_fwd_partials(L->y1, L->gamma1, L->beta1, L->running_mean1, L->running_var1, L->tracked1, L->n_tracked1, nullptr,
+                                             N, F, n, 1, L->momentum1, L->eps1, L->act1, 0.f, 0, 0ull, L->a1, L->stats1, L->stats1 + F, part,
+                                             32, stream);
+    else
+      rc = phc_bn_act_drop_skip_fwd(L->y1, L->gamma1, L->beta1, L->use_bn1 ? L->running_mean1 : nullptr,
+                                    L->use_bn1 ? L->running_var1 : nullptr, (L->use_bn1 && L->training) ? L->tracked1 : nullptr,
+                                    L->n_tracked1, nullptr, N, F, n, L->use_bn1, L->training, L->momentum1, L->eps1, L->act1, 0.f, 0, 0ull,
+                                    L->a1, L->use_bn1 ? L->stats1 : nullptr, L->use_bn1 ? L->stats1 + F : nullptr, L->ws, L->ws_bytes, stream);
     if (rc) return rc;
-    rc = phc_phm_linear_fwd(L->a1, L->rule2, L->W2, L->b2, nullptr, L->z, N, F, F, n, PHC_ACT_IDENTITY, L->precision, L->ws_lin2,
-                            L->ws_lin2_bytes, stream);
-  } else {
-    rc = phc_phm_linear_fwd(L->agg, L->rule1, L->W1, L->b1, L->self_loops ? L->x : nullptr, L->z, N, F, F, n, PHC_ACT_IDENTITY, L->precision,
-                            L->ws_lin1, L->ws_lin1_bytes, stream);
   }
+  const bool want2 = L->use_bn2 && L->training && part_fits;
+  if (L->mlp)
+    rc = phc_phm_linear_fwd_bnstats(L->a1, L->rule2, L->W2, L->b2, nullptr, L->z, N, F, F, n, PHC_ACT_IDENTITY, L->precision, L->ws_lin2,
+                                    L->ws_lin2_bytes, want2 ? part : nullptr, &got2, stream);
+  else
+    rc = phc_phm_linear_fwd_bnstats(L->agg, L->rule1, L->W1, L->b1, L->self_loops ? L->x : nullptr, L->z, N, F, F, n, PHC_ACT_IDENTITY,
+                                    L->precision, L->ws_lin1, L->ws_lin1_bytes, want2 ? part : nullptr, &got2, stream);
   if (rc) return rc;
   // 5. norm -> act -> dropout -> + skip
+  if (got2)
+    return phc_bn_act_drop_skip_fwd_partials(L->z, L->gamma2, L->beta2, L->running_mean2, L->running_var2, L->tracked2, L->n_tracked2, L->skip, N,
+                                             F, n, 1, L->momentum2, L->eps2, L->act2, L->drop_p, L->drop_same, L->seed, L->out, L->stats2,
+                                             L->stats2 + F, part, 32, stream);
   return phc_bn_act_drop_skip_fwd(L->z, L->gamma2, L->beta2, L->use_bn2 ? L->running_mean2 : nullptr, L->use_bn2 ? L->running_var2 : nullptr,
                                   (L->use_bn2 && L->training) ? L->tracked2 : nullptr, L->n_tracked2, L->skip, N, F, n, L->use_bn2, L->training,
                                   L->momentum2, L->eps2, L->act2, L->drop_p, L->drop_same, L->seed, L->out, L->use_bn2 ? L->stats2 : nullptr,

@@ -455,11 +455,39 @@ extern "C" {
 
 size_t phc_bn_workspace_bytes(int rows, int width) { return sizeof(float) * 2 * ((size_t)phc_div_up(rows, BN_MIN_ROWS) + 1) * width + 16; }
 
+static int bn_fwd_impl(const float* h, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                       long long* num_batches_tracked, int n_tracked, const float* skip, int rows, int width, int phm_dim,
+                       int use_bn, int training, float momentum, float eps, int act, float drop_p, int drop_same,
+                       unsigned long long seed, float* y, float* save_mean, float* save_rstd, void* workspace,
+                       size_t workspace_bytes, const float* pre_partials, int pre_chunk_rows, cudaStream_t stream);
+
 int phc_bn_act_drop_skip_fwd(const float* h, const float* gamma, const float* beta, float* running_mean, float* running_var,
                              long long* num_batches_tracked, int n_tracked, const float* skip, int rows, int width, int phm_dim,
                              int use_bn, int training, float momentum, float eps, int act, float drop_p, int drop_same,
                              unsigned long long seed, float* y, float* save_mean, float* save_rstd, void* workspace,
                              size_t workspace_bytes, cudaStream_t stream) {
+  return bn_fwd_impl(h, gamma, beta, running_mean, running_var, num_batches_tracked, n_tracked, skip, rows, width, phm_dim, use_bn, training,
+                     momentum, eps, act, drop_p, drop_same, seed, y, save_mean, save_rstd, workspace, workspace_bytes, nullptr, 0, stream);
+}
+
+int phc_bn_act_drop_skip_fwd_partials(const float* h, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                      long long* num_batches_tracked, int n_tracked, const float* skip, int rows, int width, int phm_dim,
+                                      int training, float momentum, float eps, int act, float drop_p, int drop_same,
+                                      unsigned long long seed, float* y, float* save_mean, float* save_rstd, const float* partials,
+                                      int chunk_rows, cudaStream_t stream) {
+  PHC_REQUIRE(partials != nullptr && chunk_rows > 0, "phc_bn_act_drop_skip_fwd_partials: partials / chunk_rows required");
+  PHC_REQUIRE(training, "phc_bn_act_drop_skip_fwd_partials: batch statistics are only used in training mode");
+  return bn_fwd_impl(h, gamma, beta, running_mean, running_var, num_batches_tracked, n_tracked, skip, rows, width, phm_dim, 1, 1, momentum,
+                     eps, act, drop_p, drop_same, seed, y, save_mean, save_rstd, nullptr, 0, partials, chunk_rows, stream);
+}
+
+}  // extern "C"
+
+static int bn_fwd_impl(const float* h, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                       long long* num_batches_tracked, int n_tracked, const float* skip, int rows, int width, int phm_dim,
+                       int use_bn, int training, float momentum, float eps, int act, float drop_p, int drop_same,
+                       unsigned long long seed, float* y, float* save_mean, float* save_rstd, void* workspace,
+                       size_t workspace_bytes, const float* pre_partials, int pre_chunk_rows, cudaStream_t stream) {
   PHC_REQUIRE(width > 0 && phm_dim > 0 && width % phm_dim == 0, "phc_bn_act_drop_skip_fwd: width %d not divisible by phm_dim %d", width, phm_dim);
   PHC_REQUIRE(act >= PHC_ACT_IDENTITY && act <= PHC_ACT_SWISH, "phc_bn_act_drop_skip_fwd: bad act %d", act);
   PHC_REQUIRE(drop_p >= 0.f && drop_p <= 1.f, "phc_bn_act_drop_skip_fwd: dropout rate %f outside [0,1]", drop_p);
@@ -468,7 +496,13 @@ int phc_bn_act_drop_skip_fwd(const float* h, const float* gamma, const float* be
   const int M = rows, F = width;
   if (use_bn) {
     PHC_REQUIRE(save_mean && save_rstd, "phc_bn_act_drop_skip_fwd: save_mean/save_rstd required with batch-norm");
-    if (training) {
+    if (training && pre_partials != nullptr) {
+      // chunk moments already produced by the kernel that wrote h (PHMLinear epilogue): only merge them
+      PHC_REQUIRE(M > 1, "phc_bn_act_drop_skip_fwd: batch-norm in training mode needs more than 1 row");
+      phc_launch(bn_finalize_kernel, dim3(phc_div_up((long long)F * 32, 256)), dim3(256), 0, stream, pre_partials,
+                 phc_div_up(M, pre_chunk_rows), pre_chunk_rows, M, F, eps, momentum, running_mean, running_var, save_mean, save_rstd,
+                 num_batches_tracked, n_tracked);
+    } else if (training) {
       PHC_REQUIRE(M > 1, "phc_bn_act_drop_skip_fwd: batch-norm in training mode needs more than 1 row");
       PHC_REQUIRE(workspace_bytes >= phc_bn_workspace_bytes(M, F), "phc_bn_act_drop_skip_fwd: workspace too small");
       float* part = reinterpret_cast<float*>(workspace);
@@ -495,6 +529,8 @@ int phc_bn_act_drop_skip_fwd(const float* h, const float* gamma, const float* be
   BN_DISPATCH(bn_apply_fwd_kernel, v4, p, grid, stream, p, h, gamma, beta, save_mean, save_rstd, skip, y);
   return phc_check_launch("phc_bn_act_drop_skip_fwd");
 }
+
+extern "C" {
 
 int phc_bn_act_drop_skip_bwd(const float* dy, const float* h, const float* gamma, const float* beta, const float* save_mean,
                              const float* save_rstd, int rows, int width, int phm_dim, int use_bn, int training, int act, float drop_p,

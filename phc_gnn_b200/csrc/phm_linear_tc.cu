@@ -77,6 +77,8 @@ struct MixParams {          // y = act(mix GEMM + bias) + residual   (FWD and DX
   int M, n, Kin, Pout, S, chunks, ptiles, act, num_tiles;
   int single;               // 1: "bf16" mode — operands rounded to bf16, one tensor-core pass (no big/small split)
   long long* prof;          // optional per-CTA role timers (debug), 8 slots per CTA
+  float* stat_part;         // v3: optional [ceil(M/32)][2][n*Pout] per-32-row-chunk column moments of the OUTPUT (chunk mean, chunk
+                            //     M2) for a batch-norm that follows (norm.cu merges them) — the drain owns one column per lane anyway
   float* sk_part;           // v3 stream-K: per-CTA partial accumulators [grid][16 warps][32 rows][64 cols] (NULL: whole units only)
   unsigned int* sk_flags;   // v3 stream-K: [grid][16] "partial written" flags, zero between launches
 };
@@ -787,9 +789,12 @@ __device__ __forceinline__ void v3_unit(const MixParams& p, int u, int& m0, int&
 // its LAST chunks processes them first and parks the partial accumulators in global memory (16 warp regions + flags); the
 // CTA holding its FIRST chunks processes them last, adds the partial (long since written) and stores the result.  The
 // split points and the order of the addition are fixed: results are reproducible run to run.
+#ifndef PHC_TC_STREAM_K
+#define PHC_TC_STREAM_K 0      // compile-time: the split costs registers in the producers' hot loop even when it is not used
+#endif
 struct V3Seg { int u, c0, c1; };
 __device__ __forceinline__ int v3_range(const MixParams& p, long long& gb, long long& ge) {
-  if (p.sk_part != nullptr) {
+  if (PHC_TC_STREAM_K && p.sk_part != nullptr) {
     const long long G = (long long)p.num_tiles * p.chunks;
     gb = G * blockIdx.x / gridDim.x;
     ge = G * (blockIdx.x + 1) / gridDim.x;
@@ -819,9 +824,11 @@ __device__ __forceinline__ void st_release_u32(unsigned int* ptr, unsigned int v
 // One warp drains 32 rows x 64 columns of an accumulator, 16 columns per pass: TMEM -> registers -> smem transpose ->
 // row stores (each half warp writes 64 contiguous bytes of one row; the component offset c*P makes rows only 4-byte aligned).
 // mode 0: whole unit; 1: park the partial accumulators in `part` and raise `flag`; 2: add the partner's partial first
+template <bool STATS>
 __device__ __forceinline__ void v3_drain(float* __restrict__ my, uint32_t taddr, float* __restrict__ C, int ldc, int nrows, int r0,
                                          int col0, int ncols, const float* __restrict__ bias, const float* __restrict__ residual, int act,
-                                         int mode, float* __restrict__ part, unsigned int* __restrict__ flag) {
+                                         int mode, float* __restrict__ part, unsigned int* __restrict__ flag,
+                                         float* __restrict__ stat) {
   const int lane = threadIdx.x & 31;
   const int rsel = lane >> 4, lc16 = lane & 15;
   const bool plain = act == PHC_ACT_IDENTITY && residual == nullptr;
@@ -864,11 +871,47 @@ __device__ __forceinline__ void v3_drain(float* __restrict__ my, uint32_t taddr,
           make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
     __syncwarp();
     const int lc = cc * 16 + lc16;
-    if (lc < ncols) {
-      const int col = col0 + lc;
-      const float bv = bias != nullptr ? __ldg(bias + col) : 0.f;
-      float* dst = C + (size_t)r0 * ldc + col;
-      const float* src = my + lc16;
+    const bool on = lc < ncols;
+    const int col = col0 + lc;
+    const float bv = (on && bias != nullptr) ? __ldg(bias + col) : 0.f;
+    float* dst = C + (size_t)r0 * ldc + col;
+    const float* src = my + lc16;
+    if (STATS) {
+      // batch-norm statistics of the stored values for free: shifted moments of this warp's 32-row chunk (shift = the
+      // chunk's first row); the two half warps hold the even / odd rows of a column and are combined by one shuffle
+      const float* res = residual != nullptr ? residual + (size_t)r0 * ldc + col : nullptr;
+      float sh = 0.f, s1 = 0.f, s2 = 0.f;
+      if (on && plain && nrows == 32) {                            // the common case, fully unrolled
+        sh = src[0] + bv;
+#pragma unroll
+        for (int rr = 0; rr < 16; ++rr) {
+          const float o = src[(2 * rr + rsel) * V3_SPITCH] + bv;
+          dst[(2 * rr + rsel) * ldc] = o;
+          const float d = o - sh;
+          s1 += d;
+          s2 = fmaf(d, d, s2);
+        }
+      } else if (on) {
+        sh = act_fwd_rt(act, src[0] + bv);
+        if (res != nullptr) sh += res[0];
+        for (int rr = rsel; rr < nrows; rr += 2) {
+          float o = act_fwd_rt(act, src[rr * V3_SPITCH] + bv);
+          if (res != nullptr) o += res[rr * ldc];
+          dst[rr * ldc] = o;
+          const float d = o - sh;
+          s1 += d;
+          s2 += d * d;
+        }
+      }
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+      if (on && rsel == 0) {
+        const float cnt = (float)nrows;
+        float* sp = stat + ((size_t)(r0 >> 5) * 2) * ldc + col;
+        sp[0] = sh + s1 / cnt;
+        sp[ldc] = fmaxf(s2 - s1 * s1 / cnt, 0.f);
+      }
+    } else if (on) {
       if (plain && nrows == 32) {
 #pragma unroll
         for (int rr = 0; rr < 16; ++rr) dst[(2 * rr + rsel) * ldc] = src[(2 * rr + rsel) * V3_SPITCH] + bv;
@@ -896,7 +939,7 @@ __device__ __forceinline__ void v3_drain(float* __restrict__ my, uint32_t taddr,
 }
 
 // R = Kin & 3: component uu's box starts (uu*R)&3 floats before its first needed float (TMA boxes start 16-byte aligned)
-template <int R, bool SINGLE>
+template <int R, bool SINGLE, bool STATS>
 __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixParams p, const __grid_constant__ CUtensorMap tmapX) {
   pdl_begin();
   constexpr int NT = 4, KQ = BK / NT;                       // 8 k values per chunk
@@ -1041,13 +1084,13 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
       const int r0 = m0 + q * 32;
       // split unit: its last chunks (c0 > 0) are parked in this CTA's slot; its first chunks (c1 < chunks) belong to the
       // owner, which adds the partial parked by the NEXT CTA (whose first segment is the rest of this unit)
-      const int mode = sg.c0 > 0 ? 1 : (sg.c1 < p.chunks ? 2 : 0);
+      const int mode = PHC_TC_STREAM_K ? (sg.c0 > 0 ? 1 : (sg.c1 < p.chunks ? 2 : 0)) : 0;
       const int slot = (int)blockIdx.x + (mode == 2 ? 1 : 0);
       if (ncols > 0 && r0 < p.M)
-        v3_drain(my, tmem_base + lane_base + (uint32_t)(h * BN + g * 64), p.C, ldc, min(32, p.M - r0), r0,
+        v3_drain<STATS>(my, tmem_base + lane_base + (uint32_t)(h * BN + g * 64), p.C, ldc, min(32, p.M - r0), r0,
                  (2 * pair + h) * p.Pout + pt * BN + g * 64, ncols, p.bias, p.residual, p.act, mode,
                  mode ? p.sk_part + ((size_t)slot * PROD_WARPS + warp) * (32 * 64) : nullptr,
-                 mode ? p.sk_flags + slot * PROD_WARPS + warp : nullptr);
+                 mode ? p.sk_flags + slot * PROD_WARPS + warp : nullptr, p.stat_part);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(tempty));
@@ -1442,9 +1485,10 @@ size_t smem_bytes(int coef_floats) {
 
 // Stream-K split of the n = 4 mix kernel's unit list (v3_range): balances the CTAs (244 units on 148 CTAs at ppa shape) but
 // every split unit costs two extra accumulator drains (park + add), and the drain is not overlapped with the MMAs because
-// tensor memory is full.  Measured on B200 at ppa shape: 61.7 us with the split against 50.1 us without — opt-in only.
+// tensor memory is full.  Measured on B200 at ppa shape: 61.7 us with the split against 50.1 us without — opt-in only
+// (build with -DPHC_TC_STREAM_K=1 and set PHC_TC_STREAM_K=1 in the environment).
 bool stream_k_enabled() {
-  static const bool on = getenv("PHC_TC_STREAM_K") != nullptr;
+  static const bool on = PHC_TC_STREAM_K && getenv("PHC_TC_STREAM_K") != nullptr;
   return on;
 }
 
@@ -1520,7 +1564,7 @@ int launch_mix_nt(const MixParams& p, cudaStream_t stream) {
   return phc_check_launch("phm_tc_mix_kernel");
 }
 
-int launch_mix(const MixParams& p, cudaStream_t stream);
+int launch_mix(const MixParams& p, cudaStream_t stream, int* v3_used = nullptr);
 int launch_mix_v2(const MixParams& p, cudaStream_t stream) {
   switch (p.n) {
     case 1: return launch_mix_nt<1>(p, stream);
@@ -1594,11 +1638,11 @@ size_t smem_bytes_v3() {
   return 1024 + (size_t)V3_NB * 2 * TILE_BYTES + (size_t)V3_NRAW * V3_RAW_BYTES + V3_SCRATCH + sizeof(float) * 64 + 8 * V3_BARS + 16;
 }
 
-template <int R, bool SINGLE>
+template <int R, bool SINGLE, bool STATS>
 int launch_mix_v3_rs(const MixParams& p, const CUtensorMap& tmap, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(phm_tc_mix_v3_kernel<R, SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_v3());
+    cudaError_t e = cudaFuncSetAttribute(phm_tc_mix_v3_kernel<R, SINGLE, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_v3());
     if (e != cudaSuccess) {
       phc_set_error("phm_tc: cannot reserve %zu bytes of shared memory: %s", smem_bytes_v3(), cudaGetErrorString(e));
       return PHC_ERR_CUDA;
@@ -1608,13 +1652,15 @@ int launch_mix_v3_rs(const MixParams& p, const CUtensorMap& tmap, cudaStream_t s
   MixParams q = p;
   q.num_tiles = phc_div_up(p.M, BM) * 2 * p.ptiles;           // units: (m-tile, p-tile, component pair)
   const int grid = q.num_tiles < num_sms() ? q.num_tiles : num_sms();
-  phc_launch(phm_tc_mix_v3_kernel<R, SINGLE>, dim3(grid), dim3(V3_THREADS), smem_bytes_v3(), stream, q, tmap);
+  phc_launch(phm_tc_mix_v3_kernel<R, SINGLE, STATS>, dim3(grid), dim3(V3_THREADS), smem_bytes_v3(), stream, q, tmap);
   return phc_check_launch("phm_tc_mix_v3_kernel");
 }
 
 template <int R>
 int launch_mix_v3_r(const MixParams& p, const CUtensorMap& tmap, cudaStream_t stream) {
-  return p.single ? launch_mix_v3_rs<R, true>(p, tmap, stream) : launch_mix_v3_rs<R, false>(p, tmap, stream);
+  if (p.stat_part != nullptr)
+    return p.single ? launch_mix_v3_rs<R, true, true>(p, tmap, stream) : launch_mix_v3_rs<R, false, true>(p, tmap, stream);
+  return p.single ? launch_mix_v3_rs<R, true, false>(p, tmap, stream) : launch_mix_v3_rs<R, false, false>(p, tmap, stream);
 }
 
 // TMEM-operand path: n == 4, 16-byte aligned rows.  Returns -1 when not applicable (caller falls back).
@@ -1689,11 +1735,15 @@ int try_launch_dh_tma(const DhParams& d, cudaStream_t stream) {
   return phc_check_launch("phm_tc_dh_tma_kernel");
 }
 
-int launch_mix(const MixParams& p, cudaStream_t stream) {
+int launch_mix(const MixParams& p, cudaStream_t stream, int* v3_used) {
   static const bool use_tma = getenv("PHC_TC_NO_TMA") == nullptr;       // debug switch: force the register-prefetch kernel
+  if (v3_used) *v3_used = 0;
   if (use_tma) {
     int rc = try_launch_mix_v3(p, stream);
-    if (rc >= 0) return rc;
+    if (rc >= 0) {
+      if (v3_used) *v3_used = rc == 0;
+      return rc;
+    }
     rc = p.prof == nullptr ? try_launch_mix_tma(p, stream) : -1;
     if (rc >= 0) return rc;
   }
@@ -1722,7 +1772,8 @@ size_t phm_tc_bwd_workspace_bytes(int rows, int in_features, int out_features, i
 static uint8_t* align1k(void* p) { return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023); }
 
 int phm_tc_fwd(const float* x, const float* A, const float* W, const float* bias, const float* residual, float* y, int rows,
-               int in_features, int out_features, int phm_dim, int act, int precision, void* workspace, cudaStream_t stream) {
+               int in_features, int out_features, int phm_dim, int act, int precision, void* workspace, float* bn_partials,
+               int* bn_produced, cudaStream_t stream) {
   const int n = phm_dim, K = in_features / n, P = out_features / n;
   const int single = precision == 2;
   uint8_t* buf = align1k(workspace);
@@ -1740,7 +1791,11 @@ int phm_tc_fwd(const float* x, const float* A, const float* W, const float* bias
     p.sk_part = reinterpret_cast<float*>(buf + L.sk_part);
     p.sk_flags = reinterpret_cast<unsigned int*>(buf + L.sk_flags);
   }
-  return tc::launch_mix(p, stream);
+  p.stat_part = bn_partials;
+  int v3 = 0;
+  rc = tc::launch_mix(p, stream, &v3);
+  if (bn_produced) *bn_produced = (v3 && bn_partials != nullptr) ? 1 : 0;
+  return rc;
 }
 
 int phm_tc_bwd(const float* gy, const float* x, const float* A, const float* W, float* dx, float* dA, float* dW, float* db, int rows,

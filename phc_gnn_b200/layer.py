@@ -311,7 +311,9 @@ def _call_fwd(cfg, struct: EdgeStructure, flats, x, skip, attr, tensors):
     if mlp:
         D.ws_lin2, D.ws_lin2_bytes = ws_lin.data_ptr() + nb_lin, nb_lin
     D.ws, D.ws_bytes = ws.data_ptr(), ws.numel()
-    run("phc_conv_layer_fwd", None, ctypes.byref(D), st, launches=11 if mlp else 6)
+    fused_stats = precision != 0 and n == 4 and training        # batch-norm statistics come out of the PHMLinear epilogue
+    run("phc_conv_layer_fwd", None, ctypes.byref(D), st,
+        launches=(11 if mlp else 6) - ((int(use_bn1 and mlp) + int(use_bn2)) if fused_stats else 0))
     return out, (acts, stats, aux_f, aux_i), (D, vc, encp, ws_lin)
 
 

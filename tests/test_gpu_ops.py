@@ -401,3 +401,56 @@ def test_conv_aggregate_with_fused_encoder(reduce, act, linear, F, n):
         assert_close(v.grad.cpu(), po["e." + k].grad.float(), 2e-4, grad_tol(po["e." + k].grad, 2e-4), k)
     if reduce == "softmax":
         assert_close(bs.grad.cpu(), bo.grad.float(), 1e-3, grad_tol(bo.grad, 1e-3), "dbeta")
+
+
+@pytest.mark.parametrize("fin,fout,M,residual", [(500, 500, 1000, False), (256, 256, 4099, True), (200, 200, 333, False)])
+def test_phm_linear_epilogue_batch_norm_statistics(fin, fout, M, residual):
+    """phc_phm_linear_fwd_bnstats: the tensor-core epilogue's per-32-row chunk moments, merged by
+    phc_bn_act_drop_skip_fwd_partials, give the batch-norm of the separate stats kernel."""
+    import ctypes
+    from phc_gnn_b200 import _lib
+    from phc_gnn_b200.graph import _stream
+    from phc_gnn_b200.ops import run
+    lib = _lib.load()
+    n = 4
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(M, fin, generator=g).to(DEV)
+    A = torch.randn(n, n, n, generator=g).to(DEV)
+    W = (torch.randn(n, fin // n, fout // n, generator=g) * 0.1).to(DEV)
+    b = torch.randn(fout, generator=g).to(DEV)
+    res = torch.randn(M, fout, generator=g).to(DEV) if residual else None
+    gamma = torch.rand(fout, generator=g).to(DEV) + 0.5
+    beta = torch.randn(fout, generator=g).to(DEV)
+    st = _stream(torch.device(DEV))
+    y = torch.empty(M, fout, device=DEV)
+    nb = lib.phc_phm_linear_fwd_workspace_bytes(M, fin, fout, n, 1)
+    ws = torch.empty(nb, dtype=torch.uint8, device=DEV)
+    part = torch.full(((M + 31) // 32, 2, fout), float("nan"), device=DEV)
+    produced = ctypes.c_int(0)
+    run("phc_phm_linear_fwd_bnstats", None, x.data_ptr(), A.data_ptr(), W.data_ptr(), b.data_ptr(), 0 if res is None else res.data_ptr(),
+        y.data_ptr(), M, fin, fout, n, 0, 1, ws.data_ptr(), ws.numel(), part.data_ptr(), ctypes.addressof(produced), st)
+    torch.cuda.synchronize()
+    assert produced.value == 1, "the n = 4 tensor-core path did not report batch-norm partials"
+    assert torch.isfinite(part).all()
+    outs = []
+    for use_partials in (True, False):
+        rm, rv = torch.zeros(fout, device=DEV), torch.ones(fout, device=DEV)
+        tracked = torch.zeros(n, dtype=torch.int64, device=DEV)
+        o = torch.empty_like(y)
+        mean, rstd = torch.empty(fout, device=DEV), torch.empty(fout, device=DEV)
+        if use_partials:
+            run("phc_bn_act_drop_skip_fwd_partials", None, y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), rm.data_ptr(), rv.data_ptr(),
+                tracked.data_ptr(), n, 0, M, fout, n, 1, 0.1, 1e-5, 1, 0.0, 0, 0, o.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                part.data_ptr(), 32, st)
+        else:
+            w2 = torch.empty(lib.phc_bn_workspace_bytes(M, fout), dtype=torch.uint8, device=DEV)
+            run("phc_bn_act_drop_skip_fwd", None, y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), rm.data_ptr(), rv.data_ptr(),
+                tracked.data_ptr(), n, 0, M, fout, n, 1, 1, 0.1, 1e-5, 1, 0.0, 0, 0, o.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                w2.data_ptr(), w2.numel(), st)
+        torch.cuda.synchronize()
+        outs.append((o.cpu(), mean.cpu(), rstd.cpu(), rm.cpu(), rv.cpu(), tracked.cpu()))
+    for a, c, what in zip(outs[0], outs[1], ("y", "mean", "rstd", "running_mean", "running_var", "tracked")):
+        assert_close(a.float(), c.float(), 1e-5, 1e-5, what)
+    y64 = y.double().cpu()
+    assert_close(outs[0][1].double(), y64.mean(0), 1e-5, 1e-6, "mean vs fp64")
+    assert_close(outs[0][2].double(), 1.0 / torch.sqrt(y64.var(0, unbiased=False) + 1e-5), 1e-4, 1e-6, "rstd vs fp64")
