@@ -65,6 +65,18 @@ int phc_csr_build(const long long* edge_index, int num_edges, int num_nodes, int
 int phc_segment_ptr_build(const long long* batch, int num_nodes, int num_graphs, int* graph_ptr, int* status, phc_stream_t stream);
 int phc_narrow_int64(const long long* in, int n, int* out, phc_stream_t stream);
 
+/* ---- batch preparation: RemoveIsolatedNodes (train_hiv.py:171-173 `data = transform(data)`, :457; benchmarks/utils.py:39-49;
+ * arithmetic in torch_geometric 1.6.1 utils/isolated.py remove_isolated_nodes, restated in oracle/phc_oracle.py) ------------
+ * keep_mask[N] (bytes): node is an endpoint of a non-self-loop edge; assoc[N]: new id or -1; new_edge_index: int64 [2,E]
+ * buffer (row stride E) holding the relabelled non-loop edges in original order followed by one self loop per kept node
+ * that has any (ascending node id, last such edge wins); edge_order[E]: source edge id of every output edge (to gather
+ * edge_attr); counts: DEVICE int[4] = kept nodes, kept non-loop edges, kept self loops, status (bit0 index out of range).
+ * Bit-exact with the CPU restatement. */
+size_t phc_isolated_workspace_bytes(int num_nodes, int num_edges);
+int phc_remove_isolated_nodes(const long long* edge_index, int num_edges, int num_nodes, unsigned char* keep_mask, long long* assoc,
+                              long long* new_edge_index, long long* edge_order, int* counts, void* workspace, size_t workspace_bytes,
+                              phc_stream_t stream);
+
 /* ---- fused neighbour aggregation (messagepassing.py:72-74,136-138,297-300) -------------------
  * out[i] = (self_loop ? x[i] : 0) + AGG_{e: dst(e)=i} act(x[src(e)] + ea[e])
  * aux_f: [2,N,F] (softmax only: log-sum-exp and aggregate), aux_i: [N,F] (max/min only: winning edge id).

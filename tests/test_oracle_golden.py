@@ -75,3 +75,17 @@ def test_structure_oracle_small():
     assert perm.tolist() == [1, 0, 2, 5, 4, 3]
     assert col.tolist() == [1, 0, 2, 0, 3, 2]
     assert O.graph_ptr(torch.tensor([0, 0, 2, 2, 2]), 4).tolist() == [0, 2, 2, 5, 5]
+
+
+def test_remove_isolated_nodes_known_answer():
+    """Hand-worked example of torch_geometric 1.6.1 remove_isolated_nodes (documented behaviour: nodes without a non-loop
+    edge are dropped together with their self loops; surviving self loops move behind the other edges)."""
+    import torch
+    from oracle import phc_oracle as O
+    #           0->1  2->2  1->0  1->1  3->3  4->1
+    ei = torch.tensor([[0, 2, 1, 1, 3, 4], [1, 2, 0, 1, 3, 1]])
+    attr = torch.arange(6).view(6, 1)
+    out, ea, mask = O.remove_isolated_nodes(ei, attr, 6)
+    assert mask.tolist() == [True, True, False, False, True, False]
+    assert out.tolist() == [[0, 1, 2, 1], [1, 0, 1, 1]]          # node 4 -> id 2; self loop of node 1 last
+    assert ea.view(-1).tolist() == [0, 2, 5, 3]
