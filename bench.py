@@ -169,8 +169,8 @@ def cpu_baseline(wl, budget_s: float = 25.0):
 
 
 # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the aggregation forward kernel from the
-# committed ncu --set full capture of this same command (profiles/r01_fused_conv_and_tc_kernels_ncu.txt)
-NCU_TRAFFIC_BYTES = {"ppa": 41.93e6 + 5.19e6}
+# committed ncu --set full capture of this same command (profiles/r01_conv_fwd_ppa_ncu_full.txt)
+NCU_TRAFFIC_BYTES = {"ppa": 42.00e6 + 7.48e6}
 
 
 def aggregation_bytes(N, E, F, softmax):

@@ -341,19 +341,27 @@ __global__ void conv_bwd_param_kernel(const EncDesc enc, const float* __restrict
   }
 }
 
-// sum block partials (lane l takes blocks l, l+32, ... in order, then a fixed butterfly) and scatter into the
-// individual parameter gradients; one warp per table element
-__global__ void __launch_bounds__(256) conv_bwd_param_final_kernel(const EncDesc enc, const float* __restrict__ part, int blocks, int F) {
+// sum block partials and scatter into the individual parameter gradients.  Block = 32 consecutive table elements (lanes,
+// coalesced 128-byte reads of part[b][r][f..f+31]) x 32 slices of the partial list (slice s takes blocks s, s+32, ... in
+// order); the 32 slice sums are then added in slice order — a fixed association, hence deterministic.
+__global__ void __launch_bounds__(1024) conv_bwd_param_final_kernel(const EncDesc enc, const float* __restrict__ part, int blocks, int F) {
   pdl_begin();
-  const long long t = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (t >= (long long)enc.R * F) return;
-  const int r = (int)(t / F), f = (int)(t - (long long)r * F);
+  __shared__ float red[32][33];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const long long total = (long long)enc.R * F;
+  const long long t = (long long)blockIdx.x * 32 + lane;
   float s = 0.f;
-  for (int b = lane; b < blocks; b += 32) s += part[((size_t)b * enc.R + r) * F + f];
+  if (t < total) {
+#pragma unroll 4
+    for (int b = slice; b < blocks; b += 32) s += part[(size_t)b * total + t];
+  }
+  red[slice][lane] = s;
+  __syncthreads();
+  if (slice != 0 || t >= total) return;
+  s = 0.f;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane != 0) return;
+  for (int q = 0; q < 32; ++q) s += red[q][lane];
+  const int r = (int)(t / F), f = (int)(t - (long long)r * F);
   const int c = f / enc.Fc, fp = f - c * enc.Fc;
   if (enc.kind == ENC_LINEAR) {
     if (r < enc.D) enc.dp[c][(size_t)fp * enc.D + r] = s;
@@ -626,7 +634,7 @@ int phc_conv_fused_bwd(const float* gout, const float* x, const void* edge_attr,
       PHC_CASE(9) PHC_CASE(10) PHC_CASE(11) PHC_CASE(12) PHC_CASE(13) PHC_CASE(14) PHC_CASE(15) PHC_CASE(16)
 #undef PHC_CASE
     }
-    phc_launch(conv_bwd_param_final_kernel, dim3(phc_div_up((long long)d.R * F * 32, 256)), dim3(256), 0, stream, d, part, nb, F);
+    phc_launch(conv_bwd_param_final_kernel, dim3(phc_div_up((long long)d.R * F, 32)), dim3(1024), 0, stream, d, part, nb, F);
     int rc = phc_check_launch("phc_conv_fused_bwd(node sums)");
     if (rc) return rc;
     if (dx) return phc_aggregate_bwd_node_simple(reduce == PHC_RED_MEAN, gout, rowptr, rowptr_t, col_t, perm_t, N, F, self_loop, dx, stream);
@@ -656,7 +664,7 @@ int phc_conv_fused_bwd(const float* gout, const float* x, const void* edge_attr,
 #undef PHC_LAUNCH
 #undef PHC_PARAM
   const int blocks_used = N > 0 ? g.blocks : 0;
-  phc_launch(conv_bwd_param_final_kernel, dim3(phc_div_up((long long)d.R * F * 32, 256)), dim3(256), 0, stream, d, part, blocks_used, F);
+  phc_launch(conv_bwd_param_final_kernel, dim3(phc_div_up((long long)d.R * F, 32)), dim3(1024), 0, stream, d, part, blocks_used, F);
   if (reduce == PHC_RED_SOFTMAX && dbeta) phc_launch(sum_partials_kernel, dim3(1), dim3(256), 0, stream, dbp, blocks_used, dbeta);
   int rc = phc_check_launch("phc_conv_fused_bwd");
   if (rc) return rc;

@@ -129,11 +129,20 @@ class NaivePHMNorm(nn.Module):
     def __getstate__(self):          # flat caches are re-derived after unpickling
         d = dict(self.__dict__)
         d["_flat"] = [None] * 5
+        d.pop("_flat_cache", None)
         return d
 
     def flat_views(self):
         """(gamma, beta, running_mean, running_var, num_batches_tracked) flat vectors aliasing the
         n BatchNorm1d modules' tensors."""
+        # hot path: the modules' tensors still sit where the cached flat vectors alias them (checked on the first tensor
+        # of each kind; a module is moved / re-initialised as a whole)
+        b0 = self.bn[0]
+        key = (b0.weight.data_ptr() if self.affine else 0, b0.bias.data_ptr() if self.affine else 0,
+               b0.running_mean.data_ptr() if self.track_running_stats else 0)
+        cached = self.__dict__.get("_flat_cache")
+        if cached is not None and cached[0] == key:
+            return cached[1]
         groups = []
         if self.affine:
             groups += [[m.weight for m in self.bn], [m.bias for m in self.bn]]
@@ -145,8 +154,13 @@ class NaivePHMNorm(nn.Module):
         else:
             groups += [None, None, None]
         for i, g in enumerate(groups):
-            self._flat[i] = alias_flat(self._flat[i], g, quick=True) if g is not None else None
-        return tuple(self._flat)
+            self._flat[i] = alias_flat(self._flat[i], g) if g is not None else None
+        out = tuple(self._flat)
+        b0 = self.bn[0]                  # alias_flat may have re-pointed the tensors: key on the final addresses
+        key = (b0.weight.data_ptr() if self.affine else 0, b0.bias.data_ptr() if self.affine else 0,
+               b0.running_mean.data_ptr() if self.track_running_stats else 0)
+        self.__dict__["_flat_cache"] = (key, out)
+        return out
 
     def autograd_params(self):
         return ([m.weight for m in self.bn] + [m.bias for m in self.bn]) if self.affine else []
