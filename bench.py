@@ -363,7 +363,8 @@ def run_b200(args):
             roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": NCU_TRAFFIC_BYTES.get(wl.name) if fused else None,
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": byt, "avg_launch_us": us,
-                    "share_of_step": agg_ms / ms_instr, "timed": "CUDA events around each launch, instrumented repeat of the K steps"}
+                    "share_of_step": agg_ms / ms,      # of the headline (uninstrumented) step; the instrumented repeat is slower
+                    "timed": "CUDA events around each launch, instrumented repeat of the K steps"}
             if fused:
                 dims = wl.model["bond_input_dims"]
                 attr_b = (4 * dims if isinstance(dims, int) else 8 * len(dims)) * E
