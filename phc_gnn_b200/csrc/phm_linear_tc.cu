@@ -1430,6 +1430,260 @@ __global__ void __launch_bounds__(DH_TMA_THREADS, 1) phm_tc_dh_tma_kernel(const 
   cta_epilogue(tmem_base);
 }
 
+// ---------------------------------------------------------------------------- dH kernel v2: x^T operand in TENSOR MEMORY,
+// two dy tiles per x tile.
+// The TMA-staged kernel above sits at its SHARED-MEMORY roofline: both operands are transposed through shared memory
+// (per 32-sample chunk: 32 KiB TMA in, 32 KiB read, 64 KiB operand tiles written, 96 KiB read by the 12 MMAs = 292 B/clk
+// against 128 B/clk).  Here one CTA computes a 128 x 256 block of dH: the x^T operand (tile row = feature = TMEM lane)
+// is written by 128 producer threads straight into tensor memory (tcgen05.st) and serves TWO 128-column dy tiles; only
+// the dy^T operand goes through shared memory: 48 + 48 + 64 + 96 KiB per 24 MMAs = 167 B/clk.  A producer thread owns
+// one feature row, so the transpose is a conflict-free column read of the raw box.
+// (Tried and rejected: loading the operands straight from global memory with a one-chunk register prefetch instead of
+//  TMA staging — 57 us against 45 us, the prefetch is too shallow for DRAM latency.)
+//   warps 0-3 x^T -> TMEM | 4-11 dy^T -> smem (and the column sums of dy: bias gradient) | 12-15 epilogue | 16 MMA | 17 TMA
+//   TMEM: 2 accumulators x 128 columns | 2 chunk parities x (32 big + 32 small) operand columns
+constexpr int DH2_BN = 2 * BN;
+constexpr int DH2_RAW_X = BK * BM * 4, DH2_RAW_G = BK * DH2_BN * 4;      // 16 KiB + 32 KiB per raw stage
+constexpr int DH2_RAW_BYTES = DH2_RAW_X + DH2_RAW_G;
+constexpr int DH2_B_STAGE = 4 * TILE_BYTES;                              // two dy tiles x (big, small) = 64 KiB
+constexpr int DH2_A_WARPS = 4, DH2_B_WARPS = 8, DH2_EPI_WARP0 = 12, DH2_MMA_WARP = 16, DH2_TMA_WARP = 17;
+constexpr int DH2_THREADS = 18 * 32;
+constexpr int DH2_A_COL0 = 2 * BN;
+constexpr int DH2_BARS = 14;
+static_assert(DH2_EPI_WARP0 % 4 == 0, "epilogue warps must be aligned to the TMEM lane quarters");
+
+__device__ __forceinline__ void dh2_tile(const DhParams& p, int t, int& i0, int& o0, int& split, int& kbeg, int& kend) {
+  const int per = p.tiles_m * p.tiles_n;                 // tiles_n counts 256-column tiles here
+  split = t / per;
+  const int r = t % per;
+  i0 = (r / p.tiles_n) * BM;
+  o0 = (r % p.tiles_n) * DH2_BN;
+  kbeg = split * p.rows_per_split;
+  kend = min(kbeg + p.rows_per_split, p.M);
+}
+
+__global__ void __launch_bounds__(DH2_THREADS, 1) phm_tc_dh_v2_kernel(const DhParams p, const __grid_constant__ CUtensorMap tmapX,
+                                                                     const __grid_constant__ CUtensorMap tmapG) {
+  pdl_begin();
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* bstage = base;                                        // [2][tile0 big | tile0 small | tile1 big | tile1 small]
+  uint8_t* rawbuf = base + 2 * DH2_B_STAGE;                      // [2][x box 32x128 | dy box 32x256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rawbuf + 2 * DH2_RAW_BYTES);
+  uint64_t* rfull = bars;           // [2] TMA transaction
+  uint64_t* rempty = bars + 2;      // [2] 12 producer warps
+  uint64_t* afull = bars + 4;       // [2] 4 x^T warps
+  uint64_t* aempty = bars + 6;      // [2] tcgen05.commit
+  uint64_t* bfull = bars + 8;       // [2] 8 dy^T warps
+  uint64_t* bempty = bars + 10;     // [2] tcgen05.commit
+  uint64_t* tfull = bars + 12;
+  uint64_t* tempty = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + DH2_BARS);
+  uint32_t* landed = tmem_slot + 4;                              // [12 producer warps][32]: see the early release below
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&rfull[i]), 1);
+      mbar_init(smem_u32(&rempty[i]), DH2_A_WARPS + DH2_B_WARPS);
+      mbar_init(smem_u32(&afull[i]), DH2_A_WARPS);
+      mbar_init(smem_u32(&aempty[i]), 1);
+      mbar_init(smem_u32(&bfull[i]), DH2_B_WARPS);
+      mbar_init(smem_u32(&bempty[i]), 1);
+    }
+    mbar_init(smem_u32(tfull), 1);
+    mbar_init(smem_u32(tempty), 4 * 32);
+    fence_barrier_init();
+  }
+  if (warp == DH2_MMA_WARP) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < DH2_A_WARPS) {
+    // ===================================================================== x^T -> tensor memory (thread = feature row = lane)
+    const int f = warp * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    int g = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      int i0, o0, split, kbeg, kend;
+      dh2_tile(p, t, i0, o0, split, kbeg, kend);
+      for (int k0 = kbeg; k0 < kend; k0 += BK, ++g) {
+        const int rs = g & 1, ph = (g >> 1) & 1;
+        mbar_wait(smem_u32(&rfull[rs]), ph);
+        const float* raw = reinterpret_cast<const float*>(rawbuf + rs * DH2_RAW_BYTES) + f;
+        float v[BK];
+        uint32_t lor = 0;
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) { v[kk] = raw[kk * BM]; lor |= __float_as_uint(v[kk]); }
+        // Early release: the column is in registers, let TMA refill the raw stage while we wait for the operand slot.
+        // The arrive must not overtake the loads: a shared-memory store of a value that depends on every load cannot
+        // issue before they have returned, and the arrive (release) stays behind the store.
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(smem_u32(landed + warp * 32 + lane)), "r"(lor) : "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&rempty[rs]));
+        mbar_wait(smem_u32(&aempty[rs]), ph ^ 1);                 // the MMAs that read this operand slot have retired
+        tc_fence_after();
+        const uint32_t slot = tmem_base + lane_base + (uint32_t)(DH2_A_COL0 + rs * 64);
+#pragma unroll
+        for (int c8 = 0; c8 < BK; c8 += 8) {
+          float big[8], small[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (p.single) {
+              big[j] = __uint_as_float((__float_as_uint(v[c8 + j]) + 0x8000u) & 0xFFFF0000u);
+              small[j] = 0.f;
+            } else {
+              big[j] = __uint_as_float(__float_as_uint(v[c8 + j]) & 0xFFFFE000u);   // exact split: the tensor core ignores
+              small[j] = v[c8 + j] - big[j];                                        // the low 13 bits of `small`
+            }
+          }
+          tmem_st8(slot + c8, big);
+          tmem_st8(slot + 32 + c8, small);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&afull[rs]));
+      }
+    }
+  } else if (warp < DH2_A_WARPS + DH2_B_WARPS) {
+    // ===================================================================== dy^T -> shared memory (thread = feature row of 256)
+    const int q = threadIdx.x - DH2_A_WARPS * 32;                 // 0..255
+    const int tsel = q >> 7, row = q & (BN - 1);
+    int g = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      int i0, o0, split, kbeg, kend;
+      dh2_tile(p, t, i0, o0, split, kbeg, kend);
+      float colsum = 0.f;                                          // column sum of feature o0 + q over the split: bias gradient
+      for (int k0 = kbeg; k0 < kend; k0 += BK, ++g) {
+        const int rs = g & 1, ph = (g >> 1) & 1;
+        mbar_wait(smem_u32(&rfull[rs]), ph);
+        const float* raw = reinterpret_cast<const float*>(rawbuf + rs * DH2_RAW_BYTES + DH2_RAW_X) + q;
+        float v[BK];
+        uint32_t lor = 0;
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) { v[kk] = raw[kk * DH2_BN]; lor |= __float_as_uint(v[kk]); }
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(smem_u32(landed + warp * 32 + lane)), "r"(lor) : "memory");   // early release, as above
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&rempty[rs]));
+        mbar_wait(smem_u32(&bempty[rs]), ph ^ 1);
+        uint8_t* tb = bstage + rs * DH2_B_STAGE + tsel * 2 * TILE_BYTES;
+#pragma unroll
+        for (int ku = 0; ku < 8; ++ku) {
+          float b[4], sm[4];
+          colsum += (v[ku * 4] + v[ku * 4 + 1]) + (v[ku * 4 + 2] + v[ku * 4 + 3]);     // rows past M are zero-filled by TMA
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float x = v[ku * 4 + j];
+            if (p.single) { b[j] = __uint_as_float((__float_as_uint(x) + 0x8000u) & 0xFFFF0000u); sm[j] = 0.f; }
+            else { b[j] = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); sm[j] = x - b[j]; }
+          }
+          const int off = swz(row, ku);
+          *reinterpret_cast<float4*>(tb + off) = make_float4(b[0], b[1], b[2], b[3]);
+          *reinterpret_cast<float4*>(tb + TILE_BYTES + off) = make_float4(sm[0], sm[1], sm[2], sm[3]);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bfull[rs]));
+      }
+      if (p.db_part != nullptr && i0 == 0 && o0 + q < p.Out) p.db_part[(size_t)split * p.Out + o0 + q] = colsum;
+    }
+  } else if (warp == DH2_TMA_WARP) {
+    if (lane == 0) {
+      int g = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        int i0, o0, split, kbeg, kend;
+        dh2_tile(p, t, i0, o0, split, kbeg, kend);
+        for (int k0 = kbeg; k0 < kend; k0 += BK, ++g) {
+          const int rs = g & 1;
+          mbar_wait(smem_u32(&rempty[rs]), ((g >> 1) & 1) ^ 1);
+          const uint32_t bar = smem_u32(&rfull[rs]);
+          mbar_arrive_expect_tx(bar, DH2_RAW_BYTES);
+          tma_load_2d(smem_u32(rawbuf + rs * DH2_RAW_BYTES), &tmapX, i0, k0, bar);
+          tma_load_2d(smem_u32(rawbuf + rs * DH2_RAW_BYTES + DH2_RAW_X), &tmapG, o0, k0, bar);
+        }
+      }
+    }
+  } else if (warp == DH2_MMA_WARP) {
+    int g = 0, it = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      int i0, o0, split, kbeg, kend;
+      dh2_tile(p, t, i0, o0, split, kbeg, kend);
+      mbar_wait(smem_u32(tempty), (it & 1) ^ 1);                  // accumulators drained
+      tc_fence_after();
+      uint32_t accum = 0;
+      for (int k0 = kbeg; k0 < kend; k0 += BK, ++g) {
+        const int rs = g & 1, ph = (g >> 1) & 1;
+        mbar_wait(smem_u32(&afull[rs]), ph);
+        mbar_wait(smem_u32(&bfull[rs]), ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_big = tmem_base + (uint32_t)(DH2_A_COL0 + rs * 64), a_small = a_big + 32;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t sb = smem_u32(bstage + rs * DH2_B_STAGE + h * 2 * TILE_BYTES);
+            const uint64_t b_big = make_desc(sb), b_small = make_desc(sb + TILE_BYTES);
+            const uint32_t d_tmem = tmem_base + h * BN;
+            uint32_t acc = accum;
+#pragma unroll
+            for (int ks = 0; ks < BK / 8; ++ks) {
+              const uint64_t adv = (uint64_t)((ks * 32) >> 4);
+              if (p.single) {
+                umma_tf32_ts(d_tmem, a_big + ks * 8, b_big + adv, IDESC_TF32, acc);
+              } else {
+                umma_tf32_ts(d_tmem, a_small + ks * 8, b_big + adv, IDESC_TF32, acc);
+                umma_tf32_ts(d_tmem, a_big + ks * 8, b_small + adv, IDESC_TF32, 1u);
+                umma_tf32_ts(d_tmem, a_big + ks * 8, b_big + adv, IDESC_TF32, 1u);
+              }
+              acc = 1u;
+            }
+          }
+          accum = 1u;
+          umma_commit(smem_u32(&aempty[rs]));
+          umma_commit(smem_u32(&bempty[rs]));
+        }
+        __syncwarp();
+      }
+      if (lane == 0) umma_commit(smem_u32(tfull));
+      __syncwarp();
+    }
+  } else {
+    // ===================================================================== epilogue: TMEM -> registers -> 16-byte row stores
+    const int e = warp - DH2_EPI_WARP0;                            // TMEM lane quarter
+    int it = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      int i0, o0, split, kbeg, kend;
+      dh2_tile(p, t, i0, o0, split, kbeg, kend);
+      mbar_wait(smem_u32(tfull), it & 1);
+      tc_fence_after();
+      const int rowi = i0 + e * 32 + lane;
+      float* dst = p.C + (size_t)split * p.In * p.Out + (size_t)rowi * p.Out + o0;
+#pragma unroll 1
+      for (int cc = 0; cc < DH2_BN / 32; ++cc) {
+        if (o0 + cc * 32 >= p.Out) break;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)(cc * 32), v);
+        if (rowi < p.In) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (o0 + cc * 32 + j * 4 < p.Out)                      // Out % 4 == 0 on this path: whole float4 in or out
+              *reinterpret_cast<float4*>(dst + cc * 32 + j * 4) =
+                  make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(tempty));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == DH2_MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ---------------------------------------------------------------------------- pack kernel
 // Writes, for one direction, the rule re-indexed per output component and the W operand as tf32 big/small
 // tile images:  Bpack[pt][chunk][half][q][32]  with element (q, s) = Wsrc(b = s % n, kk = s / n, p = pt*128 + q).
@@ -1512,6 +1766,17 @@ int dh_splits(int M, int In, int Out, int* rows_per_split) {
   const int rps = phc_div_up(phc_div_up(M, s), BK) * BK;
   if (rows_per_split) *rows_per_split = rps;
   return phc_div_up(M, rps);               // every split owns at least one K chunk
+}
+
+int dh2_splits(int M, int In, int Out, int* rows_per_split) {
+  const int tiles = phc_div_up(In, BM) * phc_div_up(Out, DH2_BN);
+  int s = num_sms() / tiles;
+  const int maxs = phc_div_up(M, 4 * BK);
+  s = s > maxs ? maxs : s;
+  s = s < 1 ? 1 : (s > 64 ? 64 : s);
+  const int rps = phc_div_up(phc_div_up(M, s), BK) * BK;
+  if (rows_per_split) *rows_per_split = rps;
+  return phc_div_up(M, rps);
 }
 
 struct PackLayout {
@@ -1716,6 +1981,27 @@ size_t smem_bytes_dh_tma() {
   return 1024 + (size_t)TMA_OP_STAGES * STAGE_BYTES + (size_t)DH_RAW_STAGES * DH_RAW_BYTES + EPI_SCRATCH + 8 * 16 + 16;
 }
 
+size_t smem_bytes_dh_v2() { return 1024 + 2 * (size_t)DH2_B_STAGE + 2 * (size_t)DH2_RAW_BYTES + 8 * DH2_BARS + 16 + 12 * 32 * 4; }
+
+// TMEM-operand dH kernel; `d` must carry the wide tiling (tiles_n = 256-column tiles, dh2_splits).  -1: not applicable.
+int try_launch_dh_v2(const DhParams& d, cudaStream_t stream) {
+  static const bool use_v2 = getenv("PHC_TC_NO_DH_V2") == nullptr && getenv("PHC_TC_NO_TMA") == nullptr;
+  if (!use_v2 || d.Out % 4 != 0 || (reinterpret_cast<uintptr_t>(d.C) & 15u) != 0) return -1;
+  CUtensorMap tx, tg;
+  if (!encode_2d(&tx, d.X, d.M, d.In, BM, BK) || !encode_2d(&tg, d.G, d.M, d.Out, DH2_BN, BK)) return -1;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(phm_tc_dh_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_dh_v2()) != cudaSuccess) {
+      cudaGetLastError();
+      return -1;
+    }
+    configured = true;
+  }
+  const int grid = d.num_tiles < num_sms() ? d.num_tiles : num_sms();
+  phc_launch(phm_tc_dh_v2_kernel, dim3(grid), dim3(DH2_THREADS), smem_bytes_dh_v2(), stream, d, tx, tg);
+  return phc_check_launch("phm_tc_dh_v2_kernel");
+}
+
 // returns -1 when the TMA path is not applicable
 int try_launch_dh_tma(const DhParams& d, cudaStream_t stream) {
   static const bool use_tma = getenv("PHC_TC_NO_TMA") == nullptr;
@@ -1764,7 +2050,8 @@ size_t phm_tc_fwd_workspace_bytes(int, int in_features, int out_features, int ph
 }
 
 size_t phm_tc_bwd_workspace_bytes(int rows, int in_features, int out_features, int phm_dim, int) {
-  const size_t part = (size_t)tc::dh_splits(rows, in_features, out_features, nullptr) * in_features * out_features;
+  const int s1 = tc::dh_splits(rows, in_features, out_features, nullptr), s2 = tc::dh2_splits(rows, in_features, out_features, nullptr);
+  const size_t part = (size_t)(s1 > s2 ? s1 : s2) * in_features * out_features;
   return tc::pack_layout(phm_dim, in_features / phm_dim, out_features / phm_dim).total + 1024 +
          sizeof(float) * (part + phm_contract_scratch_floats(rows, in_features, out_features, phm_dim)) + 64;
 }
@@ -1834,10 +2121,23 @@ int phm_tc_bwd(const float* gy, const float* x, const float* A, const float* W, 
   d.splits = tc::dh_splits(rows, in_features, out_features, &d.rows_per_split);
   d.num_tiles = d.tiles_m * d.tiles_n * d.splits;
   d.single = single;
+  // first choice: x^T operand in tensor memory, 128 x 256 blocks (more, shorter splits)
+  tc::DhParams w = d;
+  w.tiles_n = phc_div_up(out_features, tc::DH2_BN);
+  w.splits = tc::dh2_splits(rows, in_features, out_features, &w.rows_per_split);
+  w.num_tiles = w.tiles_m * w.tiles_n * w.splits;
+  float* wscratch = part + (size_t)w.splits * in_features * out_features;
+  w.db_part = db ? phm_contract_bias_partials(wscratch, in_features, out_features, n) : nullptr;
+  int rc = tc::try_launch_dh_v2(w, stream);
+  if (rc >= 0) {
+    if (rc) return rc;
+    return phm_contract_and_bias(part, w.splits, gy, A, W, dA, dW, db, rows, in_features, out_features, n, wscratch, db ? w.splits : 0,
+                                 stream);
+  }
   float* scratch = part + (size_t)d.splits * in_features * out_features;
   d.db_part = db ? phm_contract_bias_partials(scratch, in_features, out_features, n) : nullptr;
   int db_parts = db ? 2 * d.splits : 0;            // the TMA kernel also emits the column sums of gy (bias gradient)
-  int rc = tc::try_launch_dh_tma(d, stream);
+  rc = tc::try_launch_dh_tma(d, stream);
   if (rc < 0) {
     db_parts = 0;
     static bool configured = false;
