@@ -184,27 +184,40 @@ __device__ __forceinline__ double warp_sum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ part, int chunks, int rpc, int M, int F, float eps,
-                                                          float momentum, float* __restrict__ running_mean,
-                                                          float* __restrict__ running_var, float* __restrict__ save_mean,
-                                                          float* __restrict__ save_rstd, long long* __restrict__ tracked, int n_tracked) {
+// FW warps cooperate on one feature (the PHMLinear epilogue emits one partial per 32 rows: 488 at ppa shape, a single
+// warp spends most of its time in dependent load rounds); the per-warp sums are combined in warp order.
+constexpr int BN_FW = 4;
+__device__ __forceinline__ double block_sum4(double v, double (&sh)[BN_FW], int warp, int lane) {
+  v = warp_sum(v);
+  __syncthreads();                       // sh may still be read from the previous use
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int w = 0; w < BN_FW; ++w) t += sh[w];
+  return t;
+}
+__global__ void __launch_bounds__(BN_FW * 32) bn_finalize_kernel(const float* __restrict__ part, int chunks, int rpc, int M, int F, float eps,
+                                                                 float momentum, float* __restrict__ running_mean,
+                                                                 float* __restrict__ running_var, float* __restrict__ save_mean,
+                                                                 float* __restrict__ save_rstd, long long* __restrict__ tracked, int n_tracked) {
   pdl_begin();
-  const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+  __shared__ double sh[BN_FW];
+  const int f = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (blockIdx.x == 0 && threadIdx.x == 0 && tracked) for (int c = 0; c < n_tracked; ++c) tracked[c] += 1;
-  if (f >= F) return;
   double s = 0.0;
 #pragma unroll 4
-  for (int c = lane; c < chunks; c += 32) s += (double)min(rpc, M - c * rpc) * (double)part[((size_t)c * 2 + 0) * F + f];
-  const double mean = warp_sum(s) / (double)M;
+  for (int c = threadIdx.x; c < chunks; c += BN_FW * 32) s += (double)min(rpc, M - c * rpc) * (double)part[((size_t)c * 2 + 0) * F + f];
+  const double mean = block_sum4(s, sh, warp, lane) / (double)M;
   double m2 = 0.0;
 #pragma unroll 4
-  for (int c = lane; c < chunks; c += 32) {
+  for (int c = threadIdx.x; c < chunks; c += BN_FW * 32) {
     const double d = (double)part[((size_t)c * 2 + 0) * F + f] - mean;
     m2 += (double)part[((size_t)c * 2 + 1) * F + f] + (double)min(rpc, M - c * rpc) * d * d;
   }
-  m2 = warp_sum(m2);
-  if (lane != 0) return;
+  m2 = block_sum4(m2, sh, warp, lane);
+  if (threadIdx.x != 0) return;
   const double var = m2 / (double)M;
   save_mean[f] = (float)mean;
   save_rstd[f] = (float)(1.0 / sqrt(var + (double)eps));
@@ -499,7 +512,7 @@ static int bn_fwd_impl(const float* h, const float* gamma, const float* beta, fl
     if (training && pre_partials != nullptr) {
       // chunk moments already produced by the kernel that wrote h (PHMLinear epilogue): only merge them
       PHC_REQUIRE(M > 1, "phc_bn_act_drop_skip_fwd: batch-norm in training mode needs more than 1 row");
-      phc_launch(bn_finalize_kernel, dim3(phc_div_up((long long)F * 32, 256)), dim3(256), 0, stream, pre_partials,
+      phc_launch(bn_finalize_kernel, dim3(F), dim3(BN_FW * 32), 0, stream, pre_partials,
                  phc_div_up(M, pre_chunk_rows), pre_chunk_rows, M, F, eps, momentum, running_mean, running_var, save_mean, save_rstd,
                  num_batches_tracked, n_tracked);
     } else if (training) {
@@ -513,7 +526,7 @@ static int bn_fwd_impl(const float* h, const float* gamma, const float* beta, fl
       dim3 grid(chunks, colgroups);
       if (v4s) phc_launch(bn_chunk_stats_kernel<4>, dim3(grid), dim3(BN_THREADS), 0, stream, h, M, F, rpc, part);
       else phc_launch(bn_chunk_stats_kernel<1>, dim3(grid), dim3(BN_THREADS), 0, stream, h, M, F, rpc, part);
-      phc_launch(bn_finalize_kernel, dim3(phc_div_up((long long)F * 32, 256)), dim3(256), 0, stream, part, chunks, rpc, M, F, eps, momentum, running_mean,
+      phc_launch(bn_finalize_kernel, dim3(F), dim3(BN_FW * 32), 0, stream, part, chunks, rpc, M, F, eps, momentum, running_mean,
                                                                                 running_var, save_mean, save_rstd, num_batches_tracked,
                                                                                 n_tracked);
     } else {

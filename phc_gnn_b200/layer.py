@@ -22,6 +22,7 @@ import torch
 
 from . import _lib
 from .graph import EdgeStructure, _stream
+from .parallel import grad_sink
 from .ops import PROFILE, REDUCE_IDS, _ptr, _ptr_array, _ws, act_id, default_precision, next_dropout_seed, run
 
 _WS_CACHE = {}
@@ -445,7 +446,7 @@ class _ConvLayerCall(torch.autograd.Function):
 class _ConvLayerDirect(torch.autograd.Function):
     """The node with the parameters OUTSIDE the autograd graph: only x and skip are graph inputs; backward writes every
     parameter gradient straight into its final place — the parameter's slice of the flat gradient buffer when a
-    GradientBucket registered one (``param._phc_sink``), fresh storage otherwise — and assigns / accumulates ``param.grad``
+    GradientBucket registered one (``parallel.register_grad_sink``), fresh storage otherwise — and assigns / accumulates ``param.grad``
     itself, as AccumulateGrad would.  At ppa shape the 24 parameter inputs per layer cost more host time in
     Function.apply, the engine and AccumulateGrad than the layer's kernels take on the GPU.  Not visible to
     torch.autograd.grad(), parameter hooks or double backward: set ``layer.DIRECT_PARAM_GRADS = False`` for those."""
@@ -462,7 +463,7 @@ class _ConvLayerDirect(torch.autograd.Function):
     def backward(ctx, g):
         cfg, struct, host, tensors, has_skip = ctx.misc
         x, attr = ctx.saved_tensors[:2]
-        sinks = [None if (t is None or t.grad is not None) else getattr(t, "_phc_sink", None) for t in tensors]
+        sinks = [None if (t is None or t.grad is not None) else grad_sink(t) for t in tensors]
         dx, g, grads = _call_bwd(cfg, struct, host, x, attr, g, tensors, sinks)
         for t, gr in zip(tensors, grads):
             if gr is None or t is None or not t.requires_grad:

@@ -9,11 +9,27 @@ uses per-rank batch statistics (DDP semantics).
 """
 from __future__ import annotations
 
+import weakref
 from typing import List, Optional
 
 import torch
 import torch.distributed as dist
 import torch.nn as nn
+
+
+# parameter -> its slice of a flat gradient buffer (set by GradientBucket, read by layer.py's in-place gradient path);
+# a side table rather than an attribute so that it is never pickled with the parameter
+_SINKS = {}     # id(param) -> (weakref to the parameter, view); keyed by id because tensors do not compare as scalars
+
+
+def register_grad_sink(param: torch.nn.Parameter, view: torch.Tensor) -> None:
+    key = id(param)
+    _SINKS[key] = (weakref.ref(param, lambda _r, k=key: _SINKS.pop(k, None)), view)
+
+
+def grad_sink(param) -> Optional[torch.Tensor]:
+    e = _SINKS.get(id(param))
+    return e[1] if (e is not None and e[0]() is param) else None
 
 
 class GradientBucket(object):
@@ -35,17 +51,20 @@ class GradientBucket(object):
                 self.views.append(self.flat[off:off + p.numel()].view(p.shape))
                 off += p.numel()
             for p, v in zip(self.params, self.views):
-                p._phc_sink = v            # layer.py writes this parameter's gradient straight into the flat buffer
+                register_grad_sink(p, v)   # layer.py writes this parameter's gradient straight into the flat buffer
 
     def pack(self):
         dev = self.params[0].device
         self._ensure(dev)
         src, dst = [], []
         for p, v in zip(self.params, self.views):
-            if p.grad is None:
+            g = p.grad
+            if g is v:
+                continue                   # written in place by the layer's backward
+            if g is None:
                 v.zero_()
-            elif p.grad.data_ptr() != v.data_ptr():
-                src.append(p.grad)
+            elif g.data_ptr() != v.data_ptr():
+                src.append(g)
                 dst.append(v)
         if src:
             torch._foreach_copy_(dst, src)
