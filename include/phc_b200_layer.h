@@ -48,9 +48,10 @@ typedef struct phc_conv_layer {
   size_t ws_lin1_bytes, ws_lin2_bytes;
   void* ws;                                /* scratch, phc_conv_layer_workspace_bytes() */
   size_t ws_bytes;
+  const float* node_sums;                  /* optional (sum / mean + identity message): phc_edge_feature_sums output, used by
+                                              forward (phc_conv_fused_fwd_sums) and backward (phc_conv_fused_bwd) */
   /* backward only */
   const float* gout;                       /* [N, width] gradient of `out` */
-  const float* node_sums;                  /* optional, see phc_conv_fused_bwd */
   float *tmp_a, *tmp_b;                    /* two [N, width] scratch matrices; with mlp=0 tmp_a holds d(z) on return */
   float* dx;                               /* [N, width] */
   float* d_softmax_beta;                   /* scalar (zero-initialised by the caller) or NULL */

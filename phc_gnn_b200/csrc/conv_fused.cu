@@ -401,6 +401,77 @@ __global__ void __launch_bounds__(256) edge_feature_sums_kernel(const EncDesc en
   S[t] = mean ? s / (float)max(end - beg, 1) : s;
 }
 
+// Forward with the per-node feature sums: the encoder is linear in phi(edge_attr) (a Linear layer, or a sum of embedding
+// rows = one-hot features), so for sum / mean aggregation with the identity message the edge term leaves the edge loop:
+//   out[i,:] = self * x[i,:] + scale_i * sum_{e -> i} x[src(e),:]  +  sum_r S[i,r] * Tab[r,:]
+// (S already carries the mean scale).  The kernel is then a pure row gather (same shape as the input-gradient kernel,
+// which moves the same 4*E*F bytes through L2 in ~40 us where the per-edge kernel needs ~138 us for 7 FMAs, 7 feature
+// loads and 28 weight registers per edge and thread) plus R FMAs per output element.
+// the encoder parameters as one [R, F] table in global memory (16 KB at ppa shape: lives in L1 / L2)
+__global__ void __launch_bounds__(256) enc_table_kernel(const EncDesc enc, int F, float* __restrict__ tab) {
+  pdl_begin();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= enc.R * F) return;
+  const int r = idx / F, f = idx - r * F;
+  const int c = f / enc.Fc, fp = f - c * enc.Fc;
+  float v;
+  if (enc.kind == ENC_LINEAR) {
+    if (r < enc.D) v = __ldg(enc.p[c] + (size_t)fp * enc.D + r);
+    else v = enc.p[enc.n + c] ? __ldg(enc.p[enc.n + c] + fp) : 0.f;
+  } else {
+    int col = 0;
+    while (col + 1 < enc.D && enc.voff[col + 1] <= r) ++col;
+    v = __ldg(enc.p[c * enc.D + col] + (size_t)(r - enc.voff[col]) * enc.Fc + fp);
+  }
+  tab[idx] = v;
+}
+
+// one thread per (node, 4 features), flat grid, ~32 registers: full occupancy for the row gather
+template <bool MEAN>
+__global__ void __launch_bounds__(256) conv_fwd_sums_kernel(const float* __restrict__ x, const float* __restrict__ S,
+                                                            const float* __restrict__ tab, const int* __restrict__ rowptr,
+                                                            const int* __restrict__ col, int N, int F, int R, int self_loop,
+                                                            float* __restrict__ out) {
+  pdl_begin();
+  const int fv = F / 4;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)N * fv) return;
+  const int i = (int)(t / fv), f = (int)(t - (long long)i * fv) * 4;
+  const int beg = rowptr[i], end = rowptr[i + 1];
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int k = beg;
+  for (; k + 4 <= end; k += 4) {                 // four rows in flight
+    int j[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) j[u] = __ldg(col + k + u);
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(x + (size_t)j[u] * F + f);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { a0 += v[u].x; a1 += v[u].y; a2 += v[u].z; a3 += v[u].w; }
+  }
+  for (; k < end; ++k) {
+    const float4 v = *reinterpret_cast<const float4*>(x + (size_t)__ldg(col + k) * F + f);
+    a0 += v.x; a1 += v.y; a2 += v.z; a3 += v.w;
+  }
+  if (MEAN) {
+    const float sc = 1.f / (float)max(end - beg, 1);
+    a0 *= sc; a1 *= sc; a2 *= sc; a3 *= sc;
+  }
+  const float* si = S + (size_t)i * R;
+  for (int r = 0; r < R; ++r) {
+    const float sv = __ldg(si + r);
+    const float4 w = __ldg(reinterpret_cast<const float4*>(tab + (size_t)r * F + f));
+    a0 += sv * w.x; a1 += sv * w.y; a2 += sv * w.z; a3 += sv * w.w;
+  }
+  const size_t off = (size_t)i * F + f;
+  if (self_loop) {
+    const float4 xi = *reinterpret_cast<const float4*>(x + off);
+    a0 += xi.x; a1 += xi.y; a2 += xi.z; a3 += xi.w;
+  }
+  *reinterpret_cast<float4*>(out + off) = make_float4(a0, a1, a2, a3);
+}
+
 template <int RT>
 __global__ void __launch_bounds__(128) conv_bwd_param_simple_kernel(const float* __restrict__ g, const float* __restrict__ S, int N, int F,
                                                                     int rows_per_block, float* __restrict__ part) {
@@ -585,6 +656,29 @@ int phc_conv_fused_fwd(const float* x, const void* edge_attr, int enc_kind, int 
 #undef PHC_LAUNCH
 #undef PHC_LAUNCH2
   return phc_check_launch("phc_conv_fused_fwd");
+}
+
+size_t phc_conv_fused_fwd_sums_workspace_bytes(int width, int table_rows) { return sizeof(float) * (size_t)table_rows * width + 16; }
+
+int phc_conv_fused_fwd_sums(const float* x, const float* node_sums, int enc_kind, int enc_dim, const int* vocab, const float* const* params,
+                            const int* rowptr, const int* col, int num_nodes, int width, int phm_dim, int reduce, int self_loop,
+                            float* out, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  PHC_REQUIRE(reduce == PHC_RED_SUM || reduce == PHC_RED_MEAN, "phc_conv_fused_fwd_sums: sum / mean only (got reduce %d)", reduce);
+  PHC_REQUIRE(node_sums != nullptr, "phc_conv_fused_fwd_sums: node_sums required");
+  EncDesc d;
+  PHC_REQUIRE(make_desc(d, enc_kind, enc_dim, vocab, params, nullptr, phm_dim, width) == 0, "phc_conv_fused_fwd_sums: unsupported encoder");
+  PHC_REQUIRE(phc_conv_fused_supported(width, phm_dim, enc_kind, enc_dim, d.R), "phc_conv_fused_fwd_sums: unsupported shape");
+  PHC_REQUIRE(workspace != nullptr && workspace_bytes >= phc_conv_fused_fwd_sums_workspace_bytes(width, d.R) && phc_aligned16(workspace),
+              "phc_conv_fused_fwd_sums: workspace too small or misaligned");
+  if (num_nodes == 0) return PHC_OK;
+  float* tab = reinterpret_cast<float*>(workspace);
+  phc_launch(enc_table_kernel, dim3(phc_div_up((long long)d.R * width, 256)), dim3(256), 0, stream, d, width, tab);
+  const int grid = phc_div_up((long long)num_nodes * (width / 4), 256);
+  if (reduce == PHC_RED_MEAN)
+    phc_launch(conv_fwd_sums_kernel<true>, dim3(grid), dim3(256), 0, stream, x, node_sums, tab, rowptr, col, num_nodes, width, d.R, self_loop, out);
+  else
+    phc_launch(conv_fwd_sums_kernel<false>, dim3(grid), dim3(256), 0, stream, x, node_sums, tab, rowptr, col, num_nodes, width, d.R, self_loop, out);
+  return phc_check_launch("phc_conv_fused_fwd_sums");
 }
 
 int phc_edge_feature_sums(const void* edge_attr, int enc_kind, int enc_dim, const int* vocab, const int* rowptr, const int* perm,

@@ -30,6 +30,7 @@ size_t phc_conv_layer_workspace_bytes(int num_nodes, int width, int phm_dim, int
   size_t b = phc_bn_workspace_bytes(num_nodes, width);
   b = max_sz(b, phc_phm_linear_bwd_workspace_bytes(num_nodes, width, width, phm_dim, precision));
   b = max_sz(b, phc_conv_fused_bwd_workspace_bytes(num_nodes, width, table_rows));
+  b = max_sz(b, phc_conv_fused_fwd_sums_workspace_bytes(width, table_rows));
   return b + 1024;
 }
 
@@ -50,8 +51,12 @@ int phc_conv_layer_fwd(const phc_conv_layer* L, phc_stream_t stream) {
   const int N = L->num_nodes, F = L->width, n = L->phm_dim;
   if (N == 0) return 0;
   // 1. aggregation with the edge encoder fused in
-  rc = phc_conv_fused_fwd(L->x, L->edge_attr, L->enc_kind, L->enc_dim, L->vocab, L->enc_params, L->rowptr, L->col, L->perm, N, F, n, L->reduce,
-                          L->msg_act, L->softmax_beta, L->self_loops && L->mlp, L->agg, L->aux_f, L->aux_i, stream);
+  if (L->node_sums != nullptr && (L->reduce == PHC_RED_SUM || L->reduce == PHC_RED_MEAN) && L->msg_act == PHC_ACT_IDENTITY)
+    rc = phc_conv_fused_fwd_sums(L->x, L->node_sums, L->enc_kind, L->enc_dim, L->vocab, L->enc_params, L->rowptr, L->col, N, F, n, L->reduce,
+                                 L->self_loops && L->mlp, L->agg, L->ws, L->ws_bytes, stream);   // encoder term from the per-node sums
+  else
+    rc = phc_conv_fused_fwd(L->x, L->edge_attr, L->enc_kind, L->enc_dim, L->vocab, L->enc_params, L->rowptr, L->col, L->perm, N, F, n, L->reduce,
+                            L->msg_act, L->softmax_beta, L->self_loops && L->mlp, L->agg, L->aux_f, L->aux_i, stream);
   if (rc) return rc;
   // 2.-4. PHM transform.  When a training-mode batch-norm follows a PHMLinear, the linear kernel's epilogue also emits the
   // chunk moments of its output (into the scratch workspace) and the norm only merges them.

@@ -120,9 +120,17 @@ class _ConvLayer(torch.autograd.Function):
         aux_f = torch.empty((2, N, F), dtype=torch.float32, device=dev) if reduce == 4 else None
         aux_i = torch.empty((N, F), dtype=torch.int32, device=dev) if reduce in (2, 3) else None
         vc = (ctypes.c_int * max(len(vocab), 1))(*vocab) if vocab else None
-        run("phc_conv_fused_fwd", None, x.data_ptr(), attr.data_ptr(), 0 if linear else 1, enc_dim, vc, _ptr_array(enc),
-            struct.rowptr.data_ptr(), struct.col.data_ptr(), struct.perm.data_ptr(), N, F, n, reduce, msg_act, _ptr(beta),
-            int(self_loops and mlp), agg.data_ptr(), _ptr(aux_f), _ptr(aux_i), st)
+        rows = enc_dim + 1 if linear else int(sum(vocab))
+        sums = _node_sums(struct, attr, linear, enc_dim, vocab, vc, reduce, msg_act, rows, N, dev, st) if NODE_SUM_FORWARD else None
+        if sums is not None:
+            tws = _ws(_ws_bytes("phc_conv_fused_fwd_sums_workspace_bytes", F, rows), dev)
+            run("phc_conv_fused_fwd_sums", None, x.data_ptr(), sums.data_ptr(), 0 if linear else 1, enc_dim, vc, _ptr_array(enc),
+                struct.rowptr.data_ptr(), struct.col.data_ptr(), N, F, n, reduce, int(self_loops and mlp), agg.data_ptr(),
+                tws.data_ptr(), tws.numel(), st, launches=2)
+        else:
+            run("phc_conv_fused_fwd", None, x.data_ptr(), attr.data_ptr(), 0 if linear else 1, enc_dim, vc, _ptr_array(enc),
+                struct.rowptr.data_ptr(), struct.col.data_ptr(), struct.perm.data_ptr(), N, F, n, reduce, msg_act, _ptr(beta),
+                int(self_loops and mlp), agg.data_ptr(), _ptr(aux_f), _ptr(aux_i), st)
         # 2.-4. PHM transform
         if mlp:
             y1, ws1 = _lin_fwd(agg, r1, W1, b1, None, precision, st)
@@ -210,6 +218,7 @@ class _ConvLayer(torch.autograd.Function):
 
 SINGLE_CALL = True      # False: one C-ABI call per operator (the cross-check path of the tests)
 DIRECT_PARAM_GRADS = True   # parameter gradients written in place by the layer's backward instead of flowing through autograd
+NODE_SUM_FORWARD = True     # sum / mean + identity message: encoder term from the per-node feature sums (pure row gather)
 _SCRATCH = {}
 
 
@@ -312,6 +321,8 @@ def _call_fwd(cfg, struct: EdgeStructure, flats, x, skip, attr, tensors):
     if mlp:
         D.ws_lin2, D.ws_lin2_bytes = ws_lin.data_ptr() + nb_lin, nb_lin
     D.ws, D.ws_bytes = ws.data_ptr(), ws.numel()
+    sums = _node_sums(struct, attr, linear, enc_dim, vocab, vc, reduce, msg_act, rows, N, dev, st) if NODE_SUM_FORWARD else None
+    D.node_sums = _ptr(sums)
     fused_stats = precision != 0 and n == 4 and training        # batch-norm statistics come out of the PHMLinear epilogue
     run("phc_conv_layer_fwd", None, ctypes.byref(D), st,
         launches=(11 if mlp else 6) - ((int(use_bn1 and mlp) + int(use_bn2)) if fused_stats else 0))
