@@ -171,6 +171,8 @@ def cpu_baseline(wl, budget_s: float = 25.0):
 # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the aggregation forward kernel from the
 # committed ncu --set full capture of this same command (profiles/r01_conv_fwd_ppa_ncu_full.txt)
 NCU_TRAFFIC_BYTES = {"ppa": 42.00e6 + 7.48e6}
+# the same for conv_fwd_sums_kernel (profiles/r01_conv_fwd_sums_ppa_ncu_full.txt); filled from the capture, None until then
+NCU_TRAFFIC_BYTES_SUMS = {}
 
 
 def aggregation_bytes(N, E, F, softmax):
@@ -229,6 +231,10 @@ def run_b200(args):
             timing_events.append((a, b))
         return loss
 
+    # untimed: one step on every distinct batch first (each batch shape is new to the caching allocator: without this the
+    # first timed visit of a batch pays cudaMalloc inside the timed region), then the W warm-up steps
+    for i in range(len(devb)):
+        one(i)
     for i in range(args.warmup):
         one(i)
     # ---- timed region: K steps, device-resident batches, no per-op instrumentation --------------------------
@@ -319,25 +325,30 @@ def run_b200(args):
                 ev.record(copy_stream)
             return d, ev
 
+        def e2e_loop(n_steps, first):
+            total = 0.0
+            nxt = fetch(first)
+            for i in range(n_steps):
+                d, ev = nxt
+                main.wait_event(ev)
+                if i + 1 < n_steps:
+                    nxt = fetch(first + i + 1)
+                graph.clear_cache()
+                l = step(d)
+                loss_host[i & 1].copy_(l, non_blocking=True)
+                loss_ev[i & 1].record(main)
+                if i > 0:
+                    loss_ev[(i - 1) & 1].synchronize()
+                    total += float(loss_host[(i - 1) & 1]) * wl.batch_graphs
+            loss_ev[(n_steps - 1) & 1].synchronize()
+            return total + float(loss_host[(n_steps - 1) & 1]) * wl.batch_graphs
+
+        e2e_loop(len(host) + 1, 0)        # untimed: the staging tensors of every batch shape exist in the allocator afterwards
         barrier()
         t0 = torch.cuda.Event(enable_timing=True)
         t1 = torch.cuda.Event(enable_timing=True)
         t0.record()
-        nxt = fetch(args.warmup)
-        for i in range(args.steps):
-            d, ev = nxt
-            main.wait_event(ev)
-            if i + 1 < args.steps:
-                nxt = fetch(args.warmup + i + 1)
-            graph.clear_cache()
-            l = step(d)
-            loss_host[i & 1].copy_(l, non_blocking=True)
-            loss_ev[i & 1].record(main)
-            if i > 0:
-                loss_ev[(i - 1) & 1].synchronize()
-                total_loss += float(loss_host[(i - 1) & 1]) * wl.batch_graphs
-        loss_ev[(args.steps - 1) & 1].synchronize()
-        total_loss += float(loss_host[(args.steps - 1) & 1]) * wl.batch_graphs
+        total_loss = e2e_loop(args.steps, args.warmup)
         t1.record()
         barrier()
         tt = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
@@ -352,8 +363,10 @@ def run_b200(args):
         N = sum(b.num_nodes for b in host) / len(host)
         E = sum(b.num_edges for b in host) / len(host)
         F = wl.model["mp_layers"][0]
-        fused = "phc_conv_fused_fwd" in prof
-        calls, agg_ms = prof.get("phc_conv_fused_fwd" if fused else "phc_aggregate_fwd", (0, 0.0))
+        sums_path = "phc_conv_fused_fwd_sums" in prof
+        fused = sums_path or "phc_conv_fused_fwd" in prof
+        key = "phc_conv_fused_fwd_sums" if sums_path else ("phc_conv_fused_fwd" if fused else "phc_aggregate_fwd")
+        calls, agg_ms = prof.get(key, (0, 0.0))
         roof = None
         if calls:
             softmax = wl.model["msg_aggr"] == "softmax"
@@ -361,20 +374,34 @@ def run_b200(args):
             us = 1e3 * agg_ms / calls
             ach = byt / us / 1e3
             roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": NCU_TRAFFIC_BYTES.get(wl.name) if fused else None,
+                    "traffic": (NCU_TRAFFIC_BYTES_SUMS if sums_path else NCU_TRAFFIC_BYTES).get(wl.name) if fused else None,
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": byt, "avg_launch_us": us,
                     "share_of_step": agg_ms / ms,      # of the headline (uninstrumented) step; the instrumented repeat is slower
                     "timed": "CUDA events around each launch, instrumented repeat of the K steps"}
             if fused:
                 dims = wl.model["bond_input_dims"]
                 attr_b = (4 * dims if isinstance(dims, int) else 8 * len(dims)) * E
-                actual = 4 * F * 2 * N + attr_b + 8 * E + 4 * (N + 1) + (8 * N * F if softmax else 0)
-                roof.update({
-                    "kernel": "conv_fwd_kernel (gather + edge ENCODER + edge add + reduce fused)",
-                    "note": "achieved = SURVEY 8(d) algorithmic bytes of the unit (edge embedding [E,F] counted) / time, i.e. "
-                            "effective bandwidth; the fused kernel rebuilds the embedding from the raw edge features and really "
-                            "moves only hbm_bytes_model bytes, it is bound by the L2 row gather and FMA issue, not by HBM",
-                    "hbm_bytes_model": actual, "hbm_gbs_model": actual / us / 1e3, "unfused_boundary_kernel": unfused})
+                rows = (dims + 1) if isinstance(dims, int) else sum(dims)
+                if sums_path:
+                    actual = 4 * F * 2 * N + 4 * rows * N + 4 * E + 4 * (N + 1) + 4 * rows * F
+                    roof.update({
+                        "kernel": "conv_fwd_sums_kernel (row gather + per-node encoder term; + enc_table_kernel)",
+                        "note": "achieved = SURVEY 8(d) algorithmic bytes of the unit (x, the [E,F] edge embedding, out, indices) / time, "
+                                "i.e. EFFECTIVE bandwidth at the reference's operator boundary; it exceeds the HBM peak because for "
+                                "sum/mean aggregation with an identity message the linear edge encoder is applied to per-node feature "
+                                "sums (computed once per batch), so the [E,F] operand is never formed or read: the kernel really moves "
+                                "hbm_bytes_model bytes and is bound by the L2 row gather (l2_gather_gbs = 4*E*F bytes / time); the "
+                                "HBM-streaming kernel of the same boundary is reported under unfused_boundary_kernel",
+                        "hbm_bytes_model": actual, "hbm_gbs_model": actual / us / 1e3, "l2_gather_gbs": 4 * E * F / us / 1e3,
+                        "unfused_boundary_kernel": unfused})
+                else:
+                    actual = 4 * F * 2 * N + attr_b + 8 * E + 4 * (N + 1) + (8 * N * F if softmax else 0)
+                    roof.update({
+                        "kernel": "conv_fwd_kernel (gather + edge ENCODER + edge add + reduce fused)",
+                        "note": "achieved = SURVEY 8(d) algorithmic bytes of the unit (edge embedding [E,F] counted) / time, i.e. "
+                                "effective bandwidth; the fused kernel rebuilds the embedding from the raw edge features and really "
+                                "moves only hbm_bytes_model bytes, it is bound by the L2 row gather and FMA issue, not by HBM",
+                        "hbm_bytes_model": actual, "hbm_gbs_model": actual / us / 1e3, "unfused_boundary_kernel": unfused})
                 if unfused:
                     unfused["frac"] = unfused["achieved"] / peak
             else:
