@@ -171,8 +171,8 @@ def cpu_baseline(wl, budget_s: float = 25.0):
 # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the aggregation forward kernel from the
 # committed ncu --set full capture of this same command (profiles/r01_conv_fwd_ppa_ncu_full.txt)
 NCU_TRAFFIC_BYTES = {"ppa": 42.00e6 + 7.48e6}
-# the same for conv_fwd_sums_kernel (profiles/r01_conv_fwd_sums_ppa_ncu_full.txt); filled from the capture, None until then
-NCU_TRAFFIC_BYTES_SUMS = {}
+# the same for conv_fwd_sums_kernel (profiles/r01_conv_fwd_sums_ppa_ncu_full.txt)
+NCU_TRAFFIC_BYTES_SUMS = {"ppa": 33.07e6 + 1.78e6}
 
 
 def aggregation_bytes(N, E, F, softmax):
