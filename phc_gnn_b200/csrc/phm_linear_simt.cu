@@ -286,19 +286,23 @@ __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restri
 // (64 pairs per block, 64*N threads, the two warps of one `a` are adjacent).  The thread folds the split partials of
 // its N dH entries (a; c = 0..N-1) with independent loads, contributes sum_c A[b,a,c] dh[c] to dW[b,k,p] (summed over a
 // through shared memory, a = 0..N-1 in order) and w[b] dh[c] to dA[b,a,c] (warp butterfly, then the a's two warps).
-constexpr int CJ = 64;
+// CG thread groups share the split list (group g folds splits g, g + CG, ...; the group sums are added in group order):
+// with the 18 short splits of the wide dH kernel one group spends its time in dependent L2 round trips.
+constexpr int CJ = 64, CG = 3;
 template <int N>
-__global__ void __launch_bounds__(CJ * N) phm_contract_small_kernel(const float* __restrict__ part, int splits, const float* __restrict__ A,
-                                                                    const float* __restrict__ W, int K, int P, float* __restrict__ dW,
-                                                                    float* __restrict__ dA_part) {
+__global__ void __launch_bounds__(CG * CJ * N) phm_contract_small_kernel(const float* __restrict__ part, int splits, const float* __restrict__ A,
+                                                                         const float* __restrict__ W, int K, int P, float* __restrict__ dW,
+                                                                         float* __restrict__ dA_part) {
   pdl_begin();
   constexpr int N2 = N * N, N3 = N * N * N;
   __shared__ float As[N3];
   __shared__ float dws[N][CJ][N];
   __shared__ float red[2 * N][N2];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ float dhs[CG - 1][CJ * N][N];
+  const int grp = threadIdx.x / (CJ * N);
+  const int tid = threadIdx.x - grp * (CJ * N), lane = tid & 31, warp = tid >> 5;
   const int a = tid / CJ, j = tid % CJ;
-  for (int i = tid; i < N3; i += CJ * N) As[i] = A[i];
+  for (int i = threadIdx.x; i < N3; i += CG * CJ * N) As[i] = A[i];
   __syncthreads();
   const int In = N * K, Out = N * P;
   const long long t = (long long)blockIdx.x * CJ + j;
@@ -313,10 +317,20 @@ __global__ void __launch_bounds__(CJ * N) phm_contract_small_kernel(const float*
     const float* src = part + (size_t)(a * K + k) * Out + p;
     const size_t stride = (size_t)In * Out;
 #pragma unroll 4
-    for (int s = 0; s < splits; ++s)
+    for (int s = grp; s < splits; s += CG)
 #pragma unroll
       for (int c = 0; c < N; ++c) dh[c] += src[(size_t)s * stride + c * P];
   }
+  if (grp > 0) {
+#pragma unroll
+    for (int c = 0; c < N; ++c) dhs[grp - 1][tid][c] = dh[c];
+  }
+  __syncthreads();
+  if (grp > 0) return;                       // group 0 carries on with the folded values
+#pragma unroll
+  for (int g2 = 0; g2 < CG - 1; ++g2)
+#pragma unroll
+    for (int c = 0; c < N; ++c) dh[c] += dhs[g2][tid][c];
 #pragma unroll
   for (int b = 0; b < N; ++b) {
     float v = 0.f;
@@ -333,7 +347,7 @@ __global__ void __launch_bounds__(CJ * N) phm_contract_small_kernel(const float*
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
       if (lane == 0) red[warp][b * N + c] = v;
     }
-  __syncthreads();
+  asm volatile("bar.sync 1, %0;" ::"r"(CJ * N) : "memory");      // group 0 only (the other groups have left)
   if (a == 0 && active) {
 #pragma unroll
     for (int b = 0; b < N; ++b) {
@@ -387,10 +401,10 @@ int phm_contract_and_bias(const float* part, int splits, const float* gy, const 
   float* da_part = scratch;
   float* cs_part = phm_contract_bias_partials(scratch, in_features, out_features, n);
   switch (n) {
-    case 1: phc_launch(phm_contract_small_kernel<1>, dim3(cblocks), dim3(CJ * 1), 0, stream, part, splits, A, W, K, P, dW, da_part); break;
-    case 2: phc_launch(phm_contract_small_kernel<2>, dim3(cblocks), dim3(CJ * 2), 0, stream, part, splits, A, W, K, P, dW, da_part); break;
-    case 3: phc_launch(phm_contract_small_kernel<3>, dim3(cblocks), dim3(CJ * 3), 0, stream, part, splits, A, W, K, P, dW, da_part); break;
-    case 4: phc_launch(phm_contract_small_kernel<4>, dim3(cblocks), dim3(CJ * 4), 0, stream, part, splits, A, W, K, P, dW, da_part); break;
+    case 1: phc_launch(phm_contract_small_kernel<1>, dim3(cblocks), dim3(CG * CJ * 1), 0, stream, part, splits, A, W, K, P, dW, da_part); break;
+    case 2: phc_launch(phm_contract_small_kernel<2>, dim3(cblocks), dim3(CG * CJ * 2), 0, stream, part, splits, A, W, K, P, dW, da_part); break;
+    case 3: phc_launch(phm_contract_small_kernel<3>, dim3(cblocks), dim3(CG * CJ * 3), 0, stream, part, splits, A, W, K, P, dW, da_part); break;
+    case 4: phc_launch(phm_contract_small_kernel<4>, dim3(cblocks), dim3(CG * CJ * 4), 0, stream, part, splits, A, W, K, P, dW, da_part); break;
     default: phc_launch(phm_contract_kernel, dim3(cblocks), dim3(256), sizeof(float) * (n3 + 8), stream, part, splits, A, W, n, K, P, dW, da_part);
   }
   const bool fused_bias = db != nullptr && db_parts > 0;
