@@ -454,3 +454,50 @@ def test_phm_linear_epilogue_batch_norm_statistics(fin, fout, M, residual):
     y64 = y.double().cpu()
     assert_close(outs[0][1].double(), y64.mean(0), 1e-5, 1e-6, "mean vs fp64")
     assert_close(outs[0][2].double(), 1.0 / torch.sqrt(y64.var(0, unbiased=False) + 1e-5), 1e-4, 1e-6, "rstd vs fp64")
+
+
+@pytest.mark.parametrize("reduce,linear,F,n,self_loop", [("add", True, 500, 4, True), ("mean", True, 64, 4, False),
+                                                         ("add", False, 200, 4, True), ("mean", False, 180, 2, True)])
+def test_conv_forward_from_node_sums(reduce, linear, F, n, self_loop):
+    """phc_conv_fused_fwd_sums (encoder applied to per-node feature sums, pure row gather) == the per-edge fused kernel
+    == encoder followed by aggregation (fp64 oracle); isolated nodes included."""
+    import ctypes
+    from phc.hypercomplex.encoder import PHMEncoder
+    from phc_gnn_b200 import _lib, ops
+    from phc_gnn_b200.graph import EdgeStructure, _stream
+    from phc_gnn_b200.ops import _ptr_array, run
+    N, E = 333, 2900
+    ei = _graph(N - 5, E, 11)                                      # the last five nodes have no edges
+    E = ei.size(1)
+    g = torch.Generator().manual_seed(6)
+    dims = 7 if linear else [5, 6, 2]
+    enc = PHMEncoder(F // n, dims, n)
+    attr = torch.rand(E, 7, generator=g) if linear else torch.stack([torch.randint(0, d, (E,), generator=g) for d in dims], 1)
+    x = torch.randn(N, F, generator=g)
+    po = {f"e.{k}": v.detach().clone().double() for k, v in enc.state_dict().items()}
+    ref = O.propagate(x.double(), ei, O.encoder(attr, po, "e", n, dims, torch.float64), reduce, "identity", torch.tensor(1.0).double())
+    if self_loop:
+        ref = ref + x.double()
+    enc = enc.to(DEV)
+    linear_, params, vocab = enc.fusable_params()
+    s = EdgeStructure(ei.to(DEV), N)
+    xs, at = x.to(DEV), attr.to(DEV)
+    at = at.float().contiguous() if linear_ else at.long().contiguous()
+    edge = ops.conv_aggregate_fused(xs, at, s, linear=linear_, params=params, phm_dim=n, vocab=vocab, reduce=reduce, msg_act="identity",
+                                    beta=None, self_loop=self_loop)
+    lib = _lib.load()
+    st = _stream(torch.device(DEV))
+    red = ops.REDUCE_IDS[reduce]
+    enc_dim = at.size(1)
+    rows = enc_dim + 1 if linear_ else int(sum(vocab))
+    vc = (ctypes.c_int * max(len(vocab), 1))(*vocab) if vocab else None
+    sums = torch.empty((N, rows), device=DEV)
+    run("phc_edge_feature_sums", None, at.data_ptr(), 0 if linear_ else 1, enc_dim, vc, s.rowptr.data_ptr(), s.perm.data_ptr(), N,
+        int(red == 1), sums.data_ptr(), st)
+    out = torch.empty_like(xs)
+    ws = torch.empty(lib.phc_conv_fused_fwd_sums_workspace_bytes(F, rows), dtype=torch.uint8, device=DEV)
+    run("phc_conv_fused_fwd_sums", None, xs.data_ptr(), sums.data_ptr(), 0 if linear_ else 1, enc_dim, vc, _ptr_array(params),
+        s.rowptr.data_ptr(), s.col.data_ptr(), N, F, n, red, int(self_loop), out.data_ptr(), ws.data_ptr(), ws.numel(), st)
+    torch.cuda.synchronize()
+    assert_close(out.cpu(), ref.float(), RTOL, 5e-5, "node-sums kernel vs fp64 oracle")
+    assert_close(out.cpu(), edge.detach().cpu(), RTOL, 5e-5, "node-sums kernel vs per-edge kernel")
