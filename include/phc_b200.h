@@ -121,6 +121,10 @@ int phc_bn_act_drop_skip_bwd(const float* dy, const float* h, const float* gamma
                              int drop_same, unsigned long long seed, float* dh, float* dgamma, float* dbeta, void* workspace,
                              size_t workspace_bytes, phc_stream_t stream);
 
+/* out = srcs[0] + srcs[1] + ... (list order) over `numel` floats; srcs is a HOST array of up to 16 device pointers.  Used for the
+ * gradient of a skip connection that fans out to every layer (models.py:227-236, sc_type="first"). */
+int phc_sum_tensors(const float* const* srcs, int count, long long numel, float* out, phc_stream_t stream);
+
 /* ---- encoders (encoder.py:31-34; quaternion/encoder.py:44-56) ---------------------------------
  * tables / weights / biases are HOST arrays of device pointers, ordered [component][column]. */
 int phc_embed_sum_fwd(const long long* idx, const float* const* tables, const int* vocab, int rows, int cols, int phm_dim,

@@ -573,4 +573,47 @@ int phc_bn_act_drop_skip_bwd(const float* dy, const float* h, const float* gamma
   return phc_check_launch("phc_bn_act_drop_skip_bwd");
 }
 
+// ---- out = sum of `count` equally shaped tensors, in list order (fixed association) ----------------------------------
+// The gradient of a skip connection that fans out to L layers (models.py:227-236, sc_type="first": every layer adds the
+// same h0) is the sum of L [N,F] tensors; autograd adds them pairwise (L-1 kernels, 3 tensors of traffic each), this is
+// one pass: L reads + 1 write.
+#define PHC_SUM_MAX 16
+struct SumTable { const float* src[PHC_SUM_MAX]; };
+__global__ void __launch_bounds__(256) sum_tensors_kernel(SumTable t, int count, long long n4, long long numel, float* __restrict__ out) {
+  pdl_begin();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n4) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(t.src[0]) + i);
+    for (int k = 1; k < count; ++k) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(t.src[k]) + i);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = a;
+  } else {
+    const long long j = n4 * 4 + (i - n4);                        // scalar tail
+    if (j < numel) {
+      float a = t.src[0][j];
+      for (int k = 1; k < count; ++k) a += t.src[k][j];
+      out[j] = a;
+    }
+  }
+}
+
+int phc_sum_tensors(const float* const* srcs, int count, long long numel, float* out, cudaStream_t stream) {
+  PHC_REQUIRE(count >= 1 && count <= PHC_SUM_MAX, "phc_sum_tensors: count %d not in 1..%d", count, PHC_SUM_MAX);
+  PHC_REQUIRE(numel >= 0 && out != nullptr, "phc_sum_tensors: bad arguments");
+  if (numel == 0) return PHC_OK;
+  SumTable t;
+  bool vec = phc_aligned16(out);
+  for (int k = 0; k < count; ++k) {
+    PHC_REQUIRE(srcs[k] != nullptr, "phc_sum_tensors: null source %d", k);
+    t.src[k] = srcs[k];
+    vec = vec && phc_aligned16(srcs[k]);
+  }
+  const long long n4 = vec ? numel / 4 : 0;
+  const long long threads = n4 + (numel - 4 * n4);
+  phc_launch(sum_tensors_kernel, dim3(phc_div_up(threads, 256)), dim3(256), 0, stream, t, count, n4, numel, out);
+  return phc_check_launch("phc_sum_tensors");
+}
+
 }  // extern "C"

@@ -829,8 +829,13 @@ class PHMSkipConnectAdd(_PHMSkipConnectBase):
             edge_attr = edge_attr.to(torch.long)
         h0 = self.atomencoder.flat(x)
         h = h0
-        for i in range(len(self.mp_layers)):
-            if i == 0 or self.sc_type == "first":
+        L = len(self.mp_layers)
+        # sc_type "first": every layer adds h0 — hand each its own alias so that the L skip gradients are summed in one pass
+        first = ops.fan_out(h0, L) if (self.sc_type == "first" and L > 1) else None
+        for i in range(L):
+            if first is not None:
+                skip = first[i]
+            elif i == 0 or self.sc_type == "first":
                 skip = h0
             elif self.sc_type == "last":
                 skip = h

@@ -504,6 +504,42 @@ def weight_regularization_l2(weights: Sequence[torch.Tensor]) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------- aggregation with fused edge encoder
+# --------------------------------------------------------------------------------- skip fan-out
+class _FanOut(torch.autograd.Function):
+    """``count`` aliases of one tensor whose gradients are summed in ONE pass (csrc/norm.cu phc_sum_tensors) instead of
+    the engine's count-1 pairwise adds.  Used for the skip input that every layer of a ``sc_type="first"`` model adds
+    (reference models.py:227-236): at ppa shape seven [N,F] gradients, 105 us of pairwise adds -> one 40 us kernel."""
+
+    @staticmethod
+    def forward(ctx, x, count):
+        ctx.count = count
+        return tuple(x.detach() for _ in range(count))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        gs = [g for g in grads if g is not None]
+        if not gs:
+            return None, None
+        if len(gs) == 1:
+            return gs[0], None
+        gs = [g.contiguous() for g in gs]
+        if len(gs) > 16 or any(g.dtype != torch.float32 for g in gs):
+            out = gs[0].clone()
+            for g in gs[1:]:
+                out.add_(g)
+            return out, None
+        out = torch.empty_like(gs[0])
+        run("phc_sum_tensors", None, _ptr_array(gs), len(gs), gs[0].numel(), out.data_ptr(), _stream(out.device))
+        return out, None
+
+
+def fan_out(x: torch.Tensor, count: int):
+    """count views of x for count consumers; identity when no gradient is needed."""
+    if count <= 1 or not (torch.is_grad_enabled() and x.requires_grad) or not x.is_cuda:
+        return (x,) * max(count, 1)
+    return _FanOut.apply(x, count)
+
+
 def conv_fused_supported(width: int, phm_dim: int, linear: bool, enc_dim: int, vocab: Sequence[int]) -> bool:
     rows = enc_dim + 1 if linear else int(sum(vocab))
     return bool(_lib.load().phc_conv_fused_supported(width, phm_dim, 0 if linear else 1, enc_dim, rows))
