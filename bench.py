@@ -197,6 +197,7 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep NCCL's own messages off stdout: ONE JSON line there
         dist.init_process_group("nccl", device_id=dev)
     wl = workload(args)
     torch.manual_seed(0)
