@@ -23,6 +23,7 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
+JSON_OUT = sys.stdout
 METRIC = "train_graphs_per_sec"
 UNIT = "graphs/s"
 
@@ -131,7 +132,7 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": config_dict(args, wl, sample_graphs, "cpu"),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), file=JSON_OUT, flush=True)
 
 
 def config_dict(args, wl, graphs_per_gpu, l2):
@@ -436,12 +437,23 @@ def run_b200(args):
                "final_loss": float(loss.item())}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(wl)
-        print(json.dumps(out))
+        print(json.dumps(out), file=JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+def _claim_stdout():
+    """Only the JSON line may appear on stdout: native libraries (NCCL prints its version banner there) are pointed at
+    stderr by swapping the descriptors; the JSON is written to the saved original."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
+
+
 def main():
+    global JSON_OUT
+    JSON_OUT = _claim_stdout()
     args = parse()
     if args.impl == "reference":
         run_reference(args)
