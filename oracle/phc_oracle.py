@@ -26,6 +26,9 @@ Reference locations restated here (relative to /root/reference):
   model_forward (Add model)  phc/hypercomplex/undirectional/models.py:200-249
   weight_regularization      phc/hypercomplex/regularization.py:15-23
   train_step                 benchmarks/train_hiv.py:165-202 (and the zinc/ppa/mnist variants)
+  quaternion_* / legacy_*    phc/quaternion/layers.py:50-126, algebra.py (Hamilton product), encoder.py:62-91,
+                             norm.py:268-287, regularization.py:27-97; phc/hypercomplex/layers.py:58-78,114-192
+                             (pinned by oracle/make_golden_family.py -> tests/golden/family/)
 """
 from __future__ import annotations
 
@@ -299,6 +302,106 @@ def weight_regularization(p: Params, order: int = 2) -> torch.Tensor:
         if k.endswith(".W"):
             reg = reg + v.norm(p=order, dim=0).mean()
     return reg
+
+
+# ----------------------------------------------------------------------------- quaternion family / legacy layout
+# Hamilton product y = W (x) q written out (algebra.py QTensor.__matmul__ / hamilton_product_Wq :662-672):
+#   y_r = W_r q_r - W_i q_i - W_j q_j - W_k q_k        y_i = W_r q_i + W_i q_r + W_j q_k - W_k q_j
+#   y_j = W_r q_j - W_i q_k + W_j q_r + W_k q_i        y_k = W_r q_k + W_i q_j - W_j q_i + W_k q_r
+# as (weight component c, input component a, output component o, sign) with r,i,j,k = 0..3
+_HAMILTON_TERMS = [(0, 0, 0, 1), (1, 1, 0, -1), (2, 2, 0, -1), (3, 3, 0, -1),
+                   (0, 1, 1, 1), (1, 0, 1, 1), (2, 3, 1, 1), (3, 2, 1, -1),
+                   (0, 2, 2, 1), (1, 3, 2, -1), (2, 0, 2, 1), (3, 1, 2, 1),
+                   (0, 3, 3, 1), (1, 2, 3, 1), (2, 1, 3, -1), (3, 0, 3, 1)]
+_QNAMES = "rijk"
+
+
+def quaternion_linear(x: torch.Tensor, pq: Params, key: str) -> torch.Tensor:
+    """QLinear.forward on the flat layout [rows, 4*in] -> [rows, 4*out] (component c in column block c)."""
+    xs = x.chunk(4, dim=-1)
+    ys = [0, 0, 0, 0]
+    for c, a, o, sign in _HAMILTON_TERMS:
+        ys[o] = ys[o] + sign * (xs[a] @ pq[f"{key}.W_{_QNAMES[c]}"].t())
+    if f"{key}.b_r" in pq:
+        ys = [ys[c] + pq[f"{key}.b_{_QNAMES[c]}"] for c in range(4)]
+    return torch.cat(ys, dim=-1)
+
+
+def quaternion_as_phm(pq: Params) -> Params:
+    """Quaternion-named parameters re-expressed under the PHM keys this oracle's blocks read, as differentiable
+    functions of the quaternion leaves: W = stack(W_c^T), rule[c][a][o] = sign of the Hamilton term, b = cat(b_c);
+    encoders / batch norms named r,i,j,k become list entries 0..3; qlinear1/2 -> linear1/2."""
+    import re
+    out: Params = {}
+    rule = torch.zeros(4, 4, 4)
+    for c, a, o, sign in _HAMILTON_TERMS:
+        rule[c, a, o] = sign
+    done = set()
+    for k, v in pq.items():
+        m = re.match(r"^(.*)\.([Wb])_([rijk])$", k)
+        name = k if m is None else m.group(1)
+        name = name.replace(".qlinear1", ".linear1").replace(".qlinear2", ".linear2")
+        name = re.sub(r"\.bn\.bn\.([rijk])\.", lambda t: ".bn.bn.%d." % _QNAMES.index(t.group(1)), name)
+        name = re.sub(r"^(atomencoder|bondencoders\.\d+)\.([rijk])\.", lambda t: "%s.encoders.%d." % (t.group(1), _QNAMES.index(t.group(2))), name)
+        if m is None:
+            out[name] = v
+            continue
+        src = m.group(1)
+        if (src, m.group(2)) in done:
+            continue
+        done.add((src, m.group(2)))
+        if m.group(2) == "W":
+            out[name + ".W"] = torch.stack([pq[f"{src}.W_{q}"].t() for q in _QNAMES], dim=0)
+            out[name + ".phm_rule"] = rule.to(v.dtype)
+        else:
+            out[name + ".b"] = torch.cat([pq[f"{src}.b_{q}"] for q in _QNAMES], dim=0)
+    return out
+
+
+def quaternion_cfg(cfg: Dict) -> Dict:
+    """Constructor arguments of QuaternionSkipConnectAdd -> the cfg keys ``model_forward`` reads."""
+    c = dict(cfg)
+    c.update(phm_dim=4, sc_type="first")
+    return c
+
+
+def quaternion_model_forward(pq: Params, cfg: Dict, data, training: bool = True, generator=None) -> torch.Tensor:
+    """QuaternionSkipConnectAdd.forward (phc/quaternion/undirectional/models.py:198-215) — block for block the PHM
+    forward at n = 4 with the Hamilton product as the linear map (every skip adds the atom embedding)."""
+    return model_forward(quaternion_as_phm(pq), quaternion_cfg(cfg), data, training, generator)
+
+
+def quaternion_weight_regularization(pq: Params, cfg: Dict, order: int = 1) -> torch.Tensor:
+    """phc/quaternion/regularization.py:27-97, undirectional branch: message-passing weights, the pooling weight stacked
+    as (W_r, W_i, W_k, W_k) — line 77 as written —, downstream weights; each stack.norm(p, dim=0).mean()."""
+    stacks = []
+    for i in range(len(cfg["mp_layers"])):
+        t = f"convs.{i}.transform.transform"
+        keys = [t + ".qlinear1", t + ".qlinear2"] if cfg["mlp"] else [t]
+        for k in keys:
+            stacks.append(torch.stack([pq[f"{k}.W_{q}"] for q in _QNAMES], dim=0))
+    if cfg["pooling"] == "softattention":
+        stacks.append(torch.stack([pq[f"pooling.linear.W_{q}"] for q in "rikk"], dim=0))
+    for j in range(len(cfg["downstream_layers"]) + 1):
+        stacks.append(torch.stack([pq[f"downstream.affine.{j}.W_{q}"] for q in _QNAMES], dim=0))
+    reg = 0.0
+    for w in stacks:
+        reg = reg + w.norm(p=order, dim=0).mean()
+    return reg
+
+
+def legacy_phm_linear(x: torch.Tensor, p: Params, key: str, n: int) -> torch.Tensor:
+    """PHMLinear_Old.forward = matvec_product (phc/hypercomplex/layers.py:58-78): H = sum_i kron(A_i, W_i) with
+    W_i [out/n, in/n], y = (H x^T)^T + cat(b_i).  ``key`` may be "" for a bare layer."""
+    pre = key + "." if key else ""
+    H = 0
+    for i in range(n):                                   # kron(A_i, W_i)[(a,o),(c,k)] = A_i[a,c] * W_i[o,k]
+        A, W = p[f"{pre}phm_rule.{i}"], p[f"{pre}W.{i}"]
+        H = H + (A[:, None, :, None] * W[None, :, None, :]).reshape(n * W.size(0), n * W.size(1))
+    y = x @ H.t()
+    if f"{pre}b.0" in p:
+        y = y + torch.cat([p[f"{pre}b.{i}"] for i in range(n)], dim=-1)
+    return y
 
 
 def task_loss(logits: torch.Tensor, y: torch.Tensor, kind: str) -> torch.Tensor:

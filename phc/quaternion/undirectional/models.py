@@ -1,12 +1,2 @@
-class _OutOfScope(object):
-    def __init__(self, *a, **k):
-        raise NotImplementedError("the quaternion model family is out of scope of the B200 hot path (SURVEY.md §2); "
-                                  "use --type undirectional-phm-sc-add")
-
-
-class QuaternionSkipConnectAdd(_OutOfScope):
-    pass
-
-
-class QuaternionSkipConnectConcat(_OutOfScope):
-    pass
+"""reference phc/quaternion/undirectional/models.py — the quaternion family on the PHM kernels (n = 4, fixed Hamilton rule)."""
+from phc_gnn_b200.quaternion import QuaternionSkipConnectAdd, QuaternionSkipConnectConcat  # noqa: F401

@@ -1,0 +1,93 @@
+"""Quaternion family and legacy-layout parameters on the CUDA path against the vectors recorded from
+the UNMODIFIED reference (tests/golden/family, oracle/make_golden_family.py).  The quaternion models run the same kernels
+as the PHM models with n = 4 and a frozen Hamilton rule — this file is also the coverage of ``learn_phm=False``."""
+import pytest
+import torch
+
+from gpu_util import assert_close
+from oracle import phc_oracle as O
+from test_family_host import load_family, quaternion_cases
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4      # north_star fp32 tolerance
+DEV = "cuda:0"
+
+
+def _tol(ref, rtol=RTOL):
+    return max(rtol * float(ref.abs().max()), 2e-6)
+
+
+def _run(fx, fuse):
+    from phc.quaternion.regularization import quaternion_weight_regularization
+    from phc.quaternion.undirectional.models import QuaternionSkipConnectAdd
+    m = QuaternionSkipConnectAdd(**fx["cfg"])
+    m.load_quaternion_state_dict(fx["state"])
+    m = m.to(DEV)
+    m.fuse_edge_encoder = fuse != "none"
+    m.fuse_layer = fuse == "direct"
+    data = fx["batch"].to(DEV)
+    m.train()
+    logits = m(data)
+    reg = quaternion_weight_regularization(m, device=DEV, p=2)
+    loss = O.task_loss(logits, data.y, fx["loss_kind"]) + fx["reg_scale"] * reg
+    loss.backward()
+    torch.cuda.synchronize()
+    grads = {k: v.detach().cpu() for k, v in m.quaternion_named_gradients().items()}
+    running = {k: v.detach().cpu() for k, v in m.quaternion_state_dict().items() if "running" in k or "tracked" in k}
+    m.eval()
+    with torch.no_grad():
+        ev = m(data).cpu()
+    return m, logits.detach().cpu(), reg.detach().cpu(), loss.detach().cpu(), grads, running, ev
+
+
+@pytest.mark.parametrize("fuse", ["direct", "none"], ids=["one-call-per-layer", "separate-ops"])
+@pytest.mark.parametrize("name", quaternion_cases())
+def test_quaternion_model_matches_reference_golden(name, fuse, monkeypatch):
+    monkeypatch.setenv("PHC_PRECISION", "fp32")
+    fx = load_family(name)
+    m, logits, reg, loss, grads, running, ev = _run(fx, fuse)
+    assert_close(logits, fx["logits_train"], RTOL, _tol(fx["logits_train"]), f"{name}: train logits")
+    assert_close(reg, fx["reg"], RTOL, 1e-6, f"{name}: regulariser")
+    assert_close(loss, fx["loss"], RTOL, _tol(fx["loss"]), f"{name}: loss")
+    assert_close(ev, fx["logits_eval"], RTOL, _tol(fx["logits_eval"]), f"{name}: eval logits")
+    for k, g in fx["grads"].items():
+        assert k in grads, f"{name}: no gradient for {k}"
+        assert_close(grads[k], g, 5 * RTOL, 10 * _tol(g), f"{name}: grad {k}")
+    for k, v in fx["running_after"].items():
+        assert_close(running[k].float(), v.float(), RTOL, max(1e-5, _tol(v.float())), f"{name}: {k}")
+    for mod in m.modules():                                      # the rule stayed frozen and untouched
+        r = getattr(mod, "phm_rule", None)
+        if isinstance(r, torch.nn.Parameter):
+            assert r.grad is None and not r.requires_grad
+
+
+def test_quaternion_regulariser_p1_matches_oracle():
+    from phc.quaternion.regularization import quaternion_weight_regularization
+    from phc.quaternion.undirectional.models import QuaternionSkipConnectAdd
+    fx = load_family("quaternion_hiv_softmax_mlp")
+    m = QuaternionSkipConnectAdd(**fx["cfg"])
+    m.load_quaternion_state_dict(fx["state"])
+    m = m.to(DEV)
+    got = quaternion_weight_regularization(m, device=DEV, p=1)
+    want = O.quaternion_weight_regularization({k: v for k, v in fx["state"].items()}, fx["cfg"], 1)
+    assert_close(got.detach().cpu(), want, RTOL, 1e-6, "p=1 regulariser")
+
+
+def test_legacy_phm_linear_on_device(monkeypatch):
+    """PHMLinear_Old vectors from the reference through the CUDA PHMLinear on converted parameters."""
+    monkeypatch.setenv("PHC_PRECISION", "fp32")
+    from phc.hypercomplex.layers import PHMLinear
+    from phc_gnn_b200 import legacy
+    for key, fx in load_family("legacy_phmlinear").items():
+        n = fx["n"]
+        lin = PHMLinear(n * fx["in_per"], n * fx["out_per"], n, c_init="standard")
+        lin.load_state_dict(legacy.convert_legacy_phm_state_dict(fx["state"]), strict=True)
+        lin = lin.to(DEV)
+        x = fx["x"].to(DEV).requires_grad_(True)
+        y = lin(x)
+        assert_close(y.detach().cpu(), fx["y"], RTOL, _tol(fx["y"]), f"{key}: y")
+        y.backward(fx["gy"].to(DEV))
+        assert_close(x.grad.cpu(), fx["gx"], RTOL, _tol(fx["gx"]), f"{key}: dx")
+        g = legacy.to_legacy_phm_state_dict({k: p.grad.detach().cpu() for k, p in lin.named_parameters()})
+        for k, want in fx["grads"].items():
+            assert_close(g[k], want, 5 * RTOL, 10 * _tol(want), f"{key}: grad {k}")
