@@ -77,6 +77,20 @@ int phc_remove_isolated_nodes(const long long* edge_index, int num_edges, int nu
                               long long* new_edge_index, long long* edge_order, int* counts, void* workspace, size_t workspace_bytes,
                               phc_stream_t stream);
 
+/* ---- batch preparation: Batch collate from a dataset resident in HBM (replaces the CPU DataLoader collate,
+ * torch_geometric.data.DataLoader -> Batch.from_data_list, reference benchmarks/train_hiv.py:556-561 and the other train_*.py;
+ * restated in oracle/phc_oracle.py::collate).  Store: graphs packed back to back — node_ptr / edge_ptr int64 [store_graphs+1],
+ * edge_index int64 [2, store_edges] with node ids LOCAL to each graph, x rows per node, edge_attr rows per edge, y rows per graph
+ * (row sizes in bytes, multiples of 4; pass 0 / NULL to skip a tensor).  Batch: graph_ids int64 [num_graphs] (any order,
+ * repeats allowed), out_node_ptr / out_edge_ptr int64 [num_graphs+1] = exclusive prefix sums of the selected graphs' sizes
+ * (checked on the device).  Writes out_edge_index [2, out_edges] (shifted by the batch node offsets), out_batch [out_nodes],
+ * and the gathered rows.  status: DEVICE int, bit0 graph id out of range, bit1 prefix sums do not match.  Bit-exact. */
+int phc_collate_batch(const long long* graph_ids, int num_graphs, int store_graphs, const long long* node_ptr, const long long* edge_ptr,
+                      const long long* out_node_ptr, const long long* out_edge_ptr, const long long* edge_index, long long store_edges,
+                      long long* out_edge_index, long long out_edges, long long out_nodes, long long* out_batch, const void* x, void* out_x,
+                      int x_row_bytes, const void* edge_attr, void* out_edge_attr, int edge_attr_row_bytes, const void* y, void* out_y,
+                      int y_row_bytes, int* status, phc_stream_t stream);
+
 /* ---- fused neighbour aggregation (messagepassing.py:72-74,136-138,297-300) -------------------
  * out[i] = (self_loop ? x[i] : 0) + AGG_{e: dst(e)=i} act(x[src(e)] + ea[e])
  * aux_f: [2,N,F] (softmax only: log-sum-exp and aggregate), aux_i: [N,F] (max/min only: winning edge id).

@@ -484,3 +484,43 @@ def remove_isolated_nodes(edge_index: torch.Tensor, edge_attr=None, num_nodes=No
         ea = edge_attr.cpu()
         attr = torch.cat([ea[nl_idx], ea[keep_loops]], dim=0)
     return out, attr, mask
+
+
+def collate(graphs):
+    """torch_geometric.data.Batch.from_data_list (PyG 1.6.1, as the reference's DataLoader calls it for every mini-batch,
+    benchmarks/train_hiv.py:556-561): per key concatenate along the node / edge axis, ``edge_index`` shifted by the
+    cumulative node count (``__inc__``), ``batch`` = position of the graph repeated per node, ``y`` concatenated along
+    dim 0.  Returns (x, edge_index, edge_attr, batch, y).  Documented PyG behaviour; the package is not installable here,
+    so this is pinned by a hand-worked example and by the round trip against synthetic.make_batch (which builds its batches
+    graph by graph in exactly this way)."""
+    xs, eis, eas, bs, ys = [], [], [], [], []
+    off = 0
+    for b, g in enumerate(graphs):
+        n = g.x.size(0)
+        xs.append(g.x)
+        eis.append(g.edge_index + off)
+        if getattr(g, "edge_attr", None) is not None:
+            eas.append(g.edge_attr)
+        if getattr(g, "y", None) is not None:
+            ys.append(g.y if g.y.dim() > 0 else g.y.view(1))
+        bs.append(torch.full((n,), b, dtype=torch.int64))
+        off += n
+    return (torch.cat(xs, 0), torch.cat(eis, 1), torch.cat(eas, 0) if eas else None, torch.cat(bs, 0),
+            torch.cat(ys, 0) if ys else None)
+
+
+def split_batch(data):
+    """Inverse of ``collate`` for a batch whose edges are grouped by graph: list of single-graph GraphBatch-like objects
+    with local node ids (test helper: turns a synthetic mini-batch into a dataset)."""
+    import types
+    out = []
+    B = int(data.num_graphs)
+    nptr = graph_ptr(data.batch, B).tolist()
+    egraph = data.batch[data.edge_index[0]]
+    eptr = graph_ptr(egraph, B).tolist()
+    for b in range(B):
+        n0, n1, e0, e1 = nptr[b], nptr[b + 1], eptr[b], eptr[b + 1]
+        out.append(types.SimpleNamespace(x=data.x[n0:n1].clone(), edge_index=(data.edge_index[:, e0:e1] - n0).clone(),
+                                         edge_attr=None if data.edge_attr is None else data.edge_attr[e0:e1].clone(),
+                                         y=None if data.y is None else data.y[b:b + 1].clone()))
+    return out

@@ -138,3 +138,111 @@ int phc_remove_isolated_nodes(const long long* edge_index, int num_edges, int nu
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------------
+// Batch collate on the device: what the reference's DataLoader does on the CPU for every step
+// (torch_geometric.data.DataLoader -> Batch.from_data_list, used at benchmarks/train_hiv.py:556-561 and the other
+// train_*.py): node / edge tensors of the selected graphs concatenated in batch order, each graph's edge_index shifted
+// by the number of nodes before it, `batch` = graph position repeated per node, graph-level targets stacked.
+// Here the dataset is RESIDENT IN HBM as one packed store (graphs back to back, edge ids local to their graph), so a
+// mini-batch is B contiguous segment copies per tensor — one launch, one pass over the bytes, no host involvement
+// beyond the [B] graph ids and their size prefix sums.  Integer / byte work only: bit-exact with the CPU restatement
+// (oracle/phc_oracle.py::collate).
+namespace {
+
+struct CollateRows {
+  const char* src;
+  char* dst;
+  long long row_bytes;        // multiple of 4; 0 = tensor absent
+};
+
+template <typename Word>
+__device__ __forceinline__ void collate_copy_words(const char* src, char* dst, long long bytes, long long tid, long long nth) {
+  const Word* s = reinterpret_cast<const Word*>(src);
+  Word* d = reinterpret_cast<Word*>(dst);
+  const long long n = bytes / (long long)sizeof(Word);
+  for (long long j = tid; j < n; j += nth) d[j] = s[j];
+}
+
+// rows [first, first+count) of the store -> rows [out_first, ...) of the batch; widest word the row size allows (the
+// tensors come from the torch allocator, 256-byte aligned, so a segment offset is aligned to gcd(row_bytes, 16))
+__device__ __forceinline__ void collate_copy_rows(const CollateRows& r, long long first, long long count, long long out_first,
+                                                  long long tid, long long nth) {
+  if (r.row_bytes == 0 || count <= 0) return;
+  const char* src = r.src + first * r.row_bytes;
+  char* dst = r.dst + out_first * r.row_bytes;
+  const long long bytes = count * r.row_bytes;
+  if (r.row_bytes % 16 == 0) collate_copy_words<uint4>(src, dst, bytes, tid, nth);
+  else if (r.row_bytes % 8 == 0) collate_copy_words<unsigned long long>(src, dst, bytes, tid, nth);
+  else collate_copy_words<unsigned int>(src, dst, bytes, tid, nth);
+}
+
+// grid = (slices, B): blockIdx.y = position of the graph in the batch, the slices of one row of blocks share its elements
+__global__ void __launch_bounds__(256) collate_kernel(const long long* __restrict__ ids, int B, int G,
+                                                      const long long* __restrict__ node_ptr, const long long* __restrict__ edge_ptr,
+                                                      const long long* __restrict__ out_node_ptr,
+                                                      const long long* __restrict__ out_edge_ptr,
+                                                      const long long* __restrict__ ei, long long store_edges,
+                                                      long long* __restrict__ out_ei, long long out_edges,
+                                                      long long* __restrict__ out_batch, CollateRows xr, CollateRows er, CollateRows yr,
+                                                      int* __restrict__ status) {
+  pdl_begin();
+  const int b = blockIdx.y;
+  const long long g = ids[b];
+  if (g < 0 || g >= G) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(status, 1);
+    return;
+  }
+  const long long n0 = node_ptr[g], nn = node_ptr[g + 1] - n0;
+  const long long e0 = edge_ptr[g], ne = edge_ptr[g + 1] - e0;
+  const long long on0 = out_node_ptr[b], oe0 = out_edge_ptr[b];
+  if (nn < 0 || ne < 0 || nn != out_node_ptr[b + 1] - on0 || ne != out_edge_ptr[b + 1] - oe0) {   // offsets not of THESE graphs
+    if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(status, 2);
+    return;
+  }
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nth = (long long)gridDim.x * blockDim.x;
+  for (long long j = tid; j < nn; j += nth) out_batch[on0 + j] = b;
+  for (long long j = tid; j < ne; j += nth) {
+    out_ei[oe0 + j] = ei[e0 + j] + on0;
+    out_ei[out_edges + oe0 + j] = ei[store_edges + e0 + j] + on0;
+  }
+  collate_copy_rows(xr, n0, nn, on0, tid, nth);
+  collate_copy_rows(er, e0, ne, oe0, tid, nth);
+  if (blockIdx.x == 0) collate_copy_rows(yr, g, 1, b, threadIdx.x, blockDim.x);
+}
+
+}  // namespace
+
+extern "C" {
+
+// status (device int, zeroed here): bit0 = graph id outside [0, store_graphs), bit1 = out_*_ptr are not the prefix sums of the
+// selected graphs' sizes.  A tensor is skipped when its row size is 0.
+int phc_collate_batch(const long long* graph_ids, int num_graphs, int store_graphs, const long long* node_ptr, const long long* edge_ptr,
+                      const long long* out_node_ptr, const long long* out_edge_ptr, const long long* edge_index, long long store_edges,
+                      long long* out_edge_index, long long out_edges, long long out_nodes, long long* out_batch, const void* x, void* out_x,
+                      int x_row_bytes, const void* edge_attr, void* out_edge_attr, int edge_attr_row_bytes, const void* y, void* out_y,
+                      int y_row_bytes, int* status, cudaStream_t stream) {
+  PHC_REQUIRE(num_graphs >= 0 && store_graphs >= 0 && store_edges >= 0 && out_edges >= 0 && out_nodes >= 0,
+              "phc_collate_batch: negative size");
+  PHC_REQUIRE(x_row_bytes >= 0 && edge_attr_row_bytes >= 0 && y_row_bytes >= 0 && x_row_bytes % 4 == 0 &&
+                  edge_attr_row_bytes % 4 == 0 && y_row_bytes % 4 == 0,
+              "phc_collate_batch: row sizes must be non-negative multiples of 4 bytes");
+  PHC_REQUIRE(num_graphs <= 65535, "phc_collate_batch: at most 65535 graphs per batch");
+  cudaMemsetAsync(status, 0, sizeof(int), stream);
+  if (num_graphs == 0) return phc_check_launch("phc_collate_batch");
+  CollateRows xr{static_cast<const char*>(x), static_cast<char*>(out_x), (x && out_x) ? (long long)x_row_bytes : 0};
+  CollateRows er{static_cast<const char*>(edge_attr), static_cast<char*>(out_edge_attr),
+                 (edge_attr && out_edge_attr) ? (long long)edge_attr_row_bytes : 0};
+  CollateRows yr{static_cast<const char*>(y), static_cast<char*>(out_y), (y && out_y) ? (long long)y_row_bytes : 0};
+  // bytes one graph moves on average -> slices of 256 threads x 64 B each, at most 16 per graph
+  const long long per_graph = (out_edges * (16 + er.row_bytes) + out_nodes * (8 + xr.row_bytes)) / num_graphs;
+  long long slices = (per_graph + 256 * 64 - 1) / (256 * 64);
+  slices = slices < 1 ? 1 : (slices > 16 ? 16 : slices);
+  phc_launch(collate_kernel, dim3((unsigned)slices, (unsigned)num_graphs), dim3(256), 0, stream, graph_ids, num_graphs, store_graphs,
+             node_ptr, edge_ptr, out_node_ptr, out_edge_ptr, edge_index, store_edges, out_edge_index, out_edges, out_batch, xr, er, yr,
+             status);
+  return phc_check_launch("phc_collate_batch");
+}
+
+}  // extern "C"

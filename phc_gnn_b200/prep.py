@@ -1,16 +1,23 @@
-"""Batch preparation on the device: ``RemoveIsolatedNodes``.
+"""Batch preparation on the device: ``RemoveIsolatedNodes`` and the mini-batch collate (``DeviceGraphStore``).
 
 The reference's training loops apply ``torch_geometric.transforms.RemoveIsolatedNodes`` to every batch after moving it
 to the GPU (benchmarks/train_hiv.py:171-173, :233-234, :457; benchmarks/utils.py:39-49 has the same transform spelled
 out).  PyG runs it as a dozen index kernels plus boolean-mask gathers; here the index work is one C-ABI call
 (``phc_remove_isolated_nodes``, csrc/prep.cu) and the only host synchronisation is the read-back of the three output
 sizes, which PyG needs as well (``mask.sum()``).
+
+The reference's ``DataLoader`` collates every mini-batch on the CPU (``Batch.from_data_list``: concatenate, shift each graph's
+``edge_index``, build ``batch``; benchmarks/train_hiv.py:556-561) and the loop then copies it to the GPU (:171).  With 180 GB of
+HBM the whole dataset fits on the device (ogbg-ppa, the largest, is ~10 GB as int64/fp32 tensors): ``DeviceGraphStore`` keeps it
+packed in HBM and ``collate(ids)`` assembles a mini-batch with ONE kernel (``phc_collate_batch``, csrc/prep.cu) — the host only
+sends the [B] graph ids and their size prefix sums (a few KB, one pinned copy), and there is no host synchronisation.
 """
 from __future__ import annotations
 
 import copy
-from typing import Optional, Tuple
+from typing import Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -69,3 +76,107 @@ class RemoveIsolatedNodes(object):
 
     def __repr__(self):
         return f"{self.__class__.__name__}()"
+
+
+class DeviceGraphStore(object):
+    """A graph dataset packed in device memory + the PyG-compatible collate of a mini-batch from it.
+
+    ``graphs``: sequence of objects with ``x`` [n_g, ...], ``edge_index`` int64 [2, e_g] (node ids local to the graph),
+    ``edge_attr`` [e_g, ...] or None, ``y`` (one row per graph, any trailing shape) or None — e.g. PyG ``Data`` objects or
+    ``synthetic.GraphBatch``es of one graph.  Row payloads must be 4- or 8-byte dtypes (int64 / float32 in the reference).
+    """
+
+    def __init__(self, graphs: Sequence, device):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("DeviceGraphStore lives in GPU memory; there is no CPU fallback")
+        assert len(graphs) > 0, "empty dataset"
+        nn = np.array([int(g.x.size(0)) for g in graphs], dtype=np.int64)
+        ne = np.array([int(g.edge_index.size(1)) for g in graphs], dtype=np.int64)
+        self.num_graphs = len(graphs)
+        self.node_ptr_host = np.concatenate([[0], np.cumsum(nn)]).astype(np.int64)
+        self.edge_ptr_host = np.concatenate([[0], np.cumsum(ne)]).astype(np.int64)
+        self.node_ptr = torch.from_numpy(self.node_ptr_host).to(device)
+        self.edge_ptr = torch.from_numpy(self.edge_ptr_host).to(device)
+        self.x = torch.cat([g.x for g in graphs], dim=0).contiguous().to(device)
+        ei = torch.cat([g.edge_index for g in graphs], dim=1)
+        assert ei.dtype == torch.int64 and ei.dim() == 2 and ei.size(0) == 2, "edge_index must be int64 [2, E]"
+        self.edge_index = ei.contiguous().to(device)
+        has_attr = getattr(graphs[0], "edge_attr", None) is not None
+        self.edge_attr = torch.cat([g.edge_attr for g in graphs], dim=0).contiguous().to(device) if has_attr else None
+        has_y = getattr(graphs[0], "y", None) is not None
+        if has_y:
+            ys = [g.y if g.y.dim() > 0 else g.y.view(1) for g in graphs]
+            assert all(y.size(0) == 1 for y in ys), "y must hold one row per graph"
+            self.y = torch.cat(ys, dim=0).contiguous().to(device)
+        else:
+            self.y = None
+        for name in ("x", "edge_attr", "y"):
+            t = getattr(self, name)
+            if t is not None:
+                assert t.element_size() in (4, 8), f"{name}: 4- or 8-byte element types only, got {t.dtype}"
+                assert t.data_ptr() % 16 == 0
+        self.device = device
+        self._staging = None                 # pinned [ids | out_node_ptr | out_edge_ptr], reused between calls
+        self._copy_done = None
+        self._last_status = None
+
+    @staticmethod
+    def _row_bytes(t: Optional[torch.Tensor]) -> int:
+        if t is None:
+            return 0
+        return int(t[0].numel()) * t.element_size() if t.size(0) > 0 else int(np.prod(t.shape[1:], dtype=np.int64)) * t.element_size()
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in (self.x, self.edge_index, self.edge_attr, self.y, self.node_ptr, self.edge_ptr)
+                   if t is not None)
+
+    def collate(self, ids) -> "object":
+        """``Batch.from_data_list([dataset[i] for i in ids])`` -> ``synthetic.GraphBatch`` on the device.  ``ids``: host
+        sequence / numpy array / CPU tensor of graph indices (any order, repeats allowed)."""
+        from .synthetic import GraphBatch
+        ids_np = np.asarray(ids.cpu().numpy() if torch.is_tensor(ids) else ids, dtype=np.int64).reshape(-1)
+        B = int(ids_np.shape[0])
+        if B and (ids_np.min() < 0 or ids_np.max() >= self.num_graphs):
+            raise IndexError("graph id outside the store")
+        onp = np.zeros(B + 1, dtype=np.int64)
+        oep = np.zeros(B + 1, dtype=np.int64)
+        np.cumsum(self.node_ptr_host[ids_np + 1] - self.node_ptr_host[ids_np], out=onp[1:])
+        np.cumsum(self.edge_ptr_host[ids_np + 1] - self.edge_ptr_host[ids_np], out=oep[1:])
+        N, E = int(onp[-1]), int(oep[-1])
+        words = 3 * B + 2
+        if self._staging is None or self._staging.numel() < words:
+            self._staging = torch.empty(max(words, 1024), dtype=torch.int64).pin_memory()
+        if self._copy_done is not None:
+            self._copy_done.synchronize()         # previous batch's ids have left the pinned buffer (normally long done)
+        host = self._staging[:words]
+        host[:B] = torch.from_numpy(ids_np)
+        host[B:2 * B + 1] = torch.from_numpy(onp)
+        host[2 * B + 1:] = torch.from_numpy(oep)
+        dev = self.device
+        meta = host.to(dev, non_blocking=True)
+        self._copy_done = torch.cuda.Event()      # the staging buffer is reused by the next call: it waits for this copy
+        self._copy_done.record(torch.cuda.current_stream(dev))
+        d_ids, d_onp, d_oep = meta[:B], meta[B:2 * B + 1], meta[2 * B + 1:]
+        out_ei = torch.empty((2, E), dtype=torch.int64, device=dev)
+        out_batch = torch.empty(N, dtype=torch.int64, device=dev)
+        out_x = torch.empty((N,) + tuple(self.x.shape[1:]), dtype=self.x.dtype, device=dev)
+        out_ea = (torch.empty((E,) + tuple(self.edge_attr.shape[1:]), dtype=self.edge_attr.dtype, device=dev)
+                  if self.edge_attr is not None else None)
+        out_y = torch.empty((B,) + tuple(self.y.shape[1:]), dtype=self.y.dtype, device=dev) if self.y is not None else None
+        status = torch.empty(1, dtype=torch.int32, device=dev)
+        p = lambda t: 0 if t is None else t.data_ptr()      # noqa: E731
+        run("phc_collate_batch", dev, d_ids.data_ptr(), B, self.num_graphs, self.node_ptr.data_ptr(), self.edge_ptr.data_ptr(),
+            d_onp.data_ptr(), d_oep.data_ptr(), self.edge_index.data_ptr(), int(self.edge_index.size(1)), out_ei.data_ptr(), E, N,
+            out_batch.data_ptr(), p(self.x), p(out_x), self._row_bytes(self.x), p(self.edge_attr), p(out_ea),
+            self._row_bytes(self.edge_attr), p(self.y), p(out_y), self._row_bytes(self.y), status.data_ptr(), _stream(dev), launches=1)
+        self._last_status = status               # checked lazily (check_status) so that collate itself never synchronises
+        return GraphBatch(out_x, out_ei, out_ea, out_batch, out_y, B)
+
+    def check_status(self) -> None:
+        """Raise if the last collate reported an inconsistency (synchronises; for tests / debugging)."""
+        s = int(self._last_status.item())
+        if s & 1:
+            raise IndexError("phc_collate_batch: graph id outside the store")
+        if s & 2:
+            raise RuntimeError("phc_collate_batch: size prefix sums do not match the selected graphs")

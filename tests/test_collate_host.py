@@ -1,0 +1,40 @@
+"""CPU restatement of the PyG mini-batch collate (oracle/phc_oracle.py::collate): a hand-worked known answer and the
+round trip against the synthetic batches (which are built graph by graph in the same way)."""
+import types
+
+import pytest
+import torch
+
+from oracle import phc_oracle as O
+
+
+def test_collate_known_answer():
+    g0 = types.SimpleNamespace(x=torch.tensor([[1, 2], [3, 4], [5, 6]]), edge_index=torch.tensor([[0, 1, 2], [1, 2, 0]]),
+                               edge_attr=torch.tensor([[10], [11], [12]]), y=torch.tensor([[0.5]]))
+    g1 = types.SimpleNamespace(x=torch.tensor([[7, 8], [9, 10]]), edge_index=torch.tensor([[0, 1], [1, 0]]),
+                               edge_attr=torch.tensor([[20], [21]]), y=torch.tensor([[1.5]]))
+    x, ei, ea, batch, y = O.collate([g1, g0, g1])
+    assert x.tolist() == [[7, 8], [9, 10], [1, 2], [3, 4], [5, 6], [7, 8], [9, 10]]
+    assert ei.tolist() == [[0, 1, 2, 3, 4, 5, 6], [1, 0, 3, 4, 2, 6, 5]]
+    assert ea.view(-1).tolist() == [20, 21, 10, 11, 12, 20, 21]
+    assert batch.tolist() == [0, 0, 1, 1, 1, 2, 2]
+    assert y.view(-1).tolist() == [1.5, 0.5, 1.5]
+
+
+@pytest.mark.parametrize("wl_name", ["hiv", "zinc", "mnist", "ppa"])
+def test_split_then_collate_is_identity(wl_name):
+    from phc_gnn_b200.synthetic import make_batch, workloads
+    data = make_batch(workloads(4)[wl_name], seed=2, batch_graphs=5)
+    graphs = O.split_batch(data)
+    assert len(graphs) == 5 and all(int(g.edge_index.min()) >= 0 and int(g.edge_index.max()) < g.x.size(0) for g in graphs)
+    x, ei, ea, batch, y = O.collate(graphs)
+    assert torch.equal(x, data.x) and torch.equal(ei, data.edge_index) and torch.equal(ea, data.edge_attr)
+    assert torch.equal(batch, data.batch) and torch.equal(y, data.y)
+
+
+def test_device_store_refuses_cpu():
+    from phc_gnn_b200.prep import DeviceGraphStore
+    from phc_gnn_b200.synthetic import make_batch, workloads
+    graphs = O.split_batch(make_batch(workloads(4)["zinc"], seed=0, batch_graphs=2))
+    with pytest.raises(RuntimeError):
+        DeviceGraphStore(graphs, "cpu")
