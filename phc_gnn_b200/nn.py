@@ -739,6 +739,7 @@ class _PHMSkipConnectBase(nn.Module):
         self.msg_encoder_str, self.phm_rule = msg_encoder, phm_rule
         self.variable_phm = phm_rule is None
         self.phm_dim, self.learn_phm = phm_dim, learn_phm
+        self._n = phm_dim                      # the quaternion subclasses drop the public ``phm_dim`` attribute (quaternion.py)
         self.atom_input_dims, self.bond_input_dims = atom_input_dims, bond_input_dims
         self.atom_encoded_dim = atom_encoded_dim // phm_dim
         self.naive_encoder, self.w_init, self.c_init, self.same_dropout = naive_encoder, w_init, c_init, same_dropout
@@ -820,7 +821,7 @@ class PHMSkipConnectAdd(_PHMSkipConnectBase):
     def compute_hidden_layer_embedding(self, conv, norm, x, edge_index, edge_attr, dropout_mpnn: float, size=None) -> torch.Tensor:
         """conv -> norm -> act -> dropout -> + skip   (reference models.py:200-217); the last four are one kernel."""
         h = conv(x=x[0], edge_index=edge_index, edge_attr=edge_attr, size=size)
-        return norm_act_drop_skip(norm, h, x[1], self.activation_str.lower(), self.phm_dim, self.training,
+        return norm_act_drop_skip(norm, h, x[1], self.activation_str.lower(), self._n, self.training,
                                   drop_p=dropout_mpnn, drop_same=self.same_dropout)
 
     def forward(self, data, size=None) -> torch.Tensor:
@@ -852,7 +853,7 @@ class PHMSkipConnectAdd(_PHMSkipConnectBase):
                     continue
                 # bond encoder fused into the aggregation: the [E,F] edge embedding of models.py:238-240 is never formed
                 z = self.convs[i](h, edge_index, edge_attr, size, encoder=enc)
-                h = norm_act_drop_skip(self.norms[i], z, skip, self.activation_str.lower(), self.phm_dim, self.training,
+                h = norm_act_drop_skip(self.norms[i], z, skip, self.activation_str.lower(), self._n, self.training,
                                        drop_p=self.dropout_mpnn[i], drop_same=self.same_dropout)
                 continue
             e = self._encode_edges(i, edge_attr)
@@ -891,7 +892,7 @@ class PHMSkipConnectConcat(_PHMSkipConnectBase):
             skip = h0 if (i == 0 or self.sc_type == "first") else h
             e = self._encode_edges(i, edge_attr)
             z = self.convs[i](x=h, edge_index=edge_index, edge_attr=e, size=size)
-            z = norm_act_drop_skip(self.norms[i], z, None, act, self.phm_dim, self.training, drop_p=self.dropout_mpnn[i],
+            z = norm_act_drop_skip(self.norms[i], z, None, act, self._n, self.training, drop_p=self.dropout_mpnn[i],
                                    drop_same=self.same_dropout)
             h = torch.cat([z, skip], dim=-1)          # flat concat, as the reference intends (models.py:467)
         out = self.pooling(h, batch, getattr(data, "num_graphs", None))

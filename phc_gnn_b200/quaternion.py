@@ -128,6 +128,12 @@ class _QuaternionMixin(object):
         for d in [atom_encoded_dim] + list(mp_layers) + list(downstream_layers):
             assert d % 4 == 0, f"width {d} is not divisible by 4 (the reference would silently floor it)"
 
+    def _hide_phm_attributes(self):
+        """The training scripts tell the families apart by ``hasattr(model, "phm_dim")`` (reference
+        benchmarks/train_hiv.py:182 picks quaternion_weight_regularization when it is absent), so a quaternion model must
+        not expose it; the forward reads the private ``_n``."""
+        self.__dict__.pop("phm_dim", None)
+
     def reset_parameters(self):
         super().reset_parameters()
         for m in self.modules():
@@ -169,6 +175,7 @@ class QuaternionSkipConnectAdd(_QuaternionMixin, PHMSkipConnectAdd):
             msg_aggr=msg_aggr, node_aggr=node_aggr, mlp=mlp, pooling=pooling, activation=activation, real_trafo=real_trafo,
             downstream_layers=downstream_layers, target_dim=target_dim, dropout_dn=dropout_dn, norm_dn=norm_dn,
             msg_encoder=msg_encoder, sc_type="first", **kwargs)
+        self._hide_phm_attributes()
 
 
 class QuaternionSkipConnectConcat(_QuaternionMixin, PHMSkipConnectConcat):
@@ -193,6 +200,7 @@ class QuaternionSkipConnectConcat(_QuaternionMixin, PHMSkipConnectConcat):
             msg_aggr=msg_aggr, node_aggr=node_aggr, mlp=mlp, pooling=pooling, activation=activation, real_trafo=real_trafo,
             downstream_layers=downstream_layers, target_dim=target_dim, dropout_dn=dropout_dn, norm_dn=norm_dn,
             msg_encoder=msg_encoder, sc_type="first", **kwargs)
+        self._hide_phm_attributes()
 
 
 # ------------------------------------------------------------------------------------------------- regulariser

@@ -131,6 +131,20 @@ def test_quaternion_reset_parameters(init):
         assert float((gram - eye).abs().max()) < 1e-5
 
 
+def test_scripts_family_switch():
+    """benchmarks/train_hiv.py:182 picks the regulariser by ``hasattr(model, "phm_dim")``."""
+    from phc.hypercomplex.undirectional.models import PHMSkipConnectAdd
+    from phc.quaternion.undirectional.models import QuaternionSkipConnectAdd, QuaternionSkipConnectConcat
+    kw = dict(atom_encoded_dim=16, mp_layers=[16, 16], dropout_mpnn=[0.0, 0.0], downstream_layers=[16, 8])
+    assert hasattr(PHMSkipConnectAdd(**kw), "phm_dim")
+    for cls in (QuaternionSkipConnectAdd, QuaternionSkipConnectConcat):
+        m = cls(init="glorot-uniform", **kw)
+        assert not hasattr(m, "phm_dim") and m._n == 4
+        import pickle
+        m2 = pickle.loads(pickle.dumps(m))                      # scripts save whole modules (train_hiv.py:344)
+        assert not hasattr(m2, "phm_dim") and m2._n == 4
+
+
 def test_q_batch_norm_is_refused():
     from phc.quaternion.undirectional.models import QuaternionSkipConnectAdd
     with pytest.raises(NotImplementedError):
