@@ -7,8 +7,8 @@ TEST INFRASTRUCTURE (see oracle/make_golden.py for how the reference is imported
 
 * ``legacy_phmlinear.pt`` — ``PHMLinear_Old`` (reference phc/hypercomplex/layers.py:114-192, the layout of the shipped
   checkpoints) with seeded parameters: legacy state dict, input, output, and the gradients of input and parameters;
-* ``quaternion_*.pt`` — the reference's ``QuaternionSkipConnectAdd`` (phc/quaternion/undirectional/models.py:25-230)
-  on tiny seeded configurations: quaternion-layout state dict, batch, train/eval logits, loss, regulariser
+* ``quaternion_*.pt`` — the reference's ``QuaternionSkipConnectAdd`` (phc/quaternion/undirectional/models.py:25-230) and,
+  for the names containing "concat", ``QuaternionSkipConnectConcat`` (:233-448) on tiny seeded configurations: quaternion-layout state dict, batch, train/eval logits, loss, regulariser
   (``quaternion_weight_regularization``), gradients under the quaternion parameter names, running statistics.
 
 Before anything is written the script checks, with the reference alone, the two layout relations that
@@ -50,6 +50,12 @@ def quaternion_cases():
     c = tiny(w4["mnist"], 16, 2, 4, 7, 10, head=[16, 8]); c.extra["k"] = 3
     c.model.update(msg_aggr="softmax", initial_beta=0.8, learn_beta=True, msg_encoder="relu", pooling="globalsum")
     out["quaternion_mnist_softmax_lin"] = c
+    # QuaternionSkipConnectConcat (names contain "concat"): layer widths may differ, skip = component-wise concat
+    c = tiny(w4["hiv"], 16, 2, 6, 5, 9, head=[12, 8]); c.model.update(mp_layers=[16, 24], msg_aggr="sum", mlp=False)
+    out["quaternion_concat_hiv_sum_lin"] = c
+    c = tiny(w4["zinc"], 12, 2, 6, 4, 9, head=[12]); c.model.update(mp_layers=[8, 12], msg_aggr="softmax", initial_beta=1.0,
+                                                                     learn_beta=True, mlp=True, pooling="globalsum")
+    out["quaternion_concat_zinc_softmax_mlp"] = c
     return out
 
 
@@ -123,16 +129,18 @@ def legacy_fixture(outdir):
 
 
 def quaternion_fixtures(outdir):
-    from phc.quaternion.undirectional.models import QuaternionSkipConnectAdd
+    from phc.quaternion.undirectional.models import QuaternionSkipConnectAdd, QuaternionSkipConnectConcat
     from phc.quaternion.regularization import quaternion_weight_regularization
     from phc.hypercomplex.undirectional.models import PHMSkipConnectAdd
     import phc.quaternion.undirectional.models as _ref_models
     assert _ref_models.__file__.startswith("/root/reference/"), f"not the reference: {_ref_models.__file__}"
-    for k, (name, wl) in enumerate(sorted(quaternion_cases().items())):
+    # seeds follow the alphabetical order of the Add cases; the Concat cases were appended later (existing fixtures never change)
+    for k, (name, wl) in enumerate(sorted(quaternion_cases().items(), key=lambda kv: ("concat" in kv[0], kv[0]))):
         torch.manual_seed(300 + k)
         np.random.seed(300 + k)
         kw = quaternion_kwargs(wl.model)
-        model = QuaternionSkipConnectAdd(**kw)
+        concat = "concat" in name
+        model = (QuaternionSkipConnectConcat if concat else QuaternionSkipConnectAdd)(**kw)
         seeded_fill(model, 40 + k)
         data = make_batch(wl, seed=50 + k)
         state0 = {n: v.clone() for n, v in model.state_dict().items()}
@@ -147,22 +155,24 @@ def quaternion_fixtures(outdir):
         with torch.no_grad():
             logits_eval = model(data)
 
-        # relation check inside the reference: PHM(n=4, Hamilton rule) on converted parameters
-        pkw = dict(wl.model)
-        pkw.update(dropout_mpnn=kw["dropout_mpnn"], dropout_dn=kw["dropout_dn"], phm_dim=4, learn_phm=False, sc_type="first")
-        phm = PHMSkipConnectAdd(**pkw)
-        phm.load_state_dict(legacy.quaternion_to_phm_state_dict(state0), strict=True)
-        phm.train()
-        err_t = float((phm(data) - logits.detach()).abs().max())
-        phm.eval()
-        with torch.no_grad():
-            err_e = float((phm(data) - logits_eval).abs().max())
-        scale = float(logits.detach().abs().max())
-        assert err_t <= 2e-5 * max(1.0, scale) and err_e <= 2e-5 * max(1.0, scale), (name, err_t, err_e, scale)
+        err_t = err_e = float('nan')
+        if not concat:          # (the reference's PHM concat model raises for n > 1, SURVEY.md D2: nothing to compare with)
+            # relation check inside the reference: PHM(n=4, Hamilton rule) on converted parameters
+            pkw = dict(wl.model)
+            pkw.update(dropout_mpnn=kw["dropout_mpnn"], dropout_dn=kw["dropout_dn"], phm_dim=4, learn_phm=False, sc_type="first")
+            phm = PHMSkipConnectAdd(**pkw)
+            phm.load_state_dict(legacy.quaternion_to_phm_state_dict(state0), strict=True)
+            phm.train()
+            err_t = float((phm(data) - logits.detach()).abs().max())
+            phm.eval()
+            with torch.no_grad():
+                err_e = float((phm(data) - logits_eval).abs().max())
+            scale = float(logits.detach().abs().max())
+            assert err_t <= 2e-5 * max(1.0, scale) and err_e <= 2e-5 * max(1.0, scale), (name, err_t, err_e, scale)
         back = legacy.phm_to_quaternion_state_dict(legacy.quaternion_to_phm_state_dict(state0))
         assert set(back) == set(state0) and all(torch.equal(back[n], state0[n]) for n in state0), name
 
-        fx = dict(name=name, cfg=kw, loss_kind=wl.loss, reg_scale=0.01,
+        fx = dict(name=name, model="concat" if concat else "add", cfg=kw, loss_kind=wl.loss, reg_scale=0.01,
                   data=dict(x=data.x, edge_index=data.edge_index, edge_attr=data.edge_attr, batch=data.batch,
                             y=data.y, num_graphs=data.num_graphs),
                   state=state0, logits_train=logits.detach(), loss=loss.detach(), reg=reg.detach(), grads=grads,

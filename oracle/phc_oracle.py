@@ -371,6 +371,29 @@ def quaternion_model_forward(pq: Params, cfg: Dict, data, training: bool = True,
     return model_forward(quaternion_as_phm(pq), quaternion_cfg(cfg), data, training, generator)
 
 
+def quaternion_concat_model_forward(pq: Params, cfg: Dict, data, training: bool = True, generator=None) -> torch.Tensor:
+    """QuaternionSkipConnectConcat.forward (phc/quaternion/undirectional/models.py:366-403): conv (aggregate -> add self
+    loops -> transform, ``same_dim=False``) -> norm -> act -> dropout -> ``qcat`` with the atom embedding, i.e. a
+    per-component concat; pooling and downstream act on the last layer's width + the embedding width."""
+    p = quaternion_as_phm(pq)
+    c = quaternion_cfg(cfg)
+    c["same_dim"] = False
+    n = 4
+    dtype = p["downstream.real_trafo.affine.bias"].dtype
+    h0 = encoder(data.x, p, "atomencoder", n, c["atom_input_dims"], dtype)
+    h = h0
+    for i in range(len(c["mp_layers"])):
+        e = encoder(data.edge_attr, p, f"bondencoders.{i}", n, c["bond_input_dims"], dtype)
+        z = conv(h, data.edge_index, e, p, f"convs.{i}", c, training)
+        if c["norm_mp"] not in (None, "None"):
+            z = phm_norm(z, p, f"norms.{i}", n, training)
+        z = activation(z, c["activation"])
+        z = phm_dropout(z, n, c["dropout_mpnn"][i], training, c["same_dropout"], generator)
+        h = phm_cat([z, h0], n)
+    out = pooling(h, data.batch, data.num_graphs, p, c)
+    return downstream(out, p, c, training, generator)
+
+
 def quaternion_weight_regularization(pq: Params, cfg: Dict, order: int = 1) -> torch.Tensor:
     """phc/quaternion/regularization.py:27-97, undirectional branch: message-passing weights, the pooling weight stacked
     as (W_r, W_i, W_k, W_k) — line 77 as written —, downstream weights; each stack.norm(p, dim=0).mean()."""

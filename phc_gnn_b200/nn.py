@@ -881,6 +881,10 @@ class PHMSkipConnectConcat(_PHMSkipConnectBase):
                     c_init, same_dropout, mp_layers, bias, dropout_mpnn, norm_mp, add_self_loops, msg_aggr, node_aggr, mlp, pooling,
                     activation, real_trafo, downstream_layers, target_dim, dropout_dn, norm_dn, msg_encoder, sc_type, kwargs)
 
+    def _skip_concat(self, z: torch.Tensor, skip: torch.Tensor) -> torch.Tensor:
+        """flat concat, as the reference writes it (models.py:467); the quaternion subclass concatenates per component"""
+        return torch.cat([z, skip], dim=-1)
+
     def forward(self, data, size=None) -> torch.Tensor:
         x, edge_index, edge_attr, batch = data.x, data.edge_index, data.edge_attr, data.batch
         if isinstance(self.bond_input_dims, list):
@@ -894,7 +898,7 @@ class PHMSkipConnectConcat(_PHMSkipConnectBase):
             z = self.convs[i](x=h, edge_index=edge_index, edge_attr=e, size=size)
             z = norm_act_drop_skip(self.norms[i], z, None, act, self._n, self.training, drop_p=self.dropout_mpnn[i],
                                    drop_same=self.same_dropout)
-            h = torch.cat([z, skip], dim=-1)          # flat concat, as the reference intends (models.py:467)
+            h = self._skip_concat(z, skip)
         out = self.pooling(h, batch, getattr(data, "num_graphs", None))
         return self.downstream(out)
 

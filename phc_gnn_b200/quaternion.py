@@ -23,7 +23,7 @@ import numpy as np
 import torch
 
 from . import legacy, ops
-from .functional import glorot_normal, glorot_uniform
+from .functional import glorot_normal, glorot_uniform, phm_cat
 from .nn import ATOM_FEAT_DIMS, BOND_FEAT_DIMS, PHMLinear, PHMMLP, PHMSkipConnectAdd, PHMSkipConnectConcat, PHMSoftAttentionPooling
 
 _INITS = ("glorot-normal", "glorot-uniform", "quaternion", "orthogonal")
@@ -180,6 +180,11 @@ class QuaternionSkipConnectAdd(_QuaternionMixin, PHMSkipConnectAdd):
 
 class QuaternionSkipConnectConcat(_QuaternionMixin, PHMSkipConnectConcat):
     """reference phc/quaternion/undirectional/models.py:233-448, on the PHM kernels (n = 4, Hamilton rule)."""
+
+    def _skip_concat(self, z: torch.Tensor, skip: torch.Tensor) -> torch.Tensor:
+        """``qcat([q, atom_encoded], dim=-1)`` (reference models.py:381, algebra.py cat): every component's block becomes
+        [z_c | skip_c] — in the flat layout that is the component-aware ``phm_cat``, not a flat concat."""
+        return phm_cat([z, skip], 4)
 
     def __init__(self, atom_input_dims: Union[int, list] = ATOM_FEAT_DIMS, atom_encoded_dim: int = 128,
                  bond_input_dims: Union[int, list] = BOND_FEAT_DIMS, naive_encoder: bool = False, init: str = "orthogonal",

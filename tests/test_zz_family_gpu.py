@@ -6,7 +6,7 @@ import torch
 
 from gpu_util import assert_close
 from oracle import phc_oracle as O
-from test_family_host import load_family, quaternion_cases
+from test_family_host import load_family, product_class, quaternion_cases
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-4      # north_star fp32 tolerance
@@ -19,8 +19,7 @@ def _tol(ref, rtol=RTOL):
 
 def _run(fx, fuse):
     from phc.quaternion.regularization import quaternion_weight_regularization
-    from phc.quaternion.undirectional.models import QuaternionSkipConnectAdd
-    m = QuaternionSkipConnectAdd(**fx["cfg"])
+    m = product_class(fx)(**fx["cfg"])
     m.load_quaternion_state_dict(fx["state"])
     m = m.to(DEV)
     m.fuse_edge_encoder = fuse != "none"
