@@ -247,3 +247,19 @@ def tiny(wl: Workload, width: int, layers: int, graphs: int, nodes_lo: int, node
     if und_edges is not None:
         out.extra["und_edges"] = und_edges
     return out
+
+
+def split_graphs(data: GraphBatch) -> List[GraphBatch]:
+    """Cut a synthetic mini-batch (edges grouped by graph, as ``make_batch`` builds them) into single-graph pieces with
+    local node ids — a synthetic DATASET for ``prep.DeviceGraphStore``."""
+    B = int(data.num_graphs)
+    counts = torch.bincount(data.batch, minlength=B)
+    nptr = [0] + torch.cumsum(counts, 0).tolist()
+    ecounts = torch.bincount(data.batch[data.edge_index[0]], minlength=B)
+    eptr = [0] + torch.cumsum(ecounts, 0).tolist()
+    out = []
+    for b in range(B):
+        n0, n1, e0, e1 = nptr[b], nptr[b + 1], eptr[b], eptr[b + 1]
+        out.append(GraphBatch(data.x[n0:n1].clone(), (data.edge_index[:, e0:e1] - n0).clone(), data.edge_attr[e0:e1].clone(),
+                              torch.zeros(n1 - n0, dtype=torch.int64), data.y[b:b + 1].clone(), 1))
+    return out
