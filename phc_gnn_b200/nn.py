@@ -797,6 +797,16 @@ class _PHMSkipConnectBase(nn.Module):
     def get_number_of_params_(self) -> int:
         return sum(p.numel() for p in self.parameters() if p.requires_grad)
 
+    def load_state_dict(self, state_dict, strict: bool = True, **kwargs):
+        """Also accepts the reference's other layouts: ``PHMLinear_Old`` keys (``W.0``.., the shipped checkpoints) and, for
+        n = 4, the quaternion models' ``W_r``.. keys — relabelled by legacy.py before the regular load."""
+        from . import legacy
+        if legacy.is_legacy_phm_state_dict(state_dict):
+            state_dict = legacy.convert_legacy_phm_state_dict(state_dict)
+        elif legacy.is_quaternion_state_dict(state_dict):
+            state_dict = legacy.quaternion_to_phm_state_dict(state_dict)
+        return super().load_state_dict(state_dict, strict=strict, **kwargs)
+
     def _encode_edges(self, i: int, edge_attr: torch.Tensor) -> torch.Tensor:
         return self.bondencoders[i].flat(edge_attr)
 

@@ -155,6 +155,23 @@ def test_scripts_family_switch():
         assert not hasattr(m2, "phm_dim") and m2._n == 4
 
 
+def test_load_state_dict_accepts_the_other_layouts():
+    """model.load_state_dict takes quaternion-named and legacy-named state dicts directly."""
+    from phc.hypercomplex.undirectional.models import PHMSkipConnectAdd
+    from phc_gnn_b200 import legacy
+    fx = load_family("quaternion_zinc_sum_mlp")
+    q = product_class(fx)(**fx["cfg"])
+    q.load_state_dict(fx["state"], strict=True)
+    want = legacy.quaternion_to_phm_state_dict(fx["state"])
+    assert all(torch.equal(v, want[k]) for k, v in q.state_dict().items())
+    kw = dict(phm_dim=2, atom_encoded_dim=8, mp_layers=[8, 8], dropout_mpnn=[0.0, 0.0], downstream_layers=[8, 4], mlp=True)
+    a, b = PHMSkipConnectAdd(**kw), PHMSkipConnectAdd(**kw)
+    old = legacy.to_legacy_phm_state_dict(a.state_dict())
+    assert legacy.is_legacy_phm_state_dict(old) and not legacy.is_legacy_phm_state_dict(a.state_dict())
+    b.load_state_dict(old, strict=True)
+    assert all(torch.equal(v, a.state_dict()[k]) for k, v in b.state_dict().items())
+
+
 def test_q_batch_norm_is_refused():
     from phc.quaternion.undirectional.models import QuaternionSkipConnectAdd
     with pytest.raises(NotImplementedError):
