@@ -517,7 +517,7 @@ def conv_layer(x, skip, edge_attr, struct: EdgeStructure, *, phm_dim: int, enc_l
     flat2 = norm2.flat_views() if norm2 is not None else None
     tr1 = (norm1.training or not norm1.track_running_stats) if norm1 is not None else training
     tr2 = (norm2.training or not norm2.track_running_stats) if norm2 is not None else training
-    assert tr1 == tr2 == training or norm1 is None or norm2 is None or True
+    assert tr1 == training and tr2 == training, "fused layer: batch-norm modules and the layer disagree on train/eval mode"
     cfg = (phm_dim, bool(enc_linear), int(edge_attr.size(1)), tuple(int(v) for v in enc_vocab), r, act_id(msg_act), bool(add_self_loops),
            bool(mlp), act_id(act1), act_id(act2), norm1 is not None, norm2 is not None, bool(training),
            float(drop_p) if active_drop else 0.0, bool(drop_same), seed, default_precision(), len(enc_params), has_beta, len(p1), len(p2),

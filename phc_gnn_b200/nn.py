@@ -531,7 +531,8 @@ class _PHMConvBase(nn.Module):
         norms = [outer_norm.bn] if outer_norm is not None else []
         if isinstance(self.transform, PHMMLP) and self.transform.norm_flag:
             norms.append(self.transform.norm.bn)
-        return all(nm.track_running_stats for nm in norms)
+        # one training flag drives the whole fused layer: a norm switched to another mode by hand takes the unfused path
+        return all(nm.track_running_stats and nm.training == self.training for nm in norms)
 
     def _reset_beta(self):
         if getattr(self, "beta", None) is not None:
