@@ -63,6 +63,12 @@ class TrainStep(object):
         else:
             self.opt = optimizer if optimizer is not None else make_optimizer(model, workload.lr)
         self.dp = dp                      # DataParallelPHC wrapper or None
+        # the scripts pick the regulariser by family (train_hiv.py:182: quaternion models have no ``phm_dim``)
+        if hasattr(getattr(model, "module", model), "phm_dim"):
+            self.regulariser = phm_weight_regularization
+        else:
+            from .quaternion import quaternion_weight_regularization
+            self.regulariser = quaternion_weight_regularization
         self.params = [p for p in model.parameters()]
 
     def __call__(self, data) -> torch.Tensor:
@@ -71,7 +77,7 @@ class TrainStep(object):
         logits = self.model(data)
         loss = task_loss(logits, data.y, wl.loss)
         if wl.weight_decay > 0.0:
-            loss = loss + wl.lr * wl.weight_decay * phm_weight_regularization(self.model, p=2)
+            loss = loss + wl.lr * wl.weight_decay * self.regulariser(self.model, p=2)
         loss.backward()
         if self.flat_opt:
             self.opt.step(reduce=self.dp is not None, reduce_group=self.dp.group if self.dp is not None else None)

@@ -90,3 +90,32 @@ def test_legacy_phm_linear_on_device(monkeypatch):
         g = legacy.to_legacy_phm_state_dict({k: p.grad.detach().cpu() for k, p in lin.named_parameters()})
         for k, want in fx["grads"].items():
             assert_close(g[k], want, 5 * RTOL, 10 * _tol(want), f"{key}: grad {k}")
+
+
+def test_quaternion_train_steps(monkeypatch):
+    """The timed unit (train.TrainStep: forward, loss + quaternion regulariser, backward, clip, flat Adam) on a quaternion
+    model: the loss falls on a repeated batch, weights move, the Hamilton rule stays frozen and bit-identical."""
+    monkeypatch.setenv("PHC_PRECISION", "fp32")
+    import numpy as np
+    from phc.quaternion.undirectional.models import QuaternionSkipConnectAdd
+    from phc_gnn_b200 import legacy
+    from phc_gnn_b200.quaternion import quaternion_weight_regularization
+    from phc_gnn_b200.synthetic import make_batch, tiny, workloads
+    from phc_gnn_b200.train import TrainStep
+    wl = tiny(workloads(4)["zinc"], 16, 2, 24, 5, 12, head=[16, 8])
+    kw = {k: v for k, v in wl.model.items() if k not in ("phm_dim", "learn_phm", "phm_rule", "w_init", "c_init", "sc_type")}
+    torch.manual_seed(0)
+    np.random.seed(0)
+    model = QuaternionSkipConnectAdd(init="quaternion", **kw).to(DEV)
+    model.train()
+    step = TrainStep(model, wl)
+    assert step.regulariser is quaternion_weight_regularization
+    data = make_batch(wl, seed=1).to(DEV)
+    w0 = model.downstream.affine[0].W.detach().clone()
+    losses = [float(step(data)) for _ in range(8)]
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+    assert not torch.equal(model.downstream.affine[0].W.detach(), w0)
+    for mod in model.modules():
+        r = getattr(mod, "phm_rule", None)
+        if isinstance(r, torch.nn.Parameter):
+            assert torch.equal(r.detach().cpu(), legacy.hamilton_rule())
