@@ -180,3 +180,59 @@ class DeviceGraphStore(object):
             raise IndexError("phc_collate_batch: graph id outside the store")
         if s & 2:
             raise RuntimeError("phc_collate_batch: size prefix sums do not match the selected graphs")
+
+
+class EpochSampler(object):
+    """Graph ids of one rank's mini-batches for one epoch: a seeded permutation of the dataset (``shuffle=True``, the
+    scripts' training loaders, benchmarks/train_hiv.py:556) cut into global batches of ``world * batch_graphs`` graphs, of
+    which rank r takes the r-th slice — every graph is visited once per epoch by exactly one rank, all ranks run the same
+    number of steps (a last global batch that cannot give every rank a graph is dropped; a short one is split evenly).
+    Pure host logic (numpy): data parallelism shards by graph, no collective is involved."""
+
+    def __init__(self, num_graphs: int, batch_graphs: int, rank: int = 0, world: int = 1, seed: int = 0, shuffle: bool = True,
+                 drop_last: bool = False):
+        assert num_graphs > 0 and batch_graphs > 0 and 0 <= rank < world
+        self.num_graphs, self.batch_graphs, self.rank, self.world = int(num_graphs), int(batch_graphs), int(rank), int(world)
+        self.seed, self.shuffle, self.drop_last = int(seed), bool(shuffle), bool(drop_last)
+        self.epoch = 0
+
+    def set_epoch(self, epoch: int) -> None:
+        self.epoch = int(epoch)
+
+    def _global_batches(self):
+        order = (np.random.default_rng([self.seed, self.epoch]).permutation(self.num_graphs) if self.shuffle
+                 else np.arange(self.num_graphs))
+        step = self.world * self.batch_graphs
+        for lo in range(0, self.num_graphs, step):
+            chunk = order[lo:lo + step]
+            if len(chunk) < step and (self.drop_last or len(chunk) < self.world):
+                return
+            yield chunk
+
+    def __len__(self) -> int:
+        return sum(1 for _ in self._global_batches())
+
+    def __iter__(self):
+        for chunk in self._global_batches():
+            per = len(chunk) // self.world                   # == batch_graphs except for a short last batch
+            extra = len(chunk) - per * self.world            # the first ``extra`` ranks take one more graph
+            lo = self.rank * per + min(self.rank, extra)
+            yield np.ascontiguousarray(chunk[lo:lo + per + (1 if self.rank < extra else 0)]).astype(np.int64)
+
+
+class DeviceLoader(object):
+    """Stands in for ``DataLoader(dataset, batch_size, shuffle)`` + ``data.to(device)`` + the per-batch transform of the
+    training loops (benchmarks/train_hiv.py:171-173): iterates device-resident mini-batches assembled by
+    ``DeviceGraphStore.collate``; ``transform`` is e.g. ``prep.RemoveIsolatedNodes()``."""
+
+    def __init__(self, store: DeviceGraphStore, sampler: EpochSampler, transform=None):
+        assert sampler.num_graphs == store.num_graphs
+        self.store, self.sampler, self.transform = store, sampler, transform
+
+    def __len__(self) -> int:
+        return len(self.sampler)
+
+    def __iter__(self):
+        for ids in self.sampler:
+            batch = self.store.collate(ids)
+            yield self.transform(batch) if self.transform is not None else batch

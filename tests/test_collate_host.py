@@ -38,3 +38,31 @@ def test_device_store_refuses_cpu():
     graphs = O.split_batch(make_batch(workloads(4)["zinc"], seed=0, batch_graphs=2))
     with pytest.raises(RuntimeError):
         DeviceGraphStore(graphs, "cpu")
+
+
+@pytest.mark.parametrize("G,B,W", [(100, 8, 1), (100, 8, 4), (37, 5, 2), (64, 8, 8), (10, 4, 4)])
+def test_epoch_sampler_shards_by_graph(G, B, W):
+    """Every graph is visited by exactly one rank per epoch, all ranks run the same number of steps, epochs reshuffle,
+    and the same (seed, epoch) gives the same order on every rank."""
+    import numpy as np
+    from phc_gnn_b200.prep import EpochSampler
+    samplers = [EpochSampler(G, B, rank=r, world=W, seed=3) for r in range(W)]
+    per_rank = [list(s) for s in samplers]
+    steps = {len(b) for b in per_rank}
+    assert len(steps) == 1 and steps.pop() == len(samplers[0])
+    seen = np.concatenate([ids for b in per_rank for ids in b])
+    assert len(seen) == len(set(seen.tolist()))                          # disjoint
+    dropped = G - len(seen)
+    assert 0 <= dropped < W                                              # only a tail smaller than the world is dropped
+    for step in range(len(per_rank[0])):
+        sizes = [len(per_rank[r][step]) for r in range(W)]
+        assert max(sizes) - min(sizes) <= 1 and max(sizes) <= B
+    again = [list(EpochSampler(G, B, rank=r, world=W, seed=3)) for r in range(W)]
+    assert all(np.array_equal(a, b) for r in range(W) for a, b in zip(per_rank[r], again[r]))
+    samplers[0].set_epoch(1)
+    if G > B * W:
+        assert not all(np.array_equal(a, b) for a, b in zip(per_rank[0], list(samplers[0])))
+    full = [ids for ids in EpochSampler(G, B, rank=0, world=W, seed=3, drop_last=True)]
+    assert all(len(ids) == B for ids in full)
+    ordered = np.concatenate(list(EpochSampler(G, B, shuffle=False)))
+    assert ordered.tolist() == list(range(G))

@@ -94,26 +94,50 @@ def test_legacy_phm_linear_on_device(monkeypatch):
 
 def test_quaternion_train_steps(monkeypatch):
     """The timed unit (train.TrainStep: forward, loss + quaternion regulariser, backward, clip, flat Adam) on a quaternion
-    model: the loss falls on a repeated batch, weights move, the Hamilton rule stays frozen and bit-identical."""
+    model against the same steps taken by the CPU oracle on the reference's quaternion parameters (dropout off, one
+    repeated batch): per-step losses agree, weights move, the Hamilton rule stays frozen and bit-identical."""
     monkeypatch.setenv("PHC_PRECISION", "fp32")
     import numpy as np
+    from test_family_host import leaves
     from phc.quaternion.undirectional.models import QuaternionSkipConnectAdd
     from phc_gnn_b200 import legacy
     from phc_gnn_b200.quaternion import quaternion_weight_regularization
     from phc_gnn_b200.synthetic import make_batch, tiny, workloads
     from phc_gnn_b200.train import TrainStep
     wl = tiny(workloads(4)["zinc"], 16, 2, 24, 5, 12, head=[16, 8])
+    wl.lr, wl.weight_decay = 5e-3, 0.1
     kw = {k: v for k, v in wl.model.items() if k not in ("phm_dim", "learn_phm", "phm_rule", "w_init", "c_init", "sc_type")}
+    kw["dropout_mpnn"] = [0.0] * len(kw["mp_layers"])
+    kw["dropout_dn"] = [0.0] * len(kw["downstream_layers"])
     torch.manual_seed(0)
     np.random.seed(0)
-    model = QuaternionSkipConnectAdd(init="quaternion", **kw).to(DEV)
+    model = QuaternionSkipConnectAdd(init="quaternion", **kw)
+    pq = leaves(model.quaternion_state_dict(), torch.float64)
+    model = model.to(DEV)
     model.train()
     step = TrainStep(model, wl)
     assert step.regulariser is quaternion_weight_regularization
-    data = make_batch(wl, seed=1).to(DEV)
+    host = make_batch(wl, seed=1)
+    data = host.to(DEV)
     w0 = model.downstream.affine[0].W.detach().clone()
-    losses = [float(step(data)) for _ in range(8)]
-    assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+    got = [float(step(data)) for _ in range(4)]
+
+    train = [v for v in pq.values() if v.requires_grad]
+    opt = torch.optim.Adam(train, lr=wl.lr)
+    want = []
+    for _ in range(4):
+        opt.zero_grad()
+        logits = O.quaternion_model_forward(pq, kw, host, training=True)
+        loss = O.task_loss(logits, host.y, wl.loss) + wl.lr * wl.weight_decay * O.quaternion_weight_regularization(pq, kw, 2)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(train, max_norm=wl.grad_clip, norm_type=2)
+        opt.step()
+        want.append(float(loss.detach()))
+    assert abs(got[0] - want[0]) <= 1e-4 * abs(want[0]), (got, want)
+    for g, w in zip(got[1:], want[1:]):
+        # later steps: Adam normalises gradients, so entries whose gradient is zero in exact arithmetic (a bias in front
+        # of a batch norm) take +-lr noise steps on both sides; they do not reach the loss
+        assert abs(g - w) <= 2e-3 * abs(w), (got, want)
     assert not torch.equal(model.downstream.affine[0].W.detach(), w0)
     for mod in model.modules():
         r = getattr(mod, "phm_rule", None)

@@ -69,3 +69,34 @@ def test_collated_batch_trains(monkeypatch):
         a = model(store.collate(list(range(data.num_graphs))))
         b = model(data.to(DEV))
     assert torch.equal(a, b)
+
+
+def test_device_loader_epoch():
+    """DeviceLoader = sampler + collate (+ transform): one epoch over a small store on two 'ranks' reproduces the oracle's
+    collate of the same ids, and the RemoveIsolatedNodes transform is applied per batch."""
+    from phc_gnn_b200.prep import DeviceGraphStore, DeviceLoader, EpochSampler, RemoveIsolatedNodes
+    from phc_gnn_b200.synthetic import make_batch, split_graphs, workloads
+    data = make_batch(workloads(4)["hiv"], seed=9, batch_graphs=21)
+    dataset = split_graphs(data)
+    store = DeviceGraphStore(dataset, DEV)
+    seen = []
+    for rank in range(2):
+        sampler = EpochSampler(len(dataset), 4, rank=rank, world=2, seed=5)
+        loader = DeviceLoader(store, sampler)
+        assert len(loader) == 3
+        for ids, batch in zip(sampler, loader):
+            store.check_status()
+            x, ei, ea, bvec, y = O.collate([dataset[i] for i in ids.tolist()])
+            _same(batch.x, x, "x")
+            _same(batch.edge_index, ei, "edge_index")
+            _same(batch.edge_attr, ea, "edge_attr")
+            _same(batch.batch, bvec, "batch")
+            _same(batch.y, y, "y")
+            seen += ids.tolist()
+    assert len(seen) == len(set(seen)) == 21              # global batches of 8, 8 and 5 graphs; the short one is split 3 + 2
+    loader = DeviceLoader(store, EpochSampler(len(dataset), 8, seed=1), transform=RemoveIsolatedNodes())
+    for ids, batch in zip(loader.sampler, loader):
+        x, ei, ea, bvec, y = O.collate([dataset[i] for i in ids.tolist()])
+        ei2, ea2, mask = O.remove_isolated_nodes(ei, ea, x.size(0))
+        _same(batch.edge_index, ei2, "transformed edge_index")
+        _same(batch.x, x[mask], "transformed x")
