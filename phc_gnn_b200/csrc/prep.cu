@@ -13,7 +13,9 @@
 
 namespace {
 
-constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;                               // consecutive items per thread
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;        // items per block
 
 __global__ void __launch_bounds__(256) prep_mark_kernel(const long long* __restrict__ ei, int E, int N, unsigned char* __restrict__ keep,
                                                         int* __restrict__ loop_last, int* __restrict__ status) {
@@ -26,37 +28,103 @@ __global__ void __launch_bounds__(256) prep_mark_kernel(const long long* __restr
   else atomicMax(loop_last + s, e);
 }
 
-// Exclusive scan of flag(i) over n items by ONE block (each thread owns a contiguous slice): pos[i], total -> *count.
+// Exclusive scan of flag(i) over n items -> pos[i], total -> *count, in three launches (tile counts, scan of the tile
+// counts by one block, positions), every tile of SCAN_TILE items owned by one block and every thread by SCAN_ITEMS
+// consecutive items.  Integer sums in a fixed order: deterministic and bit-exact.
 // which = 0: flag = keep[i];  1: flag = edge i is not a self loop;  2: flag = keep[i] && loop_last[i] >= 0
-__global__ void __launch_bounds__(SCAN_THREADS) prep_scan_kernel(int which, int n, const unsigned char* __restrict__ keep,
-                                                                 const int* __restrict__ loop_last, const long long* __restrict__ ei, int E,
-                                                                 int* __restrict__ pos, int* __restrict__ count) {
-  pdl_begin();
-  __shared__ int sums[SCAN_THREADS];
-  const int t = threadIdx.x;
-  const int per = (n + SCAN_THREADS - 1) / SCAN_THREADS;
-  const int b = min(t * per, n), e = min(b + per, n);
-  auto flag = [&](int i) -> int {
-    if (which == 0) return keep[i] ? 1 : 0;
-    if (which == 1) return ei[i] != ei[(size_t)E + i] ? 1 : 0;
-    return (keep[i] && loop_last[i] >= 0) ? 1 : 0;
-  };
-  int c = 0;
-  for (int i = b; i < e; ++i) c += flag(i);
-  sums[t] = c;
+__device__ __forceinline__ int prep_flag(int which, int i, const unsigned char* __restrict__ keep, const int* __restrict__ loop_last,
+                                         const long long* __restrict__ ei, int E) {
+  if (which == 0) return keep[i] ? 1 : 0;
+  if (which == 1) return ei[i] != ei[(size_t)E + i] ? 1 : 0;
+  return (keep[i] && loop_last[i] >= 0) ? 1 : 0;
+}
+
+// exclusive prefix of v over the block's threads (thread order); *total = block sum
+__device__ __forceinline__ int prep_block_exclusive(int v, int* total) {
+  __shared__ int warp_sums[SCAN_THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int up = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += up;
+  }
+  if (lane == 31) warp_sums[warp] = inc;
   __syncthreads();
-  for (int o = 1; o < SCAN_THREADS; o <<= 1) {            // Hillis-Steele inclusive scan of the slice sums
-    const int v = t >= o ? sums[t - o] : 0;
-    __syncthreads();
-    sums[t] += v;
-    __syncthreads();
+  int before = 0, all = 0;
+#pragma unroll
+  for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+    const int ws = warp_sums[w];
+    if (w < warp) before += ws;
+    all += ws;
   }
-  int run = sums[t] - c;
-  for (int i = b; i < e; ++i) {
-    pos[i] = run;
-    run += flag(i);
+  __syncthreads();                                          // warp_sums may be reused by the caller's next call
+  *total = all;
+  return before + inc - v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) prep_tile_count_kernel(int which, int n, const unsigned char* __restrict__ keep,
+                                                                      const int* __restrict__ loop_last,
+                                                                      const long long* __restrict__ ei, int E,
+                                                                      int* __restrict__ tile_sums) {
+  pdl_begin();
+  const int first = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  int c = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k)
+    if (first + k < n) c += prep_flag(which, first + k, keep, loop_last, ei, E);
+  int total;
+  prep_block_exclusive(c, &total);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+// one block: tile_sums[0..tiles) -> exclusive offsets in place, grand total -> *count
+__global__ void __launch_bounds__(SCAN_THREADS) prep_tile_scan_kernel(int tiles, int* __restrict__ tile_sums, int* __restrict__ count) {
+  pdl_begin();
+  int carry = 0;
+  for (int base = 0; base < tiles; base += SCAN_THREADS) {
+    const int i = base + threadIdx.x;
+    const int v = i < tiles ? tile_sums[i] : 0;
+    int total;
+    const int ex = prep_block_exclusive(v, &total);
+    if (i < tiles) tile_sums[i] = carry + ex;
+    carry += total;
   }
-  if (t == SCAN_THREADS - 1) *count = sums[t];
+  if (threadIdx.x == 0) *count = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) prep_tile_pos_kernel(int which, int n, const unsigned char* __restrict__ keep,
+                                                                    const int* __restrict__ loop_last, const long long* __restrict__ ei,
+                                                                    int E, const int* __restrict__ tile_offsets,
+                                                                    int* __restrict__ pos) {
+  pdl_begin();
+  const int first = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  int f[SCAN_ITEMS];
+  int c = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    f[k] = (first + k < n) ? prep_flag(which, first + k, keep, loop_last, ei, E) : 0;
+    c += f[k];
+  }
+  int total;
+  int run = tile_offsets[blockIdx.x] + prep_block_exclusive(c, &total);
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    if (first + k < n) pos[first + k] = run;
+    run += f[k];
+  }
+}
+
+// the three launches of one scan; tile_sums: scratch of prep_tiles(n) ints
+inline int prep_tiles(int n) { return (n + SCAN_TILE - 1) / SCAN_TILE; }
+
+inline void prep_scan(int which, int n, const unsigned char* keep, const int* loop_last, const long long* ei, int E, int* pos,
+                      int* count, int* tile_sums, cudaStream_t stream) {
+  const int tiles = prep_tiles(n);
+  phc_launch(prep_tile_count_kernel, dim3(tiles), dim3(SCAN_THREADS), 0, stream, which, n, keep, loop_last, ei, E, tile_sums);
+  phc_launch(prep_tile_scan_kernel, dim3(1), dim3(SCAN_THREADS), 0, stream, tiles, tile_sums, count);
+  phc_launch(prep_tile_pos_kernel, dim3(tiles), dim3(SCAN_THREADS), 0, stream, which, n, keep, loop_last, ei, E,
+             (const int*)tile_sums, pos);
 }
 
 __global__ void __launch_bounds__(256) prep_assoc_kernel(int N, const unsigned char* __restrict__ keep, const int* __restrict__ node_pos,
@@ -99,8 +167,9 @@ __global__ void __launch_bounds__(256) prep_loops_kernel(int N, int E, const uns
 extern "C" {
 
 size_t phc_isolated_workspace_bytes(int num_nodes, int num_edges) {
-  // keep flags live in the caller's mask; here: loop_last[N] + node_pos[N] + loop_pos[N] + edge_pos[E]
-  return sizeof(int) * (3 * (size_t)num_nodes + (size_t)num_edges + 4);
+  // keep flags live in the caller's mask; here: loop_last[N] + node_pos[N] + loop_pos[N] + edge_pos[E] + the scans' tile sums
+  const int n = num_nodes > num_edges ? num_nodes : num_edges;
+  return sizeof(int) * (3 * (size_t)num_nodes + (size_t)num_edges + (size_t)prep_tiles(n) + 8);
 }
 
 // counts (device int[4]): [0] kept nodes, [1] kept non-loop edges, [2] kept self loops, [3] status (bit0: index out of range)
@@ -114,6 +183,7 @@ int phc_remove_isolated_nodes(const long long* edge_index, int num_edges, int nu
   int* node_pos = loop_last + N;
   int* loop_pos = node_pos + N;
   int* edge_pos = loop_pos + N;
+  int* tile_sums = edge_pos + E;
   cudaMemsetAsync(counts, 0, sizeof(int) * 4, stream);
   if (N > 0) {
     cudaMemsetAsync(keep_mask, 0, (size_t)N, stream);
@@ -121,16 +191,16 @@ int phc_remove_isolated_nodes(const long long* edge_index, int num_edges, int nu
   }
   if (E > 0) phc_launch(prep_mark_kernel, dim3(phc_div_up(E, 256)), dim3(256), 0, stream, edge_index, E, N, keep_mask, loop_last, counts + 3);
   if (N > 0) {
-    phc_launch(prep_scan_kernel, dim3(1), dim3(SCAN_THREADS), 0, stream, 0, N, keep_mask, loop_last, edge_index, E, node_pos, counts + 0);
+    prep_scan(0, N, keep_mask, loop_last, edge_index, E, node_pos, counts + 0, tile_sums, stream);
     phc_launch(prep_assoc_kernel, dim3(phc_div_up(N, 256)), dim3(256), 0, stream, N, keep_mask, node_pos, assoc);
   }
   if (E > 0) {
-    phc_launch(prep_scan_kernel, dim3(1), dim3(SCAN_THREADS), 0, stream, 1, E, keep_mask, loop_last, edge_index, E, edge_pos, counts + 1);
+    prep_scan(1, E, keep_mask, loop_last, edge_index, E, edge_pos, counts + 1, tile_sums, stream);
     phc_launch(prep_edges_kernel, dim3(phc_div_up(E, 256)), dim3(256), 0, stream, edge_index, E, node_pos, edge_pos, new_edge_index,
                edge_order);
   }
   if (N > 0 && E > 0) {
-    phc_launch(prep_scan_kernel, dim3(1), dim3(SCAN_THREADS), 0, stream, 2, N, keep_mask, loop_last, edge_index, E, loop_pos, counts + 2);
+    prep_scan(2, N, keep_mask, loop_last, edge_index, E, loop_pos, counts + 2, tile_sums, stream);
     phc_launch(prep_loops_kernel, dim3(phc_div_up(N, 256)), dim3(256), 0, stream, N, E, keep_mask, loop_last, node_pos, loop_pos, counts,
                new_edge_index, edge_order);
   }

@@ -89,5 +89,29 @@ def main():
           f"{byt / ms / 1e6:.0f} GB/s algorithmic = {byt / ms / 1e6 / peak:.1%} of peak")
 
 
+    # kernel-only durations (CUPTI via torch.profiler: warm caches, real clocks) — the numbers above include the host side
+    import collections
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for ids in sel[5:5 + 10]:
+            store.collate(ids)
+        for _ in range(10):
+            remove_isolated_nodes(ei, ea, N)
+        torch.cuda.synchronize()
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for ev in prof.events():
+        if ev.device_type == torch.autograd.DeviceType.CUDA:
+            dur = ev.device_time if hasattr(ev, "device_time") else ev.cuda_time
+            nm = ev.name.replace("(anonymous namespace)::", "").replace("void ", "").split("(")[0].split("<")[0]
+            agg[nm][0] += 1
+            agg[nm][1] += dur
+    cb = 2 * batch.nbytes()
+    for nm, (cnt, tot) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        line = f"  kernel {nm:40s} n={cnt:3d} avg {tot / cnt:8.2f} us"
+        if "collate" in nm:
+            line += f"  -> {cb / (tot / cnt) / 1e3:.0f} GB/s = {cb / (tot / cnt) / 1e3 / peak:.1%} of peak (algorithmic 2 x batch bytes)"
+        print(line)
+
+
 if __name__ == "__main__":
     main()
