@@ -183,11 +183,65 @@ def quaternion_fixtures(outdir):
               f"loss={float(loss):.6f} phm-vs-quaternion err train {err_t:.1e} eval {err_e:.1e}  {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def phm_option_cases():
+    """PHM configurations whose constructor options the 14 fixtures of make_golden.py do not exercise: the naive encoders
+    (embedding and linear), add_self_loops=False (both convolution types), bias=False, a frozen rule on a PHM model."""
+    w4 = workloads(4)
+    out = {}
+    c = tiny(w4["hiv"], 16, 2, 6, 5, 9, head=[12, 8])
+    c.model.update(naive_encoder=True, add_self_loops=False, mlp=False, msg_aggr="sum")
+    out["phm_hiv_naive_enc_noloops_lin"] = c
+    c = tiny(workloads(2)["zinc"], 12, 2, 6, 4, 9, head=[12, 6])
+    c.model.update(bias=False, add_self_loops=False, mlp=True, msg_aggr="mean", learn_phm=False)
+    out["phm_zinc_n2_nobias_noloops_mlp_frozen"] = c
+    c = tiny(w4["mnist"], 16, 2, 4, 7, 10, head=[16, 8]); c.extra["k"] = 3
+    c.model.update(naive_encoder=True, msg_aggr="softmax", initial_beta=1.3, learn_beta=False, mlp=True)
+    out["phm_mnist_naive_linear_enc_softmax_fixed_beta"] = c
+    return out
+
+
+def phm_option_fixtures(outdir):
+    sys.path.insert(0, HERE)
+    from make_golden import seeded_fill as phm_fill        # same seeding rules as the main PHM fixtures
+    from phc.hypercomplex.undirectional.models import PHMSkipConnectAdd
+    from phc.hypercomplex.regularization import phm_weight_regularization
+    for k, (name, wl) in enumerate(sorted(phm_option_cases().items())):
+        torch.manual_seed(500 + k)
+        np.random.seed(500 + k)
+        kw = dict(wl.model)
+        kw["dropout_mpnn"] = [0.0] * len(kw["mp_layers"])
+        kw["dropout_dn"] = [0.0] * len(kw["downstream_layers"])
+        model = PHMSkipConnectAdd(**kw)
+        phm_fill(model, 60 + k)
+        data = make_batch(wl, seed=70 + k)
+        state0 = {n: v.clone() for n, v in model.state_dict().items()}
+        model.train()
+        logits = model(data)
+        reg = phm_weight_regularization(model, p=2)
+        loss = ref_loss(logits, data.y, wl.loss) + 0.01 * reg
+        loss.backward()
+        grads = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+        state1 = {n: v.clone() for n, v in model.state_dict().items() if "running" in n or "tracked" in n}
+        model.eval()
+        with torch.no_grad():
+            logits_eval = model(data)
+        fx = dict(name=name, model="phm", cfg=kw, loss_kind=wl.loss, reg_scale=0.01,
+                  data=dict(x=data.x, edge_index=data.edge_index, edge_attr=data.edge_attr, batch=data.batch,
+                            y=data.y, num_graphs=data.num_graphs),
+                  state=state0, logits_train=logits.detach(), loss=loss.detach(), reg=reg.detach(), grads=grads,
+                  running_after=state1, logits_eval=logits_eval, n_params=model.get_number_of_params_())
+        path = os.path.join(outdir, name + ".pt")
+        torch.save(fx, path)
+        print(f"{name:48s} N={data.x.size(0):4d} E={data.edge_index.size(1):4d} params={fx['n_params']:6d} "
+              f"loss={float(loss):.6f}  {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 def main():
     outdir = os.path.join(ROOT, "tests", "golden", "family")
     os.makedirs(outdir, exist_ok=True)
     legacy_fixture(outdir)
     quaternion_fixtures(outdir)
+    phm_option_fixtures(outdir)
 
 
 if __name__ == "__main__":

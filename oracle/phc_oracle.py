@@ -98,7 +98,18 @@ def phm_dropout(x: torch.Tensor, n: int, prob: float, training: bool, same: bool
 
 
 def encoder(feat: torch.Tensor, p: Params, key: str, n: int, input_dims, dtype) -> torch.Tensor:
-    """PHMEncoder -> [rows, n*out_dim] with component c in column block c."""
+    """PHMEncoder -> [rows, n*out_dim] with component c in column block c; NaivePHMEncoder (encoder.py:45-72, keys
+    ``<key>.encoder.*``): ONE encoder whose output is repeated for every component."""
+    naive = any(k.startswith(key + ".encoder.") for k in p)
+    if naive:
+        if isinstance(input_dims, (list, tuple)):
+            f = feat.unsqueeze(1) if feat.dim() == 1 else feat
+            one = 0
+            for col in range(f.size(1)):
+                one = one + p[f"{key}.encoder.embeddings.{col}.weight"][f[:, col]]
+        else:
+            one = feat.to(dtype) @ p[f"{key}.encoder.weight"].t() + p[f"{key}.encoder.bias"]
+        return torch.cat([one] * n, -1)
     comps = []
     for c in range(n):
         if isinstance(input_dims, (list, tuple)):

@@ -578,7 +578,10 @@ class PHMGINEConv(_PHMConvBase):
         super().__init__()
         self._setup(in_features, out_features, phm_dim, phm_rule, learn_phm, bias, add_self_loops, w_init, c_init, aggr, msg_encoder)
         self.norm, self.activation_str = norm, activation
-        self.transform = PHMMLP(in_features, out_features, phm_dim, phm_rule, bias=bias, learn_phm=learn_phm, activation=activation,
+        # The reference does not hand ``learn_phm`` to the MLP (messagepassing.py:119-122, :276-278), so the rules of the two
+        # MLP layers stay trainable even under learn_phm=False (its parameter count and gradients say so: fixture
+        # phm_zinc_n2_nobias_noloops_mlp_frozen).  Reproduced; the quaternion subclasses freeze every rule themselves.
+        self.transform = PHMMLP(in_features, out_features, phm_dim, phm_rule, bias=bias, learn_phm=True, activation=activation,
                                 norm=norm, w_init=w_init, c_init=c_init, factor=1)
         if aggr == "softmax":
             self.initial_beta, self.learn_beta = kwargs.get("initial_beta"), kwargs.get("learn_beta")

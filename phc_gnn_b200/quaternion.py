@@ -133,6 +133,10 @@ class _QuaternionMixin(object):
         benchmarks/train_hiv.py:182 picks quaternion_weight_regularization when it is absent), so a quaternion model must
         not expose it; the forward reads the private ``_n``."""
         self.__dict__.pop("phm_dim", None)
+        for m in self.modules():          # every rule is the fixed Hamilton rule (the PHM GINE convs keep theirs trainable, nn.py)
+            if isinstance(m, PHMLinear):
+                m.phm_rule.requires_grad_(False)
+                m.learn_phm = False
 
     def reset_parameters(self):
         super().reset_parameters()

@@ -233,3 +233,41 @@ def test_shipped_checkpoint_import(which):
     with torch.no_grad():
         out = O.model_forward(p, cfg, batch, training=False)
     assert out.shape == (8, cfg["target_dim"]) and torch.isfinite(out).all()
+
+
+def phm_option_cases():
+    return sorted(f[:-3] for f in os.listdir(FAMILY) if f.startswith("phm_") and f.endswith(".pt"))
+
+
+@pytest.mark.parametrize("name", phm_option_cases())
+def test_oracle_matches_reference_on_constructor_options(name):
+    """naive encoders, add_self_loops=False, bias=False, frozen rule, fixed softmax beta — reference-recorded."""
+    fx = load_family(name)
+    p = leaves(fx["state"])
+    for k, v in p.items():                                  # frozen parameters (learn_phm / learn_beta False) have no gradient
+        if v.requires_grad and k not in fx["grads"]:
+            v.requires_grad_(False)
+    data, cfg = fx["batch"], fx["cfg"]
+    logits = O.model_forward(p, cfg, data, training=True)
+    torch.testing.assert_close(logits, fx["logits_train"], rtol=RTOL, atol=ATOL)
+    reg = O.weight_regularization(p, 2)
+    torch.testing.assert_close(reg, fx["reg"], rtol=RTOL, atol=ATOL)
+    loss = O.task_loss(logits, data.y, fx["loss_kind"]) + fx["reg_scale"] * reg
+    torch.testing.assert_close(loss, fx["loss"], rtol=RTOL, atol=ATOL)
+    loss.backward()
+    for k, g in fx["grads"].items():
+        assert p[k].grad is not None, k
+        torch.testing.assert_close(p[k].grad, g, rtol=5e-4, atol=5e-5, msg=lambda m: f"{k}: {m}")
+    with torch.no_grad():
+        ev = O.model_forward(p, cfg, data, training=False)
+    torch.testing.assert_close(ev, fx["logits_eval"], rtol=RTOL, atol=ATOL)
+    assert sum(v.numel() for v in p.values() if v.requires_grad) == fx["n_params"]
+
+
+@pytest.mark.parametrize("name", phm_option_cases())
+def test_product_model_takes_option_state_dicts(name):
+    from phc.hypercomplex.undirectional.models import PHMSkipConnectAdd
+    fx = load_family(name)
+    m = PHMSkipConnectAdd(**fx["cfg"])
+    m.load_state_dict(fx["state"], strict=True)
+    assert m.get_number_of_params_() == fx["n_params"]

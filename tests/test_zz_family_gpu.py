@@ -143,3 +143,26 @@ def test_quaternion_train_steps(monkeypatch):
         r = getattr(mod, "phm_rule", None)
         if isinstance(r, torch.nn.Parameter):
             assert torch.equal(r.detach().cpu(), legacy.hamilton_rule())
+
+
+@pytest.mark.parametrize("fuse", ["direct", "none"], ids=["one-call-per-layer", "separate-ops"])
+@pytest.mark.parametrize("name", __import__("test_family_host").phm_option_cases())
+def test_phm_constructor_options_match_reference_golden(name, fuse, monkeypatch):
+    """Constructor options outside the 14 main fixtures — naive encoders (embedding / linear), add_self_loops=False,
+    bias=False, learn_phm=False (whose reference semantics keep the GINE MLP rules trainable), fixed softmax beta."""
+    monkeypatch.setenv("PHC_PRECISION", "fp32")
+    from gpu_util import product_train_eval
+    fx = load_family(name)
+    got = product_train_eval(fx["cfg"], fx["state"], fx["batch"], fx["loss_kind"], fx["reg_scale"], DEV,
+                             fuse_edge_encoder=fuse != "none", fuse_layer=fuse == "direct")
+    assert_close(got["logits"], fx["logits_train"], RTOL, _tol(fx["logits_train"]), f"{name}: train logits")
+    assert_close(got["reg"], fx["reg"], RTOL, 1e-6, f"{name}: regulariser")
+    assert_close(got["loss"], fx["loss"], RTOL, _tol(fx["loss"]), f"{name}: loss")
+    assert_close(got["logits_eval"], fx["logits_eval"], RTOL, _tol(fx["logits_eval"]), f"{name}: eval logits")
+    for k, g in fx["grads"].items():
+        assert k in got["grads"], f"{name}: no gradient for {k}"
+        assert_close(got["grads"][k], g, 5 * RTOL, 10 * _tol(g), f"{name}: grad {k}")
+    trainable = {k for k, p in got["model"].named_parameters() if p.requires_grad}
+    assert trainable == set(fx["grads"]), f"{name}: trainable parameter sets differ: {sorted(trainable ^ set(fx['grads']))}"
+    for k, v in fx["running_after"].items():
+        assert_close(got["running"][k].float(), v.float(), RTOL, max(1e-5, _tol(v.float())), f"{name}: {k}")
