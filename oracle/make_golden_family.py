@@ -236,10 +236,27 @@ def phm_option_fixtures(outdir):
               f"loss={float(loss):.6f}  {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def init_fixture(outdir):
+    """Known answers of the reference's quaternion initialisers under fixed seeds (phc/quaternion/inits.py:40-113)."""
+    from phc.quaternion.inits import orthogonal_init, quaternion_init
+    fx = {}
+    for fin, fout in ((6, 5), (4, 9)):
+        np.random.seed(21)
+        torch.manual_seed(21)
+        fx[f"quaternion_{fin}_{fout}"] = torch.stack(quaternion_init(fin, fout), dim=0)          # [4, out, in]
+        torch.manual_seed(22)
+        w = torch.stack(orthogonal_init(fin, fout), dim=0).double()
+        fx[f"orthogonal_{fin}_{fout}_gram"] = torch.einsum("cok,coj->kj", w, w) if fout >= fin else torch.einsum("cok,cpk->op", w, w)
+        fx[f"orthogonal_{fin}_{fout}_std"] = w.std()
+    torch.save(fx, os.path.join(outdir, "inits_quaternion.pt"))
+    print("inits_quaternion.pt:", {k: tuple(v.shape) for k, v in fx.items()})
+
+
 def main():
     outdir = os.path.join(ROOT, "tests", "golden", "family")
     os.makedirs(outdir, exist_ok=True)
     legacy_fixture(outdir)
+    init_fixture(outdir)
     quaternion_fixtures(outdir)
     phm_option_fixtures(outdir)
 

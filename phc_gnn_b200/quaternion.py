@@ -45,7 +45,7 @@ def quaternion_init(in_features: int, out_features: int, criterion: str = "gloro
     modulus = torch.from_numpy(chi.rvs(df=4, loc=0, scale=s, size=shape)).to(torch.float64)
     axis = torch.zeros(4, *shape, dtype=torch.float64)
     for c in range(1, 4):
-        axis[c] = torch.empty(shape, dtype=torch.float32).uniform_(low, high).to(torch.float64)
+        axis[c] = torch.empty(shape, dtype=torch.float64).uniform_(low, high)      # fp64 draws, as the reference's
     axis = axis / axis.norm(p=2, dim=0).clamp_min(1e-10)
     theta = torch.from_numpy(np.random.uniform(low=-np.pi, high=np.pi, size=shape)).to(torch.float64)
     share = torch.stack([torch.cos(torch.from_numpy(np.random.uniform(low=-s, high=s, size=shape)).to(torch.float64)) ** 2
@@ -72,10 +72,12 @@ def _qconj(a: torch.Tensor) -> torch.Tensor:
 
 
 def quaternion_orthogonal_init(in_features: int, out_features: int, scale: float = 1.0) -> torch.Tensor:
-    """[4, in, out] weight whose quaternion matrix has orthonormal columns (rows when it is wide), times 1/2 — the
-    property the reference gets from a quaternion Householder QR of a Gaussian matrix (phc/quaternion/inits.py:86-113,
-    qr.py:65-108).  Here: modified Gram-Schmidt in quaternion arithmetic (fp64) on the tall orientation; the two
-    constructions agree up to a unit-quaternion phase per column, which the Gaussian draw makes immaterial."""
+    """[4, in, out] weight whose quaternion matrix has orthonormal columns (rows when it is wide) — the property the
+    reference gets from a quaternion Householder QR of a Gaussian matrix (phc/quaternion/inits.py:86-113, qr.py:65-108; its
+    ``Q /= 2`` undoes the factor 2 its QR carries, cf. phc/quaternion/tests/test_quat_qr.py:17-26, so the result has UNIT
+    columns — checked against the reference: same column / row norms and element std).  Here: modified Gram-Schmidt in
+    quaternion arithmetic (fp64) on the tall orientation; the two constructions agree up to a unit-quaternion phase per
+    column, which the Gaussian draw makes immaterial."""
     rows, cols = max(in_features, out_features), min(in_features, out_features)
     a = torch.zeros(4, rows, cols, dtype=torch.float64).normal_(std=scale)
     for j in range(cols):
@@ -86,7 +88,6 @@ def quaternion_orthogonal_init(in_features: int, out_features: int, scale: float
                 coeff = _qmul(_qconj(a[:, :, :j]), v.unsqueeze(-1).expand(4, rows, j)).sum(dim=1)         # [4, j]
                 v = v - _qmul(a[:, :, :j], coeff.unsqueeze(1).expand(4, rows, j)).sum(dim=2)
         a[:, :, j] = v / v.pow(2).sum().sqrt()
-    a = a / 2.0
     if in_features < out_features:                              # built as [out, in]: transpose the quaternion matrix
         a = a.permute(0, 2, 1)
     return a.contiguous().to(torch.float32)

@@ -118,7 +118,7 @@ def test_quaternion_state_dict_relabelling(name):
 @pytest.mark.parametrize("init", ["orthogonal", "quaternion", "glorot-uniform", "glorot-normal"])
 def test_quaternion_reset_parameters(init):
     """reset_parameters keeps the Hamilton rule (the PHM layer would re-draw it from c_init, reference layers.py:281) and
-    gives the QLinear bias pattern; 'orthogonal' weights have orthonormal quaternion columns times 1/2."""
+    gives the QLinear bias pattern; 'orthogonal' weights have orthonormal quaternion columns (unit norm, as the reference's)."""
     import numpy as np
     from phc.quaternion.undirectional.models import QuaternionSkipConnectAdd
     from phc_gnn_b200 import legacy
@@ -133,7 +133,7 @@ def test_quaternion_reset_parameters(init):
     assert torch.equal(lin.b.detach(), torch.cat([torch.zeros(6), torch.full((18,), 0.2)]))
     assert torch.isfinite(lin.W).all() and float(lin.W.abs().max()) > 0
     if init == "orthogonal":
-        w = lin.W.detach().double().permute(0, 2, 1) * 2            # tall orientation [6 rows, 4 cols]
+        w = lin.W.detach().double().permute(0, 2, 1)                # tall orientation [6 rows, 4 cols]
         gram = torch.stack([torch.stack([_qmul(_qconj(w[:, :, a]), w[:, :, b]).sum(dim=1) for b in range(4)], dim=1)
                             for a in range(4)], dim=1)               # [4, cols, cols]
         eye = torch.zeros_like(gram)
@@ -271,3 +271,23 @@ def test_product_model_takes_option_state_dicts(name):
     m = PHMSkipConnectAdd(**fx["cfg"])
     m.load_state_dict(fx["state"], strict=True)
     assert m.get_number_of_params_() == fx["n_params"]
+
+
+def test_quaternion_initialisers_against_reference_known_answers():
+    """Same seeds -> the reference's 'quaternion' initialisation to rounding (same RNG streams in the same order);
+    'orthogonal': same invariants (real part of the column / row Gram matrix = identity, same element spread)."""
+    import numpy as np
+    from phc_gnn_b200.quaternion import quaternion_init, quaternion_orthogonal_init
+    fx = torch.load(os.path.join(FAMILY, "inits_quaternion.pt"), weights_only=False)
+    for fin, fout in ((6, 5), (4, 9)):
+        np.random.seed(21)
+        torch.manual_seed(21)
+        got = quaternion_init(fin, fout)                                       # [4, in, out]
+        torch.testing.assert_close(got.permute(0, 2, 1), fx[f"quaternion_{fin}_{fout}"], rtol=1e-6, atol=1e-7)
+        torch.manual_seed(22)
+        w = quaternion_orthogonal_init(fin, fout).double().permute(0, 2, 1)   # reference orientation [4, out, in]
+        gram = torch.einsum("cok,coj->kj", w, w) if fout >= fin else torch.einsum("cok,cpk->op", w, w)
+        want = fx[f"orthogonal_{fin}_{fout}_gram"]
+        torch.testing.assert_close(want, torch.eye(want.size(0), dtype=torch.float64), rtol=0, atol=1e-5)   # the reference's property
+        torch.testing.assert_close(gram, torch.eye(gram.size(0), dtype=torch.float64), rtol=0, atol=1e-5)   # ... and ours
+        assert abs(float(w.std()) - float(fx[f"orthogonal_{fin}_{fout}_std"])) < 0.02
