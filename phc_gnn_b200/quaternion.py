@@ -11,6 +11,9 @@ network with its real transform (quaternion/downstream.py).  So the family is a 
 and the tcgen05 PHMLinear, fused aggregation and batch-norm kernels run it unchanged.  Parameters live in the PHM layout;
 ``load_quaternion_state_dict`` / ``quaternion_state_dict`` translate from / to the reference's ``W_r..W_k`` names.
 
+Model construction draws its weights from the reference's distributions but not with its RNG sequence (the reference
+re-initialises every module several times while building; only the stand-alone initialisers are seed-compatible).
+
 Not covered: ``norm="q-batch-norm"`` (4x4 whitening with a Cholesky factor per feature, quaternion/norm.py:86-200) has no PHM
 counterpart and no kernel here; it raises at construction.
 """
