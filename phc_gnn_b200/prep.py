@@ -78,6 +78,20 @@ class RemoveIsolatedNodes(object):
         return f"{self.__class__.__name__}()"
 
 
+def plan_collate(ids, node_ptr: np.ndarray, edge_ptr: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Host half of a collate: (ids as int64, node prefix sums [B+1], edge prefix sums [B+1]) of the selected graphs — where
+    every graph's nodes / edges start in the assembled batch.  Raises IndexError for an id outside the store."""
+    ids_np = np.asarray(ids.cpu().numpy() if torch.is_tensor(ids) else ids, dtype=np.int64).reshape(-1)
+    B = int(ids_np.shape[0])
+    if B and (ids_np.min() < 0 or ids_np.max() >= len(node_ptr) - 1):
+        raise IndexError("graph id outside the store")
+    onp = np.zeros(B + 1, dtype=np.int64)
+    oep = np.zeros(B + 1, dtype=np.int64)
+    np.cumsum(node_ptr[ids_np + 1] - node_ptr[ids_np], out=onp[1:])
+    np.cumsum(edge_ptr[ids_np + 1] - edge_ptr[ids_np], out=oep[1:])
+    return ids_np, onp, oep
+
+
 class DeviceGraphStore(object):
     """A graph dataset packed in device memory + the PyG-compatible collate of a mini-batch from it.
 
@@ -135,14 +149,8 @@ class DeviceGraphStore(object):
         """``Batch.from_data_list([dataset[i] for i in ids])`` -> ``synthetic.GraphBatch`` on the device.  ``ids``: host
         sequence / numpy array / CPU tensor of graph indices (any order, repeats allowed)."""
         from .synthetic import GraphBatch
-        ids_np = np.asarray(ids.cpu().numpy() if torch.is_tensor(ids) else ids, dtype=np.int64).reshape(-1)
+        ids_np, onp, oep = plan_collate(ids, self.node_ptr_host, self.edge_ptr_host)
         B = int(ids_np.shape[0])
-        if B and (ids_np.min() < 0 or ids_np.max() >= self.num_graphs):
-            raise IndexError("graph id outside the store")
-        onp = np.zeros(B + 1, dtype=np.int64)
-        oep = np.zeros(B + 1, dtype=np.int64)
-        np.cumsum(self.node_ptr_host[ids_np + 1] - self.node_ptr_host[ids_np], out=onp[1:])
-        np.cumsum(self.edge_ptr_host[ids_np + 1] - self.edge_ptr_host[ids_np], out=oep[1:])
         N, E = int(onp[-1]), int(oep[-1])
         words = 3 * B + 2
         if self._staging is None or self._staging.numel() < words:

@@ -66,3 +66,26 @@ def test_epoch_sampler_shards_by_graph(G, B, W):
     assert all(len(ids) == B for ids in full)
     ordered = np.concatenate(list(EpochSampler(G, B, shuffle=False)))
     assert ordered.tolist() == list(range(G))
+
+
+def test_plan_collate_offsets_match_the_oracle_batch():
+    """Host half of the device collate: the prefix sums place every selected graph where the oracle's collate puts it."""
+    import numpy as np
+    from phc_gnn_b200.prep import plan_collate
+    from phc_gnn_b200.synthetic import make_batch, split_graphs, workloads
+    graphs = split_graphs(make_batch(workloads(4)["hiv"], seed=4, batch_graphs=9))
+    nptr = np.concatenate([[0], np.cumsum([g.x.size(0) for g in graphs])]).astype(np.int64)
+    eptr = np.concatenate([[0], np.cumsum([g.edge_index.size(1) for g in graphs])]).astype(np.int64)
+    ids = [7, 0, 7, 3, 8]
+    ids_np, onp, oep = plan_collate(torch.tensor(ids), nptr, eptr)
+    x, ei, ea, batch, y = O.collate([graphs[i] for i in ids])
+    assert ids_np.tolist() == ids and onp[-1] == x.size(0) and oep[-1] == ei.size(1)
+    assert onp.tolist() == O.graph_ptr(batch, len(ids)).tolist()
+    for b, g in enumerate(ids):
+        assert torch.equal(x[onp[b]:onp[b + 1]], graphs[g].x)
+        assert torch.equal(ei[:, oep[b]:oep[b + 1]] - int(onp[b]), graphs[g].edge_index)
+    e_ids, e_onp, e_oep = plan_collate([], nptr, eptr)
+    assert e_ids.shape == (0,) and e_onp.tolist() == [0] and e_oep.tolist() == [0]
+    for bad in ([9], [-1], [0, 12]):
+        with pytest.raises(IndexError):
+            plan_collate(bad, nptr, eptr)
