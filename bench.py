@@ -36,6 +36,8 @@ def parse():
     ap.add_argument("--workload", default="ppa")
     ap.add_argument("--phm-dim", type=int, default=4)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--family", default="phm", choices=["phm", "quaternion"],
+                    help="quaternion: the reference's QuaternionSkipConnectAdd on the same kernels (n = 4, frozen Hamilton rule)")
     ap.add_argument("--batches", type=int, default=8, help="distinct synthetic batches cycled per rank")
     ap.add_argument("--precision", default=None, help="fp32 | tf32x3 | bf16 (default: PHC_PRECISION or tf32x3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -140,7 +142,8 @@ def config_dict(args, wl, graphs_per_gpu, l2):
     return {"workload": f"{wl.name}-shaped synthetic graphs (BASELINE.json configs: PHC-GNN n={m['phm_dim']}, "
                         f"{len(m['mp_layers'])}x{m['mp_layers'][0]}, aggr={m['msg_aggr']}, mlp={m['mlp']})",
             "graphs_per_gpu_batch": graphs_per_gpu, "phm_dim": m["phm_dim"], "width": m["mp_layers"][0],
-            "layers": len(m["mp_layers"]), "aggr": m["msg_aggr"], "parallelism": f"dp{args.gpus}", "l2": l2}
+            "layers": len(m["mp_layers"]), "aggr": m["msg_aggr"], "parallelism": f"dp{args.gpus}", "l2": l2,
+            **({"family": "quaternion"} if getattr(args, "family", "phm") == "quaternion" else {})}
 
 
 def cpu_baseline(wl, budget_s: float = 25.0):
@@ -204,7 +207,13 @@ def run_b200(args):
     torch.manual_seed(0)
     import numpy as np
     np.random.seed(0)
-    model = PHMSkipConnectAdd(**wl.model).to(dev)
+    if args.family == "quaternion":
+        from phc_gnn_b200.quaternion import QuaternionSkipConnectAdd
+        assert args.phm_dim == 4, "--family quaternion is the n = 4 configuration"
+        qkw = {k: v for k, v in wl.model.items() if k not in ("phm_dim", "learn_phm", "phm_rule", "w_init", "c_init", "sc_type")}
+        model = QuaternionSkipConnectAdd(init="orthogonal", **qkw).to(dev)
+    else:
+        model = PHMSkipConnectAdd(**wl.model).to(dev)
     dp = DataParallelPHC(model) if world > 1 else None
     step = TrainStep(model, wl, None, dp)        # flat clip+Adam (optim.FlatClipAdam): same update rule, 2 launches
     model.train()
