@@ -197,21 +197,29 @@ def phm_option_cases():
     c = tiny(w4["mnist"], 16, 2, 4, 7, 10, head=[16, 8]); c.extra["k"] = 3
     c.model.update(naive_encoder=True, msg_aggr="softmax", initial_beta=1.3, learn_beta=False, mlp=True)
     out["phm_mnist_naive_linear_enc_softmax_fixed_beta"] = c
+    # PHMSkipConnectConcat runs in the reference only for phm_dim = 1: pins the concat model's structure
+    c = tiny(workloads(1)["hiv"], 8, 2, 6, 4, 8, head=[6, 4]); c.model.update(mp_layers=[8, 12], msg_aggr="sum", mlp=True)
+    out["phm_concat_n1_hiv_sum_mlp"] = c
+    c = tiny(workloads(1)["mnist"], 6, 2, 4, 7, 10, head=[5]); c.extra["k"] = 3
+    c.model.update(mp_layers=[6, 4], msg_aggr="max", mlp=False, pooling="globalsum")
+    out["phm_concat_n1_mnist_max_lin"] = c
     return out
 
 
 def phm_option_fixtures(outdir):
     sys.path.insert(0, HERE)
     from make_golden import seeded_fill as phm_fill        # same seeding rules as the main PHM fixtures
-    from phc.hypercomplex.undirectional.models import PHMSkipConnectAdd
+    from phc.hypercomplex.undirectional.models import PHMSkipConnectAdd, PHMSkipConnectConcat
     from phc.hypercomplex.regularization import phm_weight_regularization
-    for k, (name, wl) in enumerate(sorted(phm_option_cases().items())):
+    # seeds follow the alphabetical order of the Add cases; the Concat cases were appended later
+    for k, (name, wl) in enumerate(sorted(phm_option_cases().items(), key=lambda kv: ("concat" in kv[0], kv[0]))):
         torch.manual_seed(500 + k)
         np.random.seed(500 + k)
         kw = dict(wl.model)
         kw["dropout_mpnn"] = [0.0] * len(kw["mp_layers"])
         kw["dropout_dn"] = [0.0] * len(kw["downstream_layers"])
-        model = PHMSkipConnectAdd(**kw)
+        concat = "concat" in name
+        model = (PHMSkipConnectConcat if concat else PHMSkipConnectAdd)(**kw)
         phm_fill(model, 60 + k)
         data = make_batch(wl, seed=70 + k)
         state0 = {n: v.clone() for n, v in model.state_dict().items()}
@@ -225,7 +233,7 @@ def phm_option_fixtures(outdir):
         model.eval()
         with torch.no_grad():
             logits_eval = model(data)
-        fx = dict(name=name, model="phm", cfg=kw, loss_kind=wl.loss, reg_scale=0.01,
+        fx = dict(name=name, model="phm_concat" if concat else "phm", cfg=kw, loss_kind=wl.loss, reg_scale=0.01,
                   data=dict(x=data.x, edge_index=data.edge_index, edge_attr=data.edge_attr, batch=data.batch,
                             y=data.y, num_graphs=data.num_graphs),
                   state=state0, logits_train=logits.detach(), loss=loss.detach(), reg=reg.detach(), grads=grads,

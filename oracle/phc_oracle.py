@@ -382,14 +382,16 @@ def quaternion_model_forward(pq: Params, cfg: Dict, data, training: bool = True,
     return model_forward(quaternion_as_phm(pq), quaternion_cfg(cfg), data, training, generator)
 
 
-def quaternion_concat_model_forward(pq: Params, cfg: Dict, data, training: bool = True, generator=None) -> torch.Tensor:
-    """QuaternionSkipConnectConcat.forward (phc/quaternion/undirectional/models.py:366-403): conv (aggregate -> add self
-    loops -> transform, ``same_dim=False``) -> norm -> act -> dropout -> ``qcat`` with the atom embedding, i.e. a
-    per-component concat; pooling and downstream act on the last layer's width + the embedding width."""
-    p = quaternion_as_phm(pq)
-    c = quaternion_cfg(cfg)
+def concat_model_forward(p: Params, cfg: Dict, data, training: bool = True, generator=None, component_cat: bool = False):
+    """PHMSkipConnectConcat.forward (phc/hypercomplex/undirectional/models.py:452-500; runs in the reference only for
+    phm_dim = 1) and, with ``component_cat``, QuaternionSkipConnectConcat.forward
+    (phc/quaternion/undirectional/models.py:366-403): conv (aggregate -> add self loops -> transform, ``same_dim=False``)
+    -> norm -> act -> dropout -> concat with the ATOM embedding (every layer, whatever ``sc_type`` says) — a flat
+    ``torch.cat`` in the PHM model (:467), ``qcat`` = per-component concat in the quaternion one; pooling and downstream
+    act on the last layer's width + the embedding width."""
+    c = dict(cfg)
     c["same_dim"] = False
-    n = 4
+    n = c["phm_dim"]
     dtype = p["downstream.real_trafo.affine.bias"].dtype
     h0 = encoder(data.x, p, "atomencoder", n, c["atom_input_dims"], dtype)
     h = h0
@@ -400,9 +402,13 @@ def quaternion_concat_model_forward(pq: Params, cfg: Dict, data, training: bool 
             z = phm_norm(z, p, f"norms.{i}", n, training)
         z = activation(z, c["activation"])
         z = phm_dropout(z, n, c["dropout_mpnn"][i], training, c["same_dropout"], generator)
-        h = phm_cat([z, h0], n)
+        h = phm_cat([z, h0], n) if component_cat else torch.cat([z, h0], dim=-1)
     out = pooling(h, data.batch, data.num_graphs, p, c)
     return downstream(out, p, c, training, generator)
+
+
+def quaternion_concat_model_forward(pq: Params, cfg: Dict, data, training: bool = True, generator=None) -> torch.Tensor:
+    return concat_model_forward(quaternion_as_phm(pq), quaternion_cfg(cfg), data, training, generator, component_cat=True)
 
 
 def quaternion_weight_regularization(pq: Params, cfg: Dict, order: int = 1) -> torch.Tensor:

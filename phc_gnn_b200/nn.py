@@ -773,7 +773,7 @@ class _PHMSkipConnectBase(nn.Module):
                                            aggr=msg_aggr, mlp=mlp, add_self_loops=add_self_loops, same_dim=not concat,
                                            msg_encoder=msg_encoder, **kwargs))
             norms.append(PHMNorm(num_features=out_dim, phm_dim=phm_dim, type=norm_mp) if self.norm_mp else None)
-            width = out_dim + (self.input_dim if (concat and (sc_type == "first" or i == 0)) else (width if concat else 0))
+            width = out_dim + (self.input_dim if concat else 0)      # concat: always with the atom embedding (reference :467,:479-481)
         self.convs, self.norms, self.bondencoders = nn.ModuleList(convs), nn.ModuleList(norms), nn.ModuleList(bond)
         final = width if concat else mp_layers[-1]
         if pooling == "globalsum":
@@ -880,7 +880,9 @@ class PHMSkipConnectAdd(_PHMSkipConnectBase):
 class PHMSkipConnectConcat(_PHMSkipConnectBase):
     """Skip connections through concatenation — reference models.py:271-517.  The reference's forward
     raises for every phm_dim > 1 (models.py:486 reshapes the layer-0 bond embedding n times too wide,
-    SURVEY.md D2), so there is no oracle: this implements the evident intent and its parity is UNPINNED."""
+    SURVEY.md D2): parity is pinned at phm_dim = 1 (fixtures ``phm_concat_n1_*``: layer widths, skip = atom embedding for
+    every layer, pooling / downstream widths) and, for the quaternion subclass, by the reference's working
+    QuaternionSkipConnectConcat; for phm_dim > 1 this implements the evident intent (flat concat as written at :467)."""
 
     def __init__(self, phm_dim: int = 4, learn_phm: bool = True, phm_rule=None, atom_input_dims: Union[int, list] = ATOM_FEAT_DIMS,
                  atom_encoded_dim: int = 196, bond_input_dims: Union[int, list] = BOND_FEAT_DIMS, naive_encoder: bool = False,
@@ -907,7 +909,7 @@ class PHMSkipConnectConcat(_PHMSkipConnectBase):
         h = h0
         act = self.activation_str.lower()
         for i in range(len(self.mp_layers)):
-            skip = h0 if (i == 0 or self.sc_type == "first") else h
+            skip = h0                                 # the reference concatenates the atom embedding whatever sc_type says (:479-481)
             e = self._encode_edges(i, edge_attr)
             z = self.convs[i](x=h, edge_index=edge_index, edge_attr=e, size=size)
             z = norm_act_drop_skip(self.norms[i], z, None, act, self._n, self.training, drop_p=self.dropout_mpnn[i],

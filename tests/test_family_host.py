@@ -248,7 +248,8 @@ def test_oracle_matches_reference_on_constructor_options(name):
         if v.requires_grad and k not in fx["grads"]:
             v.requires_grad_(False)
     data, cfg = fx["batch"], fx["cfg"]
-    logits = O.model_forward(p, cfg, data, training=True)
+    forward = O.concat_model_forward if fx["model"] == "phm_concat" else O.model_forward     # concat: phm_dim = 1 only (D2)
+    logits = forward(p, cfg, data, training=True)
     torch.testing.assert_close(logits, fx["logits_train"], rtol=RTOL, atol=ATOL)
     reg = O.weight_regularization(p, 2)
     torch.testing.assert_close(reg, fx["reg"], rtol=RTOL, atol=ATOL)
@@ -259,16 +260,20 @@ def test_oracle_matches_reference_on_constructor_options(name):
         assert p[k].grad is not None, k
         torch.testing.assert_close(p[k].grad, g, rtol=5e-4, atol=5e-5, msg=lambda m: f"{k}: {m}")
     with torch.no_grad():
-        ev = O.model_forward(p, cfg, data, training=False)
+        ev = forward(p, cfg, data, training=False)
     torch.testing.assert_close(ev, fx["logits_eval"], rtol=RTOL, atol=ATOL)
     assert sum(v.numel() for v in p.values() if v.requires_grad) == fx["n_params"]
 
 
+def phm_product_class(fx):
+    from phc.hypercomplex.undirectional.models import PHMSkipConnectAdd, PHMSkipConnectConcat
+    return PHMSkipConnectConcat if fx["model"] == "phm_concat" else PHMSkipConnectAdd
+
+
 @pytest.mark.parametrize("name", phm_option_cases())
 def test_product_model_takes_option_state_dicts(name):
-    from phc.hypercomplex.undirectional.models import PHMSkipConnectAdd
     fx = load_family(name)
-    m = PHMSkipConnectAdd(**fx["cfg"])
+    m = phm_product_class(fx)(**fx["cfg"])
     m.load_state_dict(fx["state"], strict=True)
     assert m.get_number_of_params_() == fx["n_params"]
 

@@ -149,20 +149,37 @@ def test_quaternion_train_steps(monkeypatch):
 @pytest.mark.parametrize("name", __import__("test_family_host").phm_option_cases())
 def test_phm_constructor_options_match_reference_golden(name, fuse, monkeypatch):
     """Constructor options outside the 14 main fixtures — naive encoders (embedding / linear), add_self_loops=False,
-    bias=False, learn_phm=False (whose reference semantics keep the GINE MLP rules trainable), fixed softmax beta."""
+    bias=False, learn_phm=False (whose reference semantics keep the GINE MLP rules trainable), fixed softmax beta — and
+    PHMSkipConnectConcat at phm_dim = 1 (the only n the reference's concat model runs for)."""
     monkeypatch.setenv("PHC_PRECISION", "fp32")
-    from gpu_util import product_train_eval
+    from phc.hypercomplex.regularization import phm_weight_regularization
+    from test_family_host import phm_product_class
     fx = load_family(name)
-    got = product_train_eval(fx["cfg"], fx["state"], fx["batch"], fx["loss_kind"], fx["reg_scale"], DEV,
-                             fuse_edge_encoder=fuse != "none", fuse_layer=fuse == "direct")
-    assert_close(got["logits"], fx["logits_train"], RTOL, _tol(fx["logits_train"]), f"{name}: train logits")
-    assert_close(got["reg"], fx["reg"], RTOL, 1e-6, f"{name}: regulariser")
-    assert_close(got["loss"], fx["loss"], RTOL, _tol(fx["loss"]), f"{name}: loss")
-    assert_close(got["logits_eval"], fx["logits_eval"], RTOL, _tol(fx["logits_eval"]), f"{name}: eval logits")
+    m = phm_product_class(fx)(**fx["cfg"])
+    m.load_state_dict(fx["state"], strict=True)
+    m = m.to(DEV)
+    m.fuse_edge_encoder = fuse != "none"
+    m.fuse_layer = fuse == "direct"
+    data = fx["batch"].to(DEV)
+    m.train()
+    logits = m(data)
+    reg = phm_weight_regularization(m, p=2)
+    loss = O.task_loss(logits, data.y, fx["loss_kind"]) + fx["reg_scale"] * reg
+    loss.backward()
+    torch.cuda.synchronize()
+    grads = {k: p.grad.detach().cpu() for k, p in m.named_parameters() if p.grad is not None}
+    running = {k: v.detach().cpu() for k, v in m.state_dict().items() if "running" in k or "tracked" in k}
+    m.eval()
+    with torch.no_grad():
+        ev = m(data).cpu()
+    assert_close(logits.detach().cpu(), fx["logits_train"], RTOL, _tol(fx["logits_train"]), f"{name}: train logits")
+    assert_close(reg.detach().cpu(), fx["reg"], RTOL, 1e-6, f"{name}: regulariser")
+    assert_close(loss.detach().cpu(), fx["loss"], RTOL, _tol(fx["loss"]), f"{name}: loss")
+    assert_close(ev, fx["logits_eval"], RTOL, _tol(fx["logits_eval"]), f"{name}: eval logits")
     for k, g in fx["grads"].items():
-        assert k in got["grads"], f"{name}: no gradient for {k}"
-        assert_close(got["grads"][k], g, 5 * RTOL, 10 * _tol(g), f"{name}: grad {k}")
-    trainable = {k for k, p in got["model"].named_parameters() if p.requires_grad}
+        assert k in grads, f"{name}: no gradient for {k}"
+        assert_close(grads[k], g, 5 * RTOL, 10 * _tol(g), f"{name}: grad {k}")
+    trainable = {k for k, p in m.named_parameters() if p.requires_grad}
     assert trainable == set(fx["grads"]), f"{name}: trainable parameter sets differ: {sorted(trainable ^ set(fx['grads']))}"
     for k, v in fx["running_after"].items():
-        assert_close(got["running"][k].float(), v.float(), RTOL, max(1e-5, _tol(v.float())), f"{name}: {k}")
+        assert_close(running[k].float(), v.float(), RTOL, max(1e-5, _tol(v.float())), f"{name}: {k}")
