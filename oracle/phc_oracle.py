@@ -257,11 +257,22 @@ def conv(x, edge_index, edge_emb, p: Params, key: str, cfg: Dict, training: bool
     return phm_linear(agg + x if loops else agg, p, t)
 
 
+def real_transform(x: torch.Tensor, p: Params, key: str, cfg: Dict) -> torch.Tensor:
+    """RealTransformer.forward (layers.py:399-413).  "linear": nn.Linear(F -> F/n).  The other modes split x into pieces of
+    width ``in_features`` = the FULL width, i.e. into ONE piece, and reduce over that single piece: "sum" / "mean" return x
+    unchanged, "norm" returns |x| — all three leave the width at F; restated as observed."""
+    kind = cfg.get("real_trafo", "linear")
+    if kind == "linear":
+        return x @ p[key + ".affine.weight"].t() + p[key + ".affine.bias"]
+    return x.abs() if kind == "norm" else x
+
+
 def pooling(x, batch, num_graphs, p: Params, cfg: Dict) -> torch.Tensor:
     n = cfg["phm_dim"]
     if cfg["pooling"] == "softattention":
         g = phm_linear(x, p, "pooling.linear")
-        g = torch.sigmoid(g @ p["pooling.real_trafo.affine.weight"].t() + p["pooling.real_trafo.affine.bias"])
+        g = torch.sigmoid(real_transform(g, p, "pooling.real_trafo", cfg))
+        assert g.size(-1) * n == x.size(-1), "soft-attention gate width != F/n (the reference raises here for a non-linear real_trafo, n > 1)"
         x = (x.reshape(x.size(0), n, -1) * g[:, None, :]).reshape(x.shape)
     return seg_sum(x, batch, num_graphs)
 
@@ -278,13 +289,13 @@ def downstream(x, p: Params, cfg: Dict, training: bool, generator=None) -> torch
                 x = phm_norm(x, p, f"downstream.norm.{j}", n, training)
             x = activation(x, cfg["activation"])
             x = phm_dropout(x, n, drops[j], training, cfg["same_dropout"], generator)
-    return x @ p["downstream.real_trafo.affine.weight"].t() + p["downstream.real_trafo.affine.bias"]
+    return real_transform(x, p, "downstream.real_trafo", cfg)
 
 
 def model_forward(p: Params, cfg: Dict, data, training: bool = True, generator=None) -> torch.Tensor:
     """PHMSkipConnectAdd.forward (models.py:219-249)."""
     n = cfg["phm_dim"]
-    dtype = p["downstream.real_trafo.affine.bias"].dtype
+    dtype = p["downstream.affine.0.W"].dtype
     edge_attr = data.edge_attr
     h0 = encoder(data.x, p, "atomencoder", n, cfg["atom_input_dims"], dtype)
     h = h0
@@ -392,7 +403,7 @@ def concat_model_forward(p: Params, cfg: Dict, data, training: bool = True, gene
     c = dict(cfg)
     c["same_dim"] = False
     n = c["phm_dim"]
-    dtype = p["downstream.real_trafo.affine.bias"].dtype
+    dtype = p["downstream.affine.0.W"].dtype
     h0 = encoder(data.x, p, "atomencoder", n, c["atom_input_dims"], dtype)
     h = h0
     for i in range(len(c["mp_layers"])):
