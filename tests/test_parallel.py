@@ -78,3 +78,61 @@ def test_get_model_blocks_sees_through_wrapper():
     assert len(get_model_blocks(dp, "convs", lr=0.1)[0]["params"]) == 2
     assert get_model_blocks(dp, "pooling") == [] and get_model_blocks(dp, "nope") == []
     assert get_model_blocks(m, "convs", lr=0.1)[0]["lr"] == 0.1
+
+
+def _sharded_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from phc_gnn_b200.parallel import DataParallelPHC
+        from phc_gnn_b200.prep import EpochSampler
+        torch.manual_seed(0)
+        feats, target = torch.randn(40, 6), torch.randn(40, 1)          # one row per "graph"
+        torch.manual_seed(5 + rank)
+        model = torch.nn.Linear(6, 1)
+        dp = DataParallelPHC(model)                                     # broadcast from rank 0
+        sampler = EpochSampler(40, 4, rank=rank, world=world, seed=9, drop_last=True)
+        steps = []
+        for ids in sampler:
+            for p in model.parameters():
+                p.grad = None
+            idx = torch.from_numpy(ids)
+            ((dp(feats[idx]) - target[idx]) ** 2).mean().backward()
+            dp.reduce_gradients()
+            steps.append((ids.tolist(), [p.grad.detach().clone() for p in model.parameters()]))
+        out[rank] = dict(steps=steps, w=[p.detach().clone() for p in model.parameters()])
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_epoch_equals_global_batches_gloo():
+    """Data parallelism shards by graph: with EpochSampler's per-rank slices of every global batch, the all-reduced
+    (averaged) gradient of each step equals the single-process gradient on the union of the ranks' graphs."""
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_sharded_worker, args=(world, port, out), nprocs=world, join=True)
+    a, b = out[0], out[1]
+    assert len(a["steps"]) == len(b["steps"]) == 5
+    torch.manual_seed(0)
+    feats, target = torch.randn(40, 6), torch.randn(40, 1)
+    model = torch.nn.Linear(6, 1)
+    with torch.no_grad():
+        for p, w in zip(model.parameters(), a["w"]):
+            p.copy_(w)
+    seen = []
+    for (ia, ga), (ib, gb) in zip(a["steps"], b["steps"]):
+        assert not set(ia) & set(ib) and len(ia) == len(ib) == 4
+        seen += ia + ib
+        idx = torch.tensor(ia + ib)
+        for p in model.parameters():
+            p.grad = None
+        ((model(feats[idx]) - target[idx]) ** 2).mean().backward()
+        for p, x, y in zip(model.parameters(), ga, gb):
+            assert torch.equal(x, y)
+            torch.testing.assert_close(x, p.grad, rtol=1e-5, atol=1e-6)
+    assert len(set(seen)) == 40
