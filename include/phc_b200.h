@@ -78,7 +78,7 @@ int phc_remove_isolated_nodes(const long long* edge_index, int num_edges, int nu
                               phc_stream_t stream);
 
 /* ---- batch preparation: Batch collate from a dataset resident in HBM (replaces the CPU DataLoader collate,
- * torch_geometric.data.DataLoader -> Batch.from_data_list, reference benchmarks/train_hiv.py:556-561 and the other train_*.py;
+ * torch_geometric.data.DataLoader -> Batch.from_data_list, reference benchmarks/train_hiv.py:481-493 and the other train_*.py;
  * restated in oracle/phc_oracle.py::collate).  Store: graphs packed back to back — node_ptr / edge_ptr int64 [store_graphs+1],
  * edge_index int64 [2, store_edges] with node ids LOCAL to each graph, x rows per node, edge_attr rows per edge, y rows per graph
  * (row sizes in bytes, multiples of 4; pass 0 / NULL to skip a tensor).  Batch: graph_ids int64 [num_graphs] (any order,

@@ -539,7 +539,7 @@ def remove_isolated_nodes(edge_index: torch.Tensor, edge_attr=None, num_nodes=No
 
 def collate(graphs):
     """torch_geometric.data.Batch.from_data_list (PyG 1.6.1, as the reference's DataLoader calls it for every mini-batch,
-    benchmarks/train_hiv.py:556-561): per key concatenate along the node / edge axis, ``edge_index`` shifted by the
+    benchmarks/train_hiv.py:481-493): per key concatenate along the node / edge axis, ``edge_index`` shifted by the
     cumulative node count (``__inc__``), ``batch`` = position of the graph repeated per node, ``y`` concatenated along
     dim 0.  Returns (x, edge_index, edge_attr, batch, y).  Documented PyG behaviour; the package is not installable here,
     so this is pinned by a hand-worked example and by the round trip against synthetic.make_batch (which builds its batches

@@ -211,7 +211,7 @@ int phc_remove_isolated_nodes(const long long* edge_index, int num_edges, int nu
 
 // ------------------------------------------------------------------------------------------------------------------
 // Batch collate on the device: what the reference's DataLoader does on the CPU for every step
-// (torch_geometric.data.DataLoader -> Batch.from_data_list, used at benchmarks/train_hiv.py:556-561 and the other
+// (torch_geometric.data.DataLoader -> Batch.from_data_list, used at benchmarks/train_hiv.py:481-493 and the other
 // train_*.py): node / edge tensors of the selected graphs concatenated in batch order, each graph's edge_index shifted
 // by the number of nodes before it, `batch` = graph position repeated per node, graph-level targets stacked.
 // Here the dataset is RESIDENT IN HBM as one packed store (graphs back to back, edge ids local to their graph), so a

@@ -7,7 +7,7 @@ out).  PyG runs it as a dozen index kernels plus boolean-mask gathers; here the 
 sizes, which PyG needs as well (``mask.sum()``).
 
 The reference's ``DataLoader`` collates every mini-batch on the CPU (``Batch.from_data_list``: concatenate, shift each graph's
-``edge_index``, build ``batch``; benchmarks/train_hiv.py:556-561) and the loop then copies it to the GPU (:171).  With 180 GB of
+``edge_index``, build ``batch``; benchmarks/train_hiv.py:481-493) and the loop then copies it to the GPU (:173).  With 180 GB of
 HBM the whole dataset fits on the device (ogbg-ppa, the largest, is ~10 GB as int64/fp32 tensors): ``DeviceGraphStore`` keeps it
 packed in HBM and ``collate(ids)`` assembles a mini-batch with ONE kernel (``phc_collate_batch``, csrc/prep.cu) — the host only
 sends the [B] graph ids and their size prefix sums (a few KB, one pinned copy), and there is no host synchronisation.
@@ -192,7 +192,7 @@ class DeviceGraphStore(object):
 
 class EpochSampler(object):
     """Graph ids of one rank's mini-batches for one epoch: a seeded permutation of the dataset (``shuffle=True``, the
-    scripts' training loaders, benchmarks/train_hiv.py:556) cut into global batches of ``world * batch_graphs`` graphs, of
+    scripts' training loaders, benchmarks/train_hiv.py:488-489) cut into global batches of ``world * batch_graphs`` graphs, of
     which rank r takes the r-th slice — every graph is visited once per epoch by exactly one rank, all ranks run the same
     number of steps (a last global batch that cannot give every rank a graph is dropped; a short one is split evenly).
     Pure host logic (numpy): data parallelism shards by graph, no collective is involved."""
