@@ -26,8 +26,8 @@ Reference locations restated here (relative to /root/reference):
   model_forward (Add model)  phc/hypercomplex/undirectional/models.py:200-249
   weight_regularization      phc/hypercomplex/regularization.py:15-23
   train_step                 benchmarks/train_hiv.py:165-202 (and the zinc/ppa/mnist variants)
-  quaternion_* / legacy_*    phc/quaternion/layers.py:50-126, algebra.py (Hamilton product), encoder.py:62-91,
-                             norm.py:268-287, regularization.py:27-97; phc/hypercomplex/layers.py:58-78,114-192
+  quaternion_* / legacy_*    phc/quaternion/layers.py:50-126, algebra.py (Hamilton product), encoder.py:63-96,
+                             norm.py:279-300, regularization.py:27-97; phc/hypercomplex/layers.py:58-78,114-192
                              (pinned by oracle/make_golden_family.py -> tests/golden/family/)
 """
 from __future__ import annotations
@@ -388,7 +388,7 @@ def quaternion_cfg(cfg: Dict) -> Dict:
 
 
 def quaternion_model_forward(pq: Params, cfg: Dict, data, training: bool = True, generator=None) -> torch.Tensor:
-    """QuaternionSkipConnectAdd.forward (phc/quaternion/undirectional/models.py:198-215) — block for block the PHM
+    """QuaternionSkipConnectAdd.forward (phc/quaternion/undirectional/models.py:195-215) — block for block the PHM
     forward at n = 4 with the Hamilton product as the linear map (every skip adds the atom embedding)."""
     return model_forward(quaternion_as_phm(pq), quaternion_cfg(cfg), data, training, generator)
 
@@ -396,7 +396,7 @@ def quaternion_model_forward(pq: Params, cfg: Dict, data, training: bool = True,
 def concat_model_forward(p: Params, cfg: Dict, data, training: bool = True, generator=None, component_cat: bool = False):
     """PHMSkipConnectConcat.forward (phc/hypercomplex/undirectional/models.py:452-500; runs in the reference only for
     phm_dim = 1) and, with ``component_cat``, QuaternionSkipConnectConcat.forward
-    (phc/quaternion/undirectional/models.py:366-403): conv (aggregate -> add self loops -> transform, ``same_dim=False``)
+    (phc/quaternion/undirectional/models.py:391-430): conv (aggregate -> add self loops -> transform, ``same_dim=False``)
     -> norm -> act -> dropout -> concat with the ATOM embedding (every layer, whatever ``sc_type`` says) — a flat
     ``torch.cat`` in the PHM model (:467), ``qcat`` = per-component concat in the quaternion one; pooling and downstream
     act on the last layer's width + the embedding width."""
@@ -424,7 +424,7 @@ def quaternion_concat_model_forward(pq: Params, cfg: Dict, data, training: bool 
 
 def quaternion_weight_regularization(pq: Params, cfg: Dict, order: int = 1) -> torch.Tensor:
     """phc/quaternion/regularization.py:27-97, undirectional branch: message-passing weights, the pooling weight stacked
-    as (W_r, W_i, W_k, W_k) — line 77 as written —, downstream weights; each stack.norm(p, dim=0).mean()."""
+    as (W_r, W_i, W_k, W_k) — line 81 as written —, downstream weights; each stack.norm(p, dim=0).mean()."""
     stacks = []
     for i in range(len(cfg["mp_layers"])):
         t = f"convs.{i}.transform.transform"

@@ -99,7 +99,7 @@ def to_legacy_phm_state_dict(sd: Dict[str, torch.Tensor]) -> "OrderedDict[str, t
 def _quat_module_key(k: str) -> str:
     """Module-path differences between the quaternion and the PHM trees: QMLP's ``qlinear1/2`` are PHMMLP's
     ``linear1/2`` (reference quaternion/layers.py:139-142 vs hypercomplex/layers.py:326-331); the encoders' and the
-    naive batch-norm's children named r,i,j,k are list entries 0..3 (quaternion/encoder.py:64-73, quaternion/norm.py:275-279
+    naive batch-norm's children named r,i,j,k are list entries 0..3 (quaternion/encoder.py:63-79, quaternion/norm.py:279-300
     vs hypercomplex/encoder.py:18-25, hypercomplex/norm.py)."""
     k = k.replace(".qlinear1.", ".linear1.").replace(".qlinear2.", ".linear2.")
     k = re.sub(r"\.bn\.bn\.([rijk])\.", lambda m: f".bn.bn.{_COMP[m.group(1)]}.", k)

@@ -4,7 +4,7 @@ A quaternion linear map ``W (x) q`` (Hamilton product, reference phc/quaternion/
 n = 4, a FIXED multiplication rule and ``W'_c = W_c^T`` (see legacy.py; the relation is checked inside the reference by
 oracle/make_golden_family.py).  Every other block of ``QuaternionSkipConnectAdd/Concat``
 (phc/quaternion/undirectional/models.py:25-448) has the same arithmetic as its PHM counterpart at n = 4: the component-wise
-batch norm (quaternion/norm.py:268-287), split activations and dropout, the GINE-style convolutions
+batch norm (quaternion/norm.py:279-300), split activations and dropout, the GINE-style convolutions
 (quaternion/undirectional/messagepassing.py), soft-attention / sum pooling (quaternion/pooling.py) and the downstream
 network with its real transform (quaternion/downstream.py).  So the family is a thin subclass of the PHM models: n = 4,
 ``learn_phm=False``, the Hamilton rule, ``sc_type="first"``, the reference's constructor signature and initialisers —
@@ -14,7 +14,7 @@ and the tcgen05 PHMLinear, fused aggregation and batch-norm kernels run it uncha
 Model construction draws its weights from the reference's distributions but not with its RNG sequence (the reference
 re-initialises every module several times while building; only the stand-alone initialisers are seed-compatible).
 
-Not covered: ``norm="q-batch-norm"`` (4x4 whitening with a Cholesky factor per feature, quaternion/norm.py:86-200) has no PHM
+Not covered: ``norm="q-batch-norm"`` (4x4 whitening with a Cholesky factor per feature, quaternion/norm.py:104-276) has no PHM
 counterpart and no kernel here; it raises at construction.
 """
 from __future__ import annotations
@@ -34,7 +34,7 @@ _INITS = ("glorot-normal", "glorot-uniform", "quaternion", "orthogonal")
 
 # ------------------------------------------------------------------------------------------------- initialisers
 def quaternion_init(in_features: int, out_features: int, criterion: str = "glorot", low: float = 0, high: float = 1) -> torch.Tensor:
-    """[4, in, out] polar initialisation — reference phc/quaternion/inits.py:40-83: chi(4)-distributed modulus, a random
+    """[4, in, out] polar initialisation — reference phc/quaternion/inits.py:40-76: chi(4)-distributed modulus, a random
     unit imaginary axis, uniform phase, and the reference's extra cos^2 weighting of the three imaginary parts.  RNG
     streams are drawn in the reference's order (scipy chi, torch uniform x3, numpy uniform x4)."""
     from scipy.stats import chi
@@ -76,7 +76,7 @@ def _qconj(a: torch.Tensor) -> torch.Tensor:
 
 def quaternion_orthogonal_init(in_features: int, out_features: int, scale: float = 1.0) -> torch.Tensor:
     """[4, in, out] weight whose quaternion matrix has orthonormal columns (rows when it is wide) — the property the
-    reference gets from a quaternion Householder QR of a Gaussian matrix (phc/quaternion/inits.py:86-113, qr.py:65-108; its
+    reference gets from a quaternion Householder QR of a Gaussian matrix (phc/quaternion/inits.py:79-113, qr.py:65-108; its
     ``Q /= 2`` undoes the factor 2 its QR carries, cf. phc/quaternion/tests/test_quat_qr.py:17-26, so the result has UNIT
     columns — checked against the reference: same column / row norms and element std).  Here: modified Gram-Schmidt in
     quaternion arithmetic (fp64) on the tall orientation; the two constructions agree up to a unit-quaternion phase per
@@ -98,7 +98,7 @@ def quaternion_orthogonal_init(in_features: int, out_features: int, scale: float
 
 @torch.no_grad()
 def init_quaternion_linear(lin: PHMLinear, init: str) -> None:
-    """``QLinear.reset_parameters`` (reference quaternion/layers.py:76-106) on a PHM-layout layer: weight by ``init``,
+    """``QLinear.reset_parameters`` (reference quaternion/layers.py:76-107) on a PHM-layout layer: weight by ``init``,
     bias 0 for the real part and 0.2 for the imaginary parts, rule = Hamilton."""
     assert lin.phm_dim == 4
     k, p = lin._in_feats_per_axis, lin._out_feats_per_axis
@@ -126,7 +126,7 @@ class _QuaternionMixin(object):
         assert init in _INITS, f"init variable '{init}' wrong."
         for nm in (norm_mp, norm_dn):
             if nm == "q-batch-norm":
-                raise NotImplementedError("norm 'q-batch-norm' (4x4 whitening, reference quaternion/norm.py:86-200) is not "
+                raise NotImplementedError("norm 'q-batch-norm' (4x4 whitening, reference quaternion/norm.py:104-276) is not "
                                           "implemented on the B200 path; use 'naive-batch-norm'")
             assert nm in ["None", None, "naive-batch-norm"]
         for d in [atom_encoded_dim] + list(mp_layers) + list(downstream_layers):
@@ -187,10 +187,10 @@ class QuaternionSkipConnectAdd(_QuaternionMixin, PHMSkipConnectAdd):
 
 
 class QuaternionSkipConnectConcat(_QuaternionMixin, PHMSkipConnectConcat):
-    """reference phc/quaternion/undirectional/models.py:233-448, on the PHM kernels (n = 4, Hamilton rule)."""
+    """reference phc/quaternion/undirectional/models.py:234-448, on the PHM kernels (n = 4, Hamilton rule)."""
 
     def _skip_concat(self, z: torch.Tensor, skip: torch.Tensor) -> torch.Tensor:
-        """``qcat([q, atom_encoded], dim=-1)`` (reference models.py:381, algebra.py cat): every component's block becomes
+        """``qcat([q, atom_encoded], dim=-1)`` (reference phc/quaternion/undirectional/models.py:407, algebra.py cat): every component's block becomes
         [z_c | skip_c] — in the flat layout that is the component-aware ``phm_cat``, not a flat concat."""
         return phm_cat([z, skip], 4)
 
@@ -219,8 +219,8 @@ class QuaternionSkipConnectConcat(_QuaternionMixin, PHMSkipConnectConcat):
 # ------------------------------------------------------------------------------------------------- regulariser
 def quaternion_weights(model) -> list:
     """The [4, in, out] weight stacks ``quaternion_weight_regularization`` sums over, in the reference's order
-    (phc/quaternion/regularization.py:40-88): message-passing transforms, the soft-attention pooling layer — for which
-    the reference stacks ``W_r, W_i, W_k, W_k`` (its line 77 repeats W_k and drops W_j; reproduced) — and the downstream
+    (phc/quaternion/regularization.py:27-97): message-passing transforms, the soft-attention pooling layer — for which
+    the reference stacks ``W_r, W_i, W_k, W_k`` (its line 81 repeats W_k and drops W_j; reproduced) — and the downstream
     affine layers."""
     root = getattr(model, "module", model)
     ws = []
