@@ -77,7 +77,7 @@ def _qconj(a: torch.Tensor) -> torch.Tensor:
 def quaternion_orthogonal_init(in_features: int, out_features: int, scale: float = 1.0) -> torch.Tensor:
     """[4, in, out] weight whose quaternion matrix has orthonormal columns (rows when it is wide) — the property the
     reference gets from a quaternion Householder QR of a Gaussian matrix (phc/quaternion/inits.py:79-113, qr.py:65-108; its
-    ``Q /= 2`` undoes the factor 2 its QR carries, cf. phc/quaternion/tests/test_quat_qr.py:17-26, so the result has UNIT
+    ``Q /= 2`` undoes the factor 2 its QR carries, cf. phc/quaternion/tests/test_quat_qr.py:16-25, so the result has UNIT
     columns — checked against the reference: same column / row norms and element std).  Here: modified Gram-Schmidt in
     quaternion arithmetic (fp64) on the tall orientation; the two constructions agree up to a unit-quaternion phase per
     column, which the Gaussian draw makes immaterial."""
