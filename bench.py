@@ -55,6 +55,48 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def tensor_peak():
+    """Dense bf16 TFLOP/s the driver measured on this pool (sustained figure: the kernels are timed inside a long step)."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        v = d.get("bf16_tflops_sustained") or d.get("bf16_tflops")
+        if v:
+            return float(v), "measured (MEASURED_PEAKS.json, sustained)"
+    return 2250.0, "nominal dense bf16 (B200_PROFILING.md)"
+
+
+def phm_linear_roofline(prof, steps, wl, N, precision):
+    """Tensor-core side of the step (the PHMLinear kernels, the largest share of it): algorithmic FLOPs of the node-level
+    linears (2*M*in*out forward, 4*M*in*out backward; head layers at M = batch are negligible and not counted)
+    over their CUDA-event time in the instrumented repeat.  Never raises: returns None when the entries are missing."""
+    try:
+        cf, tf = prof.get("phc_phm_linear_fwd", (0, 0.0))
+        cb, tb = prof.get("phc_phm_linear_bwd", (0, 0.0))
+        if not cf or not cb or tf <= 0 or tb <= 0:
+            return None
+        m = wl.model
+        F = m["mp_layers"][0]
+        n_lin = len(m["mp_layers"]) * (2 if m["mlp"] else 1) + (1 if m["pooling"] == "softattention" else 0)
+        unit = 2.0 * N * F * F
+        fwd_tf = n_lin * unit / (tf / steps * 1e-3) / 1e12
+        bwd_tf = n_lin * 2.0 * unit / (tb / steps * 1e-3) / 1e12
+        ach = 3.0 * n_lin * unit / ((tf + tb) / steps * 1e-3) / 1e12
+        peak, src = tensor_peak()
+        # tf32x3: every fp32 product is three tf32 MMAs, and tf32 runs at half the bf16 rate -> fp32-equivalent ceiling = peak / 6
+        ceiling = peak / 6.0 if precision == "tf32x3" else (peak if precision == "bf16" else None)
+        return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "peak_source": src,
+                "kernels": "phm_linear mix (fwd, dX) + dH + contraction kernels; fp32-equivalent algorithmic FLOPs",
+                "fwd_tflops": fwd_tf, "bwd_tflops": bwd_tf, "node_level_linears": n_lin,
+                "algorithmic_flops_per_step": 3.0 * n_lin * unit,
+                "precision_ceiling_tflops": ceiling, "frac_of_precision_ceiling": (ach / ceiling) if ceiling else None,
+                "timed": "CUDA events around each C-ABI call, instrumented repeat of the K steps (head-level calls included in "
+                         "the time, not in the FLOPs)"}
+    except Exception:
+        return None
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons with NVML while the timed region runs."""
 
@@ -441,7 +483,9 @@ def run_b200(args):
                    os.environ.get("PHC_PRECISION", "tf32x3")],
                "data": "synthetic",
                "config": config_dict(args, wl, wl.batch_graphs, "flushed between steps" if flush else "inputs larger than L2"),
-               "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "ms_per_step_instrumented": ms_instr / args.steps,
+               "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof,
+               "roofline_phm_linear": phm_linear_roofline(prof, args.steps, wl, N, os.environ.get("PHC_PRECISION", "tf32x3")),
+               "ms_per_step_instrumented": ms_instr / args.steps,
                "op_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in breakdown.items()},
                "final_loss": float(loss.item())}
         if world == 1 and not args.no_cpu_baseline:

@@ -29,3 +29,23 @@ def test_other_ranks_of_the_reference_arm_exit_silently():
                            "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert proc.returncode == 0, proc.stderr[-2000:]
     assert proc.stdout.strip() == ""
+
+
+def test_tensor_roofline_arithmetic():
+    """roofline_phm_linear: algorithmic FLOPs of the node-level linears over their measured time (pure host arithmetic)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from phc_gnn_b200.synthetic import workloads
+    wl = workloads(4)["ppa"]                                   # 7 layers x 2 MLP linears + the pooling linear = 15, F = 500
+    steps, N = 4, 10000
+    unit = 2.0 * N * 500 * 500
+    prof = {"phc_phm_linear_fwd": (15 * steps, 1.0 * steps), "phc_phm_linear_bwd": (15 * steps, 2.0 * steps)}   # 1 ms fwd, 2 ms bwd per step
+    r = bench.phm_linear_roofline(prof, steps, wl, N, "tf32x3")
+    assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and r["node_level_linears"] == 15
+    assert abs(r["fwd_tflops"] - 15 * unit / 1e-3 / 1e12) < 1e-9 and abs(r["bwd_tflops"] - 15 * 2 * unit / 2e-3 / 1e12) < 1e-9
+    assert abs(r["achieved"] - 15 * 3 * unit / 3e-3 / 1e12) < 1e-9 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert abs(r["precision_ceiling_tflops"] - r["peak"] / 6) < 1e-9
+    assert bench.phm_linear_roofline({}, steps, wl, N, "tf32x3") is None
+    assert bench.phm_linear_roofline(prof, steps, wl, N, "fp32")["frac_of_precision_ceiling"] is None
