@@ -260,11 +260,28 @@ def init_fixture(outdir):
     print("inits_quaternion.pt:", {k: tuple(v.shape) for k, v in fx.items()})
 
 
+INIT_MODEL_KW = dict(phm_dim=4, atom_encoded_dim=16, mp_layers=[16, 16], dropout_mpnn=[0.0, 0.0], downstream_layers=[12, 8], mlp=True,
+                     msg_aggr="softmax", initial_beta=1.0, learn_beta=True)
+
+
+def init_state_fixture(outdir):
+    """Initial state dict of a freshly constructed reference model under fixed seeds (numpy + torch): what
+    ``reset_parameters`` draws — phm_init (scipy chi, torch uniform, numpy phase), embedding / linear initialisers, rules."""
+    from phc.hypercomplex.undirectional.models import PHMSkipConnectAdd
+    np.random.seed(3)
+    torch.manual_seed(3)
+    m = PHMSkipConnectAdd(**INIT_MODEL_KW)
+    torch.save(dict(kw=INIT_MODEL_KW, seed=3, state={k: v.clone() for k, v in m.state_dict().items()}),
+               os.path.join(outdir, "inits_phm_model.pt"))
+    print("inits_phm_model.pt:", len(m.state_dict()), "tensors")
+
+
 def main():
     outdir = os.path.join(ROOT, "tests", "golden", "family")
     os.makedirs(outdir, exist_ok=True)
     legacy_fixture(outdir)
     init_fixture(outdir)
+    init_state_fixture(outdir)
     quaternion_fixtures(outdir)
     phm_option_fixtures(outdir)
 

@@ -296,3 +296,26 @@ def test_quaternion_initialisers_against_reference_known_answers():
         torch.testing.assert_close(want, torch.eye(want.size(0), dtype=torch.float64), rtol=0, atol=1e-5)   # the reference's property
         torch.testing.assert_close(gram, torch.eye(gram.size(0), dtype=torch.float64), rtol=0, atol=1e-5)   # ... and ours
         assert abs(float(w.std()) - float(fx[f"orthogonal_{fin}_{fout}_std"])) < 0.02
+
+
+def test_model_initialisation_reproduces_the_reference_under_the_same_seeds():
+    """A freshly constructed PHM model draws the reference's initial weights (same RNG streams in the same order) — except
+    element ``b[out/n]`` of every PHMLinear bias, which the reference leaves uninitialised (0.2 here)."""
+    import numpy as np
+    from phc.hypercomplex.undirectional.models import PHMSkipConnectAdd
+    fx = torch.load(os.path.join(FAMILY, "inits_phm_model.pt"), weights_only=False)
+    np.random.seed(fx["seed"])
+    torch.manual_seed(fx["seed"])
+    m = PHMSkipConnectAdd(**fx["kw"])
+    got = m.state_dict()
+    assert set(got) == set(fx["state"])                      # registration order differs, names do not
+    for k, want in fx["state"].items():
+        g = got[k]
+        if k.endswith(".b"):
+            p = g.numel() // fx["kw"]["phm_dim"]
+            keep = torch.ones_like(g, dtype=torch.bool)
+            keep[p] = False
+            assert torch.equal(g[keep], want[keep]), k
+            assert float(g[p]) == pytest.approx(0.2)
+        else:
+            assert torch.equal(g, want), k
