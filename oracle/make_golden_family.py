@@ -104,7 +104,9 @@ def legacy_fixture(outdir):
         old = PHMLinear_Old(fin, fout, n, c_init="standard")
         with torch.no_grad():
             for a in old.phm_rule:
-                a.add_(0.2 * torch.randn(a.shape, generator=g))
+                # rebind, never write in place: PHMLinear_Old's rule parameters share storage with the reference's module-level
+                # rule tables (utils.py), and an in-place update would corrupt them for everything generated afterwards
+                a.data = a.data + 0.2 * torch.randn(a.shape, generator=g)
             for w in old.W:
                 w.copy_(torch.randn(w.shape, generator=g))
             for b in old.b:
