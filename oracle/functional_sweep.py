@@ -107,3 +107,38 @@ def loss_fn(logits, y, kind, target_dim, task_loss):
 def grad_summary(named_grads) -> list:
     """[[L2 norm, sum], ...] of the gradients in the order of the sorted parameter names (names are not stored)."""
     return [[float(g.double().norm()), float(g.double().sum())] for _, g in sorted(named_grads, key=lambda kv: kv[0]) if g is not None]
+
+
+def quaternion_configurations(seed: int = 1, count: int = 48):
+    """[(tag, concat, workload, kwargs, batch_seed)] for QuaternionSkipConnectAdd / Concat (norm_mp / norm_dn stay on: the
+    reference's quaternion models raise without them)."""
+    rng = random.Random(seed)
+    out = []
+    for it in range(count):
+        wname = rng.choice(["hiv", "zinc", "mnist", "pcba", "ppa"])
+        concat = rng.random() < 0.4
+        width = 4 * rng.choice([1, 2, 3])
+        layers = rng.choice([1, 2, 3])
+        head = [4 * rng.choice([1, 2]) for _ in range(rng.choice([1, 2]))]
+        wl = tiny(workloads(4)[wname], width, layers, rng.choice([3, 5]), 3, 7, und_edges=8 if wname == "ppa" else None, head=head)
+        if wname == "mnist":
+            wl.extra["k"] = 2
+        kw = {k: v for k, v in wl.model.items() if k not in ("phm_dim", "learn_phm", "phm_rule", "w_init", "c_init", "sc_type")}
+        aggr = rng.choice(["sum", "mean", "max", "min", "softmax"])
+        kw.update(init="glorot-uniform", msg_aggr=aggr, mlp=rng.random() < 0.5, activation=rng.choice(ACTS),
+                  msg_encoder=rng.choice(["identity", "relu", "swish"]), pooling=rng.choice(["globalsum", "softattention"]),
+                  naive_encoder=rng.random() < 0.3, bias=rng.random() < 0.8)
+        if concat:
+            kw["mp_layers"] = [4 * rng.choice([1, 2, 3]) for _ in range(layers)]
+        if aggr == "softmax":
+            kw.update(initial_beta=rng.choice([0.5, 1.5]), learn_beta=rng.random() < 0.7)
+        kw["dropout_mpnn"] = [0.0] * layers
+        kw["dropout_dn"] = [0.0] * len(head)
+        if wname == "pcba":
+            kw["target_dim"] = 4
+        if wname == "ppa":
+            kw["target_dim"] = 5
+        tag = (f"q{it}:{'cat' if concat else 'add'} {wname} w{width} L{layers} {aggr} mlp{int(kw['mlp'])} {kw['activation']}/"
+               f"{kw['msg_encoder']} {kw['pooling']} naive{int(kw['naive_encoder'])} bias{int(kw['bias'])}")
+        out.append((tag, concat, wl, kw, 20_000 + it))
+    return out

@@ -25,7 +25,8 @@ sys.modules["phc"] = _ref_phc
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-from functional_sweep import batch_for, configurations, fill_by_name, grad_summary, loss_fn, model_kwargs  # noqa: E402
+from functional_sweep import (batch_for, configurations, fill_by_name, grad_summary, loss_fn, model_kwargs,  # noqa: E402
+                              quaternion_configurations)
 from make_golden import ref_loss  # noqa: E402
 
 
@@ -67,6 +68,36 @@ def main():
     with open(path, "w") as fh:
         json.dump(out, fh, separators=(",", ":"))
     print(len(out), "configurations ->", path, os.path.getsize(path) // 1024, "KiB")
+    quaternion_main()
+
+
+def quaternion_main():
+    """Same for the quaternion family (48 configurations of QuaternionSkipConnectAdd / Concat) -> functional_sweep_quaternion.json;
+    weights are filled under the reference's own parameter names."""
+    from phc.quaternion.undirectional.models import QuaternionSkipConnectAdd, QuaternionSkipConnectConcat
+    from phc.quaternion.regularization import quaternion_weight_regularization
+    out = {}
+    for it, (tag, concat, wl, kw, bseed) in enumerate(quaternion_configurations()):
+        torch.manual_seed(it)
+        np.random.seed(it)
+        model = (QuaternionSkipConnectConcat if concat else QuaternionSkipConnectAdd)(**kw)
+        fill_by_name(list(model.named_parameters()) + list(model.named_buffers()), 177 + it)
+        data = batch_for(wl, kw, bseed)
+        model.train()
+        logits = model(data)
+        reg = quaternion_weight_regularization(model, device="cpu", p=2)
+        loss = loss_fn(logits, data.y, wl.loss, kw["target_dim"], ref_loss) + 0.01 * reg
+        loss.backward()
+        grads = grad_summary((k, p.grad) for k, p in model.named_parameters())
+        model.eval()
+        with torch.no_grad():
+            ev = model(data)
+        out[tag] = _round(dict(logits=logits.detach().double().tolist(), loss=float(loss), reg=float(reg), grads=grads,
+                               logits_eval=ev.double().tolist()))
+    path = os.path.join(ROOT, "tests", "golden", "family", "functional_sweep_quaternion.json")
+    with open(path, "w") as fh:
+        json.dump(out, fh, separators=(",", ":"))
+    print(len(out), "quaternion configurations ->", path, os.path.getsize(path) // 1024, "KiB")
 
 
 if __name__ == "__main__":

@@ -55,8 +55,8 @@ def test_cuda_path_matches_reference_on_random_configuration(index, reference_ou
     assert len(got) == len(want["grads"]), tag
     gscale = max(1e-3, max(w[0] for w in want["grads"]))
     for (gn, gs), (wn, ws) in zip(got, want["grads"]):
-        assert abs(gn - wn) <= 2e-3 * max(wn, 1e-2 * gscale), f"{tag}: gradient norm {gn} vs {wn}"
-        assert abs(gs - ws) <= 2e-3 * max(abs(ws), wn, 1e-2 * gscale), f"{tag}: gradient sum {gs} vs {ws}"
+        assert abs(gn - wn) <= 2e-3 * max(wn, 1e-1 * gscale), f"{tag}: gradient norm {gn} vs {wn}"
+        assert abs(gs - ws) <= 2e-3 * max(abs(ws), wn, 1e-1 * gscale), f"{tag}: gradient sum {gs} vs {ws}"
     model.eval()
     with torch.no_grad():
         ev = model(data).cpu().double()
