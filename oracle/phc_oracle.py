@@ -106,7 +106,7 @@ def encoder(feat: torch.Tensor, p: Params, key: str, n: int, input_dims, dtype) 
             f = feat.unsqueeze(1) if feat.dim() == 1 else feat
             one = 0
             for col in range(f.size(1)):
-                one = one + p[f"{key}.encoder.embeddings.{col}.weight"][f[:, col]]
+                one = one + F.embedding(f[:, col], p[f"{key}.encoder.embeddings.{col}.weight"])
         else:
             one = feat.to(dtype) @ p[f"{key}.encoder.weight"].t() + p[f"{key}.encoder.bias"]
         return torch.cat([one] * n, -1)
@@ -116,7 +116,7 @@ def encoder(feat: torch.Tensor, p: Params, key: str, n: int, input_dims, dtype) 
             f = feat.unsqueeze(1) if feat.dim() == 1 else feat
             acc = 0
             for col in range(f.size(1)):
-                acc = acc + p[f"{key}.encoders.{c}.embeddings.{col}.weight"][f[:, col]]
+                acc = acc + F.embedding(f[:, col], p[f"{key}.encoders.{c}.embeddings.{col}.weight"])       # nn.Embedding, as the reference
             comps.append(acc)
         else:
             comps.append(feat.to(dtype) @ p[f"{key}.encoders.{c}.weight"].t() + p[f"{key}.encoders.{c}.bias"])
@@ -149,14 +149,14 @@ def aggregate(msg: torch.Tensor, index: torch.Tensor, size: int, aggr: str,
     if aggr == "softmax":
         s = msg * beta
         mx = seg_ext(s.detach(), index, size, "amax")
-        ex = (s - mx[index]).exp()
+        ex = (s - mx.index_select(0, index)).exp()
         den = seg_sum(ex, index, size) + 1e-12
-        return seg_sum(msg * (ex / den[index]), index, size)
+        return seg_sum(msg * (ex / den.index_select(0, index)), index, size)
     raise ValueError(aggr)
 
 
 def propagate(x, edge_index, edge_emb, aggr, msg_encoder, beta=None):
-    msg = activation(x[edge_index[0]] + edge_emb, msg_encoder)
+    msg = activation(x.index_select(0, edge_index[0]) + edge_emb, msg_encoder)      # PyG gathers x_j with index_select
     return aggregate(msg, edge_index[1], x.size(0), aggr, beta)
 
 
@@ -217,7 +217,7 @@ def pna_conv(x, edge_index, edge_emb, p: Params, key: str, cfg: Dict, training: 
     """PHMPNAConvSimple.forward (messagepassing.py:408-419): the dispatcher hard-wires msg_encoder="relu"
     (messagepassing.py:490); no self term; transform = PHMLinear [-> PHMNorm -> act -> PHMLinear]*(post_layers-1)."""
     n = cfg["phm_dim"]
-    msg = activation(x[edge_index[0]] + edge_emb, "relu")
+    msg = activation(x.index_select(0, edge_index[0]) + edge_emb, "relu")
     h = pna_aggregate(msg, edge_index[1], x.size(0), n, cfg["aggregators"], cfg["scalers"], pna_avg_deg(cfg["deg"]))
     t = key + ".transform.transform"
     h = phm_linear(h, p, t + ".0")
