@@ -144,39 +144,130 @@ def workload(args):
     return workloads(args.phm_dim)[args.workload]
 
 
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def reference_available():
+    return os.path.exists(os.path.join(REF_DIR, "phc", "hypercomplex", "undirectional", "models.py"))
+
+
+def _import_reference():
+    """The UNMODIFIED reference package installed by baseline/install_ref.sh (byte-identical to /root/reference/phc),
+    imported under its own name ``phc`` with oracle/refshim standing in for torch_scatter / torch_geometric / ogb
+    (not installable offline).  The product's drop-in ``phc`` package at the repo root must not shadow it: the name is
+    pinned to baseline/_ref/phc before anything is imported, and the origin of the model module is asserted."""
+    import types
+    import warnings
+    warnings.filterwarnings("ignore")
+    for k in [k for k in sys.modules if k == "phc" or k.startswith("phc.")]:
+        del sys.modules[k]
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "refshim"))
+    pkg = types.ModuleType("phc")
+    pkg.__path__ = [os.path.join(REF_DIR, "phc")]
+    sys.modules["phc"] = pkg
+    import phc.hypercomplex.undirectional.models as ref_models
+    from phc.hypercomplex.regularization import phm_weight_regularization as ref_reg
+    assert os.path.realpath(ref_models.__file__).startswith(os.path.realpath(REF_DIR)), ref_models.__file__
+    return ref_models.PHMSkipConnectAdd, ref_reg
+
+
+class _ReferenceStepper(object):
+    """One iteration of the reference's train() body (benchmarks/train_hiv.py:170-202) on its own model class,
+    torch.optim.Adam and clip_grad_norm_, on the host cores.  kind = "reference" when baseline/_ref is present,
+    else the oracle port ("port")."""
+
+    def __init__(self, wl):
+        import torch.nn.functional as F
+        self.wl, self.F = wl, F
+        torch.manual_seed(0)
+        if reference_available():
+            Model, self.reg = _import_reference()
+            self.kind = "reference"
+            self.model = Model(**wl.model)
+            with torch.no_grad():      # the reference leaves one bias element uninitialised (SURVEY D8): define it
+                for n_, p_ in self.model.named_parameters():
+                    if not torch.isfinite(p_).all():
+                        p_.copy_(torch.nan_to_num(p_, nan=0.2, posinf=0.2, neginf=0.2))
+            self.model.train()
+            self.opt = torch.optim.Adam(self.model.parameters(), lr=wl.lr)
+            self.params = list(self.model.parameters())
+        else:
+            from oracle import phc_oracle as O
+            from phc_gnn_b200.nn import PHMSkipConnectAdd
+            self.kind, self.O = "port", O
+            state = PHMSkipConnectAdd(**wl.model).state_dict()
+            self.p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+                      for k, v in state.items()}
+            self.opt = torch.optim.Adam(O.trainable(self.p), lr=wl.lr)
+            self.gen = torch.Generator().manual_seed(0)
+
+    def step(self, data):
+        wl, F = self.wl, self.F
+        if self.kind == "port":
+            return float(self.O.train_step(self.p, wl.model, data, wl.loss, self.opt, wl.lr, wl.weight_decay, wl.grad_clip, self.gen))
+        self.opt.zero_grad()
+        logits = self.model(data)
+        if wl.loss in ("bce", "bce_masked"):
+            mask = ~torch.isnan(data.y)
+            loss = F.binary_cross_entropy_with_logits(input=logits[mask], target=data.y[mask].to(torch.float))
+        elif wl.loss == "l1":
+            loss = (logits.squeeze() - data.y).abs().mean()
+        else:
+            loss = F.cross_entropy(logits, data.y.view(-1))
+        if wl.weight_decay > 0.0:
+            loss = loss + wl.lr * wl.weight_decay * self.reg(self.model, p=2).squeeze()
+        loss.backward()
+        if wl.grad_clip > 0.0:
+            torch.nn.utils.clip_grad_norm_(self.params, max_norm=wl.grad_clip, norm_type=2)
+        self.opt.step()
+        return float(loss.item())
+
+    def describe(self):
+        return ("the unmodified reference (baseline/_ref, PHMSkipConnectAdd + torch.optim.Adam + clip_grad_norm_) over oracle/refshim"
+                if self.kind == "reference" else "oracle/phc_oracle.py (port of the reference; baseline/_ref not installed)")
+
+
 def run_reference(args):
-    """CPU arm: the oracle port of the reference on the host cores, bounded sample per step."""
+    """CPU arm: the reference's own implementation of the path on the host cores, at the SAME per-GPU batch as the b200
+    arm (one step = one full mini-batch), all host threads; the reference scripts' own setting (6 threads,
+    benchmarks/train_hiv.py:632) is timed on a few extra steps and reported next to it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import phc_oracle as O
     from phc_gnn_b200.synthetic import make_batch
-    from phc_gnn_b200.nn import PHMSkipConnectAdd
     wl = workload(args)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sample_graphs = max(2, wl.batch_graphs // 8) if wl.name in ("ppa", "pcba", "cifar") else wl.batch_graphs
-    torch.manual_seed(0)
-    state = PHMSkipConnectAdd(**wl.model).state_dict()
-    p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in state.items()}
-    opt = torch.optim.Adam(O.trainable(p), lr=wl.lr)
-    batches = [make_batch(wl, seed=i, batch_graphs=sample_graphs) for i in range(min(args.batches, 4))]
-    g = torch.Generator().manual_seed(0)
+    ref = _ReferenceStepper(wl)
+    batches = [make_batch(wl, seed=i) for i in range(min(args.batches, 4))]
     for i in range(args.warmup):
-        O.train_step(p, wl.model, batches[i % len(batches)], wl.loss, opt, wl.lr, wl.weight_decay, wl.grad_clip, g)
+        ref.step(batches[i % len(batches)])
     t0 = time.perf_counter()
     for i in range(args.steps):
-        O.train_step(p, wl.model, batches[i % len(batches)], wl.loss, opt, wl.lr, wl.weight_decay, wl.grad_clip, g)
+        loss = ref.step(batches[(args.warmup + i) % len(batches)])
     dt = time.perf_counter() - t0
-    val = sample_graphs * args.steps / dt
-    sample = f"{sample_graphs} graphs/step x {args.steps} steps of the {wl.name}-shaped workload (full per-GPU batch is {wl.batch_graphs})"
+    val = wl.batch_graphs * args.steps / dt
+    six = None
+    if cores > 6:
+        torch.set_num_threads(6)
+        k6 = max(2, min(args.steps, 5))
+        ref.step(batches[0])
+        t6 = time.perf_counter()
+        for i in range(k6):
+            ref.step(batches[i % len(batches)])
+        d6 = time.perf_counter() - t6
+        six = {"value": wl.batch_graphs * k6 / d6, "unit": UNIT, "cores": 6, "steps": k6,
+               "why": "torch.set_num_threads(6) is what the reference scripts run with (benchmarks/train_hiv.py:632)"}
+    sample = (f"{args.steps} steps x {wl.batch_graphs} graphs (the full per-GPU batch) of the {wl.name}-shaped workload, "
+              f"{ref.describe()}, torch CPU, {cores} threads, {dt:.1f} s")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": config_dict(args, wl, sample_graphs, "cpu"),
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), file=JSON_OUT, flush=True)
+        "config": config_dict(args, wl, wl.batch_graphs, "cpu"),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": ref.kind, "sample": sample, "six_threads": six},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "final_loss": loss}), file=JSON_OUT, flush=True)
 
 
 def config_dict(args, wl, graphs_per_gpu, l2):
@@ -188,30 +279,30 @@ def config_dict(args, wl, graphs_per_gpu, l2):
             **({"family": "quaternion"} if getattr(args, "family", "phm") == "quaternion" else {})}
 
 
-def cpu_baseline(wl, budget_s: float = 25.0):
-    """Oracle port timed on the host cores for a bounded sample (rank 0, N=1 only)."""
-    from oracle import phc_oracle as O
+def cpu_baseline(wl, budget_s: float = 20.0):
+    """The reference's CPU implementation (baseline/_ref; else the oracle port) timed on the host cores for a bounded
+    sample of the same workload at the same per-GPU batch (rank 0, N=1 only)."""
     from phc_gnn_b200.synthetic import make_batch
-    from phc_gnn_b200.nn import PHMSkipConnectAdd
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sample_graphs = max(2, wl.batch_graphs // 8) if wl.name in ("ppa", "pcba", "cifar") else wl.batch_graphs
-    torch.manual_seed(0)
-    state = PHMSkipConnectAdd(**wl.model).state_dict()
-    p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in state.items()}
-    opt = torch.optim.Adam(O.trainable(p), lr=wl.lr)
-    batch = make_batch(wl, seed=0, batch_graphs=sample_graphs)
-    g = torch.Generator().manual_seed(0)
-    O.train_step(p, wl.model, batch, wl.loss, opt, wl.lr, wl.weight_decay, wl.grad_clip, g)      # warm-up
-    t0 = time.perf_counter()
-    steps = 0
-    while steps < 2 or (time.perf_counter() - t0 < budget_s and steps < 50):
-        O.train_step(p, wl.model, batch, wl.loss, opt, wl.lr, wl.weight_decay, wl.grad_clip, g)
-        steps += 1
-    dt = time.perf_counter() - t0
-    return {"value": sample_graphs * steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{steps} steps x {sample_graphs} graphs of the same {wl.name}-shaped workload, oracle/phc_oracle.py "
-                      f"(torch CPU, {cores} threads), {dt:.1f} s"}
+    saved = {k: v for k, v in sys.modules.items() if k == "phc" or k.startswith("phc.")}
+    try:
+        ref = _ReferenceStepper(wl)
+        batch = make_batch(wl, seed=0)
+        ref.step(batch)      # warm-up
+        t0 = time.perf_counter()
+        steps = 0
+        while steps < 2 or (time.perf_counter() - t0 < budget_s and steps < 50):
+            ref.step(batch)
+            steps += 1
+        dt = time.perf_counter() - t0
+    finally:             # give the name ``phc`` back to the product's drop-in package
+        for k in [k for k in sys.modules if k == "phc" or k.startswith("phc.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+    return {"value": wl.batch_graphs * steps / dt, "unit": UNIT, "cores": cores, "kind": ref.kind,
+            "sample": f"{steps} steps x {wl.batch_graphs} graphs (the full per-GPU batch) of the same {wl.name}-shaped workload, "
+                      f"{ref.describe()}, torch CPU, {cores} threads, {dt:.1f} s"}
 
 
 # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the aggregation forward kernel from the

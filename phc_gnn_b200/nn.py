@@ -260,8 +260,8 @@ class RealTransformer(nn.Module):
         assert type in ["linear", "sum", "mean", "norm"]
         self.type, self.in_features, self.phm_dim, self.bias_flag = type, in_features, phm_dim, bias
         self.affine = nn.Linear(in_features, in_features // phm_dim, bias=bias) if type == "linear" else None
-        self.register_buffer("_one", torch.ones(1, 1, 1), persistent=False)
-        self.reset_parameters()
+        self._unit_rule = None          # [1,1,1] ones on the weight's device, created on first use (NOT a buffer: the
+        self.reset_parameters()         # reference module has none, and named_buffers() must list the same tensors)
 
     def reset_parameters(self):
         if self.type == "linear":
@@ -272,7 +272,9 @@ class RealTransformer(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if self.type == "linear":
             w = self.affine.weight.t().contiguous().unsqueeze(0)       # [1, in, out]
-            return ops.phm_linear(x, self._one, w, self.affine.bias)
+            if self._unit_rule is None or self._unit_rule.device != w.device:
+                self._unit_rule = torch.ones(1, 1, 1, device=w.device)
+            return ops.phm_linear(x, self._unit_rule, w, self.affine.bias)
         if self.type == "norm":
             return x.abs()
         return x

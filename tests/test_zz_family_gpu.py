@@ -145,8 +145,6 @@ def test_quaternion_train_steps(monkeypatch):
             assert torch.equal(r.detach().cpu(), legacy.hamilton_rule())
 
 
-@pytest.mark.skipif(__import__("os").environ.get("PHC_GPU_SWEEP") != "1",
-                    reason="written after the round's GPU budget was spent, not yet verified on a GPU: set PHC_GPU_SWEEP=1 to run")
 @pytest.mark.parametrize("fuse", ["direct", "none"], ids=["one-call-per-layer", "separate-ops"])
 @pytest.mark.parametrize("name", __import__("test_family_host").phm_option_cases())
 def test_phm_constructor_options_match_reference_golden(name, fuse, monkeypatch):

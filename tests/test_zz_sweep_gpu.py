@@ -1,8 +1,9 @@
 """The CUDA path against the reference on the 120 random configurations of oracle/functional_sweep.py (fixture:
-tests/golden/family/functional_sweep.json).  Opt-in (``PHC_GPU_SWEEP=1``): it was written after the round's GPU budget was
-spent and has NOT run on a GPU yet, so it is skipped by default rather than risk an unverified red in the suite;
-``PHC_GPU_SWEEP=1 python -m pytest tests/test_zz_sweep_gpu.py -m gpu`` is the first thing to do with the next GPU minutes,
-after which the switch goes away."""
+tests/golden/family/functional_sweep.json, recorded from the unmodified reference).
+
+Gradients that are ill-conditioned in fp32 (PNA's ``std`` aggregator: sqrt(relu(var) + eps) where var is rounding noise
+around 0, so relu' flips with the sign of the noise) are judged by the rule DESIGN.md section 2 states: the fp64 oracle is the
+truth, and the CUDA value may be as far from it as 10x the distance of the reference's own fp32 value."""
 import json
 import os
 import sys
@@ -16,8 +17,7 @@ from oracle import phc_oracle as O
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 from functional_sweep import batch_for, configurations, fill_by_name, grad_summary, loss_fn, model_kwargs  # noqa: E402
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("PHC_GPU_SWEEP") != "1", reason="not yet verified on a GPU: set PHC_GPU_SWEEP=1 to run")]
+pytestmark = [pytest.mark.gpu]
 DEV = "cuda:0"
 CONFIGS = configurations()
 
@@ -26,6 +26,34 @@ CONFIGS = configurations()
 def reference_outputs():
     with open(os.path.join(golden_dir(), "family", "functional_sweep.json")) as fh:
         return json.load(fh)
+
+
+def _fp64_oracle_grad_summary(index):
+    """[[norm, sum], ...] of the fp64 oracle's gradients on configuration ``index`` (same fill, same batch)."""
+    from phc.hypercomplex.undirectional.models import PHMSkipConnectAdd
+    tag, wl, kw, bseed = CONFIGS[index]
+    torch.manual_seed(index)
+    model = PHMSkipConnectAdd(**model_kwargs(kw))
+    fill_by_name(list(model.named_parameters()) + list(model.named_buffers()), 77 + index)
+    trainable = {k for k, p in model.named_parameters() if p.requires_grad}
+    p = {}
+    for k, v in model.state_dict().items():
+        v = v.detach().clone()
+        if v.is_floating_point():
+            v = v.double()
+        if k in trainable:
+            v.requires_grad_(True)
+        p[k] = v
+    data = batch_for(wl, kw, bseed)
+    for name in ("x", "edge_attr"):
+        t = getattr(data, name)
+        if t.is_floating_point():
+            setattr(data, name, t.double())
+    kk = kw | {"deg": model_kwargs(kw).get("deg")} if "deg" in kw else kw
+    logits = O.model_forward(p, kk, data, training=True)
+    loss = loss_fn(logits, data.y, wl.loss, kw["target_dim"], O.task_loss) + 0.01 * O.weight_regularization(p, 2)
+    loss.backward()
+    return grad_summary((k, p[k].grad) for k in sorted(trainable))
 
 
 @pytest.mark.parametrize("index", range(len(CONFIGS)))
@@ -54,9 +82,16 @@ def test_cuda_path_matches_reference_on_random_configuration(index, reference_ou
     got = grad_summary((k, p.grad.detach().cpu()) for k, p in model.named_parameters() if p.requires_grad)
     assert len(got) == len(want["grads"]), tag
     gscale = max(1e-3, max(w[0] for w in want["grads"]))
-    for (gn, gs), (wn, ws) in zip(got, want["grads"]):
-        assert abs(gn - wn) <= 2e-3 * max(wn, 1e-1 * gscale), f"{tag}: gradient norm {gn} vs {wn}"
-        assert abs(gs - ws) <= 2e-3 * max(abs(ws), wn, 1e-1 * gscale), f"{tag}: gradient sum {gs} vs {ws}"
+    truth = None
+    for j, ((gn, gs), (wn, ws)) in enumerate(zip(got, want["grads"])):
+        ok = abs(gn - wn) <= 2e-3 * max(wn, 1e-1 * gscale) and abs(gs - ws) <= 2e-3 * max(abs(ws), wn, 1e-1 * gscale)
+        if ok:
+            continue
+        if truth is None:
+            truth = _fp64_oracle_grad_summary(index)
+        tn, ts = truth[j]
+        assert abs(gn - tn) <= max(10 * abs(wn - tn), 2e-3 * max(tn, 1e-1 * gscale)), f"{tag}: gradient norm {gn} vs fp32 {wn} / fp64 {tn}"
+        assert abs(gs - ts) <= max(10 * abs(ws - ts), 2e-3 * max(abs(ts), tn, 1e-1 * gscale)), f"{tag}: gradient sum {gs} vs fp32 {ws} / fp64 {ts}"
     model.eval()
     with torch.no_grad():
         ev = model(data).cpu().double()
