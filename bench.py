@@ -23,6 +23,8 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
+DEFAULT_PRECISION = "tf32x3"      # what phc_gnn_b200.ops.default_precision() resolves to when PHC_PRECISION is unset
+
 JSON_OUT = sys.stdout
 METRIC = "train_graphs_per_sec"
 UNIT = "graphs/s"
@@ -67,32 +69,57 @@ def tensor_peak():
     return 2250.0, "nominal dense bf16 (B200_PROFILING.md)"
 
 
-def phm_linear_roofline(prof, steps, wl, N, precision):
-    """Tensor-core side of the step (the PHMLinear kernels, the largest share of it): algorithmic FLOPs of the node-level
-    linears (2*M*in*out forward, 4*M*in*out backward; head layers at M = batch are negligible and not counted)
-    over their CUDA-event time in the instrumented repeat.  Never raises: returns None when the entries are missing."""
+# tensor-core passes per fp32 product and the MMA rate relative to dense bf16, per precision mode
+PASSES = {"tf32x3": (3, 0.5), "bf16x3": (3, 1.0), "bf16": (1, 1.0)}
+
+
+def traffic_record(kernel):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of ``kernel`` from the committed ``ncu --set full``
+    capture named in profiles/traffic.json (one capture per kernel change; bench.py cannot run under ncu itself)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    with open(p) as fh:
+        d = json.load(fh).get(kernel)
+    return (d["bytes_per_launch"], d["source"]) if d else (None, None)
+
+
+def phm_linear_roofline(prof, steps, wl, N, precision, step_ms=None):
+    """The dominant kernels of the step: the node-level PHMLinear calls (tcgen05 mix kernel forward / dX, dH kernel).  achieved =
+    algorithmic FLOPs (2*M*in*out per forward launch, 4*M*in*out per backward call) / CUDA-event time of those calls in
+    the instrumented repeat; peak = the measured dense bf16 rate.  Head-level calls (M = graphs per batch) are timed under their own
+    key and excluded from both.  Never raises: returns None when the entries are missing."""
     try:
-        cf, tf = prof.get("phc_phm_linear_fwd", (0, 0.0))
-        cb, tb = prof.get("phc_phm_linear_bwd", (0, 0.0))
+        cf, tf = prof.get("phc_phm_linear_fwd:node", (0, 0.0))
+        cb, tb = prof.get("phc_phm_linear_bwd:node", (0, 0.0))
         if not cf or not cb or tf <= 0 or tb <= 0:
             return None
         m = wl.model
         F = m["mp_layers"][0]
-        n_lin = len(m["mp_layers"]) * (2 if m["mlp"] else 1) + (1 if m["pooling"] == "softattention" else 0)
+        n_lin = cf / steps
         unit = 2.0 * N * F * F
-        fwd_tf = n_lin * unit / (tf / steps * 1e-3) / 1e12
-        bwd_tf = n_lin * 2.0 * unit / (tb / steps * 1e-3) / 1e12
-        ach = 3.0 * n_lin * unit / ((tf + tb) / steps * 1e-3) / 1e12
+        fwd_us = 1e3 * tf / cf
+        bwd_us = 1e3 * tb / cb
+        fwd_tf = unit / (fwd_us * 1e-6) / 1e12
+        bwd_tf = 2.0 * unit / (bwd_us * 1e-6) / 1e12
+        ach = 3.0 * unit / ((fwd_us + bwd_us) * 1e-6) / 1e12
         peak, src = tensor_peak()
-        # tf32x3: every fp32 product is three tf32 MMAs, and tf32 runs at half the bf16 rate -> fp32-equivalent ceiling = peak / 6
-        ceiling = peak / 6.0 if precision == "tf32x3" else (peak if precision == "bf16" else None)
-        return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "peak_source": src,
-                "kernels": "phm_linear mix (fwd, dX) + dH + contraction kernels; fp32-equivalent algorithmic FLOPs",
-                "fwd_tflops": fwd_tf, "bwd_tflops": bwd_tf, "node_level_linears": n_lin,
-                "algorithmic_flops_per_step": 3.0 * n_lin * unit,
-                "precision_ceiling_tflops": ceiling, "frac_of_precision_ceiling": (ach / ceiling) if ceiling else None,
-                "timed": "CUDA events around each C-ABI call, instrumented repeat of the K steps (head-level calls included in "
-                         "the time, not in the FLOPs)"}
+        ceiling = None
+        if precision in PASSES:
+            passes, rate = PASSES[precision]
+            ceiling = peak * rate / passes       # fp32-equivalent ceiling: every product costs `passes` MMAs at `rate` x the bf16 rate
+        traffic, tsrc = traffic_record("phm_tc_mix")
+        return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
+                "traffic_source": tsrc, "peak_source": src,
+                "kernel": "node-level PHMLinear: phm_tc_mix (forward, dX) + phm_tc_dh (dH) + small contraction kernels; fp32-equivalent "
+                          "algorithmic FLOPs 6*M*in*out per linear and step",
+                "forward_launch": {"avg_us": fwd_us, "tflops": fwd_tf, "flops": unit},
+                "backward_call": {"avg_us": bwd_us, "tflops": bwd_tf, "flops": 2.0 * unit},
+                "node_level_linears": n_lin, "rows": N, "in_out": F, "algorithmic_flops_per_step": 3.0 * n_lin * unit,
+                "share_of_step": ((tf + tb) / steps / step_ms) if step_ms else None,
+                "precision": precision, "precision_ceiling_tflops": ceiling,
+                "frac_of_precision_ceiling": (ach / ceiling) if ceiling else None,
+                "timed": "CUDA events around each C-ABI call on the launching stream, instrumented repeat of the K steps"}
     except Exception:
         return None
 
@@ -305,13 +332,6 @@ def cpu_baseline(wl, budget_s: float = 20.0):
                       f"{ref.describe()}, torch CPU, {cores} threads, {dt:.1f} s"}
 
 
-# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the aggregation forward kernel from the
-# committed ncu --set full capture of this same command (profiles/r01_conv_fwd_ppa_ncu_full.txt)
-NCU_TRAFFIC_BYTES = {"ppa": 42.00e6 + 7.48e6}
-# the same for conv_fwd_sums_kernel (profiles/r01_conv_fwd_sums_ppa_ncu_full.txt)
-NCU_TRAFFIC_BYTES_SUMS = {"ppa": 33.07e6 + 1.78e6}
-
-
 def aggregation_bytes(N, E, F, softmax):
     """Algorithmic HBM bytes of one fused aggregation forward."""
     return 4 * F * (2 * N + E) + 8 * E + 4 * (N + 1) + (8 * N * F if softmax else 0)
@@ -377,8 +397,10 @@ def run_b200(args):
 
     # untimed: one step on every distinct batch first (each batch shape is new to the caching allocator: without this the
     # first timed visit of a batch pays cudaMalloc inside the timed region), then the W warm-up steps
+    preroll = 0
     for i in range(len(devb)):
         one(i)
+        preroll += 1
     # ... and keep stepping for about a second: clocks, NCCL channels and the allocator reach their steady state (a 2-GPU run
     # measured 5.59 ms/step in a timed region that started 0.3 s after the first kernel, 5.22 ms/step once warm)
     torch.cuda.synchronize()
@@ -394,6 +416,8 @@ def run_b200(args):
                 dist.all_reduce(flag, op=dist.ReduceOp.MIN)      # all ranks leave the pre-roll together
             if float(flag.item()) == 0.0:
                 break
+    preroll = {"steps": preroll + extra, "why": "untimed, BEFORE the W warm-up steps: one step per distinct batch shape (allocator) plus "
+               "about one second of stepping until clocks / NCCL channels are in steady state; the reference arm does W only"}
     for i in range(args.warmup):
         one(i)
     # ---- timed region: K steps, device-resident batches, no per-op instrumentation --------------------------
@@ -526,56 +550,52 @@ def run_b200(args):
         fused = sums_path or "phc_conv_fused_fwd" in prof
         key = "phc_conv_fused_fwd_sums" if sums_path else ("phc_conv_fused_fwd" if fused else "phc_aggregate_fwd")
         calls, agg_ms = prof.get(key, (0, 0.0))
-        roof = None
+        agg = None
         if calls:
             softmax = wl.model["msg_aggr"] == "softmax"
-            byt = aggregation_bytes(N, E, F, softmax)                 # SURVEY 8(d) unit: one layer's propagate
+            boundary = aggregation_bytes(N, E, F, softmax)            # SURVEY 8(d) unit: one layer's propagate at the reference's boundary
             us = 1e3 * agg_ms / calls
-            ach = byt / us / 1e3
-            roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": (NCU_TRAFFIC_BYTES_SUMS if sums_path else NCU_TRAFFIC_BYTES).get(wl.name) if fused else None,
-                    "peak_source": peak_src, "algorithmic_bytes_per_launch": byt, "avg_launch_us": us,
-                    "share_of_step": agg_ms / ms,      # of the headline (uninstrumented) step; the instrumented repeat is slower
-                    "timed": "CUDA events around each launch, instrumented repeat of the K steps"}
-            if fused:
-                dims = wl.model["bond_input_dims"]
-                attr_b = (4 * dims if isinstance(dims, int) else 8 * len(dims)) * E
-                rows = (dims + 1) if isinstance(dims, int) else sum(dims)
-                if sums_path:
-                    actual = 4 * F * 2 * N + 4 * rows * N + 4 * E + 4 * (N + 1) + 4 * rows * F
-                    roof.update({
-                        "kernel": "conv_fwd_sums_kernel (row gather + per-node encoder term; + enc_table_kernel)",
-                        "note": "achieved = SURVEY 8(d) algorithmic bytes of the unit (x, the [E,F] edge embedding, out, indices) / time, "
-                                "i.e. EFFECTIVE bandwidth at the reference's operator boundary; it exceeds the HBM peak because for "
-                                "sum/mean aggregation with an identity message the linear edge encoder is applied to per-node feature "
-                                "sums (computed once per batch), so the [E,F] operand is never formed or read: the kernel really moves "
-                                "hbm_bytes_model bytes and is bound by the L2 row gather (l2_gather_gbs = 4*E*F bytes / time); the "
-                                "HBM-streaming kernel of the same boundary is reported under unfused_boundary_kernel",
-                        "hbm_bytes_model": actual, "hbm_gbs_model": actual / us / 1e3, "l2_gather_gbs": 4 * E * F / us / 1e3,
-                        "unfused_boundary_kernel": unfused})
-                else:
-                    actual = 4 * F * 2 * N + attr_b + 8 * E + 4 * (N + 1) + (8 * N * F if softmax else 0)
-                    roof.update({
-                        "kernel": "conv_fwd_kernel (gather + edge ENCODER + edge add + reduce fused)",
-                        "note": "achieved = SURVEY 8(d) algorithmic bytes of the unit (edge embedding [E,F] counted) / time, i.e. "
-                                "effective bandwidth; the fused kernel rebuilds the embedding from the raw edge features and really "
-                                "moves only hbm_bytes_model bytes, it is bound by the L2 row gather and FMA issue, not by HBM",
-                        "hbm_bytes_model": actual, "hbm_gbs_model": actual / us / 1e3, "unfused_boundary_kernel": unfused})
-                if unfused:
-                    unfused["frac"] = unfused["achieved"] / peak
+            dims = wl.model["bond_input_dims"]
+            attr_b = (4 * dims if isinstance(dims, int) else 8 * len(dims)) * E
+            rows = (dims + 1) if isinstance(dims, int) else sum(dims)
+            if sums_path:      # x gathered + out + per-node feature sums + indices + the encoder table: what the kernel must move
+                model_b, kname = 4 * F * 2 * N + 4 * rows * N + 4 * E + 4 * (N + 1) + 4 * rows * F, "conv_fwd_sums"
+                kdesc = "conv_fwd_sums_kernel (row gather + per-node encoder term; + enc_table_kernel)"
+            elif fused:
+                model_b, kname = 4 * F * 2 * N + attr_b + 8 * E + 4 * (N + 1) + (8 * N * F if softmax else 0), "conv_fwd"
+                kdesc = "conv_fwd_kernel (gather + edge ENCODER + edge add + reduce fused)"
             else:
-                roof["kernel"] = "aggregate_fwd_kernel (fused gather + edge add + reduce)"
+                model_b, kname, kdesc = boundary, "aggregate_fwd", "aggregate_fwd_kernel (fused gather + edge add + reduce)"
+            traffic, tsrc = traffic_record(kname + ":" + wl.name)
+            agg = {"bound": "hbm", "kernel": kdesc, "achieved": model_b / us / 1e3, "peak": peak, "unit": "GB/s",
+                   "frac": model_b / us / 1e3 / peak, "traffic": traffic, "traffic_source": tsrc, "peak_source": peak_src,
+                   "algorithmic_bytes_per_launch": model_b, "avg_launch_us": us, "share_of_step": agg_ms / ms,
+                   "note": "achieved = the bytes this kernel must move (its own HBM model: x, out, indices and the raw edge features or "
+                           "their per-node sums) / time.  The fused kernels never form the [E,F] edge embedding the reference's operator "
+                           "boundary reads, so against the SURVEY 8(d) boundary bytes the same time is an EFFECTIVE rate "
+                           "(effective_boundary_gbs, may exceed the HBM peak); they are bound by the L2 row gather (l2_gather_gbs = "
+                           "4*E*F bytes / time).  The kernel that streams [E,F] from HBM at that boundary is unfused_boundary_kernel.",
+                   "boundary_bytes_per_launch": boundary, "effective_boundary_gbs": boundary / us / 1e3,
+                   "l2_gather_gbs": 4 * E * F / us / 1e3, "unfused_boundary_kernel": unfused,
+                   "timed": "CUDA events around each launch, instrumented repeat of the K steps"}
+            if unfused:
+                unfused["frac"] = unfused["achieved"] / peak
+        precision_name = os.environ.get("PHC_PRECISION", DEFAULT_PRECISION)
+        roof = phm_linear_roofline(prof, args.steps, wl, N, precision_name, ms_instr / args.steps)
+        if roof is None:        # a workload without node-level tensor-core linears: the aggregation is the dominant kernel
+            roof, agg = agg, None
         breakdown = {k: {"calls_per_step": v[0] / args.steps, "ms_per_step": v[1] / args.steps} for k, v in sorted(prof.items())}
         if args.kernel_timers:
             print(json.dumps(breakdown, indent=1), file=sys.stderr)
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-               "dtype": {"fp32": "f32", "tf32x3": "f32 (tf32x3 tensor-core split, fp32 accumulate)", "bf16": "bf16"}[
-                   os.environ.get("PHC_PRECISION", "tf32x3")],
+               "dtype": {"fp32": "f32", "tf32x3": "f32 (tf32x3 tensor-core split, fp32 accumulate)",
+                         "bf16x3": "f32 (bf16x3 tensor-core split: 16-bit-mantissa operands in three bf16 passes, fp32 accumulate)",
+                         "bf16": "bf16"}[precision_name],
                "data": "synthetic",
                "config": config_dict(args, wl, wl.batch_graphs, "flushed between steps" if flush else "inputs larger than L2"),
-               "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof,
-               "roofline_phm_linear": phm_linear_roofline(prof, args.steps, wl, N, os.environ.get("PHC_PRECISION", "tf32x3")),
+               "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "roofline_aggregation": agg,
+               "preroll_steps": preroll,
                "ms_per_step_instrumented": ms_instr / args.steps,
                "op_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in breakdown.items()},
                "final_loss": float(loss.item())}

@@ -81,6 +81,7 @@ struct MixParams {          // y = act(mix GEMM + bias) + residual   (FWD and DX
                             //     M2) for a batch-norm that follows (norm.cu merges them) — the drain owns one column per lane anyway
   float* sk_part;           // v3 stream-K: per-CTA partial accumulators [grid][16 warps][32 rows][64 cols] (NULL: whole units only)
   unsigned int* sk_flags;   // v3 stream-K: [grid][16] "partial written" flags, zero between launches
+  int ablate;               // debug (env PHC_TC_ABLATE): 1 no MMAs | 2 no mixing / tcgen05.st | 4 no activation TMA | 8 no drain | 16 no W TMA
 };
 
 struct DhParams {           // partial dH tiles
@@ -1010,7 +1011,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
       const int rs = gi % V3_NRAW;                               // raw stage of this chunk
       const uint32_t rawg = raw0 + (uint32_t)(rs * V3_RAW_BYTES);
       if (prof) tp = clock64();
-      mbar_wait(smem_u32(&rfull[rs]), (gi / V3_NRAW) & 1);      // raw boxes landed (TMA)
+      if (!(p.ablate & 4)) mbar_wait(smem_u32(&rfull[rs]), (gi / V3_NRAW) & 1);      // raw boxes landed (TMA)
       if (prof) { const long long tn = clock64(); t_rfull += tn - tp; tp = tn; }
       float xr[NT][KQ];
       uint32_t landed = 0;                                       // data dependence on every load (see the release below)
@@ -1035,7 +1036,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
       // the arrive (release) stays behind the store.
       asm volatile("st.shared.b32 [%0], %1;" ::"r"(smem_u32(my + lane)), "r"(landed) : "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&rempty[rs]));
+      if (lane == 0 && !(p.ablate & 4)) mbar_arrive(smem_u32(&rempty[rs]));
       if (c == p.chunks - 1) {                                   // K tail: columns past the component belong to its neighbour
 #pragma unroll
         for (int k = 0; k < KQ; ++k)
@@ -1048,6 +1049,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
       mbar_wait(smem_u32(&aempty[g]), (use & 1) ^ 1);           // the MMAs that read this operand slot have retired
       if (prof) { const long long tn = clock64(); t_aempty += tn - tp; tp = tn; }
       tc_fence_after();
+      if (!(p.ablate & 2)) {
 #pragma unroll
       for (int kp = 0; kp < KQ; kp += 2) {                       // 2 k values = 8 operand columns (column = k*4 + b)
         float big[8], small[8];
@@ -1066,6 +1068,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
           }
         tmem_st8(a_slot + kp * 4, big);
         if (!SINGLE) tmem_st8(a_slot + 32 + kp * 4, small);
+      }
       }
       tmem_st_wait();
       tc_fence_before();
@@ -1086,7 +1089,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
       // owner, which adds the partial parked by the NEXT CTA (whose first segment is the rest of this unit)
       const int mode = PHC_TC_STREAM_K ? (sg.c0 > 0 ? 1 : (sg.c1 < p.chunks ? 2 : 0)) : 0;
       const int slot = (int)blockIdx.x + (mode == 2 ? 1 : 0);
-      if (ncols > 0 && r0 < p.M)
+      if (ncols > 0 && r0 < p.M && !(p.ablate & 8))
         v3_drain<STATS>(my, tmem_base + lane_base + (uint32_t)(h * BN + g * 64), p.C, ldc, min(32, p.M - r0), r0,
                  (2 * pair + h) * p.Pout + pt * BN + g * 64, ncols, p.bias, p.residual, p.act, mode,
                  mode ? p.sk_part + ((size_t)slot * PROD_WARPS + warp) * (32 * 64) : nullptr,
@@ -1116,7 +1119,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
     }
   } else if (warp == V3_TMA_X_WARP) {
     // ===================================================================== TMA: raw activation boxes
-    if (lane == 0) {
+    if (lane == 0 && !(p.ablate & 4)) {
       int gi = 0;
       for (int si = 0; si < nseg; ++si) {
         const V3Seg sg = v3_seg(p, gb, ge, si);
@@ -1135,7 +1138,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
     }
   } else if (warp == V3_TMA_B_WARP) {
     // ===================================================================== TMA: pre-split W chunks
-    if (lane == 0) {
+    if (lane == 0 && !(p.ablate & 16)) {
       int gi = 0;
       for (int si = 0; si < nseg; ++si) {
         const V3Seg sg = v3_seg(p, gb, ge, si);
@@ -1169,12 +1172,13 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
         if (prof) tp = clock64();
         mbar_wait(smem_u32(&afull[g]), (gi >> 1) & 1);
         if (prof) { const long long tn = clock64(); t_afull += tn - tp; tp = tn; }
-        mbar_wait(smem_u32(&bfull[bs]), (gi / V3_NB) & 1);
+        if (!(p.ablate & 16)) mbar_wait(smem_u32(&bfull[bs]), (gi / V3_NB) & 1);
         if (prof) t_bfull += clock64() - tp;
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sb = smem_u32(bstage + bs * 2 * TILE_BYTES);
           const uint64_t b_big = make_desc(sb), b_small = make_desc(sb + TILE_BYTES);
+          if (!(p.ablate & 1)) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const uint32_t d_tmem = tmem_base + h * BN;
@@ -1193,9 +1197,10 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
               acc = 1u;
             }
           }
+          }
           accum = 1u;
           umma_commit(smem_u32(&aempty[g]));
-          umma_commit(smem_u32(&bempty[bs]));
+          if (!(p.ablate & 16)) umma_commit(smem_u32(&bempty[bs]));
         }
         __syncwarp();
       }
@@ -1931,6 +1936,8 @@ int launch_mix_v3_r(const MixParams& p, const CUtensorMap& tmap, cudaStream_t st
 // TMEM-operand path: n == 4, 16-byte aligned rows.  Returns -1 when not applicable (caller falls back).
 int try_launch_mix_v3(const MixParams& p, cudaStream_t stream) {
   static const bool use_v3 = getenv("PHC_TC_NO_TMEM_A") == nullptr;
+  static const int ablate = getenv("PHC_TC_ABLATE") ? atoi(getenv("PHC_TC_ABLATE")) : 0;
+  const_cast<MixParams&>(p).ablate = ablate;
   const int Fin = p.n * p.Kin;
   if (!use_v3 || p.n != 4 || Fin % 4 != 0 || (reinterpret_cast<uintptr_t>(p.X) & 15u) != 0) return -1;
   EncodeTiledFn enc = encode_tiled_fn();

@@ -44,7 +44,7 @@ def _lin_fwd(x, rule, W, b, residual, precision, stream):
     nb = _ws_bytes("phc_phm_linear_fwd_workspace_bytes", M, n * K, n * P, n, precision)
     ws = _ws(nb, x.device)
     run("phc_phm_linear_fwd", None, x.data_ptr(), rule.data_ptr(), W.data_ptr(), _ptr(b), _ptr(residual), y.data_ptr(), M, n * K, n * P,
-        n, 0, precision, ws.data_ptr(), ws.numel(), stream)
+        n, 0, precision, ws.data_ptr(), ws.numel(), stream, tag=":node" if M >= 1024 else ":head")
     return y, (ws if nb > 64 else None)
 
 
@@ -58,7 +58,7 @@ def _lin_bwd(gy, x, rule, W, has_bias, need_dx, precision, fwd_ws, stream):
     nb = _ws_bytes("phc_phm_linear_bwd_workspace_bytes", M, n * K, n * P, n, precision)
     ws = _ws(nb, x.device)
     run("phc_phm_linear_bwd", None, gy.data_ptr(), x.data_ptr(), rule.data_ptr(), W.data_ptr(), _ptr(dx), _ptr(d_rule), dW.data_ptr(),
-        _ptr(db), M, n * K, n * P, n, precision, ws.data_ptr(), ws.numel(), _ptr(fwd_ws), stream)
+        _ptr(db), M, n * K, n * P, n, precision, ws.data_ptr(), ws.numel(), _ptr(fwd_ws), stream, tag=":node" if M >= 1024 else ":head")
     return dx, d_rule, dW, db
 
 
@@ -467,12 +467,17 @@ class _ConvLayerDirect(torch.autograd.Function):
         cfg, struct, flats, attr, tensors = plan
         out, saved, host = _call_fwd(cfg, struct, flats, x, skip, attr, tensors)
         ctx.save_for_backward(x, attr, *saved)
-        ctx.misc = (cfg, struct, host, tensors, skip is not None)
+        # the parameters are not saved tensors here (they are outside the graph): do autograd's version check by hand
+        ctx.misc = (cfg, struct, host, tensors, skip is not None, tuple(-1 if t is None else t._version for t in tensors))
         return out
 
     @staticmethod
     def backward(ctx, g):
-        cfg, struct, host, tensors, has_skip = ctx.misc
+        cfg, struct, host, tensors, has_skip, versions = ctx.misc
+        for t, v in zip(tensors, versions):
+            if t is not None and t._version != v:
+                raise RuntimeError("a parameter of a fused message-passing layer was modified in place between its forward and "
+                                   "backward (the backward would read the new value); clone it or set layer.DIRECT_PARAM_GRADS = False")
         x, attr = ctx.saved_tensors[:2]
         sinks = [None if (t is None or t.grad is not None) else grad_sink(t) for t in tensors]
         dx, g, grads = _call_bwd(cfg, struct, host, x, attr, g, tensors, sinks)
@@ -484,6 +489,19 @@ class _ConvLayerDirect(torch.autograd.Function):
             else:
                 t.grad.add_(gr)
         return None, dx, (g if has_skip else None)
+
+
+def _direct_eligible(tensors) -> bool:
+    """The in-place gradient path bypasses autograd for the layer's parameters, so it is taken only when nothing can observe the
+    difference: every trainable parameter has a slice of a flat gradient buffer registered (a GradientBucket / FlatClipAdam owns
+    the step) and none carries a tensor hook or a post-accumulate-grad hook (DistributedDataParallel, gradient clipping hooks,
+    user hooks).  Anything else takes _ConvLayerCall, whose parameter gradients flow through autograd."""
+    for t in tensors:
+        if t is None or not t.requires_grad:
+            continue
+        if grad_sink(t) is None or t._backward_hooks or getattr(t, "_post_accumulate_grad_hooks", None):
+            return False
+    return True
 
 
 def conv_layer(x, skip, edge_attr, struct: EdgeStructure, *, phm_dim: int, enc_linear: bool, enc_params: Sequence[torch.Tensor],
@@ -524,7 +542,7 @@ def conv_layer(x, skip, edge_attr, struct: EdgeStructure, *, phm_dim: int, enc_l
            float(norm1.momentum) if norm1 is not None else 0.1, float(norm1.eps) if norm1 is not None else 1e-5,
            float(norm2.momentum) if norm2 is not None else 0.1, float(norm2.eps) if norm2 is not None else 1e-5)
     if SINGLE_CALL and not PROFILE.timing:
-        if DIRECT_PARAM_GRADS and torch.is_grad_enabled() and x.requires_grad:
+        if DIRECT_PARAM_GRADS and torch.is_grad_enabled() and x.requires_grad and _direct_eligible(tensors):
             return _ConvLayerDirect.apply((cfg, struct, (flat1, flat2), edge_attr, tensors), x, skip)
         return _ConvLayerCall.apply(cfg, struct, (flat1, flat2), x, skip, edge_attr, *tensors)
     return _ConvLayer.apply(cfg, struct, (flat1, flat2), x, skip, edge_attr, *tensors)       # per-operator calls (each one timed)

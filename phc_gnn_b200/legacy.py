@@ -182,6 +182,14 @@ def _placeholder_function(*args, **kwargs):
 
 
 _FOREIGN_ROOTS = ("hypercomplex", "quaternion", "phc", "torch_geometric", "torch_scatter", "ogb")
+# everything else a module pickle may legitimately name: tensor rebuilders, containers, dtypes — nothing executable beyond them
+_ALLOWED_ROOTS = ("torch", "collections", "numpy")
+# inert stdlib data classes found in the shipped checkpoints (PyG's MessagePassing keeps inspect.signature() results)
+_ALLOWED_GLOBALS = {("copyreg", "_reconstructor"), ("inspect", "Parameter"), ("inspect", "_ParameterKind"), ("inspect", "_empty"),
+                    ("inspect", "Signature"), ("typing", "Any"), ("typing", "Optional"), ("typing", "Union"),
+                    ("_operator", "getitem"), ("typing", "Tuple"), ("typing", "List"), ("typing", "Dict"), ("typing", "Callable")}
+_ALLOWED_BUILTINS = {"set", "frozenset", "list", "dict", "tuple", "int", "float", "bool", "str", "bytes", "complex", "slice", "range",
+                     "object", "long", "unicode", "type"}
 
 
 class _LegacyUnpickler(pickle.Unpickler):
@@ -194,7 +202,12 @@ class _LegacyUnpickler(pickle.Unpickler):
                 self._classes[key] = (type(name, (_Placeholder,), {"__module__": "phc_legacy." + module})
                                       if name[:1].isupper() else _placeholder_function)
             return self._classes[key]
-        return super().find_class(module, name)
+        root = module.split(".")[0]
+        if root in _ALLOWED_ROOTS or (root in ("builtins", "__builtin__") and name in _ALLOWED_BUILTINS) or \
+                (module, name) in _ALLOWED_GLOBALS:
+            return super().find_class(module, name)
+        raise pickle.UnpicklingError(f"legacy checkpoint names {module}.{name}: only torch / collections / numpy globals and the "
+                                     f"reference's own (placeholder) classes are accepted")
 
 
 def _pickle_module():

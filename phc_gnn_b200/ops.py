@@ -116,7 +116,7 @@ class _PHMLinear(torch.autograd.Function):
         nb = lib.phc_phm_linear_fwd_workspace_bytes(M, fin, fout, n, precision)
         ws = _ws(nb, x.device)
         run("phc_phm_linear_fwd", None, x.data_ptr(), rule.data_ptr(), W.data_ptr(), _ptr(bias), _ptr(residual), y.data_ptr(), M,
-                                          fin, fout, n, 0, precision, ws.data_ptr(), ws.numel(), _stream(x.device))
+                                          fin, fout, n, 0, precision, ws.data_ptr(), ws.numel(), _stream(x.device), tag=":node" if M >= 1024 else ":head")
         ctx.save_for_backward(x, rule, W)
         ctx.meta = (bias is not None, residual is not None, precision)
         ctx.fwd_ws = ws if nb > 64 else None          # tensor-core path: operand packs, reused by backward
@@ -139,7 +139,7 @@ class _PHMLinear(torch.autograd.Function):
         ws = _ws(nb, x.device)
         run("phc_phm_linear_bwd", None, gy.data_ptr(), x.data_ptr(), rule.data_ptr(), W.data_ptr(), _ptr(dx), _ptr(d_rule),
                                           dW.data_ptr(), _ptr(db), M, fin, fout, n, precision, ws.data_ptr(), ws.numel(),
-                                          _ptr(ctx.fwd_ws), _stream(x.device))
+                                          _ptr(ctx.fwd_ws), _stream(x.device), tag=":node" if M >= 1024 else ":head")
         return dx, d_rule, (dW if need[2] else None), db, (gy if (has_res and need[4]) else None), None
 
 

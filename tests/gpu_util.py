@@ -28,10 +28,16 @@ def oracle_params(state, dtype=torch.float32):
     return p
 
 
-def product_train_eval(cfg, state, batch, loss_kind, reg_scale, device, fuse_edge_encoder=True, fuse_layer=True):
-    """-> dict(logits, loss, reg, grads, running, logits_eval) from the CUDA path."""
+def product_train_eval(cfg, state, batch, loss_kind, reg_scale, device, fuse_edge_encoder=True, fuse_layer=True, bucket=True):
+    """-> dict(logits, loss, reg, grads, running, logits_eval) from the CUDA path.  bucket: register a flat gradient buffer for the
+    parameters, as FlatClipAdam / DataParallelPHC do — the precondition of the layers' in-place parameter-gradient path."""
     from phc.hypercomplex.regularization import phm_weight_regularization
     m = product_model(cfg, state, device)
+    if bucket:
+        from phc_gnn_b200.optim import ordered_parameters
+        from phc_gnn_b200.parallel import GradientBucket
+        m._test_bucket = GradientBucket(ordered_parameters(m))
+        m._test_bucket._ensure(torch.device(device))
     m.fuse_edge_encoder = fuse_edge_encoder
     m.fuse_layer = fuse_layer
     data = batch.to(device)

@@ -48,6 +48,42 @@ def test_model_matches_reference_golden(name, fuse, monkeypatch):
     _compare(got, want, RTOL, name)
 
 
+@pytest.mark.parametrize("name", golden_cases())
+def test_model_matches_reference_golden_default_precision(name, monkeypatch):
+    """The same reference-recorded fixtures in the DEFAULT precision mode (whatever ops.precision() resolves to when
+    PHC_PRECISION is unset — the mode bench.py measures), production orchestration."""
+    monkeypatch.delenv("PHC_PRECISION", raising=False)
+    fx = load_golden(name)
+    got = product_train_eval(fx["cfg"], fx["state"], fx["batch"], fx["loss_kind"], fx["reg_scale"], DEV)
+    want = dict(logits=fx["logits_train"], loss=fx["loss"], reg=fx["reg"], grads=fx["grads"], running=fx["running_after"],
+                logits_eval=fx["logits_eval"])
+    _compare(got, want, RTOL, name)
+
+
+@pytest.mark.parametrize("wl_name,n", [("ppa", 4), ("hiv", 4), ("zinc", 2), ("zinc", 4), ("pcba", 4), ("mnist", 4), ("cifar", 4)])
+def test_full_size_benchmark_config_default_precision(wl_name, n, monkeypatch):
+    """Every BASELINE.json configuration at FULL size — all layers, full width, the full per-GPU batch bench.py times (ppa: 7 x 500,
+    B = 64, M ~ 15.6k rows) — in the default precision mode, against the fp64 oracle at the north_star tolerance (rtol 1e-4; values
+    that are ill-conditioned in fp32 get 10x the fp32-oracle-to-fp64-oracle distance).  Dropout off (masks cannot match across devices)."""
+    monkeypatch.delenv("PHC_PRECISION", raising=False)
+    from phc.hypercomplex.undirectional.models import PHMSkipConnectAdd
+    from phc_gnn_b200.synthetic import workloads, make_batch
+    import numpy as np
+    wl = workloads(n)[wl_name]
+    cfg = dict(wl.model)
+    cfg["dropout_mpnn"] = [0.0] * len(cfg["mp_layers"])
+    cfg["dropout_dn"] = [0.0] * len(cfg["downstream_layers"])
+    torch.manual_seed(0)
+    np.random.seed(0)
+    state = PHMSkipConnectAdd(**cfg).state_dict()
+    batch = make_batch(wl, seed=11)
+    assert batch.num_graphs == wl.batch_graphs
+    got = product_train_eval(cfg, state, batch, wl.loss, 0.01, DEV)
+    want = oracle_train_eval(cfg, state, batch, wl.loss, 0.01, torch.float64)
+    noise = oracle_train_eval(cfg, state, batch, wl.loss, 0.01, torch.float32)
+    _compare(got, want, RTOL, f"{wl_name} n={n} full size", noise)
+
+
 @pytest.mark.parametrize("wl_name,graphs,n", [("hiv", 32, 4), ("zinc", 32, 2), ("zinc", 32, 4), ("pcba", 24, 4), ("mnist", 8, 4), ("ppa", 5, 4)])
 def test_model_matches_oracle_on_workload_shapes(wl_name, graphs, n, monkeypatch):
     """Full-width models (reference default hyper-parameters) on small batches of the benchmark shapes."""

@@ -7,7 +7,7 @@ import os
 import pytest
 import torch
 
-from conftest import golden_cases, load_golden
+from conftest import ROOT, golden_cases, load_golden
 
 
 def test_library_builds_loads_and_exports_header_symbols():
@@ -130,11 +130,42 @@ def test_phmlinear_asserts_like_reference():
         PHMLinear(8, 8, 4, w_init="glorot_uniform")     # the reference wants hyphens here (layers.py:228)
 
 
-def test_scheduler_compat_hook():
-    import phc  # noqa: F401
-    opt = torch.optim.Adam([torch.nn.Parameter(torch.zeros(1))])
-    torch.optim.lr_scheduler.ReduceLROnPlateau(opt, mode="max", factor=0.5, patience=3, verbose=True)
-    torch.optim.lr_scheduler.StepLR(opt, step_size=10, gamma=0.5, verbose=True)
+def test_import_changes_nothing_in_torch_and_compat_is_opt_in(monkeypatch):
+    """``import phc`` must not touch global torch behaviour (no TORCH_FORCE_NO_WEIGHTS_ONLY_LOAD, no patched schedulers); the shims
+    the reference's unchanged scripts need are installed by phc.compat.enable() only."""
+    import subprocess
+    import sys
+    code = ("import os, torch, inspect; import phc; "
+            "assert 'TORCH_FORCE_NO_WEIGHTS_ONLY_LOAD' not in os.environ; "
+            "assert not getattr(torch.optim.lr_scheduler.StepLR.__init__, '_phc_compat', False); print('clean')")
+    env = {k: v for k, v in os.environ.items() if k not in ("PHC_COMPAT", "TORCH_FORCE_NO_WEIGHTS_ONLY_LOAD")}
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, env=env)
+    assert out.returncode == 0 and "clean" in out.stdout, out.stderr[-1500:]
+    import phc.compat
+    saved = {c: c.__init__ for c in (torch.optim.lr_scheduler.ReduceLROnPlateau, torch.optim.lr_scheduler.StepLR)}
+    try:
+        phc.compat.enable()
+        opt = torch.optim.Adam([torch.nn.Parameter(torch.zeros(1))])
+        torch.optim.lr_scheduler.ReduceLROnPlateau(opt, mode="max", factor=0.5, patience=3, verbose=True)
+        torch.optim.lr_scheduler.StepLR(opt, step_size=10, gamma=0.5, verbose=True)
+        assert "TORCH_FORCE_NO_WEIGHTS_ONLY_LOAD" not in os.environ or os.environ.get("PHC_COMPAT") == "trust-checkpoints"
+    finally:
+        for c, init in saved.items():
+            c.__init__ = init
+    original = torch.load
+    with phc.compat.trusted_load():
+        assert torch.load is not original
+    assert torch.load is original
+
+
+def test_legacy_unpickler_refuses_foreign_globals(tmp_path):
+    import pickle
+    from phc_gnn_b200 import legacy
+    path = tmp_path / "evil.pkl"
+    with open(path, "wb") as fh:
+        pickle.dump(os.system, fh)                      # a global outside torch / collections / numpy
+    with open(path, "rb") as fh, pytest.raises(pickle.UnpicklingError):
+        legacy._LegacyUnpickler(fh).load()
 
 
 def test_synthetic_batches_are_deterministic_and_shaped():
