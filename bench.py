@@ -42,6 +42,9 @@ def parse():
                     help="quaternion: the reference's QuaternionSkipConnectAdd on the same kernels (n = 4, frozen Hamilton rule)")
     ap.add_argument("--batches", type=int, default=8, help="distinct synthetic batches cycled per rank")
     ap.add_argument("--precision", default=None, help="fp32 | tf32x3 | bf16 (default: PHC_PRECISION or tf32x3)")
+    ap.add_argument("--graph", default="on", choices=["on", "off"],
+                    help="on: the whole step (forward, loss, backward, all-reduce, clip + Adam) is replayed from one CUDA graph per batch "
+                         "shape (phc_gnn_b200/graphed.py); off: eager host path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--kernel-timers", action="store_true", help="also print the per-op CUDA-event breakdown to stderr")
@@ -369,6 +372,9 @@ def run_b200(args):
         model = PHMSkipConnectAdd(**wl.model).to(dev)
     dp = DataParallelPHC(model) if world > 1 else None
     step = TrainStep(model, wl, None, dp)        # flat clip+Adam (optim.FlatClipAdam): same update rule, 2 launches
+    if args.graph == "on":
+        from phc_gnn_b200.graphed import GraphedTrainStep
+        step = GraphedTrainStep(step, max_graphs=2 * args.batches + 4)
     model.train()
 
     host = [make_batch(wl, seed=rank * 1000 + i).pin_memory() for i in range(args.batches)]
@@ -595,7 +601,7 @@ def run_b200(args):
                "data": "synthetic",
                "config": config_dict(args, wl, wl.batch_graphs, "flushed between steps" if flush else "inputs larger than L2"),
                "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "roofline_aggregation": agg,
-               "preroll_steps": preroll,
+               "preroll_steps": preroll, "cuda_graph": step.stats() if args.graph == "on" else None,
                "ms_per_step_instrumented": ms_instr / args.steps,
                "op_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in breakdown.items()},
                "final_loss": float(loss.item())}

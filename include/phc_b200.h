@@ -243,6 +243,21 @@ size_t phc_adam_workspace_bytes(void);
 int phc_adam_clip_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long numel, float lr, float beta1,
                        float beta2, float eps, float bias_correction1, float bias_correction2, float max_norm, float* grad_norm_out,
                        void* workspace, size_t workspace_bytes, phc_stream_t stream);
+/* The same step with the learning rate and the step counter t in DEVICE memory (lr_dev[0], step_dev[0]; the call advances t and
+ * derives the bias corrections from it): nothing the host passes by value changes from step to step, so the call can be recorded
+ * into a CUDA graph and replayed (the reference's train() body as one graph: phc_gnn_b200/graphed.py). */
+int phc_adam_clip_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long numel, const float* lr_dev,
+                           float beta1, float beta2, float eps, int* step_dev, float max_norm, float* grad_norm_out, void* workspace,
+                           size_t workspace_bytes, phc_stream_t stream);
+
+/* ---- dropout epoch (graph replay) --------------------------------------------------------------------------
+ * Dropout masks are a pure function of (seed, element index) with the seed passed by value — a recorded CUDA graph would replay
+ * the same masks for ever.  With an epoch word registered (device memory, unsigned long long[1]; NULL unregisters) every dropout
+ * kernel of this library keys its Philox stream with seed + epoch[0] * 0x9E3779B97F4A7C15, read on the device at run time;
+ * phc_dropout_epoch_advance adds 1 to it on `stream` (recorded at the top of a captured step, so forward and backward of one
+ * replay agree and consecutive replays differ).  Process-global, like torch's default generator. */
+int phc_dropout_epoch_register(unsigned long long* epoch_dev);
+int phc_dropout_epoch_advance(unsigned long long* epoch_dev, phc_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -35,7 +35,15 @@ struct EwParams {
   unsigned int keep_thr;   // keep iff philox < keep_thr
   float drop_scale;        // 1/(1-p)
   unsigned long long seed;
+  const unsigned long long* epoch;   // optional device word added (times an odd constant) to the seed at run time: CUDA-graph replays
 };
+
+// registered by phc_dropout_epoch_register (process-global, like a default generator)
+static unsigned long long* g_dropout_epoch = nullptr;
+
+__device__ __forceinline__ void fold_epoch(EwParams& p) {
+  if (p.drop_on && p.epoch != nullptr) p.seed += *p.epoch * 0x9E3779B97F4A7C15ULL;
+}
 
 __device__ __forceinline__ bool drop_keep_bit(const EwParams& p, int row, int f) {
   unsigned long long idx = p.drop_same ? (unsigned long long)row * p.Fc + (f % p.Fc) : (unsigned long long)row * p.F + f;
@@ -242,6 +250,7 @@ __global__ void __launch_bounds__(BN_THREADS, 3) bn_apply_fwd_kernel(EwParams p,
                                                                      const float* __restrict__ rstd, const float* __restrict__ skip,
                                                                      float* __restrict__ y) {
   pdl_begin();
+  fold_epoch(p);
   const int lane = threadIdx.x % BN_LANES, slice = threadIdx.x / BN_LANES;
   const int f = (blockIdx.y * BN_LANES + lane) * VEC;
   if (f >= p.F) return;
@@ -290,6 +299,7 @@ __global__ void __launch_bounds__(BN_THREADS, 3) bn_bwd_reduce_kernel(EwParams p
                                                                       const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                       float* __restrict__ part) {
   pdl_begin();
+  fold_epoch(p);
   const int lane = threadIdx.x % BN_LANES, slice = threadIdx.x / BN_LANES;
   const int f = (blockIdx.y * BN_LANES + lane) * VEC;
   const int r0 = blockIdx.x * p.rpc, r1 = min(r0 + p.rpc, p.M);
@@ -366,6 +376,7 @@ __global__ void __launch_bounds__(BN_THREADS, 3) bn_apply_bwd_kernel(EwParams p,
                                                                      const float* __restrict__ rstd, const float* __restrict__ sum_da,
                                                                      const float* __restrict__ sum_da_xhat, float* __restrict__ dh) {
   pdl_begin();
+  fold_epoch(p);
   const int lane = threadIdx.x % BN_LANES, slice = threadIdx.x / BN_LANES;
   const int f = (blockIdx.y * BN_LANES + lane) * VEC;
   if (f >= p.F) return;
@@ -438,6 +449,7 @@ EwParams make_params(int M, int F, int n, int use_bn, int act, float drop_p, int
   p.keep_thr = thr >= 4294967295.0 ? 0xFFFFFFFFu : (unsigned int)thr;
   p.drop_scale = keep > 0.0 ? (float)(1.0 / keep) : 0.f;
   p.seed = seed;
+  p.epoch = g_dropout_epoch;
   return p;
 }
 
@@ -617,3 +629,21 @@ int phc_sum_tensors(const float* const* srcs, int count, long long numel, float*
 }
 
 }  // extern "C"
+
+namespace {
+__global__ void dropout_epoch_advance_kernel(unsigned long long* e) {
+  pdl_begin();
+  if (threadIdx.x == 0 && blockIdx.x == 0) *e += 1ULL;
+}
+}  // namespace
+
+extern "C" int phc_dropout_epoch_register(unsigned long long* epoch_dev) {
+  g_dropout_epoch = epoch_dev;
+  return PHC_OK;
+}
+
+extern "C" int phc_dropout_epoch_advance(unsigned long long* epoch_dev, cudaStream_t stream) {
+  PHC_REQUIRE(epoch_dev != nullptr, "phc_dropout_epoch_advance: null epoch word");
+  phc_launch(dropout_epoch_advance_kernel, dim3(1), dim3(32), 0, stream, epoch_dev);
+  return phc_check_launch("phc_dropout_epoch_advance");
+}

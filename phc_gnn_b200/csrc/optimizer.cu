@@ -9,8 +9,12 @@ namespace {
 
 constexpr int OPT_BLOCKS = 296;
 
-__global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restrict__ g, long long n, float* __restrict__ part) {
+// step_dev (optional): the optimizer's step counter in device memory, advanced here — by the FIRST kernel of the pair, so that every
+// block of the second one reads the same value — which makes the step replayable from a CUDA graph (no host scalar changes per step)
+__global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restrict__ g, long long n, float* __restrict__ part,
+                                                            int* __restrict__ step_dev) {
   pdl_begin();
+  if (step_dev != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *step_dev += 1;
   float s = 0.f;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) { const float v = g[i]; s += v * v; }
   __shared__ float red[256];
@@ -26,10 +30,19 @@ __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restr
 __global__ void __launch_bounds__(256) adam_clip_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                         float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
                                                         float bc1, float bc2, float max_norm, const float* __restrict__ part, int nparts,
-                                                        float* __restrict__ norm_out) {
+                                                        float* __restrict__ norm_out, const float* __restrict__ lr_dev,
+                                                        const int* __restrict__ step_dev) {
   pdl_begin();
-  __shared__ float coef_s;
+  __shared__ float coef_s, bc_s[2];
   if (threadIdx.x == 0) {
+    if (step_dev != nullptr) {      // bias corrections 1 - beta^t from the device-resident step count (double, as the host computes them)
+      const double t = (double)*step_dev;
+      bc_s[0] = (float)(1.0 - pow((double)b1, t));
+      bc_s[1] = (float)(1.0 - pow((double)b2, t));
+    } else {
+      bc_s[0] = bc1;
+      bc_s[1] = bc2;
+    }
     float coef = 1.f;
     if (max_norm > 0.f) {
       float s = 0.f;
@@ -42,7 +55,8 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(float* __restrict__ p, c
   }
   __syncthreads();
   const float coef = coef_s;
-  const float step = lr / bc1, isq = rsqrtf(bc2);
+  if (lr_dev != nullptr) lr = *lr_dev;
+  const float step = lr / bc_s[0], isq = rsqrtf(bc_s[1]);
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
     const float gi = g[i] * coef;
     const float mi = b1 * m[i] + (1.f - b1) * gi;
@@ -66,10 +80,25 @@ int phc_adam_clip_step(float* params, const float* grads, float* exp_avg, float*
   PHC_REQUIRE(workspace_bytes >= phc_adam_workspace_bytes(), "phc_adam_clip_step: workspace too small");
   if (numel == 0) return PHC_OK;
   float* part = reinterpret_cast<float*>(workspace);
-  if (max_norm > 0.f) phc_launch(sumsq_partial_kernel, dim3(OPT_BLOCKS), dim3(256), 0, stream, grads, numel, part);
+  if (max_norm > 0.f) phc_launch(sumsq_partial_kernel, dim3(OPT_BLOCKS), dim3(256), 0, stream, grads, numel, part, (int*)nullptr);
   phc_launch(adam_clip_kernel, dim3(OPT_BLOCKS), dim3(256), 0, stream, params, grads, exp_avg, exp_avg_sq, numel, lr, beta1, beta2, eps, bias_correction1,
-                                                   bias_correction2, max_norm, part, OPT_BLOCKS, grad_norm_out);
+                                                   bias_correction2, max_norm, part, OPT_BLOCKS, grad_norm_out, (const float*)nullptr, (const int*)nullptr);
   return phc_check_launch("phc_adam_clip_step");
+}
+
+int phc_adam_clip_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long numel, const float* lr_dev,
+                           float beta1, float beta2, float eps, int* step_dev, float max_norm, float* grad_norm_out, void* workspace,
+                           size_t workspace_bytes, cudaStream_t stream) {
+  PHC_REQUIRE(numel >= 0, "phc_adam_clip_step_dev: negative size");
+  PHC_REQUIRE(lr_dev != nullptr && step_dev != nullptr, "phc_adam_clip_step_dev: lr and step count must be device pointers");
+  PHC_REQUIRE(workspace_bytes >= phc_adam_workspace_bytes(), "phc_adam_clip_step_dev: workspace too small");
+  if (numel == 0) return PHC_OK;
+  float* part = reinterpret_cast<float*>(workspace);
+  // always two launches: the first one also advances the step counter
+  phc_launch(sumsq_partial_kernel, dim3(OPT_BLOCKS), dim3(256), 0, stream, grads, max_norm > 0.f ? numel : 0LL, part, step_dev);
+  phc_launch(adam_clip_kernel, dim3(OPT_BLOCKS), dim3(256), 0, stream, params, grads, exp_avg, exp_avg_sq, numel, 0.f, beta1, beta2, eps, 1.f, 1.f,
+                                                   max_norm, part, OPT_BLOCKS, grad_norm_out, lr_dev, (const int*)step_dev);
+  return phc_check_launch("phc_adam_clip_step_dev");
 }
 
 }  // extern "C"

@@ -2049,7 +2049,8 @@ int launch_mix(const MixParams& p, cudaStream_t stream, int* v3_used) {
 int phm_tc_supported(int rows, int in_features, int out_features, int phm_dim, int precision) {
   // tf32x3 only for now; small problems (head layers, M = graphs per batch) stay on the exact FFMA path
   // (tiny M is latency-bound either way; the tensor-core kernel needs fewer serial K iterations than the FFMA tile)
-  return (precision == 1 || precision == 2) && rows >= 32 && in_features >= 32 && out_features >= 32 && phm_dim <= 16;
+  static const int min_rows = getenv("PHC_TC_MIN_ROWS") ? atoi(getenv("PHC_TC_MIN_ROWS")) : 32;     // debug knob
+  return (precision == 1 || precision == 2) && rows >= min_rows && in_features >= 32 && out_features >= 32 && phm_dim <= 16;
 }
 
 size_t phm_tc_fwd_workspace_bytes(int, int in_features, int out_features, int phm_dim, int) {

@@ -47,7 +47,7 @@ _KERNELS = {"phc_csr_build": 6, "phc_segment_ptr_build": 2, "phc_aggregate_fwd":
             "phc_embed_sum_fwd": 1, "phc_embed_sum_bwd": 2, "phc_linear_encoder_fwd": 1, "phc_linear_encoder_bwd": 2,
             "phc_phm_linear_fwd": 2, "phc_phm_linear_bwd": 4, "phc_weight_reg_fwd": 2, "phc_weight_reg_bwd": 1,
             "phc_conv_fused_fwd": 1, "phc_conv_fused_bwd": 3, "phc_edge_feature_sums": 1, "phc_pna_aggregate_fwd": 1,
-            "phc_pna_aggregate_bwd": 2, "phc_adam_clip_step": 2}
+            "phc_pna_aggregate_bwd": 2, "phc_adam_clip_step": 2, "phc_adam_clip_step_dev": 2, "phc_dropout_epoch_advance": 1}
 
 
 def run(name: str, device, *args, tag: str = "", launches: int = 0):

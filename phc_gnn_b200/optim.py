@@ -36,48 +36,103 @@ def ordered_parameters(model: nn.Module) -> List[nn.Parameter]:
     return rest + out
 
 
-class FlatClipAdam(object):
-    def __init__(self, model_or_params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, max_norm: float = 2.0):
+class FlatClipAdam(torch.optim.Optimizer):
+    """A ``torch.optim.Optimizer`` (lr schedulers such as the scripts' ReduceLROnPlateau / StepLR, train_hiv.py:287, drive it through
+    ``param_groups[0]["lr"]``) whose whole update is two kernel launches on flat buffers.  The learning rate and the step counter
+    live in device memory (``lr_dev``, ``step_dev``), so ``step()`` passes no host scalar that changes between steps and can be
+    recorded into a CUDA graph (graphed.GraphedTrainStep).  Parameters whose ``.grad`` is None contribute a zero gradient (their
+    Adam moments still decay and move them; torch.optim.Adam would skip them) — every parameter of the PHC models gets a gradient
+    each step, see ``strict_grads`` to make a missing one an error."""
+
+    def __init__(self, model_or_params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, max_norm: float = 2.0,
+                 strict_grads: bool = False):
         if isinstance(model_or_params, nn.Module):
-            self.params = ordered_parameters(model_or_params)
+            params = ordered_parameters(model_or_params)
         else:
-            self.params = [p for p in model_or_params if p.requires_grad]
-        self.lr, self.betas, self.eps, self.max_norm = float(lr), betas, float(eps), float(max_norm)
+            params = [p for p in model_or_params if p.requires_grad]
+        super().__init__(params, dict(lr=float(lr), betas=tuple(betas), eps=float(eps), max_norm=float(max_norm)))
+        self.params = params
+        self.lr, self.betas, self.eps, self.max_norm = float(lr), tuple(betas), float(eps), float(max_norm)
+        self.strict_grads = strict_grads
         self.bucket = GradientBucket(self.params)
         self.flat = None
         self.exp_avg = self.exp_avg_sq = None
-        self.t = 0
         self.grad_norm = None
-        self.param_groups = [dict(params=self.params, lr=self.lr)]     # so lr schedulers can drive it
+        self.lr_dev = self.step_dev = None
+        self._lr_uploaded = None
+        self._t_pending = 0             # steps restored by load_state_dict before the device buffers exist
+
+    @property
+    def t(self) -> int:
+        """Number of steps taken (reads the device counter: synchronises)."""
+        return int(self.step_dev.item()) if self.step_dev is not None else self._t_pending
 
     def _ensure(self):
         self.flat = alias_flat(self.flat, self.params)
         if self.exp_avg is None or self.exp_avg.device != self.flat.device:
+            dev = self.flat.device
+            old = (self.exp_avg, self.exp_avg_sq, self.t)
             self.exp_avg = torch.zeros_like(self.flat)
             self.exp_avg_sq = torch.zeros_like(self.flat)
-            self.grad_norm = torch.zeros((), dtype=torch.float32, device=self.flat.device)
-            self._ws = _ws(_lib.load().phc_adam_workspace_bytes(), self.flat.device)
+            if old[0] is not None and old[0].numel() == self.flat.numel():      # moved to another device: keep the state
+                self.exp_avg.copy_(old[0])
+                self.exp_avg_sq.copy_(old[1])
+            self.grad_norm = torch.zeros((), dtype=torch.float32, device=dev)
+            self.lr_dev = torch.zeros((), dtype=torch.float32, device=dev)
+            self.step_dev = torch.full((), old[2], dtype=torch.int32, device=dev)
+            self._lr_uploaded = None
+            self._ws = _ws(_lib.load().phc_adam_workspace_bytes(), dev)
+
+    def sync_lr(self):
+        """Upload the learning rate when a scheduler changed ``param_groups[0]['lr']`` (a device write, no sync)."""
+        lr = float(self.param_groups[0]["lr"])
+        if lr != self._lr_uploaded:
+            self.lr_dev.fill_(lr)
+            self._lr_uploaded = lr
 
     def zero_grad(self, set_to_none: bool = True):
         for p in self.params:
             p.grad = None
 
     def state_dict(self):
-        return dict(t=self.t, exp_avg=self.exp_avg, exp_avg_sq=self.exp_avg_sq, lr=self.param_groups[0]["lr"])
+        return dict(t=self.t, exp_avg=None if self.exp_avg is None else self.exp_avg.detach().clone(),
+                    exp_avg_sq=None if self.exp_avg_sq is None else self.exp_avg_sq.detach().clone(), lr=float(self.param_groups[0]["lr"]),
+                    betas=self.betas, eps=self.eps, max_norm=self.max_norm)
+
+    def load_state_dict(self, state):
+        """Resume: moments, step count and learning rate as ``state_dict()`` wrote them (the flat layout is the order of
+        ``ordered_parameters`` — the same model class gives the same layout)."""
+        self.param_groups[0]["lr"] = float(state["lr"])
+        self.betas, self.eps, self.max_norm = tuple(state.get("betas", self.betas)), float(state.get("eps", self.eps)), float(state.get("max_norm", self.max_norm))
+        if state.get("exp_avg") is None:
+            self._t_pending = int(state["t"])
+            return
+        if next(iter(self.params)).is_cuda:
+            self._ensure()
+            assert state["exp_avg"].numel() == self.flat.numel(), "optimizer state belongs to a different parameter layout"
+            self.exp_avg.copy_(state["exp_avg"])
+            self.exp_avg_sq.copy_(state["exp_avg_sq"])
+            self.step_dev.fill_(int(state["t"]))
+        else:
+            raise RuntimeError("FlatClipAdam.load_state_dict: move the model to its CUDA device first")
 
     @torch.no_grad()
-    def step(self, reduce_group=None, reduce: bool = False):
+    def step(self, closure=None, reduce_group=None, reduce: bool = False):
         """Pack gradients (and all-reduce them when data parallel), clip by global norm, Adam update."""
+        assert closure is None, "FlatClipAdam does not re-evaluate a closure"
         self._ensure()
+        if self.strict_grads:
+            missing = [i for i, p in enumerate(self.params) if p.grad is None]
+            if missing:
+                raise RuntimeError(f"FlatClipAdam(strict_grads=True): {len(missing)} parameters have no gradient")
         if reduce:
             self.bucket.reduce(reduce_group)
             g = self.bucket.flat
         else:
             g = self.bucket.pack()
-        self.t += 1
+        self.sync_lr()
         b1, b2 = self.betas
-        lr = float(self.param_groups[0]["lr"])
         dev = self.flat.device
-        run("phc_adam_clip_step", dev, self.flat.data_ptr(), g.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
-            self.flat.numel(), lr, b1, b2, self.eps, 1.0 - b1 ** self.t, 1.0 - b2 ** self.t, self.max_norm, self.grad_norm.data_ptr(),
-            self._ws.data_ptr(), self._ws.numel(), _stream(dev))
+        run("phc_adam_clip_step_dev", dev, self.flat.data_ptr(), g.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+            self.flat.numel(), self.lr_dev.data_ptr(), b1, b2, self.eps, self.step_dev.data_ptr(), self.max_norm,
+            self.grad_norm.data_ptr(), self._ws.data_ptr(), self._ws.numel(), _stream(dev))

@@ -77,7 +77,10 @@ class GradientBucket(object):
         world = dist.get_world_size(group) if dist.is_initialized() else 1
         if world == 1:
             return None
-        flat.div_(world)
+        if dist.get_backend(group) == "nccl":
+            # ncclAvg: the 1/world factor is applied inside the collective (no separate pass over the buffer)
+            return dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group, async_op=async_op)
+        flat.div_(world)        # gloo (CPU tests) has no AVG
         return dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
 
 
