@@ -81,7 +81,7 @@ struct MixParams {          // y = act(mix GEMM + bias) + residual   (FWD and DX
                             //     M2) for a batch-norm that follows (norm.cu merges them) — the drain owns one column per lane anyway
   float* sk_part;           // v3 stream-K: per-CTA partial accumulators [grid][16 warps][32 rows][64 cols] (NULL: whole units only)
   unsigned int* sk_flags;   // v3 stream-K: [grid][16] "partial written" flags, zero between launches
-  int ablate;               // debug (env PHC_TC_ABLATE): 1 no MMAs | 2 no mixing / tcgen05.st | 4 no activation TMA | 8 no drain | 16 no W TMA
+  int ablate;               // debug (env PHC_TC_ABLATE): 1 no MMAs | 2 no mixing / tcgen05.st | 4 no activation TMA | 8 no drain | 16 no W TMA | 32 math without tcgen05.st | 64 tcgen05.st without the rule FMAs
 };
 
 struct DhParams {           // partial dH tiles
@@ -1057,8 +1057,9 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
         for (int kk = 0; kk < 2; ++kk)
 #pragma unroll
           for (int b = 0; b < NT; ++b) {
-            const float v = cf[b * 4] * xr[0][kp + kk] + cf[b * 4 + 1] * xr[1][kp + kk] + cf[b * 4 + 2] * xr[2][kp + kk] +
-                            cf[b * 4 + 3] * xr[3][kp + kk];
+            const float v = (p.ablate & 64) ? xr[b][kp + kk]
+                                            : cf[b * 4] * xr[0][kp + kk] + cf[b * 4 + 1] * xr[1][kp + kk] + cf[b * 4 + 2] * xr[2][kp + kk] +
+                                                  cf[b * 4 + 3] * xr[3][kp + kk];
             if (SINGLE) {                                        // bf16 operands: round to nearest (ties away) by add + mask
               big[kk * 4 + b] = __uint_as_float((__float_as_uint(v) + 0x8000u) & 0xFFFF0000u);
             } else {
@@ -1066,8 +1067,15 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
               small[kk * 4 + b] = v - big[kk * 4 + b];
             }
           }
-        tmem_st8(a_slot + kp * 4, big);
-        if (!SINGLE) tmem_st8(a_slot + 32 + kp * 4, small);
+        if (p.ablate & 32) {                                     // keep the arithmetic alive without the tensor-memory stores
+          float acc = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc += big[j] + (SINGLE ? 0.f : small[j]);
+          if (acc == 1.2345e-30f) my[lane] = acc;
+        } else {
+          tmem_st8(a_slot + kp * 4, big);
+          if (!SINGLE) tmem_st8(a_slot + 32 + kp * 4, small);
+        }
       }
       }
       tmem_st_wait();

@@ -19,6 +19,8 @@ def _setup(wname, dropout, seed=0):
         wl.model["dropout_mpnn"] = [0.0] * 2
         wl.model["dropout_dn"] = [0.0] * 2
     torch.manual_seed(seed)
+    import numpy as np
+    np.random.seed(seed)                                    # phm_init draws from numpy, like the reference
     model = PHMSkipConnectAdd(**wl.model).to(DEV)
     model.train()
     batches = [make_batch(wl, seed=s).to(DEV) for s in (1, 2, 3)]
