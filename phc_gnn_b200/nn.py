@@ -816,6 +816,15 @@ class _PHMSkipConnectBase(nn.Module):
     def _encode_edges(self, i: int, edge_attr: torch.Tensor) -> torch.Tensor:
         return self.bondencoders[i].flat(edge_attr)
 
+    def _report_stage(self, h: torch.Tensor, k: int) -> None:
+        """Data-parallel overlap (parallel.GradientBucket.enable_overlap): when the gradient of this layer output is complete,
+        every parameter of the layers above it and of the head — stages <= k of optim.staged_parameters — has its final gradient."""
+        cb = self.__dict__.get("_stage_hook")
+        if cb is not None and h.requires_grad:
+            def _hook(_grad, k=k, cb=cb):
+                cb(k)                                        # returns None: the gradient itself is left untouched
+            h.register_hook(_hook)
+
 
 class PHMSkipConnectAdd(_PHMSkipConnectBase):
     """Message-passing network with additive skip connections — reference
@@ -866,14 +875,17 @@ class PHMSkipConnectAdd(_PHMSkipConnectBase):
                     # the whole layer (conv + norm + act + dropout + skip) as one autograd node
                     h = conv.layer_forward(h, skip, edge_index, edge_attr, enc, self.norms[i], self.activation_str.lower(),
                                            self.training, self.dropout_mpnn[i], self.same_dropout)
+                    self._report_stage(h, L - 1 - i)
                     continue
                 # bond encoder fused into the aggregation: the [E,F] edge embedding of models.py:238-240 is never formed
                 z = self.convs[i](h, edge_index, edge_attr, size, encoder=enc)
                 h = norm_act_drop_skip(self.norms[i], z, skip, self.activation_str.lower(), self._n, self.training,
                                        drop_p=self.dropout_mpnn[i], drop_same=self.same_dropout)
+                self._report_stage(h, L - 1 - i)
                 continue
             e = self._encode_edges(i, edge_attr)
             h = self.compute_hidden_layer_embedding(self.convs[i], self.norms[i], [h, skip], edge_index, e, self.dropout_mpnn[i], size)
+            self._report_stage(h, L - 1 - i)
         num_graphs = getattr(data, "num_graphs", None)
         out = self.pooling(h, batch, num_graphs)
         return self.downstream(out)

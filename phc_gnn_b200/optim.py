@@ -21,19 +21,52 @@ from .ops import _ws, run
 from .parallel import GradientBucket
 
 
-def ordered_parameters(model: nn.Module) -> List[nn.Parameter]:
-    """All trainable parameters; the per-component BatchNorm weights (then biases) of every NaivePHMNorm are kept
-    adjacent so that the norm kernels' flat gamma / beta vectors are slices of the optimizer's flat buffer."""
+def _norm_first(module: nn.Module, seen: set) -> List[nn.Parameter]:
+    """Trainable parameters of ``module``: first the per-component BatchNorm weights (then biases) of every NaivePHMNorm inside it,
+    kept adjacent so that the norm kernels' flat gamma / beta vectors are slices of the optimizer's flat buffer, then the rest."""
     from .nn import NaivePHMNorm
-    seen, out = set(), []
-    for m in model.modules():
+    out = []
+    for m in module.modules():
         if isinstance(m, NaivePHMNorm) and m.affine:
             for p in [b.weight for b in m.bn] + [b.bias for b in m.bn]:
                 if id(p) not in seen and p.requires_grad:
                     seen.add(id(p))
                     out.append(p)
-    rest = [p for p in model.parameters() if id(p) not in seen and p.requires_grad]
-    return rest + out
+    for p in module.parameters():
+        if id(p) not in seen and p.requires_grad:
+            seen.add(id(p))
+            out.append(p)
+    return out
+
+
+def staged_parameters(model: nn.Module):
+    """(params, ends): all trainable parameters in the order in which backward COMPLETES their gradients, and the running
+    count after each stage.  For the PHC message-passing models (nn._PHMSkipConnectBase): stage 0 = pooling + downstream head,
+    stage k = message-passing layer L-k (its conv, norm and bond encoder), last stage = layer 0 + the atom encoder.  The model
+    fires ``_stage_hook(k)`` when the gradient of layer L-1-k's output is complete, i.e. when stages <= k are final — which lets
+    parallel.GradientBucket all-reduce them while the layers below still run.  Any other module is a single stage."""
+    root = getattr(model, "module", model)
+    seen: set = set()
+    params: List[nn.Parameter] = []
+    ends: List[int] = []
+    convs, norms, bonds = getattr(root, "convs", None), getattr(root, "norms", None), getattr(root, "bondencoders", None)
+    if isinstance(convs, nn.ModuleList) and hasattr(root, "pooling") and hasattr(root, "downstream") and len(convs) > 0:
+        L = len(convs)
+        params += _norm_first(root.pooling, seen) + _norm_first(root.downstream, seen)
+        ends.append(len(params))
+        for i in range(L - 1, -1, -1):
+            for group in (convs, norms, bonds):
+                if isinstance(group, nn.ModuleList) and i < len(group):
+                    params += _norm_first(group[i], seen)
+            if i > 0:
+                ends.append(len(params))
+    params += _norm_first(root, seen)        # atom encoder and anything not covered above
+    ends.append(len(params))
+    return params, ends
+
+
+def ordered_parameters(model: nn.Module) -> List[nn.Parameter]:
+    return staged_parameters(model)[0]
 
 
 class FlatClipAdam(torch.optim.Optimizer):
@@ -46,15 +79,16 @@ class FlatClipAdam(torch.optim.Optimizer):
 
     def __init__(self, model_or_params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, max_norm: float = 2.0,
                  strict_grads: bool = False):
+        stage_ends = None
         if isinstance(model_or_params, nn.Module):
-            params = ordered_parameters(model_or_params)
+            params, stage_ends = staged_parameters(model_or_params)
         else:
             params = [p for p in model_or_params if p.requires_grad]
         super().__init__(params, dict(lr=float(lr), betas=tuple(betas), eps=float(eps), max_norm=float(max_norm)))
         self.params = params
         self.lr, self.betas, self.eps, self.max_norm = float(lr), tuple(betas), float(eps), float(max_norm)
         self.strict_grads = strict_grads
-        self.bucket = GradientBucket(self.params)
+        self.bucket = GradientBucket(self.params, stage_ends)
         self.flat = None
         self.exp_avg = self.exp_avg_sq = None
         self.grad_norm = None
@@ -126,7 +160,7 @@ class FlatClipAdam(torch.optim.Optimizer):
             if missing:
                 raise RuntimeError(f"FlatClipAdam(strict_grads=True): {len(missing)} parameters have no gradient")
         if reduce:
-            self.bucket.reduce(reduce_group)
+            self.bucket.reduce(reduce_group)          # whatever the overlapped stage reductions have not covered yet, then waits for all
             g = self.bucket.flat
         else:
             g = self.bucket.pack()

@@ -33,31 +33,48 @@ def grad_sink(param) -> Optional[torch.Tensor]:
 
 
 class GradientBucket(object):
-    """Flat fp32 buffer that all gradients are packed into after backward; after ``reduce()`` every
-    ``param.grad`` is a view of the (averaged) flat buffer, so clipping and the optimizer step read
-    the reduced values without a copy back."""
+    """Flat fp32 buffer that all gradients are packed into; after ``reduce()`` every ``param.grad`` is a view of the (averaged)
+    flat buffer, so clipping and the optimizer step read the reduced values without a copy back.
 
-    def __init__(self, params: List[torch.nn.Parameter]):
-        self.params = [p for p in params if p.requires_grad]
+    Overlap with backward: ``params`` is ordered by gradient completion and ``stage_ends`` marks the stages
+    (optim.staged_parameters).  ``enable_overlap(model, group)`` installs the model's ``_stage_hook``; when backward reports stages
+    <= k final, their slice of the buffer is packed and all-reduced asynchronously (NCCL's own stream, ordered after the kernels
+    issued so far) while the layers below keep running; slices smaller than ``min_chunk_bytes`` are merged with the next stage.
+    ``reduce()`` after backward sends the remainder and makes the compute stream wait for everything.  The per-rank values and
+    the reduction order inside each slice are the same as for the single all-reduce, so replicas stay bit-identical."""
+
+    def __init__(self, params: List[torch.nn.Parameter], stage_ends: Optional[List[int]] = None, min_chunk_bytes: int = 1 << 20):
+        keep = [p.requires_grad for p in params]
+        self.params = [p for p, k in zip(params, keep) if k]
+        assert all(keep) or stage_ends is None, "stage boundaries refer to the trainable parameters"
+        self.stage_ends = list(stage_ends) if stage_ends else [len(self.params)]
+        self.min_chunk_bytes = int(min_chunk_bytes)
         self.numel = sum(p.numel() for p in self.params)
         self.flat: Optional[torch.Tensor] = None
         self.views: List[torch.Tensor] = []
+        self.offsets: List[int] = []
+        self.group = None
+        self.overlap = False
+        self._done = 0              # parameters [0, _done) are packed and their all-reduce is in flight
+        self._works = []
+        self.launched = 0           # all-reduce calls of the current step (diagnostics)
 
     def _ensure(self, device):
         if self.flat is None or self.flat.device != device:
             self.flat = torch.zeros(self.numel, dtype=torch.float32, device=device)
-            self.views, off = [], 0
+            self.views, self.offsets, off = [], [], 0
             for p in self.params:
                 self.views.append(self.flat[off:off + p.numel()].view(p.shape))
+                self.offsets.append(off)
                 off += p.numel()
+            self.offsets.append(off)
             for p, v in zip(self.params, self.views):
                 register_grad_sink(p, v)   # layer.py writes this parameter's gradient straight into the flat buffer
 
-    def pack(self):
-        dev = self.params[0].device
-        self._ensure(dev)
+    def _pack_range(self, i0: int, i1: int):
         src, dst = [], []
-        for p, v in zip(self.params, self.views):
+        for i in range(i0, i1):
+            p, v = self.params[i], self.views[i]
             g = p.grad
             if g is v:
                 continue                   # written in place by the layer's backward
@@ -66,22 +83,75 @@ class GradientBucket(object):
             elif g.data_ptr() != v.data_ptr():
                 src.append(g)
                 dst.append(v)
+            p.grad = v
         if src:
             torch._foreach_copy_(dst, src)
-        for p, v in zip(self.params, self.views):
-            p.grad = v
+
+    def pack(self):
+        dev = self.params[0].device
+        self._ensure(dev)
+        self._pack_range(self._done, len(self.params))
         return self.flat
 
-    def reduce(self, group=None, async_op: bool = False):
-        flat = self.pack()
-        world = dist.get_world_size(group) if dist.is_initialized() else 1
-        if world == 1:
+    # ---- overlapped reduction ------------------------------------------------------------------------
+    def enable_overlap(self, model: nn.Module, group=None) -> bool:
+        """Ask ``model`` (the PHC skip-connect models call ``_stage_hook`` from tensor hooks on the layer outputs) to report
+        completed stages.  Returns False — and stays with the single all-reduce — for a model without stages."""
+        root = getattr(model, "module", model)
+        self.group = group
+        if len(self.stage_ends) < 2 or not hasattr(root, "convs"):
+            return False
+        object.__setattr__(root, "_stage_hook", self.stage_ready)
+        self.overlap = True
+        return True
+
+    def _all_reduce(self, i0: int, i1: int, async_op: bool):
+        a, b = self.offsets[i0], self.offsets[i1]
+        if b == a:
             return None
-        if dist.get_backend(group) == "nccl":
+        view = self.flat[a:b]
+        self.launched += 1
+        if dist.get_backend(self.group) == "nccl":
             # ncclAvg: the 1/world factor is applied inside the collective (no separate pass over the buffer)
-            return dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group, async_op=async_op)
-        flat.div_(world)        # gloo (CPU tests) has no AVG
-        return dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+            return dist.all_reduce(view, op=dist.ReduceOp.AVG, group=self.group, async_op=async_op)
+        view.div_(dist.get_world_size(self.group))        # gloo (CPU tests) has no AVG
+        return dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=async_op)
+
+    def stage_ready(self, k: int) -> None:
+        """Backward finished every gradient of stages <= k (called from a tensor hook, on the backward stream)."""
+        if not self.overlap or not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+            return
+        end = self.stage_ends[min(k, len(self.stage_ends) - 1)]
+        if end <= self._done or end >= len(self.params):
+            return                                          # the last stage goes out with reduce()
+        dev = self.params[0].device
+        self._ensure(dev)
+        if (self.offsets[end] - self.offsets[self._done]) * 4 < self.min_chunk_bytes:
+            return                                          # too small for a launch of its own: rides with the next stage
+        self._pack_range(self._done, end)
+        w = self._all_reduce(self._done, end, async_op=True)
+        if w is not None:
+            self._works.append(w)
+        self._done = end
+
+    def reduce(self, group=None, async_op: bool = False):
+        """All-reduce (average) whatever has not been sent yet and wait for every reduction of this step."""
+        if group is not None:
+            self.group = group
+        flat = self.pack()
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        if world > 1:
+            w = self._all_reduce(self._done, len(self.params), async_op=bool(self._works) or async_op)
+            if w is not None:
+                self._works.append(w)
+            if not async_op:
+                for w in self._works:
+                    if w is not None:
+                        w.wait()                            # the compute stream waits for NCCL's stream
+                self._works = []
+        self._done = 0
+        self.launched_last, self.launched = self.launched, 0
+        return flat
 
 
 class DataParallelPHC(nn.Module):
@@ -103,7 +173,8 @@ class DataParallelPHC(nn.Module):
         return self.module(*args, **kwargs)
 
     def reduce_gradients(self, async_op: bool = False):
-        return self.bucket.reduce(self.group, async_op)
+        self.bucket.reduce(self.group, async_op)
+        return None
 
     def __getattr__(self, name):
         try:

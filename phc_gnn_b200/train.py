@@ -63,6 +63,9 @@ class TrainStep(object):
         else:
             self.opt = optimizer if optimizer is not None else make_optimizer(model, workload.lr)
         self.dp = dp                      # DataParallelPHC wrapper or None
+        if dp is not None and self.flat_opt:
+            # gradient slices are all-reduced as backward completes them (head first), overlapping the layers below
+            self.opt.bucket.enable_overlap(model, dp.group)
         # the scripts pick the regulariser by family (train_hiv.py:182: quaternion models have no ``phm_dim``)
         if hasattr(getattr(model, "module", model), "phm_dim"):
             self.regulariser = phm_weight_regularization

@@ -20,18 +20,45 @@ def main():
     from phc_gnn_b200.parallel import DataParallelPHC
     from phc_gnn_b200.synthetic import make_batch, tiny, workloads
     from phc_gnn_b200.train import TrainStep
-    steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+    steps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
     for wname in ("hiv", "ppa"):
-        wl = tiny(workloads(4)[wname], 64, 2, 24, 8, 20, und_edges=40 if wname == "ppa" else None, head=[32, 16])
-        torch.manual_seed(100 + rank)                       # different init per rank: the wrapper's broadcast must fix it
-        model = PHMSkipConnectAdd(**wl.model).to(dev)
-        dp = DataParallelPHC(model)
-        step = TrainStep(model, wl, None, dp)
-        model.train()
-        losses = []
-        for i in range(steps):
-            losses.append(float(step(make_batch(wl, seed=1000 * rank + i).to(dev))))
-        flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+        wl = tiny(workloads(4)[wname], 64, 3, 24, 8, 20, und_edges=40 if wname == "ppa" else None, head=[32, 16])
+        wl.model["dropout_mpnn"] = [0.0] * 3
+        wl.model["dropout_dn"] = [0.0] * 2
+        finals = {}
+        for mode in ("overlap", "single", "graph"):
+            torch.manual_seed(100 + rank)                   # different init per rank: the wrapper's broadcast must fix it
+            import numpy as np
+            np.random.seed(100 + rank)
+            model = PHMSkipConnectAdd(**wl.model).to(dev)
+            dp = DataParallelPHC(model)
+            step = TrainStep(model, wl, None, dp)
+            bucket = step.opt.bucket
+            if mode == "single":
+                bucket.overlap = False                      # one all-reduce after backward
+            else:
+                assert bucket.overlap
+                bucket.min_chunk_bytes = 0                  # tiny model: force one all-reduce per completed stage
+            run = step
+            if mode == "graph":
+                from phc_gnn_b200.graphed import GraphedTrainStep
+                run = GraphedTrainStep(step, capture_after=1)
+            model.train()
+            losses = []
+            for i in range(steps):
+                losses.append(float(run(make_batch(wl, seed=1000 * rank + (i % 2)).to(dev))))
+            if mode == "overlap":
+                assert bucket.launched_last == len(bucket.stage_ends), (bucket.launched_last, bucket.stage_ends)
+            if mode == "single":
+                assert bucket.launched_last == 1
+            if mode == "graph":
+                assert run.stats()["replays"] >= steps - 2, run.stats()
+            finals[mode] = torch.cat([p.detach().reshape(-1) for p in model.parameters()]).clone()
+        # two ranks: (a + b) / 2 is exact and commutative, so slicing the all-reduce cannot change a bit; the replayed graph
+        # runs the same kernels and collectives as the eager overlapped step (dropout is off in these tiny configurations)
+        assert torch.equal(finals["overlap"], finals["single"]) or world != 2, f"{wname}: overlapped != single all-reduce"
+        assert torch.equal(finals["overlap"], finals["graph"]), f"{wname}: graph replay != eager"
+        flat = finals["graph"]
         moments = torch.cat([step.opt.exp_avg, step.opt.exp_avg_sq])
         for name, t in (("parameters", flat), ("adam moments", moments)):
             gathered = [torch.empty_like(t) for _ in range(world)]

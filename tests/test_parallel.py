@@ -136,3 +136,85 @@ def test_sharded_epoch_equals_global_batches_gloo():
             assert torch.equal(x, y)
             torch.testing.assert_close(x, p.grad, rtol=1e-5, atol=1e-6)
     assert len(set(seen)) == 40
+
+
+class _StagedToy(torch.nn.Module):
+    """Stand-in with the layout optim.staged_parameters understands (convs / norms / pooling / downstream) and the
+    ``_report_stage`` protocol of the PHC models: a tensor hook on every layer output reports completed stages."""
+
+    def __init__(self, L=3, F=5):
+        super().__init__()
+        self.enc = torch.nn.Linear(4, F)
+        self.convs = torch.nn.ModuleList([torch.nn.Linear(F, F) for _ in range(L)])
+        self.norms = torch.nn.ModuleList([torch.nn.LayerNorm(F) for _ in range(L)])
+        self.pooling = torch.nn.Linear(F, F)
+        self.downstream = torch.nn.Linear(F, 2)
+
+    def forward(self, x):
+        h0 = self.enc(x)
+        h = h0
+        L = len(self.convs)
+        for i in range(L):
+            h = torch.relu(self.norms[i](self.convs[i](h))) + h0          # "first" skip: h0 feeds every layer
+            cb = self.__dict__.get("_stage_hook")
+            if cb is not None and h.requires_grad:
+                def _hook(_g, k=L - 1 - i, cb=cb):
+                    cb(k)
+                h.register_hook(_hook)
+        return self.downstream(self.pooling(h).mean(0, keepdim=True))
+
+
+def _staged_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from phc_gnn_b200.optim import staged_parameters
+        from phc_gnn_b200.parallel import GradientBucket
+        torch.manual_seed(3)
+        model = _StagedToy()
+        params, ends = staged_parameters(model)
+        assert len(ends) == 4 and ends[-1] == len(params) == len(list(model.parameters()))
+        # stage 0 = head, then layers 2, 1, and (layer 0 + encoder) last
+        assert {id(p) for p in params[:ends[0]]} == {id(p) for m in (model.pooling, model.downstream) for p in m.parameters()}
+        assert {id(p) for p in params[ends[2]:]} == {id(p) for m in (model.convs[0], model.norms[0], model.enc) for p in m.parameters()}
+        bucket = GradientBucket(params, ends, min_chunk_bytes=0)
+        assert bucket.enable_overlap(model, None)
+        torch.manual_seed(10 + rank)
+        x = torch.randn(6, 4)
+        calls = []
+        orig = bucket.stage_ready
+        object.__setattr__(model, "_stage_hook", lambda k: (calls.append((k, bucket._done)), orig(k)))
+        bucket.overlap = False                              # hooks fire but send nothing: the plain local gradients
+        model(x).square().sum().backward()
+        local = [p.grad.detach().clone() for p in params]
+        calls.clear()
+        bucket.overlap = True                               # the same backward with the overlapped reduction live
+        for p in params:
+            p.grad = None
+        model(x).square().sum().backward()
+        in_flight = bucket._done
+        bucket.reduce()
+        out[rank] = dict(local=local, reduced=[p.grad.detach().clone() for p in params], calls=calls, in_flight=in_flight,
+                         launched=bucket.launched_last, ends=ends)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_staged_overlapped_allreduce_gloo():
+    """GradientBucket with stages: slices go out as backward reports them (head first), the remainder with reduce(); the
+    result is the plain average and identical on both ranks."""
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_staged_worker, args=(world, port, out), nprocs=world, join=True)
+    a, b = out[0], out[1]
+    assert [k for k, _ in a["calls"]][:3] == [0, 1, 2] or [k for k, _ in a["calls"]][-3:] == [0, 1, 2]
+    assert a["in_flight"] == a["ends"][2]                  # three stages were sent during backward, the last one by reduce()
+    assert a["launched"] == 4
+    for ga, gb, ra, rb in zip(a["local"], b["local"], a["reduced"], b["reduced"]):
+        torch.testing.assert_close(ra, (ga + gb) / 2)
+        assert torch.equal(ra, rb)

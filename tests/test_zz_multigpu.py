@@ -24,7 +24,7 @@ def _free_port():
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
 def test_replicas_stay_bit_identical_over_nccl():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "multigpu_worker.py"), "3"]
+           "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "multigpu_worker.py"), "5"]
     proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-4000:]
     assert "MULTIGPU_OK 2" in proc.stdout
