@@ -42,9 +42,11 @@ def parse():
                     help="quaternion: the reference's QuaternionSkipConnectAdd on the same kernels (n = 4, frozen Hamilton rule)")
     ap.add_argument("--batches", type=int, default=8, help="distinct synthetic batches cycled per rank")
     ap.add_argument("--precision", default=None, help="fp32 | tf32x3 | bf16 (default: PHC_PRECISION or tf32x3)")
-    ap.add_argument("--graph", default="on", choices=["on", "off"],
-                    help="on: the whole step (forward, loss, backward, all-reduce, clip + Adam) is replayed from one CUDA graph per batch "
-                         "shape (phc_gnn_b200/graphed.py); off: eager host path")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="on: the step is replayed from one CUDA graph per batch shape (phc_gnn_b200/graphed.py; data parallel: the "
+                         "all-reduce and the optimizer kernels stay eager between graph launches); off: eager host path with the "
+                         "sliced, overlapped all-reduce; auto: graph where replay measured a gain (nodes x width per batch < 7.5e6: "
+                         "hiv, zinc, mnist, cifar 1.7-2.8x, pcba 1.13x), eager for ppa (kernel-bound: replay 5.13 vs eager 5.09 ms)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--kernel-timers", action="store_true", help="also print the per-op CUDA-event breakdown to stderr")
@@ -372,7 +374,11 @@ def run_b200(args):
         model = PHMSkipConnectAdd(**wl.model).to(dev)
     dp = DataParallelPHC(model) if world > 1 else None
     step = TrainStep(model, wl, None, dp)        # flat clip+Adam (optim.FlatClipAdam): same update rule, 2 launches
-    if args.graph == "on":
+    use_graph = args.graph == "on"
+    if args.graph == "auto":
+        probe = make_batch(wl, seed=0)
+        use_graph = probe.num_nodes * wl.model["mp_layers"][0] < 7.5e6
+    if use_graph:
         from phc_gnn_b200.graphed import GraphedTrainStep
         step = GraphedTrainStep(step, max_graphs=2 * args.batches + 4)
     model.train()
@@ -601,7 +607,7 @@ def run_b200(args):
                "data": "synthetic",
                "config": config_dict(args, wl, wl.batch_graphs, "flushed between steps" if flush else "inputs larger than L2"),
                "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "roofline_aggregation": agg,
-               "preroll_steps": preroll, "cuda_graph": step.stats() if args.graph == "on" else None,
+               "preroll_steps": preroll, "cuda_graph": step.stats() if use_graph else None,
                "ms_per_step_instrumented": ms_instr / args.steps,
                "op_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in breakdown.items()},
                "final_loss": float(loss.item())}

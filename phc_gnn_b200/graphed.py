@@ -12,7 +12,11 @@ What makes the step replayable (nothing the host passes by value may change betw
   * Adam's step counter and learning rate live in device memory (``phc_adam_clip_step_dev``);
   * dropout masks are keyed by seed + a device-resident epoch word that the graph advances at its top
     (``phc_dropout_epoch_register`` / ``_advance``), so every replay draws fresh masks;
-  * gradients are written in place into the flat gradient buffer (layer._ConvLayerDirect), which NCCL all-reduces inside the graph.
+  * gradients are written in place into the flat gradient buffer (layer._ConvLayerDirect).
+Data parallel (world size > 1): the graph holds zero_grad .. backward + the gradient pack; the all-reduce of the flat buffer stays ONE
+eager NCCL call between the graph launch and the two optimizer kernels (recording NCCL collectives issued from autograd-hook threads
+into a capture hung in testing, and the launch-bound workloads this path exists for have < 2 MB of gradients — nothing to overlap).
+The overlapped, sliced all-reduce of parallel.GradientBucket belongs to the eager step, which is what large batches (ppa) run.
 
 A graph is specific to (N, E, B) and the feature widths.  A shape is captured when it is seen for the ``capture_after``-th time
 (default: the second), at most ``max_graphs`` shapes are kept; every other call runs the eager step.  Training over a fixed set
@@ -54,6 +58,9 @@ class GraphedTrainStep(object):
         """``step``: a train.TrainStep built with the flat optimizer (optimizer=None)."""
         assert step.flat_opt, "GraphedTrainStep needs the flat clip+Adam optimizer (its step counter lives on the device)"
         self.step = step
+        self.split = step.dp is not None                    # data parallel: collective + optimizer stay outside the graph
+        if self.split:
+            step.opt.bucket.overlap = False                 # one all-reduce after the graph; no NCCL calls from backward hooks
         self.max_graphs, self.capture_after = int(max_graphs), int(capture_after)
         self.entries: "OrderedDict[tuple, _Entry]" = OrderedDict()
         self.seen = {}
@@ -83,6 +90,8 @@ class GraphedTrainStep(object):
         self.step.opt.sync_lr()
         ent.graph.replay()
         PROFILE.launches += ent.launches
+        if self.split:
+            self.step.optimizer_step()
         self.replays += 1
         return ent.loss
 
@@ -107,7 +116,11 @@ class GraphedTrainStep(object):
             ep = dropout_epoch(dev)
             run("phc_dropout_epoch_advance", None, ep.data_ptr(), _stream(dev))
             graph.clear_cache()                             # the CSR / segment build is part of every step
-            ent.loss = self.step(static)
+            if self.split:
+                ent.loss = self.step.forward_backward(static)
+                self.step.opt.bucket.pack()                 # every gradient in its slice of the flat buffer, inside the graph
+            else:
+                ent.loss = self.step(static)
         ent.launches = PROFILE.launches - before
         PROFILE.launches = before
         graph.clear_cache()                                 # structures built during capture live in the graph's pool

@@ -56,7 +56,7 @@ def staged_parameters(model: nn.Module):
         ends.append(len(params))
         for i in range(L - 1, -1, -1):
             for group in (convs, norms, bonds):
-                if isinstance(group, nn.ModuleList) and i < len(group):
+                if isinstance(group, nn.ModuleList) and i < len(group) and isinstance(group[i], nn.Module):
                     params += _norm_first(group[i], seen)
             if i > 0:
                 ends.append(len(params))

@@ -74,7 +74,9 @@ class TrainStep(object):
             self.regulariser = quaternion_weight_regularization
         self.params = [p for p in model.parameters()]
 
-    def __call__(self, data) -> torch.Tensor:
+    def forward_backward(self, data) -> torch.Tensor:
+        """zero_grad -> forward -> loss + regulariser -> backward (no collective, no optimizer): the part graphed.GraphedTrainStep
+        records when the job is data parallel (the all-reduce stays an eager NCCL call between two graph launches)."""
         wl = self.wl
         self.opt.zero_grad()
         logits = self.model(data)
@@ -82,9 +84,24 @@ class TrainStep(object):
         if wl.weight_decay > 0.0:
             loss = loss + wl.lr * wl.weight_decay * self.regulariser(self.model, p=2)
         loss.backward()
+        return loss.detach()
+
+    def optimizer_step(self) -> None:
+        """[all-reduce] -> clip -> Adam on the flat buffers (flat optimizer only)."""
+        self.opt.step(reduce=self.dp is not None, reduce_group=self.dp.group if self.dp is not None else None)
+
+    def __call__(self, data) -> torch.Tensor:
+        wl = self.wl
         if self.flat_opt:
-            self.opt.step(reduce=self.dp is not None, reduce_group=self.dp.group if self.dp is not None else None)
-            return loss.detach()
+            loss = self.forward_backward(data)
+            self.optimizer_step()
+            return loss
+        self.opt.zero_grad()
+        logits = self.model(data)
+        loss = task_loss(logits, data.y, wl.loss)
+        if wl.weight_decay > 0.0:
+            loss = loss + wl.lr * wl.weight_decay * self.regulariser(self.model, p=2)
+        loss.backward()
         if self.dp is not None:
             self.dp.reduce_gradients()
         if wl.grad_clip > 0.0:
