@@ -47,6 +47,8 @@ def parse():
                          "all-reduce and the optimizer kernels stay eager between graph launches); off: eager host path with the "
                          "sliced, overlapped all-reduce; auto: graph where replay measured a gain (nodes x width per batch < 7.5e6: "
                          "hiv, zinc, mnist, cifar 1.7-2.8x, pcba 1.13x), eager for ppa (kernel-bound: replay 5.13 vs eager 5.09 ms)")
+    ap.add_argument("--sharding", default="balanced", choices=["balanced", "random"],
+                    help="N > 1: how the graphs of a global batch are dealt to the ranks (balanced: by node count, prep.balanced_partition)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--kernel-timers", action="store_true", help="also print the per-op CUDA-event breakdown to stderr")
@@ -308,6 +310,7 @@ def config_dict(args, wl, graphs_per_gpu, l2):
                         f"{len(m['mp_layers'])}x{m['mp_layers'][0]}, aggr={m['msg_aggr']}, mlp={m['mlp']})",
             "graphs_per_gpu_batch": graphs_per_gpu, "phm_dim": m["phm_dim"], "width": m["mp_layers"][0],
             "layers": len(m["mp_layers"]), "aggr": m["msg_aggr"], "parallelism": f"dp{args.gpus}", "l2": l2,
+            **({"sharding": getattr(args, "sharding", "balanced")} if args.gpus > 1 else {}),
             **({"family": "quaternion"} if getattr(args, "family", "phm") == "quaternion" else {})}
 
 
@@ -383,7 +386,18 @@ def run_b200(args):
         step = GraphedTrainStep(step, max_graphs=2 * args.batches + 4)
     model.train()
 
-    host = [make_batch(wl, seed=rank * 1000 + i).pin_memory() for i in range(args.batches)]
+    if world > 1 and args.sharding == "balanced":
+        # every global batch (world x B graphs, sizes drawn from one seed all ranks share) is dealt to the ranks by node count
+        # (prep.balanced_partition): same graphs per rank, nearly equal nodes per rank -> no straggler wait in the synchronous step
+        from phc_gnn_b200.prep import balanced_partition
+        from phc_gnn_b200.synthetic import graph_sizes
+        host = []
+        for i in range(args.batches):
+            gs = graph_sizes(wl, 7000 + i, world * wl.batch_graphs)
+            mine = gs[balanced_partition(gs, world)[rank]]
+            host.append(make_batch(wl, seed=rank * 1000 + i, sizes=mine).pin_memory())
+    else:
+        host = [make_batch(wl, seed=rank * 1000 + i).pin_memory() for i in range(args.batches)]
     devb = [b.to(dev) for b in host]
     ws_bytes = sum(b.num_edges for b in host) / len(host) * wl.model["mp_layers"][0] * 4
     flush = ws_bytes < 256e6          # per-layer edge tensor smaller than 2x L2 -> flush L2 between steps

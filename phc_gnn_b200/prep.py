@@ -190,6 +190,21 @@ class DeviceGraphStore(object):
             raise RuntimeError("phc_collate_batch: size prefix sums do not match the selected graphs")
 
 
+def balanced_partition(costs, world: int) -> list:
+    """Split the items of one global batch between ``world`` ranks so that every rank gets the same NUMBER of items (+-1) and
+    nearly the same total cost (node or edge count): items sorted by cost, dealt out in serpentine order.  A synchronous
+    data-parallel step ends when the slowest rank does, so equalising the per-rank node counts removes the straggler wait
+    without changing which graphs form the global batch.  Returns ``world`` index arrays (positions into ``costs``), each in
+    ascending position order.  Pure host logic."""
+    costs = np.asarray(costs)
+    order = np.argsort(-costs, kind="stable")
+    parts = [[] for _ in range(world)]
+    for j, idx in enumerate(order):
+        r = j % (2 * world)
+        parts[r if r < world else 2 * world - 1 - r].append(int(idx))
+    return [np.sort(np.asarray(p, dtype=np.int64)) for p in parts]
+
+
 class EpochSampler(object):
     """Graph ids of one rank's mini-batches for one epoch: a seeded permutation of the dataset (``shuffle=True``, the
     scripts' training loaders, benchmarks/train_hiv.py:488-489) cut into global batches of ``world * batch_graphs`` graphs, of
@@ -198,10 +213,14 @@ class EpochSampler(object):
     Pure host logic (numpy): data parallelism shards by graph, no collective is involved."""
 
     def __init__(self, num_graphs: int, batch_graphs: int, rank: int = 0, world: int = 1, seed: int = 0, shuffle: bool = True,
-                 drop_last: bool = False):
+                 drop_last: bool = False, costs=None):
+        """costs (optional, one number per graph, e.g. its node count): the graphs of every global batch are dealt to the ranks by
+        ``balanced_partition`` instead of in contiguous slices, so that all ranks get nearly equal work."""
         assert num_graphs > 0 and batch_graphs > 0 and 0 <= rank < world
         self.num_graphs, self.batch_graphs, self.rank, self.world = int(num_graphs), int(batch_graphs), int(rank), int(world)
         self.seed, self.shuffle, self.drop_last = int(seed), bool(shuffle), bool(drop_last)
+        self.costs = None if costs is None else np.asarray(costs)
+        assert self.costs is None or len(self.costs) == self.num_graphs
         self.epoch = 0
 
     def set_epoch(self, epoch: int) -> None:
@@ -222,6 +241,9 @@ class EpochSampler(object):
 
     def __iter__(self):
         for chunk in self._global_batches():
+            if self.costs is not None and self.world > 1:
+                yield np.ascontiguousarray(chunk[balanced_partition(self.costs[chunk], self.world)[self.rank]]).astype(np.int64)
+                continue
             per = len(chunk) // self.world                   # == batch_graphs except for a short last batch
             extra = len(chunk) - per * self.world            # the first ``extra`` ranks take one more graph
             lo = self.rank * per + min(self.rank, extra)

@@ -122,10 +122,17 @@ def _symmetrise(und: np.ndarray) -> np.ndarray:
     return ei
 
 
-def make_batch(wl: Workload, seed: int = 0, batch_graphs: Optional[int] = None) -> GraphBatch:
+def graph_sizes(wl: Workload, seed: int, count: int) -> np.ndarray:
+    """Node counts of ``count`` synthetic graphs (the first draw make_batch makes from the same seed)."""
+    return np.random.default_rng(seed).integers(wl.nodes_lo, wl.nodes_hi + 1, count)
+
+
+def make_batch(wl: Workload, seed: int = 0, batch_graphs: Optional[int] = None, sizes=None) -> GraphBatch:
+    """sizes (optional): node count of every graph of the batch (e.g. one rank's share of a size-balanced global batch)."""
     rng = np.random.default_rng(seed)
-    B = wl.batch_graphs if batch_graphs is None else batch_graphs
-    sizes = rng.integers(wl.nodes_lo, wl.nodes_hi + 1, B)
+    B = (wl.batch_graphs if batch_graphs is None else batch_graphs) if sizes is None else len(sizes)
+    drawn = rng.integers(wl.nodes_lo, wl.nodes_hi + 1, B)
+    sizes = drawn if sizes is None else np.asarray(sizes, dtype=drawn.dtype)
     xs, eis, eas, bs = [], [], [], []
     off = 0
     ex = wl.extra
