@@ -8,7 +8,7 @@
 //   perm   = stable_argsort(key)           (edge ids, ascending inside every row)
 //   col    = other_end[perm]
 //   rowptr = exclusive_cumsum(bincount(key))
-// Algorithm: integer histogram (atomics on ints are order-independent) -> single-block scan ->
+// Algorithm: integer histogram (atomics on ints are order-independent) -> tiled single-block scan ->
 // ticket scatter (arbitrary order inside a row) -> per-row sort by edge id (restores the unique
 // stable order).  No floating point is involved, so the result is deterministic.
 #include "common.cuh"
@@ -28,35 +28,60 @@ __global__ void hist_kernel(const long long* __restrict__ ei, int E, int N, int*
 }
 
 // One block per key array (blockIdx.x = 0: target keys, 1: source keys). Exclusive scan of cnt[0..N)
-// into rowptr[0..N] and a copy into cursor[0..N) for the ticket scatter.
+// into rowptr[0..N] and a copy into cursor[0..N) for the ticket scatter.  The block walks the array in tiles of 4096 counts with
+// a running carry: coalesced loads (4 consecutive counts per thread), warp-shuffle scans, one 32-entry scan of the warp totals
+// per tile (the first version gave each thread one contiguous chunk — uncoalesced — and ran a 10-round Hillis-Steele scan over
+// 1024 partials: 24 us at N = 15.6k, ppa; now ~5 us).
 __global__ void __launch_bounds__(1024) scan_kernel(const int* __restrict__ cnt_all, int N, int* __restrict__ rowptr_dst,
                                                     int* __restrict__ rowptr_src, int* __restrict__ cursor_all) {
   pdl_begin();
   const int* cnt = cnt_all + (size_t)blockIdx.x * N;
   int* rowptr = blockIdx.x == 0 ? rowptr_dst : rowptr_src;
   int* cursor = cursor_all + (size_t)blockIdx.x * N;
-  __shared__ int part[1024];
-  int t = threadIdx.x;
-  int chunk = (N + 1023) / 1024;
-  int lo = min(t * chunk, N), hi = min(lo + chunk, N);
-  int s = 0;
-  for (int i = lo; i < hi; ++i) s += cnt[i];
-  part[t] = s;
+  __shared__ int warp_tot[32];
+  __shared__ int carry_s;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  if (t == 0) carry_s = 0;
   __syncthreads();
-  // Hillis-Steele inclusive scan over 1024 partials
-  for (int off = 1; off < 1024; off <<= 1) {
-    int v = t >= off ? part[t - off] : 0;
+  for (int base = 0; base < N; base += 4096) {
+    const int i0 = base + t * 4;
+    int v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = (i0 + j < N) ? cnt[i0 + j] : 0;
+    const int mine = v[0] + v[1] + v[2] + v[3];
+    int inc = mine;                                            // inclusive scan of the thread totals inside the warp
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int n = __shfl_up_sync(0xffffffffu, inc, off);
+      if (lane >= off) inc += n;
+    }
+    if (lane == 31) warp_tot[w] = inc;
     __syncthreads();
-    part[t] += v;
+    if (w == 0) {                                              // scan of the 32 warp totals
+      int x = warp_tot[lane];
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, x, off);
+        if (lane >= off) x += n;
+      }
+      warp_tot[lane] = x;                                      // inclusive
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    int run = carry + (w > 0 ? warp_tot[w - 1] : 0) + inc - mine;     // exclusive prefix of this thread's first count
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (i0 + j < N) {
+        rowptr[i0 + j] = run;
+        cursor[i0 + j] = run;
+      }
+      run += v[j];
+    }
+    __syncthreads();                                           // everyone has read carry_s and warp_tot
+    if (t == 1023) carry_s = carry + warp_tot[31];
     __syncthreads();
   }
-  int run = part[t] - s;  // exclusive prefix of this thread's chunk
-  for (int i = lo; i < hi; ++i) {
-    rowptr[i] = run;
-    cursor[i] = run;
-    run += cnt[i];
-  }
-  if (t == 1023) rowptr[N] = part[1023];
+  if (t == 0) rowptr[N] = carry_s;
 }
 
 __global__ void ticket_kernel(const long long* __restrict__ ei, int E, int N, int* __restrict__ cursor_all,

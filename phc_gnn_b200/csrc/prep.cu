@@ -226,25 +226,43 @@ struct CollateRows {
   long long row_bytes;        // multiple of 4; 0 = tensor absent
 };
 
-template <typename Word>
-__device__ __forceinline__ void collate_copy_words(const char* src, char* dst, long long bytes, long long tid, long long nth) {
-  const Word* s = reinterpret_cast<const Word*>(src);
-  Word* d = reinterpret_cast<Word*>(dst);
-  const long long n = bytes / (long long)sizeof(Word);
-  for (long long j = tid; j < n; j += nth) d[j] = s[j];
+// One contiguous segment (a multiple of 4 bytes, both ends 4-byte aligned) with 16-byte STORES whatever the relative phase of source
+// and destination: 28-byte edge_attr rows put a graph's segment at any multiple of 4 bytes in both tensors, which used to force
+// 4-byte words (28 % of the HBM peak at ppa size).  Destination words are written as aligned uint4; each is assembled from the two
+// aligned source uint4 that cover it (the second one is the neighbour thread's first: an L1 hit), selected by the word shift k.
+__device__ __forceinline__ void collate_copy_shifted(const char* src, char* dst, long long bytes, long long tid, long long nth) {
+  const unsigned int* sw = reinterpret_cast<const unsigned int*>(src);
+  unsigned int* dw = reinterpret_cast<unsigned int*>(dst);
+  long long head = (long long)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15) >> 2;      // words until dst is 16-byte aligned
+  const long long words = bytes >> 2;
+  if (head > words) head = words;
+  for (long long j = tid; j < head; j += nth) dw[j] = sw[j];
+  const long long n16 = (words - head) >> 2;
+  const int k = (int)((reinterpret_cast<uintptr_t>(sw + head) & 15) >> 2);                       // source phase, in words
+  uint4* d4 = reinterpret_cast<uint4*>(dw + head);
+  const uint4* s4 = reinterpret_cast<const uint4*>(sw + head - k);                                // aligned down
+  // the last destination uint4 would need source words beyond the segment when k != 0: it goes with the scalar tail
+  const long long fast = k == 0 ? n16 : (n16 > 0 ? n16 - 1 : 0);
+  if (k == 0) {
+    for (long long j = tid; j < fast; j += nth) d4[j] = s4[j];
+  } else {
+    for (long long j = tid; j < fast; j += nth) {
+      const uint4 a = s4[j], b = s4[j + 1];
+      uint4 r;
+      if (k == 1) r = make_uint4(a.y, a.z, a.w, b.x);
+      else if (k == 2) r = make_uint4(a.z, a.w, b.x, b.y);
+      else r = make_uint4(a.w, b.x, b.y, b.z);
+      d4[j] = r;
+    }
+  }
+  for (long long j = head + 4 * fast + tid; j < words; j += nth) dw[j] = sw[j];
 }
 
-// rows [first, first+count) of the store -> rows [out_first, ...) of the batch; widest word the row size allows (the
-// tensors come from the torch allocator, 256-byte aligned, so a segment offset is aligned to gcd(row_bytes, 16))
+// rows [first, first+count) of the store -> rows [out_first, ...) of the batch
 __device__ __forceinline__ void collate_copy_rows(const CollateRows& r, long long first, long long count, long long out_first,
                                                   long long tid, long long nth) {
   if (r.row_bytes == 0 || count <= 0) return;
-  const char* src = r.src + first * r.row_bytes;
-  char* dst = r.dst + out_first * r.row_bytes;
-  const long long bytes = count * r.row_bytes;
-  if (r.row_bytes % 16 == 0) collate_copy_words<uint4>(src, dst, bytes, tid, nth);
-  else if (r.row_bytes % 8 == 0) collate_copy_words<unsigned long long>(src, dst, bytes, tid, nth);
-  else collate_copy_words<unsigned int>(src, dst, bytes, tid, nth);
+  collate_copy_shifted(r.src + first * r.row_bytes, r.dst + out_first * r.row_bytes, count * r.row_bytes, tid, nth);
 }
 
 // grid = (slices, B): blockIdx.y = position of the graph in the batch, the slices of one row of blocks share its elements
@@ -273,9 +291,22 @@ __global__ void __launch_bounds__(256) collate_kernel(const long long* __restric
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long nth = (long long)gridDim.x * blockDim.x;
   for (long long j = tid; j < nn; j += nth) out_batch[on0 + j] = b;
-  for (long long j = tid; j < ne; j += nth) {
-    out_ei[oe0 + j] = ei[e0 + j] + on0;
-    out_ei[out_edges + oe0 + j] = ei[store_edges + e0 + j] + on0;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {               // sources, then targets
+    const long long* s = ei + half * store_edges + e0;
+    long long* d = out_ei + half * out_edges + oe0;
+    if (((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d)) & 15) == 0) {
+      const longlong2* s2 = reinterpret_cast<const longlong2*>(s);
+      longlong2* d2 = reinterpret_cast<longlong2*>(d);
+      for (long long j = tid; j < (ne >> 1); j += nth) {
+        longlong2 v = s2[j];
+        v.x += on0; v.y += on0;
+        d2[j] = v;
+      }
+      if ((ne & 1) && tid == 0) d[ne - 1] = s[ne - 1] + on0;
+    } else {
+      for (long long j = tid; j < ne; j += nth) d[j] = s[j] + on0;
+    }
   }
   collate_copy_rows(xr, n0, nn, on0, tid, nth);
   collate_copy_rows(er, e0, ne, oe0, tid, nth);

@@ -924,8 +924,14 @@ class PHMSkipConnectConcat(_PHMSkipConnectBase):
         act = self.activation_str.lower()
         for i in range(len(self.mp_layers)):
             skip = h0                                 # the reference concatenates the atom embedding whatever sc_type says (:479-481)
-            e = self._encode_edges(i, edge_attr)
-            z = self.convs[i](x=h, edge_index=edge_index, edge_attr=e, size=size)
+            enc = self.bondencoders[i]
+            pna = isinstance(self.convs[i].transform, PHMPNAConvSimple)       # PNA reads the materialised edge embedding
+            if self.fuse_edge_encoder and not pna and isinstance(enc, PHMEncoder) and enc.can_fuse(h.size(1)):
+                # bond encoder fused into the aggregation (any layer width, F_i + F_0 included): the [E, F] edge embedding of
+                # models.py:486-488 is never formed
+                z = self.convs[i](h, edge_index, edge_attr, size, encoder=enc)
+            else:
+                z = self.convs[i](x=h, edge_index=edge_index, edge_attr=self._encode_edges(i, edge_attr), size=size)
             z = norm_act_drop_skip(self.norms[i], z, None, act, self._n, self.training, drop_p=self.dropout_mpnn[i],
                                    drop_same=self.same_dropout)
             h = self._skip_concat(z, skip)

@@ -50,10 +50,21 @@ _KERNELS = {"phc_csr_build": 6, "phc_segment_ptr_build": 2, "phc_aggregate_fwd":
             "phc_pna_aggregate_bwd": 2, "phc_adam_clip_step": 2, "phc_adam_clip_step_dev": 2, "phc_dropout_epoch_advance": 1}
 
 
+NVTX = os.environ.get("PHC_NVTX", "") not in ("", "0")     # PHC_NVTX=1: an NVTX range around every C-ABI call (nsys / ncu --nvtx)
+
+
 def run(name: str, device, *args, tag: str = "", launches: int = 0):
     """Invoke C-ABI entry ``name`` on torch's current stream; raises on a non-zero status."""
     fn = getattr(_lib.load(), name)
     PROFILE.launches += launches or _KERNELS.get(name, 1)
+    if NVTX:
+        torch.cuda.nvtx.range_push(name + tag)
+        try:
+            rc = fn(*args)
+        finally:
+            torch.cuda.nvtx.range_pop()
+        _lib.check(rc, name)
+        return
     if PROFILE.timing:
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()

@@ -58,6 +58,7 @@ class GradientBucket(object):
         self._done = 0              # parameters [0, _done) are packed and their all-reduce is in flight
         self._works = []
         self.launched = 0           # all-reduce calls of the current step (diagnostics)
+        self.local_weight = 1.0     # this rank's share of the global batch relative to an even split (see set_batch_share)
 
     def _ensure(self, device):
         if self.flat is None or self.flat.device != device:
@@ -105,11 +106,19 @@ class GradientBucket(object):
         self.overlap = True
         return True
 
+    def set_batch_share(self, local_graphs: int, global_graphs: int, world: int) -> None:
+        """Uneven shards (a short last global batch gives some ranks one graph more): every rank's mean-loss gradient is
+        weighted by local_graphs * world / global_graphs before the average, so that the reduced gradient is the gradient of
+        the mean over the GLOBAL batch, not a mean of per-rank means.  An even split has weight 1 (no extra pass)."""
+        self.local_weight = float(local_graphs) * float(world) / float(global_graphs)
+
     def _all_reduce(self, i0: int, i1: int, async_op: bool):
         a, b = self.offsets[i0], self.offsets[i1]
         if b == a:
             return None
         view = self.flat[a:b]
+        if self.local_weight != 1.0:
+            view.mul_(self.local_weight)
         self.launched += 1
         if dist.get_backend(self.group) == "nccl":
             # ncclAvg: the 1/world factor is applied inside the collective (no separate pass over the buffer)

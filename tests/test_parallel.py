@@ -218,3 +218,39 @@ def test_staged_overlapped_allreduce_gloo():
     for ga, gb, ra, rb in zip(a["local"], b["local"], a["reduced"], b["reduced"]):
         torch.testing.assert_close(ra, (ga + gb) / 2)
         assert torch.equal(ra, rb)
+
+
+def _uneven_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from phc_gnn_b200.parallel import DataParallelPHC
+        torch.manual_seed(0)
+        feats, target = torch.randn(5, 6), torch.randn(5, 1)
+        model = torch.nn.Linear(6, 1)
+        dp = DataParallelPHC(model)
+        idx = torch.tensor([0, 1, 2]) if rank == 0 else torch.tensor([3, 4])          # a short last batch: 3 + 2 graphs
+        ((dp(feats[idx]) - target[idx]) ** 2).mean().backward()
+        dp.bucket.set_batch_share(len(idx), 5, world)
+        dp.reduce_gradients()
+        out[rank] = [p.grad.detach().clone() for p in model.parameters()]
+    finally:
+        dist.destroy_process_group()
+
+
+def test_uneven_shards_reduce_to_the_global_batch_gradient_gloo():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_uneven_worker, args=(world, port, out), nprocs=world, join=True)
+    torch.manual_seed(0)
+    feats, target = torch.randn(5, 6), torch.randn(5, 1)
+    model = torch.nn.Linear(6, 1)
+    ((model(feats) - target) ** 2).mean().backward()
+    for p, a, b in zip(model.parameters(), out[0], out[1]):
+        assert torch.equal(a, b)
+        torch.testing.assert_close(a, p.grad, rtol=1e-5, atol=1e-6)
