@@ -14,6 +14,8 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 wl = workloads(4)[name]
 if len(sys.argv) > 3:               # fewer graphs per batch: the GPU work shrinks, the step time approaches the pure host cost
     wl.batch_graphs = int(sys.argv[3])
+if os.environ.get("STEP_AGGR"):   # e.g. STEP_AGGR=max: the workload with another aggregator (run_script_ppa_phm4.sh alternates sum / max)
+    wl.model["msg_aggr"] = os.environ["STEP_AGGR"]
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 model = PHMSkipConnectAdd(**wl.model).to(dev)
