@@ -774,6 +774,24 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
                : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// packed fp32x2 arithmetic (PTX fma.rn.f32x2 -> SASS FFMA2, sm_100+); a pair lives in a 64-bit register, lane 0 = low word
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t bcast_f32x2(float v) { return pack_f32x2(v, v); }
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 
 // unit u -> (m-tile, p-tile, component pair)
 __device__ __forceinline__ void v3_unit(const MixParams& p, int u, int& m0, int& pair, int& pt) {
@@ -1053,20 +1071,33 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
 #pragma unroll
       for (int kp = 0; kp < KQ; kp += 2) {                       // 2 k values = 8 operand columns (column = k*4 + b)
         float big[8], small[8];
+        // the two k values of a column pair are mixed together with packed fp32x2 FMAs (FFMA2, sm_100: one instruction, two
+        // products; the rule coefficient is the scalar-broadcast operand): half the FMA issue slots of the scalar loop.  The
+        // producers' FMA issue is what stretches the MMAs from 68 to 78-87 cycles (profiles/r02_mix_v3_ablation.md).
+        uint64_t xp[NT];
 #pragma unroll
-        for (int kk = 0; kk < 2; ++kk)
+        for (int uu = 0; uu < NT; ++uu) xp[uu] = pack_f32x2(xr[uu][kp], xr[uu][kp + 1]);
 #pragma unroll
-          for (int b = 0; b < NT; ++b) {
-            const float v = (p.ablate & 64) ? xr[b][kp + kk]
-                                            : cf[b * 4] * xr[0][kp + kk] + cf[b * 4 + 1] * xr[1][kp + kk] + cf[b * 4 + 2] * xr[2][kp + kk] +
-                                                  cf[b * 4 + 3] * xr[3][kp + kk];
-            if (SINGLE) {                                        // bf16 operands: round to nearest (ties away) by add + mask
-              big[kk * 4 + b] = __uint_as_float((__float_as_uint(v) + 0x8000u) & 0xFFFF0000u);
-            } else {
-              big[kk * 4 + b] = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-              small[kk * 4 + b] = v - big[kk * 4 + b];
-            }
+        for (int b = 0; b < NT; ++b) {
+          uint64_t v2;
+          if (p.ablate & 64) {
+            v2 = xp[b];
+          } else {
+            v2 = mul_f32x2(bcast_f32x2(cf[b * 4]), xp[0]);
+#pragma unroll
+            for (int uu = 1; uu < NT; ++uu) v2 = fma_f32x2(bcast_f32x2(cf[b * 4 + uu]), xp[uu], v2);
           }
+          if (SINGLE) {                                          // bf16 operands: round to nearest (ties away) by add + mask
+            const uint64_t r = ((v2 & 0xFFFFFFFFull) + 0x8000ull) & 0xFFFF0000ull;
+            const uint64_t h = (((v2 >> 32) + 0x8000ull) & 0xFFFF0000ull) << 32;
+            unpack_f32x2(r | h, big[b], big[4 + b]);
+          } else {
+            const uint64_t b2 = v2 & 0xFFFFE000FFFFE000ull;      // tf32 "big" parts of both lanes
+            const uint64_t s2 = fma_f32x2(b2, bcast_f32x2(-1.f), v2);   // v - big, exact
+            unpack_f32x2(b2, big[b], big[4 + b]);
+            unpack_f32x2(s2, small[b], small[4 + b]);
+          }
+        }
         if (p.ablate & 32) {                                     // keep the arithmetic alive without the tensor-memory stores
           float acc = 0.f;
 #pragma unroll
@@ -1542,13 +1573,16 @@ __global__ void __launch_bounds__(DH2_THREADS, 1) phm_tc_dh_v2_kernel(const DhPa
         for (int c8 = 0; c8 < BK; c8 += 8) {
           float big[8], small[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < 8; j += 2) {
             if (p.single) {
               big[j] = __uint_as_float((__float_as_uint(v[c8 + j]) + 0x8000u) & 0xFFFF0000u);
-              small[j] = 0.f;
-            } else {
-              big[j] = __uint_as_float(__float_as_uint(v[c8 + j]) & 0xFFFFE000u);   // exact split: the tensor core ignores
-              small[j] = v[c8 + j] - big[j];                                        // the low 13 bits of `small`
+              big[j + 1] = __uint_as_float((__float_as_uint(v[c8 + j + 1]) + 0x8000u) & 0xFFFF0000u);
+              small[j] = small[j + 1] = 0.f;
+            } else {                                   // exact split, two elements per instruction (64-bit mask, FFMA2): the tensor
+              const uint64_t v2 = pack_f32x2(v[c8 + j], v[c8 + j + 1]);               // core ignores the low 13 bits of `small`
+              const uint64_t b2 = v2 & 0xFFFFE000FFFFE000ull;
+              unpack_f32x2(b2, big[j], big[j + 1]);
+              unpack_f32x2(fma_f32x2(b2, bcast_f32x2(-1.f), v2), small[j], small[j + 1]);
             }
           }
           tmem_st8(slot + c8, big);
@@ -1587,10 +1621,17 @@ __global__ void __launch_bounds__(DH2_THREADS, 1) phm_tc_dh_v2_kernel(const DhPa
           float b[4], sm[4];
           colsum += (v[ku * 4] + v[ku * 4 + 1]) + (v[ku * 4 + 2] + v[ku * 4 + 3]);     // rows past M are zero-filled by TMA
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float x = v[ku * 4 + j];
-            if (p.single) { b[j] = __uint_as_float((__float_as_uint(x) + 0x8000u) & 0xFFFF0000u); sm[j] = 0.f; }
-            else { b[j] = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); sm[j] = x - b[j]; }
+          for (int j = 0; j < 4; j += 2) {
+            if (p.single) {
+              b[j] = __uint_as_float((__float_as_uint(v[ku * 4 + j]) + 0x8000u) & 0xFFFF0000u);
+              b[j + 1] = __uint_as_float((__float_as_uint(v[ku * 4 + j + 1]) + 0x8000u) & 0xFFFF0000u);
+              sm[j] = sm[j + 1] = 0.f;
+            } else {
+              const uint64_t v2 = pack_f32x2(v[ku * 4 + j], v[ku * 4 + j + 1]);
+              const uint64_t b2 = v2 & 0xFFFFE000FFFFE000ull;
+              unpack_f32x2(b2, b[j], b[j + 1]);
+              unpack_f32x2(fma_f32x2(b2, bcast_f32x2(-1.f), v2), sm[j], sm[j + 1]);
+            }
           }
           const int off = swz(row, ku);
           *reinterpret_cast<float4*>(tb + off) = make_float4(b[0], b[1], b[2], b[3]);

@@ -24,7 +24,7 @@ def _compare(got, want, rtol, what, noise=None, chaotic=False):
     (measured, tools/diag_fullsize.py: the fp32 CPU oracle sits 3e-3..8e-3 (relative) from the fp64 oracle on all gradients of the
     ppa model and 5e-3 on zinc in one process, 1e-6 in another with a different thread count, while logits and loss agree to 1e-5).
     Gradients of those models are therefore held to: median relative error over all tensors <= max(5 x the fp32 oracle's median,
-    2e-2), each tensor within 10x that floor — "as accurate as an fp32 implementation of this model can be"; logits, loss,
+    2e-2), each tensor within max(10 x the fp32 median, 5 %) of its largest entry — "as accurate as an fp32 implementation of this model can be"; logits, loss,
     running statistics and eval logits keep rtol 1e-4, and the reference-recorded fixtures keep rtol 1e-4 on every gradient."""
     gfloor = 0.0
     if chaotic:
@@ -32,7 +32,7 @@ def _compare(got, want, rtol, what, noise=None, chaotic=False):
         g_med = sorted(_rel(got["grads"][k], g) for k, g in want["grads"].items() if float(g.abs().max()) > 0)
         n_med, g_med = n_med[len(n_med) // 2], g_med[len(g_med) // 2]
         assert g_med <= max(5.0 * n_med, 2e-2), f"{what}: median relative gradient error {g_med:.2e} vs fp32-oracle noise {n_med:.2e}"
-        gfloor = max(n_med, 2e-3)
+        gfloor = max(n_med, 5e-3)       # x10 in the per-tensor check below: 5 % of the tensor's largest entry
 
     def tol(key, ref, sub=None):
         floor = 0.0

@@ -16,4 +16,11 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:"con
 STEP_AGGR=max timeout 600 ncu --set full --clock-control none --import-source on -k regex:"conv_fwd_kernel|aggregate_bwd" -s 8 -c 6 \
   -o $O/${R}_ppa_max_full -f python tools/step_time.py ppa 1 > $O/${R}_ppa_max_full.log 2>&1
 python tools/prep_bench.py > $O/${R}_prep.txt 2>&1
+# gpurun_out/ travels back only below 64 MiB: keep the text summaries (what profiles/ commits), drop the reports
+python tools/ncu_summary.py launches $O/${R}_launches_ppa.csv > $O/${R}_launches_ppa.txt 2>&1
+for n in ppa_full hiv_softmax_full ppa_max_full; do
+  python tools/ncu_summary.py kernel $O/${R}_$n.ncu-rep > $O/${R}_$n.txt 2>&1
+  rm -f $O/${R}_$n.ncu-rep
+done
+rm -f $O/${R}_launches_ppa.csv
 ls -la $O/${R}_*
