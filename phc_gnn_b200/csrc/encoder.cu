@@ -52,6 +52,29 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const long long* __restr
   acc.store(out + (size_t)r * F + c * Fc + f);
 }
 
+// Component width not a multiple of 4 (ppa: Fc = 125) but flat rows 16-byte aligned: a thread owns 4 consecutive FLAT features
+// (they may straddle a component boundary), gathers them with scalar table loads and writes one 128-bit word
+// (the per-element kernel above: 7.8 M threads and 41 us for a ppa batch; this one: a quarter of the threads, vector stores).
+__global__ void __launch_bounds__(256) embed_fwd_flat4_kernel(const long long* __restrict__ idx, PtrTable tables, IntTable vocab, int R, int C,
+                                                              int n, int Fc, float* __restrict__ out) {
+  pdl_begin();
+  const int F = n * Fc, fq = F / 4;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)R * fq) return;
+  const int r = (int)(t / fq), f = (int)(t % fq) * 4;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  int c[4], fp[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { c[q] = (f + q) / Fc; fp[q] = (f + q) - c[q] * Fc; }
+  for (int col = 0; col < C; ++col) {
+    long long v = __ldg(idx + (size_t)r * C + col);
+    v = v < 0 ? 0 : (v >= vocab.v[col] ? vocab.v[col] - 1 : v);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q] += __ldg(tables.p[c[q] * C + col] + (size_t)v * Fc + fp[q]);
+  }
+  *reinterpret_cast<float4*>(out + (size_t)r * F + f) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+}
+
 // grid (row chunks, C, feature tiles of blockDim.x flat features). dynamic smem: vocab[col] * blockDim.x floats.
 __global__ void embed_bwd_partial_kernel(const float* __restrict__ g, const long long* __restrict__ idx, IntTable vocab, IntTable voff,
                                          int R, int C, int F, int rows_per_chunk, int vtot, float* __restrict__ part) {
@@ -65,7 +88,22 @@ __global__ void embed_bwd_partial_kernel(const float* __restrict__ g, const long
   for (int v = 0; v < V; ++v) acc[v * ft + threadIdx.x] = 0.f;
   const int r0 = blockIdx.x * rows_per_chunk, r1 = min(r0 + rows_per_chunk, R);
   if (active) {
-    for (int r = r0; r < r1; ++r) {
+    int r = r0;
+    for (; r + 4 <= r1; r += 4) {                     // four rows in flight: the loads are issued before the (ordered) accumulation
+      long long v[4];
+      float gv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        v[u] = __ldg(idx + (size_t)(r + u) * C + col);
+        gv[u] = g[(size_t)(r + u) * F + f];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int vi = (int)(v[u] < 0 ? 0 : (v[u] >= V ? V - 1 : v[u]));
+        acc[vi * ft + threadIdx.x] += gv[u];
+      }
+    }
+    for (; r < r1; ++r) {
       long long v = __ldg(idx + (size_t)r * C + col);
       v = v < 0 ? 0 : (v >= V ? V - 1 : v);
       acc[(int)v * ft + threadIdx.x] += g[(size_t)r * F + f];
@@ -227,9 +265,14 @@ void launch_linenc_bwd(const float* g, const float* feat, int R, int F, int rpc,
   phc_launch(linenc_bwd_partial_kernel<D>, dim3(grid), dim3(128), 0, st, g, feat, R, F, rpc, part);
 }
 
-int embed_chunks(int R) {
-  int chunks = phc_div_up(R, 512);
-  return chunks < 1 ? 1 : (chunks > 64 ? 64 : chunks);
+// row chunks of the embedding backward: 64 rows each (a chunk is one thread's serial walk; round 1 used 512-row chunks, i.e. 124
+// blocks for a ppa batch — fewer than SMs — and 55 us), bounded so that the [chunks][vocab][F] partials stay below 32 MiB
+int embed_chunks(int R, int vtot, int F) {
+  long long chunks = phc_div_up(R, 64);
+  const long long cap = (32ll << 20) / (4ll * (vtot > 0 ? vtot : 1) * (F > 0 ? F : 1));
+  if (chunks > cap) chunks = cap;
+  if (chunks > 1024) chunks = 1024;
+  return chunks < 1 ? 1 : (int)chunks;
 }
 int linenc_chunks(int R) {
   int chunks = phc_div_up(R, 128);
@@ -241,7 +284,7 @@ int linenc_chunks(int R) {
 extern "C" {
 
 size_t phc_embed_bwd_workspace_bytes(int rows, int total_vocab, int width) {
-  return sizeof(float) * (size_t)embed_chunks(rows) * total_vocab * width;
+  return sizeof(float) * (size_t)embed_chunks(rows, total_vocab, width) * total_vocab * width;
 }
 
 int phc_embed_sum_fwd(const long long* idx, const float* const* tables, const int* vocab, int rows, int cols, int phm_dim,
@@ -255,6 +298,8 @@ int phc_embed_sum_fwd(const long long* idx, const float* const* tables, const in
   for (int i = 0; i < cols; ++i) vc.v[i] = vocab[i];
   const int n = phm_dim, Fc = width_per_component;
   if (v4) phc_launch(embed_fwd_kernel<4>, dim3(phc_div_up((long long)rows * n * (Fc / 4), 256)), dim3(256), 0, stream, idx, tb, vc, rows, cols, n, Fc, out);
+  else if ((n * Fc) % 4 == 0 && phc_aligned16(out))
+    phc_launch(embed_fwd_flat4_kernel, dim3(phc_div_up((long long)rows * (n * Fc / 4), 256)), dim3(256), 0, stream, idx, tb, vc, rows, cols, n, Fc, out);
   else phc_launch(embed_fwd_kernel<1>, dim3(phc_div_up((long long)rows * n * Fc, 256)), dim3(256), 0, stream, idx, tb, vc, rows, cols, n, Fc, out);
   return phc_check_launch("phc_embed_sum_fwd");
 }
@@ -271,7 +316,7 @@ int phc_embed_sum_bwd(const float* gout, const long long* idx, float* const* dta
   const int ft = 128;
   const size_t smem = sizeof(float) * (size_t)vmax * ft;
   PHC_REQUIRE(smem <= 200 * 1024, "phc_embed_sum_bwd: vocabulary %d too large for the shared-memory accumulator", vmax);
-  const int chunks = embed_chunks(rows);
+  const int chunks = embed_chunks(rows, vtot, F);
   const int rpc = phc_div_up(rows > 0 ? rows : 1, chunks);
   float* part = reinterpret_cast<float*>(workspace);
   static bool attr_set = false;
