@@ -44,8 +44,8 @@ def parse():
     ap.add_argument("--precision", default=None, help="fp32 | tf32x3 | bf16 (default: PHC_PRECISION or tf32x3)")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="on: the step is replayed from one CUDA graph per batch shape (phc_gnn_b200/graphed.py; data parallel: the "
-                         "all-reduce and the optimizer kernels stay eager between graph launches); off: eager host path with the "
-                         "sliced, overlapped all-reduce; auto: graph where replay measured a gain (nodes x width per batch < 7.5e6: "
+                         "all-reduce and the optimizer kernels stay eager between graph launches); off: eager host path (one all-reduce after "
+                         "backward; PHC_OVERLAP_ALLREDUCE=1 slices and overlaps it); auto: graph where replay measured a gain (nodes x width per batch < 7.5e6: "
                          "hiv, zinc, mnist, cifar 1.7-2.8x, pcba 1.13x), eager for ppa (kernel-bound: replay 5.13 vs eager 5.09 ms)")
     ap.add_argument("--sharding", default="balanced", choices=["balanced", "random"],
                     help="N > 1: how the graphs of a global batch are dealt to the ranks (balanced: by node count, prep.balanced_partition)")

@@ -16,7 +16,7 @@ What makes the step replayable (nothing the host passes by value may change betw
 Data parallel (world size > 1): the graph holds zero_grad .. backward + the gradient pack; the all-reduce of the flat buffer stays ONE
 eager NCCL call between the graph launch and the two optimizer kernels (recording NCCL collectives issued from autograd-hook threads
 into a capture hung in testing, and the launch-bound workloads this path exists for have < 2 MB of gradients — nothing to overlap).
-The overlapped, sliced all-reduce of parallel.GradientBucket belongs to the eager step, which is what large batches (ppa) run.
+(The optional overlapped, sliced all-reduce of parallel.GradientBucket belongs to the eager step.)
 
 A graph is specific to (N, E, B) and the feature widths.  A shape is captured when it is seen for the ``capture_after``-th time
 (default: the second), at most ``max_graphs`` shapes are kept; every other call runs the eager step.  Training over a fixed set

@@ -6,6 +6,7 @@
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -64,8 +65,14 @@ class TrainStep(object):
             self.opt = optimizer if optimizer is not None else make_optimizer(model, workload.lr)
         self.dp = dp                      # DataParallelPHC wrapper or None
         if dp is not None and self.flat_opt:
-            # gradient slices are all-reduced as backward completes them (head first), overlapping the layers below
-            self.opt.bucket.enable_overlap(model, dp.group)
+            # Default: ONE all-reduce of the flat gradient buffer after backward (ncclAvg, no separate scaling pass).
+            # PHC_OVERLAP_ALLREDUCE=1: slices are all-reduced as backward completes them (parallel.GradientBucket.enable_overlap).
+            # Measured at 8 GPUs on the ppa workload the overlapped mode is SLOWER and noisy (84.9k - 94.5k graphs/s against
+            # 97.0k): the step's persistent tcgen05 kernels need all 148 SMs, so an NCCL kernel running beside them delays
+            # whichever came second on every rank, and the ring stalls on the slowest one; the buffer is only 4.7 MB.
+            self.opt.bucket.group = dp.group
+            if os.environ.get("PHC_OVERLAP_ALLREDUCE", "") not in ("", "0"):
+                self.opt.bucket.enable_overlap(model, dp.group)
         # the scripts pick the regulariser by family (train_hiv.py:182: quaternion models have no ``phm_dim``)
         if hasattr(getattr(model, "module", model), "phm_dim"):
             self.regulariser = phm_weight_regularization

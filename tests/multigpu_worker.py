@@ -34,11 +34,11 @@ def main():
             dp = DataParallelPHC(model)
             step = TrainStep(model, wl, None, dp)
             bucket = step.opt.bucket
-            if mode == "single":
-                bucket.overlap = False                      # one all-reduce after backward
-            else:
-                assert bucket.overlap
+            if mode == "overlap":
+                assert bucket.enable_overlap(model, dp.group)   # opt-in (PHC_OVERLAP_ALLREDUCE=1 does the same in TrainStep)
                 bucket.min_chunk_bytes = 0                  # tiny model: force one all-reduce per completed stage
+            else:
+                assert not bucket.overlap                   # default: one all-reduce after backward
             run = step
             if mode == "graph":
                 from phc_gnn_b200.graphed import GraphedTrainStep
