@@ -656,7 +656,7 @@ def run_b200(args):
             if unfused:
                 unfused["frac"] = unfused["achieved"] / peak
         precision_name = os.environ.get("PHC_PRECISION", DEFAULT_PRECISION)
-        roof = phm_linear_roofline(prof, args.steps, wl, N, precision_name, ms_instr / args.steps)
+        roof = phm_linear_roofline(prof, args.steps, wl, N, precision_name, ms / args.steps)   # share of the headline (uninstrumented) step
         if roof is None:        # a workload without node-level tensor-core linears: the aggregation is the dominant kernel
             roof, agg = agg, None
         breakdown = {k: {"calls_per_step": v[0] / args.steps, "ms_per_step": v[1] / args.steps} for k, v in sorted(prof.items())}
