@@ -757,6 +757,13 @@ constexpr int V3_MMA_WARP = PROD_WARPS, V3_TMA_X_WARP = PROD_WARPS + 1, V3_TMA_B
 constexpr int V3_THREADS = (PROD_WARPS + 3) * 32;
 constexpr int V3_SPITCH = 20;                   // floats per scratch row (16 columns per drain pass): 16-byte aligned rows, conflict-free writes
 constexpr int V3_SCRATCH = PROD_WARPS * 32 * V3_SPITCH * 4;
+#ifndef PHC_TC_PROF
+#define PHC_TC_PROF 0
+#endif
+#ifndef PHC_V3_HOIST
+#define PHC_V3_HOIST 0
+#endif
+constexpr int V3_HOIST = PHC_V3_HOIST;          // column pairs (of 4 per chunk) mixed before the producers wait for their operand slot
 
 __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -1016,7 +1023,9 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
     const int ldc = p.n * p.Pout;
     float cf[NT * NT];
     int cur_comp = -1;
-    const bool prof = p.prof != nullptr && warp == 0 && lane == 0;
+    // producer-side role timers only in -DPHC_TC_PROF=1 builds: five 64-bit counters live across the whole loop cost the registers
+    // the hoisted mixing needs (the kernel sits at its 96-register cap); the MMA issuer's timers (waits, kernel total) stay
+    const bool prof = PHC_TC_PROF && p.prof != nullptr && warp == 0 && lane == 0;
     long long t_rfull = 0, t_aempty = 0, t_work = 0, t_drain = 0, tp = 0;
 
     auto produce = [&](int gi, int c, int comp) {
@@ -1063,17 +1072,11 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
             for (int uu = 0; uu < NT; ++uu) xr[uu][k] = 0.f;
           }
       }
-      if (prof) { const long long tn = clock64(); t_work += tn - tp; tp = tn; }
-      mbar_wait(smem_u32(&aempty[g]), (use & 1) ^ 1);           // the MMAs that read this operand slot have retired
-      if (prof) { const long long tn = clock64(); t_aempty += tn - tp; tp = tn; }
-      tc_fence_after();
-      if (!(p.ablate & 2)) {
-#pragma unroll
-      for (int kp = 0; kp < KQ; kp += 2) {                       // 2 k values = 8 operand columns (column = k*4 + b)
-        float big[8], small[8];
-        // the two k values of a column pair are mixed together with packed fp32x2 FMAs (FFMA2, sm_100: one instruction, two
-        // products; the rule coefficient is the scalar-broadcast operand): half the FMA issue slots of the scalar loop.  The
-        // producers' FMA issue is what stretches the MMAs from 68 to 78-87 cycles (profiles/r02_mix_v3_ablation.md).
+      // mixing of one column pair (2 k values = 8 operand columns, column = k*4 + b).  The two k values are mixed together with
+      // packed fp32x2 FMAs (FFMA2, sm_100: one instruction, two products; the rule coefficient is the scalar-broadcast operand):
+      // half the FMA issue slots of a scalar loop — the producers' FMA issue is what stretches the MMAs from 68 to 78-87 cycles
+      // (profiles/r02_mix_v3_ablation.md).
+      auto mix_pair = [&](int kp, float (&big)[8], float (&small)[8]) {
         uint64_t xp[NT];
 #pragma unroll
         for (int uu = 0; uu < NT; ++uu) xp[uu] = pack_f32x2(xr[uu][kp], xr[uu][kp + 1]);
@@ -1098,6 +1101,8 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
             unpack_f32x2(s2, small[b], small[4 + b]);
           }
         }
+      };
+      auto store_pair = [&](int kp, const float (&big)[8], const float (&small)[8]) {
         if (p.ablate & 32) {                                     // keep the arithmetic alive without the tensor-memory stores
           float acc = 0.f;
 #pragma unroll
@@ -1107,7 +1112,29 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
           tmem_st8(a_slot + kp * 4, big);
           if (!SINGLE) tmem_st8(a_slot + 32 + kp * 4, small);
         }
+      };
+      // V3_HOIST column pairs of the chunk can be mixed BEFORE waiting for the operand slot (the producers' turn-around, slot free ->
+      // operand written, is ~1 500 cycles against ~1 750 tensor cycles per chunk, and the MMA issuer waits for operands 12 % of the
+      // kernel).  Measured: one hoisted pair spills (the kernel sits at its 96-register cap) and is 3 % SLOWER (83.3k vs 80.4k
+      // cycles), two pairs spill 300 bytes per thread — the default is 0 (profiles/r02_mix_v3_ablation.md).
+      float bigA[V3_HOIST][8], smallA[V3_HOIST][8];
+      if (!(p.ablate & 2)) {
+#pragma unroll
+        for (int h2 = 0; h2 < V3_HOIST; ++h2) mix_pair(2 * h2, bigA[h2], smallA[h2]);
       }
+      if (prof) { const long long tn = clock64(); t_work += tn - tp; tp = tn; }
+      mbar_wait(smem_u32(&aempty[g]), (use & 1) ^ 1);           // the MMAs that read this operand slot have retired
+      if (prof) { const long long tn = clock64(); t_aempty += tn - tp; tp = tn; }
+      tc_fence_after();
+      if (!(p.ablate & 2)) {
+#pragma unroll
+        for (int h2 = 0; h2 < V3_HOIST; ++h2) store_pair(2 * h2, bigA[h2], smallA[h2]);
+#pragma unroll
+        for (int kp = 2 * V3_HOIST; kp < KQ; kp += 2) {
+          float big[8], small[8];
+          mix_pair(kp, big, small);
+          store_pair(kp, big, small);
+        }
       }
       tmem_st_wait();
       tc_fence_before();
