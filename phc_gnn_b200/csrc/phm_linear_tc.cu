@@ -126,6 +126,27 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (clock64() - t0 > 4000000000LL) __trap();
   }
 }
+// Spinning wait on the non-blocking test_wait: try_wait may park the warp and wake it late; the MMA issuer has nothing else to do
+// and every cycle between "operands ready" and the next tcgen05.mma is a tensor-pipe bubble.  One warp only — producers keep try_wait
+// (sixteen spinning warps would take the issue slots of the ones that work).
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity) {
+  if (mbar_test_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_test_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -760,6 +781,14 @@ constexpr int V3_SCRATCH = PROD_WARPS * 32 * V3_SPITCH * 4;
 #ifndef PHC_TC_PROF
 #define PHC_TC_PROF 0
 #endif
+#ifndef PHC_TC_SPIN
+#define PHC_TC_SPIN 1
+#endif
+#if PHC_TC_SPIN
+#define MMA_WAIT(bar, parity) mbar_spin(bar, parity)
+#else
+#define MMA_WAIT(bar, parity) mbar_wait(bar, parity)
+#endif
 #ifndef PHC_V3_HOIST
 #define PHC_V3_HOIST 0
 #endif
@@ -1117,7 +1146,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
       // operand written, is ~1 500 cycles against ~1 750 tensor cycles per chunk, and the MMA issuer waits for operands 12 % of the
       // kernel).  Measured: one hoisted pair spills (the kernel sits at its 96-register cap) and is 3 % SLOWER (83.3k vs 80.4k
       // cycles), two pairs spill 300 bytes per thread — the default is 0 (profiles/r02_mix_v3_ablation.md).
-      float bigA[V3_HOIST][8], smallA[V3_HOIST][8];
+      float bigA[V3_HOIST > 0 ? V3_HOIST : 1][8], smallA[V3_HOIST > 0 ? V3_HOIST : 1][8];
       if (!(p.ablate & 2)) {
 #pragma unroll
         for (int h2 = 0; h2 < V3_HOIST; ++h2) mix_pair(2 * h2, bigA[h2], smallA[h2]);
@@ -1229,16 +1258,16 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
     for (int si = 0; si < nseg; ++si) {
       const V3Seg sg = v3_seg(p, gb, ge, si);
       if (prof) tp = clock64();
-      mbar_wait(smem_u32(tempty), (si & 1) ^ 1);                // both accumulators drained
+      MMA_WAIT(smem_u32(tempty), (si & 1) ^ 1);                // both accumulators drained
       if (prof) t_tempty += clock64() - tp;
       tc_fence_after();
       uint32_t accum = 0;
       for (int c = sg.c0; c < sg.c1; ++c, ++gi) {
         const int g = gi & 1, bs = gi % V3_NB;
         if (prof) tp = clock64();
-        mbar_wait(smem_u32(&afull[g]), (gi >> 1) & 1);
+        MMA_WAIT(smem_u32(&afull[g]), (gi >> 1) & 1);
         if (prof) { const long long tn = clock64(); t_afull += tn - tp; tp = tn; }
-        if (!(p.ablate & 16)) mbar_wait(smem_u32(&bfull[bs]), (gi / V3_NB) & 1);
+        if (!(p.ablate & 16)) MMA_WAIT(smem_u32(&bfull[bs]), (gi / V3_NB) & 1);
         if (prof) t_bfull += clock64() - tp;
         tc_fence_after();
         if (lane == 0) {
