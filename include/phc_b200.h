@@ -134,6 +134,19 @@ int phc_bn_act_drop_skip_bwd(const float* dy, const float* h, const float* gamma
                              const float* save_rstd, int rows, int width, int phm_dim, int use_bn, int training, int act, float drop_p,
                              int drop_same, unsigned long long seed, float* dh, float* dgamma, float* dbeta, void* workspace,
                              size_t workspace_bytes, phc_stream_t stream);
+/* The same pair with a ROW STRIDE on the forward output / the incoming gradient: they are the left column block of a wider
+ * [rows, y_row_stride] buffer whose right block holds the skip features — PHMSkipConnectConcat's `torch.cat([h, x0], -1)`
+ * (undirectional/models.py:467) without the concatenation pass: the norm writes straight into the layer's input buffer. */
+int phc_bn_act_drop_skip_fwd_strided(const float* h, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                     long long* num_batches_tracked, int n_tracked, const float* skip, int rows, int width, int phm_dim,
+                                     int use_bn, int training, float momentum, float eps, int act, float drop_p, int drop_same,
+                                     unsigned long long seed, float* y, int y_row_stride, float* save_mean, float* save_rstd,
+                                     void* workspace, size_t workspace_bytes, phc_stream_t stream);
+int phc_bn_act_drop_skip_bwd_strided(const float* dy, int dy_row_stride, const float* h, const float* gamma, const float* beta,
+                                     const float* save_mean, const float* save_rstd, int rows, int width, int phm_dim, int use_bn,
+                                     int training, int act, float drop_p, int drop_same, unsigned long long seed, float* dh,
+                                     float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes, phc_stream_t stream);
+
 
 /* out = srcs[0] + srcs[1] + ... (list order) over `numel` floats; srcs is a HOST array of up to 16 device pointers.  Used for the
  * gradient of a skip connection that fans out to every layer (models.py:227-236, sc_type="first"). */

@@ -36,6 +36,8 @@ struct EwParams {
   float drop_scale;        // 1/(1-p)
   unsigned long long seed;
   const unsigned long long* epoch;   // optional device word added (times an odd constant) to the seed at run time: CUDA-graph replays
+  int ldy;                 // row stride (floats) of the forward OUTPUT and of the incoming gradient in backward: F, or the width of the
+                           // [M, F + F0] buffer whose left column block they are (PHMSkipConnectConcat: no torch.cat)
 };
 
 // registered by phc_dropout_epoch_register (process-global, like a default generator)
@@ -279,7 +281,7 @@ __global__ void __launch_bounds__(BN_THREADS, 3) bn_apply_fwd_kernel(EwParams p,
         a = actf<ACT>(p.act, a) * drop_of<DROP>(p, keep, j, q);
         v[j].v[q] = skip ? a + s[j].v[q] : a;
       }
-      v[j].store(y + (size_t)r * p.F + f);
+      v[j].store(y + (size_t)r * p.ldy + f);
     }
   }
 }
@@ -316,7 +318,7 @@ __global__ void __launch_bounds__(BN_THREADS, 3) bn_bwd_reduce_kernel(EwParams p
       for (int j = 0; j < BN_BATCH; ++j) {
         const int r = rb + j * BN_SLICES;
         if (r < r1) {
-          g[j] = Vec<VEC>::load(dy + (size_t)r * p.F + f);
+          g[j] = Vec<VEC>::load(dy + (size_t)r * p.ldy + f);
           v[j] = Vec<VEC>::load(h + (size_t)r * p.F + f);
         }
       }
@@ -397,7 +399,7 @@ __global__ void __launch_bounds__(BN_THREADS, 3) bn_apply_bwd_kernel(EwParams p,
     for (int j = 0; j < BN_BATCH; ++j) {
       const int r = rb + j * BN_SLICES;
       if (r < r1) {
-        g[j] = Vec<VEC>::load(dy + (size_t)r * p.F + f);
+        g[j] = Vec<VEC>::load(dy + (size_t)r * p.ldy + f);
         v[j] = Vec<VEC>::load(h + (size_t)r * p.F + f);
       }
     }
@@ -450,6 +452,7 @@ EwParams make_params(int M, int F, int n, int use_bn, int act, float drop_p, int
   p.drop_scale = keep > 0.0 ? (float)(1.0 / keep) : 0.f;
   p.seed = seed;
   p.epoch = g_dropout_epoch;
+  p.ldy = F;
   return p;
 }
 
@@ -484,7 +487,7 @@ static int bn_fwd_impl(const float* h, const float* gamma, const float* beta, fl
                        long long* num_batches_tracked, int n_tracked, const float* skip, int rows, int width, int phm_dim,
                        int use_bn, int training, float momentum, float eps, int act, float drop_p, int drop_same,
                        unsigned long long seed, float* y, float* save_mean, float* save_rstd, void* workspace,
-                       size_t workspace_bytes, const float* pre_partials, int pre_chunk_rows, cudaStream_t stream);
+                       size_t workspace_bytes, const float* pre_partials, int pre_chunk_rows, cudaStream_t stream, int ldy = 0);
 
 int phc_bn_act_drop_skip_fwd(const float* h, const float* gamma, const float* beta, float* running_mean, float* running_var,
                              long long* num_batches_tracked, int n_tracked, const float* skip, int rows, int width, int phm_dim,
@@ -493,6 +496,16 @@ int phc_bn_act_drop_skip_fwd(const float* h, const float* gamma, const float* be
                              size_t workspace_bytes, cudaStream_t stream) {
   return bn_fwd_impl(h, gamma, beta, running_mean, running_var, num_batches_tracked, n_tracked, skip, rows, width, phm_dim, use_bn, training,
                      momentum, eps, act, drop_p, drop_same, seed, y, save_mean, save_rstd, workspace, workspace_bytes, nullptr, 0, stream);
+}
+
+int phc_bn_act_drop_skip_fwd_strided(const float* h, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                     long long* num_batches_tracked, int n_tracked, const float* skip, int rows, int width, int phm_dim,
+                                     int use_bn, int training, float momentum, float eps, int act, float drop_p, int drop_same,
+                                     unsigned long long seed, float* y, int y_row_stride, float* save_mean, float* save_rstd,
+                                     void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  return bn_fwd_impl(h, gamma, beta, running_mean, running_var, num_batches_tracked, n_tracked, skip, rows, width, phm_dim, use_bn, training,
+                     momentum, eps, act, drop_p, drop_same, seed, y, save_mean, save_rstd, workspace, workspace_bytes, nullptr, 0, stream,
+                     y_row_stride);
 }
 
 int phc_bn_act_drop_skip_fwd_partials(const float* h, const float* gamma, const float* beta, float* running_mean, float* running_var,
@@ -512,8 +525,9 @@ static int bn_fwd_impl(const float* h, const float* gamma, const float* beta, fl
                        long long* num_batches_tracked, int n_tracked, const float* skip, int rows, int width, int phm_dim,
                        int use_bn, int training, float momentum, float eps, int act, float drop_p, int drop_same,
                        unsigned long long seed, float* y, float* save_mean, float* save_rstd, void* workspace,
-                       size_t workspace_bytes, const float* pre_partials, int pre_chunk_rows, cudaStream_t stream) {
+                       size_t workspace_bytes, const float* pre_partials, int pre_chunk_rows, cudaStream_t stream, int ldy) {
   PHC_REQUIRE(width > 0 && phm_dim > 0 && width % phm_dim == 0, "phc_bn_act_drop_skip_fwd: width %d not divisible by phm_dim %d", width, phm_dim);
+  PHC_REQUIRE(ldy == 0 || ldy >= width, "phc_bn_act_drop_skip_fwd: output row stride %d smaller than the width %d", ldy, width);
   PHC_REQUIRE(act >= PHC_ACT_IDENTITY && act <= PHC_ACT_SWISH, "phc_bn_act_drop_skip_fwd: bad act %d", act);
   PHC_REQUIRE(drop_p >= 0.f && drop_p <= 1.f, "phc_bn_act_drop_skip_fwd: dropout rate %f outside [0,1]", drop_p);
   PHC_REQUIRE((gamma == nullptr) == (beta == nullptr), "phc_bn_act_drop_skip_fwd: gamma/beta must both be given or both null");
@@ -547,7 +561,8 @@ static int bn_fwd_impl(const float* h, const float* gamma, const float* beta, fl
     }
   }
   EwParams p = make_params(M, F, phm_dim, use_bn, act, drop_p, drop_same, training, seed);
-  const bool v4 = F % 4 == 0 && phc_aligned16(h) && phc_aligned16(y) && phc_aligned16(skip);
+  if (ldy > 0) p.ldy = ldy;
+  const bool v4 = F % 4 == 0 && p.ldy % 4 == 0 && phc_aligned16(h) && phc_aligned16(y) && phc_aligned16(skip);
   const int colgroups = phc_div_up(F, BN_LANES * (v4 ? 4 : 1));
   p.rpc = bn_rows_per_chunk(M, colgroups, 3);
   dim3 grid(phc_div_up(M, p.rpc), colgroups);
@@ -557,15 +572,30 @@ static int bn_fwd_impl(const float* h, const float* gamma, const float* beta, fl
 
 extern "C" {
 
+int phc_bn_act_drop_skip_bwd_strided(const float* dy, int dy_row_stride, const float* h, const float* gamma, const float* beta,
+                                     const float* save_mean, const float* save_rstd, int rows, int width, int phm_dim, int use_bn,
+                                     int training, int act, float drop_p, int drop_same, unsigned long long seed, float* dh,
+                                     float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
 int phc_bn_act_drop_skip_bwd(const float* dy, const float* h, const float* gamma, const float* beta, const float* save_mean,
                              const float* save_rstd, int rows, int width, int phm_dim, int use_bn, int training, int act, float drop_p,
                              int drop_same, unsigned long long seed, float* dh, float* dgamma, float* dbeta, void* workspace,
                              size_t workspace_bytes, cudaStream_t stream) {
+  return phc_bn_act_drop_skip_bwd_strided(dy, width, h, gamma, beta, save_mean, save_rstd, rows, width, phm_dim, use_bn, training, act,
+                                          drop_p, drop_same, seed, dh, dgamma, dbeta, workspace, workspace_bytes, stream);
+}
+
+int phc_bn_act_drop_skip_bwd_strided(const float* dy, int dy_row_stride, const float* h, const float* gamma, const float* beta,
+                                     const float* save_mean, const float* save_rstd, int rows, int width, int phm_dim, int use_bn,
+                                     int training, int act, float drop_p, int drop_same, unsigned long long seed, float* dh,
+                                     float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   PHC_REQUIRE(width > 0 && phm_dim > 0 && width % phm_dim == 0, "phc_bn_act_drop_skip_bwd: width %d not divisible by phm_dim %d", width, phm_dim);
+  PHC_REQUIRE(dy_row_stride >= width, "phc_bn_act_drop_skip_bwd: gradient row stride %d smaller than the width %d", dy_row_stride, width);
   if (rows == 0) return PHC_OK;
   const int M = rows, F = width;
   EwParams p = make_params(M, F, phm_dim, use_bn, act, drop_p, drop_same, training, seed);
-  const bool v4 = F % 4 == 0 && phc_aligned16(h) && phc_aligned16(dy) && phc_aligned16(dh);
+  p.ldy = dy_row_stride;
+  const bool v4 = F % 4 == 0 && dy_row_stride % 4 == 0 && phc_aligned16(h) && phc_aligned16(dy) && phc_aligned16(dh);
   const int colgroups = phc_div_up(F, BN_LANES * (v4 ? 4 : 1));
   float* sum_da = dbeta;
   float* sum_da_xhat = dgamma;

@@ -165,11 +165,12 @@ class NaivePHMNorm(nn.Module):
     def autograd_params(self):
         return ([m.weight for m in self.bn] + [m.bias for m in self.bn]) if self.affine else []
 
-    def fused(self, x, skip=None, act: str = "identity", drop_p: float = 0.0, drop_same: bool = False, dropout_training=None):
+    def fused(self, x, skip=None, act: str = "identity", drop_p: float = 0.0, drop_same: bool = False, dropout_training=None,
+              concat_right=None):
         training = self.training or not self.track_running_stats
         return ops.bn_act_drop_skip(x, skip, phm_dim=self.phm_dim, flat=self.flat_views(), params=self.autograd_params(),
                                     use_bn=True, training=training, momentum=self.momentum, eps=self.eps, act=act,
-                                    drop_p=drop_p if self.training else 0.0, drop_same=drop_same)
+                                    drop_p=drop_p if self.training else 0.0, drop_same=drop_same, concat_right=concat_right)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return self.fused(x)
@@ -205,15 +206,16 @@ class PHMNorm(nn.Module):
 
 
 def norm_act_drop_skip(norm: Optional[PHMNorm], x, skip, act: str, phm_dim: int, training: bool, drop_p: float = 0.0,
-                       drop_same: bool = False) -> torch.Tensor:
+                       drop_same: bool = False, concat_right: Optional[torch.Tensor] = None) -> torch.Tensor:
     """skip + dropout(act(norm(x))) as ONE kernel pair — reference models.py:206-215, layers.py:349-355,
-    downstream.py:98-113 spell this as 4-5 separate modules."""
+    downstream.py:98-113 spell this as 4-5 separate modules.  ``concat_right``: [ dropout(act(norm(x))) | concat_right ] as one
+    buffer (the concat skip connection of models.py:467 without the concatenation pass)."""
     if norm is not None:
-        return norm.fused(x, skip=skip, act=act, drop_p=drop_p, drop_same=drop_same)
-    if act == "identity" and skip is None and not (training and drop_p > 0.0):
+        return norm.fused(x, skip=skip, act=act, drop_p=drop_p, drop_same=drop_same, concat_right=concat_right)
+    if act == "identity" and skip is None and concat_right is None and not (training and drop_p > 0.0):
         return x
     return ops.bn_act_drop_skip(x, skip, phm_dim=phm_dim, use_bn=False, training=training, act=act, drop_p=drop_p,
-                                drop_same=drop_same)
+                                drop_same=drop_same, concat_right=concat_right)
 
 
 class PHMMLP(nn.Module):
@@ -932,6 +934,12 @@ class PHMSkipConnectConcat(_PHMSkipConnectBase):
                 z = self.convs[i](h, edge_index, edge_attr, size, encoder=enc)
             else:
                 z = self.convs[i](x=h, edge_index=edge_index, edge_attr=self._encode_edges(i, edge_attr), size=size)
+            if type(self)._skip_concat is PHMSkipConnectConcat._skip_concat and self.fuse_edge_encoder:
+                # flat concat: norm / act / dropout write the left column block of the next layer's input buffer, the atom
+                # embedding is copied into the right one — no torch.cat pass (csrc/norm.cu, *_strided)
+                h = norm_act_drop_skip(self.norms[i], z, None, act, self._n, self.training, drop_p=self.dropout_mpnn[i],
+                                       drop_same=self.same_dropout, concat_right=skip)
+                continue
             z = norm_act_drop_skip(self.norms[i], z, None, act, self._n, self.training, drop_p=self.dropout_mpnn[i],
                                    drop_same=self.same_dropout)
             h = self._skip_concat(z, skip)

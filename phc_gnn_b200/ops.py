@@ -43,7 +43,7 @@ PROFILE = _Profile()
 
 # kernels launched per C-ABI call (memsets included), for the gpu_launches claim
 _KERNELS = {"phc_csr_build": 6, "phc_segment_ptr_build": 2, "phc_aggregate_fwd": 1, "phc_aggregate_bwd": 2,
-            "phc_segment_pool_fwd": 1, "phc_segment_pool_bwd": 1, "phc_bn_act_drop_skip_fwd": 3, "phc_bn_act_drop_skip_bwd": 3,
+            "phc_segment_pool_fwd": 1, "phc_segment_pool_bwd": 1, "phc_bn_act_drop_skip_fwd": 3, "phc_bn_act_drop_skip_bwd": 3, "phc_bn_act_drop_skip_fwd_strided": 3, "phc_bn_act_drop_skip_bwd_strided": 3,
             "phc_embed_sum_fwd": 1, "phc_embed_sum_bwd": 2, "phc_linear_encoder_fwd": 1, "phc_linear_encoder_bwd": 2,
             "phc_phm_linear_fwd": 2, "phc_phm_linear_bwd": 4, "phc_weight_reg_fwd": 2, "phc_weight_reg_bwd": 1,
             "phc_conv_fused_fwd": 1, "phc_conv_fused_bwd": 3, "phc_edge_feature_sums": 1, "phc_pna_aggregate_fwd": 1,
@@ -316,8 +316,13 @@ def next_dropout_seed(device) -> int:
 
 
 class _BnActDropSkip(torch.autograd.Function):
+    """y = skip + dropout(act(batchnorm(h))), or — with ``right`` — out = [ dropout(act(batchnorm(h))) | right ] written as ONE
+    [M, F + Fr] buffer: the norm kernel stores its rows with the buffer's row stride (``phc_bn_act_drop_skip_fwd_strided``) and the
+    skip features are copied into the right column block, so PHMSkipConnectConcat needs no ``torch.cat`` pass; backward reads the
+    left block of the incoming gradient in place (``_bwd_strided``) and hands the right block on as a view."""
+
     @staticmethod
-    def forward(ctx, h, skip, cfg, flat, *params):
+    def forward(ctx, h, skip, right, cfg, flat, *params):
         # params = n gammas followed by n betas (only for autograd bookkeeping; the kernel reads `flat`)
         lib = _lib.load()
         h = _f32c(h, "h")
@@ -327,23 +332,34 @@ class _BnActDropSkip(torch.autograd.Function):
         if skip is not None:
             skip = _f32c(skip, "skip")
             assert skip.shape == h.shape
-        y = torch.empty_like(h)
         dev = h.device
+        Fr = 0
+        if right is not None:
+            require_cuda(right, "right")
+            assert right.dim() == 2 and right.size(0) == M and right.dtype == torch.float32 and skip is None
+            Fr = right.size(1)
+            out = torch.empty((M, F + Fr), dtype=torch.float32, device=dev)
+            out[:, F:].copy_(right)
+            y, ldy = out, F + Fr
+        else:
+            out = y = torch.empty_like(h)
+            ldy = F
         stats = torch.empty((2, F), dtype=torch.float32, device=dev) if use_bn else None
         nb = lib.phc_bn_workspace_bytes(M, F) if (use_bn and training) else 16
         ws = _ws(nb, dev)
         upd = training and use_bn
-        run("phc_bn_act_drop_skip_fwd", None, 
+        run("phc_bn_act_drop_skip_fwd_strided", None,
             h.data_ptr(), _ptr(gamma), _ptr(beta), _ptr(rmean) if (upd or not training) else 0,
             _ptr(rvar) if (upd or not training) else 0, _ptr(tracked) if upd else 0,
             0 if tracked is None else tracked.numel(), _ptr(skip), M, F, n, int(use_bn), int(training), momentum, eps, act,
-            float(p), int(same), seed, y.data_ptr(), _ptr(stats[0]) if use_bn else 0, _ptr(stats[1]) if use_bn else 0,
+            float(p), int(same), seed, y.data_ptr(), ldy, _ptr(stats[0]) if use_bn else 0, _ptr(stats[1]) if use_bn else 0,
             ws.data_ptr(), ws.numel(), _stream(dev))
         ctx.save_for_backward(h, gamma, beta, stats)
         ctx.cfg = cfg
         ctx.nparams = len(params)
         ctx.has_skip = skip is not None
-        return y
+        ctx.right_width = Fr
+        return out
 
     @staticmethod
     def backward(ctx, gy):
@@ -352,13 +368,14 @@ class _BnActDropSkip(torch.autograd.Function):
         (n, use_bn, training, momentum, eps, act, p, same, seed) = ctx.cfg
         gy = _f32c(gy, "grad_output")
         M, F = h.shape
+        Fr = ctx.right_width
         dev = h.device
         dh = torch.empty_like(h)
         dgb = torch.empty((2, F), dtype=torch.float32, device=dev) if use_bn else None
         nb = lib.phc_bn_workspace_bytes(M, F) if use_bn else 16
         ws = _ws(nb, dev)
-        run("phc_bn_act_drop_skip_bwd", None, 
-            gy.data_ptr(), h.data_ptr(), _ptr(gamma), _ptr(beta), _ptr(stats[0]) if use_bn else 0,
+        run("phc_bn_act_drop_skip_bwd_strided", None,
+            gy.data_ptr(), F + Fr, h.data_ptr(), _ptr(gamma), _ptr(beta), _ptr(stats[0]) if use_bn else 0,
             _ptr(stats[1]) if use_bn else 0, M, F, n, int(use_bn), int(training), act, float(p), int(same), seed, dh.data_ptr(),
             _ptr(dgb[0]) if use_bn else 0, _ptr(dgb[1]) if use_bn else 0, ws.data_ptr(), ws.numel(), _stream(dev))
         grads: List[Optional[torch.Tensor]] = []
@@ -366,20 +383,21 @@ class _BnActDropSkip(torch.autograd.Function):
             k = ctx.nparams // 2
             fc = F // k
             grads = [dgb[0, c * fc:(c + 1) * fc] for c in range(k)] + [dgb[1, c * fc:(c + 1) * fc] for c in range(k)]
-        return (dh, gy if ctx.has_skip else None, None, None) + tuple(grads)
+        return (dh, gy if ctx.has_skip else None, gy[:, F:] if Fr else None, None, None) + tuple(grads)
 
 
 def bn_act_drop_skip(h, skip, *, phm_dim: int, flat=None, params: Sequence[torch.Tensor] = (), use_bn: bool, training: bool,
                      momentum: float = 0.1, eps: float = 1e-5, act: str = "identity", drop_p: float = 0.0,
-                     drop_same: bool = False) -> torch.Tensor:
+                     drop_same: bool = False, concat_right: Optional[torch.Tensor] = None) -> torch.Tensor:
     """y = skip + dropout(act(batchnorm(h)));  ``flat`` = (gamma[F], beta[F], running_mean[F], running_var[F],
-    num_batches_tracked[n]) flat device vectors that alias the n per-component BatchNorm1d parameters."""
+    num_batches_tracked[n]) flat device vectors that alias the n per-component BatchNorm1d parameters.
+    ``concat_right`` [M, Fr] (instead of ``skip``): returns the [M, F + Fr] buffer [ y | concat_right ] (see _BnActDropSkip)."""
     assert 0.0 <= drop_p <= 1.0, f"dropout rate must be in [0.0 ; 1.0]. {drop_p} was inserted!"
     active_drop = training and drop_p > 0.0
     seed = next_dropout_seed(h.device) if active_drop else 0
     cfg = (phm_dim, bool(use_bn), bool(training), float(momentum), float(eps), act_id(act),
            float(drop_p) if active_drop else 0.0, bool(drop_same), seed)
-    return _BnActDropSkip.apply(h, skip, cfg, flat, *params)
+    return _BnActDropSkip.apply(h, skip, concat_right, cfg, flat, *params)
 
 
 # --------------------------------------------------------------------------------- encoders

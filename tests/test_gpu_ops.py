@@ -196,6 +196,33 @@ def test_norm_act_skip(M, F, n, act, affine, skip, training):
         assert int(bn.num_batches_tracked) == (1 if training else 0)
 
 
+@pytest.mark.parametrize("M,F,Fr,n,act,use_norm", [(257, 48, 24, 4, "relu", True), (1000, 500, 500, 4, "relu", True), (64, 10, 7, 1, "swish", True),
+                                                  (300, 36, 12, 3, "elu", False), (33, 8, 9, 2, "identity", True)])
+def test_norm_act_into_concat_buffer(M, F, Fr, n, act, use_norm):
+    """concat_right: [ act(norm(h)) | right ] as ONE buffer (strided store / strided gradient read) == torch.cat of the two,
+    values and every gradient bit for bit (same kernels, only the row stride differs)."""
+    from phc.hypercomplex.norm import PHMNorm
+    from phc_gnn_b200.nn import norm_act_drop_skip
+    g = torch.Generator().manual_seed(2)
+    h = (torch.randn(M, F, generator=g) * 1.5 + 0.5).to(DEV)
+    right = torch.randn(M, Fr, generator=g).to(DEV)
+    gout = torch.randn(M, F + Fr, generator=g).to(DEV)
+    res = []
+    for fused in (True, False):
+        torch.manual_seed(5)
+        norm = PHMNorm(F, n).to(DEV) if use_norm else None
+        hs, rs = h.clone().requires_grad_(True), right.clone().requires_grad_(True)
+        if fused:
+            out = norm_act_drop_skip(norm, hs, None, act, n, True, concat_right=rs)
+        else:
+            out = torch.cat([norm_act_drop_skip(norm, hs, None, act, n, True), rs], dim=-1)
+        assert out.shape == (M, F + Fr) and out.is_contiguous()
+        out.backward(gout)
+        res.append((out.detach(), hs.grad, rs.grad) + (tuple(p.grad for p in norm.parameters()) if use_norm else ()))
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
+
+
 def test_dropout_invariants():
     # mirrors reference phc/hypercomplex/tests/test_ops_equal_quaternion.py:62-103
     from phc.hypercomplex.layers import phm_dropout
