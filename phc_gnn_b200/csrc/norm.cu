@@ -194,45 +194,86 @@ __device__ __forceinline__ double warp_sum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-// FW warps cooperate on one feature (the PHMLinear epilogue emits one partial per 32 rows: 488 at ppa shape, a single
-// warp spends most of its time in dependent load rounds); the per-warp sums are combined in warp order.
-constexpr int BN_FW = 4;
-__device__ __forceinline__ double block_sum4(double v, double (&sh)[BN_FW], int warp, int lane) {
-  v = warp_sum(v);
-  __syncthreads();                       // sh may still be read from the previous use
-  if (lane == 0) sh[warp] = v;
+// Merge of the chunk moments.  A block owns BNF_FL adjacent features and splits the chunks over BNF_CS slices: a warp reads four
+// chunk rows x eight features = four fully used 32-byte sectors per request (one block per feature read 4 bytes of every sector it
+// touched), and with 128 slices the 488 chunk rows of the ppa shape are one round of four independent loads per thread and pass.
+// Two passes in double as before (mean, then M2 about that mean); slices are combined in a fixed order (xor-shuffles inside the
+// warp, warps in index order), so the result is reproducible.
+constexpr int BNF_FL = 8, BNF_CS = 128, BNF_WARPS = BNF_FL * BNF_CS / 32;
+__device__ __forceinline__ double bnf_block_sum(double v, double (&sh)[BNF_WARPS][BNF_FL], int fl) {
+  v += __shfl_xor_sync(0xffffffffu, v, 8);            // the four slices of this warp (lane = slice-in-warp * 8 + feature lane)
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();                                    // sh may still be read from the previous use
+  if (lane < BNF_FL) sh[warp][lane] = v;
   __syncthreads();
   double t = 0.0;
-#pragma unroll
-  for (int w = 0; w < BN_FW; ++w) t += sh[w];
+#pragma unroll 8
+  for (int w = 0; w < BNF_WARPS; ++w) t += sh[w][fl];
   return t;
 }
-__global__ void __launch_bounds__(BN_FW * 32) bn_finalize_kernel(const float* __restrict__ part, int chunks, int rpc, int M, int F, float eps,
-                                                                 float momentum, float* __restrict__ running_mean,
-                                                                 float* __restrict__ running_var, float* __restrict__ save_mean,
-                                                                 float* __restrict__ save_rstd, long long* __restrict__ tracked, int n_tracked) {
+__global__ void __launch_bounds__(BNF_FL * BNF_CS) bn_finalize_kernel(const float* __restrict__ part, int chunks, int rpc, int M, int F, float eps,
+                                                                      float momentum, float* __restrict__ running_mean,
+                                                                      float* __restrict__ running_var, float* __restrict__ save_mean,
+                                                                      float* __restrict__ save_rstd, long long* __restrict__ tracked, int n_tracked) {
   pdl_begin();
-  __shared__ double sh[BN_FW];
-  const int f = blockIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (blockIdx.x == 0 && threadIdx.x == 0 && tracked) for (int c = 0; c < n_tracked; ++c) tracked[c] += 1;
-  double s = 0.0;
+  __shared__ double sh[BNF_WARPS][BNF_FL];
+  const int fl = threadIdx.x & (BNF_FL - 1), cs = threadIdx.x / BNF_FL;
+  const int f = blockIdx.x * BNF_FL + fl;
+  const bool on = f < F;
+  // num_batches_tracked counters: one thread each, the load up here and the store at the very end (four serial read-modify-writes
+  // on one thread used to hold the whole block back by four memory latencies)
+  const bool tracker = blockIdx.x == 0 && tracked != nullptr && (int)threadIdx.x >= BNF_FL * BNF_CS - n_tracked;
+  long long* tslot = tracker ? tracked + (BNF_FL * BNF_CS - 1 - (int)threadIdx.x) : nullptr;
+  const long long tval = tracker ? *tslot : 0;
+  // running statistics: loaded up front, their latency overlaps the merge
+  const bool writer = cs == 0 && on;
+  const float rm_old = (writer && running_mean) ? running_mean[f] : 0.f;
+  const float rv_old = (writer && running_var) ? running_var[f] : 0.f;
+  double s = 0.0, mean, m2 = 0.0;
+  if (chunks <= BNF_CS * 4) {
+    // common case (<= 512 chunks: 16k rows of 32): every partial of this thread is loaded once, in ONE round of independent loads,
+    // and both passes run on registers
+    float mc[4], qc[4];
+    int nc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = cs + u * BNF_CS;
+      const bool valid = on && c < chunks;
+      mc[u] = valid ? part[((size_t)c * 2 + 0) * F + f] : 0.f;
+      qc[u] = valid ? part[((size_t)c * 2 + 1) * F + f] : 0.f;
+      nc[u] = valid ? min(rpc, M - c * rpc) : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) s += (double)nc[u] * (double)mc[u];
+    mean = bnf_block_sum(s, sh, fl) / (double)M;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const double d = (double)mc[u] - mean;
+      if (nc[u] > 0) m2 += (double)qc[u] + (double)nc[u] * d * d;
+    }
+  } else {
+    if (on) {
 #pragma unroll 4
-  for (int c = threadIdx.x; c < chunks; c += BN_FW * 32) s += (double)min(rpc, M - c * rpc) * (double)part[((size_t)c * 2 + 0) * F + f];
-  const double mean = block_sum4(s, sh, warp, lane) / (double)M;
-  double m2 = 0.0;
+      for (int c = cs; c < chunks; c += BNF_CS) s += (double)min(rpc, M - c * rpc) * (double)part[((size_t)c * 2 + 0) * F + f];
+    }
+    mean = bnf_block_sum(s, sh, fl) / (double)M;
+    if (on) {
 #pragma unroll 4
-  for (int c = threadIdx.x; c < chunks; c += BN_FW * 32) {
-    const double d = (double)part[((size_t)c * 2 + 0) * F + f] - mean;
-    m2 += (double)part[((size_t)c * 2 + 1) * F + f] + (double)min(rpc, M - c * rpc) * d * d;
+      for (int c = cs; c < chunks; c += BNF_CS) {
+        const double d = (double)part[((size_t)c * 2 + 0) * F + f] - mean;
+        m2 += (double)part[((size_t)c * 2 + 1) * F + f] + (double)min(rpc, M - c * rpc) * d * d;
+      }
+    }
   }
-  m2 = block_sum4(m2, sh, warp, lane);
-  if (threadIdx.x != 0) return;
+  m2 = bnf_block_sum(m2, sh, fl);
+  if (tracker) *tslot = tval + 1;
+  if (cs != 0 || !on) return;
   const double var = m2 / (double)M;
   save_mean[f] = (float)mean;
   save_rstd[f] = (float)(1.0 / sqrt(var + (double)eps));
-  if (running_mean) running_mean[f] = (1.f - momentum) * running_mean[f] + momentum * (float)mean;
-  if (running_var) running_var[f] = (1.f - momentum) * running_var[f] + momentum * (float)(m2 / (double)(M - 1));
+  if (running_mean) running_mean[f] = (1.f - momentum) * rm_old + momentum * (float)mean;
+  if (running_var) running_var[f] = (1.f - momentum) * rv_old + momentum * (float)(m2 / (double)(M - 1));
 }
 
 __global__ void __launch_bounds__(128) bn_eval_stats_kernel(const float* __restrict__ running_mean, const float* __restrict__ running_var,
@@ -538,7 +579,7 @@ static int bn_fwd_impl(const float* h, const float* gamma, const float* beta, fl
     if (training && pre_partials != nullptr) {
       // chunk moments already produced by the kernel that wrote h (PHMLinear epilogue): only merge them
       PHC_REQUIRE(M > 1, "phc_bn_act_drop_skip_fwd: batch-norm in training mode needs more than 1 row");
-      phc_launch(bn_finalize_kernel, dim3(F), dim3(BN_FW * 32), 0, stream, pre_partials,
+      phc_launch(bn_finalize_kernel, dim3(phc_div_up(F, BNF_FL)), dim3(BNF_FL * BNF_CS), 0, stream, pre_partials,
                  phc_div_up(M, pre_chunk_rows), pre_chunk_rows, M, F, eps, momentum, running_mean, running_var, save_mean, save_rstd,
                  num_batches_tracked, n_tracked);
     } else if (training) {
@@ -552,7 +593,7 @@ static int bn_fwd_impl(const float* h, const float* gamma, const float* beta, fl
       dim3 grid(chunks, colgroups);
       if (v4s) phc_launch(bn_chunk_stats_kernel<4>, dim3(grid), dim3(BN_THREADS), 0, stream, h, M, F, rpc, part);
       else phc_launch(bn_chunk_stats_kernel<1>, dim3(grid), dim3(BN_THREADS), 0, stream, h, M, F, rpc, part);
-      phc_launch(bn_finalize_kernel, dim3(F), dim3(BN_FW * 32), 0, stream, part, chunks, rpc, M, F, eps, momentum, running_mean,
+      phc_launch(bn_finalize_kernel, dim3(phc_div_up(F, BNF_FL)), dim3(BNF_FL * BNF_CS), 0, stream, part, chunks, rpc, M, F, eps, momentum, running_mean,
                                                                                 running_var, save_mean, save_rstd, num_batches_tracked,
                                                                                 n_tracked);
     } else {

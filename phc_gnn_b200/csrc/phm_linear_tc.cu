@@ -147,6 +147,16 @@ __device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity) {
     if (clock64() - t0 > 4000000000LL) __trap();
   }
 }
+// One lane of a converged warp (elect.sync): unlike `lane == 0`, the compiler knows the guarded region runs on a single lane.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -196,6 +206,24 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr)
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// split form for software-pipelined drains: issue the load of the NEXT column block, work on the current one, then wait.  The wait
+// names the destination registers as in/out operands so that no use of them can be scheduled above it.
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_wait(uint32_t (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
+                 "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :
+               : "memory");
 }
 
 // Shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor).
@@ -773,7 +801,24 @@ constexpr int V3_NRAW = 3;                      // raw activation stages: deeper
 constexpr int V3_RAW_BYTES = BM * 12 * 4 * 4;   // 4 input components x 128 rows x (8 + 4 pad) floats = 24 KiB
 constexpr int V3_A_COL0 = 2 * BN;               // first operand-slot column
 constexpr int V3_TMEM_COLS = 512;
-constexpr int V3_BARS = 2 * V3_NB + 2 * V3_NR + 2 * V3_NRAW + 2;
+// PHC_V3_SPLIT_H: operand-slot hand-over per (chunk parity, component) — a commit behind each component's twelve MMAs and a wait
+// just before them, so that the four slots rotate (busy 768 tensor cycles, free 2 304) instead of being handed over in pairs (free
+// 1 536, about the producers' turn-around).  With the warp-wide issue loop of rounds 1-2 this was SLOWER (52.9 us against 48.1 us:
+// every commit / wait boundary cost the tensor pipe ~200 idle cycles and this doubled them); issue modes 1 / 2 only.
+#ifndef PHC_V3_SPLIT_H
+#define PHC_V3_SPLIT_H 0
+#endif
+constexpr int V3_AH = PHC_V3_SPLIT_H ? 2 : 1;   // operand barriers per chunk parity
+constexpr int V3_BARS = 2 * V3_NB + 2 * V3_NR * V3_AH + 2 * V3_NRAW + 2;
+// MMA issue loop: 0 = the whole warp waits on the barriers, lane 0 issues (rounds 1-2); 1 = lane 0 runs the loop alone; 2 = lane 0
+// alone, and the barriers of the NEXT chunk are probed (mbarrier.test_wait, no spin) before the last PHC_V3_HOLD MMAs of the current
+// chunk are issued, so that a chunk boundary carries no barrier round trips when the operands are already there.
+#ifndef PHC_V3_ISSUE_MODE
+#define PHC_V3_ISSUE_MODE 2
+#endif
+#ifndef PHC_V3_HOLD
+#define PHC_V3_HOLD 4
+#endif
 constexpr int V3_MMA_WARP = PROD_WARPS, V3_TMA_X_WARP = PROD_WARPS + 1, V3_TMA_B_WARP = PROD_WARPS + 2;
 constexpr int V3_THREADS = (PROD_WARPS + 3) * 32;
 constexpr int V3_SPITCH = 20;                   // floats per scratch row (16 columns per drain pass): 16-byte aligned rows, conflict-free writes
@@ -788,6 +833,17 @@ constexpr int V3_SCRATCH = PROD_WARPS * 32 * V3_SPITCH * 4;
 #define MMA_WAIT(bar, parity) mbar_spin(bar, parity)
 #else
 #define MMA_WAIT(bar, parity) mbar_wait(bar, parity)
+#endif
+// Role-ablation switches (MixParams::ablate, env PHC_TC_ABLATE) are compiled in only on request: as run-time tests they cost ~10
+// instructions per column pair in the producers' hot loop.  Build with -DPHC_TC_ABLATE_SWITCHES=1 for tools/tc_ablate.sh.
+#ifndef PHC_TC_ABLATE_SWITCHES
+#define PHC_TC_ABLATE_SWITCHES 0
+#endif
+#define V3_ABL(mask) (PHC_TC_ABLATE_SWITCHES && (p.ablate & (mask)))
+// Experiment: start component boxes at their exact (possibly not 16-byte aligned) column instead of the aligned column below it
+// with a 4-float pad (R != 0 kernels): 16 instead of 24 KiB per raw stage.  Only if TMA accepts such coordinates — off by default.
+#ifndef PHC_V3_UNALIGNED_TMA
+#define PHC_V3_UNALIGNED_TMA 0
 #endif
 #ifndef PHC_V3_HOIST
 #define PHC_V3_HOIST 0
@@ -827,6 +883,17 @@ __device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
   uint64_t d;
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
+}
+
+// explicit shared-space accesses (a generic pointer into dynamic shared memory compiles to LD.E / ST.E, which resolve the address
+// space per access)
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
 // unit u -> (m-tile, p-tile, component pair)
@@ -876,6 +943,9 @@ __device__ __forceinline__ void st_release_u32(unsigned int* ptr, unsigned int v
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory");
 }
 
+#ifndef PHC_V3_DRAIN_PIPE
+#define PHC_V3_DRAIN_PIPE 1
+#endif
 // One warp drains 32 rows x 64 columns of an accumulator, 16 columns per pass: TMEM -> registers -> smem transpose ->
 // row stores (each half warp writes 64 contiguous bytes of one row; the component offset c*P makes rows only 4-byte aligned).
 // mode 0: whole unit; 1: park the partial accumulators in `part` and raise `flag`; 2: add the partner's partial first
@@ -897,11 +967,22 @@ __device__ __forceinline__ void v3_drain(float* __restrict__ my, uint32_t taddr,
     }
     __syncwarp();
   }
+  // Software pipeline (PHC_V3_DRAIN_PIPE): the tensor-memory load of column block cc + 1 is in flight while block cc goes through the
+  // transpose and the row stores (tensor memory reads run at 64 B/clk per SM: 2 048 cycles for the 128 KiB of a unit, the exposed
+  // load latency of four serial passes came on top).
+  // The block's registers are dead once it sits in the transpose scratch, so the next load reuses them: no extra registers.
+  uint32_t v[16];
+#if PHC_V3_DRAIN_PIPE
+  if (ncols > 0) tmem_ld16_issue(taddr, v);
+#endif
 #pragma unroll 1
   for (int cc = 0; cc < 4; ++cc) {
     if (cc * 16 >= ncols) break;
-    uint32_t v[16];
+#if PHC_V3_DRAIN_PIPE
+    tmem_ld16_wait(v);
+#else
     tmem_ld16(taddr + (uint32_t)(cc * 16), v);
+#endif
     if (mode != 0) {
       float4* pp = reinterpret_cast<float4*>(part + lane * 64 + cc * 16);
       if (mode == 1) {
@@ -909,6 +990,9 @@ __device__ __forceinline__ void v3_drain(float* __restrict__ my, uint32_t taddr,
         for (int j = 0; j < 4; ++j)
           __stcg(pp + j, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
                                      __uint_as_float(v[4 * j + 3])));
+#if PHC_V3_DRAIN_PIPE
+        if (cc + 1 < 4 && (cc + 1) * 16 < ncols) tmem_ld16_issue(taddr + (uint32_t)((cc + 1) * 16), v);
+#endif
         continue;
       }
 #pragma unroll
@@ -925,6 +1009,9 @@ __device__ __forceinline__ void v3_drain(float* __restrict__ my, uint32_t taddr,
       *reinterpret_cast<float4*>(my + lane * V3_SPITCH + j * 4) =
           make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
     __syncwarp();
+#if PHC_V3_DRAIN_PIPE
+    if (cc + 1 < 4 && (cc + 1) * 16 < ncols && mode != 1) tmem_ld16_issue(taddr + (uint32_t)((cc + 1) * 16), v);
+#endif
     const int lc = cc * 16 + lc16;
     const bool on = lc < ncols;
     const int col = col0 + lc;
@@ -1008,9 +1095,9 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
   uint64_t* bars = reinterpret_cast<uint64_t*>(coef + NT * NT * NT);
   uint64_t* bfull = bars;                                  // [V3_NB]
   uint64_t* bempty = bars + V3_NB;                         // [V3_NB]
-  uint64_t* afull = bars + 2 * V3_NB;                      // [2]
-  uint64_t* aempty = afull + V3_NR;                        // [2]
-  uint64_t* rfull = aempty + V3_NR;                        // [V3_NRAW]
+  uint64_t* afull = bars + 2 * V3_NB;                      // [V3_NR][V3_AH]
+  uint64_t* aempty = afull + V3_NR * V3_AH;                // [V3_NR][V3_AH]
+  uint64_t* rfull = aempty + V3_NR * V3_AH;                // [V3_NRAW]
   uint64_t* rempty = rfull + V3_NRAW;                      // [V3_NRAW]
   uint64_t* tfull = rempty + V3_NRAW;                      // accumulators complete -> drain
   uint64_t* tempty = tfull + 1;                            // accumulators drained  -> MMA
@@ -1020,9 +1107,9 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
   for (int i = threadIdx.x; i < NT * NT * NT; i += V3_THREADS) coef[i] = p.coef[i];
   if (threadIdx.x == 0) {
     for (int i = 0; i < V3_NB; ++i) { mbar_init(smem_u32(&bfull[i]), 1); mbar_init(smem_u32(&bempty[i]), 1); }
-    for (int i = 0; i < V3_NR; ++i) {
-      mbar_init(smem_u32(&afull[i]), 8);      // the parity's eight producer warps (2 components x 4 lane quarters)
-      mbar_init(smem_u32(&aempty[i]), 1);     // tcgen05.commit
+    for (int i = 0; i < V3_NR * V3_AH; ++i) {
+      mbar_init(smem_u32(&afull[i]), 8 / V3_AH);   // the producer warps of the slot(s): (2 components x) 4 lane quarters
+      mbar_init(smem_u32(&aempty[i]), 1);          // tcgen05.commit
     }
     for (int i = 0; i < V3_NRAW; ++i) {
       mbar_init(smem_u32(&rfull[i]), 1);      // TMA transaction
@@ -1047,10 +1134,11 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
     const int row = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const uint32_t a_slot = tmem_base + lane_base + (uint32_t)(V3_A_COL0 + (g * 2 + h) * 64);
+    const int ab = PHC_V3_SPLIT_H ? g * 2 + h : g;               // this warp's operand barrier pair
     const uint32_t raw0 = smem_u32(rawbuf) + (uint32_t)(row * PITCH * 4);
     float* my = scratch + warp * 32 * V3_SPITCH;
     const int ldc = p.n * p.Pout;
-    float cf[NT * NT];
+    uint64_t cf2[NT][2];                                         // rule coefficients as packed pairs: [uu][b pair] = (A'[2bp][uu], A'[2bp+1][uu])
     int cur_comp = -1;
     // producer-side role timers only in -DPHC_TC_PROF=1 builds: five 64-bit counters live across the whole loop cost the registers
     // the hoisted mixing needs (the kernel sits at its 96-register cap); the MMA issuer's timers (waits, kernel total) stay
@@ -1060,14 +1148,17 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
     auto produce = [&](int gi, int c, int comp) {
       if (comp != cur_comp) {
 #pragma unroll
-        for (int i = 0; i < NT * NT; ++i) cf[i] = coef[comp * NT * NT + i];      // [b][uu]
+        for (int uu = 0; uu < NT; ++uu)
+#pragma unroll
+          for (int bp = 0; bp < 2; ++bp)                                          // smem table is [b][uu]
+            cf2[uu][bp] = pack_f32x2(coef[comp * NT * NT + (2 * bp) * NT + uu], coef[comp * NT * NT + (2 * bp + 1) * NT + uu]);
         cur_comp = comp;
       }
       const int use = gi >> 1;                                   // how often this parity's operand slot has been used
       const int rs = gi % V3_NRAW;                               // raw stage of this chunk
       const uint32_t rawg = raw0 + (uint32_t)(rs * V3_RAW_BYTES);
       if (prof) tp = clock64();
-      if (!(p.ablate & 4)) mbar_wait(smem_u32(&rfull[rs]), (gi / V3_NRAW) & 1);      // raw boxes landed (TMA)
+      if (!V3_ABL(4)) mbar_wait(smem_u32(&rfull[rs]), (gi / V3_NRAW) & 1);      // raw boxes landed (TMA)
       if (prof) { const long long tn = clock64(); t_rfull += tn - tp; tp = tn; }
       float xr[NT][KQ];
       uint32_t landed = 0;                                       // data dependence on every load (see the release below)
@@ -1092,7 +1183,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
       // the arrive (release) stays behind the store.
       asm volatile("st.shared.b32 [%0], %1;" ::"r"(smem_u32(my + lane)), "r"(landed) : "memory");
       __syncwarp();
-      if (lane == 0 && !(p.ablate & 4)) mbar_arrive(smem_u32(&rempty[rs]));
+      if (lane == 0 && !V3_ABL(4)) mbar_arrive(smem_u32(&rempty[rs]));
       if (c == p.chunks - 1) {                                   // K tail: columns past the component belong to its neighbour
 #pragma unroll
         for (int k = 0; k < KQ; ++k)
@@ -1101,38 +1192,43 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
             for (int uu = 0; uu < NT; ++uu) xr[uu][k] = 0.f;
           }
       }
-      // mixing of one column pair (2 k values = 8 operand columns, column = k*4 + b).  The two k values are mixed together with
-      // packed fp32x2 FMAs (FFMA2, sm_100: one instruction, two products; the rule coefficient is the scalar-broadcast operand):
-      // half the FMA issue slots of a scalar loop — the producers' FMA issue is what stretches the MMAs from 68 to 78-87 cycles
-      // (profiles/r02_mix_v3_ablation.md).
+      // mixing of one column pair (2 k values = 8 operand columns, column = k*4 + b) with packed fp32x2 FMAs (FFMA2, sm_100: one
+      // instruction, two products) — the producers' FMA issue is what stretches the MMAs from 68 to 78-87 cycles
+      // (profiles/r02_mix_v3_ablation.md).  The two lanes of a packed operation are two RULE ROWS b, b+1 of the same k: the raw
+      // activation is the scalar-broadcast operand (a plain register, whatever its alignment in the staged row), the coefficient
+      // pair is loop-invariant, and the results (k: b0 b1 | b2 b3) are already in operand-column order, so the eight registers of a
+      // tcgen05.st need no shuffling.  (Pairing two k values instead cost 16 register moves per column pair to transpose the
+      // results and up to 19 more to assemble unaligned input pairs when Kin % 4 != 0: 142 moves against 80 packed FMAs per chunk.)
       auto mix_pair = [&](int kp, float (&big)[8], float (&small)[8]) {
-        uint64_t xp[NT];
 #pragma unroll
-        for (int uu = 0; uu < NT; ++uu) xp[uu] = pack_f32x2(xr[uu][kp], xr[uu][kp + 1]);
+        for (int kk = 0; kk < 2; ++kk) {
+          const int k = kp + kk;
 #pragma unroll
-        for (int b = 0; b < NT; ++b) {
-          uint64_t v2;
-          if (p.ablate & 64) {
-            v2 = xp[b];
-          } else {
-            v2 = mul_f32x2(bcast_f32x2(cf[b * 4]), xp[0]);
+          for (int bp = 0; bp < 2; ++bp) {
+            uint64_t v2;
+            if (V3_ABL(64)) {
+              v2 = pack_f32x2(xr[2 * bp][k], xr[2 * bp + 1][k]);
+            } else {
+              v2 = mul_f32x2(bcast_f32x2(xr[0][k]), cf2[0][bp]);
 #pragma unroll
-            for (int uu = 1; uu < NT; ++uu) v2 = fma_f32x2(bcast_f32x2(cf[b * 4 + uu]), xp[uu], v2);
-          }
-          if (SINGLE) {                                          // bf16 operands: round to nearest (ties away) by add + mask
-            const uint64_t r = ((v2 & 0xFFFFFFFFull) + 0x8000ull) & 0xFFFF0000ull;
-            const uint64_t h = (((v2 >> 32) + 0x8000ull) & 0xFFFF0000ull) << 32;
-            unpack_f32x2(r | h, big[b], big[4 + b]);
-          } else {
-            const uint64_t b2 = v2 & 0xFFFFE000FFFFE000ull;      // tf32 "big" parts of both lanes
-            const uint64_t s2 = fma_f32x2(b2, bcast_f32x2(-1.f), v2);   // v - big, exact
-            unpack_f32x2(b2, big[b], big[4 + b]);
-            unpack_f32x2(s2, small[b], small[4 + b]);
+              for (int uu = 1; uu < NT; ++uu) v2 = fma_f32x2(bcast_f32x2(xr[uu][k]), cf2[uu][bp], v2);
+            }
+            const int o = kk * 4 + bp * 2;
+            if (SINGLE) {                                          // bf16 operands: round to nearest (ties away) by add + mask
+              const uint64_t r = ((v2 & 0xFFFFFFFFull) + 0x8000ull) & 0xFFFF0000ull;
+              const uint64_t h = (((v2 >> 32) + 0x8000ull) & 0xFFFF0000ull) << 32;
+              unpack_f32x2(r | h, big[o], big[o + 1]);
+            } else {
+              const uint64_t b2 = v2 & 0xFFFFE000FFFFE000ull;      // tf32 "big" parts of both lanes
+              const uint64_t s2 = fma_f32x2(b2, bcast_f32x2(-1.f), v2);   // v - big, exact
+              unpack_f32x2(b2, big[o], big[o + 1]);
+              unpack_f32x2(s2, small[o], small[o + 1]);
+            }
           }
         }
       };
       auto store_pair = [&](int kp, const float (&big)[8], const float (&small)[8]) {
-        if (p.ablate & 32) {                                     // keep the arithmetic alive without the tensor-memory stores
+        if (V3_ABL(32)) {                                     // keep the arithmetic alive without the tensor-memory stores
           float acc = 0.f;
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc += big[j] + (SINGLE ? 0.f : small[j]);
@@ -1147,15 +1243,15 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
       // kernel).  Measured: one hoisted pair spills (the kernel sits at its 96-register cap) and is 3 % SLOWER (83.3k vs 80.4k
       // cycles), two pairs spill 300 bytes per thread — the default is 0 (profiles/r02_mix_v3_ablation.md).
       float bigA[V3_HOIST > 0 ? V3_HOIST : 1][8], smallA[V3_HOIST > 0 ? V3_HOIST : 1][8];
-      if (!(p.ablate & 2)) {
+      if (!V3_ABL(2)) {
 #pragma unroll
         for (int h2 = 0; h2 < V3_HOIST; ++h2) mix_pair(2 * h2, bigA[h2], smallA[h2]);
       }
       if (prof) { const long long tn = clock64(); t_work += tn - tp; tp = tn; }
-      mbar_wait(smem_u32(&aempty[g]), (use & 1) ^ 1);           // the MMAs that read this operand slot have retired
+      mbar_wait(smem_u32(&aempty[ab]), (use & 1) ^ 1);         // the MMAs that read this operand slot have retired
       if (prof) { const long long tn = clock64(); t_aempty += tn - tp; tp = tn; }
       tc_fence_after();
-      if (!(p.ablate & 2)) {
+      if (!V3_ABL(2)) {
 #pragma unroll
         for (int h2 = 0; h2 < V3_HOIST; ++h2) store_pair(2 * h2, bigA[h2], smallA[h2]);
 #pragma unroll
@@ -1168,7 +1264,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&afull[g]));
+      if (lane == 0) mbar_arrive(smem_u32(&afull[ab]));
       if (prof) t_work += clock64() - tp;
     };
     auto drain = [&](int si) {
@@ -1184,7 +1280,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
       // owner, which adds the partial parked by the NEXT CTA (whose first segment is the rest of this unit)
       const int mode = PHC_TC_STREAM_K ? (sg.c0 > 0 ? 1 : (sg.c1 < p.chunks ? 2 : 0)) : 0;
       const int slot = (int)blockIdx.x + (mode == 2 ? 1 : 0);
-      if (ncols > 0 && r0 < p.M && !(p.ablate & 8))
+      if (ncols > 0 && r0 < p.M && !V3_ABL(8))
         v3_drain<STATS>(my, tmem_base + lane_base + (uint32_t)(h * BN + g * 64), p.C, ldc, min(32, p.M - r0), r0,
                  (2 * pair + h) * p.Pout + pt * BN + g * 64, ncols, p.bias, p.residual, p.act, mode,
                  mode ? p.sk_part + ((size_t)slot * PROD_WARPS + warp) * (32 * 64) : nullptr,
@@ -1214,7 +1310,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
     }
   } else if (warp == V3_TMA_X_WARP) {
     // ===================================================================== TMA: raw activation boxes
-    if (lane == 0 && !(p.ablate & 4)) {
+    if (elect_one() && !V3_ABL(4)) {
       int gi = 0;
       for (int si = 0; si < nseg; ++si) {
         const V3Seg sg = v3_seg(p, gb, ge, si);
@@ -1227,13 +1323,14 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
           mbar_arrive_expect_tx(bar, NT * BM * PITCH * 4);
 #pragma unroll
           for (int uu = 0; uu < NT; ++uu)
-            tma_load_2d(smem_u32(rawbuf + rs * V3_RAW_BYTES + uu * (BM * PITCH * 4)), &tmapX, (uu * p.Kin + c * KQ) & ~3, m0, bar);
+            tma_load_2d(smem_u32(rawbuf + rs * V3_RAW_BYTES + uu * (BM * PITCH * 4)), &tmapX,
+                        PHC_V3_UNALIGNED_TMA ? uu * p.Kin + c * KQ : (uu * p.Kin + c * KQ) & ~3, m0, bar);
         }
       }
     }
   } else if (warp == V3_TMA_B_WARP) {
     // ===================================================================== TMA: pre-split W chunks
-    if (lane == 0 && !(p.ablate & 16)) {
+    if (elect_one() && !V3_ABL(16)) {
       int gi = 0;
       for (int si = 0; si < nseg; ++si) {
         const V3Seg sg = v3_seg(p, gb, ge, si);
@@ -1251,56 +1348,111 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
     }
   } else {
     // ===================================================================== MMA issuer: A from TMEM, B from smem
-    int gi = 0;
     const bool prof = p.prof != nullptr && lane == 0;
     long long t_tempty = 0, t_afull = 0, t_bfull = 0, tp = 0;
     const long long tk0 = prof ? clock64() : 0;
-    for (int si = 0; si < nseg; ++si) {
-      const V3Seg sg = v3_seg(p, gb, ge, si);
-      if (prof) tp = clock64();
-      MMA_WAIT(smem_u32(tempty), (si & 1) ^ 1);                // both accumulators drained
-      if (prof) t_tempty += clock64() - tp;
-      tc_fence_after();
-      uint32_t accum = 0;
-      for (int c = sg.c0; c < sg.c1; ++c, ++gi) {
-        const int g = gi & 1, bs = gi % V3_NB;
+    // the 24 (SINGLE: 8) MMAs of a chunk in issue order; `first` clears the accumulators at the start of a unit
+    auto issue = [&](int m, int g, uint64_t b_big, uint64_t b_small, uint32_t first) {
+      constexpr int PER_H = SINGLE ? BK / 8 : 3 * (BK / 8);
+      const int h = m / PER_H, r = m % PER_H;
+      const int ks = SINGLE ? r : r / 3, pass = SINGLE ? 2 : r % 3;
+      const uint32_t d_tmem = tmem_base + h * BN;
+      const uint32_t a_big = tmem_base + (uint32_t)(V3_A_COL0 + (g * 2 + h) * 64) + ks * 8, a_small = a_big + 32;
+      const uint64_t adv = (uint64_t)((ks * 32) >> 4);
+      const uint32_t acc = r == 0 ? first : 1u;
+      if (SINGLE) umma_tf32_ts(d_tmem, a_big, b_big + adv, IDESC_TF32, acc);
+      else if (pass == 0) umma_tf32_ts(d_tmem, a_small, b_big + adv, IDESC_TF32, acc);
+      else if (pass == 1) umma_tf32_ts(d_tmem, a_big, b_small + adv, IDESC_TF32, 1u);
+      else umma_tf32_ts(d_tmem, a_big, b_big + adv, IDESC_TF32, 1u);
+    };
+    constexpr int NMMA = SINGLE ? 2 * (BK / 8) : 6 * (BK / 8);
+    if (PHC_V3_ISSUE_MODE == 0) {
+      int gi = 0;
+      for (int si = 0; si < nseg; ++si) {
+        const V3Seg sg = v3_seg(p, gb, ge, si);
         if (prof) tp = clock64();
-        MMA_WAIT(smem_u32(&afull[g]), (gi >> 1) & 1);
-        if (prof) { const long long tn = clock64(); t_afull += tn - tp; tp = tn; }
-        if (!(p.ablate & 16)) MMA_WAIT(smem_u32(&bfull[bs]), (gi / V3_NB) & 1);
-        if (prof) t_bfull += clock64() - tp;
+        MMA_WAIT(smem_u32(tempty), (si & 1) ^ 1);                // both accumulators drained
+        if (prof) t_tempty += clock64() - tp;
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sb = smem_u32(bstage + bs * 2 * TILE_BYTES);
-          const uint64_t b_big = make_desc(sb), b_small = make_desc(sb + TILE_BYTES);
-          if (!(p.ablate & 1)) {
+        uint32_t accum = 0;
+        for (int c = sg.c0; c < sg.c1; ++c, ++gi) {
+          const int g = gi & 1, bs = gi % V3_NB;
+          if (prof) tp = clock64();
+          MMA_WAIT(smem_u32(&afull[g]), (gi >> 1) & 1);
+          if (prof) { const long long tn = clock64(); t_afull += tn - tp; tp = tn; }
+          if (!V3_ABL(16)) MMA_WAIT(smem_u32(&bfull[bs]), (gi / V3_NB) & 1);
+          if (prof) t_bfull += clock64() - tp;
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t sb = smem_u32(bstage + bs * 2 * TILE_BYTES);
+            const uint64_t b_big = make_desc(sb), b_small = make_desc(sb + TILE_BYTES);
+            if (!V3_ABL(1)) {
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const uint32_t d_tmem = tmem_base + h * BN;
-            const uint32_t a_big = tmem_base + (uint32_t)(V3_A_COL0 + (g * 2 + h) * 64), a_small = a_big + 32;
-            uint32_t acc = accum;
-#pragma unroll
-            for (int ks = 0; ks < BK / 8; ++ks) {
-              const uint64_t adv = (uint64_t)((ks * 32) >> 4);
-              if (SINGLE) {
-                umma_tf32_ts(d_tmem, a_big + ks * 8, b_big + adv, IDESC_TF32, acc);
-              } else {
-                umma_tf32_ts(d_tmem, a_small + ks * 8, b_big + adv, IDESC_TF32, acc);
-                umma_tf32_ts(d_tmem, a_big + ks * 8, b_small + adv, IDESC_TF32, 1u);
-                umma_tf32_ts(d_tmem, a_big + ks * 8, b_big + adv, IDESC_TF32, 1u);
-              }
-              acc = 1u;
+              for (int m = 0; m < NMMA; ++m) issue(m, g, b_big, b_small, accum);
             }
-          }
+            umma_commit(smem_u32(&aempty[g]));
+            if (!V3_ABL(16)) umma_commit(smem_u32(&bempty[bs]));
           }
           accum = 1u;
-          umma_commit(smem_u32(&aempty[g]));
-          if (!(p.ablate & 16)) umma_commit(smem_u32(&bempty[bs]));
+          __syncwarp();
         }
+        if (elect_one()) umma_commit(smem_u32(tfull));
         __syncwarp();
       }
-      if (lane == 0) umma_commit(smem_u32(tfull));
-      __syncwarp();
+    } else if (elect_one()) {
+      // One thread runs the whole issue loop.  Measured (round 2): the tensor pipe idles ~200 cycles at every chunk boundary — the
+      // queue behind tcgen05.mma is shallow, and commit + two barrier round trips + fence sit between the last MMA of a chunk and
+      // the first of the next.  Mode 2 moves the round trips in front of the chunk's last MMAs.
+      static_assert(PHC_V3_ISSUE_MODE != 0 || !PHC_V3_SPLIT_H, "PHC_V3_SPLIT_H needs the single-thread issue loop");
+      constexpr int NGRP = V3_AH, PER = NMMA / NGRP;             // issue groups per chunk (one per operand barrier), MMAs per group
+      constexpr int HOLD = PHC_V3_HOLD < PER ? PHC_V3_HOLD : PER - 1;
+      int gi = 0;
+      bool ready = false;                                        // the next group's barriers were already seen complete
+      for (int si = 0; si < nseg; ++si) {
+        const V3Seg sg = v3_seg(p, gb, ge, si);
+        if (prof) tp = clock64();
+        MMA_WAIT(smem_u32(tempty), (si & 1) ^ 1);                // both accumulators drained
+        if (prof) t_tempty += clock64() - tp;
+        uint32_t accum = 0;
+        for (int c = sg.c0; c < sg.c1; ++c, ++gi) {
+          const int g = gi & 1, bs = gi % V3_NB;
+          const uint32_t sb = smem_u32(bstage + bs * 2 * TILE_BYTES);
+          const uint64_t b_big = make_desc(sb), b_small = make_desc(sb + TILE_BYTES);
+#pragma unroll
+          for (int hg = 0; hg < NGRP; ++hg) {
+            if (!ready) {
+              if (prof) tp = clock64();
+              MMA_WAIT(smem_u32(&afull[g * NGRP + hg]), (gi >> 1) & 1);
+              if (prof) { const long long tn = clock64(); t_afull += tn - tp; tp = tn; }
+              if (hg == 0 && !V3_ABL(16)) MMA_WAIT(smem_u32(&bfull[bs]), (gi / V3_NB) & 1);
+              if (prof) t_bfull += clock64() - tp;
+            }
+            tc_fence_after();
+            ready = false;
+            if (!V3_ABL(1)) {
+#pragma unroll
+              for (int m = hg * PER; m < (hg + 1) * PER - HOLD; ++m) issue(m, g, b_big, b_small, accum);
+            }
+            if (PHC_V3_ISSUE_MODE == 2) {
+              if (hg + 1 < NGRP) {                               // the other component of this chunk
+                ready = mbar_test_wait(smem_u32(&afull[g * NGRP + hg + 1]), (gi >> 1) & 1);
+              } else if (c + 1 < sg.c1 || si + 1 < nseg) {       // the next chunk of this CTA, whatever its unit
+                const int gn = gi + 1;
+                ready = mbar_test_wait(smem_u32(&afull[(gn & 1) * NGRP]), (gn >> 1) & 1) &&
+                        (V3_ABL(16) || mbar_test_wait(smem_u32(&bfull[gn % V3_NB]), (gn / V3_NB) & 1));
+              }
+            }
+            if (!V3_ABL(1)) {
+#pragma unroll
+              for (int m = (hg + 1) * PER - HOLD; m < (hg + 1) * PER; ++m) issue(m, g, b_big, b_small, accum);
+            }
+            umma_commit(smem_u32(&aempty[g * NGRP + hg]));       // the slot(s) are free once these MMAs have retired
+          }
+          if (!V3_ABL(16)) umma_commit(smem_u32(&bempty[bs]));
+          accum = 1u;
+        }
+        umma_commit(smem_u32(tfull));
+      }
     }
     if (prof) {
       p.prof[blockIdx.x * 8 + 2] = t_tempty; p.prof[blockIdx.x * 8 + 3] = t_afull; p.prof[blockIdx.x * 8 + 4] = t_bfull;
@@ -1611,11 +1763,11 @@ __global__ void __launch_bounds__(DH2_THREADS, 1) phm_tc_dh_v2_kernel(const DhPa
       for (int k0 = kbeg; k0 < kend; k0 += BK, ++g) {
         const int rs = g & 1, ph = (g >> 1) & 1;
         mbar_wait(smem_u32(&rfull[rs]), ph);
-        const float* raw = reinterpret_cast<const float*>(rawbuf + rs * DH2_RAW_BYTES) + f;
+        const uint32_t raw = smem_u32(rawbuf + rs * DH2_RAW_BYTES) + (uint32_t)f * 4u;
         float v[BK];
         uint32_t lor = 0;
 #pragma unroll
-        for (int kk = 0; kk < BK; ++kk) { v[kk] = raw[kk * BM]; lor |= __float_as_uint(v[kk]); }
+        for (int kk = 0; kk < BK; ++kk) { v[kk] = lds_f32(raw + (uint32_t)(kk * BM * 4)); lor |= __float_as_uint(v[kk]); }
         // Early release: the column is in registers, let TMA refill the raw stage while we wait for the operand slot.
         // The arrive must not overtake the loads: a shared-memory store of a value that depends on every load cannot
         // issue before they have returned, and the arrive (release) stays behind the store.
@@ -1662,16 +1814,16 @@ __global__ void __launch_bounds__(DH2_THREADS, 1) phm_tc_dh_v2_kernel(const DhPa
       for (int k0 = kbeg; k0 < kend; k0 += BK, ++g) {
         const int rs = g & 1, ph = (g >> 1) & 1;
         mbar_wait(smem_u32(&rfull[rs]), ph);
-        const float* raw = reinterpret_cast<const float*>(rawbuf + rs * DH2_RAW_BYTES + DH2_RAW_X) + q;
+        const uint32_t raw = smem_u32(rawbuf + rs * DH2_RAW_BYTES + DH2_RAW_X) + (uint32_t)q * 4u;
         float v[BK];
         uint32_t lor = 0;
 #pragma unroll
-        for (int kk = 0; kk < BK; ++kk) { v[kk] = raw[kk * DH2_BN]; lor |= __float_as_uint(v[kk]); }
+        for (int kk = 0; kk < BK; ++kk) { v[kk] = lds_f32(raw + (uint32_t)(kk * DH2_BN * 4)); lor |= __float_as_uint(v[kk]); }
         asm volatile("st.shared.b32 [%0], %1;" ::"r"(smem_u32(landed + warp * 32 + lane)), "r"(lor) : "memory");   // early release, as above
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&rempty[rs]));
         mbar_wait(smem_u32(&bempty[rs]), ph ^ 1);
-        uint8_t* tb = bstage + rs * DH2_B_STAGE + tsel * 2 * TILE_BYTES;
+        const uint32_t tb = smem_u32(bstage + rs * DH2_B_STAGE + tsel * 2 * TILE_BYTES);
 #pragma unroll
         for (int ku = 0; ku < 8; ++ku) {
           float b[4], sm[4];
@@ -1689,9 +1841,9 @@ __global__ void __launch_bounds__(DH2_THREADS, 1) phm_tc_dh_v2_kernel(const DhPa
               unpack_f32x2(fma_f32x2(b2, bcast_f32x2(-1.f), v2), sm[j], sm[j + 1]);
             }
           }
-          const int off = swz(row, ku);
-          *reinterpret_cast<float4*>(tb + off) = make_float4(b[0], b[1], b[2], b[3]);
-          *reinterpret_cast<float4*>(tb + TILE_BYTES + off) = make_float4(sm[0], sm[1], sm[2], sm[3]);
+          const uint32_t off = (uint32_t)swz(row, ku);
+          sts_v4(tb + off, b[0], b[1], b[2], b[3]);
+          sts_v4(tb + TILE_BYTES + off, sm[0], sm[1], sm[2], sm[3]);
         }
         fence_proxy_async();
         __syncwarp();
@@ -1700,7 +1852,7 @@ __global__ void __launch_bounds__(DH2_THREADS, 1) phm_tc_dh_v2_kernel(const DhPa
       if (p.db_part != nullptr && i0 == 0 && o0 + q < p.Out) p.db_part[(size_t)split * p.Out + o0 + q] = colsum;
     }
   } else if (warp == DH2_TMA_WARP) {
-    if (lane == 0) {
+    if (elect_one()) {
       int g = 0;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
         int i0, o0, split, kbeg, kend;
@@ -1716,19 +1868,25 @@ __global__ void __launch_bounds__(DH2_THREADS, 1) phm_tc_dh_v2_kernel(const DhPa
       }
     }
   } else if (warp == DH2_MMA_WARP) {
-    int g = 0, it = 0;
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
-      int i0, o0, split, kbeg, kend;
-      dh2_tile(p, t, i0, o0, split, kbeg, kend);
-      mbar_wait(smem_u32(tempty), (it & 1) ^ 1);                  // accumulators drained
-      tc_fence_after();
-      uint32_t accum = 0;
-      for (int k0 = kbeg; k0 < kend; k0 += BK, ++g) {
-        const int rs = g & 1, ph = (g >> 1) & 1;
-        mbar_wait(smem_u32(&afull[rs]), ph);
-        mbar_wait(smem_u32(&bfull[rs]), ph);
-        tc_fence_after();
-        if (lane == 0) {
+    // One elected thread runs the whole issue loop (elect.sync, not `lane == 0`: the compiler then keeps descriptors and tensor-memory
+    // addresses in uniform registers instead of a per-MMA broadcast loop), spins on test_wait, and probes the next chunk's
+    // barriers before the last MMAs of the current one — see the mix kernel's issue loop.
+    if (elect_one()) {
+      int g = 0, it = 0;
+      bool ready = false;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+        int i0, o0, split, kbeg, kend;
+        dh2_tile(p, t, i0, o0, split, kbeg, kend);
+        mbar_spin(smem_u32(tempty), (it & 1) ^ 1);                // accumulators drained
+        uint32_t accum = 0;
+        for (int k0 = kbeg; k0 < kend; k0 += BK, ++g) {
+          const int rs = g & 1, ph = (g >> 1) & 1;
+          if (!ready) {
+            mbar_spin(smem_u32(&afull[rs]), ph);
+            mbar_spin(smem_u32(&bfull[rs]), ph);
+          }
+          tc_fence_after();
+          ready = false;
           const uint32_t a_big = tmem_base + (uint32_t)(DH2_A_COL0 + rs * 64), a_small = a_big + 32;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -1739,6 +1897,10 @@ __global__ void __launch_bounds__(DH2_THREADS, 1) phm_tc_dh_v2_kernel(const DhPa
 #pragma unroll
             for (int ks = 0; ks < BK / 8; ++ks) {
               const uint64_t adv = (uint64_t)((ks * 32) >> 4);
+              if (h == 1 && ks == BK / 8 - 1 && (k0 + BK < kend || t + (int)gridDim.x < p.num_tiles)) {
+                const int gn = g + 1;                            // next chunk of this CTA (this tile's or the next one's)
+                ready = mbar_test_wait(smem_u32(&afull[gn & 1]), (gn >> 1) & 1) && mbar_test_wait(smem_u32(&bfull[gn & 1]), (gn >> 1) & 1);
+              }
               if (p.single) {
                 umma_tf32_ts(d_tmem, a_big + ks * 8, b_big + adv, IDESC_TF32, acc);
               } else {
@@ -1753,10 +1915,8 @@ __global__ void __launch_bounds__(DH2_THREADS, 1) phm_tc_dh_v2_kernel(const DhPa
           umma_commit(smem_u32(&aempty[rs]));
           umma_commit(smem_u32(&bempty[rs]));
         }
-        __syncwarp();
+        umma_commit(smem_u32(tfull));
       }
-      if (lane == 0) umma_commit(smem_u32(tfull));
-      __syncwarp();
     }
   } else {
     // ===================================================================== epilogue: TMEM -> registers -> 16-byte row stores
@@ -2048,7 +2208,7 @@ int try_launch_mix_v3(const MixParams& p, cudaStream_t stream) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (enc == nullptr) return -1;
   CUtensorMap tmap;
-  const int R = p.Kin & 3;
+  const int R = PHC_V3_UNALIGNED_TMA ? 0 : (p.Kin & 3);
   const cuuint64_t gdim[2] = {(cuuint64_t)Fin, (cuuint64_t)p.M};
   const cuuint64_t gstride[1] = {(cuuint64_t)Fin * 4};
   const cuuint32_t box[2] = {(cuuint32_t)(BK / 4 + (R ? 4 : 0)), (cuuint32_t)BM};
