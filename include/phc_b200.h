@@ -205,29 +205,12 @@ size_t phc_conv_fused_fwd_sums_workspace_bytes(int width, int table_rows);
 int phc_conv_fused_fwd_sums(const float* x, const float* node_sums, int enc_kind, int enc_dim, const int* vocab, const float* const* params,
                             const int* rowptr, const int* col, int num_nodes, int width, int phm_dim, int reduce, int self_loop,
                             float* out, void* workspace, size_t workspace_bytes, phc_stream_t stream);
-/* Same, with the graph table of the mini-batch (graph_ptr [num_graphs+1] from phc_segment_ptr_build; NULL: as above): one CTA per
- * (graph, 64-feature slice) stages the graph's rows in shared memory and gathers from there instead of from L2 — a PyG batch is
- * block diagonal, so every neighbour of a node is one of its graph's contiguous rows (neighbours outside the graph and graphs larger
- * than the staging buffer are read from global memory: the result never depends on the table being "right").  Bit-identical to the
- * untiled call.  Reference: the propagate() gather + scatter of messagepassing.py:55-70 on a torch_geometric Batch. */
-int phc_conv_fused_fwd_sums_tiled(const float* x, const float* node_sums, int enc_kind, int enc_dim, const int* vocab,
-                                  const float* const* params, const int* rowptr, const int* col, const int* graph_ptr, int num_graphs,
-                                  int num_nodes, int width, int phm_dim, int reduce, int self_loop, float* out, void* workspace,
-                                  size_t workspace_bytes, phc_stream_t stream);
 size_t phc_conv_fused_bwd_workspace_bytes(int num_nodes, int width, int table_rows);
 int phc_conv_fused_bwd(const float* gout, const float* x, const void* edge_attr, int enc_kind, int enc_dim, const int* vocab,
                        const float* const* params, float* const* dparams, const float* aux_f, const int* aux_i, const int* rowptr,
                        const int* col, const int* perm, const int* rowptr_t, const int* col_t, const int* perm_t, int num_nodes,
                        int width, int phm_dim, int reduce, int msg_act, const float* beta, int self_loop, const float* node_sums,
                        float* dx, float* dbeta, void* workspace, size_t workspace_bytes, phc_stream_t stream);
-/* phc_conv_fused_bwd with the graph table (see phc_conv_fused_fwd_sums_tiled): the input gradient of the sum / mean + identity-message
- * case gathers from shared memory. */
-int phc_conv_fused_bwd_tiled(const float* gout, const float* x, const void* edge_attr, int enc_kind, int enc_dim, const int* vocab,
-                             const float* const* params, float* const* dparams, const float* aux_f, const int* aux_i, const int* rowptr,
-                             const int* col, const int* perm, const int* rowptr_t, const int* col_t, const int* perm_t,
-                             const int* graph_ptr, int num_graphs, int num_nodes, int width, int phm_dim, int reduce, int msg_act,
-                             const float* beta, int self_loop, const float* node_sums, float* dx, float* dbeta, void* workspace,
-                             size_t workspace_bytes, phc_stream_t stream);
 /* node_sums [N, table_rows] (optional, sum/mean + identity message only): per-node sums of the edge features
  * (Linear: raw features and in-degree; embeddings: value histograms), scaled by 1/deg for mean.  Depends only on
  * the batch, so it is computed once and shared by all layers; with it the encoder gradients need no edge loop. */

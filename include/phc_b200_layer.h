@@ -58,9 +58,6 @@ typedef struct phc_conv_layer {
   float* const* d_enc_params;              /* HOST array of device pointers */
   float *d_rule1, *d_W1, *d_b1, *d_rule2, *d_W2, *d_b2;   /* d_rule*, d_b* may be NULL */
   float *d_gb1, *d_gb2;                    /* [2, width] each: dgamma then dbeta */
-  /* optional graph table of the mini-batch (phc_segment_ptr_build): graph-tiled gather, see phc_conv_fused_fwd_sums_tiled */
-  const int* graph_ptr;                    /* [num_graphs + 1] or NULL */
-  int num_graphs;
 } phc_conv_layer;
 
 #endif /* PHC_B200_LAYER_H */

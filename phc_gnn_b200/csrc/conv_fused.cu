@@ -15,14 +15,6 @@
 #include <float.h>
 
 // simple (sum/mean, identity message) input gradient lives in aggregate.cu
-// gather_tiled.cu: the same aggregation with the gathered rows staged in shared memory per graph of the batch
-bool phc_gather_tiled_ok(const int* graph_ptr, int num_graphs, int num_nodes, int width, const void* a, const void* b);
-int phc_conv_fwd_sums_tiled_launch(bool mean, const float* x, const float* node_sums, const float* tab, const int* rowptr, const int* col,
-                                   const int* graph_ptr, int num_graphs, int num_nodes, int width, int table_rows, int self_loop,
-                                   float* out, cudaStream_t stream);
-int phc_aggregate_bwd_node_tiled_launch(bool mean, const float* g, const int* rowptr, const int* rowptr_t, const int* col_t,
-                                        const int* graph_ptr, int num_graphs, int num_nodes, int width, int self_loop, float* dx,
-                                        cudaStream_t stream);
 int phc_aggregate_bwd_node_simple(bool mean, const float* g, const int* rowptr, const int* rowptr_t, const int* col_t, const int* perm_t,
                                   int N, int F, int self_loop, float* dx, cudaStream_t stream);
 
@@ -623,18 +615,6 @@ bool ensure_smem(K kern, size_t bytes) {
 
 extern "C" {
 
-int phc_conv_fused_fwd_sums_tiled(const float* x, const float* node_sums, int enc_kind, int enc_dim, const int* vocab,
-                                  const float* const* params, const int* rowptr, const int* col, const int* graph_ptr, int num_graphs,
-                                  int num_nodes, int width, int phm_dim, int reduce, int self_loop, float* out, void* workspace,
-                                  size_t workspace_bytes, cudaStream_t stream);
-int phc_conv_fused_bwd_tiled(const float* gout, const float* x, const void* edge_attr, int enc_kind, int enc_dim, const int* vocab,
-                             const float* const* params, float* const* dparams, const float* aux_f, const int* aux_i, const int* rowptr,
-                             const int* col, const int* perm, const int* rowptr_t, const int* col_t, const int* perm_t,
-                             const int* graph_ptr, int num_graphs, int num_nodes, int width, int phm_dim, int reduce, int msg_act,
-                             const float* beta, int self_loop, const float* node_sums, float* dx, float* dbeta, void* workspace,
-                             size_t workspace_bytes, cudaStream_t stream);
-
-
 // 1 if the fused path can run this configuration (otherwise the caller uses encoder + phc_aggregate_*)
 int phc_conv_fused_supported(int width, int phm_dim, int enc_kind, int enc_dim, int table_rows) {
   if (width % 4 != 0 || width / 4 > 256 || phm_dim < 1 || width % phm_dim != 0) return 0;
@@ -683,14 +663,6 @@ size_t phc_conv_fused_fwd_sums_workspace_bytes(int width, int table_rows) { retu
 int phc_conv_fused_fwd_sums(const float* x, const float* node_sums, int enc_kind, int enc_dim, const int* vocab, const float* const* params,
                             const int* rowptr, const int* col, int num_nodes, int width, int phm_dim, int reduce, int self_loop,
                             float* out, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-  return phc_conv_fused_fwd_sums_tiled(x, node_sums, enc_kind, enc_dim, vocab, params, rowptr, col, nullptr, 0, num_nodes, width, phm_dim,
-                                       reduce, self_loop, out, workspace, workspace_bytes, stream);
-}
-
-int phc_conv_fused_fwd_sums_tiled(const float* x, const float* node_sums, int enc_kind, int enc_dim, const int* vocab,
-                                  const float* const* params, const int* rowptr, const int* col, const int* graph_ptr, int num_graphs,
-                                  int num_nodes, int width, int phm_dim, int reduce, int self_loop, float* out, void* workspace,
-                                  size_t workspace_bytes, cudaStream_t stream) {
   PHC_REQUIRE(reduce == PHC_RED_SUM || reduce == PHC_RED_MEAN, "phc_conv_fused_fwd_sums: sum / mean only (got reduce %d)", reduce);
   PHC_REQUIRE(node_sums != nullptr, "phc_conv_fused_fwd_sums: node_sums required");
   EncDesc d;
@@ -701,9 +673,6 @@ int phc_conv_fused_fwd_sums_tiled(const float* x, const float* node_sums, int en
   if (num_nodes == 0) return PHC_OK;
   float* tab = reinterpret_cast<float*>(workspace);
   phc_launch(enc_table_kernel, dim3(phc_div_up((long long)d.R * width, 256)), dim3(256), 0, stream, d, width, tab);
-  if (phc_gather_tiled_ok(graph_ptr, num_graphs, num_nodes, width, x, out))
-    return phc_conv_fwd_sums_tiled_launch(reduce == PHC_RED_MEAN, x, node_sums, tab, rowptr, col, graph_ptr, num_graphs, num_nodes, width, d.R,
-                                          self_loop, out, stream);
   const int grid = phc_div_up((long long)num_nodes * (width / 4), 256);
   if (reduce == PHC_RED_MEAN)
     phc_launch(conv_fwd_sums_kernel<true>, dim3(grid), dim3(256), 0, stream, x, node_sums, tab, rowptr, col, num_nodes, width, d.R, self_loop, out);
@@ -736,24 +705,6 @@ int phc_conv_fused_bwd(const float* gout, const float* x, const void* edge_attr,
                        const int* col, const int* perm, const int* rowptr_t, const int* col_t, const int* perm_t, int num_nodes,
                        int width, int phm_dim, int reduce, int msg_act, const float* beta, int self_loop, const float* node_sums,
                        float* dx, float* dbeta, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-  return phc_conv_fused_bwd_tiled(gout, x, edge_attr, enc_kind, enc_dim, vocab, params, dparams, aux_f, aux_i, rowptr, col, perm, rowptr_t,
-                                  col_t, perm_t, nullptr, 0, num_nodes, width, phm_dim, reduce, msg_act, beta, self_loop, node_sums, dx, dbeta,
-                                  workspace, workspace_bytes, stream);
-}
-
-int phc_conv_fused_bwd_tiled(const float* gout, const float* x, const void* edge_attr, int enc_kind, int enc_dim, const int* vocab,
-                             const float* const* params, float* const* dparams, const float* aux_f, const int* aux_i, const int* rowptr,
-                             const int* col, const int* perm, const int* rowptr_t, const int* col_t, const int* perm_t,
-                             const int* graph_ptr, int num_graphs, int num_nodes, int width, int phm_dim, int reduce, int msg_act,
-                             const float* beta, int self_loop, const float* node_sums, float* dx, float* dbeta, void* workspace,
-                             size_t workspace_bytes, cudaStream_t stream) {
-  // input gradient of the sum / mean + identity-message case: graph-tiled gather when the batch's graph table is given
-  auto node_simple = [&]() -> int {
-    if (phc_gather_tiled_ok(graph_ptr, num_graphs, num_nodes, width, gout, dx))
-      return phc_aggregate_bwd_node_tiled_launch(reduce == PHC_RED_MEAN, gout, rowptr, rowptr_t, col_t, graph_ptr, num_graphs, num_nodes, width,
-                                                 self_loop, dx, stream);
-    return phc_aggregate_bwd_node_simple(reduce == PHC_RED_MEAN, gout, rowptr, rowptr_t, col_t, perm_t, num_nodes, width, self_loop, dx, stream);
-  };
   EncDesc d;
   PHC_REQUIRE(make_desc(d, enc_kind, enc_dim, vocab, params, dparams, phm_dim, width) == 0, "phc_conv_fused_bwd: unsupported encoder");
   PHC_REQUIRE(phc_conv_fused_supported(width, phm_dim, enc_kind, enc_dim, d.R), "phc_conv_fused_bwd: unsupported shape");
@@ -780,7 +731,7 @@ int phc_conv_fused_bwd_tiled(const float* gout, const float* x, const void* edge
     phc_launch(conv_bwd_param_final_kernel, dim3(phc_div_up((long long)d.R * F, 32)), dim3(1024), 0, stream, d, part, nb, F);
     int rc = phc_check_launch("phc_conv_fused_bwd(node sums)");
     if (rc) return rc;
-    if (dx) return node_simple();
+    if (dx) return phc_aggregate_bwd_node_simple(reduce == PHC_RED_MEAN, gout, rowptr, rowptr_t, col_t, perm_t, N, F, self_loop, dx, stream);
     return PHC_OK;
   }
   const int dt = (enc_kind == ENC_LINEAR && enc_dim <= 8) ? enc_dim : 0;
@@ -811,7 +762,8 @@ int phc_conv_fused_bwd_tiled(const float* gout, const float* x, const void* edge
   if (reduce == PHC_RED_SOFTMAX && dbeta) phc_launch(sum_partials_kernel, dim3(1), dim3(256), 0, stream, dbp, blocks_used, dbeta);
   int rc = phc_check_launch("phc_conv_fused_bwd");
   if (rc) return rc;
-  if (dx && simple && N > 0) return node_simple();
+  if (dx && simple && N > 0)
+    return phc_aggregate_bwd_node_simple(reduce == PHC_RED_MEAN, gout, rowptr, rowptr_t, col_t, perm_t, N, F, self_loop, dx, stream);
   return PHC_OK;
 }
 

@@ -52,9 +52,8 @@ int phc_conv_layer_fwd(const phc_conv_layer* L, phc_stream_t stream) {
   if (N == 0) return 0;
   // 1. aggregation with the edge encoder fused in
   if (L->node_sums != nullptr && (L->reduce == PHC_RED_SUM || L->reduce == PHC_RED_MEAN) && L->msg_act == PHC_ACT_IDENTITY)
-    rc = phc_conv_fused_fwd_sums_tiled(L->x, L->node_sums, L->enc_kind, L->enc_dim, L->vocab, L->enc_params, L->rowptr, L->col, L->graph_ptr,
-                                       L->num_graphs, N, F, n, L->reduce, L->self_loops && L->mlp, L->agg, L->ws, L->ws_bytes,
-                                       stream);                                                  // encoder term from the per-node sums
+    rc = phc_conv_fused_fwd_sums(L->x, L->node_sums, L->enc_kind, L->enc_dim, L->vocab, L->enc_params, L->rowptr, L->col, N, F, n, L->reduce,
+                                 L->self_loops && L->mlp, L->agg, L->ws, L->ws_bytes, stream);   // encoder term from the per-node sums
   else
     rc = phc_conv_fused_fwd(L->x, L->edge_attr, L->enc_kind, L->enc_dim, L->vocab, L->enc_params, L->rowptr, L->col, L->perm, N, F, n, L->reduce,
                             L->msg_act, L->softmax_beta, L->self_loops && L->mlp, L->agg, L->aux_f, L->aux_i, stream);
@@ -133,10 +132,9 @@ int phc_conv_layer_bwd(const phc_conv_layer* L, phc_stream_t stream) {
   }
   if (rc) return rc;
   // 1'
-  return phc_conv_fused_bwd_tiled(dagg, L->x, L->edge_attr, L->enc_kind, L->enc_dim, L->vocab, L->enc_params, L->d_enc_params, L->aux_f,
-                                  L->aux_i, L->rowptr, L->col, L->perm, L->rowptr_t, L->col_t, L->perm_t, L->graph_ptr, L->num_graphs, N, F, n,
-                                  L->reduce, L->msg_act, L->softmax_beta, L->self_loops && L->mlp, L->node_sums, L->dx, L->d_softmax_beta,
-                                  L->ws, L->ws_bytes, stream);
+  return phc_conv_fused_bwd(dagg, L->x, L->edge_attr, L->enc_kind, L->enc_dim, L->vocab, L->enc_params, L->d_enc_params, L->aux_f, L->aux_i,
+                            L->rowptr, L->col, L->perm, L->rowptr_t, L->col_t, L->perm_t, N, F, n, L->reduce, L->msg_act, L->softmax_beta,
+                            L->self_loops && L->mlp, L->node_sums, L->dx, L->d_softmax_beta, L->ws, L->ws_bytes, stream);
 }
 
 }  // extern "C"

@@ -323,9 +323,6 @@ def _call_fwd(cfg, struct: EdgeStructure, flats, x, skip, attr, tensors):
     D.ws, D.ws_bytes = ws.data_ptr(), ws.numel()
     sums = _node_sums(struct, attr, linear, enc_dim, vocab, vc, reduce, msg_act, rows, N, dev, st) if NODE_SUM_FORWARD else None
     D.node_sums = _ptr(sums)
-    seg = struct.extras.get("graph_table")                     # nn.attach_graph_table: graph-tiled gather (kept alive by `struct`)
-    if seg is not None:
-        D.graph_ptr, D.num_graphs = seg.graph_ptr.data_ptr(), seg.num_graphs
     fused_stats = precision != 0 and n == 4 and training        # batch-norm statistics come out of the PHMLinear epilogue
     run("phc_conv_layer_fwd", None, ctypes.byref(D), st,
         launches=(11 if mlp else 6) - ((int(use_bn1 and mlp) + int(use_bn2)) if fused_stats else 0))

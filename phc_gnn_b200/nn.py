@@ -855,7 +855,6 @@ class PHMSkipConnectAdd(_PHMSkipConnectBase):
         x, edge_index, edge_attr, batch = data.x, data.edge_index, data.edge_attr, data.batch
         if isinstance(self.bond_input_dims, list):
             edge_attr = edge_attr.to(torch.long)
-        attach_graph_table(data)
         h0 = self.atomencoder.flat(x)
         h = h0
         L = len(self.mp_layers)
@@ -894,24 +893,6 @@ class PHMSkipConnectAdd(_PHMSkipConnectBase):
         return self.downstream(out)
 
 
-GRAPH_TILED_GATHER = True      # A/B switch: sum / mean aggregation from shared-memory tiles, one per graph of the batch
-
-
-def attach_graph_table(data) -> None:
-    """Hand the batch's graph offsets (the ``batch`` vector the pooling reads, models.py:219-232) to the message-passing layers: with
-    them the sum / mean aggregation stages each graph's rows in shared memory (csrc/gather_tiled.cu).  The convolutions keep the
-    reference's signature (x, edge_index, edge_attr), so the table travels on the cached edge structure of this batch.  Only when
-    the number of graphs is known without a device read-back and rows are gathered often enough for the staging to pay."""
-    num_graphs = getattr(data, "num_graphs", None)
-    if not GRAPH_TILED_GATHER or num_graphs is None or not data.edge_index.is_cuda:
-        return
-    struct = edge_structure(data.edge_index, data.x.size(0))
-    if "graph_table" in struct.extras:
-        return
-    N, E, B = struct.num_nodes, struct.num_edges, int(num_graphs)
-    struct.extras["graph_table"] = segment_structure(data.batch, B) if (B > 0 and E >= 4 * N and N >= 16 * B) else None
-
-
 class PHMSkipConnectConcat(_PHMSkipConnectBase):
     """Skip connections through concatenation — reference models.py:271-517.  The reference's forward
     raises for every phm_dim > 1 (models.py:486 reshapes the layer-0 bond embedding n times too wide,
@@ -940,7 +921,6 @@ class PHMSkipConnectConcat(_PHMSkipConnectBase):
         x, edge_index, edge_attr, batch = data.x, data.edge_index, data.edge_attr, data.batch
         if isinstance(self.bond_input_dims, list):
             edge_attr = edge_attr.to(torch.long)
-        attach_graph_table(data)
         h0 = self.atomencoder.flat(x)
         h = h0
         act = self.activation_str.lower()

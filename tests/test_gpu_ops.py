@@ -528,78 +528,3 @@ def test_conv_forward_from_node_sums(reduce, linear, F, n, self_loop):
     torch.cuda.synchronize()
     assert_close(out.cpu(), ref.float(), RTOL, 5e-5, "node-sums kernel vs fp64 oracle")
     assert_close(out.cpu(), edge.detach().cpu(), RTOL, 5e-5, "node-sums kernel vs per-edge kernel")
-
-
-def _block_diagonal_graph(sizes, deg, seed, cross=0):
-    """Directed edges inside consecutive node blocks (a PyG mini-batch); `cross` extra edges between arbitrary blocks."""
-    g = torch.Generator().manual_seed(seed)
-    src, dst, off = [], [], 0
-    for s in sizes:
-        if s > 1:
-            m = s * deg
-            src.append(torch.randint(0, s, (m,), generator=g) + off)
-            dst.append(torch.randint(0, s, (m,), generator=g) + off)
-        off += s
-    ei = torch.stack([torch.cat(src), torch.cat(dst)])
-    if cross:
-        ei = torch.cat([ei, torch.randint(0, off, (2, cross), generator=g)], 1)
-    return ei.contiguous(), off
-
-
-@pytest.mark.parametrize("reduce,F,sizes,cross,self_loop", [
-    ("add", 500, [243, 187, 300, 1, 0, 260], 0, True),          # ppa-like blocks, a single-node and an EMPTY graph
-    ("mean", 224, [70, 66, 75, 71] * 6, 0, False),              # superpixel-like, mean
-    ("add", 52, [40, 500, 33], 0, True),                        # one slice narrower than 64 features; a graph above the staging cap
-    ("mean", 200, [90, 110, 95], 37, True),                     # NOT a PyG batch: edges that cross graph boundaries
-])
-def test_graph_tiled_gather_is_bit_identical(reduce, F, sizes, cross, self_loop):
-    """phc_conv_fused_fwd_sums_tiled / phc_conv_fused_bwd_tiled (rows staged in shared memory per graph, gather_tiled.cu) against the
-    untiled calls on the same inputs: bit-identical outputs and input gradients, whatever the graph table looks like."""
-    import ctypes
-    from phc.hypercomplex.encoder import PHMEncoder
-    from phc_gnn_b200 import _lib
-    from phc_gnn_b200.graph import EdgeStructure, SegmentStructure, _stream
-    from phc_gnn_b200.ops import REDUCE_IDS, _ptr_array, run
-    n = 4
-    ei, N = _block_diagonal_graph(sizes, 9, 3, cross)
-    E = ei.size(1)
-    g = torch.Generator().manual_seed(8)
-    enc = PHMEncoder(F // n, 7, n).to(DEV)
-    linear_, params, vocab = enc.fusable_params()
-    at = torch.rand(E, 7, generator=g).to(DEV)
-    x, gout = torch.randn(N, F, generator=g).to(DEV), torch.randn(N, F, generator=g).to(DEV)
-    batch = torch.repeat_interleave(torch.arange(len(sizes)), torch.tensor(sizes)).to(DEV)
-    s = EdgeStructure(ei.to(DEV), N)
-    seg = SegmentStructure(batch, len(sizes))
-    lib = _lib.load()
-    st = _stream(torch.device(DEV))
-    red = REDUCE_IDS[reduce]
-    rows = 8
-    sums = torch.empty((N, rows), device=DEV)
-    run("phc_edge_feature_sums", None, at.data_ptr(), 0, 7, None, s.rowptr.data_ptr(), s.perm.data_ptr(), N, int(red == 1), sums.data_ptr(), st)
-    ws = torch.empty(max(lib.phc_conv_fused_fwd_sums_workspace_bytes(F, rows), lib.phc_conv_fused_bwd_workspace_bytes(N, F, rows)) + 64,
-                     dtype=torch.uint8, device=DEV)
-    outs, dxs, dps = [], [], []
-    for gp, ng in ((None, 0), (seg.graph_ptr.data_ptr(), len(sizes))):
-        out = torch.full((N, F), float("nan"), device=DEV)
-        run("phc_conv_fused_fwd_sums_tiled", None, x.data_ptr(), sums.data_ptr(), 0, 7, None, _ptr_array(params), s.rowptr.data_ptr(),
-            s.col.data_ptr(), gp, ng, N, F, n, red, int(self_loop), out.data_ptr(), ws.data_ptr(), ws.numel(), st)
-        dx = torch.full((N, F), float("nan"), device=DEV)
-        grads = [torch.zeros_like(p) for p in params]
-        run("phc_conv_fused_bwd_tiled", None, gout.data_ptr(), x.data_ptr(), at.data_ptr(), 0, 7, None, _ptr_array(params), _ptr_array(grads),
-            None, None, s.rowptr.data_ptr(), s.col.data_ptr(), s.perm.data_ptr(), s.rowptr_t.data_ptr(), s.col_t.data_ptr(),
-            s.perm_t.data_ptr(), gp, ng, N, F, n, red, 0, None, int(self_loop), sums.data_ptr(), dx.data_ptr(), None, ws.data_ptr(),
-            ws.numel(), st)
-        torch.cuda.synchronize()
-        outs.append(out.cpu()); dxs.append(dx.cpu()); dps.append([p.cpu() for p in grads])
-    assert not torch.isnan(outs[1]).any() and not torch.isnan(dxs[1]).any(), "tiled kernels left rows unwritten"
-    assert torch.equal(outs[0], outs[1]), "forward: tiled != untiled"
-    assert torch.equal(dxs[0], dxs[1]), "input gradient: tiled != untiled"
-    for a, b in zip(dps[0], dps[1]):
-        assert torch.equal(a, b)
-    # and against the fp64 restatement
-    po = {f"e.{k}": v.detach().cpu().double() for k, v in enc.state_dict().items()}
-    ref = O.propagate(x.cpu().double(), ei, O.encoder(at.cpu(), po, "e", n, 7, torch.float64), reduce, "identity", torch.tensor(1.0).double())
-    if self_loop:
-        ref = ref + x.cpu().double()
-    assert_close(outs[1], ref.float(), RTOL, 5e-5, "tiled node-sums kernel vs fp64 oracle")
