@@ -329,7 +329,7 @@ __device__ __forceinline__ void mma_tile(const Smem& s, uint32_t tmem_base, int 
     mbar_wait(smem_u32(&s.full_bar[stage]), phase);
     if (prof && lane == 0) prof[3] += clock64() - t0;
     tc_fence_after();
-    if (lane == 0) {
+    if (elect_one()) {                  // elect.sync: descriptors and tensor-memory addresses stay in uniform registers
       const uint32_t sa = smem_u32(s.stages + stage * STAGE_BYTES);
       const uint64_t a_big = make_desc(sa), a_small = make_desc(sa + TILE_BYTES);
       const uint64_t b_big = make_desc(sa + 2 * TILE_BYTES), b_small = make_desc(sa + 3 * TILE_BYTES);
@@ -350,7 +350,7 @@ __device__ __forceinline__ void mma_tile(const Smem& s, uint32_t tmem_base, int 
     __syncwarp();
     if (++stage == NS) { stage = 0; phase ^= 1; }
   }
-  if (lane == 0) umma_commit(smem_u32(&s.tfull_bar[buf]));          // accumulator complete -> epilogue
+  if (elect_one()) umma_commit(smem_u32(&s.tfull_bar[buf]));        // accumulator complete -> epilogue
   __syncwarp();
 }
 
@@ -728,7 +728,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) phm_tc_mix_tma_kernel(const Mi
     }
   } else if (warp == TMA_X_WARP) {
     // ===================================================================== TMA: raw activation boxes
-    if (lane == 0) {
+    if (elect_one()) {
       int g = 0;
       for (int ti = 0; ti < my_tiles; ++ti) {
         int m0, comp, pt;
@@ -746,7 +746,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) phm_tc_mix_tma_kernel(const Mi
     }
   } else if (warp == TMA_B_WARP) {
     // ===================================================================== TMA: pre-split W chunks
-    if (lane == 0) {
+    if (elect_one()) {
       int g = 0;
       for (int ti = 0; ti < my_tiles; ++ti) {
         int m0, comp, pt;
@@ -1648,7 +1648,7 @@ __global__ void __launch_bounds__(DH_TMA_THREADS, 1) phm_tc_dh_tma_kernel(const 
         p.db_part[((size_t)split * 2 + (q >> 7)) * p.Out + o0 + (q & (BN - 1))] = colsum;
     }
   } else if (warp == MMA_WARP + 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       int g = 0;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
         int i0, o0, split, kbeg, kend;
