@@ -152,6 +152,10 @@ int phc_bn_act_drop_skip_bwd_strided(const float* dy, int dy_row_stride, const f
  * gradient of a skip connection that fans out to every layer (models.py:227-236, sc_type="first"). */
 int phc_sum_tensors(const float* const* srcs, int count, long long numel, float* out, phc_stream_t stream);
 
+/* ---- index validation: the embedding kernels clamp an index outside its table (nn.Embedding raises); this ORs bit 0 into the device
+ * word *status for any idx[r, c] outside [0, vocab[c]) — read it back when you want to know (synchronising, debug / tests). ---------- */
+int phc_index_check(const long long* idx, const int* vocab, int rows, int cols, int* status, phc_stream_t stream);
+
 /* ---- encoders (encoder.py:31-34; quaternion/encoder.py:44-56) ---------------------------------
  * tables / weights / biases are HOST arrays of device pointers, ordered [component][column]. */
 int phc_embed_sum_fwd(const long long* idx, const float* const* tables, const int* vocab, int rows, int cols, int phm_dim,
@@ -248,6 +252,17 @@ int phc_weight_reg_fwd(const float* const* weights, const int* phm_dims, const i
                        size_t workspace_bytes, phc_stream_t stream);
 int phc_weight_reg_bwd(const float* gout, const float* const* weights, float* const* dweights, const int* phm_dims, const int* kp,
                        int count, phc_stream_t stream);
+/* dweights[l] += ... : the regulariser's gradient added onto gradients that are already in place (the flat gradient buffer), one
+ * launch for all weight tensors instead of one autograd accumulation kernel per tensor. */
+int phc_weight_reg_bwd_accumulate(const float* gout, const float* const* weights, float* const* dweights, const int* phm_dims,
+                                  const int* kp, int count, phc_stream_t stream);
+
+/* ---- task loss of the training step and its gradient in one launch (train_ppa.py / train_mnist.py:200 cross entropy;
+ * train_hiv.py:174-178 / train_pcba.py BCE-with-logits over the labelled entries; train_zinc.py:192 mean absolute error) -------
+ * kind 0: logits [rows, cols], targets int64 [rows];  kind 1: targets float [rows, cols], NaN = unlabelled;  kind 2: cols = 1,
+ * targets float [rows].  loss: device scalar (mean);  dlogits [rows, cols]: d(loss)/d(logits). */
+int phc_task_loss(int kind, const float* logits, const void* targets, int rows, int cols, float* loss, float* dlogits,
+                  phc_stream_t stream);
 
 /* ---- clip_grad_norm_(max_norm) + Adam.step() on one flat buffer (train_hiv.py:199-201) --------------------
  * coef = min(1, max_norm/(||grads||_2 + 1e-6)) (max_norm <= 0: no clipping); Adam with weight_decay 0;

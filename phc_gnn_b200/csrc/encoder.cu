@@ -293,7 +293,31 @@ int linenc_chunks(int R) {
 
 }  // namespace
 
+namespace {
+// The embedding kernels (here and the fused edge encoder in conv_fused.cu) CLAMP an index outside its table, where nn.Embedding raises
+// (a device-side assertion that would poison the context).  This check is the reporting side: it ORs bit 0 into *status for any
+// index outside [0, vocab[col]); the host reads the word when it wants to know (ops.validate_indices — debug / tests, synchronising).
+__global__ void __launch_bounds__(256) index_check_kernel(const long long* __restrict__ idx, IntTable vocab, long long total, int C,
+                                                          int* __restrict__ status) {
+  pdl_begin();
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const long long v = __ldg(idx + t);
+  if (v < 0 || v >= vocab.v[(int)(t % C)]) atomicOr(status, 1);
+}
+}  // namespace
+
 extern "C" {
+
+int phc_index_check(const long long* idx, const int* vocab, int rows, int cols, int* status, cudaStream_t stream) {
+  PHC_REQUIRE(cols > 0 && cols <= PHC_MAX_TABLES && status != nullptr, "phc_index_check: cols=%d (max %d), status required", cols, PHC_MAX_TABLES);
+  if (rows == 0) return PHC_OK;
+  IntTable vc;
+  for (int i = 0; i < cols; ++i) vc.v[i] = vocab[i];
+  const long long total = (long long)rows * cols;
+  phc_launch(index_check_kernel, dim3(phc_div_up(total, 256)), dim3(256), 0, stream, idx, vc, total, cols, status);
+  return phc_check_launch("phc_index_check");
+}
 
 size_t phc_embed_bwd_workspace_bytes(int rows, int total_vocab, int width) {
   return sizeof(float) * (size_t)embed_chunks(rows, total_vocab, width) * total_vocab * width;

@@ -46,7 +46,7 @@ __global__ void reg_final_kernel(const float* __restrict__ part, int count, floa
 }
 
 // dW[b,i] = g * W[b,i] / (||W[:,i]|| * kp)
-__global__ void __launch_bounds__(256) reg_bwd_kernel(RegTable t, const float* __restrict__ gout) {
+__global__ void __launch_bounds__(256) reg_bwd_kernel(RegTable t, const float* __restrict__ gout, int accumulate) {
   pdl_begin();
   const int l = blockIdx.y;
   const int n = t.n[l], kp = t.kp[l];
@@ -57,7 +57,11 @@ __global__ void __launch_bounds__(256) reg_bwd_kernel(RegTable t, const float* _
     float q = 0.f;
     for (int b = 0; b < n; ++b) { const float v = w[(size_t)b * kp + i]; q += v * v; }
     const float inv = q > 0.f ? g * rsqrtf(q) : 0.f;
-    for (int b = 0; b < n; ++b) dw[(size_t)b * kp + i] = w[(size_t)b * kp + i] * inv;
+    if (accumulate) {
+      for (int b = 0; b < n; ++b) dw[(size_t)b * kp + i] += w[(size_t)b * kp + i] * inv;
+    } else {
+      for (int b = 0; b < n; ++b) dw[(size_t)b * kp + i] = w[(size_t)b * kp + i] * inv;
+    }
   }
 }
 
@@ -90,14 +94,24 @@ int phc_weight_reg_fwd(const float* const* weights, const int* phm_dims, const i
   return phc_check_launch("phc_weight_reg_fwd");
 }
 
-int phc_weight_reg_bwd(const float* gout, const float* const* weights, float* const* dweights, const int* phm_dims, const int* kp,
-                       int count, cudaStream_t stream) {
+static int reg_bwd(const float* gout, const float* const* weights, float* const* dweights, const int* phm_dims, const int* kp, int count,
+                   int accumulate, cudaStream_t stream) {
   PHC_REQUIRE(count >= 0 && count <= PHC_REG_MAX, "phc_weight_reg_bwd: %d weight tensors (max %d)", count, PHC_REG_MAX);
   if (count == 0) return PHC_OK;
   RegTable t;
   fill(t, weights, dweights, phm_dims, kp, count);
-  phc_launch(reg_bwd_kernel, dim3(dim3(PHC_REG_BLOCKS, count)), dim3(256), 0, stream, t, gout);
+  phc_launch(reg_bwd_kernel, dim3(dim3(PHC_REG_BLOCKS, count)), dim3(256), 0, stream, t, gout, accumulate);
   return phc_check_launch("phc_weight_reg_bwd");
+}
+
+int phc_weight_reg_bwd(const float* gout, const float* const* weights, float* const* dweights, const int* phm_dims, const int* kp,
+                       int count, cudaStream_t stream) {
+  return reg_bwd(gout, weights, dweights, phm_dims, kp, count, 0, stream);
+}
+
+int phc_weight_reg_bwd_accumulate(const float* gout, const float* const* weights, float* const* dweights, const int* phm_dims,
+                                  const int* kp, int count, cudaStream_t stream) {
+  return reg_bwd(gout, weights, dweights, phm_dims, kp, count, 1, stream);
 }
 
 }  // extern "C"

@@ -858,8 +858,11 @@ class PHMSkipConnectAdd(_PHMSkipConnectBase):
         h0 = self.atomencoder.flat(x)
         h = h0
         L = len(self.mp_layers)
-        # sc_type "first": every layer adds h0 — hand each its own alias so that the L skip gradients are summed in one pass
-        first = ops.fan_out(h0, L) if (self.sc_type == "first" and L > 1) else None
+        # sc_type "first": every layer adds h0 — hand each its own alias so that the L skip gradients are summed in one pass; one more
+        # alias for h0 as the INPUT of layer 0, so that its gradient joins the same pass instead of an accumulation kernel of its own
+        first = ops.fan_out(h0, L + 1) if (self.sc_type == "first" and L > 1) else None
+        if first is not None:
+            h = first[L]
         for i in range(L):
             if first is not None:
                 skip = first[i]

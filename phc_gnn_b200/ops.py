@@ -444,9 +444,28 @@ class _EmbedSum(torch.autograd.Function):
         return (None, None, None, None) + tuple(grads)
 
 
+VALIDATE_INDICES = os.environ.get("PHC_VALIDATE_INDICES", "") not in ("", "0")   # check every embedding input (synchronising: debug)
+
+
+def validate_indices(idx: torch.Tensor, vocab: Sequence[int], what: str = "index") -> None:
+    """Raise IndexError — as nn.Embedding does — if any idx[r, c] lies outside [0, vocab[c]).  The embedding kernels themselves
+    clamp such an index instead of faulting; this is the (synchronising) check for debugging and tests, cf. EdgeStructure.validate()."""
+    require_cuda(idx, what)
+    ix = idx if idx.dim() == 2 else idx.reshape(-1, 1)
+    ix = ix.to(torch.int64).contiguous()
+    assert ix.size(1) == len(vocab), f"{what}: {ix.size(1)} columns for {len(vocab)} vocabularies"
+    status = torch.zeros(1, dtype=torch.int32, device=ix.device)
+    vc = (ctypes.c_int * len(vocab))(*[int(v) for v in vocab])
+    run("phc_index_check", ix.device, ix.data_ptr(), vc, ix.size(0), ix.size(1), status.data_ptr(), _stream(ix.device))
+    if int(status.item()) & 1:
+        raise IndexError(f"{what} out of range in self (vocabulary sizes {list(vocab)})")
+
+
 def embed_sum(idx: torch.Tensor, tables: Sequence[torch.Tensor], phm_dim: int, vocab: Sequence[int]) -> torch.Tensor:
     """out[r, c*Fc+f] = sum_col tables[c*cols+col][idx[r,col], f]."""
     cols = len(vocab)
+    if VALIDATE_INDICES:
+        validate_indices(idx, vocab, "embedding index")
     return _EmbedSum.apply(idx, phm_dim, cols, tuple(int(v) for v in vocab), *tables)
 
 
@@ -508,6 +527,7 @@ class _WeightReg(torch.autograd.Function):
         ws = _ws(nb, dev)
         run("phc_weight_reg_fwd", dev, _ptr_array(ws_), ns, kps, cnt, out.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev))
         ctx.save_for_backward(*ws_)
+        ctx.params = weights              # the Parameter objects themselves (deferred accumulation, see backward)
         return out
 
     @staticmethod
@@ -516,6 +536,28 @@ class _WeightReg(torch.autograd.Function):
         dev = ws_[0].device
         cnt = len(ws_)
         g = _f32c(g, "grad_output")
+        if DEFER_REG_GRADS and not torch.is_grad_enabled() and _reg_deferrable(ctx.params, ws_):
+            # Every weight owns a slice of a flat gradient buffer (a FlatClipAdam / GradientBucket runs the step): add the
+            # regulariser's gradient onto whatever the rest of backward leaves there, with ONE launch at the END of this backward
+            # pass (engine callback) — instead of one AccumulateGrad kernel per weight tensor (18 per ppa step) and their later
+            # copy into the flat buffer.  a + b == b + a: same bits as the accumulation it replaces.
+            params = ctx.params
+
+            def flush(params=params, ws_=ws_, g=g, cnt=cnt, dev=dev):
+                from .parallel import grad_sink
+                dst = []
+                for p in params:
+                    if p.grad is None:
+                        v = grad_sink(p)
+                        v.zero_()
+                        p.grad = v
+                    dst.append(p.grad)
+                ns_ = (ctypes.c_int * cnt)(*[w.size(0) for w in ws_])
+                kps_ = (ctypes.c_int * cnt)(*[w.size(1) * w.size(2) for w in ws_])
+                run("phc_weight_reg_bwd_accumulate", dev, g.data_ptr(), _ptr_array(ws_), _ptr_array(dst), ns_, kps_, cnt, _stream(dev))
+
+            torch.autograd.Variable._execution_engine.queue_callback(flush)
+            return (None,) * cnt
         flat = torch.empty(sum(w.numel() for w in ws_), dtype=torch.float32, device=dev)
         grads, o = [], 0
         for w in ws_:
@@ -525,6 +567,60 @@ class _WeightReg(torch.autograd.Function):
         kps = (ctypes.c_int * cnt)(*[w.size(1) * w.size(2) for w in ws_])
         run("phc_weight_reg_bwd", dev, g.data_ptr(), _ptr_array(ws_), _ptr_array(grads), ns, kps, cnt, _stream(dev))
         return tuple(grads)
+
+
+DEFER_REG_GRADS = os.environ.get("PHC_NO_DEFERRED_REG", "") in ("", "0")     # A/B switch
+
+
+# --------------------------------------------------------------------------------- task loss
+LOSS_KINDS = {"ce": 0, "bce": 1, "bce_masked": 1, "l1": 2}
+
+
+class _TaskLoss(torch.autograd.Function):
+    """Mean task loss and its gradient in one launch (csrc/loss.cu) instead of the eager chains of the reference's train() bodies
+    (train_hiv.py:174-178, train_zinc.py:192, train_ppa.py:200)."""
+
+    @staticmethod
+    def forward(ctx, logits, y, kind):
+        l = _f32c(logits, "logits")
+        rows = l.size(0)
+        cols = l.numel() // max(rows, 1)
+        if kind == 0:
+            tgt = y.reshape(-1).to(torch.int64).contiguous()
+            assert tgt.numel() == rows, "cross entropy: one class id per row"
+        else:
+            tgt = y.reshape(-1).to(torch.float32).contiguous()
+            assert tgt.numel() == l.numel(), "targets and logits differ in size"
+        require_cuda(tgt, "targets")
+        loss = torch.empty((), dtype=torch.float32, device=l.device)
+        dl = torch.empty_like(l)
+        run("phc_task_loss", l.device, kind, l.data_ptr(), tgt.data_ptr(), rows, cols, loss.data_ptr(), dl.data_ptr(), _stream(l.device))
+        ctx.save_for_backward(dl)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dl,) = ctx.saved_tensors
+        return dl * g, None, None
+
+
+def task_loss(logits: torch.Tensor, y: torch.Tensor, kind: str) -> torch.Tensor:
+    return _TaskLoss.apply(logits, y, LOSS_KINDS[kind])
+
+
+def _reg_deferrable(params, saved) -> bool:
+    """The deferred accumulation bypasses autograd for the weights, so it is taken only when nothing can observe the difference
+    (cf. layer._direct_eligible): every weight is a leaf with a registered flat-gradient slice, contiguous fp32 (the saved tensor IS
+    the parameter), and carries no hooks."""
+    from .parallel import grad_sink
+    for p, s in zip(params, saved):
+        if not isinstance(p, torch.nn.Parameter) or not p.requires_grad or p.data_ptr() != s.data_ptr() or grad_sink(p) is None:
+            return False
+        if p._backward_hooks or getattr(p, "_post_accumulate_grad_hooks", None):
+            return False
+        if p.grad is not None and (not p.grad.is_contiguous() or p.grad.dtype != torch.float32):
+            return False
+    return True
 
 
 def weight_regularization_l2(weights: Sequence[torch.Tensor]) -> torch.Tensor:

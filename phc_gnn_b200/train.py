@@ -18,7 +18,13 @@ from .synthetic import Workload
 BLOCKS = ("convs", "pooling", "downstream", "norms", "atomencoder", "bondencoders")
 
 
+FUSED_LOSS = os.environ.get("PHC_NO_FUSED_LOSS", "") in ("", "0")      # A/B switch
+
+
 def task_loss(logits: torch.Tensor, y: torch.Tensor, kind: str) -> torch.Tensor:
+    if FUSED_LOSS and logits.is_cuda and kind in ("ce", "bce", "bce_masked", "l1"):
+        from . import ops
+        return ops.task_loss(logits, y, kind)               # loss + gradient in one launch (csrc/loss.cu)
     if kind in ("bce", "bce_masked"):
         # mean BCE over the labelled entries (train_hiv.py:174,178); written without boolean-mask
         # indexing so that no host sync is needed — same value as logits[mask] / y[mask]

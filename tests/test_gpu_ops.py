@@ -528,3 +528,53 @@ def test_conv_forward_from_node_sums(reduce, linear, F, n, self_loop):
     torch.cuda.synchronize()
     assert_close(out.cpu(), ref.float(), RTOL, 5e-5, "node-sums kernel vs fp64 oracle")
     assert_close(out.cpu(), edge.detach().cpu(), RTOL, 5e-5, "node-sums kernel vs per-edge kernel")
+
+
+@pytest.mark.parametrize("kind,B,C", [("ce", 64, 37), ("ce", 128, 10), ("bce", 128, 1), ("bce_masked", 512, 128), ("l1", 128, 1)])
+def test_fused_task_loss_matches_the_eager_expression(kind, B, C, monkeypatch):
+    """phc_task_loss (loss + gradient in one launch, csrc/loss.cu) against the eager chain of the reference's train() bodies
+    (train_hiv.py:174-178, train_zinc.py:192, train_ppa.py:200) on the same logits: value and d(loss)/d(logits), also under a
+    non-unit upstream gradient."""
+    from phc_gnn_b200 import train
+    g = torch.Generator().manual_seed(3)
+    logits = (torch.randn(B, C, generator=g) * 3).to(DEV)
+    if kind == "ce":
+        y = torch.randint(0, C, (B,), generator=g).to(DEV)
+    elif kind == "l1":
+        y = torch.randn(B, generator=g).to(DEV)
+    else:
+        y = torch.randint(0, 2, (B, C), generator=g).float()
+        if kind == "bce_masked":
+            y[torch.rand(B, C, generator=g) < 0.4] = float("nan")
+        y = y.to(DEV)
+    outs = []
+    for fused in (False, True):
+        monkeypatch.setattr(train, "FUSED_LOSS", fused)
+        l = logits.clone().requires_grad_(True)
+        loss = train.task_loss(l, y, kind)
+        (loss * 0.37).backward()
+        outs.append((loss.detach().cpu(), l.grad.cpu()))
+    assert_close(outs[1][0], outs[0][0], 1e-5, 1e-6, f"{kind}: loss")
+    assert_close(outs[1][1], outs[0][1], 1e-5, 1e-7, f"{kind}: d loss / d logits")
+
+
+def test_embedding_index_validation_reports_what_the_kernels_clamp():
+    """nn.Embedding raises on an index outside its table; the embedding kernels clamp it (a device assertion would poison the context) and
+    ops.validate_indices reports it."""
+    from phc_gnn_b200 import ops
+    vocab = [5, 6, 2]
+    g = torch.Generator().manual_seed(1)
+    idx = torch.stack([torch.randint(0, d, (300,), generator=g) for d in vocab], 1).to(DEV)
+    ops.validate_indices(idx, vocab)                                  # in range: silent
+    bad = idx.clone()
+    bad[123, 1] = 6
+    with pytest.raises(IndexError):
+        ops.validate_indices(bad, vocab)
+    bad = idx.clone()
+    bad[7, 0] = -1
+    with pytest.raises(IndexError):
+        ops.validate_indices(bad, vocab)
+    tables = [torch.randn(d, 8, generator=g).to(DEV) for d in vocab]
+    out = ops.embed_sum(bad, tables, 1, vocab)                        # clamped, finite, no fault
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
