@@ -612,7 +612,9 @@ def _reg_deferrable(params, saved) -> bool:
     """The deferred accumulation bypasses autograd for the weights, so it is taken only when nothing can observe the difference
     (cf. layer._direct_eligible): every weight is a leaf with a registered flat-gradient slice, contiguous fp32 (the saved tensor IS
     the parameter), and carries no hooks."""
-    from .parallel import grad_sink
+    from .parallel import grad_sink, overlap_in_use
+    if overlap_in_use():
+        return False
     for p, s in zip(params, saved):
         if not isinstance(p, torch.nn.Parameter) or not p.requires_grad or p.data_ptr() != s.data_ptr() or grad_sink(p) is None:
             return False

@@ -20,6 +20,13 @@ import torch.nn as nn
 # parameter -> its slice of a flat gradient buffer (set by GradientBucket, read by layer.py's in-place gradient path);
 # a side table rather than an attribute so that it is never pickled with the parameter
 _SINKS = {}     # id(param) -> (weakref to the parameter, view); keyed by id because tensors do not compare as scalars
+_OVERLAP_IN_USE = False
+
+
+def overlap_in_use() -> bool:
+    """True once a bucket all-reduces gradient slices while backward still runs (ops._WeightReg then accumulates through autograd)."""
+    return _OVERLAP_IN_USE
+
 
 
 def register_grad_sink(param: torch.nn.Parameter, view: torch.Tensor) -> None:
@@ -104,6 +111,8 @@ class GradientBucket(object):
             return False
         object.__setattr__(root, "_stage_hook", self.stage_ready)
         self.overlap = True
+        global _OVERLAP_IN_USE
+        _OVERLAP_IN_USE = True            # slices leave for the all-reduce DURING backward: nothing may be added to them at its end
         return True
 
     def set_batch_share(self, local_graphs: int, global_graphs: int, world: int) -> None:
