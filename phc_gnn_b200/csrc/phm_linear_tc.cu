@@ -840,11 +840,8 @@ constexpr int V3_SCRATCH = PROD_WARPS * 32 * V3_SPITCH * 4;
 #define PHC_TC_ABLATE_SWITCHES 0
 #endif
 #define V3_ABL(mask) (PHC_TC_ABLATE_SWITCHES && (p.ablate & (mask)))
-// Experiment: start component boxes at their exact (possibly not 16-byte aligned) column instead of the aligned column below it
-// with a 4-float pad (R != 0 kernels): 16 instead of 24 KiB per raw stage.  Only if TMA accepts such coordinates — off by default.
-#ifndef PHC_V3_UNALIGNED_TMA
-#define PHC_V3_UNALIGNED_TMA 0
-#endif
+// (Tried: component boxes at their exact, not 16-byte aligned column instead of the aligned column below it plus a 4-float pad — 16
+// instead of 24 KiB per raw stage.  cp.async.bulk.tensor rejects such coordinates on sm_100a: illegal instruction.)
 #ifndef PHC_V3_HOIST
 #define PHC_V3_HOIST 0
 #endif
@@ -1323,8 +1320,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
           mbar_arrive_expect_tx(bar, NT * BM * PITCH * 4);
 #pragma unroll
           for (int uu = 0; uu < NT; ++uu)
-            tma_load_2d(smem_u32(rawbuf + rs * V3_RAW_BYTES + uu * (BM * PITCH * 4)), &tmapX,
-                        PHC_V3_UNALIGNED_TMA ? uu * p.Kin + c * KQ : (uu * p.Kin + c * KQ) & ~3, m0, bar);
+            tma_load_2d(smem_u32(rawbuf + rs * V3_RAW_BYTES + uu * (BM * PITCH * 4)), &tmapX, (uu * p.Kin + c * KQ) & ~3, m0, bar);
         }
       }
     }
@@ -2208,7 +2204,7 @@ int try_launch_mix_v3(const MixParams& p, cudaStream_t stream) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (enc == nullptr) return -1;
   CUtensorMap tmap;
-  const int R = PHC_V3_UNALIGNED_TMA ? 0 : (p.Kin & 3);
+  const int R = p.Kin & 3;
   const cuuint64_t gdim[2] = {(cuuint64_t)Fin, (cuuint64_t)p.M};
   const cuuint64_t gstride[1] = {(cuuint64_t)Fin * 4};
   const cuuint32_t box[2] = {(cuuint32_t)(BK / 4 + (R ? 4 : 0)), (cuuint32_t)BM};
