@@ -545,16 +545,25 @@ class _WeightReg(torch.autograd.Function):
 
             def flush(params=params, ws_=ws_, g=g, cnt=cnt, dev=dev):
                 from .parallel import grad_sink
-                dst = []
+                dst, late = [], []
                 for p in params:
                     if p.grad is None:
                         v = grad_sink(p)
                         v.zero_()
                         p.grad = v
-                    dst.append(p.grad)
+                    gr = p.grad
+                    if gr.dtype != torch.float32 or not gr.is_contiguous() or not gr.is_cuda:
+                        # a gradient this kernel cannot add onto in place (never produced by this package's own operators):
+                        # accumulate through a temporary
+                        tmp = torch.zeros(p.shape, dtype=torch.float32, device=dev)
+                        late.append((p, tmp))
+                        gr = tmp
+                    dst.append(gr)
                 ns_ = (ctypes.c_int * cnt)(*[w.size(0) for w in ws_])
                 kps_ = (ctypes.c_int * cnt)(*[w.size(1) * w.size(2) for w in ws_])
                 run("phc_weight_reg_bwd_accumulate", dev, g.data_ptr(), _ptr_array(ws_), _ptr_array(dst), ns_, kps_, cnt, _stream(dev))
+                for p, tmp in late:
+                    p.grad = p.grad + tmp.to(p.grad.dtype)
 
             torch.autograd.Variable._execution_engine.queue_callback(flush)
             return (None,) * cnt
