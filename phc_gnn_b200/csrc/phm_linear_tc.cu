@@ -49,6 +49,9 @@ long long* g_phm_tc_prof = nullptr;   // set via phc_debug_set_tc_profile (debug
 
 namespace tc {
 
+#ifndef PHC_SMEM_SPACE
+#define PHC_SMEM_SPACE 1
+#endif
 constexpr int BM = 128, BN = 128, BK = 32;          // BK fp32 elements = one 128-byte swizzle row
 constexpr int STAGES = 3;
 constexpr int EPI_WARPS = 4, PROD_WARPS = 16;
@@ -1084,7 +1087,13 @@ __global__ void __launch_bounds__(V3_THREADS, 1) phm_tc_mix_v3_kernel(const MixP
   constexpr int NT = 4, KQ = BK / NT;                       // 8 k values per chunk
   constexpr int PITCH = R == 0 ? KQ : KQ + 4;               // floats per raw row (must match the tensor map's box)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+#if PHC_SMEM_SPACE
+  // 1 KiB alignment by POINTER arithmetic on the shared array: the detour through uintptr_t made every pointer derived from `base`
+  // generic, and the drain's transpose scratch, the rule table and the barrier words were read with LD.E / ST.E instead of LDS / STS
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+#else
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+#endif
   uint8_t* bstage = base;                                                   // [V3_NB][B_big | B_small]
   uint8_t* rawbuf = base + V3_NB * 2 * TILE_BYTES;                          // [V3_NRAW][4][128][PITCH]
   float* scratch = reinterpret_cast<float*>(rawbuf + V3_NRAW * V3_RAW_BYTES);  // [16 warps][32][V3_SPITCH]
@@ -1714,7 +1723,13 @@ __global__ void __launch_bounds__(DH2_THREADS, 1) phm_tc_dh_v2_kernel(const DhPa
                                                                      const __grid_constant__ CUtensorMap tmapG) {
   pdl_begin();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+#if PHC_SMEM_SPACE
+  // 1 KiB alignment by POINTER arithmetic on the shared array: the detour through uintptr_t made every pointer derived from `base`
+  // generic, and the drain's transpose scratch, the rule table and the barrier words were read with LD.E / ST.E instead of LDS / STS
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+#else
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+#endif
   uint8_t* bstage = base;                                        // [2][tile0 big | tile0 small | tile1 big | tile1 small]
   uint8_t* rawbuf = base + 2 * DH2_B_STAGE;                      // [2][x box 32x128 | dy box 32x256]
   uint64_t* bars = reinterpret_cast<uint64_t*>(rawbuf + 2 * DH2_RAW_BYTES);
